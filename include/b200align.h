@@ -1,0 +1,190 @@
+/*
+ * b200align.h -- C ABI of libb200align.so: the drop-in boundary for the
+ * `bio::alignment::pairwise` hot path of rust-bio 4.0.1, rebuilt B200-native.
+ *
+ * The reference has no FFI for this path: its boundary is the Rust method
+ * surface (reference src/alignment/pairwise/mod.rs):
+ *     Scoring<F>                       mod.rs:238-429
+ *     Aligner::with_capacity / ...     mod.rs:495-583
+ *     Aligner::custom                  mod.rs:591-922
+ *     Aligner::global                  mod.rs:925-951
+ *     Aligner::semiglobal              mod.rs:954-983
+ *     Aligner::local                   mod.rs:986-1015
+ *     banded::Aligner::*               banded.rs:150-401, 872-1004
+ * A per-pair call cannot feed a GPU, so every entry point here is the BATCH
+ * form of one of those methods; a single-pair call is a batch of one.  The
+ * Rust shim (rust_bio_b200/rust/src/lib.rs) and the Python mirror
+ * (rust_bio_b200/pairwise.py) bind exactly these symbols.
+ *
+ * Conventions
+ *   - plain C, no exceptions / unwinding across the boundary;
+ *   - every function returns 0 on success or a negative B2A_E_* code;
+ *     b2a_last_error() gives the text for the calling engine;
+ *   - an engine handle is bound to ONE CUDA device and may be used by one
+ *     host thread at a time (the reference's `&mut self` contract,
+ *     mod.rs:591,925,954,986);
+ *   - there is NO CPU fallback: every align call fails with
+ *     B2A_E_NO_DEVICE if the CUDA device cannot be used.
+ */
+#ifndef B200ALIGN_H_
+#define B200ALIGN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pairwise::MIN_SCORE (mod.rs:174) */
+#define B2A_MIN_SCORE (-858993459)
+
+/* banded::MAX_CELLS (banded.rs:104) */
+#define B2A_BANDED_MAX_CELLS 5000000ull
+
+/* AlignmentMode, in bio-types variant order (used at mod.rs:920,942,971,1003) */
+enum {
+  B2A_MODE_CUSTOM = 0,     /* Aligner::custom      mod.rs:591 */
+  B2A_MODE_GLOBAL = 1,     /* Aligner::global      mod.rs:925 */
+  B2A_MODE_SEMIGLOBAL = 2, /* Aligner::semiglobal  mod.rs:954 */
+  B2A_MODE_LOCAL = 3       /* Aligner::local       mod.rs:986 */
+};
+
+/* AlignmentOperation codes (bio-types variant order; pushed at mod.rs:860-900) */
+enum {
+  B2A_OP_MATCH = 0,
+  B2A_OP_SUBST = 1,
+  B2A_OP_DEL = 2,
+  B2A_OP_INS = 3,
+  B2A_OP_XCLIP = 4, /* length is in clip_len, in order of appearance */
+  B2A_OP_YCLIP = 5
+};
+
+/* error codes */
+enum {
+  B2A_OK = 0,
+  B2A_E_INVALID = -1,     /* bad argument (the reference would panic: mod.rs:517-518,554-571) */
+  B2A_E_NO_DEVICE = -2,   /* CUDA device / driver unusable: no CPU fallback exists */
+  B2A_E_CUDA = -3,        /* a CUDA runtime call failed; see b2a_last_error */
+  B2A_E_RANGE = -4,       /* scores/lengths would overflow i32 in the reference recurrence */
+  B2A_E_CAPACITY = -5,    /* caller's ops buffer too small */
+  B2A_E_STATE = -6,       /* stage/run/fetch called out of order */
+  B2A_E_UNSUPPORTED = -7  /* sequence too long for this build's on-chip staging */
+};
+
+/* Scoring<F> (mod.rs:238-247).  `table`, when non-NULL, is the host-tabulated
+ * MatchFunc: 256x256 row-major, table[a*256+b] = match_fn.score(a, b)
+ * (mod.rs:177-228); only entries for symbols present in the batch are read.
+ * When NULL, MatchParams semantics apply (mod.rs:208-217).
+ * has_match_scores/match_score mirror `match_scores: Option<(i32,i32)>`
+ * (mod.rs:242), which only banded::Band::create consults (banded.rs:1315-1318). */
+typedef struct b2a_scoring {
+  int32_t gap_open;
+  int32_t gap_extend;
+  int32_t xclip_prefix;
+  int32_t xclip_suffix;
+  int32_t yclip_prefix;
+  int32_t yclip_suffix;
+  int32_t match_score;
+  int32_t mismatch_score;
+  int32_t has_match_scores;
+  const int32_t* table;
+} b2a_scoring;
+
+/* A batch of (x, y) pairs: TextSlice arguments of the align methods. */
+typedef struct b2a_pairs {
+  const uint8_t* seq_blob;  /* all sequences, any layout */
+  const uint64_t* x_off;    /* [n_pairs] byte offset of x in seq_blob */
+  const uint32_t* x_len;    /* [n_pairs] m */
+  const uint64_t* y_off;    /* [n_pairs] */
+  const uint32_t* y_len;    /* [n_pairs] n */
+  uint64_t blob_bytes;
+  uint64_t n_pairs;
+} b2a_pairs;
+
+/* Caller-allocated host outputs == the fields of bio_types Alignment
+ * (built at mod.rs:911-921); xlen/ylen/mode are known to the caller. */
+typedef struct b2a_results {
+  int32_t* score;      /* [n_pairs] */
+  uint32_t* xstart;    /* [n_pairs] */
+  uint32_t* xend;      /* [n_pairs] */
+  uint32_t* ystart;    /* [n_pairs] */
+  uint32_t* yend;      /* [n_pairs] */
+  uint64_t* ops_off;   /* [n_pairs+1] prefix offsets into ops */
+  uint8_t* ops;        /* [ops_capacity] B2A_OP_* codes, alignment order */
+  uint64_t ops_capacity;
+  uint32_t* clip_len;  /* [4*n_pairs] lengths of the Xclip/Yclip ops of a pair, in order of appearance */
+} b2a_results;
+
+typedef struct b2a_stats {
+  uint64_t cells;          /* sum of DP cells (m*n, or Band::num_cells for banded) */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint64_t traceback_bytes; /* traceback bit-vector bytes the fill kernel stores */
+  float pack_ms;           /* K0 */
+  float fill_ms;           /* K1 (or K3) */
+  float walk_ms;           /* K2 epilogue + traceback walk (+ ops compaction) */
+  float band_ms;           /* K4 (banded only) */
+  uint32_t kernel_launches;
+  uint32_t waves;          /* sub-batches the traceback budget forced */
+  uint32_t fill_lanes_per_pair; /* G of the fill kernel variant used */
+  uint32_t fill_rows_per_lane;  /* R */
+} b2a_stats;
+
+typedef struct b2a_engine b2a_engine;
+
+/* lifecycle */
+int32_t b2a_engine_create(b2a_engine** out, int32_t device_id);
+int32_t b2a_engine_destroy(b2a_engine* e);
+const char* b2a_last_error(const b2a_engine* e);
+const char* b2a_version(void);
+
+/* Run all engine work on this cudaStream_t (default: an engine-owned stream). */
+int32_t b2a_engine_set_stream(b2a_engine* e, void* cuda_stream);
+/* Upper bound (bytes) on device scratch for traceback bit-vectors; larger
+ * batches are processed in waves. 0 = default (60% of free HBM). */
+int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes);
+/* Force the fill-kernel shape (lanes per pair G in {1,2,4,8,16,32}, rows per
+ * lane R in {4,8,12,16,20}); 0,0 = automatic. */
+int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t rows_per_lane);
+
+/* One-call form: Aligner::{custom,global,semiglobal,local} over a batch with
+ * HOST inputs and HOST outputs (copies inside). mode = B2A_MODE_*. */
+int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                        const b2a_pairs* pairs, b2a_results* results, b2a_stats* stats);
+
+/* banded::Aligner::{custom,global,semiglobal,local} (banded.rs:282,872,901,942)
+ * with k-mer length k and band half-width w (banded.rs:150-180). */
+int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                               uint32_t k, uint32_t w, const b2a_pairs* pairs,
+                               b2a_results* results, b2a_stats* stats);
+
+/* Staged form of b2a_align_batch, so a caller can keep a batch resident in HBM:
+ *   stage: validate, plan, host->device copy of the batch (async on the stream);
+ *   run:   launch K0..K2 on the stream (async; may be called repeatedly);
+ *   fetch: device->host copy of the results, stream-synchronised. */
+int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                        const b2a_pairs* pairs);
+int32_t b2a_batch_run(b2a_engine* e);
+int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* results, b2a_stats* stats);
+
+/* Fixed-stride per-pair result records of the staged batch in DEVICE memory,
+ * the unit that is all-gathered across GPUs (one ncclAllGather):
+ *   record = { int32 score; uint32 xstart, xend, ystart, yend, n_ops;
+ *              uint32 clip_len[4]; uint8 ops[stride - 40] }.
+ * Valid after b2a_batch_run until the next stage. */
+int32_t b2a_batch_records(b2a_engine* e, void** dev_records, uint32_t* stride_bytes,
+                          uint64_t* n_records);
+/* Same records, but written into caller-provided DEVICE memory (e.g. a torch
+ * tensor that is then handed to torch.distributed.all_gather_into_tensor). */
+int32_t b2a_batch_records_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes,
+                               uint32_t* stride_bytes);
+uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n);
+
+/* Decode host copies of gathered records into b2a_results (pure host code). */
+int32_t b2a_records_decode(const void* host_records, uint32_t stride_bytes, uint64_t n_records,
+                           b2a_results* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ALIGN_H_ */

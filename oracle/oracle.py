@@ -1,0 +1,118 @@
+"""ctypes wrapper around oracle/liboracle.so -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+MIN_SCORE = -858993459
+MODES = {"custom": 0, "global": 1, "semiglobal": 2, "local": 3}
+
+
+class OrcScoring(C.Structure):
+    _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32),
+                ("xclip_prefix", C.c_int32), ("xclip_suffix", C.c_int32),
+                ("yclip_prefix", C.c_int32), ("yclip_suffix", C.c_int32),
+                ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
+                ("has_match_scores", C.c_int32),
+                ("table", C.POINTER(C.c_int32))]
+
+
+class OrcAlignment(C.Structure):
+    _fields_ = [("score", C.c_int32), ("ystart", C.c_uint32), ("xstart", C.c_uint32),
+                ("yend", C.c_uint32), ("xend", C.c_uint32), ("ylen", C.c_uint32),
+                ("xlen", C.c_uint32), ("mode", C.c_uint32), ("n_ops", C.c_uint32)]
+
+
+ALN_DTYPE = np.dtype([("score", "<i4"), ("ystart", "<u4"), ("xstart", "<u4"), ("yend", "<u4"),
+                      ("xend", "<u4"), ("ylen", "<u4"), ("xlen", "<u4"), ("mode", "<u4"),
+                      ("n_ops", "<u4")])
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle if needed (g++ only; no reference sources are involved)."""
+    srcs = [os.path.join(_HERE, f) for f in ("pairwise_oracle.cpp", "banded_oracle.cpp")]
+    if force or not os.path.exists(_SO) or any(
+            os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orc_align.restype = C.c_int
+        L.orc_align_batch.restype = C.c_double
+        L.orc_hardware_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def make_scoring(gap_open, gap_extend, match=0, mismatch=0, table=None, xclip_prefix=MIN_SCORE,
+                 xclip_suffix=MIN_SCORE, yclip_prefix=MIN_SCORE, yclip_suffix=MIN_SCORE,
+                 has_match_scores=0):
+    s = OrcScoring(gap_open, gap_extend, xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix,
+                   match, mismatch, has_match_scores, None)
+    keep = None
+    if table is not None:
+        keep = np.ascontiguousarray(table, dtype=np.int32).reshape(256 * 256)
+        s.table = keep.ctypes.data_as(C.POINTER(C.c_int32))
+    return s, keep
+
+
+def align(mode, scoring: OrcScoring, x: bytes, y: bytes):
+    """One pair -> (dict of Alignment fields, [(code, len), ...])."""
+    mode = MODES.get(mode, mode)
+    m, n = len(x), len(y)
+    out = OrcAlignment()
+    ops = (C.c_uint32 * (m + n + 4))()
+    rc = lib().orc_align(int(mode), C.byref(scoring), x, C.c_uint32(m), y, C.c_uint32(n),
+                         C.byref(out), ops)
+    if rc != 0:
+        raise RuntimeError("oracle: traceback panic path (mod.rs:905)")
+    d = {f: getattr(out, f) for f, _ in OrcAlignment._fields_}
+    return d, [(int(v) & 7, int(v) >> 3) for v in ops[:out.n_ops]]
+
+
+def align_batch(mode, scoring: OrcScoring, blob, x_off, x_len, y_off, y_len, threads=1,
+                want_ops=True):
+    """Batch -> (structured array of Alignment fields, ops uint32 flat, ops_off uint64, seconds)."""
+    mode = MODES.get(mode, mode)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    x_off = np.ascontiguousarray(x_off, dtype=np.uint64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.uint64)
+    x_len = np.ascontiguousarray(x_len, dtype=np.uint32)
+    y_len = np.ascontiguousarray(y_len, dtype=np.uint32)
+    n = len(x_len)
+    out = np.zeros(n, dtype=ALN_DTYPE)
+    if want_ops:
+        cap = x_len.astype(np.uint64) + y_len.astype(np.uint64) + np.uint64(4)
+        ops_off = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+        ops = np.zeros(int(ops_off[-1]), dtype=np.uint32)
+        ops_p, off_p = ops.ctypes.data_as(C.c_void_p), ops_off.ctypes.data_as(C.c_void_p)
+    else:
+        ops, ops_off, ops_p, off_p = None, None, None, None
+    secs = lib().orc_align_batch(
+        int(mode), C.byref(scoring), blob.ctypes.data_as(C.c_void_p),
+        x_off.ctypes.data_as(C.c_void_p), x_len.ctypes.data_as(C.c_void_p),
+        y_off.ctypes.data_as(C.c_void_p), y_len.ctypes.data_as(C.c_void_p),
+        C.c_uint64(n), out.ctypes.data_as(C.c_void_p), ops_p, off_p, C.c_int(int(threads)))
+    return out, ops, ops_off, secs
+
+
+def hardware_threads() -> int:
+    return int(lib().orc_hardware_threads())

@@ -1,0 +1,405 @@
+// K1: DP fill of rows 1..m-1 as a row-strip wavefront.
+//
+// What it computes (reference rust-bio 4.0.1 src/alignment/pairwise/mod.rs):
+//   the per-cell rule of Aligner::custom, mod.rs:729-805, for rows i < m:
+//     M = S(i-1,j-1) + score          733
+//     I = max(I(i-1,j)+ge, S(i-1,j)+go), ties -> open      735-744
+//     D = max(D(i,j-1)+ge, S(i,j-1)+go), ties -> open      746-755
+//     S = first strict maximum in the order M, I, D, xclip_score   757-778
+//       (for i < m the running value starts at MIN_SCORE and the y-prefix clip
+//        can never beat I -- DESIGN.md "dead terms" -- so S has 4 sources)
+//     column tracker (S[curr][m], Lx[j]) and row tracker (Sn[i], Ly[i])  793-802
+// How: G lanes own one pair; lane l owns R consecutive rows held in registers
+// (S and D of the previous column, row trackers, traceback accumulators); at
+// step t lane l is at column t-l+1 (anti-diagonal wavefront), handing
+// (S, I, column tracker) of its bottom row to lane l+1 by warp shuffle.  Rows
+// beyond G*R are done in further strips; the strip boundary row lives in HBM
+// ([column][pair] so a warp's access is one line) and is also what the walk
+// kernel needs to finish row m.  Traceback is 4 bits per cell, eight columns
+// per 32-bit register, flushed with 128-bit stores that are contiguous across
+// the warp.  Sequences arrive in shared memory by cp.async.bulk (TMA bulk copy)
+// completing on an mbarrier; substitution scores come from MatchParams
+// compare/select or from a compact LUT in shared memory.
+#pragma once
+#include "b2a_common.cuh"
+
+namespace b2a {
+
+struct FillParams {
+  const Block* blocks;
+  uint32_t nblocks;
+  const uint32_t* pm;  // [sorted pair] m
+  const uint32_t* pn;  // [sorted pair] n
+  const uint8_t* seq;  // staged sequences
+  uint8_t* bnd;
+  uint8_t* rows;
+  uint8_t* tb;
+  const int32_t* lut;  // alpha*alpha (global) or null
+  uint32_t* task_counter;
+  uint32_t smem_seq_bytes;  // per-warp staging bytes
+  DevScoring sc;
+};
+
+// Per-lane view of one warp-task (32/G pairs of one block).
+template <int G>
+struct LaneCtx {
+  DevScoring sc;
+  const int32_t* lut;    // LUT in shared memory (device) / host memory (sim)
+  const uint32_t* xs;    // staged x words of the task: [w][P]
+  const uint32_t* ys;    // staged y words of the task: [w][P]
+  int32_t m, n;          // this lane's pair
+  int32_t maxn;          // block maximum (loop bound shared by the warp)
+  int32_t g;             // pair slot inside the task (lane / G)
+  int32_t l;             // lane inside the group (lane % G)
+  int32_t lane;          // 0..31
+  int32_t pi;            // pair index inside the block
+  int32_t nstrips;
+  int32_t K;
+  int32_t rows_pad;
+  bool uniform;
+  int4* bnd;             // block base, [column][32]
+  int32_t* rows;         // block base, ROWS_ARRAYS arrays of [rows_pad][32]
+  uint4* tb;             // task base: [strip][k][q][32]
+};
+
+#if defined(__CUDA_ARCH__)
+#define B2A_SHFL_UP(v, G) __shfl_up_sync(0xffffffffu, (v), 1, (G))
+#else
+#define B2A_SHFL_UP(v, G) (v)
+#endif
+
+template <int G, int R, int FLAGS, bool MASKED, bool LAST>
+B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, const int32_t rowbase,
+                        const int32_t rv, int32_t (&Sp)[R], int32_t (&Dp)[R], int32_t (&SnR)[R],
+                        int32_t (&LyR)[R], uint32_t (&tbacc)[R], const int32_t (&xc)[R],
+                        int32_t sdiag, int32_t& sup, int32_t& iup, int32_t& Tv, int32_t& Ti,
+                        int32_t& cap_s, int32_t& cap_i) {
+  constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
+  constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
+  constexpr bool CX = (FLAGS & F_CLIPX) != 0;
+  constexpr bool LUT = (FLAGS & F_LUT) != 0;
+  const int32_t go = c.sc.gap_open, ge = c.sc.gap_extend;
+  const int32_t xcs = CX ? xclip_score(c.sc, j) : 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int32_t sub;
+    if (LUT) {
+      sub = c.lut[xc[r] + q];
+    } else {
+      sub = (xc[r] == q) ? c.sc.match_score : c.sc.mismatch_score;
+    }
+    const int32_t mval = sdiag + sub;
+    const int32_t iop = sup + go;
+    const int32_t iex = iup + ge;
+    const int32_t ival = imax(iex, iop);
+    uint32_t nib = (iex > iop) ? (uint32_t)NB_IEXT : 0u;
+    const int32_t dop = Sp[r] + go;
+    const int32_t dex = Dp[r] + ge;
+    const int32_t dval = imax(dex, dop);
+    nib |= (dex > dop) ? (uint32_t)NB_DEXT : 0u;
+    const int32_t gapbest = imax(ival, dval);
+    int32_t s = imax(mval, gapbest);
+    uint32_t code = (mval >= gapbest) ? (uint32_t)NB_DIAG
+                                      : ((ival >= dval) ? (uint32_t)NB_INS : (uint32_t)NB_DEL);
+    if (CX) {
+      code = (xcs > s) ? (uint32_t)NB_CLIP : code;
+      s = imax(s, xcs);
+    }
+    nib |= code;
+    tbacc[r] = (tbacc[r] << 4) | nib;
+    if (TC) {
+      const int32_t v = s + c.sc.xclip_suffix;
+      if ((!MASKED || r < rv) && v > Tv) {
+        Tv = v;
+        Ti = rowbase + 1 + r;
+      }
+    }
+    if (TR) {
+      const int32_t v = s + c.sc.yclip_suffix;
+      if (v > SnR[r]) {
+        SnR[r] = v;
+        LyR[r] = j;
+      }
+    }
+    if (LAST) {
+      const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
+      c.rows[ROWS_SL * c.rows_pad * 32 + slot] = s;
+      c.rows[ROWS_IL * c.rows_pad * 32 + slot] = ival;
+      c.rows[ROWS_NL * c.rows_pad * 32 + slot] = (int32_t)nib;
+    }
+    if (MASKED) {
+      if (r == rv - 1) {
+        cap_s = s;
+        cap_i = ival;
+      }
+    }
+    sdiag = Sp[r];
+    Sp[r] = s;
+    Dp[r] = dval;
+    sup = s;
+    iup = ival;
+  }
+}
+
+// One strip (rows s*G*R+1 .. (s+1)*G*R) of one lane's pair.
+template <int G, int R, int FLAGS, bool MASKED>
+B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
+  constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
+  constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
+  constexpr bool LUT = (FLAGS & F_LUT) != 0;
+  constexpr int P = 32 / G;
+  constexpr int TBW = tbw_of(R);
+  const int32_t m = c.m, n = c.n;
+  const int32_t rowbase = s * (G * R) + c.l * R;  // row above this lane's first row
+  // valid rows of this lane: rows <= m-1
+  int32_t rv = m - 1 - rowbase;
+  rv = rv < 0 ? 0 : (rv > R ? R : rv);
+
+  int32_t Sp[R], Dp[R], SnR[R], LyR[R], xc[R];
+  uint32_t tbacc[R];
+  // x symbols of my rows: rows rowbase+1.. are x[rowbase..], R % 4 == 0 so word aligned
+#pragma unroll
+  for (int w = 0; w < R / 4; ++w) {
+    const uint32_t xw = c.xs[(rowbase / 4 + w) * P + c.g];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int32_t sym = (int32_t)((xw >> (8 * b)) & 0xffu);
+      xc[w * 4 + b] = LUT ? sym * c.sc.alpha : sym;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int32_t i = rowbase + 1 + r;
+    const int32_t s0 = col0_S(c.sc, i);
+    Sp[r] = s0;
+    Dp[r] = MIN_SCORE;
+    tbacc[r] = 0;
+    if (TR) {  // mod.rs:667-670
+      const int32_t v = s0 + c.sc.yclip_suffix;
+      SnR[r] = v > MIN_SCORE ? v : MIN_SCORE;
+      LyR[r] = 0;
+    } else {
+      SnR[r] = 0;
+      LyR[r] = 0;
+    }
+  }
+  // S of the row above my first row, in column 0 (the first diagonal input)
+  int32_t sup_prev = rowbase == 0 ? 0 : col0_S(c.sc, rowbase);
+  // values arriving from above for my next column
+  int32_t in_s = 0, in_i = MIN_SCORE, in_tv = MIN_SCORE, in_ti = m;
+  int4 pre = make_int4(0, 0, 0, 0);
+  const bool top_from_mem = (c.l == 0) && (s > 0);
+  const bool top_from_row0 = (c.l == 0) && (s == 0);
+  if (top_from_mem) pre = c.bnd[1 * 32 + c.pi];  // column 1 (n >= 1 or garbage-but-unused)
+  const bool writer =
+      MASKED ? (rv >= 1 && (c.l == G - 1 || rowbase + R >= m - 1)) : (c.l == G - 1);
+  int32_t cap_s = 0, cap_i = 0;
+  uint32_t yw = 0;
+  uint4* tbs = c.tb + (size_t)s * c.K * TBW * 32;
+  const int32_t nsteps = c.K * 8;
+
+  for (int32_t t = 0; t < nsteps; ++t) {
+    const int32_t j = t - c.l + 1;
+    const bool active = (j >= 1) && (j <= n);
+    if (active) {
+      // y symbol of column j
+      int32_t q;
+      if (G == 1) {
+        if ((t & 3) == 0) yw = c.ys[(t >> 2) * P + c.g];
+        q = (int32_t)(yw & 0xffu);
+        yw >>= 8;
+      } else {
+        const int32_t jb = j - 1;
+        q = (int32_t)((c.ys[(jb >> 2) * P + c.g] >> (8 * (jb & 3))) & 0xffu);
+      }
+      if (top_from_row0) {
+        in_s = row0_S(c.sc, j, n);
+        in_i = MIN_SCORE;
+        in_tv = MIN_SCORE;
+        in_ti = m;
+      } else if (top_from_mem) {
+        in_s = pre.x;
+        in_i = pre.y;
+        in_tv = pre.z;
+        in_ti = pre.w;
+        if (j < c.maxn) pre = c.bnd[(j + 1) * 32 + c.pi];  // prefetch next column's boundary
+      }
+      int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
+      if (j == n) {
+        column_step<G, R, FLAGS, MASKED, true>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+                                               sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
+      } else {
+        column_step<G, R, FLAGS, MASKED, false>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+                                                sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
+      }
+      sup_prev = in_s;
+      if (writer) {
+        int4 o;
+        o.x = MASKED ? cap_s : sup;
+        o.y = MASKED ? cap_i : iup;
+        o.z = TC ? Tv : MIN_SCORE;
+        o.w = TC ? Ti : m;
+        c.bnd[j * 32 + c.pi] = o;
+      }
+      in_s = sup;
+      in_i = iup;
+      in_tv = Tv;
+      in_ti = Ti;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) tbacc[r] <<= 4;
+    }
+    if (G > 1) {  // hand my bottom row to the lane below (it is one column behind me)
+      in_s = B2A_SHFL_UP(in_s, G);
+      in_i = B2A_SHFL_UP(in_i, G);
+      if (TC) {
+        in_tv = B2A_SHFL_UP(in_tv, G);
+        in_ti = B2A_SHFL_UP(in_ti, G);
+      }
+    }
+    if ((t & 7) == 7) {
+      uint4* dst = tbs + (size_t)(t >> 3) * TBW * 32 + c.lane;
+#pragma unroll
+      for (int qd = 0; qd < TBW; ++qd) {
+        uint4 v;
+        v.x = tbacc[qd * 4 + 0];
+        v.y = (qd * 4 + 1 < R) ? tbacc[qd * 4 + 1] : 0u;
+        v.z = (qd * 4 + 2 < R) ? tbacc[qd * 4 + 2] : 0u;
+        v.w = (qd * 4 + 3 < R) ? tbacc[qd * 4 + 3] : 0u;
+        dst[qd * 32] = v;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) tbacc[r] = 0;
+    }
+  }
+  if (TR) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
+      c.rows[ROWS_SN * c.rows_pad * 32 + slot] = SnR[r];
+      c.rows[ROWS_LY * c.rows_pad * 32 + slot] = LyR[r];
+    }
+  }
+}
+
+template <int G, int R, int FLAGS>
+B2A_HD void fill_lane(const LaneCtx<G>& c) {
+  for (int32_t s = 0; s < c.nstrips; ++s) {
+    // a strip is "full" when every lane of every pair of the task owns R valid rows
+    const bool full = c.uniform && ((s + 1) * (G * R) <= c.m - 1);
+    if (full) {
+      run_strip<G, R, FLAGS, false>(c, s);
+    } else {
+      run_strip<G, R, FLAGS, true>(c, s);
+    }
+  }
+}
+
+#if defined(__CUDACC__)
+
+// ---- TMA bulk copy + mbarrier helpers (sm_90+ PTX; UBLKCP / SYNCS in SASS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+constexpr int FILL_WARPS = 4;
+
+// Persistent kernel: every warp pulls warp-tasks (32/G pairs) from a global
+// counter, stages their sequences with two bulk copies and fills them.
+template <int G, int R, int FLAGS>
+__global__ void __launch_bounds__(FILL_WARPS * 32) fill_kernel(const FillParams prm) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int P = 32 / G;
+  constexpr bool LUT = (FLAGS & F_LUT) != 0;
+  constexpr int TBW = tbw_of(R);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // smem: [FILL_WARPS mbarriers][LUT][per-warp staging]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  int32_t* lut_s = reinterpret_cast<int32_t*>(smem + 64);
+  const uint32_t lut_bytes = LUT ? ((uint32_t)(prm.sc.alpha * prm.sc.alpha * 4 + 127) & ~127u) : 0u;
+  uint8_t* stage = smem + 64 + lut_bytes + (size_t)warp * prm.smem_seq_bytes;
+  uint64_t* bar = &bars[warp];
+  if (threadIdx.x < FILL_WARPS) mbar_init(&bars[threadIdx.x], 1);
+  if (LUT) {
+    for (int k = threadIdx.x; k < prm.sc.alpha * prm.sc.alpha; k += blockDim.x) lut_s[k] = prm.lut[k];
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t ntasks = prm.nblocks * G;
+  uint32_t parity = 0;
+  for (;;) {
+    uint32_t task = 0;
+    if (lane == 0) task = atomicAdd(prm.task_counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= ntasks) break;
+    const uint32_t b = task / G, sub = task % G;
+    const Block blk = prm.blocks[b];
+    const uint32_t xbytes = blk.xwords * P * 4, ybytes = blk.ywords * P * 4;
+    if (lane == 0) {
+      // the previous task's generic-proxy reads of the staging buffer are done (syncwarp below)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, xbytes + ybytes);
+      const uint8_t* src = prm.seq + blk.seq_off;
+      tma_bulk_g2s(stage, src + (size_t)sub * xbytes, xbytes, bar);
+      tma_bulk_g2s(stage + xbytes, src + (size_t)G * xbytes + (size_t)sub * ybytes, ybytes, bar);
+    }
+    LaneCtx<G> c;
+    c.sc = prm.sc;
+    c.lut = lut_s;
+    c.xs = reinterpret_cast<const uint32_t*>(stage);
+    c.ys = reinterpret_cast<const uint32_t*>(stage + xbytes);
+    c.g = lane / G;
+    c.l = lane % G;
+    c.lane = lane;
+    c.pi = (int32_t)(sub * P) + c.g;
+    const bool valid = (uint32_t)c.pi < blk.npairs;
+    c.m = valid ? (int32_t)prm.pm[blk.first + c.pi] : 0;
+    c.n = valid ? (int32_t)prm.pn[blk.first + c.pi] : 0;
+    c.maxn = (int32_t)blk.maxn;
+    c.nstrips = (int32_t)blk.nstrips;
+    c.K = (int32_t)blk.K;
+    c.rows_pad = (int32_t)blk.rows_pad;
+    c.uniform = blk.uniform != 0;
+    c.bnd = reinterpret_cast<int4*>(prm.bnd + blk.bnd_off);
+    c.rows = reinterpret_cast<int32_t*>(prm.rows + blk.rows_off);
+    c.tb = reinterpret_cast<uint4*>(prm.tb + blk.tb_off) +
+           (size_t)sub * blk.nstrips * blk.K * TBW * 32;
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    parity ^= 1u;
+    fill_lane<G, R, FLAGS>(c);
+    __syncwarp();
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2a

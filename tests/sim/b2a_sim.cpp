@@ -1,0 +1,186 @@
+// CPU simulation harness for the kernel LOGIC (test tool, not a product path and
+// not a fallback: nothing in rust_bio_b200/ loads it).  It compiles the very same
+// per-lane code the GPU runs -- fill_lane<1,R,FLAGS> (b2a_fill.cuh, thread-per-pair
+// shape, which needs no warp shuffles) and walk_pair (b2a_walk.cuh) -- for the
+// host, stages a batch exactly as K0 does, and lets tests/test_sim_logic.py diff
+// the result against the oracle without a GPU.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../rust_bio_b200/csrc/b2a_fill.cuh"
+#include "../../rust_bio_b200/csrc/b2a_plan.h"
+#include "../../rust_bio_b200/csrc/b2a_walk.cuh"
+
+using namespace b2a;
+
+namespace {
+
+template <int R, int FLAGS>
+void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int32_t* lut,
+                std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd, std::vector<uint8_t>& rows,
+                std::vector<uint8_t>& tb) {
+  constexpr int G = 1, P = 32, TBW = tbw_of(R);
+  for (int lane = 0; lane < 32; ++lane) {
+    LaneCtx<G> c;
+    c.sc = sc;
+    c.lut = lut;
+    const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
+    c.xs = seqw;
+    c.ys = seqw + (size_t)G * blk.xwords * P;
+    c.g = lane;
+    c.l = 0;
+    c.lane = lane;
+    c.pi = lane;
+    const bool valid = (uint32_t)lane < blk.npairs;
+    c.m = valid ? (int32_t)p.pm[blk.first + lane] : (int32_t)blk.maxm;
+    c.n = valid ? (int32_t)p.pn[blk.first + lane] : (int32_t)blk.maxn;
+    c.maxn = (int32_t)blk.maxn;
+    c.nstrips = (int32_t)blk.nstrips;
+    c.K = (int32_t)blk.K;
+    c.rows_pad = (int32_t)blk.rows_pad;
+    c.uniform = blk.uniform != 0;
+    c.bnd = reinterpret_cast<int4*>(bnd.data() + blk.bnd_off);
+    c.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
+    c.tb = reinterpret_cast<uint4*>(tb.data() + blk.tb_off);
+    (void)TBW;
+    fill_lane<G, R, FLAGS>(c);
+  }
+}
+
+template <int R>
+void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring& sc,
+                   const int32_t* lut, std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd,
+                   std::vector<uint8_t>& rows, std::vector<uint8_t>& tb) {
+  switch (flags) {
+    case 0: fill_block<R, 0>(p, blk, sc, lut, seq, bnd, rows, tb); break;
+    case F_TRACK_ROWS: fill_block<R, F_TRACK_ROWS>(p, blk, sc, lut, seq, bnd, rows, tb); break;
+    case F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX:
+      fill_block<R, F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX>(p, blk, sc, lut, seq, bnd, rows, tb);
+      break;
+    case F_LUT: fill_block<R, F_LUT>(p, blk, sc, lut, seq, bnd, rows, tb); break;
+    case F_LUT | F_TRACK_ROWS:
+      fill_block<R, F_LUT | F_TRACK_ROWS>(p, blk, sc, lut, seq, bnd, rows, tb);
+      break;
+    default:
+      fill_block<R, F_LUT | F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX>(p, blk, sc, lut, seq, bnd, rows,
+                                                                   tb);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+struct sim_scoring {
+  int32_t gap_open, gap_extend, xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix;
+  int32_t match_score, mismatch_score, has_match_scores;
+  const int32_t* table;
+};
+
+// Same outputs as the engine: per pair score/xstart/xend/ystart/yend/n_ops/clip_len[4]/status and
+// ops (m+n+4 bytes per pair at ops + ops_off[p], alignment order).
+int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
+                    const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len,
+                    uint64_t n_pairs, int R, int force_general, int32_t* score, uint32_t* xstart,
+                    uint32_t* xend, uint32_t* ystart, uint32_t* yend, uint32_t* n_ops,
+                    uint32_t* clip_len, uint32_t* status, uint8_t* ops, const uint64_t* ops_off) {
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  if (mode == 1) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
+  if (mode == 2) { sc.xclip_prefix = sc.xclip_suffix = MIN_SCORE; sc.yclip_prefix = sc.yclip_suffix = 0; }
+  if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  // compact alphabet over the symbols present (LUT mode)
+  uint8_t codemap[256];
+  for (int k = 0; k < 256; ++k) codemap[k] = (uint8_t)k;
+  std::vector<int32_t> lut;
+  if (s->table) {
+    bool present[256] = {false};
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+      for (uint32_t k = 0; k < x_len[p]; ++k) present[blob[x_off[p] + k]] = true;
+      for (uint32_t k = 0; k < y_len[p]; ++k) present[blob[y_off[p] + k]] = true;
+    }
+    std::vector<int> syms;
+    for (int k = 0; k < 256; ++k)
+      if (present[k]) { codemap[k] = (uint8_t)syms.size(); syms.push_back(k); }
+    if (syms.empty()) syms.push_back(0);
+    sc.alpha = (int32_t)syms.size();
+    lut.resize((size_t)sc.alpha * sc.alpha);
+    for (int a = 0; a < sc.alpha; ++a)
+      for (int b = 0; b < sc.alpha; ++b) lut[(size_t)a * sc.alpha + b] = s->table[syms[a] * 256 + syms[b]];
+  }
+  Plan p;
+  build_plan(p, x_len, y_len, n_pairs, 1, R, ~0ull);
+  int flags = scoring_flags(sc);
+  if (force_general) flags = (flags & F_LUT) | F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+  std::vector<uint8_t> seq(p.seq_bytes, 0), bnd(p.max_bnd, 0xCD), rows(p.max_rows, 0xCD),
+      rowm(p.max_rowm, 0xCD), tb(p.max_tb, 0xCD), opsb(p.ops_bytes, 0);
+  // K0 equivalent: stage sequences as [task][word][pair] (G = 1: one task per block)
+  for (const Block& blk : p.blocks) {
+    uint32_t* seqw = reinterpret_cast<uint32_t*>(seq.data() + blk.seq_off);
+    for (uint32_t q = 0; q < blk.npairs; ++q) {
+      const uint32_t orig = p.order[blk.first + q];
+      for (uint32_t k = 0; k < x_len[orig]; ++k)
+        reinterpret_cast<uint8_t*>(&seqw[(k >> 2) * 32 + q])[k & 3] = codemap[blob[x_off[orig] + k]];
+      uint32_t* yw = seqw + (size_t)blk.xwords * 32;
+      for (uint32_t k = 0; k < y_len[orig]; ++k)
+        reinterpret_cast<uint8_t*>(&yw[(k >> 2) * 32 + q])[k & 3] = codemap[blob[y_off[orig] + k]];
+    }
+  }
+  for (const Block& blk : p.blocks) {
+    switch (R) {
+      case 4: fill_dispatch<4>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
+      case 8: fill_dispatch<8>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
+      case 16: fill_dispatch<16>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
+      default: return -1;
+    }
+    for (uint32_t lane = 0; lane < blk.npairs; ++lane) {
+      const uint32_t sp = blk.first + lane;
+      PairView v;
+      v.sc = sc;
+      v.lut = lut.data();
+      v.P = 32;
+      v.m = (int32_t)p.pm[sp];
+      v.n = (int32_t)p.pn[sp];
+      v.pi = (int32_t)lane;
+      v.G = 1;
+      v.R = R;
+      v.TBW = (R + 3) / 4;
+      v.nstrips = (int32_t)blk.nstrips;
+      v.K = (int32_t)blk.K;
+      v.sub = (int32_t)lane / 32;
+      v.g = (int32_t)lane % 32;
+      const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
+      v.xw = seqw + v.g;
+      v.yw = seqw + (size_t)blk.xwords * 32 + v.g;
+      v.bnd = reinterpret_cast<const int4*>(bnd.data() + blk.bnd_off);
+      v.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
+      v.rows_pad = (int32_t)blk.rows_pad;
+      v.rowm = reinterpret_cast<uint16_t*>(rowm.data() + blk.rowm_off);
+      v.tb = reinterpret_cast<const uint32_t*>(tb.data() + blk.tb_off);
+      const uint32_t cap = blk.maxm + blk.maxn + 4;
+      uint8_t* ops_end = opsb.data() + blk.ops_off + (size_t)(lane + 1) * cap;
+      WalkOut o;
+      walk_pair(v, mode == 2 || mode == 3, ops_end, o);
+      const uint32_t dst = p.order[sp];
+      score[dst] = o.score;
+      xstart[dst] = o.xstart;
+      xend[dst] = o.xend;
+      ystart[dst] = o.ystart;
+      yend[dst] = o.yend;
+      n_ops[dst] = o.n_ops;
+      status[dst] = o.status;
+      for (int k = 0; k < 4; ++k) clip_len[4 * (size_t)dst + k] = o.clip[k];
+      std::memcpy(ops + ops_off[dst], ops_end - o.n_ops, o.n_ops);
+    }
+  }
+  return 0;
+}
+}

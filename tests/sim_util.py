@@ -1,0 +1,80 @@
+"""ctypes driver for tests/sim/libb2asim.so: the GPU kernels' per-lane logic compiled for the host
+(thread-per-pair shape).  A test tool for the not-gpu suite; the product never loads it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "sim", "b2a_sim.cpp")
+SO = os.path.join(HERE, "sim", "libb2asim.so")
+DEPS = [SRC] + [os.path.join(ROOT, "rust_bio_b200", "csrc", f)
+                for f in ("b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h")]
+
+
+class SimScoring(C.Structure):
+    _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("xclip_prefix", C.c_int32),
+                ("xclip_suffix", C.c_int32), ("yclip_prefix", C.c_int32), ("yclip_suffix", C.c_int32),
+                ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
+                ("has_match_scores", C.c_int32), ("table", C.POINTER(C.c_int32))]
+
+
+def build():
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fwrapv", "-fPIC", "-shared",
+                               "-Wno-unknown-pragmas", "-o", SO, SRC])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.sim_align_batch.restype = C.c_int
+    return _lib
+
+
+def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0):
+    """Takes an oracle.OrcScoring (same layout). Returns dict of arrays + list of op lists."""
+    s = SimScoring.from_buffer_copy(bytes(orc_scoring))
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    x_off = np.ascontiguousarray(x_off, dtype=np.uint64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.uint64)
+    x_len = np.ascontiguousarray(x_len, dtype=np.uint32)
+    y_len = np.ascontiguousarray(y_len, dtype=np.uint32)
+    n = len(x_len)
+    cap = x_len.astype(np.uint64) + y_len.astype(np.uint64) + np.uint64(4)
+    ops_off = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+    ops = np.zeros(int(ops_off[-1]), dtype=np.uint8)
+    out = {k: np.zeros(n, dtype=np.uint32) for k in ("xstart", "xend", "ystart", "yend", "n_ops", "status")}
+    out["score"] = np.zeros(n, dtype=np.int32)
+    out["clip_len"] = np.zeros(4 * n, dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib().sim_align_batch(int(mode), C.byref(s), p(blob), p(x_off), p(x_len), p(y_off), p(y_len),
+                               C.c_uint64(n), int(R), int(force_general), p(out["score"]),
+                               p(out["xstart"]), p(out["xend"]), p(out["ystart"]), p(out["yend"]),
+                               p(out["n_ops"]), p(out["clip_len"]), p(out["status"]), p(ops), p(ops_off))
+    assert rc == 0
+    oplists = []
+    for i in range(n):
+        codes = ops[int(ops_off[i]):int(ops_off[i]) + int(out["n_ops"][i])]
+        oplists.append(decode_ops(codes, out["clip_len"][4 * i:4 * i + 4]))
+    return out, oplists
+
+
+def decode_ops(codes, clips):
+    """uint8 op codes + clip_len[4] -> [(code, len)] like the oracle wrapper returns."""
+    res, k = [], 0
+    for c in codes:
+        c = int(c)
+        if c >= 4:
+            res.append((c, int(clips[k])))
+            k += 1
+        else:
+            res.append((c, 0))
+    return res

@@ -1,0 +1,108 @@
+"""Host logic: the kernels' per-lane code (fill_lane<1,R,*> + walk_pair), compiled for the CPU by
+tests/sim, against the oracle -- golden vectors, ragged/edge shapes, random custom clip penalties."""
+import numpy as np
+import pytest
+
+import sim_util
+from golden_util import load_cases, parse_ops, scoring_fields
+from parity_util import MODES, assert_same, oracle_batch
+from rust_bio_b200 import synth
+
+CASES = load_cases()
+MIN = -858993459
+
+
+def _one(x: bytes, y: bytes):
+    blob = np.frombuffer(x + y + b"\0", dtype=np.uint8)
+    return (blob, np.array([0], dtype=np.uint64), np.array([len(x)], dtype=np.uint32),
+            np.array([len(x)], dtype=np.uint64), np.array([len(y)], dtype=np.uint32))
+
+
+def _scoring(orc, sc):
+    f = scoring_fields(sc)
+    table = None
+    if f["matrix"]:
+        from rust_bio_b200 import scores
+        table = scores.matrix_table256(f["matrix"])
+    return orc.make_scoring(f["gap_open"], f["gap_extend"], f["match"], f["mismatch"], table,
+                            f["xclip_prefix"], f["xclip_suffix"], f["yclip_prefix"], f["yclip_suffix"])
+
+
+@pytest.mark.parametrize("R", [4, 16])
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_sim_golden(oracle, case, R):
+    s, keep = _scoring(oracle, case["scoring"])
+    got, ops = sim_util.align_batch(MODES[case["mode"]], s, *_one(case["x"].encode(), case["y"].encode()), R=R)
+    exp = case["expect"]
+    for k in ("score", "xstart", "xend", "ystart", "yend"):
+        if k in exp:
+            assert int(got[k][0]) == exp[k], (case["name"], k)
+    if "ops" in exp:
+        assert ops[0] == parse_ops(exp["ops"])
+    assert got["status"][0] == 0
+
+
+@pytest.mark.parametrize("mode", ["local", "global", "semiglobal"])
+@pytest.mark.parametrize("R,general", [(4, 0), (8, 1), (16, 0)])
+def test_sim_ragged_presets(oracle, mode, R, general):
+    batch = synth.ragged_pairs(11 + R, 300, 70, 90)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=R, force_general=general)
+    assert_same(got, ops, ref, ref_ops, batch, f"{mode} R={R}")
+
+
+def test_sim_uniform_150_local(oracle):
+    batch = synth.uniform_pairs(synth.BASES["C1"], 0, 96, 150, 150)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "local", s, batch)
+    got, ops = sim_util.align_batch(MODES["local"], s, *batch, R=16)
+    assert_same(got, ops, ref, ref_ops, batch, "C1-shape local")
+
+
+def test_sim_tiny_shapes_all_modes(oracle):
+    """Empty and 1-2 symbol sequences (m == 0 / n == 0 alias S[k][m] with S[k][0], mod.rs:551 note)."""
+    xs, ys = [], []
+    for m in range(0, 4):
+        for n in range(0, 4):
+            for rep in range(4):
+                xs.append(m)
+                ys.append(n)
+    rng = np.random.default_rng(5)
+    total = sum(xs) + sum(ys)
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 2, size=total + 1)]
+    lens = np.array([v for pair in zip(xs, ys) for v in pair], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    batch = (blob, offs[0::2].copy(), np.array(xs, dtype=np.uint32), offs[1::2].copy(), np.array(ys, dtype=np.uint32))
+    for mode in ("custom", "local", "global", "semiglobal"):
+        for clips in [(MIN, MIN, MIN, MIN), (0, 0, 0, 0), (-1, 0, MIN, -2), (0, MIN, MIN, 0), (MIN, 0, 0, MIN)]:
+            s, _ = oracle.make_scoring(-2, -1, 2, -1, None, *clips)
+            ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+            got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=4)
+            assert_same(got, ops, ref, ref_ops, batch, f"tiny {mode} {clips}")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sim_random_custom_clips(oracle, seed):
+    """Arbitrary live/dead mixes of the four clip penalties, zero gap costs included."""
+    rng = np.random.default_rng(100 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -1, -3, -7, -20]))
+    go, ge = int(rng.choice([0, -1, -2, -5, -6])), int(rng.choice([0, -1, -1, -2]))
+    ma, mi = int(rng.choice([1, 2, 4])), int(rng.choice([-1, -3, -7, 0]))
+    s, _ = oracle.make_scoring(go, ge, ma, mi, None, pick(), pick(), pick(), pick())
+    batch = synth.ragged_pairs(seed, 200, 40, 45, alphabet=b"AC" if seed % 2 else b"ACGT")
+    ref, ref_ops = oracle_batch(oracle, "custom", s, batch)
+    for R in (4, 8):
+        got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R)
+        assert_same(got, ops, ref, ref_ops, batch, f"custom seed={seed} R={R}")
+
+
+def test_sim_blosum62_protein(oracle):
+    from rust_bio_b200 import scores
+    table = scores.matrix_table256("blosum62")
+    batch = synth.ragged_pairs(3, 120, 60, 60, alphabet=synth.PROTEIN, min_len=1)
+    for mode, go in (("local", -10), ("global", -5), ("semiglobal", -11)):
+        s, keep = oracle.make_scoring(go, -1, 0, 0, table)
+        ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+        got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=8)
+        assert_same(got, ops, ref, ref_ops, batch, f"blosum62 {mode}")

@@ -88,6 +88,12 @@ typedef struct b2a_scoring {
   int32_t mismatch_score;
   int32_t has_match_scores;
   const int32_t* table;
+  /* Symbols for which `table` is valid (e.g. "A-Z*" for bio::scores matrices).
+   * NULL with a non-NULL table: the engine scans the batch for the symbols
+   * present (slower).  A sequence byte outside the alphabet is B2A_E_INVALID
+   * (bio::scores::lookup would index out of bounds, scores/mod.rs:22-35). */
+  const uint8_t* alphabet;
+  uint32_t alphabet_len;
 } b2a_scoring;
 
 /* A batch of (x, y) pairs: TextSlice arguments of the align methods. */
@@ -183,6 +189,10 @@ uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n);
 /* Decode host copies of gathered records into b2a_results (pure host code). */
 int32_t b2a_records_decode(const void* host_records, uint32_t stride_bytes, uint64_t n_records,
                            b2a_results* results);
+
+/* Measurement utility for the int32-ALU roofline: tera lane-ops/s of
+ * independent add / min-max / add+max register chains over all SMs of the device. */
+int32_t b2a_util_int32_peak(int32_t device_id, float* tops_add, float* tops_minmax, float* tops_mixed);
 
 #ifdef __cplusplus
 }

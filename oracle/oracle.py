@@ -23,7 +23,8 @@ class OrcScoring(C.Structure):
                 ("yclip_prefix", C.c_int32), ("yclip_suffix", C.c_int32),
                 ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
                 ("has_match_scores", C.c_int32),
-                ("table", C.POINTER(C.c_int32))]
+                ("table", C.POINTER(C.c_int32)),
+                ("alphabet", C.c_void_p), ("alphabet_len", C.c_uint32)]
 
 
 class OrcAlignment(C.Structure):
@@ -66,7 +67,7 @@ def make_scoring(gap_open, gap_extend, match=0, mismatch=0, table=None, xclip_pr
                  xclip_suffix=MIN_SCORE, yclip_prefix=MIN_SCORE, yclip_suffix=MIN_SCORE,
                  has_match_scores=0):
     s = OrcScoring(gap_open, gap_extend, xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix,
-                   match, mismatch, has_match_scores, None)
+                   match, mismatch, has_match_scores, None, None, 0)
     keep = None
     if table is not None:
         keep = np.ascontiguousarray(table, dtype=np.int32).reshape(256 * 256)

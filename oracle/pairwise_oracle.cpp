@@ -55,6 +55,8 @@ struct orc_scoring {
   int32_t match_score, mismatch_score;
   int32_t has_match_scores;
   const int32_t* table;  // 256x256 tabulated MatchFunc or NULL (MatchParams)
+  const uint8_t* alphabet;  // unused by the oracle (layout parity with b2a_scoring)
+  uint32_t alphabet_len;
 };
 
 // bio_types::alignment::Alignment (fields built at mod.rs:911-921)

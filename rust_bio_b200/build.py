@@ -1,0 +1,74 @@
+"""Builds rust_bio_b200/csrc/libb200align.so in-tree with nvcc for sm_100a.
+
+Usage: python -m rust_bio_b200.build [--force]
+The K1 fill kernel is instantiated once per (lanes-per-pair, rows-per-lane) shape in its own
+translation unit so the shapes compile in parallel; everything is linked into one shared library
+that exports the C ABI of include/b200align.h.  cudart is linked statically so the library loads
+(and reports B2A_E_NO_DEVICE) on a machine without a GPU driver.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+SO = os.path.join(CSRC, "libb200align.so")
+SHAPES = [(1, 16), (1, 8), (4, 16), (8, 16), (32, 8), (32, 16)]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fwrapv", "--expt-relaxed-constexpr"]
+HEADERS = ["b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_kernels.cuh", "b2a_plan.h",
+           "b2a_fill_launch.h", os.path.join("..", "..", "include", "b200align.h")]
+
+
+def _stale(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return r.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    jobs = []
+    objs = []
+    for g, r in SHAPES:
+        o = os.path.join(OBJ, f"fill_{g}_{r}.o")
+        objs.append(o)
+        src = os.path.join(CSRC, "b2a_fill_inst.cu")
+        if force or _stale(o, hdrs + [src]):
+            jobs.append([NVCC, *FLAGS, f"-DB2A_G={g}", f"-DB2A_R={r}", "-c", src, "-o", o])
+    eo = os.path.join(OBJ, "engine.o")
+    objs.append(eo)
+    esrc = os.path.join(CSRC, "b2a_engine.cu")
+    if force or _stale(eo, hdrs + [esrc]):
+        jobs.append([NVCC, *FLAGS, "-c", esrc, "-o", eo])
+    po = os.path.join(OBJ, "peak.o")
+    objs.append(po)
+    psrc = os.path.join(CSRC, "b2a_peak.cu")
+    if force or _stale(po, [psrc]):
+        jobs.append([NVCC, *FLAGS, "-c", psrc, "-o", po])
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for log in ex.map(_run, jobs):
+                if verbose and log:
+                    print(log, file=sys.stderr)
+    if jobs or force or _stale(SO, objs):
+        _run([NVCC, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -133,6 +133,9 @@ B2A_HD int32_t xclip_score(const DevScoring& sc, int32_t j) {
 
 // Traceback words per lane per 8-column group: rows are grouped by four so the
 // fill stores whole 128-bit vectors.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 constexpr int tbw_of(int R) { return (R + 3) / 4; }
 
 }  // namespace b2a

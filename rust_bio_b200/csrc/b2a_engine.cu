@@ -1,0 +1,648 @@
+// libb200align.so: engine + C ABI (include/b200align.h).
+//
+// Host side of the B200 pairwise path: validates a batch the way the reference's
+// constructors do (mod.rs:517-518, 554-571), plans it (b2a_plan.h), moves it to
+// HBM and launches K0 (pack) -> K1 (fill) -> K2 (row m, fix-ups, walk) ->
+// ops compaction on one CUDA stream.  There is no CPU implementation of the
+// alignment in this library: without a usable CUDA device every call fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/b200align.h"
+#include "b2a_fill_launch.h"
+#include "b2a_kernels.cuh"
+#include "b2a_plan.h"
+#include "b2a_walk.cuh"
+
+using namespace b2a;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      want = n;
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+const FillLaunch kFillShapes[] = {
+    {1, 16, launch_fill_1_16}, {1, 8, launch_fill_1_8},   {4, 16, launch_fill_4_16},
+    {8, 16, launch_fill_8_16}, {32, 8, launch_fill_32_8}, {32, 16, launch_fill_32_16},
+};
+
+const FillLaunch* find_shape(int G, int R) {
+  for (const FillLaunch& f : kFillShapes)
+    if (f.G == G && f.R == R) return &f;
+  return nullptr;
+}
+
+constexpr uint32_t kMaxStageSmem = 200 * 1024;  // of the 227 KB a CTA may use
+constexpr int kMaxAlpha = 64;
+
+}  // namespace
+
+struct b2a_engine {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  std::string err;
+  int tune_G = 0, tune_R = 0;
+  uint64_t tb_budget = 0;
+
+  // batch state
+  bool staged = false, ran = false;
+  Plan plan;
+  DevScoring sc{};
+  int flags = 0, mode = 0;
+  const FillLaunch* shape = nullptr;
+  uint64_t n_pairs = 0, blob_bytes = 0;
+  uint64_t h2d_bytes = 0;
+  std::vector<int32_t> lut_host;
+  uint8_t codemap_host[256];
+
+  DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
+      d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
+      d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> wave_ev;  // 3 per wave: fill start, fill stop / walk start, walk stop
+  uint32_t launches = 0;
+  int last_grid = 0;
+
+  int fail(int code, const std::string& what) {
+    err = what;
+    return code;
+  }
+  int cuda_fail(const char* what, cudaError_t e) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return B2A_E_CUDA;
+  }
+};
+
+#define CK(expr)                                              \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return e->cuda_fail(#expr, _e);    \
+  } while (0)
+
+namespace {
+
+// pick the fill shape for a batch (measured crossover: see DESIGN.md "shape selection")
+void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_pairs, int* G, int* R) {
+  if (e->tune_G && e->tune_R) {
+    *G = e->tune_G;
+    *R = e->tune_R;
+    return;
+  }
+  const uint64_t stage1 = (uint64_t)((maxm + 15) / 16 * 16 + 64 + (maxn + 15) / 16 * 16 + 64) * 32 * FILL_WARPS;
+  if (n_pairs >= 32ull * 148 * 4 && stage1 <= kMaxStageSmem && maxm <= 2048) {
+    *G = 1;
+    *R = 16;
+  } else if (n_pairs >= 4ull * 148 * 8 && maxm <= 4096) {
+    *G = 8;
+    *R = 16;
+  } else {
+    *G = 32;
+    *R = 8;
+  }
+}
+
+int validate_scoring(b2a_engine* e, const b2a_scoring* s) {
+  // the reference's constructor asserts (mod.rs:517-518, 554-571)
+  if (s->gap_open > 0) return e->fail(B2A_E_INVALID, "gap_open can't be positive");
+  if (s->gap_extend > 0) return e->fail(B2A_E_INVALID, "gap_extend can't be positive");
+  if (s->xclip_prefix > 0) return e->fail(B2A_E_INVALID, "Clipping penalty (x prefix) can't be positive");
+  if (s->xclip_suffix > 0) return e->fail(B2A_E_INVALID, "Clipping penalty (x suffix) can't be positive");
+  if (s->yclip_prefix > 0) return e->fail(B2A_E_INVALID, "Clipping penalty (y prefix) can't be positive");
+  if (s->yclip_suffix > 0) return e->fail(B2A_E_INVALID, "Clipping penalty (y suffix) can't be positive");
+  const int32_t clips[4] = {s->xclip_prefix, s->xclip_suffix, s->yclip_prefix, s->yclip_suffix};
+  for (int32_t c : clips)
+    if (c < B2A_MIN_SCORE) return e->fail(B2A_E_RANGE, "clip penalty below MIN_SCORE");
+  return B2A_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2a_version(void) { return "b200align 0.1 (sm_100a)"; }
+
+const char* b2a_last_error(const b2a_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
+  if (!out) return B2A_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0 || device_id < 0 || device_id >= count) return B2A_E_NO_DEVICE;
+  if (cudaSetDevice(device_id) != cudaSuccess) return B2A_E_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return B2A_E_NO_DEVICE;
+  if (prop.major < 10) return B2A_E_NO_DEVICE;  // kernels are built for sm_100a only
+  b2a_engine* e = new b2a_engine();
+  e->device = device_id;
+  e->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return B2A_E_CUDA;
+  }
+  e->stream = e->own_stream;
+  for (auto& v : e->ev) cudaEventCreate(&v);
+  *out = e;
+  return B2A_OK;
+}
+
+int32_t b2a_engine_destroy(b2a_engine* e) {
+  if (!e) return B2A_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  DevBuf* bufs[] = {&e->d_blob, &e->d_xoff, &e->d_xlen, &e->d_yoff, &e->d_ylen, &e->d_order, &e->d_pm,
+                    &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
+                    &e->d_opsscratch, &e->d_lut, &e->d_codemap, &e->d_ctl, &e->d_score, &e->d_xs,
+                    &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
+                    &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& v : e->ev)
+    if (v) cudaEventDestroy(v);
+  for (auto& v : e->wave_ev) cudaEventDestroy(v);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return B2A_OK;
+}
+
+int32_t b2a_engine_set_stream(b2a_engine* e, void* cuda_stream) {
+  if (!e) return B2A_E_INVALID;
+  e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return B2A_OK;
+}
+
+int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes) {
+  if (!e) return B2A_E_INVALID;
+  e->tb_budget = bytes;
+  return B2A_OK;
+}
+
+int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t G, int32_t R) {
+  if (!e) return B2A_E_INVALID;
+  if (G == 0 && R == 0) {
+    e->tune_G = e->tune_R = 0;
+    return B2A_OK;
+  }
+  if (!find_shape(G, R)) return e->fail(B2A_E_INVALID, "fill shape (G,R) not built into this library");
+  e->tune_G = G;
+  e->tune_R = R;
+  return B2A_OK;
+}
+
+int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const b2a_pairs* pairs) {
+  if (!e || !s || !pairs) return B2A_E_INVALID;
+  e->staged = e->ran = false;
+  if (mode < 0 || mode > 3) return e->fail(B2A_E_INVALID, "mode must be B2A_MODE_*");
+  int rc = validate_scoring(e, s);
+  if (rc) return rc;
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const uint64_t n = pairs->n_pairs;
+  if (n > 0x7fffffffull) return e->fail(B2A_E_INVALID, "more than 2^31 pairs in one batch");
+  e->n_pairs = n;
+  e->mode = mode;
+
+  // scoring with the mode's clip preset (mod.rs:935-938, 964-967, 996-999)
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  if (mode == B2A_MODE_GLOBAL) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
+  if (mode == B2A_MODE_SEMIGLOBAL) {
+    sc.xclip_prefix = sc.xclip_suffix = MIN_SCORE;
+    sc.yclip_prefix = sc.yclip_suffix = 0;
+  }
+  if (mode == B2A_MODE_LOCAL) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  sc.alpha = 0;
+
+  // lengths / offsets sanity
+  uint32_t maxm = 0, maxn = 0;
+  for (uint64_t p = 0; p < n; ++p) {
+    const uint64_t xe = pairs->x_off[p] + pairs->x_len[p], ye = pairs->y_off[p] + pairs->y_len[p];
+    if (xe > pairs->blob_bytes || ye > pairs->blob_bytes)
+      return e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
+    maxm = std::max(maxm, pairs->x_len[p]);
+    maxn = std::max(maxn, pairs->y_len[p]);
+  }
+  if (maxm > (1u << 24) || maxn > (1u << 24)) return e->fail(B2A_E_RANGE, "sequence longer than 2^24");
+
+  // substitution scores: MatchParams, or a compact LUT over the alphabet
+  int64_t maxabs = std::max<int64_t>(std::llabs((long long)s->match_score), std::llabs((long long)s->mismatch_score));
+  for (int k = 0; k < 256; ++k) e->codemap_host[k] = (uint8_t)k;
+  e->lut_host.clear();
+  if (s->table) {
+    bool present[256] = {false};
+    if (s->alphabet && s->alphabet_len) {
+      for (uint32_t k = 0; k < s->alphabet_len; ++k) present[s->alphabet[k]] = true;
+    } else {
+      for (uint64_t p = 0; p < n; ++p) {
+        const uint8_t* x = pairs->seq_blob + pairs->x_off[p];
+        const uint8_t* y = pairs->seq_blob + pairs->y_off[p];
+        for (uint32_t k = 0; k < pairs->x_len[p]; ++k) present[x[k]] = true;
+        for (uint32_t k = 0; k < pairs->y_len[p]; ++k) present[y[k]] = true;
+      }
+    }
+    std::vector<int> syms;
+    for (int k = 0; k < 256; ++k) {
+      e->codemap_host[k] = 0xFF;
+      if (present[k]) {
+        e->codemap_host[k] = (uint8_t)syms.size();
+        syms.push_back(k);
+      }
+    }
+    if (syms.empty()) {
+      syms.push_back(0);
+      e->codemap_host[0] = 0;
+    }
+    if ((int)syms.size() > kMaxAlpha)
+      return e->fail(B2A_E_UNSUPPORTED, "MatchFunc table over more than 64 distinct symbols");
+    sc.alpha = (int32_t)syms.size();
+    e->lut_host.resize((size_t)sc.alpha * sc.alpha);
+    maxabs = 0;
+    for (int a = 0; a < sc.alpha; ++a)
+      for (int b = 0; b < sc.alpha; ++b) {
+        const int32_t v = s->table[syms[a] * 256 + syms[b]];
+        e->lut_host[(size_t)a * sc.alpha + b] = v;
+        maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
+      }
+  }
+  // i32 range guard: every S/I/D of a real path stays within +-2^27, so MIN_SCORE-based
+  // sentinels can neither win nor overflow (the reference would silently wrap)
+  {
+    const int64_t unit = std::max<int64_t>(maxabs, std::max<int64_t>(-(int64_t)sc.gap_open, -(int64_t)sc.gap_extend));
+    const int64_t bound = ((int64_t)maxm + maxn + 2) * unit - (int64_t)sc.gap_open;
+    if (bound > (1ll << 27)) return e->fail(B2A_E_RANGE, "scores x lengths exceed the i32-safe range (2^27)");
+    const int32_t clips[4] = {sc.xclip_prefix, sc.xclip_suffix, sc.yclip_prefix, sc.yclip_suffix};
+    for (int32_t c : clips)
+      if (c > DEAD_CLIP && -(int64_t)c > (1ll << 27))
+        return e->fail(B2A_E_RANGE, "clip penalty between -2^27 and MIN_SCORE/2 is not supported");
+  }
+  e->sc = sc;
+  e->flags = scoring_flags(sc);
+
+  // shape + plan
+  int G = 1, R = 16;
+  choose_shape(e, maxm, maxn, n, &G, &R);
+  e->shape = find_shape(G, R);
+  if (!e->shape) return e->fail(B2A_E_INVALID, "no fill kernel for the requested shape");
+  uint64_t budget = e->tb_budget;
+  if (!budget) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    budget = (uint64_t)((double)fr * 0.6);
+  }
+  build_plan(e->plan, pairs->x_len, pairs->y_len, n, G, R, budget);
+  const Plan& pl = e->plan;
+  const uint32_t lut_bytes = sc.alpha ? ((uint32_t)(sc.alpha * sc.alpha * 4 + 127) & ~127u) : 0u;
+  if (64 + lut_bytes + (uint64_t)FILL_WARPS * pl.smem_seq_bytes > kMaxStageSmem)
+    return e->fail(B2A_E_UNSUPPORTED, "sequences too long for on-chip staging with this fill shape");
+
+  // device memory
+  e->blob_bytes = pairs->blob_bytes;
+  CK(e->d_blob.reserve(pairs->blob_bytes + 16));
+  CK(e->d_xoff.reserve(n * 8 + 8));
+  CK(e->d_yoff.reserve(n * 8 + 8));
+  CK(e->d_xlen.reserve(n * 4 + 4));
+  CK(e->d_ylen.reserve(n * 4 + 4));
+  CK(e->d_order.reserve(n * 4 + 4));
+  CK(e->d_pm.reserve(n * 4 + 4));
+  CK(e->d_pn.reserve(n * 4 + 4));
+  CK(e->d_blocks.reserve(pl.blocks.size() * sizeof(Block) + 8));
+  CK(e->d_seq.reserve(pl.seq_bytes + 16));
+  CK(e->d_bnd.reserve(pl.max_bnd + 16));
+  CK(e->d_rows.reserve(pl.max_rows + 16));
+  CK(e->d_rowm.reserve(pl.max_rowm + 16));
+  CK(e->d_tb.reserve(pl.max_tb + 16));
+  CK(e->d_opsscratch.reserve(pl.ops_bytes + 16));
+  CK(e->d_lut.reserve(e->lut_host.size() * 4 + 16));
+  CK(e->d_codemap.reserve(256));
+  CK(e->d_ctl.reserve(256));
+  CK(e->d_score.reserve(n * 4 + 4));
+  CK(e->d_xs.reserve(n * 4 + 4));
+  CK(e->d_xe.reserve(n * 4 + 4));
+  CK(e->d_ys.reserve(n * 4 + 4));
+  CK(e->d_ye.reserve(n * 4 + 4));
+  CK(e->d_nops.reserve(n * 4 + 4));
+  CK(e->d_opssrc.reserve(n * 8 + 8));
+  CK(e->d_clip.reserve(n * 16 + 16));
+  CK(e->d_status.reserve(n * 4 + 4));
+  CK(e->d_nops64.reserve((n + 1) * 8));
+  CK(e->d_opsoff.reserve((n + 1) * 8));
+
+  // host -> device
+  cudaStream_t st = e->stream;
+  e->h2d_bytes = 0;
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    e->h2d_bytes += bytes;
+    return bytes ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
+  CK(up(e->d_xoff, pairs->x_off, n * 8));
+  CK(up(e->d_yoff, pairs->y_off, n * 8));
+  CK(up(e->d_xlen, pairs->x_len, n * 4));
+  CK(up(e->d_ylen, pairs->y_len, n * 4));
+  CK(up(e->d_order, pl.order.data(), n * 4));
+  CK(up(e->d_pm, pl.pm.data(), n * 4));
+  CK(up(e->d_pn, pl.pn.data(), n * 4));
+  CK(up(e->d_blocks, pl.blocks.data(), pl.blocks.size() * sizeof(Block)));
+  CK(up(e->d_codemap, e->codemap_host, 256));
+  if (!e->lut_host.empty()) CK(up(e->d_lut, e->lut_host.data(), e->lut_host.size() * 4));
+  // plan vectors are host-pageable and reused by the next stage: make the copies land first
+  CK(cudaStreamSynchronize(st));
+  e->staged = true;
+  return B2A_OK;
+}
+
+int32_t b2a_batch_run(b2a_engine* e) {
+  if (!e) return B2A_E_INVALID;
+  if (!e->staged) return e->fail(B2A_E_STATE, "b2a_batch_run before b2a_batch_stage");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const Plan& pl = e->plan;
+  cudaStream_t st = e->stream;
+  const uint64_t n = e->n_pairs;
+  e->launches = 0;
+  uint32_t* ctl = e->d_ctl.as<uint32_t>();  // [0] bad symbol, [1] walk error, [2..] per-wave task counters
+  CK(cudaMemsetAsync(ctl, 0, 256, st));
+  CK(cudaEventRecord(e->ev[0], st));
+  if (!pl.blocks.empty()) {
+    PackParams pk{};
+    pk.blocks = e->d_blocks.as<Block>();
+    pk.order = e->d_order.as<uint32_t>();
+    pk.blob = e->d_blob.as<uint8_t>();
+    pk.x_off = e->d_xoff.as<uint64_t>();
+    pk.x_len = e->d_xlen.as<uint32_t>();
+    pk.y_off = e->d_yoff.as<uint64_t>();
+    pk.y_len = e->d_ylen.as<uint32_t>();
+    pk.codemap = e->d_codemap.as<uint8_t>();
+    pk.seq = e->d_seq.as<uint8_t>();
+    pk.bad_symbol = ctl;
+    pk.G = pl.G;
+    pack_kernel<<<(unsigned)pl.blocks.size(), 256, 0, st>>>(pk);
+    CK(cudaGetLastError());
+    ++e->launches;
+  }
+  CK(cudaEventRecord(e->ev[1], st));
+  float fill_ms = 0.f, walk_ms = 0.f;
+  (void)fill_ms;
+  (void)walk_ms;
+  size_t wi = 0;
+  for (const Wave& w : pl.waves) {
+    const uint32_t nb = w.block_hi - w.block_lo;
+    if (wi >= 60) return e->fail(B2A_E_UNSUPPORTED, "more than 60 traceback waves; raise the budget");
+    FillParams fp{};
+    fp.blocks = e->d_blocks.as<Block>() + w.block_lo;
+    fp.nblocks = nb;
+    fp.pm = e->d_pm.as<uint32_t>();
+    fp.pn = e->d_pn.as<uint32_t>();
+    fp.seq = e->d_seq.as<uint8_t>();
+    fp.bnd = e->d_bnd.as<uint8_t>();
+    fp.rows = e->d_rows.as<uint8_t>();
+    fp.tb = e->d_tb.as<uint8_t>();
+    fp.lut = e->d_lut.as<int32_t>();
+    fp.task_counter = ctl + 2 + wi;
+    fp.smem_seq_bytes = pl.smem_seq_bytes;
+    fp.sc = e->sc;
+    while (e->wave_ev.size() < 3 * (wi + 1)) {
+      cudaEvent_t v;
+      CK(cudaEventCreate(&v));
+      e->wave_ev.push_back(v);
+    }
+    CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
+    CK(e->shape->launch(e->flags, fp, nb * (uint32_t)pl.G, e->num_sms, st, &e->last_grid));
+    ++e->launches;
+    CK(cudaEventRecord(e->wave_ev[3 * wi + 1], st));
+
+    WalkParams wp{};
+    wp.blocks = fp.blocks;
+    wp.nblocks = nb;
+    wp.pm = fp.pm;
+    wp.pn = fp.pn;
+    wp.order = e->d_order.as<uint32_t>();
+    wp.seq = fp.seq;
+    wp.bnd = fp.bnd;
+    wp.rows = fp.rows;
+    wp.rowm = e->d_rowm.as<uint8_t>();
+    wp.tb = fp.tb;
+    wp.ops_scratch = e->d_opsscratch.as<uint8_t>();
+    wp.lut = fp.lut;
+    wp.sc = e->sc;
+    wp.G = pl.G;
+    wp.R = pl.R;
+    wp.filter_clips = (e->mode == B2A_MODE_SEMIGLOBAL || e->mode == B2A_MODE_LOCAL) ? 1 : 0;
+    wp.score = e->d_score.as<int32_t>();
+    wp.xstart = e->d_xs.as<uint32_t>();
+    wp.xend = e->d_xe.as<uint32_t>();
+    wp.ystart = e->d_ys.as<uint32_t>();
+    wp.yend = e->d_ye.as<uint32_t>();
+    wp.n_ops = e->d_nops.as<uint32_t>();
+    wp.ops_src = e->d_opssrc.as<uint64_t>();
+    wp.clip_len = e->d_clip.as<uint32_t>();
+    wp.status = e->d_status.as<uint32_t>();
+    wp.err_flag = ctl + 1;
+    const unsigned wgrid = (nb * 32 + 127) / 128;
+    walk_kernel<<<wgrid, 128, 0, st>>>(wp);
+    CK(cudaGetLastError());
+    ++e->launches;
+    CK(cudaEventRecord(e->wave_ev[3 * wi + 2], st));
+    ++wi;
+  }
+  CK(cudaEventRecord(e->ev[4], st));
+  // ops compaction: widen -> exclusive scan -> gather
+  if (n) {
+    const unsigned g1 = (unsigned)((n + 1 + 255) / 256);
+    widen_kernel<<<g1, 256, 0, st>>>(e->d_nops.as<uint32_t>(), e->d_nops64.as<uint64_t>(), n);
+    CK(cudaGetLastError());
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->d_nops64.as<uint64_t>(), e->d_opsoff.as<uint64_t>(),
+                                     (int)(n + 1), st));
+    CK(e->d_scan.reserve(tmp + 16));
+    CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_nops64.as<uint64_t>(),
+                                     e->d_opsoff.as<uint64_t>(), (int)(n + 1), st));
+    // worst case every pair emits m+n+4 ops; size the dense buffer by the scratch size
+    CK(e->d_opsdense.reserve(pl.ops_bytes + 16));
+    const unsigned g2 = (unsigned)((n * 32 + 255) / 256);
+    gather_ops_kernel<<<g2, 256, 0, st>>>(e->d_opsscratch.as<uint8_t>(), e->d_opssrc.as<uint64_t>(),
+                                          e->d_opsoff.as<uint64_t>(), e->d_opsdense.as<uint8_t>(), n);
+    CK(cudaGetLastError());
+    e->launches += 4;
+  }
+  CK(cudaEventRecord(e->ev[5], st));
+  e->ran = true;
+  return B2A_OK;
+}
+
+int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
+  if (!e) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "b2a_batch_fetch before b2a_batch_run");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  cudaStream_t st = e->stream;
+  const uint64_t n = e->n_pairs;
+  uint64_t d2h = 0;
+  uint32_t ctl[2] = {0, 0};
+  CK(cudaMemcpyAsync(ctl, e->d_ctl.p, 8, cudaMemcpyDeviceToHost, st));
+  if (r && n) {
+    auto down = [&](void* dst, const DevBuf& b, size_t bytes) -> cudaError_t {
+      if (!dst || !bytes) return cudaSuccess;
+      d2h += bytes;
+      return cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CK(down(r->score, e->d_score, n * 4));
+    CK(down(r->xstart, e->d_xs, n * 4));
+    CK(down(r->xend, e->d_xe, n * 4));
+    CK(down(r->ystart, e->d_ys, n * 4));
+    CK(down(r->yend, e->d_ye, n * 4));
+    CK(down(r->clip_len, e->d_clip, n * 16));
+    uint64_t total = 0;
+    if (r->ops_off) {
+      CK(down(r->ops_off, e->d_opsoff, (n + 1) * 8));
+      CK(cudaStreamSynchronize(st));
+      total = r->ops_off[n];
+    } else {
+      CK(cudaMemcpyAsync(&total, e->d_opsoff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    if (r->ops) {
+      if (total > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for this batch");
+      CK(down(r->ops, e->d_opsdense, total));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  if (ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
+  if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->cells = e->plan.cells;
+    stats->h2d_bytes = e->h2d_bytes;
+    stats->d2h_bytes = d2h;
+    stats->traceback_bytes = e->plan.total_tb;
+    cudaEventElapsedTime(&stats->pack_ms, e->ev[0], e->ev[1]);
+    for (size_t wv = 0; wv < e->plan.waves.size(); ++wv) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, e->wave_ev[3 * wv + 0], e->wave_ev[3 * wv + 1]);
+      cudaEventElapsedTime(&b, e->wave_ev[3 * wv + 1], e->wave_ev[3 * wv + 2]);
+      stats->fill_ms += a;
+      stats->walk_ms += b;
+    }
+    float tail = 0.f;
+    cudaEventElapsedTime(&tail, e->ev[4], e->ev[5]);  // ops compaction
+    stats->walk_ms += tail;
+    stats->kernel_launches = e->launches;
+    stats->waves = (uint32_t)e->plan.waves.size();
+    stats->fill_lanes_per_pair = (uint32_t)e->plan.G;
+    stats->fill_rows_per_lane = (uint32_t)e->plan.R;
+  }
+  return B2A_OK;
+}
+
+int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring, const b2a_pairs* pairs,
+                        b2a_results* results, b2a_stats* stats) {
+  int rc = b2a_batch_stage(e, mode, scoring, pairs);
+  if (rc) return rc;
+  rc = b2a_batch_run(e);
+  if (rc) return rc;
+  return b2a_batch_fetch(e, results, stats);
+}
+
+int32_t b2a_align_batch_banded(b2a_engine* e, int32_t, const b2a_scoring*, uint32_t, uint32_t,
+                               const b2a_pairs*, b2a_results*, b2a_stats*) {
+  if (!e) return B2A_E_INVALID;
+  return e->fail(B2A_E_UNSUPPORTED, "banded::Aligner path (SURVEY 8 rows a10-a15) is not built yet");
+}
+
+uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n) {
+  return 40u + ((max_m + max_n + 4u + 15u) & ~15u);
+}
+
+int32_t b2a_batch_records_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes, uint32_t* stride_bytes) {
+  if (!e) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "records requested before b2a_batch_run");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const uint32_t stride = b2a_record_stride(e->plan.maxm, e->plan.maxn);
+  if (stride_bytes) *stride_bytes = stride;
+  const uint64_t n = e->n_pairs;
+  if (dst_bytes < n * stride) return e->fail(B2A_E_CAPACITY, "record buffer too small");
+  if (n) {
+    const unsigned g = (unsigned)((n * 32 + 255) / 256);
+    records_kernel<<<g, 256, 0, e->stream>>>(
+        e->d_score.as<int32_t>(), e->d_xs.as<uint32_t>(), e->d_xe.as<uint32_t>(), e->d_ys.as<uint32_t>(),
+        e->d_ye.as<uint32_t>(), e->d_nops.as<uint32_t>(), e->d_clip.as<uint32_t>(),
+        e->d_opsscratch.as<uint8_t>(), e->d_opssrc.as<uint64_t>(), reinterpret_cast<uint8_t*>(dev_dst),
+        stride, n);
+    CK(cudaGetLastError());
+  }
+  return B2A_OK;
+}
+
+int32_t b2a_batch_records(b2a_engine* e, void** dev_records, uint32_t* stride_bytes, uint64_t* n_records) {
+  if (!e || !dev_records) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "records requested before b2a_batch_run");
+  const uint32_t stride = b2a_record_stride(e->plan.maxm, e->plan.maxn);
+  CK(e->d_records.reserve(e->n_pairs * (uint64_t)stride + 16));
+  int rc = b2a_batch_records_into(e, e->d_records.p, e->n_pairs * (uint64_t)stride, stride_bytes);
+  if (rc) return rc;
+  *dev_records = e->d_records.p;
+  if (n_records) *n_records = e->n_pairs;
+  return B2A_OK;
+}
+
+int32_t b2a_records_decode(const void* host_records, uint32_t stride, uint64_t n, b2a_results* r) {
+  if (!host_records || !r || stride < 40) return B2A_E_INVALID;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(host_records);
+  uint64_t off = 0;
+  for (uint64_t p = 0; p < n; ++p) {
+    const uint32_t* h = reinterpret_cast<const uint32_t*>(base + p * stride);
+    if (r->score) r->score[p] = (int32_t)h[0];
+    if (r->xstart) r->xstart[p] = h[1];
+    if (r->xend) r->xend[p] = h[2];
+    if (r->ystart) r->ystart[p] = h[3];
+    if (r->yend) r->yend[p] = h[4];
+    const uint32_t nops = h[5];
+    if (nops > stride - 40) return B2A_E_INVALID;
+    if (r->clip_len)
+      for (int k = 0; k < 4; ++k) r->clip_len[4 * p + k] = h[6 + k];
+    if (r->ops_off) r->ops_off[p] = off;
+    if (r->ops) {
+      if (off + nops > r->ops_capacity) return B2A_E_CAPACITY;
+      std::memcpy(r->ops + off, base + p * stride + 40, nops);
+    }
+    off += nops;
+  }
+  if (r->ops_off) r->ops_off[n] = off;
+  return B2A_OK;
+}
+
+}  // extern "C"

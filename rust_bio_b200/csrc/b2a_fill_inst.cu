@@ -1,0 +1,54 @@
+// One (G, R) shape of the K1 fill kernel: compile with -DB2A_G=<G> -DB2A_R=<R>.
+#include "b2a_fill_launch.h"
+
+#ifndef B2A_G
+#error "compile with -DB2A_G=... -DB2A_R=..."
+#endif
+
+namespace b2a {
+
+namespace {
+
+template <int FLAGS>
+cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t stream,
+               int* grid_out) {
+  auto kern = fill_kernel<B2A_G, B2A_R, FLAGS>;
+  const uint32_t lut_bytes =
+      (FLAGS & F_LUT) ? ((uint32_t)(prm.sc.alpha * prm.sc.alpha * 4 + 127) & ~127u) : 0u;
+  const size_t smem = 64 + lut_bytes + (size_t)FILL_WARPS * prm.smem_seq_bytes;
+  cudaError_t err =
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FILL_WARPS * 32, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  const uint32_t want = (ntasks + FILL_WARPS - 1) / FILL_WARPS;
+  uint32_t grid = (uint32_t)(num_sms * per_sm);
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  if (grid_out) *grid_out = (int)grid;
+  kern<<<grid, FILL_WARPS * 32, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+#define B2A_CAT2(a, b, c) a##b##_##c
+#define B2A_CAT(a, b, c) B2A_CAT2(a, b, c)
+
+cudaError_t B2A_CAT(launch_fill_, B2A_G, B2A_R)(int flags, const FillParams& prm, uint32_t ntasks,
+                                                int num_sms, cudaStream_t stream, int* grid_out) {
+  constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+  switch (flags) {
+    case 0: return go<0>(prm, ntasks, num_sms, stream, grid_out);
+    case F_TRACK_ROWS: return go<F_TRACK_ROWS>(prm, ntasks, num_sms, stream, grid_out);
+    case ALL: return go<ALL>(prm, ntasks, num_sms, stream, grid_out);
+    case F_LUT: return go<F_LUT>(prm, ntasks, num_sms, stream, grid_out);
+    case F_LUT | F_TRACK_ROWS: return go<F_LUT | F_TRACK_ROWS>(prm, ntasks, num_sms, stream, grid_out);
+    case F_LUT | ALL: return go<F_LUT | ALL>(prm, ntasks, num_sms, stream, grid_out);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace b2a

@@ -1,0 +1,104 @@
+// Small support kernels around K1/K2: K0 (pack/stage sequences into the
+// TMA-friendly [task][word][pair] layout), ops compaction, and the fixed-stride
+// result records that are all-gathered across GPUs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "b2a_common.cuh"
+
+namespace b2a {
+
+struct PackParams {
+  const Block* blocks;
+  const uint32_t* order;    // sorted -> caller index
+  const uint8_t* blob;      // caller's sequence blob (device copy)
+  const uint64_t* x_off;    // caller order
+  const uint32_t* x_len;
+  const uint64_t* y_off;
+  const uint32_t* y_len;
+  const uint8_t* codemap;   // 256 bytes: symbol -> staged code (identity for MatchParams); 0xFF = not in alphabet
+  uint8_t* seq;             // staged arena
+  uint32_t* bad_symbol;     // set to 1 if a byte outside the alphabet is met
+  int32_t G;
+};
+
+// K0: one CTA per block; each thread produces staged 32-bit words.
+// Staged layout of a block (32-bit words): x: [task sub][word w][pair slot p], then y likewise,
+// with P = 32/G pairs per task.  Bytes past the end of a sequence are 0.
+__global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
+  const Block blk = prm.blocks[blockIdx.x];
+  const int G = prm.G, P = 32 / G;
+  uint32_t* out = reinterpret_cast<uint32_t*>(prm.seq + blk.seq_off);
+  const uint32_t xtot = blk.xwords * 32, ytot = blk.ywords * 32;
+  for (uint32_t k = threadIdx.x; k < xtot + ytot; k += blockDim.x) {
+    const bool isy = k >= xtot;
+    const uint32_t kk = isy ? k - xtot : k;
+    const uint32_t words = isy ? blk.ywords : blk.xwords;
+    // walk the pair fastest inside a sequence word so that a thread's 4 source bytes are adjacent
+    const uint32_t pair = kk / words, w = kk % words;  // pair slot in block, word in sequence
+    uint32_t val = 0;
+    if (pair < blk.npairs) {
+      const uint32_t orig = prm.order[blk.first + pair];
+      const uint64_t off = isy ? prm.y_off[orig] : prm.x_off[orig];
+      const uint32_t len = isy ? prm.y_len[orig] : prm.x_len[orig];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const uint32_t pos = w * 4 + b;
+        if (pos < len) {
+          const uint32_t code = prm.codemap[prm.blob[off + pos]];
+          if (code == 0xFFu) *prm.bad_symbol = 1u;
+          val |= (code & 0xFFu) << (8 * b);
+        }
+      }
+    }
+    const uint32_t sub = pair / P, p = pair % P;
+    out[(isy ? (size_t)G * blk.xwords * P : 0) + ((size_t)sub * words + w) * P + p] = val;
+  }
+}
+
+// ops compaction: pair p's ops move from the walk scratch to ops_dense[ops_off[p] ..].
+__global__ void gather_ops_kernel(const uint8_t* __restrict__ scratch,
+                                  const uint64_t* __restrict__ ops_src,
+                                  const uint64_t* __restrict__ ops_off, uint8_t* __restrict__ dense,
+                                  uint64_t n_pairs) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n_pairs) return;
+  const uint64_t lo = ops_off[warp], n = ops_off[warp + 1] - lo;
+  const uint8_t* src = scratch + ops_src[warp];
+  for (uint64_t k = lane; k < n; k += 32) dense[lo + k] = src[k];
+}
+
+// n_ops (u32) -> u64 with a trailing 0 so one exclusive scan yields n_pairs+1 offsets
+__global__ void widen_kernel(const uint32_t* __restrict__ n_ops, uint64_t* __restrict__ out,
+                             uint64_t n_pairs) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i <= n_pairs) out[i] = i < n_pairs ? n_ops[i] : 0;
+}
+
+// fixed-stride records: {score, xstart, xend, ystart, yend, n_ops, clip_len[4]} + ops
+__global__ void records_kernel(const int32_t* score, const uint32_t* xstart, const uint32_t* xend,
+                               const uint32_t* ystart, const uint32_t* yend, const uint32_t* n_ops,
+                               const uint32_t* clip_len, const uint8_t* scratch,
+                               const uint64_t* ops_src, uint8_t* records, uint32_t stride,
+                               uint64_t n_pairs) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n_pairs) return;
+  uint8_t* rec = records + warp * stride;
+  uint32_t* head = reinterpret_cast<uint32_t*>(rec);
+  const uint32_t n = n_ops[warp];
+  if (lane == 0) {
+    head[0] = (uint32_t)score[warp];
+    head[1] = xstart[warp];
+    head[2] = xend[warp];
+    head[3] = ystart[warp];
+    head[4] = yend[warp];
+    head[5] = n;
+  }
+  if (lane < 4) head[6 + lane] = clip_len[4 * warp + lane];
+  const uint8_t* src = scratch + ops_src[warp];
+  for (uint32_t k = lane; k < stride - 40; k += 32) rec[40 + k] = k < n ? src[k] : 0;
+}
+
+}  // namespace b2a

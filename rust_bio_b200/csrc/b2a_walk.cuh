@@ -41,6 +41,7 @@ struct WalkParams {
   uint64_t* ops_src;   // where the pair's ops start inside ops_scratch
   uint32_t* clip_len;  // 4 per pair
   uint32_t* status;    // 0 ok, 1 = corrupt traceback (reference would panic, mod.rs:905)
+  uint32_t* err_flag;  // set to 1 if any pair's status is non-zero
 };
 
 constexpr uint32_t LAZY = 15;  // "came from S of the neighbour": resolved when the walk needs it
@@ -285,10 +286,12 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
   }
 
   // ------------------------------------------------ fix-up 1, mod.rs:809-821
+  // K1 only keeps the row trackers when yclip_suffix is live; a dead one can never win (Sn <= MIN/2 + S)
+  const bool ys_live = ys > DEAD_CLIP;
   if (m >= 1) {
     for (int32_t i = 0; i < m; ++i) {
       int32_t S = v.row(ROWS_SL, i);
-      const int32_t Sn = v.row(ROWS_SN, i);
+      const int32_t Sn = (i == 0 || ys_live) ? v.row(ROWS_SN, i) : MIN_SCORE;
       if (Sn > S) {
         S = Sn;
         v.row(ROWS_SL, i) = S;
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
   prm.n_ops[dst] = o.n_ops;
   prm.ops_src[dst] = blk.ops_off + (uint64_t)(lane + 1) * cap - o.n_ops;
   prm.status[dst] = o.status;
+  if (o.status) atomicOr(prm.err_flag, 1u);
 #pragma unroll
   for (int k = 0; k < 4; ++k) prm.clip_len[4 * (size_t)dst + k] = o.clip[k];
 }

@@ -1,0 +1,170 @@
+"""Engine: one CUDA device, batches in / Alignment fields out (thin wrapper over the C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import B2AError, CPairs, CResults, CScoring, CStats
+
+Batch = Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, np.ndarray]
+
+
+def pack_pairs(pairs) -> Batch:
+    """[(x_bytes, y_bytes), ...] -> (blob, x_off, x_len, y_off, y_len), 16-byte aligned sequences."""
+    n = len(pairs)
+    x_len = np.fromiter((len(p[0]) for p in pairs), dtype=np.uint32, count=n)
+    y_len = np.fromiter((len(p[1]) for p in pairs), dtype=np.uint32, count=n)
+    pad = lambda v: (v.astype(np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+    sizes = np.stack([pad(x_len), pad(y_len)], axis=1).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    blob = np.zeros(int(offs[-1]) + 16, dtype=np.uint8)
+    x_off, y_off = offs[0:-1:2].copy(), offs[1::2].copy()
+    for i, (x, y) in enumerate(pairs):
+        blob[int(x_off[i]):int(x_off[i]) + len(x)] = np.frombuffer(bytes(x), dtype=np.uint8)
+        blob[int(y_off[i]):int(y_off[i]) + len(y)] = np.frombuffer(bytes(y), dtype=np.uint8)
+    return blob, x_off, x_len, y_off, y_len
+
+
+class Results:
+    """Host outputs of one batch (numpy arrays; pass pinned arrays via `out=` for speed)."""
+
+    def __init__(self, n_pairs: int, ops_capacity: int, out: Optional[Dict[str, np.ndarray]] = None):
+        mk = lambda name, shape, dt: (out[name] if out and name in out else np.zeros(shape, dtype=dt))
+        self.n_pairs = n_pairs
+        self.score = mk("score", n_pairs, np.int32)
+        self.xstart = mk("xstart", n_pairs, np.uint32)
+        self.xend = mk("xend", n_pairs, np.uint32)
+        self.ystart = mk("ystart", n_pairs, np.uint32)
+        self.yend = mk("yend", n_pairs, np.uint32)
+        self.ops_off = mk("ops_off", n_pairs + 1, np.uint64)
+        self.ops = mk("ops", max(1, ops_capacity), np.uint8)
+        self.clip_len = mk("clip_len", 4 * max(1, n_pairs), np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.c = CResults(p(self.score), p(self.xstart), p(self.xend), p(self.ystart), p(self.yend),
+                          p(self.ops_off), p(self.ops), len(self.ops), p(self.clip_len))
+
+    def ops_of(self, i: int):
+        """[(code, clip_len)] of pair i in alignment order."""
+        lo, hi = int(self.ops_off[i]), int(self.ops_off[i + 1])
+        res, k = [], 0
+        for c in self.ops[lo:hi]:
+            c = int(c)
+            if c >= 4:
+                res.append((c, int(self.clip_len[4 * i + k])))
+                k += 1
+            else:
+                res.append((c, 0))
+        return res
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k in ("score", "xstart", "xend", "ystart", "yend")}
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.b2a_engine_create(C.byref(h), int(device))
+        if rc != 0:
+            raise B2AError(rc, f"cannot create engine on cuda:{device} (no CPU fallback exists)")
+        self._h = h
+        self.device = device
+        self.stats = CStats()
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2a_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B2AError(rc, self._L.b2a_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.b2a_engine_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_tuning(self, lanes_per_pair: int, rows_per_lane: int):
+        self._check(self._L.b2a_engine_set_tuning(self._h, lanes_per_pair, rows_per_lane))
+
+    def set_traceback_budget(self, nbytes: int):
+        self._check(self._L.b2a_engine_set_traceback_budget(self._h, int(nbytes)))
+
+    @staticmethod
+    def _cpairs(batch: Batch):
+        blob, x_off, x_len, y_off, y_len = batch
+        assert blob.dtype == np.uint8 and x_off.dtype == np.uint64 and y_off.dtype == np.uint64
+        assert x_len.dtype == np.uint32 and y_len.dtype == np.uint32
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        return CPairs(p(blob), p(x_off), p(x_len), p(y_off), p(y_len), blob.nbytes, len(x_len))
+
+    @staticmethod
+    def default_ops_capacity(batch: Batch) -> int:
+        return int(batch[2].astype(np.uint64).sum() + batch[4].astype(np.uint64).sum() + 4 * len(batch[2]))
+
+    def align_batch(self, mode: int, cscoring: CScoring, batch: Batch, results: Optional[Results] = None,
+                    ops_capacity: Optional[int] = None) -> Results:
+        """b2a_align_batch: host buffers in, host buffers out."""
+        if results is None:
+            results = Results(len(batch[2]), ops_capacity if ops_capacity is not None
+                              else self.default_ops_capacity(batch))
+        cp = self._cpairs(batch)
+        self._check(self._L.b2a_align_batch(self._h, int(mode), C.byref(cscoring), C.byref(cp),
+                                            C.byref(results.c), C.byref(self.stats)))
+        return results
+
+    def align_batch_banded(self, mode: int, cscoring: CScoring, k: int, w: int, batch: Batch,
+                           results: Optional[Results] = None) -> Results:
+        if results is None:
+            results = Results(len(batch[2]), self.default_ops_capacity(batch))
+        cp = self._cpairs(batch)
+        self._check(self._L.b2a_align_batch_banded(self._h, int(mode), C.byref(cscoring), int(k), int(w),
+                                                   C.byref(cp), C.byref(results.c), C.byref(self.stats)))
+        return results
+
+    # staged form
+    def stage(self, mode: int, cscoring: CScoring, batch: Batch):
+        self._keep = (batch, cscoring)
+        cp = self._cpairs(batch)
+        self._check(self._L.b2a_batch_stage(self._h, int(mode), C.byref(cscoring), C.byref(cp)))
+
+    def run(self):
+        self._check(self._L.b2a_batch_run(self._h))
+
+    def fetch(self, results: Optional[Results]) -> Optional[Results]:
+        self._check(self._L.b2a_batch_fetch(self._h, C.byref(results.c) if results else None,
+                                            C.byref(self.stats)))
+        return results
+
+    def records_into(self, dev_ptr: int, nbytes: int) -> int:
+        stride = C.c_uint32()
+        self._check(self._L.b2a_batch_records_into(self._h, C.c_void_p(dev_ptr), int(nbytes), C.byref(stride)))
+        return stride.value
+
+    def record_stride(self, max_m: int, max_n: int) -> int:
+        return int(self._L.b2a_record_stride(max_m, max_n))
+
+    def decode_records(self, host_records: np.ndarray, stride: int, n: int, ops_capacity: int) -> Results:
+        res = Results(n, ops_capacity)
+        rc = self._L.b2a_records_decode(host_records.ctypes.data_as(C.c_void_p), stride, n, C.byref(res.c))
+        if rc != 0:
+            raise B2AError(rc, "b2a_records_decode")
+        return res
+
+
+_default: Dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

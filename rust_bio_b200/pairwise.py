@@ -1,0 +1,211 @@
+"""Mirror of `bio::alignment::pairwise` (reference src/alignment/pairwise/mod.rs) on the B200 engine.
+
+Same names, argument meaning and error behaviour as the reference:
+  MIN_SCORE (mod.rs:174), MatchParams (186-217), Scoring (238-429), Aligner (472-1015).
+`Aligner.global` is spelled `global_` (Python keyword).  Every per-pair method is a batch of one;
+`*_batch` methods take [(x, y), ...] and are the form the GPU is built for.  The reference panics on
+bad parameters (assert!); this mirror raises AssertionError with the same message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, replace
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import scores as _scores
+from ._lib import (CScoring, MIN_SCORE, MODE_CUSTOM, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL)
+from .alignment import Alignment, AlignmentMode, AlignmentOperation
+from .engine import Engine, Results, default_engine, pack_pairs
+
+__all__ = ["MIN_SCORE", "MatchParams", "Scoring", "Aligner", "MatchFunc"]
+
+MatchFunc = Union["MatchParams", Callable[[int, int], int]]
+DEFAULT_ALIGNER_CAPACITY = 200  # mod.rs:483
+_MATRIX_ALPHABET = bytes(range(65, 91)) + b"*"
+
+
+@dataclass(frozen=True)
+class MatchParams:
+    """mod.rs:186-217"""
+    match_score: int
+    mismatch_score: int
+
+    @staticmethod
+    def new(match_score: int, mismatch_score: int) -> "MatchParams":
+        assert match_score >= 0, "match_score can't be negative"
+        assert mismatch_score <= 0, "mismatch_score can't be positive"
+        return MatchParams(match_score, mismatch_score)
+
+    def score(self, a: int, b: int) -> int:
+        return self.match_score if a == b else self.mismatch_score
+
+    def __call__(self, a: int, b: int) -> int:
+        return self.score(a, b)
+
+
+@dataclass
+class Scoring:
+    """mod.rs:238-429. Builders return a modified copy (the reference's `mut self -> Self`)."""
+    gap_open: int
+    gap_extend: int
+    match_fn: MatchFunc
+    match_scores: Optional[Tuple[int, int]] = None
+    xclip_prefix: int = MIN_SCORE
+    xclip_suffix: int = MIN_SCORE
+    yclip_prefix: int = MIN_SCORE
+    yclip_suffix: int = MIN_SCORE
+
+    @staticmethod
+    def from_scores(gap_open: int, gap_extend: int, match_score: int, mismatch_score: int) -> "Scoring":
+        assert gap_open <= 0, "gap_open can't be positive"
+        assert gap_extend <= 0, "gap_extend can't be positive"
+        return Scoring(gap_open, gap_extend, MatchParams.new(match_score, mismatch_score),
+                       (match_score, mismatch_score))
+
+    @staticmethod
+    def new(gap_open: int, gap_extend: int, match_fn: MatchFunc) -> "Scoring":
+        assert gap_open <= 0, "gap_open can't be positive"
+        assert gap_extend <= 0, "gap_extend can't be positive"
+        return Scoring(gap_open, gap_extend, match_fn, None)
+
+    def _clip(self, **kw) -> "Scoring":
+        for v in kw.values():
+            assert v <= 0, "Clipping penalty can't be positive"
+        return replace(self, **kw)
+
+    def xclip(self, penalty: int) -> "Scoring":
+        return self._clip(xclip_prefix=penalty, xclip_suffix=penalty)
+
+    def xclip_prefix_(self, penalty: int) -> "Scoring":
+        return self._clip(xclip_prefix=penalty)
+
+    def xclip_suffix_(self, penalty: int) -> "Scoring":
+        return self._clip(xclip_suffix=penalty)
+
+    def yclip(self, penalty: int) -> "Scoring":
+        return self._clip(yclip_prefix=penalty, yclip_suffix=penalty)
+
+    def yclip_prefix_(self, penalty: int) -> "Scoring":
+        return self._clip(yclip_prefix=penalty)
+
+    def yclip_suffix_(self, penalty: int) -> "Scoring":
+        return self._clip(yclip_suffix=penalty)
+
+    # -- C ABI view --------------------------------------------------------------------------
+    def to_c(self, blob: Optional[np.ndarray] = None):
+        """-> (CScoring, keepalive). Closures are tabulated over the symbols present (mod.rs:221-228)."""
+        keep = []
+        cs = CScoring(self.gap_open, self.gap_extend, self.xclip_prefix, self.xclip_suffix,
+                      self.yclip_prefix, self.yclip_suffix, 0, 0, 0, None, None, 0)
+        if self.match_scores is not None:
+            cs.has_match_scores = 1
+        fn = self.match_fn
+        if isinstance(fn, MatchParams):
+            cs.match_score, cs.mismatch_score = fn.match_score, fn.mismatch_score
+            if self.match_scores is not None:
+                assert tuple(self.match_scores) == (fn.match_score, fn.mismatch_score)
+        else:
+            if getattr(fn, "matrix_name", None):
+                table = _scores.matrix_table256(fn.matrix_name)
+                alpha = np.frombuffer(_MATRIX_ALPHABET, dtype=np.uint8).copy()
+            else:
+                syms = np.unique(blob) if blob is not None and len(blob) else np.zeros(1, np.uint8)
+                table = _scores.tabulate(fn, syms.tolist())
+                alpha = syms.astype(np.uint8)
+            table = np.ascontiguousarray(table, dtype=np.int32)
+            keep += [table, alpha]
+            cs.table = table.ctypes.data_as(C.c_void_p)
+            cs.alphabet = alpha.ctypes.data_as(C.c_void_p)
+            cs.alphabet_len = len(alpha)
+            if self.match_scores is not None:
+                cs.match_score, cs.mismatch_score = self.match_scores
+        return cs, keep
+
+
+def _check_scoring(s: Scoring):
+    """Aligner::with_capacity_and_scoring asserts, mod.rs:554-571"""
+    assert s.gap_open <= 0, "gap_open can't be positive"
+    assert s.gap_extend <= 0, "gap_extend can't be positive"
+    assert s.xclip_prefix <= 0, "Clipping penalty (x prefix) can't be positive"
+    assert s.xclip_suffix <= 0, "Clipping penalty (x suffix) can't be positive"
+    assert s.yclip_prefix <= 0, "Clipping penalty (y prefix) can't be positive"
+    assert s.yclip_suffix <= 0, "Clipping penalty (y suffix) can't be positive"
+
+
+class Aligner:
+    """mod.rs:472-1015. Holds a Scoring and an engine handle instead of host scratch vectors."""
+
+    def __init__(self, scoring: Scoring, engine: Optional[Engine] = None):
+        self.scoring = scoring
+        self._engine = engine
+
+    # constructors, mod.rs:495-583 (capacities are hints there; here they are ignored)
+    @staticmethod
+    def new(gap_open: int, gap_extend: int, match_fn: MatchFunc, engine: Optional[Engine] = None) -> "Aligner":
+        return Aligner.with_capacity(DEFAULT_ALIGNER_CAPACITY, DEFAULT_ALIGNER_CAPACITY, gap_open,
+                                     gap_extend, match_fn, engine)
+
+    @staticmethod
+    def with_capacity(m: int, n: int, gap_open: int, gap_extend: int, match_fn: MatchFunc,
+                      engine: Optional[Engine] = None) -> "Aligner":
+        assert gap_open <= 0, "gap_open can't be positive"
+        assert gap_extend <= 0, "gap_extend can't be positive"
+        return Aligner(Scoring.new(gap_open, gap_extend, match_fn), engine)
+
+    @staticmethod
+    def with_scoring(scoring: Scoring, engine: Optional[Engine] = None) -> "Aligner":
+        return Aligner.with_capacity_and_scoring(DEFAULT_ALIGNER_CAPACITY, DEFAULT_ALIGNER_CAPACITY,
+                                                 scoring, engine)
+
+    @staticmethod
+    def with_capacity_and_scoring(m: int, n: int, scoring: Scoring, engine: Optional[Engine] = None) -> "Aligner":
+        _check_scoring(scoring)
+        return Aligner(scoring, engine)
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = default_engine(0)
+        return self._engine
+
+    # batch forms ------------------------------------------------------------------------------
+    def _batch(self, mode: int, pairs: Sequence[Tuple[bytes, bytes]]) -> List[Alignment]:
+        batch = pack_pairs(pairs)
+        cs, keep = self.scoring.to_c(batch[0])
+        res = self.engine.align_batch(mode, cs, batch)
+        out = []
+        for i, (x, y) in enumerate(pairs):
+            ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
+            out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]),
+                                 int(res.yend[i]), int(res.xend[i]), len(y), len(x), ops, mode))
+        return out
+
+    def custom_batch(self, pairs):
+        return self._batch(MODE_CUSTOM, pairs)
+
+    def global_batch(self, pairs):
+        return self._batch(MODE_GLOBAL, pairs)
+
+    def semiglobal_batch(self, pairs):
+        return self._batch(MODE_SEMIGLOBAL, pairs)
+
+    def local_batch(self, pairs):
+        return self._batch(MODE_LOCAL, pairs)
+
+    # per-pair forms, mod.rs:591, 925, 954, 986
+    def custom(self, x: bytes, y: bytes) -> Alignment:
+        return self._batch(MODE_CUSTOM, [(x, y)])[0]
+
+    def global_(self, x: bytes, y: bytes) -> Alignment:
+        return self._batch(MODE_GLOBAL, [(x, y)])[0]
+
+    def semiglobal(self, x: bytes, y: bytes) -> Alignment:
+        return self._batch(MODE_SEMIGLOBAL, [(x, y)])[0]
+
+    def local(self, x: bytes, y: bytes) -> Alignment:
+        return self._batch(MODE_LOCAL, [(x, y)])[0]
+
+
+setattr(Aligner, "global", Aligner.global_)  # reachable as getattr(aligner, "global")

@@ -76,13 +76,15 @@ struct sim_scoring {
   int32_t gap_open, gap_extend, xclip_prefix, xclip_suffix, yclip_prefix, yclip_suffix;
   int32_t match_score, mismatch_score, has_match_scores;
   const int32_t* table;
+  const uint8_t* alphabet;
+  uint32_t alphabet_len;
 };
 
 // Same outputs as the engine: per pair score/xstart/xend/ystart/yend/n_ops/clip_len[4]/status and
 // ops (m+n+4 bytes per pair at ops + ops_off[p], alignment order).
 int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
                     const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len,
-                    uint64_t n_pairs, int R, int force_general, int32_t* score, uint32_t* xstart,
+                    uint64_t n_pairs, int R, int force_general, int garbage, int32_t* score, uint32_t* xstart,
                     uint32_t* xend, uint32_t* ystart, uint32_t* yend, uint32_t* n_ops,
                     uint32_t* clip_len, uint32_t* status, uint8_t* ops, const uint64_t* ops_off) {
   DevScoring sc{};
@@ -120,8 +122,10 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   build_plan(p, x_len, y_len, n_pairs, 1, R, ~0ull);
   int flags = scoring_flags(sc);
   if (force_general) flags = (flags & F_LUT) | F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
-  std::vector<uint8_t> seq(p.seq_bytes, 0), bnd(p.max_bnd, 0xCD), rows(p.max_rows, 0xCD),
-      rowm(p.max_rowm, 0xCD), tb(p.max_tb, 0xCD), opsb(p.ops_bytes, 0);
+  // scratch starts as caller-chosen garbage: nothing may depend on its initial contents
+  const uint8_t gb = (uint8_t)garbage;
+  std::vector<uint8_t> seq(p.seq_bytes, 0), bnd(p.max_bnd, gb), rows(p.max_rows, gb),
+      rowm(p.max_rowm, gb), tb(p.max_tb, gb), opsb(p.ops_bytes, 0);
   // K0 equivalent: stage sequences as [task][word][pair] (G = 1: one task per block)
   for (const Block& blk : p.blocks) {
     uint32_t* seqw = reinterpret_cast<uint32_t*>(seq.data() + blk.seq_off);

@@ -18,7 +18,8 @@ class SimScoring(C.Structure):
     _fields_ = [("gap_open", C.c_int32), ("gap_extend", C.c_int32), ("xclip_prefix", C.c_int32),
                 ("xclip_suffix", C.c_int32), ("yclip_prefix", C.c_int32), ("yclip_suffix", C.c_int32),
                 ("match_score", C.c_int32), ("mismatch_score", C.c_int32),
-                ("has_match_scores", C.c_int32), ("table", C.POINTER(C.c_int32))]
+                ("has_match_scores", C.c_int32), ("table", C.POINTER(C.c_int32)),
+                ("alphabet", C.c_void_p), ("alphabet_len", C.c_uint32)]
 
 
 def build():
@@ -39,7 +40,7 @@ def lib():
     return _lib
 
 
-def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0):
+def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0, garbage=None):
     """Takes an oracle.OrcScoring (same layout). Returns dict of arrays + list of op lists."""
     s = SimScoring.from_buffer_copy(bytes(orc_scoring))
     blob = np.ascontiguousarray(blob, dtype=np.uint8)
@@ -55,8 +56,15 @@ def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force
     out["score"] = np.zeros(n, dtype=np.int32)
     out["clip_len"] = np.zeros(4 * n, dtype=np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
+    if garbage is None:  # run with two different scratch fills and insist on identical results
+        a = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x00)
+        b = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x7F)
+        for k in a[0]:
+            assert np.array_equal(a[0][k], b[0][k]), ("scratch-dependent result", k)
+        assert a[1] == b[1], "scratch-dependent ops"
+        return a
     rc = lib().sim_align_batch(int(mode), C.byref(s), p(blob), p(x_off), p(x_len), p(y_off), p(y_len),
-                               C.c_uint64(n), int(R), int(force_general), p(out["score"]),
+                               C.c_uint64(n), int(R), int(force_general), int(garbage), p(out["score"]),
                                p(out["xstart"]), p(out["xend"]), p(out["ystart"]), p(out["yend"]),
                                p(out["n_ops"]), p(out["clip_len"]), p(out["status"]), p(ops), p(ops_off))
     assert rc == 0

@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+Bit-exact on every Alignment field and on the operation vectors."""
+import numpy as np
+import pytest
+
+from golden_util import load_cases, parse_ops, scoring_fields
+from parity_util import MODES, assert_same, oracle_batch
+
+pytestmark = pytest.mark.gpu
+MIN = -858993459
+CASES = load_cases()
+SHAPES = [(1, 16), (1, 8), (4, 16), (8, 16), (32, 8), (32, 16)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rust_bio_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _mirror_scoring(sc):
+    from rust_bio_b200 import scores
+    from rust_bio_b200.pairwise import MatchParams, Scoring
+    f = scoring_fields(sc)
+    if f["matrix"]:
+        fn = getattr(scores, f["matrix"])
+        s = Scoring.new(f["gap_open"], f["gap_extend"], fn)
+    elif f["from_scores"]:
+        s = Scoring.from_scores(f["gap_open"], f["gap_extend"], f["match"], f["mismatch"])
+    else:
+        ma, mi = f["match"], f["mismatch"]
+        s = Scoring.new(f["gap_open"], f["gap_extend"], lambda a, b: ma if a == b else mi)
+    s.xclip_prefix, s.xclip_suffix = f["xclip_prefix"], f["xclip_suffix"]
+    s.yclip_prefix, s.yclip_suffix = f["yclip_prefix"], f["yclip_suffix"]
+    return s
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reference_known_answers_through_the_mirror(eng, case):
+    """Reads like the reference's tests (mod.rs:1203-1769): Aligner::with_scoring(..).<mode>(x, y)."""
+    from rust_bio_b200.pairwise import Aligner
+    aligner = Aligner.with_scoring(_mirror_scoring(case["scoring"]), engine=eng)
+    method = {"custom": aligner.custom, "global": aligner.global_, "semiglobal": aligner.semiglobal,
+              "local": aligner.local}[case["mode"]]
+    alignment = method(case["x"].encode(), case["y"].encode())
+    exp = case["expect"]
+    for k in ("score", "xstart", "xend", "ystart", "yend"):
+        if k in exp:
+            assert getattr(alignment, k) == exp[k], (case["name"], k, alignment)
+    if "ops" in exp:
+        assert [(o.code, o.len) for o in alignment.operations] == parse_ops(exp["ops"])
+    assert alignment.xlen == len(case["x"]) and alignment.ylen == len(case["y"])
+
+
+def _c_scoring(go, ge, ma, mi, clips=(MIN, MIN, MIN, MIN), table=None, alphabet=None):
+    import ctypes as C
+    from rust_bio_b200._lib import CScoring
+    cs = CScoring(go, ge, clips[0], clips[1], clips[2], clips[3], ma, mi, 0, None, None, 0)
+    keep = []
+    if table is not None:
+        t = np.ascontiguousarray(table, dtype=np.int32)
+        keep.append(t)
+        cs.table = t.ctypes.data_as(C.c_void_p)
+        if alphabet is not None:
+            a = np.frombuffer(alphabet, dtype=np.uint8).copy()
+            keep.append(a)
+            cs.alphabet = a.ctypes.data_as(C.c_void_p)
+            cs.alphabet_len = len(a)
+    return cs, keep
+
+
+def _engine_result(eng, mode, cs, batch):
+    res = eng.align_batch(MODES[mode], cs, batch)
+    got = res.as_dict()
+    ops = [res.ops_of(i) for i in range(res.n_pairs)]
+    return got, ops
+
+
+@pytest.mark.parametrize("G,R", SHAPES)
+def test_c1_1k_pairs_150x150_local_every_field(eng, oracle, G, R):
+    """BASELINE config 1: 1k pairs of 150x150 random DNA, local affine (1,-1,-5,-1), all fill shapes."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(synth.BASES["C1"], 0, 1000, 150, 150)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "local", s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    eng.set_tuning(G, R)
+    try:
+        got, ops = _engine_result(eng, "local", cs, batch)
+    finally:
+        eng.set_tuning(0, 0)
+    assert eng.stats.fill_lanes_per_pair == G and eng.stats.fill_rows_per_lane == R
+    assert_same(got, ops, ref, ref_ops, batch, f"C1 local G={G} R={R}")
+
+
+@pytest.mark.parametrize("G,R", SHAPES)
+@pytest.mark.parametrize("mode", ["local", "global", "semiglobal"])
+def test_ragged_presets(eng, oracle, mode, G, R):
+    from rust_bio_b200 import synth
+    batch = synth.ragged_pairs(40 + G, 500, 200, 260)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    eng.set_tuning(G, R)
+    try:
+        got, ops = _engine_result(eng, mode, cs, batch)
+    finally:
+        eng.set_tuning(0, 0)
+    assert_same(got, ops, ref, ref_ops, batch, f"ragged {mode} G={G} R={R}")
+
+
+@pytest.mark.parametrize("G,R", [(1, 16), (8, 16), (32, 8)])
+def test_tiny_and_empty_shapes(eng, oracle, G, R):
+    xs, ys = [], []
+    for m in range(0, 5):
+        for n in range(0, 5):
+            for rep in range(3):
+                xs.append(m)
+                ys.append(n)
+    rng = np.random.default_rng(5)
+    total = sum(xs) + sum(ys)
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 2, size=total + 1)]
+    lens = np.array([v for pair in zip(xs, ys) for v in pair], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    batch = (blob, offs[0::2].copy(), np.array(xs, dtype=np.uint32), offs[1::2].copy(),
+             np.array(ys, dtype=np.uint32))
+    eng.set_tuning(G, R)
+    try:
+        for mode in ("custom", "local", "global", "semiglobal"):
+            for clips in [(MIN, MIN, MIN, MIN), (0, 0, 0, 0), (-1, 0, MIN, -2), (0, MIN, MIN, 0)]:
+                s, _ = oracle.make_scoring(-2, -1, 2, -1, None, *clips)
+                ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+                cs, keep = _c_scoring(-2, -1, 2, -1, clips)
+                got, ops = _engine_result(eng, mode, cs, batch)
+                assert_same(got, ops, ref, ref_ops, batch, f"tiny {mode} {clips} G={G}")
+    finally:
+        eng.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_custom_clip_penalties(eng, oracle, seed):
+    from rust_bio_b200 import synth
+    rng = np.random.default_rng(100 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -1, -3, -7, -20]))
+    go, ge = int(rng.choice([0, -1, -2, -5, -6])), int(rng.choice([0, -1, -1, -2]))
+    ma, mi = int(rng.choice([1, 2, 4])), int(rng.choice([-1, -3, -7, 0]))
+    clips = (pick(), pick(), pick(), pick())
+    s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips)
+    batch = synth.ragged_pairs(seed, 300, 90, 110, alphabet=b"AC" if seed % 2 else b"ACGT")
+    ref, ref_ops = oracle_batch(oracle, "custom", s, batch, threads=8)
+    cs, keep = _c_scoring(go, ge, ma, mi, clips)
+    for G, R in [(1, 16), (8, 16), (32, 8)]:
+        eng.set_tuning(G, R)
+        try:
+            got, ops = _engine_result(eng, "custom", cs, batch)
+        finally:
+            eng.set_tuning(0, 0)
+        assert_same(got, ops, ref, ref_ops, batch, f"custom seed={seed} clips={clips} G={G}")
+
+
+@pytest.mark.parametrize("G,R", [(1, 16), (8, 16), (32, 8)])
+def test_blosum62_protein_lut_path(eng, oracle, G, R):
+    from rust_bio_b200 import scores, synth
+    table = scores.matrix_table256("blosum62")
+    alpha = bytes(range(65, 91)) + b"*"
+    batch = synth.ragged_pairs(3, 300, 180, 170, alphabet=synth.PROTEIN, min_len=1)
+    eng.set_tuning(G, R)
+    try:
+        for mode, go in (("local", -10), ("global", -5), ("semiglobal", -11)):
+            s, keep1 = oracle.make_scoring(go, -1, 0, 0, table)
+            ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)
+            cs, keep2 = _c_scoring(go, -1, 0, 0, table=table, alphabet=alpha)
+            got, ops = _engine_result(eng, mode, cs, batch)
+            assert_same(got, ops, ref, ref_ops, batch, f"blosum62 {mode} G={G}")
+    finally:
+        eng.set_tuning(0, 0)
+
+
+def test_c3_shape_global_1000x1000_sample(eng, oracle):
+    """BASELINE config 3 shape (global 1000x1000), a 96-pair sample, warp-per-pair and 8-lane shapes."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(synth.BASES["C3"], 0, 96, 1000, 1000)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "global", s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    for G, R in [(32, 8), (8, 16), (1, 16)]:
+        eng.set_tuning(G, R)
+        try:
+            got, ops = _engine_result(eng, "global", cs, batch)
+        finally:
+            eng.set_tuning(0, 0)
+        assert_same(got, ops, ref, ref_ops, batch, f"C3 global G={G}")
+
+
+def test_waves_give_identical_results(eng, oracle):
+    """A traceback budget that forces several waves must not change any result."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(synth.BASES["C1"] + 77, 0, 2000, 150, 150)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    got1, ops1 = _engine_result(eng, "local", cs, batch)
+    assert eng.stats.waves == 1
+    eng.set_traceback_budget(3 << 20)
+    try:
+        got2, ops2 = _engine_result(eng, "local", cs, batch)
+        assert eng.stats.waves > 1
+    finally:
+        eng.set_traceback_budget(0)
+    for k in got1:
+        assert np.array_equal(got1[k], got2[k])
+    assert ops1 == ops2
+
+
+def test_full_size_c2_properties(eng, oracle):
+    """BASELINE config 2 at full size (1M pairs): size-independent properties + sampled oracle parity.
+    - every returned path re-scores to the returned score (4.0 gap model, mod.rs:9-15);
+    - coordinates are consistent with the ops; scores are >= 0 (local);
+    - the first 2,000 and 2,000 random pairs are bit-exact against the oracle."""
+    from rust_bio_b200 import synth
+    n = 1_000_000
+    batch = synth.uniform_pairs(synth.BASES["C2"], 0, n, 150, 150)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    res = eng.align_batch(MODES["local"], cs, batch)
+    blob, xo, xl, yo, yl = batch
+    assert int(res.score.min()) >= 0
+    ops_off = res.ops_off.astype(np.int64)
+    codes = res.ops[:ops_off[-1]]
+    assert codes.max() <= 3  # clips are filtered in local mode (mod.rs:1006)
+    # vectorised consistency: #ops consuming x == xend-xstart, consuming y == yend-ystart
+    cons_x = np.add.reduceat(np.concatenate([(codes != 2).astype(np.int64), [0]]), np.minimum(ops_off[:-1], len(codes)))
+    cons_y = np.add.reduceat(np.concatenate([(codes != 3).astype(np.int64), [0]]), np.minimum(ops_off[:-1], len(codes)))
+    nops = np.diff(ops_off)
+    cons_x = np.where(nops > 0, cons_x, 0)
+    cons_y = np.where(nops > 0, cons_y, 0)
+    assert np.array_equal(cons_x, res.xend.astype(np.int64) - res.xstart)
+    assert np.array_equal(cons_y, res.yend.astype(np.int64) - res.ystart)
+    rng = np.random.default_rng(1)
+    idx = np.unique(np.concatenate([np.arange(2000), rng.integers(0, n, size=2000)]))
+    # re-score sampled paths
+    for p in idx[::8]:
+        i, j = int(res.xstart[p]), int(res.ystart[p])
+        x = blob[int(xo[p]):int(xo[p]) + 150]
+        y = blob[int(yo[p]):int(yo[p]) + 150]
+        score, last = 0, None
+        for c, _ in res.ops_of(int(p)):
+            if c in (0, 1):
+                assert (x[i] == y[j]) == (c == 0)
+                score += 1 if c == 0 else -1
+                i += 1
+                j += 1
+            elif c == 2:
+                score += -1 if last == 2 else -5
+                j += 1
+            else:
+                score += -1 if last == 3 else -5
+                i += 1
+            last = c
+        assert (i, j) == (int(res.xend[p]), int(res.yend[p]))
+        assert score == int(res.score[p])
+    sub = (blob, xo[idx], xl[idx], yo[idx], yl[idx])
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "local", s, sub, threads=8)
+    got = {k: v[idx] for k, v in res.as_dict().items()}
+    assert_same(got, [res.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "C2 sample")
+
+
+def test_error_paths(eng):
+    """Bad parameters are refused like the reference's assert!s; out-of-alphabet bytes are an error."""
+    from rust_bio_b200 import scores, synth
+    from rust_bio_b200._lib import B2AError
+    batch = synth.uniform_pairs(1, 0, 4, 20, 20)
+    cs, _ = _c_scoring(1, -1, 1, -1)
+    with pytest.raises(B2AError, match="gap_open can't be positive"):
+        eng.align_batch(MODES["local"], cs, batch)
+    cs, _ = _c_scoring(-1, -1, 1, -1, clips=(1, 0, 0, 0))
+    with pytest.raises(B2AError, match="x prefix"):
+        eng.align_batch(MODES["custom"], cs, batch)
+    table = scores.matrix_table256("blosum62")
+    bad = (np.full(64, ord("a"), dtype=np.uint8), batch[1][:1] * 0, batch[2][:1], batch[1][:1] * 0 + 32, batch[4][:1])
+    cs, keep = _c_scoring(-5, -1, 0, 0, table=table, alphabet=bytes(range(65, 91)) + b"*")
+    with pytest.raises(B2AError, match="alphabet"):
+        eng.align_batch(MODES["local"], cs, bad)
+    cs, _ = _c_scoring(-5, -1, 1 << 20, -1)
+    with pytest.raises(B2AError, match="RANGE"):
+        eng.align_batch(MODES["local"], cs, synth.uniform_pairs(1, 0, 4, 2000, 2000))

@@ -202,7 +202,11 @@ def main():
     results = Results(P, ops_cap, out=views)
 
     eng = Engine(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-legacy-default) torch stream: the engine launches on it, torch.cuda.Event times it,
+    # and NCCL collectives issued under torch.cuda.stream(stream) are ordered on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
     cs = CScoring(SCORING["gap_open"], SCORING["gap_extend"], MIN_SCORE, MIN_SCORE, MIN_SCORE, MIN_SCORE,
                   SCORING["match"], SCORING["mismatch"], 1, None, None, 0)

@@ -33,11 +33,12 @@ enum : uint32_t {
 };
 
 // Compressed interior traceback nibble (rows 1..m-1, columns 1..n):
-//   bits 1:0  S source: 0 diagonal (Match/Subst by byte equality), 1 Ins, 2 Del,
-//             3 x-prefix clip (the only other move that can win there)
+//   bits 1:0  S source = the priority code the fill's packed max carries:
+//             3 diagonal (Match/Subst by byte equality), 2 Ins, 1 Del,
+//             0 x-prefix clip (the only other move that can win there)
 //   bit  2    I came from extension (else from S of the cell above)
 //   bit  3    D came from extension (else from S of the cell to the left)
-enum : uint32_t { NB_DIAG = 0, NB_INS = 1, NB_DEL = 2, NB_CLIP = 3, NB_IEXT = 4, NB_DEXT = 8 };
+enum : uint32_t { NB_DIAG = 3, NB_INS = 2, NB_DEL = 1, NB_CLIP = 0, NB_IEXT = 4, NB_DEXT = 8 };
 
 // Kernel specialisation flags
 enum : int {
@@ -45,6 +46,7 @@ enum : int {
   F_TRACK_COLS = 2,  // xclip_suffix live: per-column (S[curr][m], Lx) arg-max over rows (mod.rs:793-796)
   F_CLIPX = 4,       // xclip_prefix and yclip_prefix live: xclip_score term (mod.rs:724-728,775-778)
   F_LUT = 8,         // substitution scores from a compact LUT in shared memory (else MatchParams)
+  F_PACKTRK = 16,    // trackers as packed keys 4096*value + (4095-index): needs m,n <= 4095, |S| < 2^17
 };
 
 struct DevScoring {

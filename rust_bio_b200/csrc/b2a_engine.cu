@@ -260,51 +260,67 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   }
   if (maxm > (1u << 24) || maxn > (1u << 24)) return e->fail(B2A_E_RANGE, "sequence longer than 2^24");
 
-  // substitution scores: MatchParams, or a compact LUT over the alphabet
+  // The alphabet: given by the caller, else found on the device (one flat pass over the blob).
+  // Both MatchParams and tabulated MatchFuncs then run from a compact LUT in shared memory;
+  // MatchParams over more than 64 distinct bytes falls back to compare/select in the kernel.
+  cudaStream_t st = e->stream;
+  e->blob_bytes = pairs->blob_bytes;
+  e->h2d_bytes = 0;
+  auto up = [&](DevBuf& bf, const void* src, size_t bytes) -> cudaError_t {
+    e->h2d_bytes += bytes;
+    return bytes ? cudaMemcpyAsync(bf.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  CK(e->d_blob.reserve(pairs->blob_bytes + 16));
+  CK(e->d_ctl.reserve(2048));
+  CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
+  bool present[256] = {false};
+  if (s->table && s->alphabet && s->alphabet_len) {
+    for (uint32_t k = 0; k < s->alphabet_len; ++k) present[s->alphabet[k]] = true;
+  } else {
+    uint32_t* flags = e->d_ctl.as<uint32_t>() + 256;  // 256 words
+    CK(cudaMemsetAsync(flags, 0, 1024, st));
+    if (pairs->blob_bytes) {
+      symbols_kernel<<<e->num_sms * 8, 256, 0, st>>>(e->d_blob.as<uint8_t>(), pairs->blob_bytes, flags);
+      CK(cudaGetLastError());
+    }
+    uint32_t hflags[256];
+    CK(cudaMemcpyAsync(hflags, flags, 1024, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 256; ++k) present[k] = hflags[k] != 0;
+  }
+  std::vector<int> syms;
+  for (int k = 0; k < 256; ++k)
+    if (present[k]) syms.push_back(k);
+  if (syms.empty()) syms.push_back(0);
   int64_t maxabs = std::max<int64_t>(std::llabs((long long)s->match_score), std::llabs((long long)s->mismatch_score));
   for (int k = 0; k < 256; ++k) e->codemap_host[k] = (uint8_t)k;
   e->lut_host.clear();
-  if (s->table) {
-    bool present[256] = {false};
-    if (s->alphabet && s->alphabet_len) {
-      for (uint32_t k = 0; k < s->alphabet_len; ++k) present[s->alphabet[k]] = true;
-    } else {
-      for (uint64_t p = 0; p < n; ++p) {
-        const uint8_t* x = pairs->seq_blob + pairs->x_off[p];
-        const uint8_t* y = pairs->seq_blob + pairs->y_off[p];
-        for (uint32_t k = 0; k < pairs->x_len[p]; ++k) present[x[k]] = true;
-        for (uint32_t k = 0; k < pairs->y_len[p]; ++k) present[y[k]] = true;
-      }
-    }
-    std::vector<int> syms;
-    for (int k = 0; k < 256; ++k) {
-      e->codemap_host[k] = 0xFF;
-      if (present[k]) {
-        e->codemap_host[k] = (uint8_t)syms.size();
-        syms.push_back(k);
-      }
-    }
-    if (syms.empty()) {
-      syms.push_back(0);
-      e->codemap_host[0] = 0;
-    }
-    if ((int)syms.size() > kMaxAlpha)
-      return e->fail(B2A_E_UNSUPPORTED, "MatchFunc table over more than 64 distinct symbols");
+  if (s->table && (int)syms.size() > kMaxAlpha)
+    return e->fail(B2A_E_UNSUPPORTED, "MatchFunc table over more than 64 distinct symbols");
+  if ((int)syms.size() <= kMaxAlpha) {
     sc.alpha = (int32_t)syms.size();
-    e->lut_host.resize((size_t)sc.alpha * sc.alpha);
-    maxabs = 0;
+    for (int k = 0; k < 256; ++k) e->codemap_host[k] = 0xFF;
+    for (int a = 0; a < sc.alpha; ++a) e->codemap_host[syms[a]] = (uint8_t)a;
+    const size_t aa = (size_t)sc.alpha * sc.alpha;
+    e->lut_host.resize(2 * aa);  // [plain | 4*v+3 for K1's packed domain]
+    if (s->table) maxabs = 0;
     for (int a = 0; a < sc.alpha; ++a)
       for (int b = 0; b < sc.alpha; ++b) {
-        const int32_t v = s->table[syms[a] * 256 + syms[b]];
+        const int32_t v = s->table ? s->table[syms[a] * 256 + syms[b]]
+                                   : (a == b ? s->match_score : s->mismatch_score);
         e->lut_host[(size_t)a * sc.alpha + b] = v;
         maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
       }
+    if (maxabs > (1ll << 27)) return e->fail(B2A_E_RANGE, "substitution score magnitude above 2^27");
+    for (size_t k = 0; k < aa; ++k) e->lut_host[aa + k] = 4 * e->lut_host[k] + 3;
   }
+  int64_t score_bound = 0;
   // i32 range guard: every S/I/D of a real path stays within +-2^27, so MIN_SCORE-based
   // sentinels can neither win nor overflow (the reference would silently wrap)
   {
     const int64_t unit = std::max<int64_t>(maxabs, std::max<int64_t>(-(int64_t)sc.gap_open, -(int64_t)sc.gap_extend));
     const int64_t bound = ((int64_t)maxm + maxn + 2) * unit - (int64_t)sc.gap_open;
+    score_bound = bound;
     if (bound > (1ll << 27)) return e->fail(B2A_E_RANGE, "scores x lengths exceed the i32-safe range (2^27)");
     const int32_t clips[4] = {sc.xclip_prefix, sc.xclip_suffix, sc.yclip_prefix, sc.yclip_suffix};
     for (int32_t c : clips)
@@ -312,7 +328,7 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
         return e->fail(B2A_E_RANGE, "clip penalty between -2^27 and MIN_SCORE/2 is not supported");
   }
   e->sc = sc;
-  e->flags = scoring_flags(sc);
+  e->flags = scoring_flags(sc, score_bound, maxm, maxn);
 
   // shape + plan
   int G = 1, R = 16;
@@ -332,8 +348,6 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
     return e->fail(B2A_E_UNSUPPORTED, "sequences too long for on-chip staging with this fill shape");
 
   // device memory
-  e->blob_bytes = pairs->blob_bytes;
-  CK(e->d_blob.reserve(pairs->blob_bytes + 16));
   CK(e->d_xoff.reserve(n * 8 + 8));
   CK(e->d_yoff.reserve(n * 8 + 8));
   CK(e->d_xlen.reserve(n * 4 + 4));
@@ -350,7 +364,6 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   CK(e->d_opsscratch.reserve(pl.ops_bytes + 16));
   CK(e->d_lut.reserve(e->lut_host.size() * 4 + 16));
   CK(e->d_codemap.reserve(256));
-  CK(e->d_ctl.reserve(256));
   CK(e->d_score.reserve(n * 4 + 4));
   CK(e->d_xs.reserve(n * 4 + 4));
   CK(e->d_xe.reserve(n * 4 + 4));
@@ -364,13 +377,6 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   CK(e->d_opsoff.reserve((n + 1) * 8));
 
   // host -> device
-  cudaStream_t st = e->stream;
-  e->h2d_bytes = 0;
-  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
-    e->h2d_bytes += bytes;
-    return bytes ? cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
-  };
-  CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
   CK(up(e->d_xoff, pairs->x_off, n * 8));
   CK(up(e->d_yoff, pairs->y_off, n * 8));
   CK(up(e->d_xlen, pairs->x_len, n * 4));
@@ -432,7 +438,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     fp.bnd = e->d_bnd.as<uint8_t>();
     fp.rows = e->d_rows.as<uint8_t>();
     fp.tb = e->d_tb.as<uint8_t>();
-    fp.lut = e->d_lut.as<int32_t>();
+    fp.lut = e->d_lut.as<int32_t>() + (size_t)e->sc.alpha * e->sc.alpha;  // the scaled copy
     fp.task_counter = ctl + 2 + wi;
     fp.smem_seq_bytes = pl.smem_seq_bytes;
     fp.sc = e->sc;
@@ -458,7 +464,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     wp.rowm = e->d_rowm.as<uint8_t>();
     wp.tb = fp.tb;
     wp.ops_scratch = e->d_opsscratch.as<uint8_t>();
-    wp.lut = fp.lut;
+    wp.lut = e->d_lut.as<int32_t>();  // the unscaled copy
     wp.sc = e->sc;
     wp.G = pl.G;
     wp.R = pl.R;

@@ -34,7 +34,7 @@ struct FillParams {
   uint8_t* bnd;
   uint8_t* rows;
   uint8_t* tb;
-  const int32_t* lut;  // alpha*alpha (global) or null
+  const int32_t* lut;  // scaled LUT 4*score+3, alpha*alpha (global) or null
   uint32_t* task_counter;
   uint32_t smem_seq_bytes;  // per-warp staging bytes
   DevScoring sc;
@@ -68,6 +68,30 @@ struct LaneCtx {
 #define B2A_SHFL_UP(v, G) (v)
 #endif
 
+// ---- scaled/packed score domain of the fill ------------------------------------------------
+// Inside K1 every score is carried as 4*value + a 2-bit priority code in the low bits:
+//   S4 = 4*S (clean), M4 = 4*M + 3, I4 = 4*I + 2, D4 = 4*D + 1, X4 = 4*xclip_score + 0.
+// One 3-way integer max of (M4, I4, D4) [then max with X4] yields the new S *and* which source won,
+// with exactly the reference's tie order M > I > D > x-prefix-clip (mod.rs:757-778: each later
+// candidate must be strictly greater).  The I/D "came from extension" flags are min(I4 - open, 4):
+// 0 when the open candidate won or tied (mod.rs:738-744, 749-755), 4 otherwise.
+// The engine only uses K1 when every real score fits in +-2^27, so 4x fits in i32.
+constexpr int32_t NEG4 = -(1 << 30);  // "-infinity" in the scaled domain
+
+B2A_HD int32_t max3(int32_t a, int32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __vimax3_s32(a, b, c);
+#else
+  return imax(a, imax(b, c));
+#endif
+}
+B2A_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+// 4*v, except that dead (MIN_SCORE-like) penalties map to NEG4 instead of overflowing
+B2A_HD int32_t scale4(int32_t v) { return v <= DEAD_CLIP ? NEG4 : 4 * v; }
+
+// packed arg-max keys (F_PACKTRK): 4096*value + (4095 - index): max() keeps the first index on ties
+constexpr int32_t KEY_NONE = (int32_t)0x80000000;
+
 template <int G, int R, int FLAGS, bool MASKED, bool LAST>
 B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, const int32_t rowbase,
                         const int32_t rv, int32_t (&Sp)[R], int32_t (&Dp)[R], int32_t (&SnR)[R],
@@ -78,66 +102,76 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool CX = (FLAGS & F_CLIPX) != 0;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
-  const int32_t go = c.sc.gap_open, ge = c.sc.gap_extend;
-  const int32_t xcs = CX ? xclip_score(c.sc, j) : 0;
+  constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
+  const int32_t go4i = 4 * c.sc.gap_open + 2, go4d = 4 * c.sc.gap_open + 1, ge4 = 4 * c.sc.gap_extend;
+  const int32_t ma4 = 4 * c.sc.match_score + 3, mi4 = 4 * c.sc.mismatch_score + 3;
+  const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
+  const int32_t xs4 = scale4(c.sc.xclip_suffix), ys4 = scale4(c.sc.yclip_suffix);
+  const int32_t cj = 4095 - j;  // packed row-tracker index field
+  int32_t Tl = KEY_NONE;        // packed column tracker of this lane's rows (local row index)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int32_t sub;
+    int32_t sub4;
     if (LUT) {
-      sub = c.lut[xc[r] + q];
+      sub4 = c.lut[xc[r] + q];
     } else {
-      sub = (xc[r] == q) ? c.sc.match_score : c.sc.mismatch_score;
+      sub4 = (xc[r] == q) ? ma4 : mi4;
     }
-    const int32_t mval = sdiag + sub;
-    const int32_t iop = sup + go;
-    const int32_t iex = iup + ge;
-    const int32_t ival = imax(iex, iop);
-    uint32_t nib = (iex > iop) ? (uint32_t)NB_IEXT : 0u;
-    const int32_t dop = Sp[r] + go;
-    const int32_t dex = Dp[r] + ge;
-    const int32_t dval = imax(dex, dop);
-    nib |= (dex > dop) ? (uint32_t)NB_DEXT : 0u;
-    const int32_t gapbest = imax(ival, dval);
-    int32_t s = imax(mval, gapbest);
-    uint32_t code = (mval >= gapbest) ? (uint32_t)NB_DIAG
-                                      : ((ival >= dval) ? (uint32_t)NB_INS : (uint32_t)NB_DEL);
-    if (CX) {
-      code = (xcs > s) ? (uint32_t)NB_CLIP : code;
-      s = imax(s, xcs);
-    }
-    nib |= code;
-    tbacc[r] = (tbacc[r] << 4) | nib;
+    const int32_t m4 = sdiag + sub4;
+    const int32_t iop = sup + go4i;
+    const int32_t i4 = imax(iup + ge4, iop);
+    const int32_t dop = Sp[r] + go4d;
+    const int32_t d4 = imax(Dp[r] + ge4, dop);
+    int32_t sP = max3(m4, i4, d4);
+    if (CX) sP = imax(sP, x4);
+    const int32_t s4 = sP & ~3;
+    // nibble = code | iext << 2 | dext << 3
+    const uint32_t nib = (uint32_t)((sP - s4) + imin(i4 - iop, 4) + 2 * imin(d4 - dop, 4));
+    tbacc[r] = tbacc[r] * 16u + nib;
     if (TC) {
-      const int32_t v = s + c.sc.xclip_suffix;
-      if ((!MASKED || r < rv) && v > Tv) {
-        Tv = v;
-        Ti = rowbase + 1 + r;
+      if (PK) {
+        const int32_t key = s4 * 1024 + (4095 - r);
+        if (!MASKED || r < rv) Tl = imax(Tl, key);
+      } else {
+        const int32_t v = s4 + xs4;
+        if ((!MASKED || r < rv) && v > Tv) {
+          Tv = v;
+          Ti = rowbase + 1 + r;
+        }
       }
     }
     if (TR) {
-      const int32_t v = s + c.sc.yclip_suffix;
-      if (v > SnR[r]) {
-        SnR[r] = v;
-        LyR[r] = j;
+      if (PK) {
+        SnR[r] = imax(SnR[r], s4 * 1024 + cj);
+      } else {
+        const int32_t v = s4 + ys4;
+        if (v > SnR[r]) {
+          SnR[r] = v;
+          LyR[r] = j;
+        }
       }
     }
     if (LAST) {
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
-      c.rows[ROWS_SL * c.rows_pad * 32 + slot] = s;
-      c.rows[ROWS_IL * c.rows_pad * 32 + slot] = ival;
+      c.rows[ROWS_SL * c.rows_pad * 32 + slot] = s4 >> 2;
+      c.rows[ROWS_IL * c.rows_pad * 32 + slot] = i4 >> 2;
       c.rows[ROWS_NL * c.rows_pad * 32 + slot] = (int32_t)nib;
     }
     if (MASKED) {
       if (r == rv - 1) {
-        cap_s = s;
-        cap_i = ival;
+        cap_s = s4;
+        cap_i = i4;
       }
     }
     sdiag = Sp[r];
-    Sp[r] = s;
-    Dp[r] = dval;
-    sup = s;
-    iup = ival;
+    Sp[r] = s4;
+    Dp[r] = d4;
+    sup = s4;
+    iup = i4;
+  }
+  if (TC && PK) {
+    // local row index -> global: (4095 - r) - (rowbase + 1) = 4095 - i ; Tv carries the packed key
+    if (Tl != KEY_NONE) Tv = imax(Tv, Tl - (rowbase + 1));
   }
 }
 
@@ -147,6 +181,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
+  constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
   constexpr int P = 32 / G;
   constexpr int TBW = tbw_of(R);
   const int32_t m = c.m, n = c.n;
@@ -154,6 +189,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   // valid rows of this lane: rows <= m-1
   int32_t rv = m - 1 - rowbase;
   rv = rv < 0 ? 0 : (rv > R ? R : rv);
+  const int32_t xs = c.sc.xclip_suffix, ys = c.sc.yclip_suffix;
 
   int32_t Sp[R], Dp[R], SnR[R], LyR[R], xc[R];
   uint32_t tbacc[R];
@@ -171,26 +207,30 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   for (int r = 0; r < R; ++r) {
     const int32_t i = rowbase + 1 + r;
     const int32_t s0 = col0_S(c.sc, i);
-    Sp[r] = s0;
-    Dp[r] = MIN_SCORE;
+    Sp[r] = 4 * s0;
+    Dp[r] = NEG4;
     tbacc[r] = 0;
-    if (TR) {  // mod.rs:667-670
-      const int32_t v = s0 + c.sc.yclip_suffix;
-      SnR[r] = v > MIN_SCORE ? v : MIN_SCORE;
-      LyR[r] = 0;
+    LyR[r] = 0;
+    if (TR) {  // mod.rs:667-670 (column 0 is index 0)
+      if (PK) {
+        SnR[r] = s0 * 4096 + 4095;
+      } else {
+        const int32_t v = s0 + ys;
+        SnR[r] = (ys > DEAD_CLIP && v > MIN_SCORE) ? 4 * v : NEG4;
+      }
     } else {
       SnR[r] = 0;
-      LyR[r] = 0;
     }
   }
-  // S of the row above my first row, in column 0 (the first diagonal input)
-  int32_t sup_prev = rowbase == 0 ? 0 : col0_S(c.sc, rowbase);
-  // values arriving from above for my next column
-  int32_t in_s = 0, in_i = MIN_SCORE, in_tv = MIN_SCORE, in_ti = m;
+  // S of the row above my first row, in column 0 (the first diagonal input), scaled
+  int32_t sup_prev = rowbase == 0 ? 0 : 4 * col0_S(c.sc, rowbase);
+  // values arriving from above for my next column (scaled domain; tracker as key or as (4*T, index))
+  const int32_t t_none = PK ? KEY_NONE : NEG4;
+  int32_t in_s = 0, in_i = NEG4, in_tv = t_none, in_ti = m;
   int4 pre = make_int4(0, 0, 0, 0);
   const bool top_from_mem = (c.l == 0) && (s > 0);
   const bool top_from_row0 = (c.l == 0) && (s == 0);
-  if (top_from_mem) pre = c.bnd[1 * 32 + c.pi];  // column 1 (n >= 1 or garbage-but-unused)
+  if (top_from_mem && c.maxn >= 1) pre = c.bnd[1 * 32 + c.pi];
   const bool writer =
       MASKED ? (rv >= 1 && (c.l == G - 1 || rowbase + R >= m - 1)) : (c.l == G - 1);
   int32_t cap_s = 0, cap_i = 0;
@@ -213,15 +253,21 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         q = (int32_t)((c.ys[(jb >> 2) * P + c.g] >> (8 * (jb & 3))) & 0xffu);
       }
       if (top_from_row0) {
-        in_s = row0_S(c.sc, j, n);
-        in_i = MIN_SCORE;
-        in_tv = MIN_SCORE;
+        in_s = 4 * row0_S(c.sc, j, n);
+        in_i = NEG4;
+        in_tv = t_none;
         in_ti = m;
       } else if (top_from_mem) {
-        in_s = pre.x;
-        in_i = pre.y;
-        in_tv = pre.z;
-        in_ti = pre.w;
+        in_s = 4 * pre.x;
+        in_i = 4 * pre.y + 2;
+        if (TC) {
+          if (PK) {
+            in_tv = (pre.z == MIN_SCORE) ? KEY_NONE : (pre.z - xs) * 4096 + (4095 - pre.w);
+          } else {
+            in_tv = (pre.z == MIN_SCORE) ? NEG4 : 4 * pre.z;
+            in_ti = pre.w;
+          }
+        }
         if (j < c.maxn) pre = c.bnd[(j + 1) * 32 + c.pi];  // prefetch next column's boundary
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
@@ -235,10 +281,21 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       sup_prev = in_s;
       if (writer) {
         int4 o;
-        o.x = MASKED ? cap_s : sup;
-        o.y = MASKED ? cap_i : iup;
-        o.z = TC ? Tv : MIN_SCORE;
-        o.w = TC ? Ti : m;
+        o.x = (MASKED ? cap_s : sup) >> 2;
+        o.y = (MASKED ? cap_i : iup) >> 2;
+        o.z = MIN_SCORE;
+        o.w = m;
+        if (TC) {
+          if (PK) {
+            if (Tv != KEY_NONE) {
+              o.z = (Tv >> 12) + xs;
+              o.w = 4095 - (Tv & 4095);
+            }
+          } else if (Tv > NEG4 / 2) {
+            o.z = Tv >> 2;
+            o.w = Ti;
+          }
+        }
         c.bnd[j * 32 + c.pi] = o;
       }
       in_s = sup;
@@ -254,7 +311,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       in_i = B2A_SHFL_UP(in_i, G);
       if (TC) {
         in_tv = B2A_SHFL_UP(in_tv, G);
-        in_ti = B2A_SHFL_UP(in_ti, G);
+        if (!PK) in_ti = B2A_SHFL_UP(in_ti, G);
       }
     }
     if ((t & 7) == 7) {
@@ -276,8 +333,16 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
-      c.rows[ROWS_SN * c.rows_pad * 32 + slot] = SnR[r];
-      c.rows[ROWS_LY * c.rows_pad * 32 + slot] = LyR[r];
+      int32_t sn, ly;
+      if (PK) {
+        sn = (SnR[r] >> 12) + ys;
+        ly = 4095 - (SnR[r] & 4095);
+      } else {
+        sn = (SnR[r] <= NEG4 / 2) ? MIN_SCORE : (SnR[r] >> 2);
+        ly = LyR[r];
+      }
+      c.rows[ROWS_SN * c.rows_pad * 32 + slot] = sn;
+      c.rows[ROWS_LY * c.rows_pad * 32 + slot] = ly;
     }
   }
 }

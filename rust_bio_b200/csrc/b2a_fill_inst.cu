@@ -40,13 +40,19 @@ cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t
 cudaError_t B2A_CAT(launch_fill_, B2A_G, B2A_R)(int flags, const FillParams& prm, uint32_t ntasks,
                                                 int num_sms, cudaStream_t stream, int* grid_out) {
   constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+#define B2A_CASE(F) \
+  case (F): return go<(F)>(prm, ntasks, num_sms, stream, grid_out);
   switch (flags) {
-    case 0: return go<0>(prm, ntasks, num_sms, stream, grid_out);
-    case F_TRACK_ROWS: return go<F_TRACK_ROWS>(prm, ntasks, num_sms, stream, grid_out);
-    case ALL: return go<ALL>(prm, ntasks, num_sms, stream, grid_out);
-    case F_LUT: return go<F_LUT>(prm, ntasks, num_sms, stream, grid_out);
-    case F_LUT | F_TRACK_ROWS: return go<F_LUT | F_TRACK_ROWS>(prm, ntasks, num_sms, stream, grid_out);
-    case F_LUT | ALL: return go<F_LUT | ALL>(prm, ntasks, num_sms, stream, grid_out);
+    B2A_CASE(0)
+    B2A_CASE(F_TRACK_ROWS)
+    B2A_CASE(F_TRACK_ROWS | F_PACKTRK)
+    B2A_CASE(ALL)
+    B2A_CASE(ALL | F_PACKTRK)
+    B2A_CASE(F_LUT)
+    B2A_CASE(F_LUT | F_TRACK_ROWS)
+    B2A_CASE(F_LUT | F_TRACK_ROWS | F_PACKTRK)
+    B2A_CASE(F_LUT | ALL)
+    B2A_CASE(F_LUT | ALL | F_PACKTRK)
     default: return cudaErrorInvalidValue;
   }
 }

@@ -45,15 +45,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
       for (int b = 0; b < 4; ++b) {
         const uint32_t pos = w * 4 + b;
         if (pos < len) {
-          const uint32_t code = prm.codemap[prm.blob[off + pos]];
-          if (code == 0xFFu) *prm.bad_symbol = 1u;
-          val |= (code & 0xFFu) << (8 * b);
+          uint32_t code = prm.codemap[prm.blob[off + pos]];
+          if (code == 0xFFu) {  // outside the scoring alphabet: flag it, stage a valid code
+            *prm.bad_symbol = 1u;
+            code = 0;
+          }
+          val |= code << (8 * b);
         }
       }
     }
     const uint32_t sub = pair / P, p = pair % P;
     out[(isy ? (size_t)G * blk.xwords * P : 0) + ((size_t)sub * words + w) * P + p] = val;
   }
+}
+
+// which byte values occur in the blob (flags[v] != 0): decides the scoring alphabet
+__global__ void __launch_bounds__(256) symbols_kernel(const uint8_t* __restrict__ blob, uint64_t n,
+                                                      uint32_t* __restrict__ flags) {
+  __shared__ uint32_t seen[256];
+  seen[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) seen[blob[i]] = 1u;
+  __syncthreads();
+  if (seen[threadIdx.x]) flags[threadIdx.x] = 1u;
 }
 
 // ops compaction: pair p's ops move from the walk scratch to ops_dense[ops_off[p] ..].

@@ -124,7 +124,9 @@ inline void build_plan(Plan& p, const uint32_t* x_len, const uint32_t* y_len, ui
 }
 
 // Kernel flags for a scoring (SURVEY 3.2 "derived mode specialisations").
-inline int scoring_flags(const DevScoring& sc) {
+// `score_bound` = (maxm+maxn+2)*max|score, go, ge| + |go|: every real S/I/D lies within +-score_bound.
+inline int scoring_flags(const DevScoring& sc, int64_t score_bound = (1ll << 40), uint32_t maxm = ~0u,
+                         uint32_t maxn = ~0u) {
   const bool xp = sc.xclip_prefix > DEAD_CLIP, xs = sc.xclip_suffix > DEAD_CLIP;
   const bool yp = sc.yclip_prefix > DEAD_CLIP, ys = sc.yclip_suffix > DEAD_CLIP;
   int f = 0;
@@ -134,6 +136,8 @@ inline int scoring_flags(const DevScoring& sc) {
     f = F_TRACK_ROWS;
   }
   if (sc.alpha) f |= F_LUT;
+  if ((f & (F_TRACK_ROWS | F_TRACK_COLS)) && score_bound < (1ll << 17) && maxm <= 4095 && maxn <= 4095)
+    f |= F_PACKTRK;
   return f;
 }
 

@@ -5,6 +5,7 @@
 // host, stages a batch exactly as K0 does, and lets tests/test_sim_logic.py diff
 // the result against the oracle without a GPU.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -52,19 +53,21 @@ template <int R>
 void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring& sc,
                    const int32_t* lut, std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd,
                    std::vector<uint8_t>& rows, std::vector<uint8_t>& tb) {
+  constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+#define SIM_CASE(F) \
+  case (F): fill_block<R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb); break;
   switch (flags) {
-    case 0: fill_block<R, 0>(p, blk, sc, lut, seq, bnd, rows, tb); break;
-    case F_TRACK_ROWS: fill_block<R, F_TRACK_ROWS>(p, blk, sc, lut, seq, bnd, rows, tb); break;
-    case F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX:
-      fill_block<R, F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX>(p, blk, sc, lut, seq, bnd, rows, tb);
-      break;
-    case F_LUT: fill_block<R, F_LUT>(p, blk, sc, lut, seq, bnd, rows, tb); break;
-    case F_LUT | F_TRACK_ROWS:
-      fill_block<R, F_LUT | F_TRACK_ROWS>(p, blk, sc, lut, seq, bnd, rows, tb);
-      break;
-    default:
-      fill_block<R, F_LUT | F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX>(p, blk, sc, lut, seq, bnd, rows,
-                                                                   tb);
+    SIM_CASE(0)
+    SIM_CASE(F_TRACK_ROWS)
+    SIM_CASE(F_TRACK_ROWS | F_PACKTRK)
+    SIM_CASE(ALL)
+    SIM_CASE(ALL | F_PACKTRK)
+    SIM_CASE(F_LUT)
+    SIM_CASE(F_LUT | F_TRACK_ROWS)
+    SIM_CASE(F_LUT | F_TRACK_ROWS | F_PACKTRK)
+    SIM_CASE(F_LUT | ALL)
+    SIM_CASE(F_LUT | ALL | F_PACKTRK)
+    default: std::abort();
   }
 }
 
@@ -84,7 +87,7 @@ struct sim_scoring {
 // ops (m+n+4 bytes per pair at ops + ops_off[p], alignment order).
 int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
                     const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len,
-                    uint64_t n_pairs, int R, int force_general, int garbage, int32_t* score, uint32_t* xstart,
+                    uint64_t n_pairs, int R, int modebits /*1 general variant, 2 no packed trackers, 4 no LUT for MatchParams*/, int garbage, int32_t* score, uint32_t* xstart,
                     uint32_t* xend, uint32_t* ystart, uint32_t* yend, uint32_t* n_ops,
                     uint32_t* clip_len, uint32_t* status, uint8_t* ops, const uint64_t* ops_off) {
   DevScoring sc{};
@@ -99,11 +102,12 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
   sc.match_score = s->match_score;
   sc.mismatch_score = s->mismatch_score;
-  // compact alphabet over the symbols present (LUT mode)
+  // alphabet + LUT exactly as the engine builds them (b2a_engine.cu): LUT whenever <= 64 symbols
   uint8_t codemap[256];
   for (int k = 0; k < 256; ++k) codemap[k] = (uint8_t)k;
-  std::vector<int32_t> lut;
-  if (s->table) {
+  std::vector<int32_t> lut;  // [plain | 4*v+3]
+  int64_t maxabs = std::max<int64_t>(std::llabs((long long)s->match_score), std::llabs((long long)s->mismatch_score));
+  {
     bool present[256] = {false};
     for (uint64_t p = 0; p < n_pairs; ++p) {
       for (uint32_t k = 0; k < x_len[p]; ++k) present[blob[x_off[p] + k]] = true;
@@ -111,17 +115,37 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
     }
     std::vector<int> syms;
     for (int k = 0; k < 256; ++k)
-      if (present[k]) { codemap[k] = (uint8_t)syms.size(); syms.push_back(k); }
+      if (present[k]) syms.push_back(k);
     if (syms.empty()) syms.push_back(0);
-    sc.alpha = (int32_t)syms.size();
-    lut.resize((size_t)sc.alpha * sc.alpha);
-    for (int a = 0; a < sc.alpha; ++a)
-      for (int b = 0; b < sc.alpha; ++b) lut[(size_t)a * sc.alpha + b] = s->table[syms[a] * 256 + syms[b]];
+    const bool use_lut = s->table || !(modebits & 4);  // modebits & 4: force MatchParams compare path
+    if (use_lut && syms.size() <= 64) {
+      for (size_t a = 0; a < syms.size(); ++a) codemap[syms[a]] = (uint8_t)a;
+      sc.alpha = (int32_t)syms.size();
+      const size_t aa = (size_t)sc.alpha * sc.alpha;
+      lut.resize(2 * aa);
+      if (s->table) maxabs = 0;
+      for (int a = 0; a < sc.alpha; ++a)
+        for (int b = 0; b < sc.alpha; ++b) {
+          const int32_t v = s->table ? s->table[syms[a] * 256 + syms[b]]
+                                     : (a == b ? s->match_score : s->mismatch_score);
+          lut[(size_t)a * sc.alpha + b] = v;
+          maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
+        }
+      for (size_t k = 0; k < aa; ++k) lut[aa + k] = 4 * lut[k] + 3;
+    }
   }
   Plan p;
   build_plan(p, x_len, y_len, n_pairs, 1, R, ~0ull);
-  int flags = scoring_flags(sc);
-  if (force_general) flags = (flags & F_LUT) | F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+  const int64_t unit = std::max<int64_t>(maxabs, std::max<int64_t>(-(int64_t)sc.gap_open, -(int64_t)sc.gap_extend));
+  const int64_t bound = ((int64_t)p.maxm + p.maxn + 2) * unit - (int64_t)sc.gap_open;
+  int flags = scoring_flags(sc, bound, p.maxm, p.maxn);
+  if (modebits & 1) {
+    flags |= F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
+    if (bound < (1ll << 17) && p.maxm <= 4095 && p.maxn <= 4095) flags |= F_PACKTRK;
+  }
+  if (modebits & 2) flags &= ~F_PACKTRK;
+  const int32_t* lut_plain = lut.data();
+  const int32_t* lut_scaled = lut.data() + (size_t)sc.alpha * sc.alpha;
   // scratch starts as caller-chosen garbage: nothing may depend on its initial contents
   const uint8_t gb = (uint8_t)garbage;
   std::vector<uint8_t> seq(p.seq_bytes, 0), bnd(p.max_bnd, gb), rows(p.max_rows, gb),
@@ -140,16 +164,16 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   }
   for (const Block& blk : p.blocks) {
     switch (R) {
-      case 4: fill_dispatch<4>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
-      case 8: fill_dispatch<8>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
-      case 16: fill_dispatch<16>(flags, p, blk, sc, lut.data(), seq, bnd, rows, tb); break;
+      case 4: fill_dispatch<4>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 8: fill_dispatch<8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 16: fill_dispatch<16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       default: return -1;
     }
     for (uint32_t lane = 0; lane < blk.npairs; ++lane) {
       const uint32_t sp = blk.first + lane;
       PairView v;
       v.sc = sc;
-      v.lut = lut.data();
+      v.lut = lut_plain;
       v.P = 32;
       v.m = (int32_t)p.pm[sp];
       v.n = (int32_t)p.pn[sp];

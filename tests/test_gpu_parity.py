@@ -185,13 +185,23 @@ def test_c3_shape_global_1000x1000_sample(eng, oracle):
     s, _ = oracle.make_scoring(-5, -1, 1, -1)
     ref, ref_ops = oracle_batch(oracle, "global", s, batch, threads=8)
     cs, keep = _c_scoring(-5, -1, 1, -1)
-    for G, R in [(32, 8), (8, 16), (1, 16)]:
+    for G, R in [(32, 8), (32, 16), (8, 16), (4, 16)]:
         eng.set_tuning(G, R)
         try:
             got, ops = _engine_result(eng, "global", cs, batch)
         finally:
             eng.set_tuning(0, 0)
         assert_same(got, ops, ref, ref_ops, batch, f"C3 global G={G}")
+    # thread-per-pair staging of 32 x (1000+1000) bytes per warp does not fit on chip: refused, not wrong
+    from rust_bio_b200._lib import B2AError
+    eng.set_tuning(1, 16)
+    try:
+        with pytest.raises(B2AError, match="UNSUPPORTED"):
+            eng.align_batch(MODES["global"], cs, batch)
+    finally:
+        eng.set_tuning(0, 0)
+    got, ops = _engine_result(eng, "global", cs, batch)  # automatic shape
+    assert_same(got, ops, ref, ref_ops, batch, "C3 global auto shape")
 
 
 def test_waves_give_identical_results(eng, oracle):

@@ -43,12 +43,15 @@ def test_sim_golden(oracle, case, R):
 
 
 @pytest.mark.parametrize("mode", ["local", "global", "semiglobal"])
-@pytest.mark.parametrize("R,general", [(4, 0), (8, 1), (16, 0)])
-def test_sim_ragged_presets(oracle, mode, R, general):
+@pytest.mark.parametrize("R,general,no_pack,no_lut", [(4, 0, 0, 0), (8, 1, 0, 0), (16, 0, 0, 0), (8, 0, 1, 0),
+                                                      (4, 1, 1, 1), (16, 0, 0, 1)])
+def test_sim_ragged_presets(oracle, mode, R, general, no_pack, no_lut):
+    """Every kernel variant: specialised / general flags, packed / unpacked trackers, LUT / compare scores."""
     batch = synth.ragged_pairs(11 + R, 300, 70, 90)
     s, _ = oracle.make_scoring(-5, -1, 1, -1)
     ref, ref_ops = oracle_batch(oracle, mode, s, batch)
-    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=R, force_general=general)
+    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=R, force_general=general, no_pack=no_pack,
+                                    no_lut=no_lut)
     assert_same(got, ops, ref, ref_ops, batch, f"{mode} R={R}")
 
 
@@ -92,8 +95,8 @@ def test_sim_random_custom_clips(oracle, seed):
     s, _ = oracle.make_scoring(go, ge, ma, mi, None, pick(), pick(), pick(), pick())
     batch = synth.ragged_pairs(seed, 200, 40, 45, alphabet=b"AC" if seed % 2 else b"ACGT")
     ref, ref_ops = oracle_batch(oracle, "custom", s, batch)
-    for R in (4, 8):
-        got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R)
+    for R, no_pack in ((4, 0), (8, 1)):
+        got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R, no_pack=no_pack, no_lut=seed % 3 == 0)
         assert_same(got, ops, ref, ref_ops, batch, f"custom seed={seed} R={R}")
 
 

@@ -52,7 +52,8 @@ struct DevBuf {
 };
 
 const FillLaunch kFillShapes[] = {
-    {1, 16, launch_fill_1_16}, {1, 8, launch_fill_1_8},   {4, 16, launch_fill_4_16},
+    {1, 16, launch_fill_1_16}, {1, 8, launch_fill_1_8},   {1, 20, launch_fill_1_20},
+    {2, 16, launch_fill_2_16}, {2, 20, launch_fill_2_20}, {4, 16, launch_fill_4_16},
     {8, 16, launch_fill_8_16}, {32, 8, launch_fill_32_8}, {32, 16, launch_fill_32_16},
 };
 
@@ -441,6 +442,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     fp.lut = e->d_lut.as<int32_t>() + (size_t)e->sc.alpha * e->sc.alpha;  // the scaled copy
     fp.task_counter = ctl + 2 + wi;
     fp.smem_seq_bytes = pl.smem_seq_bytes;
+    fp.one = 1;
     fp.sc = e->sc;
     while (e->wave_ev.size() < 3 * (wi + 1)) {
       cudaEvent_t v;
@@ -468,6 +470,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     wp.sc = e->sc;
     wp.G = pl.G;
     wp.R = pl.R;
+    wp.packtrk = (e->flags & F_PACKTRK) ? 1 : 0;
     wp.filter_clips = (e->mode == B2A_MODE_SEMIGLOBAL || e->mode == B2A_MODE_LOCAL) ? 1 : 0;
     wp.score = e->d_score.as<int32_t>();
     wp.xstart = e->d_xs.as<uint32_t>();

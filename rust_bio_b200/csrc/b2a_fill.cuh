@@ -37,6 +37,7 @@ struct FillParams {
   const int32_t* lut;  // scaled LUT 4*score+3, alpha*alpha (global) or null
   uint32_t* task_counter;
   uint32_t smem_seq_bytes;  // per-warp staging bytes
+  int32_t one;              // must be 1 (opaque to the compiler, see fadd())
   DevScoring sc;
 };
 
@@ -60,6 +61,8 @@ struct LaneCtx {
   int4* bnd;             // block base, [column][32]
   int32_t* rows;         // block base, ROWS_ARRAYS arrays of [rows_pad][32]
   uint4* tb;             // task base: [strip][k][q][32]
+  uint32_t lut_base;     // device: shared-space byte address of the LUT; host sim: 0
+  int32_t one;           // an opaque 1 (kernel parameter): lets adds be issued as IMAD on the FMA pipe
 };
 
 #if defined(__CUDA_ARCH__)
@@ -86,8 +89,45 @@ B2A_HD int32_t max3(int32_t a, int32_t b, int32_t c) {
 #endif
 }
 B2A_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+// fused add+max / add+min (DPX: one VIADDMNMX on the ALU pipe)
+B2A_HD int32_t addmax(int32_t a, int32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __viaddmax_s32(a, b, c);
+#else
+  return imax(a + b, c);
+#endif
+}
+B2A_HD int32_t addmin(int32_t a, int32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __viaddmin_s32(a, b, c);
+#else
+  return imin(a + b, c);
+#endif
+}
 // 4*v, except that dead (MIN_SCORE-like) penalties map to NEG4 instead of overflowing
 B2A_HD int32_t scale4(int32_t v) { return v <= DEAD_CLIP ? NEG4 : 4 * v; }
+
+// The fill is bound by the integer ALU pipe (VIMNMX/LOP3/...), while the FMA pipe (IMAD) idles.
+// Plain adds are therefore written as a*k+b with k an opaque kernel parameter, which ptxas must
+// issue as IMAD: the max/min/select work stays on the ALU pipe, the additions move to the FMA pipe.
+B2A_HD int32_t fmad(int32_t a, int32_t k, int32_t b) {
+#if defined(__CUDA_ARCH__)
+  int32_t d;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(k), "r"(b));
+  return d;
+#else
+  return a * k + b;
+#endif
+}
+B2A_HD int32_t lut_at(const void* host_base, uint32_t byte_addr) {
+#if defined(__CUDA_ARCH__)
+  int32_t v;
+  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(byte_addr));
+  return v;
+#else
+  return *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(host_base) + byte_addr);
+#endif
+}
 
 // packed arg-max keys (F_PACKTRK): 4096*value + (4095 - index): max() keeps the first index on ties
 constexpr int32_t KEY_NONE = (int32_t)0x80000000;
@@ -108,30 +148,34 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
   const int32_t xs4 = scale4(c.sc.xclip_suffix), ys4 = scale4(c.sc.yclip_suffix);
   const int32_t cj = 4095 - j;  // packed row-tracker index field
+  const int32_t one = c.one, k2 = one + one, k16 = k2 * 8, k1024 = k16 * 64;
+  const int32_t q4 = q * 4;
   int32_t Tl = KEY_NONE;        // packed column tracker of this lane's rows (local row index)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int32_t sub4;
     if (LUT) {
-      sub4 = c.lut[xc[r] + q];
+      sub4 = lut_at(c.lut, (uint32_t)fmad(q4, one, xc[r]));
     } else {
       sub4 = (xc[r] == q) ? ma4 : mi4;
     }
-    const int32_t m4 = sdiag + sub4;
-    const int32_t iop = sup + go4i;
-    const int32_t i4 = imax(iup + ge4, iop);
-    const int32_t dop = Sp[r] + go4d;
-    const int32_t d4 = imax(Dp[r] + ge4, dop);
+    const int32_t m4 = fmad(sdiag, one, sub4);
+    const int32_t iop = fmad(sup, one, go4i);
+    const int32_t i4 = addmax(iup, ge4, iop);
+    const int32_t dop = fmad(Sp[r], one, go4d);
+    const int32_t d4 = addmax(Dp[r], ge4, dop);
     int32_t sP = max3(m4, i4, d4);
     if (CX) sP = imax(sP, x4);
     const int32_t s4 = sP & ~3;
-    // nibble = code | iext << 2 | dext << 3
-    const uint32_t nib = (uint32_t)((sP - s4) + imin(i4 - iop, 4) + 2 * imin(d4 - dop, 4));
-    tbacc[r] = tbacc[r] * 16u + nib;
+    // nibble = code | iext << 2 | dext << 3 = (sP - s4) + min(i4 - iop, 4) + 2 * min(d4 - dop, 4),
+    // accumulated as tbacc*16 + nibble with the additions on the FMA pipe
+    const int32_t fi = addmin(i4, -iop, 4), fd = addmin(d4, -dop, 4);
+    const int32_t nib = (sP - s4) + fmad(fd, k2, fi);  // one 3-input add + one IMAD
+    tbacc[r] = (uint32_t)fmad((int32_t)tbacc[r], k16, nib);  // the oldest nibble falls off the top
+    const int32_t s4k = (TR || TC) && PK ? fmad(s4, k1024, 0) : 0;  // 4096*S, shared by both trackers
     if (TC) {
       if (PK) {
-        const int32_t key = s4 * 1024 + (4095 - r);
-        if (!MASKED || r < rv) Tl = imax(Tl, key);
+        if (!MASKED || r < rv) Tl = addmax(s4k, 4095 - r, Tl);
       } else {
         const int32_t v = s4 + xs4;
         if ((!MASKED || r < rv) && v > Tv) {
@@ -142,7 +186,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
     }
     if (TR) {
       if (PK) {
-        SnR[r] = imax(SnR[r], s4 * 1024 + cj);
+        SnR[r] = addmax(s4k, cj, SnR[r]);
       } else {
         const int32_t v = s4 + ys4;
         if (v > SnR[r]) {
@@ -155,7 +199,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
       c.rows[ROWS_SL * c.rows_pad * 32 + slot] = s4 >> 2;
       c.rows[ROWS_IL * c.rows_pad * 32 + slot] = i4 >> 2;
-      c.rows[ROWS_NL * c.rows_pad * 32 + slot] = (int32_t)nib;
+      c.rows[ROWS_NL * c.rows_pad * 32 + slot] = nib;
     }
     if (MASKED) {
       if (r == rv - 1) {
@@ -189,7 +233,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   // valid rows of this lane: rows <= m-1
   int32_t rv = m - 1 - rowbase;
   rv = rv < 0 ? 0 : (rv > R ? R : rv);
-  const int32_t xs = c.sc.xclip_suffix, ys = c.sc.yclip_suffix;
+  const int32_t ys = c.sc.yclip_suffix;
 
   int32_t Sp[R], Dp[R], SnR[R], LyR[R], xc[R];
   uint32_t tbacc[R];
@@ -200,7 +244,8 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int32_t sym = (int32_t)((xw >> (8 * b)) & 0xffu);
-      xc[w * 4 + b] = LUT ? sym * c.sc.alpha : sym;
+      // LUT mode: byte address of the symbol's LUT row (shared-space on the device)
+      xc[w * 4 + b] = LUT ? (int32_t)(c.lut_base + (uint32_t)(sym * c.sc.alpha * 4)) : sym;
     }
   }
 #pragma unroll
@@ -257,16 +302,12 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         in_i = NEG4;
         in_tv = t_none;
         in_ti = m;
-      } else if (top_from_mem) {
-        in_s = 4 * pre.x;
-        in_i = 4 * pre.y + 2;
+      } else if (top_from_mem) {  // the boundary row is kept in the fill's own scaled domain
+        in_s = pre.x;
+        in_i = pre.y;
         if (TC) {
-          if (PK) {
-            in_tv = (pre.z == MIN_SCORE) ? KEY_NONE : (pre.z - xs) * 4096 + (4095 - pre.w);
-          } else {
-            in_tv = (pre.z == MIN_SCORE) ? NEG4 : 4 * pre.z;
-            in_ti = pre.w;
-          }
+          in_tv = pre.z;
+          in_ti = pre.w;
         }
         if (j < c.maxn) pre = c.bnd[(j + 1) * 32 + c.pi];  // prefetch next column's boundary
       }
@@ -280,22 +321,11 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       }
       sup_prev = in_s;
       if (writer) {
-        int4 o;
-        o.x = (MASKED ? cap_s : sup) >> 2;
-        o.y = (MASKED ? cap_i : iup) >> 2;
-        o.z = MIN_SCORE;
-        o.w = m;
-        if (TC) {
-          if (PK) {
-            if (Tv != KEY_NONE) {
-              o.z = (Tv >> 12) + xs;
-              o.w = 4095 - (Tv & 4095);
-            }
-          } else if (Tv > NEG4 / 2) {
-            o.z = Tv >> 2;
-            o.w = Ti;
-          }
-        }
+        int4 o;  // decoded by decode_boundary() in b2a_walk.cuh
+        o.x = MASKED ? cap_s : sup;
+        o.y = MASKED ? cap_i : iup;
+        o.z = TC ? Tv : t_none;
+        o.w = TC ? Ti : m;
         c.bnd[j * 32 + c.pi] = o;
       }
       in_s = sup;
@@ -325,8 +355,6 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         v.w = (qd * 4 + 3 < R) ? tbacc[qd * 4 + 3] : 0u;
         dst[qd * 32] = v;
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r) tbacc[r] = 0;
     }
   }
   if (TR) {
@@ -439,6 +467,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) fill_kernel(const FillParams 
     LaneCtx<G> c;
     c.sc = prm.sc;
     c.lut = lut_s;
+    c.lut_base = smem_u32(lut_s);
+    c.one = prm.one;
     c.xs = reinterpret_cast<const uint32_t*>(stage);
     c.ys = reinterpret_cast<const uint32_t*>(stage + xbytes);
     c.g = lane / G;

@@ -20,6 +20,9 @@ struct FillLaunch {
 
 B2A_DECLARE_FILL(1, 16)
 B2A_DECLARE_FILL(1, 8)
+B2A_DECLARE_FILL(1, 20)
+B2A_DECLARE_FILL(2, 16)
+B2A_DECLARE_FILL(2, 20)
 B2A_DECLARE_FILL(4, 16)
 B2A_DECLARE_FILL(8, 16)
 B2A_DECLARE_FILL(32, 8)

@@ -31,6 +31,7 @@ struct WalkParams {
   DevScoring sc;
   int32_t G, R;
   int32_t filter_clips;  // semiglobal / local: Alignment::filter_clip_operations
+  int32_t packtrk;       // K1 ran with F_PACKTRK (how the column tracker in the boundary row is encoded)
   // outputs, indexed by the caller's pair index
   int32_t* score;
   uint32_t* xstart;
@@ -60,6 +61,7 @@ struct PairView {
   uint16_t* rowm;      // [column][32]
   const uint32_t* tb;  // block base
   int32_t sub, g;      // task inside the block, slot inside the task
+  int32_t packtrk;
 
   B2A_HD int32_t xsym(int32_t i) const {  // x[i-1]
     const int32_t b = i - 1;
@@ -94,6 +96,29 @@ struct PairView {
     }
   }
 };
+
+// Boundary row m-1 as K1 leaves it (scaled domain, b2a_fill.cuh): x = 4*S, y = 4*I + 2,
+// z/w = column tracker: packed key 4096*(max S) + (4095 - first row) [F_PACKTRK] or (4*(T), row).
+struct Boundary {
+  int32_t S, I, Tv, Ti;
+};
+B2A_HD Boundary decode_boundary(const int4 b, const bool packtrk, const int32_t xs, const int32_t m) {
+  Boundary o;
+  o.S = b.x >> 2;
+  o.I = b.y >> 2;
+  o.Tv = MIN_SCORE;
+  o.Ti = m;
+  if (packtrk) {
+    if (b.z != (int32_t)0x80000000) {
+      o.Tv = (b.z >> 12) + xs;
+      o.Ti = 4095 - (b.z & 4095);
+    }
+  } else if (b.z > -(1 << 29)) {
+    o.Tv = b.z >> 2;
+    o.Ti = b.w;
+  }
+  return o;
+}
 
 // cells kept as the reference's u16: i | d << 4 | s << 8 (mod.rs:1031-1033)
 B2A_HD uint32_t cell_make(uint32_t i, uint32_t d, uint32_t s) { return i | (d << 4) | (s << 8); }
@@ -163,11 +188,11 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
         Tv = MIN_SCORE;
         Ti = m;
       } else {
-        const int4 b = v.bnd[j * 32 + v.pi];
-        sup = b.x;
-        iup = b.y;
-        Tv = b.z;
-        Ti = b.w;
+        const Boundary b = decode_boundary(v.bnd[j * 32 + v.pi], v.packtrk != 0, xs, m);
+        sup = b.S;
+        iup = b.I;
+        Tv = b.Tv;
+        Ti = b.Ti;
       }
       const int32_t q = v.ysym(j);
       const int32_t m_score = sdiag + v.score(p, q);
@@ -413,7 +438,7 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
       int32_t lx;
       if (j == n) lx = LxN;
       else if (j == 0) lx = Lx0;
-      else lx = (m >= 2) ? m - v.bnd[j * 32 + v.pi].w : 0;
+      else lx = (m >= 2) ? m - decode_boundary(v.bnd[j * 32 + v.pi], v.packtrk != 0, xs, m).Ti : 0;
       if (!filter_clips) {
         *(--ops_end) = 4;
         ++nops;
@@ -494,6 +519,7 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
   v.K = (int32_t)blk.K;
   v.sub = lane / P;
   v.g = lane % P;
+  v.packtrk = prm.packtrk;
   const uint32_t* seqw = reinterpret_cast<const uint32_t*>(prm.seq + blk.seq_off);
   v.xw = seqw + (size_t)v.sub * blk.xwords * P + v.g;
   v.yw = seqw + (size_t)prm.G * blk.xwords * P + (size_t)v.sub * blk.ywords * P + v.g;

@@ -26,6 +26,8 @@ void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int
     LaneCtx<G> c;
     c.sc = sc;
     c.lut = lut;
+    c.lut_base = 0;
+    c.one = 1;
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
     c.xs = seqw;
     c.ys = seqw + (size_t)G * blk.xwords * P;
@@ -185,6 +187,7 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
       v.K = (int32_t)blk.K;
       v.sub = (int32_t)lane / 32;
       v.g = (int32_t)lane % 32;
+      v.packtrk = (flags & F_PACKTRK) ? 1 : 0;
       const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
       v.xw = seqw + v.g;
       v.yw = seqw + (size_t)blk.xwords * 32 + v.g;

@@ -117,3 +117,95 @@ def align_batch(mode, scoring: OrcScoring, blob, x_off, x_len, y_off, y_len, thr
 
 def hardware_threads() -> int:
     return int(lib().orc_hardware_threads())
+
+
+# ------------------------------------------------------------------ banded::Aligner + sparse pieces
+def banded_align(mode, scoring: OrcScoring, k: int, w: int, x: bytes, y: bytes):
+    mode = MODES.get(mode, mode)
+    m, n = len(x), len(y)
+    out = OrcAlignment()
+    ops = (C.c_uint32 * (m + n + 8))()
+    L = lib()
+    L.orc_banded_align.restype = C.c_int
+    rc = L.orc_banded_align(int(mode), C.byref(scoring), C.c_uint32(k), C.c_uint32(w), x, C.c_uint32(m), y,
+                            C.c_uint32(n), C.byref(out), ops)
+    if rc != 0:
+        raise RuntimeError("banded oracle: the reference would panic on this input")
+    d = {f: getattr(out, f) for f, _ in OrcAlignment._fields_}
+    return d, [(int(v) & 7, int(v) >> 3) for v in ops[:out.n_ops]]
+
+
+def banded_align_batch(mode, scoring: OrcScoring, k, w, blob, x_off, x_len, y_off, y_len, threads=1,
+                       want_ops=True):
+    """-> (fields, ops uint32 flat, ops_off, seconds, band cells)"""
+    mode = MODES.get(mode, mode)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    x_off = np.ascontiguousarray(x_off, dtype=np.uint64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.uint64)
+    x_len = np.ascontiguousarray(x_len, dtype=np.uint32)
+    y_len = np.ascontiguousarray(y_len, dtype=np.uint32)
+    n = len(x_len)
+    out = np.zeros(n, dtype=ALN_DTYPE)
+    if want_ops:
+        cap = x_len.astype(np.uint64) + y_len.astype(np.uint64) + np.uint64(8)
+        ops_off = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+        ops = np.zeros(int(ops_off[-1]), dtype=np.uint32)
+        ops_p, off_p = ops.ctypes.data_as(C.c_void_p), ops_off.ctypes.data_as(C.c_void_p)
+    else:
+        ops, ops_off, ops_p, off_p = None, None, None, None
+    cells = C.c_uint64(0)
+    L = lib()
+    L.orc_banded_align_batch.restype = C.c_double
+    secs = L.orc_banded_align_batch(
+        int(mode), C.byref(scoring), C.c_uint32(k), C.c_uint32(w), blob.ctypes.data_as(C.c_void_p),
+        x_off.ctypes.data_as(C.c_void_p), x_len.ctypes.data_as(C.c_void_p),
+        y_off.ctypes.data_as(C.c_void_p), y_len.ctypes.data_as(C.c_void_p), C.c_uint64(n),
+        out.ctypes.data_as(C.c_void_p), ops_p, off_p, C.byref(cells), C.c_int(int(threads)))
+    return out, ops, ops_off, secs, int(cells.value)
+
+
+def band_create(mode, scoring: OrcScoring, k, w, x: bytes, y: bytes):
+    """Band::create -> (ranges [(start, end)] per column, num_cells)"""
+    mode = MODES.get(mode, mode)
+    n = len(y)
+    ranges = (C.c_uint64 * (2 * (n + 1)))()
+    cells = C.c_uint64(0)
+    rc = lib().orc_band_create(int(mode), C.byref(scoring), C.c_uint32(k), C.c_uint32(w), x, C.c_uint32(len(x)),
+                               y, C.c_uint32(n), ranges, C.byref(cells))
+    if rc != 0:
+        raise RuntimeError("banded oracle: Band::create would panic")
+    return [(int(ranges[2 * j]), int(ranges[2 * j + 1])) for j in range(n + 1)], int(cells.value)
+
+
+def band_ops(m, n, ops):
+    """ops: [("entry"|"kmer", r, c, k, w)] applied to Band::new(m, n) -> ranges"""
+    flat = (C.c_uint32 * (5 * len(ops)))()
+    for t, (kind, r, c, k, w) in enumerate(ops):
+        flat[5 * t:5 * t + 5] = [0 if kind == "entry" else 1, r, c, k, w]
+    ranges = (C.c_uint64 * (2 * (n + 1)))()
+    rc = lib().orc_band_ops(C.c_uint32(m), C.c_uint32(n), flat, C.c_uint32(len(ops)), ranges)
+    assert rc == 0
+    return [[int(ranges[2 * j]), int(ranges[2 * j + 1])] for j in range(n + 1)]
+
+
+def find_kmer_matches(x: bytes, y: bytes, k: int):
+    L = lib()
+    L.orc_find_kmer_matches.restype = C.c_uint64
+    cap = 1 << 16
+    buf = (C.c_uint32 * (2 * cap))()
+    cnt = L.orc_find_kmer_matches(x, C.c_uint32(len(x)), y, C.c_uint32(len(y)), C.c_uint32(k), buf, C.c_uint64(cap))
+    assert cnt <= cap
+    return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(cnt)]
+
+
+def sdpkpp(matches, k, match_score, gap_open, gap_extend):
+    n = len(matches)
+    xy = (C.c_uint32 * (2 * max(1, n)))()
+    for i, (a, b) in enumerate(matches):
+        xy[2 * i], xy[2 * i + 1] = a, b
+    path = (C.c_uint64 * max(1, n))()
+    npath, score = C.c_uint64(0), C.c_uint32(0)
+    rc = lib().orc_sdpkpp(xy, C.c_uint64(n), C.c_uint32(k), C.c_uint32(match_score), C.c_int32(gap_open),
+                          C.c_int32(gap_extend), path, C.byref(npath), C.byref(score))
+    assert rc == 0
+    return [int(path[i]) for i in range(npath.value)], int(score.value)

@@ -36,19 +36,27 @@ constexpr uint16_t TB_START = 0, TB_INS = 1, TB_DEL = 2, TB_SUBST = 3, TB_MATCH 
                    TB_XCLIP_PREFIX = 5, TB_XCLIP_SUFFIX = 6, TB_YCLIP_PREFIX = 7,
                    TB_YCLIP_SUFFIX = 8;
 
-struct Panic : std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
+// A panic (or a traceback that never terminates) in the reference is recorded here instead of being
+// thrown: C++ exceptions across this dlopen'ed, statically-linked-libstdc++ library are not reliable.
+thread_local bool g_panic = false;
+inline void panic(const char*) { g_panic = true; }
 
 template <class T>
 struct Vec {  // bounds-checked like a Rust Vec
   std::vector<T> v;
+  mutable T dummy{};
   T& operator[](uint64_t i) {
-    if (i >= v.size()) throw Panic("index out of bounds");
+    if (i >= v.size()) {
+      panic("index out of bounds");
+      return dummy;
+    }
     return v[i];
   }
   const T& operator[](uint64_t i) const {
-    if (i >= v.size()) throw Panic("index out of bounds");
+    if (i >= v.size()) {
+      panic("index out of bounds");
+      return dummy;
+    }
     return v[i];
   }
   uint64_t len() const { return v.size(); }
@@ -151,10 +159,10 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
   SparseResult res;
   if (matches.empty()) return res;
   const uint32_t k = (uint32_t)k_;
-  if (!(gap_open <= 0 && gap_extend <= 0)) throw Panic("gap parameters cannot be positive");
+  if (!(gap_open <= 0 && gap_extend <= 0)) { panic("gap parameters cannot be positive"); return res; }
   const uint32_t go = (uint32_t)(-gap_open), ge = (uint32_t)(-gap_extend);
   for (size_t i = 1; i < matches.size(); ++i)
-    if (!(matches[i - 1] < matches[i])) throw Panic("incoming matches must be sorted");
+    if (!(matches[i - 1] < matches[i])) { panic("incoming matches must be sorted"); return res; }
   std::vector<std::tuple<uint32_t, uint32_t, uint32_t>> events;
   uint32_t n = 0;
   const uint32_t nm = (uint32_t)matches.size();
@@ -167,14 +175,15 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
   }
   std::sort(events.begin(), events.end());
   MaxBitTree max_col_dp(n);
-  std::vector<std::pair<uint32_t, int32_t>> dp(events.size(), {0u, 0});
+  Vec<std::pair<uint32_t, int32_t>> dp;
+  dp.v.assign(events.size(), {0u, 0});
   std::pair<uint32_t, int32_t> best_dp{k, 0};
   for (const auto& ev : events) {
     const uint32_t e0 = std::get<0>(ev), e1 = std::get<1>(ev), e2 = std::get<2>(ev);
     const uint64_t p = e2 % nm;
     const bool is_start = e2 >= nm;
     if (is_start) {
-      dp.at(p) = {k * match_score, -1};
+      dp[p] = {k * match_score, -1};
       const PrevPtr best_prev = max_col_dp.get(e1);
       if (best_prev.score > 0) {
         const uint32_t gap = std::max(e0 - best_prev.x, e1 - best_prev.y);
@@ -182,8 +191,8 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
         const uint32_t reward = k * match_score;
         const uint32_t sum = best_prev.score + reward;
         const uint32_t new_score = sum > gap_penalty ? sum - gap_penalty : 0;  // saturating_sub
-        dp.at(p) = std::max(dp.at(p), std::make_pair(new_score, (int32_t)best_prev.id));
-        best_dp = std::max(best_dp, std::make_pair(dp.at(p).first, (int32_t)p));
+        dp[p] = std::max(dp[p], std::make_pair(new_score, (int32_t)best_prev.id));
+        best_dp = std::max(best_dp, std::make_pair(dp[p].first, (int32_t)p));
       }
     } else {
       if (e0 > k && e1 > k) {
@@ -191,15 +200,15 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
         auto it = std::lower_bound(matches.begin(), matches.end(), want);
         if (it != matches.end() && *it == want) {
           const uint64_t cont_idx = (uint64_t)(it - matches.begin());
-          const auto cand = std::make_pair(dp.at(cont_idx).first + match_score, (int32_t)cont_idx);
-          dp.at(p) = std::max(dp.at(p), cand);
-          best_dp = std::max(best_dp, std::make_pair(dp.at(p).first, (int32_t)p));
+          const auto cand = std::make_pair(dp[cont_idx].first + match_score, (int32_t)cont_idx);
+          dp[p] = std::max(dp[p], cand);
+          best_dp = std::max(best_dp, std::make_pair(dp[p].first, (int32_t)p));
         }
       }
       PrevPtr pf;
       pf.d = e0 + e1;
-      pf.plane = dp.at(p).first + pf.d * ge;
-      pf.score = dp.at(p).first;
+      pf.plane = dp[p].first + pf.d * ge;
+      pf.score = dp[p].first;
       pf.id = p;
       pf.x = e0;
       pf.y = e1;
@@ -209,7 +218,7 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
   int32_t prev_match = best_dp.second;
   while (prev_match >= 0) {
     res.path.push_back((uint64_t)prev_match);
-    prev_match = dp.at((uint64_t)prev_match).second;
+    prev_match = dp[(uint64_t)prev_match].second;
   }
   std::reverse(res.path.begin(), res.path.end());
   res.score = best_dp.first;
@@ -277,14 +286,14 @@ struct Band {
     if (nrows > ncols) {
       for (uint32_t r = start.first; r < end.first; ++r) {
         const uint32_t den = end.first - start.first;
-        if (den == 0) throw Panic("attempt to divide by zero");
+        if (den == 0) { panic("attempt to divide by zero"); return; }
         const uint32_t c = start.second + (end.second - start.second) * (r - start.first) / den;
         add_entry({r, c}, w);
       }
     } else {
       for (uint32_t c = start.second; c < end.second; ++c) {
         const uint32_t den = end.second - start.second;
-        if (den == 0) throw Panic("attempt to divide by zero");
+        if (den == 0) { panic("attempt to divide by zero"); return; }
         const uint32_t r = start.first + (end.first - start.first) * (c - start.second) / den;
         add_entry({r, c}, w);
       }
@@ -359,13 +368,13 @@ struct Band {
       band.full_matrix();
       return band;
     }
-    if (path.empty()) throw Panic("index out of bounds");
+    if (path.empty()) { panic("index out of bounds"); band.full_matrix(); return band; }
     const uint64_t ps = path.front(), pe = path.back();
-    band.set_boundaries(matches.at(ps), matches.at(pe), k, w, sc);
+    band.set_boundaries(matches[ps], matches[pe], k, w, sc);
     bool has_prev = false;
     Match prev{0, 0};
     for (uint64_t idx : path) {
-      const Match curr = matches.at(idx);
+      const Match curr = matches[idx];
       const bool cont = has_prev && curr.first == prev.first + 1 && curr.second == prev.second + 1;
       if (cont) {
         band.add_entry({prev.first + (uint32_t)k, prev.second + (uint32_t)k}, w);
@@ -699,24 +708,24 @@ struct BandedAligner {
     for (;;) {
       uint16_t next_layer;
       if (last_layer == TB_START) break;
-      if (guard-- == 0) throw Panic("traceback does not terminate");
+      if (guard-- == 0) { panic("traceback does not terminate"); break; }
       switch (last_layer) {
         case TB_INS:
           operations.push_back({3, 0});
           next_layer = at(i, j).i();
-          if (i == 0) throw Panic("attempt to subtract with overflow");
+          if (i == 0) { panic("attempt to subtract with overflow"); last_layer = TB_START; continue; }
           i -= 1;
           break;
         case TB_DEL:
           operations.push_back({2, 0});
           next_layer = at(i, j).d();
-          if (j == 0) throw Panic("attempt to subtract with overflow");
+          if (j == 0) { panic("attempt to subtract with overflow"); last_layer = TB_START; continue; }
           j -= 1;
           break;
         case TB_MATCH:
         case TB_SUBST:
           operations.push_back({last_layer == TB_MATCH ? 0u : 1u, 0});
-          if (i == 0 || j == 0) throw Panic("attempt to subtract with overflow");
+          if (i == 0 || j == 0) { panic("attempt to subtract with overflow"); last_layer = TB_START; continue; }
           next_layer = at(i - 1, j - 1).s();
           i -= 1;
           j -= 1;
@@ -729,7 +738,7 @@ struct BandedAligner {
           break;
         case TB_XCLIP_SUFFIX:
           operations.push_back({4, (uint32_t)Lx[j]});
-          if (Lx[j] > i) throw Panic("attempt to subtract with overflow");
+          if (Lx[j] > i) { panic("attempt to subtract with overflow"); last_layer = TB_START; continue; }
           i -= Lx[j];
           xend = i;
           next_layer = at(i, j).s();
@@ -742,13 +751,15 @@ struct BandedAligner {
           break;
         case TB_YCLIP_SUFFIX:
           operations.push_back({5, (uint32_t)Ly[i]});
-          if (Ly[i] > j) throw Panic("attempt to subtract with overflow");
+          if (Ly[i] > j) { panic("attempt to subtract with overflow"); last_layer = TB_START; continue; }
           j -= Ly[i];
           yend = j;
           next_layer = at(i, j).s();
           break;
         default:
-          throw Panic("Dint expect this!");
+          panic("Dint expect this!");
+          last_layer = TB_START;
+          continue;
       }
       last_layer = next_layer;
     }
@@ -828,23 +839,23 @@ uint64_t orc_find_kmer_matches(const uint8_t* x, uint32_t m, const uint8_t* y, u
 // sdpkpp over sorted matches; path indices written to out_path (cap >= n_matches). Returns -1 on a panic path.
 int orc_sdpkpp(const uint32_t* xy, uint64_t n_matches, uint32_t k, uint32_t match_score, int32_t gap_open,
                int32_t gap_extend, uint64_t* out_path, uint64_t* n_path, uint32_t* score) {
-  try {
+  {
+    g_panic = false;
     std::vector<Match> m(n_matches);
     for (uint64_t i = 0; i < n_matches; ++i) m[i] = {xy[2 * i], xy[2 * i + 1]};
     const SparseResult r = sdpkpp(m, k, match_score, gap_open, gap_extend);
     for (uint64_t i = 0; i < r.path.size(); ++i) out_path[i] = r.path[i];
     *n_path = r.path.size();
     *score = r.score;
-    return 0;
-  } catch (const std::exception&) {
-    return -1;
+    return g_panic ? -1 : 0;
   }
 }
 
 // Band::create(x, y, k, w, scoring) with the clip presets of `mode` applied; ranges as (start,end) pairs.
 int orc_band_create(int mode, const orc_scoring* scoring, uint32_t k, uint32_t w, const uint8_t* x, uint32_t m,
                     const uint8_t* y, uint32_t n, uint64_t* ranges /*2*(n+1)*/, uint64_t* num_cells) {
-  try {
+  {
+    g_panic = false;
     orc_scoring sc = *scoring;
     if (mode == 1) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
     if (mode == 2) {
@@ -859,16 +870,15 @@ int orc_band_create(int mode, const orc_scoring* scoring, uint32_t k, uint32_t w
       ranges[2 * j + 1] = b.ranges[j].end;
     }
     *num_cells = b.num_cells();
-    return 0;
-  } catch (const std::exception&) {
-    return -1;
+    return g_panic ? -1 : 0;
   }
 }
 
 // Band geometry primitives for the reference's unit tests (banded.rs:1470-1618): ops is a list of
 // (kind, r, c, k, w): kind 0 add_entry, 1 add_kmer.
 int orc_band_ops(uint32_t m, uint32_t n, const uint32_t* ops, uint32_t n_ops, uint64_t* ranges) {
-  try {
+  {
+    g_panic = false;
     Band b = Band::make(m, n);
     for (uint32_t t = 0; t < n_ops; ++t) {
       const uint32_t* o = ops + 5 * t;
@@ -879,27 +889,25 @@ int orc_band_ops(uint32_t m, uint32_t n, const uint32_t* ops, uint32_t n_ops, ui
       ranges[2 * j] = b.ranges[j].start;
       ranges[2 * j + 1] = b.ranges[j].end;
     }
-    return 0;
-  } catch (const std::exception&) {
-    return -1;
+    return g_panic ? -1 : 0;
   }
 }
 
 int orc_banded_align(int mode, const orc_scoring* scoring, uint32_t k, uint32_t w, const uint8_t* x, uint32_t m,
                      const uint8_t* y, uint32_t n, orc_alignment* out, uint32_t* ops) {
-  try {
-    BandedAligner a;
-    a.sc = *scoring;
-    a.k = k;
-    a.w = w;
-    std::vector<Op> v;
-    a.align(mode, x, m, y, n, out, v);
-    for (size_t t = 0; t < v.size(); ++t) ops[t] = v[t].code | (v[t].len << 3);
-    return 0;
-  } catch (const std::exception&) {
+  g_panic = false;
+  BandedAligner a;
+  a.sc = *scoring;
+  a.k = k;
+  a.w = w;
+  std::vector<Op> v;
+  a.align(mode, x, m, y, n, out, v);
+  if (g_panic) {
     out->n_ops = 0xFFFFFFFFu;
     return -1;
   }
+  for (size_t t = 0; t < v.size(); ++t) ops[t] = v[t].code | (v[t].len << 3);
+  return 0;
 }
 
 double orc_banded_align_batch(int mode, const orc_scoring* scoring, uint32_t k, uint32_t w, const uint8_t* blob,
@@ -920,13 +928,13 @@ double orc_banded_align_batch(int mode, const orc_scoring* scoring, uint32_t k, 
       const uint64_t lo = n_pairs * (uint64_t)t / (uint64_t)threads;
       const uint64_t hi = n_pairs * (uint64_t)(t + 1) / (uint64_t)threads;
       for (uint64_t p = lo; p < hi; ++p) {
-        try {
-          a.align(mode, blob + x_off[p], x_len[p], blob + y_off[p], y_len[p], &out[p], v);
-          cell_acc[t] += a.band.num_cells();
-          if (ops)
-            for (size_t q = 0; q < v.size(); ++q) ops[ops_off[p] + q] = v[q].code | (v[q].len << 3);
-        } catch (const std::exception&) {
+        g_panic = false;
+        a.align(mode, blob + x_off[p], x_len[p], blob + y_off[p], y_len[p], &out[p], v);
+        cell_acc[t] += a.band.num_cells();
+        if (g_panic) {
           out[p].n_ops = 0xFFFFFFFFu;
+        } else if (ops) {
+          for (size_t q = 0; q < v.size(); ++q) ops[ops_off[p] + q] = v[q].code | (v[q].len << 3);
         }
       }
     });

@@ -1,0 +1,1064 @@
+// K4 + K3: banded::Aligner on the device, one lane per pair.
+//
+// Reference rust-bio 4.0.1:
+//   sparse::find_kmer_matches          src/alignment/sparse.rs:337-402
+//   sparse::sdpkpp + PrevPtr           sparse.rs:145-295   (prefix-max of bit_tree.rs:45-99)
+//   Band::{add_kmer,add_entry,add_gap,set_boundaries,create_*,num_cells}   banded.rs:1047-1380
+//   banded::Aligner::compute_alignment banded.rs:406-869
+// The banded DP is full of order-dependent quirks (rolling arrays keep leftovers from earlier
+// columns, eager traceback writes that later stores overwrite, a walk that may stop on an untouched
+// cell outside the band), so K3 replays the column loop literally -- but on GPU-sized state:
+//   * the reference's (m+1)(n+1) u16 traceback (10 MB for 500x10,000, re-zeroed per call) becomes
+//     band cells + row 0 + row m + column 0 + column n; every other cell is a constant START;
+//   * k-mer matches come from a rolling-hash table of the shorter sequence (exact: verified bytes);
+//   * the Fenwick tree over coordinates 0..n becomes a Fenwick tree over the (<= #matches) distinct
+//     end coordinates -- the same prefix-max, since only inserted coordinates can ever answer.
+// All per-pair state lives in one HBM scratch slab per pair (BandedSlab).
+#pragma once
+#include "b2a_common.cuh"
+
+namespace b2a {
+
+constexpr uint64_t BANDED_MAX_CELLS = 5000000ull;  // banded.rs:104
+constexpr int32_t BANDED_DEFAULT_MATCH_SCORE = 2;  // banded.rs:105
+
+struct BandedParams {
+  const uint8_t* blob;
+  const uint64_t* x_off;
+  const uint32_t* x_len;
+  const uint64_t* y_off;
+  const uint32_t* y_len;
+  const uint8_t* codemap;  // symbol -> LUT code (LUT mode)
+  const int32_t* lut;      // alpha*alpha plain scores, or null
+  DevScoring sc;           // clip presets already applied
+  int32_t has_match_scores;
+  uint32_t k, w;
+  uint32_t cap_matches;    // per pair
+  uint64_t n_pairs;
+  uint32_t pair_lo;        // first pair of this wave
+  // per-pair slabs
+  uint8_t* slab;           // K4 slab base (wave-relative pair index * slab_stride)
+  uint64_t slab_stride;
+  uint32_t* ranges;        // [(n_pad+1) * 2] per pair, wave arena: ranges_off[p]
+  const uint64_t* ranges_off;
+  uint64_t* num_cells;     // [n_pairs] out (K4), in (K3)
+  uint32_t* k4_status;     // [n_pairs] 0 ok, 1 too many matches
+  // K3 state
+  uint8_t* fill;           // K3 slab arena
+  const uint64_t* fill_off;  // per pair byte offset of the K3 slab
+  int32_t filter_clips;
+  // outputs (caller order)
+  int32_t* score;
+  uint32_t* xstart;
+  uint32_t* xend;
+  uint32_t* ystart;
+  uint32_t* yend;
+  uint32_t* n_ops;
+  uint64_t* ops_src;
+  uint32_t* clip_len;
+  uint32_t* status;
+  uint32_t* err_flag;
+  uint8_t* ops_scratch;
+  const uint64_t* ops_off;  // per pair: end of its ops region (ops are written backwards)
+};
+
+B2A_HD uint64_t sat_sub64(uint64_t a, uint64_t b) { return a > b ? a - b : 0; }
+B2A_HD uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+B2A_HD uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------ heap sort on 64-bit keys
+B2A_HD void sift_down(uint64_t* a, uint64_t start, uint64_t end) {
+  uint64_t root = start;
+  for (;;) {
+    uint64_t child = 2 * root + 1;
+    if (child > end) break;
+    if (child + 1 <= end && a[child] < a[child + 1]) child += 1;
+    if (a[root] < a[child]) {
+      const uint64_t t = a[root];
+      a[root] = a[child];
+      a[child] = t;
+      root = child;
+    } else {
+      break;
+    }
+  }
+}
+B2A_HD void heap_sort_u64(uint64_t* a, uint64_t n) {
+  if (n < 2) return;
+  for (uint64_t s = (n - 2) / 2 + 1; s-- > 0;) sift_down(a, s, n - 1);
+  for (uint64_t end = n - 1; end > 0; --end) {
+    const uint64_t t = a[0];
+    a[0] = a[end];
+    a[end] = t;
+    sift_down(a, 0, end - 1);
+  }
+}
+
+// ------------------------------------------------------------------ K4 slab layout
+struct PrevPtrD {  // sparse.rs:145-153, compared lexicographically (plane, score, d, id, x, y)
+  uint32_t plane, score, d, id, x, y;
+};
+B2A_HD bool prev_ge(const PrevPtrD& b, const PrevPtrD& a) {  // b >= a
+  if (b.plane != a.plane) return b.plane > a.plane;
+  if (b.score != a.score) return b.score > a.score;
+  if (b.d != a.d) return b.d > a.d;
+  if (b.id != a.id) return b.id > a.id;
+  if (b.x != a.x) return b.x > a.x;
+  return b.y >= a.y;
+}
+
+struct K4Slab {
+  uint64_t* matches;   // cap: (x << 32) | y, sorted
+  uint64_t* table;     // H entries: (hash_hi32 << 32) | (pos + 1); 0 = empty
+  uint64_t* events;    // 2*cap: (x << 40) | (y << 16)... see pack_event
+  uint32_t* ev_id;     // unused (ids are packed in events)
+  uint32_t* dp_score;  // cap
+  int32_t* dp_prev;    // cap
+  PrevPtrD* fen;       // cap + 2
+  uint32_t* ycoord;    // cap: sorted distinct end-y coordinates
+  uint32_t* path;      // cap
+  uint32_t H;
+};
+
+B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
+  uint32_t H = 16;
+  while (H < 2 * (short_len + 1)) H <<= 1;
+  uint64_t b = 0;
+  b += (uint64_t)cap * 8;          // matches
+  b += (uint64_t)H * 8;            // table
+  b += (uint64_t)2 * cap * 8 * 2;  // events (two u64 per event)
+  b += (uint64_t)cap * 4 * 2;      // dp
+  b += (uint64_t)(cap + 2) * sizeof(PrevPtrD);
+  b += (uint64_t)cap * 4 * 2;      // ycoord, path
+  return (b + 255) & ~255ull;
+}
+
+// ------------------------------------------------------------------ Band (ranges as u32 pairs)
+struct BandD {
+  uint32_t* r;  // r[2j] = start, r[2j+1] = end
+  uint64_t rows, cols;
+  B2A_HD void init(uint64_t m, uint64_t n) {  // Band::new, banded.rs:1061-1067
+    rows = m + 1;
+    cols = n + 1;
+    for (uint64_t j = 0; j < cols; ++j) {
+      r[2 * j] = (uint32_t)(m + 1);
+      r[2 * j + 1] = 0;
+    }
+  }
+  B2A_HD void lo(uint64_t j, uint64_t v) {
+    if ((uint64_t)r[2 * j] > v) r[2 * j] = (uint32_t)v;
+  }
+  B2A_HD void hi(uint64_t j, uint64_t v) {
+    if ((uint64_t)r[2 * j + 1] < v) r[2 * j + 1] = (uint32_t)v;
+  }
+  B2A_HD void add_kmer(uint64_t r0, uint64_t c0, uint64_t k, uint64_t w) {  // banded.rs:1071-1107
+    if (k == 0) return;
+    {
+      const uint64_t i = sat_sub64(r0, w);
+      for (uint64_t j = sat_sub64(c0, w); j < umin64(c0 + w + 1, cols); ++j) lo(j, i);
+    }
+    {
+      uint64_t i = sat_sub64(r0, w);
+      for (uint64_t j = umin64(c0 + w, cols); j < umin64(c0 + k + w, cols); ++j) {
+        lo(j, i);
+        i += 1;
+      }
+    }
+    {
+      uint64_t i = r0 + w + k;
+      uint64_t j = sat_sub64(c0 + k - 1, w);
+      for (;;) {
+        if (j <= sat_sub64(c0, w)) break;
+        j -= 1;
+        i -= 1;
+        hi(j, umin64(i, rows));
+      }
+    }
+    {
+      const uint64_t i = umin64(r0 + w + k, rows);
+      for (uint64_t j = sat_sub64(c0 + k - 1, w); j < umin64(c0 + k + w, cols); ++j) hi(j, i);
+    }
+  }
+  B2A_HD void add_entry(uint64_t r0, uint64_t c0, uint64_t w) {  // banded.rs:1111-1120
+    const uint64_t istart = sat_sub64(r0, w), iend = umin64(r0 + w + 1, rows);
+    for (uint64_t j = sat_sub64(c0, w); j < umin64(c0 + w + 1, cols); ++j) {
+      lo(j, istart);
+      hi(j, iend);
+    }
+  }
+  // banded.rs:1123-1137, u32 arithmetic.  Returns false where the reference would divide by zero.
+  B2A_HD bool add_gap(uint32_t s0, uint32_t s1, uint32_t e0, uint32_t e1, uint64_t w) {
+    const uint32_t nrows = e0 - s0, ncols = e1 - s1;
+    if (nrows > ncols) {
+      for (uint32_t rr = s0; rr < e0; ++rr) {
+        const uint32_t den = e0 - s0;
+        if (den == 0) return false;
+        const uint32_t c = s1 + (e1 - s1) * (rr - s0) / den;
+        add_entry(rr, c, w);
+      }
+    } else {
+      for (uint32_t c = s1; c < e1; ++c) {
+        const uint32_t den = e1 - s1;
+        if (den == 0) return false;
+        const uint32_t rr = s0 + (e0 - s0) * (c - s1) / den;
+        add_entry(rr, c, w);
+      }
+    }
+    return true;
+  }
+  B2A_HD bool set_boundaries(uint32_t st0, uint32_t st1, uint32_t en0, uint32_t en1, uint64_t k, uint64_t w,
+                             const DevScoring& sc) {  // banded.rs:1150-1276
+    const uint64_t lazy = 2 * k;
+    bool ok = true;
+    {
+      const uint64_t rr = st0, c = st1;
+      if (!(rr == 0 && c == 0)) {
+        int32_t to_start = rr > 0 ? sc.xclip_prefix : 0;
+        to_start += c > 0 ? sc.yclip_prefix : 0;
+        if (to_start == 0) {
+          const uint64_t d = umin64(lazy, umin64(rr, c));
+          add_kmer(rr - d, c - d, d, w);
+          ok &= add_gap((uint32_t)sat_sub64(rr, lazy), (uint32_t)sat_sub64(c, lazy), (uint32_t)(rr - d),
+                        (uint32_t)(c - d), w);
+        } else {
+          const int32_t diag = rr > c ? sc.xclip_prefix : (rr < c ? sc.yclip_prefix : 0);
+          if (diag == 0) {
+            const uint64_t d = umin64(rr, c);
+            add_kmer(rr - d, c - d, d, w);
+            const uint32_t a0 = (uint32_t)sat_sub64(rr, lazy), a1 = (uint32_t)sat_sub64(c, lazy);
+            const uint32_t b0 = (uint32_t)(rr - d), b1 = (uint32_t)(c - d);
+            if (a0 <= b0 && a1 <= b1) ok &= add_gap(a0, a1, b0, b1, w);
+          } else {
+            ok &= add_gap(0u, 0u, st0, st1, w);
+          }
+        }
+      }
+    }
+    {
+      const uint64_t rr = (uint64_t)en0 + k, c = (uint64_t)en1 + k;
+      if (!(rr == rows && c == cols)) {
+        int32_t from_end = rr == rows ? 0 : sc.xclip_suffix;
+        from_end += c == cols ? 0 : sc.yclip_suffix;
+        if (from_end == 0) {
+          const uint64_t d = umin64(lazy, umin64(rows - rr, cols - c));
+          add_kmer(rr, c, d, w);
+          const uint64_t r1 = umin64(rows, rr + d) - 1, c1 = umin64(cols, c + d) - 1;
+          const uint64_t r2 = umin64(rows, rr + lazy), c2 = umin64(cols, c + lazy);
+          if (r1 <= r2 && c1 <= c2) ok &= add_gap((uint32_t)r1, (uint32_t)c1, (uint32_t)r2, (uint32_t)c2, w);
+        } else {
+          const uint64_t dr = rows - rr, dc = cols - c;
+          const int32_t diag = dr > dc ? sc.xclip_suffix : (dr < dc ? sc.yclip_suffix : 0);
+          if (diag == 0) {
+            const uint64_t d = umin64(dr, dc);
+            add_kmer(rr, c, d, w);
+            const uint64_t r1 = umin64(rows, rr + d) - 1, c1 = umin64(cols, c + d) - 1;
+            const uint64_t r2 = umin64(rows, rr + lazy), c2 = umin64(cols, c + lazy);
+            if (r1 <= r2 && c1 <= c2) ok &= add_gap((uint32_t)r1, (uint32_t)c1, (uint32_t)r2, (uint32_t)c2, w);
+          } else {
+            ok &= add_gap((uint32_t)rr, (uint32_t)c, (uint32_t)rows, (uint32_t)cols, w);
+          }
+        }
+      }
+    }
+    return ok;
+  }
+  B2A_HD void full_matrix() {  // banded.rs:1369-1372
+    for (uint64_t j = 0; j < cols; ++j) {
+      r[2 * j] = 0;
+      r[2 * j + 1] = (uint32_t)rows;
+    }
+  }
+  B2A_HD uint64_t num_cells() const {  // banded.rs:1374-1380
+    uint64_t cells = 0;
+    for (uint64_t j = 0; j < cols; ++j) cells += sat_sub64(r[2 * j + 1], r[2 * j]);
+    return cells;
+  }
+};
+
+// ------------------------------------------------------------------ k-mer matches (exact)
+constexpr uint64_t HASH_B = 0x9E3779B97F4A7C15ull | 1ull;
+
+// all (i, j) with x[i..i+k] == y[j..j+k] as (i << 32 | j), sorted; returns count or ~0 on overflow
+B2A_HD uint64_t find_kmer_matches_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint64_t k,
+                                    uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap) {
+  const uint64_t nx = sat_sub64(m + 1, k), ny = sat_sub64(n + 1, k);
+  if (nx == 0 || ny == 0 || k == 0) return 0;
+  const bool hash_x = m <= n;  // hash the shorter one
+  const uint8_t* hs = hash_x ? x : y;
+  const uint8_t* ps = hash_x ? y : x;
+  const uint64_t nh = hash_x ? nx : ny, np = hash_x ? ny : nx;
+  for (uint32_t s = 0; s < H; ++s) table[s] = 0;
+  uint64_t bk = 1;  // B^(k-1)
+  for (uint64_t t = 1; t < k; ++t) bk *= HASH_B;
+  auto mix = [](uint64_t h) { return h ^ (h >> 29); };
+  uint64_t h = 0;
+  for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(hs[t] + 1);
+  const uint32_t mask = H - 1;
+  for (uint64_t i = 0; i < nh; ++i) {
+    const uint64_t hm = mix(h);
+    uint32_t slot = (uint32_t)hm & mask;
+    while (table[slot] != 0) slot = (slot + 1) & mask;
+    table[slot] = ((hm >> 32) << 32) | (i + 1);
+    if (i + 1 < nh) h = (h - (uint64_t)(hs[i] + 1) * bk) * HASH_B + (uint64_t)(hs[i + k] + 1);
+  }
+  uint64_t cnt = 0;
+  h = 0;
+  for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(ps[t] + 1);
+  for (uint64_t j = 0; j < np; ++j) {
+    const uint64_t hm = mix(h);
+    uint32_t slot = (uint32_t)hm & mask;
+    while (table[slot] != 0) {
+      const uint64_t e = table[slot];
+      if ((e >> 32) == (hm >> 32)) {
+        const uint64_t i = (e & 0xffffffffull) - 1;
+        bool same = true;
+        for (uint64_t t = 0; t < k; ++t)
+          if (hs[i + t] != ps[j + t]) {
+            same = false;
+            break;
+          }
+        if (same) {
+          if (cnt >= cap) return ~0ull;
+          out[cnt++] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
+        }
+      }
+      slot = (slot + 1) & mask;
+    }
+    if (j + 1 < np) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
+  }
+  heap_sort_u64(out, cnt);
+  return cnt;
+}
+
+// ------------------------------------------------------------------ sdpkpp, sparse.rs:188-295
+// events are two u64: key0 = (x << 32 | y), key1 = id; sorted by (x, y, id).
+B2A_HD uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {  // first index with a[i] >= v
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) / 2;
+    if (a[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// returns path length (path[] = indices into matches), 0 if no matches
+B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint32_t match_score, int32_t gap_open,
+                         int32_t gap_extend, uint64_t* ev /*4*nm u64*/, uint32_t* dp_score, int32_t* dp_prev,
+                         PrevPtrD* fen, uint32_t* ycoord, uint32_t* path) {
+  if (nm == 0) return 0;
+  const uint32_t go = (uint32_t)(-gap_open), ge = (uint32_t)(-gap_extend);
+  // events sorted lexicographically by (x, y, id): pack (x, y) in one key and sort pairs by two passes:
+  // sort by combined 64-bit key (x << 32 | y) with id as tie-break -> id < 2*nm <= 2^31; use a stable
+  // trick: key = (x,y) and secondary array; simplest exact way: sort 128-bit items by heap sort on
+  // an index permutation is costly, so encode id into a second heap sort pass:
+  //   ends (id < nm) sort before starts (id >= nm) at equal (x, y); among equal (x, y, kind) ids are
+  //   unique per match and (x, y) is unique per match for starts and for ends, so (x, y, kind) is a
+  //   total order: key = (x << 33) | (y << 1) | kind needs 65 bits when x,y use 32 -> lengths are
+  //   limited to 2^24 by the engine, so x,y < 2^25 and the key fits.
+  for (uint32_t idx = 0; idx < nm; ++idx) {
+    const uint64_t x = matches[idx] >> 32, y = matches[idx] & 0xffffffffull;
+    ev[2 * idx] = (x << 33) | (y << 1) | 1ull;              // start (id = idx + nm)
+    ev[2 * idx + 1] = ((x + k) << 33) | ((y + k) << 1);     // end   (id = idx)
+  }
+  heap_sort_u64(ev, 2ull * nm);
+  // distinct end-y coordinates, ascending (the only indices ever set in the prefix-max tree)
+  uint32_t ny = 0;
+  {
+    uint64_t* tmp = ev + 2ull * nm;  // scratch half
+    for (uint32_t idx = 0; idx < nm; ++idx) tmp[idx] = (matches[idx] & 0xffffffffull) + k;
+    heap_sort_u64(tmp, nm);
+    for (uint32_t t = 0; t < nm; ++t)
+      if (ny == 0 || ycoord[ny - 1] != (uint32_t)tmp[t]) ycoord[ny++] = (uint32_t)tmp[t];
+  }
+  for (uint32_t t = 0; t <= ny + 1; ++t) fen[t] = PrevPtrD{0, 0, 0, 0, 0, 0};
+  for (uint32_t t = 0; t < nm; ++t) {
+    dp_score[t] = 0;
+    dp_prev[t] = 0;
+  }
+  uint32_t best_score = k;
+  int32_t best_idx = 0;
+  auto dp_gt = [](uint32_t s1, int32_t p1, uint32_t s2, int32_t p2) {  // (s1,p1) > (s2,p2)
+    return s1 != s2 ? s1 > s2 : p1 > p2;
+  };
+  for (uint64_t e = 0; e < 2ull * nm; ++e) {
+    const uint64_t key = ev[e];
+    const bool is_start = (key & 1ull) != 0;
+    const uint32_t e0 = (uint32_t)(key >> 33), e1 = (uint32_t)((key >> 1) & 0xffffffffull);
+    // the match this event belongs to: binary search its start coordinates in the sorted matches
+    const uint64_t want = is_start ? (((uint64_t)e0 << 32) | e1) : (((uint64_t)(e0 - k) << 32) | (e1 - k));
+    uint32_t lo = 0, hi = nm;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) / 2;
+      if (matches[mid] < want) lo = mid + 1;
+      else hi = mid;
+    }
+    const uint32_t p = lo;
+    if (is_start) {
+      dp_score[p] = k * match_score;
+      dp_prev[p] = -1;
+      // max_col_dp.get(j): prefix max over inserted coordinates <= e1
+      PrevPtrD best{0, 0, 0, 0, 0, 0};
+      {
+        uint32_t cnt = lower_bound_u32(ycoord, ny, e1 + 1);  // number of coordinates <= e1
+        uint32_t idx = cnt;                                  // Fenwick positions are 1-based
+        while (idx > 0) {
+          if (prev_ge(fen[idx], best)) best = fen[idx];
+          idx -= idx & (0u - idx);
+        }
+      }
+      if (best.score > 0) {
+        const uint32_t g0 = e0 - best.x, g1 = e1 - best.y;
+        const uint32_t gap = g0 > g1 ? g0 : g1;
+        const uint32_t pen = gap > 0 ? go + gap * ge : 0;
+        const uint32_t sum = best.score + k * match_score;
+        const uint32_t ns = sum > pen ? sum - pen : 0;
+        if (dp_gt(ns, (int32_t)best.id, dp_score[p], dp_prev[p])) {
+          dp_score[p] = ns;
+          dp_prev[p] = (int32_t)best.id;
+        }
+        if (dp_gt(dp_score[p], (int32_t)p, best_score, best_idx)) {
+          best_score = dp_score[p];
+          best_idx = (int32_t)p;
+        }
+      }
+    } else {
+      if (e0 > k && e1 > k) {
+        const uint64_t cw = ((uint64_t)(e0 - k - 1) << 32) | (e1 - k - 1);
+        uint32_t l2 = 0, h2 = nm;
+        while (l2 < h2) {
+          const uint32_t mid = (l2 + h2) / 2;
+          if (matches[mid] < cw) l2 = mid + 1;
+          else h2 = mid;
+        }
+        if (l2 < nm && matches[l2] == cw) {
+          const uint32_t cs = dp_score[l2] + match_score;
+          if (dp_gt(cs, (int32_t)l2, dp_score[p], dp_prev[p])) {
+            dp_score[p] = cs;
+            dp_prev[p] = (int32_t)l2;
+          }
+          if (dp_gt(dp_score[p], (int32_t)p, best_score, best_idx)) {
+            best_score = dp_score[p];
+            best_idx = (int32_t)p;
+          }
+        }
+      }
+      PrevPtrD pf;
+      pf.d = e0 + e1;
+      pf.plane = dp_score[p] + pf.d * ge;
+      pf.score = dp_score[p];
+      pf.id = p;
+      pf.x = e0;
+      pf.y = e1;
+      uint32_t idx = lower_bound_u32(ycoord, ny, e1) + 1;  // 1-based rank of this coordinate
+      while (idx <= ny) {
+        if (prev_ge(pf, fen[idx])) fen[idx] = pf;
+        idx += idx & (0u - idx);
+      }
+    }
+  }
+  uint32_t np = 0;
+  int32_t pm = best_idx;
+  while (pm >= 0 && np < nm) {
+    path[np++] = (uint32_t)pm;
+    pm = dp_prev[pm];
+  }
+  for (uint32_t a = 0, b = np ? np - 1 : 0; a < b; ++a, --b) {
+    const uint32_t t = path[a];
+    path[a] = path[b];
+    path[b] = t;
+  }
+  return np;
+}
+
+// ------------------------------------------------------------------ K4: Band::create for one pair
+// returns status: 0 ok, 1 too many matches (capacity), 2 reference would panic (divide by zero)
+B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint32_t k, uint32_t w,
+                              const DevScoring& sc, int32_t has_match_scores, uint8_t* slab, uint32_t cap,
+                              uint32_t* ranges, uint64_t* cells_out) {
+  const uint64_t short_len = m <= n ? m : n;
+  uint32_t H = 16;
+  while (H < 2 * (short_len + 1)) H <<= 1;
+  uint64_t* matches = reinterpret_cast<uint64_t*>(slab);
+  uint64_t* table = matches + cap;
+  uint64_t* ev = table + H;
+  uint32_t* dp_score = reinterpret_cast<uint32_t*>(ev + 4ull * cap);
+  int32_t* dp_prev = reinterpret_cast<int32_t*>(dp_score + cap);
+  PrevPtrD* fen = reinterpret_cast<PrevPtrD*>(dp_prev + cap);
+  uint32_t* ycoord = reinterpret_cast<uint32_t*>(fen + cap + 2);
+  uint32_t* path = ycoord + cap;
+  BandD band;
+  band.r = ranges;
+  band.init(m, n);
+  const uint64_t nm64 = find_kmer_matches_d(x, m, y, n, k, table, H, matches, cap);
+  if (nm64 == ~0ull) {
+    *cells_out = 0;
+    return 1;
+  }
+  const uint32_t nm = (uint32_t)nm64;
+  uint32_t status = 0;
+  if (nm == 0) {
+    band.full_matrix();  // banded.rs:1309-1313
+  } else {
+    const int32_t ms = has_match_scores ? sc.match_score : BANDED_DEFAULT_MATCH_SCORE;  // 1315-1318
+    const uint32_t np = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score, dp_prev,
+                                 fen, ycoord, path);
+    // create_from_match_path, banded.rs:1330-1367
+    const uint64_t first = matches[path[0]], last = matches[path[np - 1]];
+    if (!band.set_boundaries((uint32_t)(first >> 32), (uint32_t)first, (uint32_t)(last >> 32), (uint32_t)last, k, w, sc))
+      status = 2;
+    bool has_prev = false;
+    uint32_t p0 = 0, p1 = 0;
+    for (uint32_t t = 0; t < np; ++t) {
+      const uint64_t cur = matches[path[t]];
+      const uint32_t c0 = (uint32_t)(cur >> 32), c1 = (uint32_t)cur;
+      if (has_prev && c0 == p0 + 1 && c1 == p1 + 1) {
+        band.add_entry((uint64_t)p0 + k, (uint64_t)p1 + k, w);
+      } else {
+        if (has_prev)
+          if (!band.add_gap(p0 + (k - 1), p1 + (k - 1), c0, c1, w)) status = 2;
+        band.add_kmer(c0, c1, k, w);
+      }
+      p0 = c0;
+      p1 = c1;
+      has_prev = true;
+    }
+  }
+  *cells_out = band.num_cells();
+  return status;
+}
+
+// ------------------------------------------------------------------ K3: compute_alignment for one pair
+// K3 slab of one pair (byte offsets; every array starts 16-byte aligned)
+struct K3Layout {
+  uint64_t colstart, S, Sn, Ly, Lx, row0, rowm, col0, coln, cells, total;
+};
+B2A_HD uint64_t al16(uint64_t v) { return (v + 15) & ~15ull; }
+B2A_HD K3Layout k3_layout(uint64_t m, uint64_t n, uint64_t ncells) {
+  K3Layout L;
+  uint64_t b = 0;
+  L.colstart = b; b = al16(b + (n + 2) * 4);
+  L.S = b;        b = al16(b + 6 * (m + 1) * 4);   // S[2], I[2], D[2]
+  L.Sn = b;       b = al16(b + (m + 1) * 4);
+  L.Ly = b;       b = al16(b + (m + 1) * 4);
+  L.Lx = b;       b = al16(b + (n + 1) * 4);
+  L.row0 = b;     b = al16(b + (n + 1) * 2);
+  L.rowm = b;     b = al16(b + (n + 1) * 2);
+  L.col0 = b;     b = al16(b + (m + 1) * 2);
+  L.coln = b;     b = al16(b + (m + 1) * 2);
+  L.cells = b;    b = al16(b + ncells * 2);
+  L.total = (b + 255) & ~255ull;
+  return L;
+}
+B2A_HD uint64_t k3_slab_bytes(uint64_t m, uint64_t n, uint64_t cells) {
+  // a refused band (> MAX_CELLS) needs no state at all
+  return cells > BANDED_MAX_CELLS ? 256 : k3_layout(m, n, cells).total;
+}
+
+struct BandedOut {
+  int32_t score;
+  uint32_t xstart, xend, ystart, yend, xlen, ylen, n_ops, status;
+  uint32_t clip[4];
+};
+
+template <class ScoreFn>
+B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, const DevScoring& sc,
+                             ScoreFn score, const uint32_t* rng, uint64_t num_cells, uint8_t* slab,
+                             bool filter_clips, uint8_t* ops_end, BandedOut& out) {
+  out.status = 0;
+  out.n_ops = 0;
+  for (int q = 0; q < 4; ++q) out.clip[q] = 0;
+  if (num_cells > BANDED_MAX_CELLS) {  // banded.rs:407-420
+    out.score = MIN_SCORE;
+    out.xstart = out.xend = out.ystart = out.yend = out.xlen = out.ylen = 0;
+    return;
+  }
+  out.xlen = (uint32_t)m;
+  out.ylen = (uint32_t)n;
+  const K3Layout L = k3_layout(m, n, num_cells);
+  uint32_t* colstart = reinterpret_cast<uint32_t*>(slab + L.colstart);
+  int32_t* S0 = reinterpret_cast<int32_t*>(slab + L.S);
+  int32_t* Sarr[2] = {S0, S0 + (m + 1)};
+  int32_t* Iarr[2] = {S0 + 2 * (m + 1), S0 + 3 * (m + 1)};
+  int32_t* Darr[2] = {S0 + 4 * (m + 1), S0 + 5 * (m + 1)};
+  int32_t* Sn = reinterpret_cast<int32_t*>(slab + L.Sn);
+  uint32_t* Ly = reinterpret_cast<uint32_t*>(slab + L.Ly);
+  uint32_t* Lx = reinterpret_cast<uint32_t*>(slab + L.Lx);
+  uint16_t* row0 = reinterpret_cast<uint16_t*>(slab + L.row0);
+  uint16_t* rowm = reinterpret_cast<uint16_t*>(slab + L.rowm);
+  uint16_t* col0 = reinterpret_cast<uint16_t*>(slab + L.col0);
+  uint16_t* coln = reinterpret_cast<uint16_t*>(slab + L.coln);
+  uint16_t* cells = reinterpret_cast<uint16_t*>(slab + L.cells);
+  // init (banded.rs:423-438): only the cells that can ever be non-START are stored
+  {
+    uint32_t acc = 0;
+    for (uint64_t j = 0; j <= n; ++j) {
+      colstart[j] = acc;
+      acc += (uint32_t)sat_sub64(rng[2 * j + 1], rng[2 * j]);
+    }
+    colstart[n + 1] = acc;
+  }
+  for (int kk = 0; kk < 2; ++kk)
+    for (uint64_t i = 0; i <= m; ++i) {
+      Sarr[kk][i] = MIN_SCORE;
+      Iarr[kk][i] = MIN_SCORE;
+      Darr[kk][i] = MIN_SCORE;
+    }
+  for (uint64_t i = 0; i <= m; ++i) {
+    Sn[i] = MIN_SCORE;
+    Ly[i] = 0;
+    col0[i] = 0;
+    coln[i] = 0;
+  }
+  for (uint64_t j = 0; j <= n; ++j) {
+    Lx[j] = 0;
+    row0[j] = 0;
+    rowm[j] = 0;
+  }
+  // traceback cell access: pointer for writes (nullptr = a cell the reference never writes there),
+  // value for reads (untouched cells read as 0 = START in every nibble)
+  auto cellp = [&](uint64_t i, uint64_t j) -> uint16_t* {
+    if (i == 0) return &row0[j];
+    if (i == m) return &rowm[j];
+    if (j == 0) return &col0[i];
+    if (j == n) return &coln[i];
+    const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
+    if (i >= s && i < e) return &cells[colstart[j] + (i - s)];
+    return nullptr;
+  };
+  auto rd = [&](uint64_t i, uint64_t j) -> uint32_t {
+    uint16_t* p = cellp(i, j);
+    return p ? (uint32_t)*p : 0u;
+  };
+  auto set_s = [&](uint64_t i, uint64_t j, uint32_t v) {
+    uint16_t* p = cellp(i, j);
+    if (p) *p = (uint16_t)((*p & ~0x0F00u) | (v << 8));
+  };
+  auto set_i = [&](uint64_t i, uint64_t j, uint32_t v) {
+    uint16_t* p = cellp(i, j);
+    if (p) *p = (uint16_t)((*p & ~0x000Fu) | v);
+  };
+  auto put = [&](uint64_t i, uint64_t j, uint32_t c) {
+    uint16_t* p = cellp(i, j);
+    if (p) *p = (uint16_t)c;
+  };
+  const int32_t go = sc.gap_open, ge = sc.gap_extend;
+  const int32_t xp = sc.xclip_prefix, xs = sc.xclip_suffix, yp = sc.yclip_prefix, ys = sc.yclip_suffix;
+  {  // j = 0, banded.rs:440-509
+    int32_t* S = Sarr[0];
+    int32_t* I = Iarr[0];
+    const uint64_t i_start = rng[0], i_end = rng[1];
+    if (i_start == 0) S[0] = 0;
+    for (uint64_t i = umax64(1, i_start); i < i_end; ++i) {
+      uint32_t ib, sb = TB_START;
+      if (i == 1) {
+        I[i] = go;
+        ib = TB_START;
+      } else {
+        const int32_t i_score = go + ge * ((int32_t)i - 1), c_score = xp + go;
+        if (i_score > c_score) {
+          I[i] = i_score;
+          ib = TB_INS;
+        } else {
+          I[i] = c_score;
+          ib = TB_XCLIP_PREFIX;
+        }
+      }
+      if (i == m) sb = TB_XCLIP_SUFFIX;
+      if (I[i] > S[i]) {
+        S[i] = I[i];
+        sb = TB_INS;
+      }
+      if (xp > S[i]) {
+        S[i] = xp;
+        sb = TB_XCLIP_PREFIX;
+      }
+      if (S[i] + xs > S[m]) {
+        S[m] = S[i] + xs;
+        Lx[0] = (uint32_t)(m - i);
+        set_s(m, 0, TB_XCLIP_SUFFIX);
+      }
+      put(i, 0, ib | (TB_START << 4) | (sb << 8));
+    }
+    for (uint64_t i = i_end; i < umin64(m + 1, rng[2 * umin64(n, 1) + 1]); ++i) {
+      S[i] = MIN_SCORE;
+      I[i] = MIN_SCORE;
+    }
+    if (i_end < m + 1) S[m] = MIN_SCORE;
+    if (yp > ys) {
+      Sn[0] = yp;
+      set_s(0, n, TB_YCLIP_PREFIX);
+    } else {
+      Sn[0] = ys;
+      Ly[0] = (uint32_t)n;
+      set_s(0, n, TB_YCLIP_SUFFIX);
+    }
+  }
+  for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
+    int32_t* S = Sarr[j % 2];
+    int32_t* I = Iarr[j % 2];
+    int32_t* D = Darr[j % 2];
+    const int32_t* Sp = Sarr[1 - j % 2];
+    const int32_t* Dp = Darr[1 - j % 2];
+    const uint64_t i_start = rng[2 * j], i_end = rng[2 * j + 1];
+    if (i_start == 0) {
+      uint32_t db, sb;
+      I[0] = MIN_SCORE;
+      if (j == 1) {
+        D[0] = go;
+        db = TB_START;
+      } else {
+        const int32_t d_score = go + ge * ((int32_t)j - 1), c_score = yp + go;
+        if (d_score > c_score) {
+          D[0] = d_score;
+          db = TB_DEL;
+        } else {
+          D[0] = c_score;
+          db = TB_YCLIP_PREFIX;
+        }
+      }
+      if (D[0] > yp) {
+        S[0] = D[0];
+        sb = TB_DEL;
+      } else {
+        S[0] = yp;
+        sb = TB_YCLIP_PREFIX;
+      }
+      if (S[0] + ys > Sn[0]) {
+        Sn[0] = S[0] + ys;
+        Ly[0] = (uint32_t)(n - j);
+        set_s(0, n, TB_YCLIP_SUFFIX);
+      }
+      put(0, j, (db << 4) | (sb << 8));
+    }
+    for (uint64_t i = sat_sub64(i_start, 1); i < i_start; ++i) {
+      S[i] = MIN_SCORE;
+      I[i] = MIN_SCORE;
+      D[i] = MIN_SCORE;
+    }
+    S[m] = MIN_SCORE;
+    const uint8_t q = y[j - 1];
+    const int32_t xclip_score = xp + imax(j == n ? imax(yp, Sn[0]) : yp, go + ge * ((int32_t)j - 1));
+    for (uint64_t i = umax64(1, i_start); i < i_end; ++i) {
+      const uint8_t p = x[i - 1];
+      uint32_t ib, db, sb = TB_START;
+      const int32_t m_score = Sp[i - 1] + score(p, q);
+      const int32_t i_score = I[i - 1] + ge;
+      int32_t s_score = S[i - 1] + go;
+      int32_t best_i;
+      if (i_score > s_score) {
+        best_i = i_score;
+        ib = TB_INS;
+      } else {
+        best_i = s_score;
+        ib = (rd(i - 1, j) >> 8) & 15u;
+      }
+      if (j == n) {
+        const int32_t clip_score = Sn[i - 1] + go;
+        if (clip_score > best_i) {
+          best_i = clip_score;
+          ib = TB_YCLIP_SUFFIX;
+        }
+      }
+      const int32_t d_score = Dp[i] + ge;
+      s_score = Sp[i] + go;
+      int32_t best_d;
+      if (d_score > s_score) {
+        best_d = d_score;
+        db = TB_DEL;
+      } else {
+        best_d = s_score;
+        db = (rd(i, j - 1) >> 8) & 15u;
+      }
+      if (i == m) {
+        sb = TB_XCLIP_SUFFIX;
+      } else {
+        S[i] = MIN_SCORE;
+      }
+      int32_t best = S[i];
+      if (m_score > best) {
+        best = m_score;
+        sb = (p == q) ? TB_MATCH : TB_SUBST;
+      }
+      if (best_i > best) {
+        best = best_i;
+        sb = TB_INS;
+      }
+      if (best_d > best) {
+        best = best_d;
+        sb = TB_DEL;
+      }
+      if (xclip_score > best) {
+        best = xclip_score;
+        sb = TB_XCLIP_PREFIX;
+      }
+      const int32_t yclip_score = yp + go + ge * ((int32_t)i - 1);
+      if (yclip_score > best) {
+        best = yclip_score;
+        sb = TB_YCLIP_PREFIX;
+      }
+      S[i] = best;
+      I[i] = best_i;
+      D[i] = best_d;
+      if (S[i] + xs > S[m]) {
+        S[m] = S[i] + xs;
+        Lx[j] = (uint32_t)(m - i);
+        set_s(m, j, TB_XCLIP_SUFFIX);
+      }
+      if (S[i] + ys > Sn[i]) {
+        Sn[i] = S[i] + ys;
+        Ly[i] = (uint32_t)(n - j);
+        set_s(i, n, TB_YCLIP_SUFFIX);
+      }
+      put(i, j, ib | (db << 4) | (sb << 8));
+    }
+    if (S[m] + ys > Sn[m]) {
+      Sn[m] = S[m] + ys;
+      Ly[m] = (uint32_t)(n - j);
+      set_s(m, n, TB_YCLIP_SUFFIX);
+    }
+    if (i_end < m + 1) {
+      set_s(m, j, TB_XCLIP_SUFFIX);
+      S[m] = MIN_SCORE;
+    }
+    for (uint64_t i = i_end; i < umin64(m + 1, rng[2 * umin64(n, j + 1) + 1]); ++i) {
+      S[i] = MIN_SCORE;
+      I[i] = MIN_SCORE;
+      D[i] = MIN_SCORE;
+    }
+  }
+  {
+    int32_t* S = Sarr[n % 2];
+    int32_t* I = Iarr[n % 2];
+    const uint64_t bs = rng[2 * n], be = rng[2 * n + 1];
+    for (uint64_t i = 0; i <= m; ++i) {  // banded.rs:684-701
+      if (i != m && (i < bs || i > be)) S[i] = MIN_SCORE;
+      if (Sn[i] > S[i]) {
+        S[i] = Sn[i];
+        set_s(i, n, TB_YCLIP_SUFFIX);
+      }
+      if (S[i] + xs > S[m]) {
+        S[m] = S[i] + xs;
+        Lx[n] = (uint32_t)(m - i);
+        set_s(m, n, TB_XCLIP_SUFFIX);
+      }
+    }
+    for (uint64_t i = umax64(1, bs); i < be; ++i) {  // banded.rs:705-723
+      const int32_t s_score = S[i - 1] + go;
+      if (s_score > I[i]) {
+        I[i] = s_score;
+        set_i(i, n, (rd(i - 1, n) >> 8) & 15u);
+      }
+      if (s_score > S[i]) {
+        S[i] = s_score;
+        set_s(i, n, TB_INS);
+        if (S[i] + xs > S[m]) {
+          S[m] = S[i] + xs;
+          Lx[n] = (uint32_t)(m - i);
+          set_s(m, n, TB_XCLIP_SUFFIX);
+        }
+      }
+    }
+    for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:725-744
+      const int32_t d_score = go + ge * ((int32_t)j - 1);
+      set_s(0, j, d_score > yp ? TB_DEL : TB_YCLIP_PREFIX);
+      if (j == n) {
+        int32_t best_score = imax(d_score, yp);
+        if (ys > best_score) {
+          best_score = ys;
+          set_s(0, j, TB_YCLIP_SUFFIX);
+        }
+        if (xs + best_score > S[m]) {
+          S[m] = xs + best_score;
+          Lx[n] = (uint32_t)m;
+          set_s(m, n, TB_XCLIP_SUFFIX);
+        }
+      }
+    }
+    for (uint64_t i = 1; i <= m; ++i) {  // banded.rs:746-765
+      const int32_t c_score = go + ge * ((int32_t)i - 1);
+      set_s(i, 0, c_score > xp ? TB_INS : TB_XCLIP_PREFIX);
+      if (i == m) {
+        int32_t best_score = imax(c_score, xp);
+        if (xs > best_score) {
+          best_score = xs;
+          set_s(i, 0, TB_XCLIP_SUFFIX);
+        }
+        if (ys + best_score > S[m]) {
+          S[m] = ys + best_score;
+          Ly[m] = (uint32_t)n;
+          set_s(m, n, TB_YCLIP_SUFFIX);
+        }
+      }
+    }
+    out.score = S[m];
+  }
+  // walk, banded.rs:767-855 (ops written backwards).  A legitimate walk emits at most m + n + 4 ops; the
+  // reference can loop forever on some custom clip settings (an Xclip/Yclip of length 0): that is
+  // reported as status 1 instead of hanging.
+  uint64_t i = m, j = n;
+  uint32_t xstart = 0, ystart = 0, xend = (uint32_t)m, yend = (uint32_t)n;
+  uint32_t nops = 0, nclip = 0, clips[4] = {0, 0, 0, 0};
+  const uint64_t ops_cap = m + n + 4;
+  bool overflow = false;
+  auto push = [&](uint32_t code) {
+    if (nops >= ops_cap) {
+      overflow = true;
+      return;
+    }
+    *(--ops_end) = (uint8_t)code;
+    ++nops;
+  };
+  auto push_clip = [&](uint32_t code, uint32_t len) {
+    if (!filter_clips) {
+      push(code);
+      if (nclip < 4) clips[nclip] = len;
+      ++nclip;
+    }
+  };
+  uint32_t layer = (rd(i, j) >> 8) & 15u;
+  uint64_t guard = 4 * (m + n) + 64;
+  while (layer != TB_START) {
+    if (guard-- == 0 || overflow) {
+      out.status = 1;
+      break;
+    }
+    uint32_t next;
+    if (layer == TB_INS) {
+      push(3);
+      next = rd(i, j) & 15u;
+      if (i == 0) { out.status = 1; break; }
+      i -= 1;
+    } else if (layer == TB_DEL) {
+      push(2);
+      next = (rd(i, j) >> 4) & 15u;
+      if (j == 0) { out.status = 1; break; }
+      j -= 1;
+    } else if (layer == TB_MATCH || layer == TB_SUBST) {
+      push(layer == TB_MATCH ? 0 : 1);
+      if (i == 0 || j == 0) { out.status = 1; break; }
+      next = (rd(i - 1, j - 1) >> 8) & 15u;
+      i -= 1;
+      j -= 1;
+    } else if (layer == TB_XCLIP_PREFIX) {
+      push_clip(4, (uint32_t)i);
+      xstart = (uint32_t)i;
+      i = 0;
+      next = (rd(0, j) >> 8) & 15u;
+    } else if (layer == TB_XCLIP_SUFFIX) {
+      push_clip(4, Lx[j]);
+      if (Lx[j] > i) { out.status = 1; break; }
+      i -= Lx[j];
+      xend = (uint32_t)i;
+      next = (rd(i, j) >> 8) & 15u;
+    } else if (layer == TB_YCLIP_PREFIX) {
+      push_clip(5, (uint32_t)j);
+      ystart = (uint32_t)j;
+      j = 0;
+      next = (rd(i, 0) >> 8) & 15u;
+    } else if (layer == TB_YCLIP_SUFFIX) {
+      push_clip(5, Ly[i]);
+      if (Ly[i] > j) { out.status = 1; break; }
+      j -= Ly[i];
+      yend = (uint32_t)j;
+      next = (rd(i, j) >> 8) & 15u;
+    } else {
+      out.status = 1;
+      break;
+    }
+    layer = next;
+  }
+  if (out.status == 0) {
+    if (i != 0) {  // banded.rs:834-844
+      const int32_t i_score = go + ge * ((int32_t)i - 1);
+      if (i_score > xp) {
+        for (uint64_t t = 0; t < i; ++t) push(3);
+        xstart = 0;
+      } else {
+        push_clip(4, (uint32_t)i);
+        xstart = (uint32_t)i;
+      }
+    }
+    if (j != 0) {  // banded.rs:845-855
+      const int32_t d_score = go + ge * ((int32_t)j - 1);
+      if (d_score > yp) {
+        for (uint64_t t = 0; t < j; ++t) push(2);
+        ystart = 0;
+      } else {
+        push_clip(5, (uint32_t)j);
+        ystart = (uint32_t)j;
+      }
+    }
+  }
+  if (overflow) out.status = 1;
+  if (nclip > 4) out.status = 1;
+  out.xstart = xstart;
+  out.xend = xend;
+  out.ystart = ystart;
+  out.yend = yend;
+  out.n_ops = nops;
+  const uint32_t nc = nclip > 4 ? 4 : nclip;
+  for (uint32_t q = 0; q < 4; ++q) out.clip[q] = q < nc ? clips[nc - 1 - q] : 0u;
+}
+
+#if defined(__CUDACC__)
+
+__global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint32_t n_wave) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_wave) return;
+  const uint64_t p = (uint64_t)prm.pair_lo + t;
+  const uint64_t m = prm.x_len[p], n = prm.y_len[p];
+  uint64_t cells = 0;
+  const uint32_t st = band_create_d(prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.k, prm.w, prm.sc,
+                                    prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride, prm.cap_matches,
+                                    prm.ranges + prm.ranges_off[t] / 4, &cells);
+  prm.num_cells[p] = cells;
+  prm.k4_status[p] = st;
+}
+
+__global__ void __launch_bounds__(128) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_wave) return;
+  const uint64_t p = (uint64_t)prm.pair_lo + t;
+  const uint64_t m = prm.x_len[p], n = prm.y_len[p];
+  BandedOut o;
+  const uint32_t k4 = prm.k4_status[p];
+  if (k4 != 0) {
+    o = BandedOut{};
+    o.status = 1 + k4;
+  } else {
+    const uint8_t* cm = prm.codemap;
+    const int32_t* lut = prm.lut;
+    const int32_t alpha = prm.sc.alpha;
+    const DevScoring sc = prm.sc;
+    uint32_t* err = prm.err_flag;
+    auto score = [=](uint8_t a, uint8_t b) -> int32_t {
+      if (alpha) {
+        int32_t ca = cm[a], cb = cm[b];
+        if (ca == 0xFF || cb == 0xFF) {  // byte outside the scoring alphabet: flag, stay in bounds
+          atomicOr(err, 4u);
+          ca = cb = 0;
+        }
+        return lut[ca * alpha + cb];
+      }
+      return a == b ? sc.match_score : sc.mismatch_score;
+    };
+    banded_compute_d(prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc, score,
+                     prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p], prm.fill + prm.fill_off[t],
+                     prm.filter_clips != 0, prm.ops_scratch + prm.ops_off[p], o);
+  }
+  prm.score[p] = o.score;
+  prm.xstart[p] = o.xstart;
+  prm.xend[p] = o.xend;
+  prm.ystart[p] = o.ystart;
+  prm.yend[p] = o.yend;
+  prm.n_ops[p] = o.n_ops;
+  prm.ops_src[p] = prm.ops_off[p] - o.n_ops;
+  prm.status[p] = o.status;
+  if (o.status) atomicOr(prm.err_flag, o.status == 2 ? 2u : 1u);
+  for (int q = 0; q < 4; ++q) prm.clip_len[4 * p + q] = o.clip[q];
+}
+
+#endif
+
+}  // namespace b2a

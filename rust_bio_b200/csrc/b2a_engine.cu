@@ -18,6 +18,7 @@
 #include "b2a_kernels.cuh"
 #include "b2a_plan.h"
 #include "b2a_walk.cuh"
+#include "b2a_banded.cuh"
 
 using namespace b2a;
 
@@ -89,7 +90,8 @@ struct b2a_engine {
 
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
-      d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records;
+      d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_bcells, d_bstatus,
+      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> wave_ev;  // 3 per wave: fill start, fill stop / walk start, walk stop
   uint32_t launches = 0;
@@ -186,7 +188,9 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
                     &e->d_opsscratch, &e->d_lut, &e->d_codemap, &e->d_ctl, &e->d_score, &e->d_xs,
                     &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
-                    &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records};
+                    &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_bcells,
+                    &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill,
+                    &e->d_bfoff};
   for (DevBuf* b : bufs) b->release();
   for (auto& v : e->ev)
     if (v) cudaEventDestroy(v);
@@ -220,7 +224,12 @@ int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t G, int32_t R) {
   return B2A_OK;
 }
 
-int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const b2a_pairs* pairs) {
+}  // extern "C"
+
+// Shared front half of a batch: validation (the reference's constructor asserts), clip presets, the
+// i32 range guard, alphabet discovery + LUT, and the upload of the caller's blob.
+static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, const b2a_pairs* pairs,
+                           uint32_t& maxm, uint32_t& maxn, int64_t& score_bound) {
   if (!e || !s || !pairs) return B2A_E_INVALID;
   e->staged = e->ran = false;
   if (mode < 0 || mode > 3) return e->fail(B2A_E_INVALID, "mode must be B2A_MODE_*");
@@ -251,7 +260,8 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   sc.alpha = 0;
 
   // lengths / offsets sanity
-  uint32_t maxm = 0, maxn = 0;
+  maxm = 0;
+  maxn = 0;
   for (uint64_t p = 0; p < n; ++p) {
     const uint64_t xe = pairs->x_off[p] + pairs->x_len[p], ye = pairs->y_off[p] + pairs->y_len[p];
     if (xe > pairs->blob_bytes || ye > pairs->blob_bytes)
@@ -315,7 +325,7 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
     if (maxabs > (1ll << 27)) return e->fail(B2A_E_RANGE, "substitution score magnitude above 2^27");
     for (size_t k = 0; k < aa; ++k) e->lut_host[aa + k] = 4 * e->lut_host[k] + 3;
   }
-  int64_t score_bound = 0;
+  score_bound = 0;
   // i32 range guard: every S/I/D of a real path stays within +-2^27, so MIN_SCORE-based
   // sentinels can neither win nor overflow (the reference would silently wrap)
   {
@@ -331,6 +341,49 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   e->sc = sc;
   e->flags = scoring_flags(sc, score_bound, maxm, maxn);
 
+  return B2A_OK;
+}
+
+// ops compaction shared by the full and the banded path: widen -> exclusive scan -> gather
+static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes) {
+  cudaStream_t st = e->stream;
+  const uint64_t n = e->n_pairs;
+  if (n) {
+    const unsigned g1 = (unsigned)((n + 1 + 255) / 256);
+    widen_kernel<<<g1, 256, 0, st>>>(e->d_nops.as<uint32_t>(), e->d_nops64.as<uint64_t>(), n);
+    CK(cudaGetLastError());
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->d_nops64.as<uint64_t>(), e->d_opsoff.as<uint64_t>(),
+                                     (int)(n + 1), st));
+    CK(e->d_scan.reserve(tmp + 16));
+    CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_nops64.as<uint64_t>(),
+                                     e->d_opsoff.as<uint64_t>(), (int)(n + 1), st));
+    // worst case every pair emits m+n+4 ops; size the dense buffer by the scratch size
+    CK(e->d_opsdense.reserve(scratch_bytes + 16));
+    const unsigned g2 = (unsigned)((n * 32 + 255) / 256);
+    gather_ops_kernel<<<g2, 256, 0, st>>>(e->d_opsscratch.as<uint8_t>(), e->d_opssrc.as<uint64_t>(),
+                                          e->d_opsoff.as<uint64_t>(), e->d_opsdense.as<uint8_t>(), n);
+    CK(cudaGetLastError());
+    e->launches += 4;
+  }
+  return B2A_OK;
+}
+
+extern "C" {
+
+int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const b2a_pairs* pairs) {
+  if (!e || !s || !pairs) return B2A_E_INVALID;
+  uint32_t maxm = 0, maxn = 0;
+  int64_t score_bound = 0;
+  int rc = stage_front(e, mode, s, pairs, maxm, maxn, score_bound);
+  if (rc) return rc;
+  const uint64_t n = e->n_pairs;
+  const DevScoring sc = e->sc;
+  cudaStream_t st = e->stream;
+  auto up = [&](DevBuf& bf, const void* src, size_t bytes) -> cudaError_t {
+    e->h2d_bytes += bytes;
+    return bytes ? cudaMemcpyAsync(bf.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
   // shape + plan
   int G = 1, R = 16;
   choose_shape(e, maxm, maxn, n, &G, &R);
@@ -490,24 +543,9 @@ int32_t b2a_batch_run(b2a_engine* e) {
     ++wi;
   }
   CK(cudaEventRecord(e->ev[4], st));
-  // ops compaction: widen -> exclusive scan -> gather
-  if (n) {
-    const unsigned g1 = (unsigned)((n + 1 + 255) / 256);
-    widen_kernel<<<g1, 256, 0, st>>>(e->d_nops.as<uint32_t>(), e->d_nops64.as<uint64_t>(), n);
-    CK(cudaGetLastError());
-    size_t tmp = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->d_nops64.as<uint64_t>(), e->d_opsoff.as<uint64_t>(),
-                                     (int)(n + 1), st));
-    CK(e->d_scan.reserve(tmp + 16));
-    CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_nops64.as<uint64_t>(),
-                                     e->d_opsoff.as<uint64_t>(), (int)(n + 1), st));
-    // worst case every pair emits m+n+4 ops; size the dense buffer by the scratch size
-    CK(e->d_opsdense.reserve(pl.ops_bytes + 16));
-    const unsigned g2 = (unsigned)((n * 32 + 255) / 256);
-    gather_ops_kernel<<<g2, 256, 0, st>>>(e->d_opsscratch.as<uint8_t>(), e->d_opssrc.as<uint64_t>(),
-                                          e->d_opsoff.as<uint64_t>(), e->d_opsdense.as<uint8_t>(), n);
-    CK(cudaGetLastError());
-    e->launches += 4;
+  {
+    int rc2 = compact_ops(e, pl.ops_bytes);
+    if (rc2) return rc2;
   }
   CK(cudaEventRecord(e->ev[5], st));
   e->ran = true;
@@ -551,7 +589,9 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
   }
   CK(cudaStreamSynchronize(st));
   if (ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
-  if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
+  if (ctl[1] & 4u) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
+  if (ctl[1] & 2u) return e->fail(B2A_E_CAPACITY, "banded: more k-mer matches than the per-pair capacity");
+  if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move or never terminates (the reference panics / hangs here: mod.rs:905, banded.rs:777-831)");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->cells = e->plan.cells;
@@ -586,10 +626,195 @@ int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
   return b2a_batch_fetch(e, results, stats);
 }
 
-int32_t b2a_align_batch_banded(b2a_engine* e, int32_t, const b2a_scoring*, uint32_t, uint32_t,
-                               const b2a_pairs*, b2a_results*, b2a_stats*) {
-  if (!e) return B2A_E_INVALID;
-  return e->fail(B2A_E_UNSUPPORTED, "banded::Aligner path (SURVEY 8 rows a10-a15) is not built yet");
+int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
+                               const b2a_pairs* pairs, b2a_results* results, b2a_stats* stats) {
+  if (!e || !s || !pairs) return B2A_E_INVALID;
+  if (k == 0) return e->fail(B2A_E_INVALID, "banded: k-mer length must be >= 1");
+  uint32_t maxm = 0, maxn = 0;
+  int64_t score_bound = 0;
+  int rc = stage_front(e, mode, s, pairs, maxm, maxn, score_bound);
+  if (rc) return rc;
+  const uint64_t n = e->n_pairs;
+  cudaStream_t st = e->stream;
+  auto up = [&](DevBuf& bf, const void* src, size_t bytes) -> cudaError_t {
+    e->h2d_bytes += bytes;
+    return bytes ? cudaMemcpyAsync(bf.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  // per-pair ops regions (written backwards from their end) and output arrays
+  std::vector<uint64_t> ops_end(n);
+  uint64_t ops_total = 0;
+  for (uint64_t p = 0; p < n; ++p) {
+    ops_total += (uint64_t)pairs->x_len[p] + pairs->y_len[p] + 8;
+    ops_end[p] = ops_total;
+  }
+  CK(e->d_xoff.reserve(n * 8 + 8));
+  CK(e->d_yoff.reserve(n * 8 + 8));
+  CK(e->d_xlen.reserve(n * 4 + 4));
+  CK(e->d_ylen.reserve(n * 4 + 4));
+  CK(e->d_codemap.reserve(256));
+  CK(e->d_lut.reserve(e->lut_host.size() * 4 + 16));
+  CK(e->d_score.reserve(n * 4 + 4));
+  CK(e->d_xs.reserve(n * 4 + 4));
+  CK(e->d_xe.reserve(n * 4 + 4));
+  CK(e->d_ys.reserve(n * 4 + 4));
+  CK(e->d_ye.reserve(n * 4 + 4));
+  CK(e->d_nops.reserve(n * 4 + 4));
+  CK(e->d_opssrc.reserve(n * 8 + 8));
+  CK(e->d_clip.reserve(n * 16 + 16));
+  CK(e->d_status.reserve(n * 4 + 4));
+  CK(e->d_nops64.reserve((n + 1) * 8));
+  CK(e->d_opsoff.reserve((n + 1) * 8));
+  CK(e->d_opsscratch.reserve(ops_total + 16));
+  CK(e->d_bcells.reserve(n * 8 + 8));
+  CK(e->d_bstatus.reserve(n * 4 + 4));
+  CK(e->d_bopsend.reserve(n * 8 + 8));
+  CK(up(e->d_xoff, pairs->x_off, n * 8));
+  CK(up(e->d_yoff, pairs->y_off, n * 8));
+  CK(up(e->d_xlen, pairs->x_len, n * 4));
+  CK(up(e->d_ylen, pairs->y_len, n * 4));
+  CK(up(e->d_codemap, e->codemap_host, 256));
+  if (!e->lut_host.empty()) CK(up(e->d_lut, e->lut_host.data(), e->lut_host.size() * 4));
+  CK(up(e->d_bopsend, ops_end.data(), n * 8));
+  uint32_t* ctl = e->d_ctl.as<uint32_t>();
+  CK(cudaMemsetAsync(ctl, 0, 256, st));
+
+  const uint32_t short_max = std::min(maxm, maxn);
+  uint32_t cap = 4 * short_max + 1024;
+  if (cap > (1u << 20)) cap = 1u << 20;
+  const uint64_t k4_bytes = k4_slab_bytes(cap, short_max);
+  uint64_t budget = e->tb_budget;
+  if (!budget) {
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    budget = (uint64_t)((double)fr * 0.5);
+  }
+  const uint64_t per_pair_k4 = k4_bytes + ((uint64_t)maxn + 1) * 8 + 64;
+  uint64_t wave = std::max<uint64_t>(1, (budget / 2) / per_pair_k4);
+  wave = std::min<uint64_t>(wave, std::max<uint64_t>(n, 1));
+  wave = std::min<uint64_t>(wave, 1u << 20);
+
+  BandedParams bp{};
+  bp.blob = e->d_blob.as<uint8_t>();
+  bp.x_off = e->d_xoff.as<uint64_t>();
+  bp.x_len = e->d_xlen.as<uint32_t>();
+  bp.y_off = e->d_yoff.as<uint64_t>();
+  bp.y_len = e->d_ylen.as<uint32_t>();
+  bp.codemap = e->d_codemap.as<uint8_t>();
+  bp.lut = e->d_lut.as<int32_t>();
+  bp.sc = e->sc;
+  // MatchParams keeps its compare/select form here (scores are read per cell from the blob bytes)
+  if (!s->table) bp.sc.alpha = 0;
+  bp.has_match_scores = s->has_match_scores;
+  bp.k = k;
+  bp.w = w;
+  bp.cap_matches = cap;
+  bp.n_pairs = n;
+  bp.slab_stride = k4_bytes;
+  bp.num_cells = e->d_bcells.as<uint64_t>();
+  bp.k4_status = e->d_bstatus.as<uint32_t>();
+  bp.filter_clips = (mode == B2A_MODE_SEMIGLOBAL || mode == B2A_MODE_LOCAL) ? 1 : 0;
+  bp.score = e->d_score.as<int32_t>();
+  bp.xstart = e->d_xs.as<uint32_t>();
+  bp.xend = e->d_xe.as<uint32_t>();
+  bp.ystart = e->d_ys.as<uint32_t>();
+  bp.yend = e->d_ye.as<uint32_t>();
+  bp.n_ops = e->d_nops.as<uint32_t>();
+  bp.ops_src = e->d_opssrc.as<uint64_t>();
+  bp.clip_len = e->d_clip.as<uint32_t>();
+  bp.status = e->d_status.as<uint32_t>();
+  bp.err_flag = ctl + 1;
+  bp.ops_scratch = e->d_opsscratch.as<uint8_t>();
+  bp.ops_off = e->d_bopsend.as<uint64_t>();
+
+  e->launches = 0;
+  float band_ms = 0.f, fill_ms = 0.f;
+  uint64_t total_cells = 0;
+  std::vector<uint64_t> h_cells, roff, foff;
+  cudaEvent_t ev0 = e->ev[0], ev1 = e->ev[1], ev2 = e->ev[2];
+  for (uint64_t lo = 0; lo < n; lo += wave) {
+    const uint32_t nw = (uint32_t)std::min<uint64_t>(wave, n - lo);
+    roff.resize(nw);
+    uint64_t rbytes = 0;
+    for (uint32_t t = 0; t < nw; ++t) {
+      roff[t] = rbytes;
+      rbytes += (((uint64_t)pairs->y_len[lo + t] + 1) * 8 + 15) & ~15ull;
+    }
+    CK(e->d_bslab.reserve((uint64_t)nw * k4_bytes + 16));
+    CK(e->d_branges.reserve(rbytes + 16));
+    CK(e->d_broff.reserve((uint64_t)nw * 8 + 8));
+    CK(up(e->d_broff, roff.data(), (size_t)nw * 8));
+    bp.pair_lo = (uint32_t)lo;
+    bp.slab = e->d_bslab.as<uint8_t>();
+    bp.ranges = e->d_branges.as<uint32_t>();
+    bp.ranges_off = e->d_broff.as<uint64_t>();
+    CK(cudaEventRecord(ev0, st));
+    band_kernel<<<(nw + 127) / 128, 128, 0, st>>>(bp, nw);
+    CK(cudaGetLastError());
+    ++e->launches;
+    CK(cudaEventRecord(ev1, st));
+    h_cells.resize(nw);
+    CK(cudaMemcpyAsync(h_cells.data(), e->d_bcells.as<uint64_t>() + lo, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev0, ev1);
+      band_ms += ms;
+    }
+    // K3 in sub-waves sized by the exact slab bytes
+    uint32_t s0 = 0;
+    while (s0 < nw) {
+      foff.clear();
+      uint64_t fbytes = 0;
+      uint32_t s1 = s0;
+      while (s1 < nw) {
+        const uint64_t need = k3_slab_bytes(pairs->x_len[lo + s1], pairs->y_len[lo + s1], h_cells[s1]);
+        if (s1 > s0 && fbytes + need > budget / 2) break;
+        foff.push_back(fbytes);
+        fbytes += need;
+        total_cells += h_cells[s1];
+        ++s1;
+      }
+      const uint32_t ns = s1 - s0;
+      CK(e->d_bfill.reserve(fbytes + 16));
+      CK(e->d_bfoff.reserve((uint64_t)ns * 8 + 8));
+      CK(up(e->d_bfoff, foff.data(), (size_t)ns * 8));
+      BandedParams b3 = bp;
+      b3.pair_lo = (uint32_t)(lo + s0);
+      b3.ranges_off = e->d_broff.as<uint64_t>() + s0;
+      b3.fill = e->d_bfill.as<uint8_t>();
+      b3.fill_off = e->d_bfoff.as<uint64_t>();
+      CK(cudaEventRecord(ev1, st));
+      banded_fill_kernel<<<(ns + 127) / 128, 128, 0, st>>>(b3, ns);
+      CK(cudaGetLastError());
+      ++e->launches;
+      CK(cudaEventRecord(ev2, st));
+      CK(cudaStreamSynchronize(st));  // foff (host vector) is reused by the next sub-wave
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev1, ev2);
+      fill_ms += ms;
+      s0 = s1;
+    }
+  }
+  CK(cudaEventRecord(e->ev[4], st));
+  rc = compact_ops(e, ops_total);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev[5], st));
+  e->plan = Plan{};
+  e->plan.cells = total_cells;
+  e->ran = true;
+  rc = b2a_batch_fetch(e, results, stats);
+  if (stats) {
+    stats->cells = total_cells;
+    stats->band_ms = band_ms;
+    stats->fill_ms = fill_ms;
+    float tail = 0.f;
+    cudaEventElapsedTime(&tail, e->ev[4], e->ev[5]);
+    stats->walk_ms = tail;
+    stats->fill_lanes_per_pair = 1;
+    stats->fill_rows_per_lane = 0;
+  }
+  e->ran = false;
+  return rc;
 }
 
 uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n) {

@@ -215,3 +215,72 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   return 0;
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Banded path: the device functions of b2a_banded.cuh (K4 band construction + K3 banded fill/walk)
+// compiled for the host, one pair at a time.
+#include "../../rust_bio_b200/csrc/b2a_banded.cuh"
+
+extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* blob,
+                                const uint64_t* x_off, const uint32_t* x_len, const uint64_t* y_off,
+                                const uint32_t* y_len, uint64_t n_pairs, uint32_t cap_matches, int garbage,
+                                int32_t* score, uint32_t* xstart, uint32_t* xend, uint32_t* ystart,
+                                uint32_t* yend, uint32_t* n_ops, uint32_t* clip_len, uint32_t* status,
+                                uint64_t* num_cells, uint64_t* ranges_out /*optional: 2*(n+1) per pair, flat*/,
+                                uint8_t* ops, const uint64_t* ops_off) {
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  if (mode == 1) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
+  if (mode == 2) { sc.xclip_prefix = sc.xclip_suffix = MIN_SCORE; sc.yclip_prefix = sc.yclip_suffix = 0; }
+  if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  const int32_t* table = s->table;
+  uint64_t rpos = 0;
+  for (uint64_t p = 0; p < n_pairs; ++p) {
+    const uint64_t m = x_len[p], n = y_len[p];
+    const uint8_t* x = blob + x_off[p];
+    const uint8_t* y = blob + y_off[p];
+    std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
+    std::vector<uint32_t> rng(2 * (n + 1), 0xCDCDCDCDu);
+    uint64_t cells = 0;
+    const uint32_t st = band_create_d(x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
+                                      rng.data(), &cells);
+    num_cells[p] = cells;
+    if (ranges_out) {
+      for (uint64_t j = 0; j <= n; ++j) {
+        ranges_out[rpos + 2 * j] = rng[2 * j];
+        ranges_out[rpos + 2 * j + 1] = rng[2 * j + 1];
+      }
+      rpos += 2 * (n + 1);
+    }
+    BandedOut o{};
+    std::vector<uint8_t> opsbuf(m + n + 16, 0);
+    if (st != 0) {
+      o.status = 1 + st;
+    } else {
+      std::vector<uint8_t> fill(k3_slab_bytes(m, n, cells), (uint8_t)garbage);
+      auto scoref = [&](uint8_t a, uint8_t b) -> int32_t {
+        if (table) return table[(size_t)a * 256 + b];
+        return a == b ? sc.match_score : sc.mismatch_score;
+      };
+      banded_compute_d(x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
+                       opsbuf.data() + opsbuf.size(), o);
+    }
+    score[p] = o.score;
+    xstart[p] = o.xstart;
+    xend[p] = o.xend;
+    ystart[p] = o.ystart;
+    yend[p] = o.yend;
+    n_ops[p] = o.n_ops;
+    status[p] = o.status;
+    for (int q = 0; q < 4; ++q) clip_len[4 * p + q] = o.clip[q];
+    std::memcpy(ops + ops_off[p], opsbuf.data() + opsbuf.size() - o.n_ops, o.n_ops);
+  }
+  return 0;
+}

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "sim", "b2a_sim.cpp")
 SO = os.path.join(HERE, "sim", "libb2asim.so")
 DEPS = [SRC] + [os.path.join(ROOT, "rust_bio_b200", "csrc", f)
-                for f in ("b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h")]
+                for f in ("b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h", "b2a_banded.cuh")]
 
 
 class SimScoring(C.Structure):
@@ -86,3 +86,42 @@ def decode_ops(codes, clips):
         else:
             res.append((c, 0))
     return res
+
+
+def banded_batch(mode, orc_scoring, k, w, blob, x_off, x_len, y_off, y_len, cap_matches=4096, want_ranges=False):
+    """K4 + K3 device functions (b2a_banded.cuh) compiled for the host; two scratch fills must agree."""
+    s = SimScoring.from_buffer_copy(bytes(orc_scoring))
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    x_off = np.ascontiguousarray(x_off, dtype=np.uint64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.uint64)
+    x_len = np.ascontiguousarray(x_len, dtype=np.uint32)
+    y_len = np.ascontiguousarray(y_len, dtype=np.uint32)
+    n = len(x_len)
+    cap = x_len.astype(np.uint64) + y_len.astype(np.uint64) + np.uint64(8)
+    ops_off = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    results = []
+    for garbage in (0x00, 0x7F):
+        ops = np.zeros(int(ops_off[-1]), dtype=np.uint8)
+        out = {k_: np.zeros(n, dtype=np.uint32) for k_ in ("xstart", "xend", "ystart", "yend", "n_ops", "status")}
+        out["score"] = np.zeros(n, dtype=np.int32)
+        out["clip_len"] = np.zeros(4 * n, dtype=np.uint32)
+        out["num_cells"] = np.zeros(n, dtype=np.uint64)
+        rng = np.zeros(int(2 * (y_len.astype(np.uint64) + 1).sum()), dtype=np.uint64) if want_ranges else None
+        L = lib()
+        L.sim_banded_batch.restype = C.c_int
+        rc = L.sim_banded_batch(int(mode), C.byref(s), C.c_uint32(k), C.c_uint32(w), p(blob), p(x_off), p(x_len),
+                                p(y_off), p(y_len), C.c_uint64(n), C.c_uint32(cap_matches), int(garbage),
+                                p(out["score"]), p(out["xstart"]), p(out["xend"]), p(out["ystart"]), p(out["yend"]),
+                                p(out["n_ops"]), p(out["clip_len"]), p(out["status"]), p(out["num_cells"]),
+                                p(rng) if want_ranges else None, p(ops), p(ops_off))
+        assert rc == 0
+        oplists = [decode_ops(ops[int(ops_off[i]):int(ops_off[i]) + int(out["n_ops"][i])],
+                              out["clip_len"][4 * i:4 * i + 4]) if out["status"][i] == 0 else None
+                   for i in range(n)]
+        results.append((out, oplists, rng))
+    a, b = results
+    for k_ in a[0]:
+        assert np.array_equal(a[0][k_], b[0][k_]), ("scratch-dependent result", k_)
+    assert a[1] == b[1]
+    return a

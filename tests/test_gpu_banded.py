@@ -1,0 +1,146 @@
+"""GPU parity of the banded path (K4 band construction + K3 banded fill/walk) against the banded oracle
+and the reference's banded known-answer tests, through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import HERE, load_cases, parse_ops, scoring_fields
+from parity_util import MODES
+from test_sim_banded import _mutated_window_batch
+
+pytestmark = pytest.mark.gpu
+MIN = -858993459
+with open(os.path.join(HERE, "golden", "banded_vectors.json")) as f:
+    G = json.load(f)
+FULL = {c["name"]: c for c in load_cases()}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rust_bio_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _mirror_scoring(sc):
+    from rust_bio_b200 import scores
+    from rust_bio_b200.pairwise import Scoring
+    f = scoring_fields(sc)
+    if f["matrix"]:
+        s = Scoring.new(f["gap_open"], f["gap_extend"], getattr(scores, f["matrix"]))
+    elif f["from_scores"]:
+        s = Scoring.from_scores(f["gap_open"], f["gap_extend"], f["match"], f["mismatch"])
+    else:
+        ma, mi = f["match"], f["mismatch"]
+        s = Scoring.new(f["gap_open"], f["gap_extend"], lambda a, b: ma if a == b else mi)
+    s.xclip_prefix, s.xclip_suffix = f["xclip_prefix"], f["xclip_suffix"]
+    s.yclip_prefix, s.yclip_suffix = f["yclip_prefix"], f["yclip_suffix"]
+    return s
+
+
+def _run(eng, case, k, w):
+    from rust_bio_b200.banded import Aligner
+    aligner = Aligner.with_scoring(_mirror_scoring(case["scoring"]), k, w, engine=eng)
+    method = {"custom": aligner.custom, "global": aligner.global_, "semiglobal": aligner.semiglobal,
+              "local": aligner.local}[case["mode"]]
+    return method(case["x"].encode(), case["y"].encode())
+
+
+def _check(case, aln):
+    exp = case["expect"]
+    for k in ("score", "xstart", "xend", "ystart", "yend"):
+        if k in exp:
+            assert getattr(aln, k) == exp[k], (case["name"], k, aln)
+    if "ops" in exp:
+        assert [(o.code, o.len) for o in aln.operations] == parse_ops(exp["ops"])
+    if "x_aln_len" in exp:
+        assert aln.x_aln_len() == exp["x_aln_len"] and aln.y_aln_len() == exp["y_aln_len"]
+    if exp.get("yend_is_ylen"):
+        assert aln.yend == aln.ylen
+
+
+@pytest.mark.parametrize("case", G["cases"], ids=lambda c: c["name"])
+def test_banded_reference_known_answers(eng, case):
+    _check(case, _run(eng, case, case["k"], case["w"]))
+
+
+@pytest.mark.parametrize("name", G["same_as_full"]["cases"])
+def test_full_vectors_through_banded(eng, name):
+    _check(FULL[name], _run(eng, FULL[name], 10, 10))
+
+
+@pytest.mark.parametrize("pair", G["differential_k10_w10"]["pairs"], ids=lambda p: p["name"])
+def test_banded_equals_full_on_gpu(eng, pair):
+    """banded.rs:1621-1753: assert_eq!(banded_alignment, full_alignment), both on the GPU."""
+    from rust_bio_b200 import banded, pairwise
+    score = lambda a, b: 1 if a == b else -1
+    x, y = pair["x"].encode(), pair["y"].encode()
+    ba = banded.Aligner.with_capacity(len(x), len(y), -5, -1, score, 10, 10, engine=eng)
+    fa = pairwise.Aligner.with_capacity(len(x), len(y), -5, -1, score, engine=eng)
+    for mode in pair["modes"]:
+        name = "global_" if mode == "global" else mode
+        assert getattr(ba, name)(x, y) == getattr(fa, name)(x, y), (pair["name"], mode)
+
+
+def _c_scoring(go, ge, ma, mi, clips=(MIN, MIN, MIN, MIN), has_ms=1):
+    from rust_bio_b200._lib import CScoring
+    return CScoring(go, ge, clips[0], clips[1], clips[2], clips[3], ma, mi, has_ms, None, None, 0)
+
+
+def _compare(eng, oracle, mode, cs, s, k, w, batch, what):
+    ref, rops, roff, _, ref_cells = oracle.banded_align_batch(mode, s, k, w, *batch, threads=8)
+    res = eng.align_batch_banded(MODES[mode], cs, k, w, batch)
+    assert int(eng.stats.cells) == ref_cells, what
+    for f in ("score", "xstart", "xend", "ystart", "yend"):
+        assert np.array_equal(getattr(res, f).astype(np.int64), ref[f].astype(np.int64)), (what, f)
+    for p in range(len(batch[2])):
+        want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+        assert res.ops_of(p) == want, (what, p)
+
+
+@pytest.mark.parametrize("mode", ["semiglobal", "local", "global"])
+def test_mutated_windows_parity(eng, oracle, mode):
+    batch = _mutated_window_batch(5, 300, 120, 700)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    _compare(eng, oracle, mode, _c_scoring(-5, -1, 1, -1), s, 12, 8, batch, f"mutated windows {mode}")
+
+
+def test_c4_shape_sample_k32_w32(eng, oracle):
+    """BASELINE config 4 shape: 500 x 10,000 semiglobal, banded k=32 (w=32), mutated-window generator."""
+    batch = _mutated_window_batch(9, 48, 500, 10000, sub=0.05, indel=0.01)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    _compare(eng, oracle, "semiglobal", _c_scoring(-5, -1, 1, -1), s, 32, 32, batch, "C4 sample")
+
+
+def test_c4_degenerate_independent_random_is_refused_like_the_reference(eng, oracle):
+    """Independent random 500 x 10,000: no 32-mer match -> full matrix -> 5,010,501 > MAX_CELLS -> empty alignment."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(synth.BASES["C4"], 0, 4, 500, 10000)
+    res = eng.align_batch_banded(MODES["semiglobal"], _c_scoring(-5, -1, 1, -1), 32, 32, batch)
+    assert all(int(v) == MIN for v in res.score) and int(res.ops_off[-1]) == 0
+    assert int(eng.stats.cells) == 4 * 501 * 10001
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    ref, *_ = oracle.banded_align_batch("semiglobal", s, 32, 32, *batch, threads=4)
+    assert all(int(v) == MIN for v in ref["score"])
+
+
+@pytest.mark.parametrize("seed", [1, 3, 5])
+def test_random_custom_clips_banded(eng, oracle, seed):
+    rng = np.random.default_rng(50 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9, -40]))
+    go, ge = int(rng.choice([0, -1, -5, -13])), int(rng.choice([0, -1, -2]))
+    ma, mi = int(rng.choice([1, 2, 3])), int(rng.choice([-1, -3, -5]))
+    clips = (pick(), pick(), pick(), pick())
+    s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips, has_match_scores=1)
+    batch = _mutated_window_batch(seed, 200, 60, 150, sub=0.08, indel=0.04)
+    k, w = int(rng.choice([4, 6, 8])), int(rng.choice([3, 5, 9]))
+    ref, *_ = oracle.banded_align_batch("custom", s, k, w, *batch, threads=8)
+    if np.any(ref["n_ops"] == 0xFFFFFFFF):
+        from rust_bio_b200._lib import B2AError
+        with pytest.raises(B2AError):  # the reference panics / hangs on some pair: the batch is refused
+            eng.align_batch_banded(MODES["custom"], _c_scoring(go, ge, ma, mi, clips), k, w, batch)
+    else:
+        _compare(eng, oracle, "custom", _c_scoring(go, ge, ma, mi, clips), s, k, w, batch, f"banded custom {seed}")

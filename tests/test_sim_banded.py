@@ -1,0 +1,150 @@
+"""Host logic of the banded path: the device functions of b2a_banded.cuh (K4 band construction, K3
+banded fill + walk), compiled for the CPU by tests/sim, against the banded oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sim_util
+from golden_util import HERE, load_cases, parse_ops, scoring_fields
+from parity_util import MODES
+from rust_bio_b200 import synth
+
+with open(os.path.join(HERE, "golden", "banded_vectors.json")) as f:
+    G = json.load(f)
+FULL = {c["name"]: c for c in load_cases()}
+MIN = -858993459
+
+
+def _one(x: bytes, y: bytes):
+    blob = np.frombuffer(x + y + b"\0", dtype=np.uint8)
+    return (blob, np.array([0], dtype=np.uint64), np.array([len(x)], dtype=np.uint32),
+            np.array([len(x)], dtype=np.uint64), np.array([len(y)], dtype=np.uint32))
+
+
+def _scoring(orc, sc):
+    f = scoring_fields(sc)
+    table = None
+    if f["matrix"]:
+        from rust_bio_b200 import scores
+        table = scores.matrix_table256(f["matrix"])
+    return orc.make_scoring(f["gap_open"], f["gap_extend"], f["match"], f["mismatch"], table,
+                            f["xclip_prefix"], f["xclip_suffix"], f["yclip_prefix"], f["yclip_suffix"],
+                            1 if f["from_scores"] else 0)
+
+
+def _check(case, got, ops):
+    exp = case["expect"]
+    for k in ("score", "xstart", "xend", "ystart", "yend"):
+        if k in exp:
+            assert int(got[k][0]) == exp[k], (case["name"], k)
+    if "ops" in exp:
+        assert ops[0] == parse_ops(exp["ops"]), (case["name"], ops[0])
+    assert got["status"][0] == 0
+
+
+@pytest.mark.parametrize("case", G["cases"], ids=lambda c: c["name"])
+def test_sim_banded_known_answers(oracle, case):
+    s, keep = _scoring(oracle, case["scoring"])
+    got, ops, _ = sim_util.banded_batch(MODES[case["mode"]], s, case["k"], case["w"],
+                                        *_one(case["x"].encode(), case["y"].encode()))
+    if "x_aln_len" in case["expect"] or case["expect"].get("yend_is_ylen"):
+        ref, ref_ops = oracle.banded_align(case["mode"], s, case["k"], case["w"], case["x"].encode(), case["y"].encode())
+        assert int(got["score"][0]) == ref["score"] and ops[0] == ref_ops
+    else:
+        _check(case, got, ops)
+
+
+@pytest.mark.parametrize("name", G["same_as_full"]["cases"])
+def test_sim_banded_full_vectors(oracle, name):
+    case = FULL[name]
+    s, keep = _scoring(oracle, case["scoring"])
+    got, ops, _ = sim_util.banded_batch(MODES[case["mode"]], s, 10, 10, *_one(case["x"].encode(), case["y"].encode()))
+    _check(case, got, ops)
+
+
+def _mutated_window_batch(seed, n_pairs, xlen, ylen, sub=0.05, indel=0.01):
+    """x = window of y with substitutions/indels, trimmed/padded to xlen (the C4 generator)."""
+    rng = np.random.default_rng(seed)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, xo, xl, yo, yl = [], [], [], [], []
+    pos = 0
+    for _ in range(n_pairs):
+        y = alpha[rng.integers(0, 4, ylen)]
+        st = int(rng.integers(0, max(1, ylen - xlen)))
+        src = y[st:st + xlen + 20]
+        out = []
+        for c in src:
+            r = rng.random()
+            if r < indel / 2:
+                continue
+            if r < indel:
+                out.append(alpha[rng.integers(0, 4)])
+            out.append(alpha[rng.integers(0, 4)] if rng.random() < sub else c)
+        x = np.array(out[:xlen], dtype=np.uint8)
+        if len(x) < xlen:
+            x = np.concatenate([x, alpha[rng.integers(0, 4, xlen - len(x))]])
+        xo.append(pos); xl.append(len(x)); pos += len(x)
+        yo.append(pos); yl.append(len(y)); pos += len(y)
+        seqs += [x, y]
+    blob = np.concatenate(seqs + [np.zeros(1, np.uint8)])
+    return (blob, np.array(xo, np.uint64), np.array(xl, np.uint32), np.array(yo, np.uint64), np.array(yl, np.uint32))
+
+
+def _compare_batch(oracle, mode, s, k, w, batch, what):
+    ref, rops, roff, _, ref_cells = oracle.banded_align_batch(mode, s, k, w, *batch, threads=4)
+    got, ops, rng = sim_util.banded_batch(MODES[mode], s, k, w, *batch, want_ranges=True)
+    blob, xo, xl, yo, yl = batch
+    pos = 0
+    n_panic = [0]
+    for p in range(len(xl)):
+        x = bytes(blob[int(xo[p]):int(xo[p]) + int(xl[p])])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + int(yl[p])])
+        want_rng, cells = oracle.band_create(mode, s, k, w, x, y)
+        n = int(yl[p])
+        got_rng = [(int(rng[pos + 2 * j]), int(rng[pos + 2 * j + 1])) for j in range(n + 1)]
+        pos += 2 * (n + 1)
+        assert got_rng == want_rng, (what, p, "band ranges differ")
+        assert int(got["num_cells"][p]) == cells
+        if int(ref["n_ops"][p]) == 0xFFFFFFFF:
+            # the reference itself panics / never terminates on this input: the device must flag it
+            assert got["status"][p] != 0, (what, p, "reference panics but the device path returned a result")
+            n_panic[0] += 1
+            continue
+        assert got["status"][p] == 0
+        for f in ("score", "xstart", "xend", "ystart", "yend"):
+            assert int(got[f][p]) == int(ref[f][p]), (what, p, f, x, y)
+        want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+        assert ops[p] == want, (what, p, x, y)
+    assert int(got["num_cells"].sum()) == ref_cells
+    assert n_panic[0] < len(xl) // 2, "too many reference panics for a meaningful comparison"
+
+
+@pytest.mark.parametrize("mode", ["semiglobal", "local", "global"])
+def test_sim_banded_mutated_windows(oracle, mode):
+    batch = _mutated_window_batch(5, 40, 120, 700)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    _compare_batch(oracle, mode, s, 12, 8, batch, f"mutated windows {mode}")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sim_banded_random_custom(oracle, seed):
+    rng = np.random.default_rng(50 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9, -40]))
+    go, ge = int(rng.choice([0, -1, -5, -13])), int(rng.choice([0, -1, -2]))
+    s, _ = oracle.make_scoring(go, ge, int(rng.choice([1, 2, 3])), int(rng.choice([-1, -3, -5])), None,
+                               pick(), pick(), pick(), pick(), has_match_scores=int(seed % 2))
+    batch = _mutated_window_batch(seed, 25, 60, 150, sub=0.08, indel=0.04) if seed % 2 else \
+        synth.ragged_pairs(seed, 40, 50, 70, alphabet=b"AC", min_len=0)
+    _compare_batch(oracle, "custom", s, int(rng.choice([4, 6, 8])), int(rng.choice([3, 5, 9])), batch,
+                   f"banded custom seed={seed}")
+
+
+def test_sim_banded_refuses_more_than_max_cells(oracle):
+    rng = np.random.default_rng(3)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    x, y = bytes(alpha[rng.integers(0, 4, 500)]), bytes(alpha[rng.integers(0, 4, 10000)])
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    got, ops, _ = sim_util.banded_batch(MODES["semiglobal"], s, 32, 32, *_one(x, y))
+    assert int(got["score"][0]) == MIN and ops[0] == [] and int(got["num_cells"][0]) == 501 * 10001

@@ -153,6 +153,11 @@ int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes);
  * lane R in {4,8,12,16,20}); 0,0 = automatic. */
 int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t rows_per_lane);
 
+/* b2a_align_batch cuts batches of >= 262,144 pairs into `chunks` pieces that alternate between two
+ * internal engines, so one chunk's copies and host planning overlap the other's kernels.
+ * chunks < 2 disables the pipeline (default 4). Results are identical either way. */
+int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks);
+
 /* One-call form: Aligner::{custom,global,semiglobal,local} over a batch with
  * HOST inputs and HOST outputs (copies inside). mode = B2A_MODE_*. */
 int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,

@@ -97,6 +97,19 @@ struct b2a_engine {
   uint32_t launches = 0;
   int last_grid = 0;
 
+  // software pipeline of b2a_align_batch: the batch is cut into chunks that alternate between two
+  // child engines (own streams and buffers) so chunk c+1's H2D and host planning overlap chunk c's kernels
+  int pipe_chunks = 4;
+  struct PipeSlot {
+    b2a_engine* eng = nullptr;
+    uint64_t* h_opsoff = nullptr;  // pinned
+    uint32_t* h_ctl = nullptr;     // pinned
+    size_t h_cap = 0;
+    std::vector<uint64_t> xoff, yoff;
+    uint64_t lo = 0, n = 0;
+    bool busy = false;
+  } slots[2];
+
   int fail(int code, const std::string& what) {
     err = what;
     return code;
@@ -183,6 +196,12 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
 int32_t b2a_engine_destroy(b2a_engine* e) {
   if (!e) return B2A_OK;
   cudaSetDevice(e->device);
+  for (auto& sl : e->slots) {
+    if (sl.h_opsoff) cudaFreeHost(sl.h_opsoff);
+    if (sl.h_ctl) cudaFreeHost(sl.h_ctl);
+    if (sl.eng) b2a_engine_destroy(sl.eng);
+    sl.eng = nullptr;
+  }
   cudaStreamSynchronize(e->stream);
   DevBuf* bufs[] = {&e->d_blob, &e->d_xoff, &e->d_xlen, &e->d_yoff, &e->d_ylen, &e->d_order, &e->d_pm,
                     &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
@@ -209,6 +228,12 @@ int32_t b2a_engine_set_stream(b2a_engine* e, void* cuda_stream) {
 int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes) {
   if (!e) return B2A_E_INVALID;
   e->tb_budget = bytes;
+  return B2A_OK;
+}
+
+int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks) {
+  if (!e) return B2A_E_INVALID;
+  e->pipe_chunks = chunks < 2 ? 0 : (chunks > 64 ? 64 : chunks);
   return B2A_OK;
 }
 
@@ -617,8 +642,171 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
   return B2A_OK;
 }
 
+// kernel-time part of the stats of an engine whose batch has completed
+static void collect_stats(b2a_engine* e, b2a_stats* stats) {
+  stats->cells += e->plan.cells;
+  stats->h2d_bytes += e->h2d_bytes;
+  stats->traceback_bytes += e->plan.total_tb;
+  float v = 0.f;
+  cudaEventElapsedTime(&v, e->ev[0], e->ev[1]);
+  stats->pack_ms += v;
+  for (size_t wv = 0; wv < e->plan.waves.size(); ++wv) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, e->wave_ev[3 * wv + 0], e->wave_ev[3 * wv + 1]);
+    cudaEventElapsedTime(&b, e->wave_ev[3 * wv + 1], e->wave_ev[3 * wv + 2]);
+    stats->fill_ms += a;
+    stats->walk_ms += b;
+  }
+  cudaEventElapsedTime(&v, e->ev[4], e->ev[5]);
+  stats->walk_ms += v;
+  stats->kernel_launches += e->launches;
+  stats->waves += (uint32_t)e->plan.waves.size();
+  stats->fill_lanes_per_pair = (uint32_t)e->plan.G;
+  stats->fill_rows_per_lane = (uint32_t)e->plan.R;
+}
+
+// finish one pipeline slot: its chunk's results are complete on the device; place its ops after `base`
+static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results* r, uint64_t& base,
+                           b2a_stats* agg) {
+  b2a_engine* c = sl.eng;
+  sl.busy = false;
+  cudaError_t ce = cudaStreamSynchronize(c->stream);
+  if (ce != cudaSuccess) return e->cuda_fail("pipeline: cudaStreamSynchronize", ce);
+  if (sl.h_ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
+  if (sl.h_ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
+  const uint64_t total = sl.h_opsoff[sl.n];
+  if (r->ops) {
+    if (base + total > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for this batch");
+    if (total) {
+      ce = cudaMemcpyAsync(r->ops + base, c->d_opsdense.p, total, cudaMemcpyDeviceToHost, c->stream);
+      if (ce != cudaSuccess) return e->cuda_fail("pipeline: ops D2H", ce);
+      agg->d2h_bytes += total;
+    }
+  }
+  if (r->ops_off)
+    for (uint64_t i = 0; i < sl.n; ++i) r->ops_off[sl.lo + i] = base + sl.h_opsoff[i];
+  base += total;
+  ce = cudaStreamSynchronize(c->stream);
+  if (ce != cudaSuccess) return e->cuda_fail("pipeline: cudaStreamSynchronize", ce);
+  collect_stats(c, agg);
+  return B2A_OK;
+}
+
+static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                                     const b2a_pairs* pairs, b2a_results* r, b2a_stats* stats) {
+  const uint64_t n = pairs->n_pairs;
+  const uint64_t K = (uint64_t)e->pipe_chunks;
+  const uint64_t CH = ((n + K - 1) / K + 31) / 32 * 32;
+  b2a_stats agg;
+  std::memset(&agg, 0, sizeof(agg));
+  uint64_t base = 0;
+  int32_t rc = B2A_OK;
+  for (uint64_t c = 0; c * CH < n && rc == B2A_OK; ++c) {
+    const uint64_t lo = c * CH, hi = std::min(n, lo + CH), nc = hi - lo;
+    b2a_engine::PipeSlot& sl = e->slots[c % 2];
+    if (sl.busy) {
+      rc = slot_finish(e, sl, r, base, &agg);
+      if (rc) break;
+    }
+    if (!sl.eng) {
+      rc = b2a_engine_create(&sl.eng, e->device);
+      if (rc) {
+        e->fail(rc, "pipeline: cannot create a slot engine");
+        break;
+      }
+    }
+    sl.eng->tune_G = e->tune_G;
+    sl.eng->tune_R = e->tune_R;
+    sl.eng->tb_budget = e->tb_budget;
+    sl.eng->pipe_chunks = 0;
+    if (sl.h_cap < nc + 1) {
+      if (sl.h_opsoff) cudaFreeHost(sl.h_opsoff);
+      sl.h_opsoff = nullptr;
+      if (cudaMallocHost(&sl.h_opsoff, (nc + 1) * 8) != cudaSuccess) {
+        rc = e->fail(B2A_E_CUDA, "pipeline: cudaMallocHost failed");
+        break;
+      }
+      sl.h_cap = nc + 1;
+    }
+    if (!sl.h_ctl && cudaMallocHost(&sl.h_ctl, 64) != cudaSuccess) {
+      rc = e->fail(B2A_E_CUDA, "pipeline: cudaMallocHost failed");
+      break;
+    }
+    // the chunk's slice of the caller's blob, offsets rebased
+    uint64_t bmin = ~0ull, bmax = 0;
+    for (uint64_t p = lo; p < hi; ++p) {
+      bmin = std::min(bmin, std::min(pairs->x_off[p], pairs->y_off[p]));
+      bmax = std::max(bmax, std::max(pairs->x_off[p] + pairs->x_len[p], pairs->y_off[p] + pairs->y_len[p]));
+    }
+    if (bmax > pairs->blob_bytes) {
+      rc = e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
+      break;
+    }
+    if (bmin > bmax) bmin = bmax = 0;
+    sl.xoff.resize(nc);
+    sl.yoff.resize(nc);
+    for (uint64_t i = 0; i < nc; ++i) {
+      sl.xoff[i] = pairs->x_off[lo + i] - bmin;
+      sl.yoff[i] = pairs->y_off[lo + i] - bmin;
+    }
+    b2a_pairs sub{pairs->seq_blob + bmin, sl.xoff.data(), pairs->x_len + lo, sl.yoff.data(), pairs->y_len + lo,
+                  bmax - bmin, nc};
+    b2a_engine* ch = sl.eng;
+    rc = b2a_batch_stage(ch, mode, scoring, &sub);
+    if (rc == B2A_OK) rc = b2a_batch_run(ch);
+    if (rc) {
+      e->fail(rc, ch->err);
+      break;
+    }
+    cudaStream_t st = ch->stream;
+    auto down = [&](void* dst, const DevBuf& bf, size_t bytes) -> cudaError_t {
+      if (!dst || !bytes) return cudaSuccess;
+      agg.d2h_bytes += bytes;
+      return cudaMemcpyAsync(dst, bf.p, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    cudaError_t ce = cudaMemcpyAsync(sl.h_ctl, ch->d_ctl.p, 8, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = down(r->score ? r->score + lo : nullptr, ch->d_score, nc * 4);
+    if (ce == cudaSuccess) ce = down(r->xstart ? r->xstart + lo : nullptr, ch->d_xs, nc * 4);
+    if (ce == cudaSuccess) ce = down(r->xend ? r->xend + lo : nullptr, ch->d_xe, nc * 4);
+    if (ce == cudaSuccess) ce = down(r->ystart ? r->ystart + lo : nullptr, ch->d_ys, nc * 4);
+    if (ce == cudaSuccess) ce = down(r->yend ? r->yend + lo : nullptr, ch->d_ye, nc * 4);
+    if (ce == cudaSuccess) ce = down(r->clip_len ? r->clip_len + 4 * lo : nullptr, ch->d_clip, nc * 16);
+    if (ce == cudaSuccess) ce = down(sl.h_opsoff, ch->d_opsoff, (nc + 1) * 8);
+    if (ce != cudaSuccess) {
+      rc = e->cuda_fail("pipeline: result D2H", ce);
+      break;
+    }
+    sl.lo = lo;
+    sl.n = nc;
+    sl.busy = true;
+  }
+  // drain in chunk order: the older chunk lives in the slot the next chunk would use
+  uint64_t nchunks = (n + CH - 1) / CH;
+  for (uint64_t c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; ++c) {
+    b2a_engine::PipeSlot& sl = e->slots[c % 2];
+    if (!sl.busy) continue;
+    if (rc == B2A_OK) {
+      rc = slot_finish(e, sl, r, base, &agg);
+    } else {
+      cudaStreamSynchronize(sl.eng->stream);
+      sl.busy = false;
+    }
+  }
+  if (rc) return rc;
+  if (r->ops_off) r->ops_off[n] = base;
+  if (stats) *stats = agg;
+  return B2A_OK;
+}
+
 int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring, const b2a_pairs* pairs,
                         b2a_results* results, b2a_stats* stats) {
+  if (!e || !scoring || !pairs) return B2A_E_INVALID;
+  // large batches with host outputs: pipeline chunks so copies and planning overlap the kernels
+  if (e->pipe_chunks >= 2 && results && pairs->n_pairs >= 262144) {
+    e->staged = e->ran = false;
+    if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+    return align_batch_pipelined(e, mode, scoring, pairs, results, stats);
+  }
   int rc = b2a_batch_stage(e, mode, scoring, pairs);
   if (rc) return rc;
   rc = b2a_batch_run(e);

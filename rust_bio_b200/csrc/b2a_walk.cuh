@@ -76,6 +76,13 @@ struct PairView {
     return p == q ? sc.match_score : sc.mismatch_score;
   }
   B2A_HD int32_t& row(int arr, int32_t i) const { return rows[(arr * rows_pad + i) * 32 + pi]; }
+  B2A_HD int4 load_bnd(int32_t j) const {
+#if defined(__CUDA_ARCH__)
+    return __ldg(&bnd[j * 32 + pi]);  // read-only path: K1 wrote it in an earlier launch
+#else
+    return bnd[j * 32 + pi];
+#endif
+  }
   // compressed traceback nibble of an interior cell 1 <= i <= m-1, 1 <= j <= n
   B2A_HD uint32_t nib(int32_t i, int32_t j) const {
     const int32_t GR = G * R;
@@ -180,7 +187,26 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
     const int32_t p = v.xsym(m);
     const int32_t yclip_score = yp + go + ge * (m - 1);
     int32_t sdiag = (m == 1) ? 0 : col0_S(sc, m - 1);
-    for (int32_t j = 1; j <= n; ++j) {
+    // columns are walked four at a time: the boundary row and y symbols of a group are loaded up front
+    // (independent loads in flight), then the recurrence runs over them in order
+    constexpr int UB = 4;
+    for (int32_t j0 = 1; j0 <= n; j0 += UB) {
+      int4 braw[UB];
+      int32_t qv[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int32_t jj = j0 + u;
+        braw[u] = make_int4(0, 0, 0, 0);
+        qv[u] = 0;
+        if (jj <= n) {
+          if (m != 1) braw[u] = v.load_bnd(jj);
+          qv[u] = v.ysym(jj);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+      const int32_t j = j0 + u;
+      if (j > n) break;
       int32_t sup, iup, Tv, Ti;
       if (m == 1) {
         sup = row0_S(sc, j, n);
@@ -188,13 +214,13 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
         Tv = MIN_SCORE;
         Ti = m;
       } else {
-        const Boundary b = decode_boundary(v.bnd[j * 32 + v.pi], v.packtrk != 0, xs, m);
+        const Boundary b = decode_boundary(braw[u], v.packtrk != 0, xs, m);
         sup = b.S;
         iup = b.I;
         Tv = b.Tv;
         Ti = b.Ti;
       }
-      const int32_t q = v.ysym(j);
+      const int32_t q = qv[u];
       const int32_t m_score = sdiag + v.score(p, q);
       int32_t best_i, best_d;
       {
@@ -258,16 +284,20 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
       cell = cell_make(ib, db, sb);
       v.rowm[j * 32 + v.pi] = (uint16_t)cell;
       sdiag = sup;
+          }
     }
     SmN = Sm;
     ImN = Im;
     cmN = cell;
   }
 
-  // ------------------------------------------- materialise column n (pre fix-up)
-  // rows 0..m: S in ROWS_SL, I in ROWS_IL, cell in ROWS_NL, Sn in ROWS_SN, Ly as column in ROWS_LY
+  // ------------------------------- column n: materialise the cells K1 left as nibbles and run fix-up 1
+  // (mod.rs:809-821) in the same pass over the rows; rows 0..m-1 keep S in ROWS_SL, I in ROWS_IL, the
+  // literal cell in ROWS_NL.  i_bits are captured from the PRE-fix-up s_bits of the row above (743),
+  // exactly as the reference's fill did before its fix-up loops ran.
+  // K1 only keeps the row trackers when yclip_suffix is live; a dead one can never win (Sn <= MIN/2 + S)
+  const bool ys_live = ys > DEAD_CLIP;
   {
-    // row 0
     int32_t s0, c0;
     if (n == 0) {
       s0 = 0;
@@ -282,83 +312,127 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
       Snm = ys;
       Lym = n;
     } else {
-      v.row(ROWS_SL, 0) = s0;
-      v.row(ROWS_IL, 0) = MIN_SCORE;
-      v.row(ROWS_NL, 0) = c0;
-      v.row(ROWS_SN, 0) = ys;
-      v.row(ROWS_LY, 0) = 0;  // Ly[0] = n
       uint32_t s_above = cell_s((uint32_t)c0);  // pre fix-up s_bits(i-1, n)
-      for (int32_t i = 1; i < m; ++i) {
-        uint32_t cell;
-        if (n == 0) {
-          const int32_t s = col0_S(sc, i);
-          v.row(ROWS_SL, i) = s;
-          v.row(ROWS_IL, i) = col0_I(sc, i);
-          cell = cell_make(col0_ibits(sc, i), TB_START, col0_sbits(sc, i));
-          const int32_t val = s + ys;
-          v.row(ROWS_SN, i) = val > MIN_SCORE ? val : MIN_SCORE;
-          v.row(ROWS_LY, i) = 0;
-        } else {
-          const uint32_t nb = (uint32_t)v.row(ROWS_NL, i);
-          const uint32_t sbit = v.nib_scode(nb, i, n);
-          cell = cell_make((nb & NB_IEXT) ? (uint32_t)TB_INS : s_above,
-                           (nb & NB_DEXT) ? (uint32_t)TB_DEL : LAZY, sbit);
+      {  // row 0: Sn[0] = yclip_suffix (mod.rs:618, 711)
+        int32_t S = s0;
+        uint32_t cell = (uint32_t)c0;
+        if (ys > S) {
+          S = ys;
+          cell = cell_set_s(cell, TB_YCLIP_SUFFIX);
         }
-        v.row(ROWS_NL, i) = (int32_t)cell;
-        s_above = cell_s(cell);
-      }
-    }
-  }
-
-  // ------------------------------------------------ fix-up 1, mod.rs:809-821
-  // K1 only keeps the row trackers when yclip_suffix is live; a dead one can never win (Sn <= MIN/2 + S)
-  const bool ys_live = ys > DEAD_CLIP;
-  if (m >= 1) {
-    for (int32_t i = 0; i < m; ++i) {
-      int32_t S = v.row(ROWS_SL, i);
-      const int32_t Sn = (i == 0 || ys_live) ? v.row(ROWS_SN, i) : MIN_SCORE;
-      if (Sn > S) {
-        S = Sn;
-        v.row(ROWS_SL, i) = S;
-        v.row(ROWS_NL, i) = (int32_t)cell_set_s((uint32_t)v.row(ROWS_NL, i), TB_YCLIP_SUFFIX);
-      }
-      if (S + xs > SmN) {
-        SmN = S + xs;
-        LxN = m - i;
-        cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
-      }
-    }
-    if (Snm > SmN) {  // i == m
-      SmN = Snm;
-      cmN = cell_set_s(cmN, TB_YCLIP_SUFFIX);
-    }
-    // ---------------------------------------------- fix-up 2, mod.rs:825-843
-    for (int32_t i = 1; i <= m; ++i) {
-      const int32_t s_score = v.row(ROWS_SL, i - 1) + go;
-      int32_t I = (i == m) ? ImN : v.row(ROWS_IL, i);
-      int32_t S = (i == m) ? SmN : v.row(ROWS_SL, i);
-      uint32_t cell = (i == m) ? cmN : (uint32_t)v.row(ROWS_NL, i);
-      if (s_score > I) {
-        I = s_score;
-        cell = cell_set_i(cell, cell_s((uint32_t)v.row(ROWS_NL, i - 1)));
-      }
-      if (s_score > S) {
-        S = s_score;
-        cell = cell_set_s(cell, TB_INS);
-        if (i != m && S + xs > SmN) {
+        v.row(ROWS_SL, 0) = S;
+        v.row(ROWS_IL, 0) = MIN_SCORE;
+        v.row(ROWS_NL, 0) = (int32_t)cell;
+        if (S + xs > SmN) {
           SmN = S + xs;
-          LxN = m - i;
+          LxN = m;
           cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
         }
       }
-      if (i == m) {
-        ImN = I;
-        SmN = S;
-        cmN = cell;
-      } else {
-        v.row(ROWS_IL, i) = I;
-        v.row(ROWS_SL, i) = S;
-        v.row(ROWS_NL, i) = (int32_t)cell;
+      constexpr int UB = 4;
+      for (int32_t i0 = 1; i0 < m; i0 += UB) {
+        int32_t nbv[UB], Sv[UB], Snv[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int32_t i = i0 + u;
+          nbv[u] = Sv[u] = 0;
+          Snv[u] = MIN_SCORE;
+          if (i < m && n != 0) {
+            nbv[u] = v.row(ROWS_NL, i);
+            Sv[u] = v.row(ROWS_SL, i);
+            if (ys_live) Snv[u] = v.row(ROWS_SN, i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int32_t i = i0 + u;
+          if (i >= m) break;
+          uint32_t cell;
+          int32_t S, Sn;
+          if (n == 0) {  // column n is column 0: closed forms (mod.rs:622-671)
+            S = col0_S(sc, i);
+            v.row(ROWS_IL, i) = col0_I(sc, i);
+            cell = cell_make(col0_ibits(sc, i), TB_START, col0_sbits(sc, i));
+            const int32_t val = S + ys;
+            Sn = val > MIN_SCORE ? val : MIN_SCORE;
+            if (!ys_live) Sn = MIN_SCORE;
+            v.row(ROWS_LY, i) = 0;
+          } else {
+            const uint32_t nb = (uint32_t)nbv[u];
+            cell = cell_make((nb & NB_IEXT) ? (uint32_t)TB_INS : s_above, (nb & NB_DEXT) ? (uint32_t)TB_DEL : LAZY,
+                             v.nib_scode(nb, i, n));
+            S = Sv[u];
+            Sn = Snv[u];
+          }
+          s_above = cell_s(cell);
+          if (Sn > S) {  // fix-up 1
+            S = Sn;
+            cell = cell_set_s(cell, TB_YCLIP_SUFFIX);
+          }
+          v.row(ROWS_SL, i) = S;
+          v.row(ROWS_NL, i) = (int32_t)cell;
+          if (S + xs > SmN) {
+            SmN = S + xs;
+            LxN = m - i;
+            cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
+          }
+        }
+      }
+      if (Snm > SmN) {  // i == m
+        SmN = Snm;
+        cmN = cell_set_s(cmN, TB_YCLIP_SUFFIX);
+      }
+      // ---------------------------------------------- fix-up 2, mod.rs:825-843
+      int32_t S_prev = v.row(ROWS_SL, 0);
+      uint32_t cell_prev = (uint32_t)v.row(ROWS_NL, 0);
+      for (int32_t i0 = 1; i0 <= m; i0 += UB) {
+        int32_t Iv[UB], Sv[UB], Cv[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int32_t i = i0 + u;
+          Iv[u] = Sv[u] = Cv[u] = 0;
+          if (i < m) {
+            Iv[u] = v.row(ROWS_IL, i);
+            Sv[u] = v.row(ROWS_SL, i);
+            Cv[u] = v.row(ROWS_NL, i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int32_t i = i0 + u;
+          if (i > m) break;
+          const int32_t s_score = S_prev + go;
+          int32_t I = (i == m) ? ImN : Iv[u];
+          int32_t S = (i == m) ? SmN : Sv[u];
+          uint32_t cell = (i == m) ? cmN : (uint32_t)Cv[u];
+          bool dirty = false;
+          if (s_score > I) {
+            I = s_score;
+            cell = cell_set_i(cell, cell_s(cell_prev));
+            dirty = true;
+          }
+          if (s_score > S) {
+            S = s_score;
+            cell = cell_set_s(cell, TB_INS);
+            dirty = true;
+            if (i != m && S + xs > SmN) {
+              SmN = S + xs;
+              LxN = m - i;
+              cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
+            }
+          }
+          if (i == m) {
+            ImN = I;
+            SmN = S;
+            cmN = cell;
+          } else if (dirty) {
+            v.row(ROWS_IL, i) = I;
+            v.row(ROWS_SL, i) = S;
+            v.row(ROWS_NL, i) = (int32_t)cell;
+          }
+          S_prev = S;
+          cell_prev = cell;
+        }
       }
     }
   }

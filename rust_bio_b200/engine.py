@@ -96,6 +96,9 @@ class Engine:
     def set_tuning(self, lanes_per_pair: int, rows_per_lane: int):
         self._check(self._L.b2a_engine_set_tuning(self._h, lanes_per_pair, rows_per_lane))
 
+    def set_pipeline(self, chunks: int):
+        self._check(self._L.b2a_engine_set_pipeline(self._h, int(chunks)))
+
     def set_traceback_budget(self, nbytes: int):
         self._check(self._L.b2a_engine_set_traceback_budget(self._h, int(nbytes)))
 

@@ -222,6 +222,31 @@ def test_waves_give_identical_results(eng, oracle):
     assert ops1 == ops2
 
 
+def test_pipelined_batch_equals_single_shot(eng, oracle):
+    """b2a_align_batch pipelines >= 262,144 pairs in chunks over two internal engines: same results,
+    ops placed contiguously in caller order (ragged lengths, so chunks have different plans)."""
+    from rust_bio_b200 import synth
+    n = 300_000
+    batch = synth.ragged_pairs(77, n, 36, 44, min_len=1)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    eng.set_pipeline(0)
+    try:
+        a = eng.align_batch(MODES["semiglobal"], cs, batch)
+    finally:
+        eng.set_pipeline(4)
+    b = eng.align_batch(MODES["semiglobal"], cs, batch)
+    for k in ("score", "xstart", "xend", "ystart", "yend", "ops_off"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    tot = int(a.ops_off[-1])
+    assert np.array_equal(a.ops[:tot], b.ops[:tot])
+    idx = np.random.default_rng(0).integers(0, n, 500)
+    sub = (batch[0], batch[1][idx], batch[2][idx], batch[3][idx], batch[4][idx])
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "semiglobal", s, sub, threads=8)
+    got = {k: v[idx] for k, v in b.as_dict().items()}
+    assert_same(got, [b.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "pipelined sample")
+
+
 def test_full_size_c2_properties(eng, oracle):
     """BASELINE config 2 at full size (1M pairs): size-independent properties + sampled oracle parity.
     - every returned path re-scores to the returned score (4.0 gap model, mod.rs:9-15);

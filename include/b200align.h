@@ -155,7 +155,7 @@ int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t row
 
 /* b2a_align_batch cuts batches of >= 262,144 pairs into `chunks` pieces that alternate between two
  * internal engines, so one chunk's copies and host planning overlap the other's kernels.
- * chunks < 2 disables the pipeline (default 4). Results are identical either way. */
+ * chunks < 2 disables the pipeline (default 5; the first and last chunk are half-size). Results are identical either way. */
 int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks);
 
 /* One-call form: Aligner::{custom,global,semiglobal,local} over a batch with

@@ -7,7 +7,9 @@
 // alignment in this library: without a usable CUDA device every call fails.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
 #include <string>
@@ -86,6 +88,7 @@ struct b2a_engine {
   uint64_t n_pairs = 0, blob_bytes = 0;
   uint64_t h2d_bytes = 0;
   std::vector<int32_t> lut_host;
+  std::vector<uint8_t> last_syms;  // alphabet used by the last stage (given or discovered)
   uint8_t codemap_host[256];
 
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
@@ -99,7 +102,7 @@ struct b2a_engine {
 
   // software pipeline of b2a_align_batch: the batch is cut into chunks that alternate between two
   // child engines (own streams and buffers) so chunk c+1's H2D and host planning overlap chunk c's kernels
-  int pipe_chunks = 4;
+  int pipe_chunks = 5;
   struct PipeSlot {
     b2a_engine* eng = nullptr;
     uint64_t* h_opsoff = nullptr;  // pinned
@@ -310,7 +313,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   CK(e->d_ctl.reserve(2048));
   CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
   bool present[256] = {false};
-  if (s->table && s->alphabet && s->alphabet_len) {
+  if (s->alphabet && s->alphabet_len) {  // caller-supplied alphabet (tabulated MatchFunc or MatchParams alike)
     for (uint32_t k = 0; k < s->alphabet_len; ++k) present[s->alphabet[k]] = true;
   } else {
     uint32_t* flags = e->d_ctl.as<uint32_t>() + 256;  // 256 words
@@ -328,6 +331,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   for (int k = 0; k < 256; ++k)
     if (present[k]) syms.push_back(k);
   if (syms.empty()) syms.push_back(0);
+  e->last_syms.assign(syms.begin(), syms.end());
   int64_t maxabs = std::max<int64_t>(std::llabs((long long)s->match_score), std::llabs((long long)s->mismatch_score));
   for (int k = 0; k < 256; ++k) e->codemap_host[k] = (uint8_t)k;
   e->lut_host.clear();
@@ -695,14 +699,31 @@ static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results*
 static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
                                      const b2a_pairs* pairs, b2a_results* r, b2a_stats* stats) {
   const uint64_t n = pairs->n_pairs;
+  // chunk boundaries: K chunks, the first and the last half as large as the middle ones (the GPU idles
+  // while the first chunk is staged and the host idles while the last one drains)
   const uint64_t K = (uint64_t)e->pipe_chunks;
-  const uint64_t CH = ((n + K - 1) / K + 31) / 32 * 32;
+  std::vector<uint64_t> cut(K + 1, 0);
+  {
+    const double unit = (double)n / (double)(K - 1);
+    double acc = 0;
+    for (uint64_t c = 0; c < K; ++c) {
+      acc += (c == 0 || c == K - 1) ? unit * 0.5 : unit;
+      cut[c + 1] = std::min<uint64_t>(n, ((uint64_t)acc + 31) / 32 * 32);
+    }
+    cut[K] = n;
+  }
   b2a_stats agg;
   std::memset(&agg, 0, sizeof(agg));
   uint64_t base = 0;
   int32_t rc = B2A_OK;
-  for (uint64_t c = 0; c * CH < n && rc == B2A_OK; ++c) {
-    const uint64_t lo = c * CH, hi = std::min(n, lo + CH), nc = hi - lo;
+  std::vector<uint8_t> inferred;
+  const bool dbg = getenv("B2A_DEBUG_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t00 = now();
+  for (uint64_t c = 0; c < K && rc == B2A_OK; ++c) {
+    const double tc0 = now();
+    if (cut[c + 1] <= cut[c]) continue;
+    const uint64_t lo = cut[c], hi = cut[c + 1], nc = hi - lo;
     b2a_engine::PipeSlot& sl = e->slots[c % 2];
     if (sl.busy) {
       rc = slot_finish(e, sl, r, base, &agg);
@@ -752,8 +773,23 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     b2a_pairs sub{pairs->seq_blob + bmin, sl.xoff.data(), pairs->x_len + lo, sl.yoff.data(), pairs->y_len + lo,
                   bmax - bmin, nc};
     b2a_engine* ch = sl.eng;
-    rc = b2a_batch_stage(ch, mode, scoring, &sub);
+    const double tc1 = now();
+    // Alphabet: chunk 0 discovers it on the (then idle) device; later chunks reuse it optimistically so
+    // that their stage does not have to wait behind the other slot's persistent fill kernel.  A byte
+    // outside it is caught by K0 (bad-symbol flag) and the whole batch is then redone in one shot.
+    b2a_scoring sc_chunk = *scoring;
+    if (!(scoring->alphabet && scoring->alphabet_len) && c > 0 && !inferred.empty()) {
+      sc_chunk.alphabet = inferred.data();
+      sc_chunk.alphabet_len = (uint32_t)inferred.size();
+    }
+    rc = b2a_batch_stage(ch, mode, &sc_chunk, &sub);
+    if (rc == B2A_OK && c == 0 && !(scoring->alphabet && scoring->alphabet_len)) inferred = ch->last_syms;
+    const double tc2 = now();
     if (rc == B2A_OK) rc = b2a_batch_run(ch);
+    const double tc3 = now();
+    if (dbg)
+      fprintf(stderr, "[b2a pipe] chunk %llu: t=%.2f finish+prep %.2f ms, stage %.2f ms, run(launch) %.2f ms\n",
+              (unsigned long long)c, tc0 - t00, tc1 - tc0, tc2 - tc1, tc3 - tc2);
     if (rc) {
       e->fail(rc, ch->err);
       break;
@@ -781,16 +817,26 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     sl.busy = true;
   }
   // drain in chunk order: the older chunk lives in the slot the next chunk would use
-  uint64_t nchunks = (n + CH - 1) / CH;
-  for (uint64_t c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; ++c) {
-    b2a_engine::PipeSlot& sl = e->slots[c % 2];
-    if (!sl.busy) continue;
+  // (slots hold chunks in alternation; the one with the smaller `lo` is the older)
+  for (int pass = 0; pass < 2; ++pass) {
+    b2a_engine::PipeSlot* pick = nullptr;
+    for (auto& cand : e->slots)
+      if (cand.busy && (!pick || cand.lo < pick->lo)) pick = &cand;
+    if (!pick) break;
+    b2a_engine::PipeSlot& sl = *pick;
     if (rc == B2A_OK) {
       rc = slot_finish(e, sl, r, base, &agg);
     } else {
       cudaStreamSynchronize(sl.eng->stream);
       sl.busy = false;
     }
+  }
+  if (rc == B2A_E_INVALID && !inferred.empty() && e->err.find("alphabet") != std::string::npos) {
+    // a later chunk held a byte the first chunk did not: redo the batch without the optimistic reuse
+    int32_t r2 = b2a_batch_stage(e, mode, scoring, pairs);
+    if (r2 == B2A_OK) r2 = b2a_batch_run(e);
+    if (r2 == B2A_OK) r2 = b2a_batch_fetch(e, r, stats);
+    return r2;
   }
   if (rc) return rc;
   if (r->ops_off) r->ops_off[n] = base;

@@ -233,7 +233,7 @@ def test_pipelined_batch_equals_single_shot(eng, oracle):
     try:
         a = eng.align_batch(MODES["semiglobal"], cs, batch)
     finally:
-        eng.set_pipeline(4)
+        eng.set_pipeline(5)
     b = eng.align_batch(MODES["semiglobal"], cs, batch)
     for k in ("score", "xstart", "xend", "ystart", "yend", "ops_off"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
@@ -245,6 +245,27 @@ def test_pipelined_batch_equals_single_shot(eng, oracle):
     ref, ref_ops = oracle_batch(oracle, "semiglobal", s, sub, threads=8)
     got = {k: v[idx] for k, v in b.as_dict().items()}
     assert_same(got, [b.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "pipelined sample")
+
+
+def test_pipeline_alphabet_reuse_falls_back_when_a_later_chunk_has_new_symbols(eng, oracle):
+    """The pipeline reuses chunk 0's discovered alphabet; a symbol that first appears in a later chunk must
+    not change results (the batch is redone in one shot)."""
+    from rust_bio_b200 import synth
+    n = 280_000
+    batch = list(synth.ragged_pairs(78, n, 20, 24, alphabet=b"ACG", min_len=1))
+    blob = batch[0].copy()
+    last = n - 5
+    blob[int(batch[1][last])] = ord("T")          # a 'T' only in the last chunk
+    batch[0] = blob
+    batch = tuple(batch)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    b = eng.align_batch(MODES["local"], cs, batch)
+    idx = np.concatenate([np.arange(200), np.arange(n - 200, n)])
+    sub = (batch[0], batch[1][idx], batch[2][idx], batch[3][idx], batch[4][idx])
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "local", s, sub, threads=8)
+    got = {k: v[idx] for k, v in b.as_dict().items()}
+    assert_same(got, [b.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "alphabet fallback")
 
 
 def test_full_size_c2_properties(eng, oracle):

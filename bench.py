@@ -287,9 +287,15 @@ def main():
         nstrips = -(-(M - 1) // (G * R))
         per_pair = (M + N_LEN) + 16 * N_LEN * (2 * nstrips - 1) + 20 * (M - 1)
         fill_bytes = P * per_pair + tb_bytes
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "fill_traffic.json")
+        if os.path.exists(tpath) and (G, R) == (1, 16):
+            with open(tpath) as f:
+                traffic = int(json.load(f)["dram_bytes_per_pair"] * P)  # ncu dram read+write per pair x pairs of this launch
         roof = {"bound": "hbm", "kernel": f"fill_kernel<G={G},R={R},local>",
                 "achieved": round(fill_bytes / (fill_ms * 1e-3) / 1e9, 2), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(fill_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak, 4), "traffic": None,
+                "frac": round(fill_bytes / (fill_ms * 1e-3) / 1e9 / hbm_peak, 4), "traffic": traffic,
+                "traffic_source": "profiles/fill_traffic.json (ncu --set full capture at 200k pairs, scaled per pair)" if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(fill_bytes),
                 "kernel_ms": round(fill_ms, 4),
                 "note": "integer DP: the binding roof is int32 ALU issue (see int32_alu), not HBM"}

@@ -18,6 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 SO = os.path.join(CSRC, "libb200align.so")
 SHAPES = [(1, 16), (1, 8), (1, 20), (2, 16), (2, 20), (4, 16), (8, 16), (32, 8), (32, 16)]
+# minimum resident CTAs per SM asked of ptxas per shape (__launch_bounds__): measured choice, see DESIGN.md
+MIN_BLOCKS = {(1, 16): int(os.environ.get("B2A_MINB_1_16", "3"))}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fwrapv", "--expt-relaxed-constexpr"]
@@ -49,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(o)
         src = os.path.join(CSRC, "b2a_fill_inst.cu")
         if force or _stale(o, hdrs + [src]):
-            jobs.append([NVCC, *FLAGS, f"-DB2A_G={g}", f"-DB2A_R={r}", "-c", src, "-o", o])
+            jobs.append([NVCC, *FLAGS, f"-DB2A_G={g}", f"-DB2A_R={r}", f"-DB2A_MINB={MIN_BLOCKS.get((g, r), 1)}", "-c", src, "-o", o])
     eo = os.path.join(OBJ, "engine.o")
     objs.append(eo)
     esrc = os.path.join(CSRC, "b2a_engine.cu")

@@ -423,11 +423,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 constexpr int FILL_WARPS = 4;
+#ifndef B2A_MINB
+#define B2A_MINB 1  // minimum resident CTAs per SM requested from ptxas (set per shape by build.py)
+#endif
 
 // Persistent kernel: every warp pulls warp-tasks (32/G pairs) from a global
 // counter, stages their sequences with two bulk copies and fills them.
 template <int G, int R, int FLAGS>
-__global__ void __launch_bounds__(FILL_WARPS * 32) fill_kernel(const FillParams prm) {
+__global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const FillParams prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int P = 32 / G;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;

@@ -571,11 +571,8 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
 
 #if defined(__CUDACC__)
 
-__global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
-  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= prm.nblocks) return;
-  const Block blk = prm.blocks[gw];
+// K2 for one pair (lane) of a block
+__device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& blk, const int lane) {
   if ((uint32_t)lane >= blk.npairs) return;
   const uint32_t sp = blk.first + lane;
   const int32_t P = 32 / prm.G;
@@ -619,6 +616,16 @@ __global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) prm.clip_len[4 * (size_t)dst + k] = o.clip[k];
 }
+
+#if defined(B2A_DEFINE_WALK_KERNEL)  // one translation unit (b2a_engine.cu) owns the stand-alone kernel
+__global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= prm.nblocks) return;
+  const Block blk = prm.blocks[gw];
+  walk_lane(prm, blk, lane);
+}
+#endif
 
 #endif
 

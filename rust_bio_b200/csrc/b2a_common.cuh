@@ -47,6 +47,7 @@ enum : int {
   F_CLIPX = 4,       // xclip_prefix and yclip_prefix live: xclip_score term (mod.rs:724-728,775-778)
   F_LUT = 8,         // substitution scores from a compact LUT in shared memory (else MatchParams)
   F_PACKTRK = 16,    // trackers as packed keys 4096*value + (4095-index): needs m,n <= 4095, |S| < 2^17
+  F_RELU = 32,       // with F_CLIPX: xclip_score(j) == 0 for every column (x/y prefix clips both 0): one fused max3-relu
 };
 
 struct DevScoring {
@@ -131,6 +132,14 @@ B2A_HD uint32_t row0_sbits(const DevScoring& sc, int32_t j, int32_t n) {
 // xclip_score of column j (mod.rs:724-728)
 B2A_HD int32_t xclip_score(const DevScoring& sc, int32_t j) {
   return sc.xclip_prefix + imax(sc.yclip_prefix, sc.gap_open + sc.gap_extend * (j - 1));
+}
+
+// Boundary-row index of (column j, pair pi) inside a block.  Fills with several pairs per warp (G < 32)
+// want [column][pair] (the warp's pairs touch one line per column); the warp-per-pair fill (G == 32)
+// reads/writes one pair's row column after column from a single lane, so [pair][column] keeps those
+// accesses inside cache lines (measured on C5: 408 -> 325 ms; the same layout for G = 8 cost C3 8 %).
+B2A_HD int64_t bnd_index(int32_t G, int32_t j, int32_t pi, int32_t maxn) {
+  return G < 32 ? (int64_t)j * 32 + pi : (int64_t)pi * (maxn + 1) + j;
 }
 
 // Traceback words per lane per 8-column group: rows are grouped by four so the

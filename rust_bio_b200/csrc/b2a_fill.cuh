@@ -88,6 +88,13 @@ B2A_HD int32_t max3(int32_t a, int32_t b, int32_t c) {
   return imax(a, imax(b, c));
 #endif
 }
+B2A_HD int32_t max3_relu(int32_t a, int32_t b, int32_t c) {  // max(a, b, c, 0): one VIMNMX3.RELU
+#if defined(__CUDA_ARCH__)
+  return __vimax3_s32_relu(a, b, c);
+#else
+  return imax(imax(a, imax(b, c)), 0);
+#endif
+}
 B2A_HD int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 // fused add+max / add+min (DPX: one VIADDMNMX on the ALU pipe)
 B2A_HD int32_t addmax(int32_t a, int32_t b, int32_t c) {
@@ -143,6 +150,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   constexpr bool CX = (FLAGS & F_CLIPX) != 0;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
   constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
+  constexpr bool RELU = (FLAGS & F_RELU) != 0;
   const int32_t go4i = 4 * c.sc.gap_open + 2, go4d = 4 * c.sc.gap_open + 1, ge4 = 4 * c.sc.gap_extend;
   const int32_t ma4 = 4 * c.sc.match_score + 3, mi4 = 4 * c.sc.mismatch_score + 3;
   const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
@@ -164,8 +172,13 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
     const int32_t i4 = addmax(iup, ge4, iop);
     const int32_t dop = fmad(Sp[r], one, go4d);
     const int32_t d4 = addmax(Dp[r], ge4, dop);
-    int32_t sP = max3(m4, i4, d4);
-    if (CX) sP = imax(sP, x4);
+    int32_t sP;
+    if (CX && RELU) {
+      sP = max3_relu(m4, i4, d4);  // x4 == 0 (code 0 in the low bits) for every column
+    } else {
+      sP = max3(m4, i4, d4);
+      if (CX) sP = imax(sP, x4);
+    }
     const int32_t s4 = sP & ~3;
     // nibble = code | iext << 2 | dext << 3 = (sP - s4) + min(i4 - iop, 4) + 2 * min(d4 - dop, 4),
     // accumulated as tbacc*16 + nibble with the additions on the FMA pipe
@@ -275,7 +288,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   int4 pre = make_int4(0, 0, 0, 0);
   const bool top_from_mem = (c.l == 0) && (s > 0);
   const bool top_from_row0 = (c.l == 0) && (s == 0);
-  if (top_from_mem && c.maxn >= 1) pre = c.bnd[1 * 32 + c.pi];
+  if (top_from_mem && c.maxn >= 1) pre = c.bnd[bnd_index(G, 1, c.pi, c.maxn)];
   const bool writer =
       MASKED ? (rv >= 1 && (c.l == G - 1 || rowbase + R >= m - 1)) : (c.l == G - 1);
   int32_t cap_s = 0, cap_i = 0;
@@ -309,7 +322,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
           in_tv = pre.z;
           in_ti = pre.w;
         }
-        if (j < c.maxn) pre = c.bnd[(j + 1) * 32 + c.pi];  // prefetch next column's boundary
+        if (j < c.maxn) pre = c.bnd[bnd_index(G, j + 1, c.pi, c.maxn)];  // prefetch next column's boundary
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
       if (j == n) {
@@ -326,7 +339,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         o.y = MASKED ? cap_i : iup;
         o.z = TC ? Tv : t_none;
         o.w = TC ? Ti : m;
-        c.bnd[j * 32 + c.pi] = o;
+        c.bnd[bnd_index(G, j, c.pi, c.maxn)] = o;
       }
       in_s = sup;
       in_i = iup;

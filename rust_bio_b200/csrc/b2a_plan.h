@@ -136,6 +136,8 @@ inline int scoring_flags(const DevScoring& sc, int64_t score_bound = (1ll << 40)
     f = F_TRACK_ROWS;
   }
   if (sc.alpha) f |= F_LUT;
+  // local-style clips: xclip_score(j) = xp + max(yp, go + ge (j-1)) == 0 for every j (go, ge <= 0)
+  if ((f & F_CLIPX) && sc.xclip_prefix == 0 && sc.yclip_prefix == 0) f |= F_RELU;
   if ((f & (F_TRACK_ROWS | F_TRACK_COLS)) && score_bound < (1ll << 17) && maxm <= 4095 && maxn <= 4095)
     f |= F_PACKTRK;
   return f;

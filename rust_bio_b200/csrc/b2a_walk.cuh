@@ -62,6 +62,9 @@ struct PairView {
   const uint32_t* tb;  // block base
   int32_t sub, g;      // task inside the block, slot inside the task
   int32_t packtrk;
+  int32_t maxn;        // block maximum of n
+  int64_t bnd_base;    // boundary row of this pair: bnd[bnd_base + j * bnd_stride] (see bnd_index)
+  int32_t bnd_stride;
 
   B2A_HD int32_t xsym(int32_t i) const {  // x[i-1]
     const int32_t b = i - 1;
@@ -78,9 +81,9 @@ struct PairView {
   B2A_HD int32_t& row(int arr, int32_t i) const { return rows[(arr * rows_pad + i) * 32 + pi]; }
   B2A_HD int4 load_bnd(int32_t j) const {
 #if defined(__CUDA_ARCH__)
-    return __ldg(&bnd[j * 32 + pi]);  // read-only path: K1 wrote it in an earlier launch
+    return __ldg(&bnd[bnd_base + (int64_t)j * bnd_stride]);  // read-only path: K1 wrote it in an earlier launch
 #else
-    return bnd[j * 32 + pi];
+    return bnd[bnd_base + (int64_t)j * bnd_stride];
 #endif
   }
   // compressed traceback nibble of an interior cell 1 <= i <= m-1, 1 <= j <= n
@@ -512,7 +515,7 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
       int32_t lx;
       if (j == n) lx = LxN;
       else if (j == 0) lx = Lx0;
-      else lx = (m >= 2) ? m - decode_boundary(v.bnd[j * 32 + v.pi], v.packtrk != 0, xs, m).Ti : 0;
+      else lx = (m >= 2) ? m - decode_boundary(v.load_bnd(j), v.packtrk != 0, xs, m).Ti : 0;
       if (!filter_clips) {
         *(--ops_end) = 4;
         ++nops;
@@ -591,6 +594,9 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
   v.sub = lane / P;
   v.g = lane % P;
   v.packtrk = prm.packtrk;
+  v.maxn = (int32_t)blk.maxn;
+  v.bnd_base = bnd_index(prm.G, 0, lane, v.maxn);
+  v.bnd_stride = (int32_t)(bnd_index(prm.G, 1, lane, v.maxn) - v.bnd_base);
   const uint32_t* seqw = reinterpret_cast<const uint32_t*>(prm.seq + blk.seq_off);
   v.xw = seqw + (size_t)v.sub * blk.xwords * P + v.g;
   v.yw = seqw + (size_t)prm.G * blk.xwords * P + (size_t)v.sub * blk.ywords * P + v.g;

@@ -69,6 +69,10 @@ void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring&
     SIM_CASE(F_LUT | F_TRACK_ROWS | F_PACKTRK)
     SIM_CASE(F_LUT | ALL)
     SIM_CASE(F_LUT | ALL | F_PACKTRK)
+    SIM_CASE(ALL | F_RELU)
+    SIM_CASE(ALL | F_PACKTRK | F_RELU)
+    SIM_CASE(F_LUT | ALL | F_RELU)
+    SIM_CASE(F_LUT | ALL | F_PACKTRK | F_RELU)
     default: std::abort();
   }
 }
@@ -188,6 +192,9 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
       v.sub = (int32_t)lane / 32;
       v.g = (int32_t)lane % 32;
       v.packtrk = (flags & F_PACKTRK) ? 1 : 0;
+      v.maxn = (int32_t)blk.maxn;
+      v.bnd_base = bnd_index(1, 0, (int32_t)lane, v.maxn);
+      v.bnd_stride = 32;
       const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
       v.xw = seqw + v.g;
       v.yw = seqw + (size_t)blk.xwords * 32 + v.g;

@@ -78,6 +78,7 @@ struct Block {
   uint64_t rowm_off; // bytes into the row-m arena: (maxn+1)*32 bytes
   uint64_t tb_off;   // bytes into the traceback arena: G * nstrips * K * TBW * 512
   uint64_t ops_off;  // bytes into the ops scratch: 32 * (maxm+maxn+4)
+  uint64_t strip_task_base;  // strip-pipelined fill (G == 32): tasks (pair, strip) of earlier blocks of the wave
 };
 
 // rows arena sub-arrays (each rows_pad*32 int32, index [row][pair])

@@ -94,7 +94,7 @@ struct b2a_engine {
 
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
-      d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_bcells, d_bstatus,
+      d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
       d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> wave_ev;  // 3 per wave: fill start, fill stop / walk start, walk stop
@@ -143,12 +143,16 @@ void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_
   if (n_pairs >= 32ull * 148 * 4 && stage1 <= kMaxStageSmem && maxm <= 2048) {
     *G = 1;
     *R = 16;
-  } else if (n_pairs >= 4ull * 148 * 8 && maxm <= 4096) {
-    *G = 8;
+  } else if ((n_pairs >= 16ull * 148 * 8 && maxm <= 4096) || maxm <= 129) {
+    *G = 8;  // enough pairs to fill the GPU four to a warp (or a single strip anyway)
     *R = 16;
   } else {
+    // warp per pair, (pair, strip) tasks pipelined through the boundary row: fills the GPU from a few long
+    // pairs.  16 rows per lane is ~15% faster per cell than 8 unless the 512-row strips pad m much more.
     *G = 32;
-    *R = 8;
+    const uint64_t rows = maxm > 1 ? maxm - 1 : 1;
+    const uint64_t pad16 = (rows + 511) / 512 * 512, pad8 = (rows + 255) / 256 * 256;
+    *R = (pad16 * 100 <= pad8 * 112) ? 16 : 8;
   }
 }
 
@@ -211,7 +215,7 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
                     &e->d_opsscratch, &e->d_lut, &e->d_codemap, &e->d_ctl, &e->d_score, &e->d_xs,
                     &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
-                    &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_bcells,
+                    &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_prog, &e->d_bcells,
                     &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill,
                     &e->d_bfoff};
   for (DevBuf* b : bufs) b->release();
@@ -445,6 +449,7 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   CK(e->d_rows.reserve(pl.max_rows + 16));
   CK(e->d_rowm.reserve(pl.max_rowm + 16));
   CK(e->d_tb.reserve(pl.max_tb + 16));
+  CK(e->d_prog.reserve(pl.max_strip_tasks * 4 + 16));
   CK(e->d_opsscratch.reserve(pl.ops_bytes + 16));
   CK(e->d_lut.reserve(e->lut_host.size() * 4 + 16));
   CK(e->d_codemap.reserve(256));
@@ -526,6 +531,16 @@ int32_t b2a_batch_run(b2a_engine* e) {
     fp.task_counter = ctl + 2 + wi;
     fp.smem_seq_bytes = pl.smem_seq_bytes;
     fp.one = 1;
+    uint32_t fill_tasks = nb * (uint32_t)pl.G;
+    if (pl.G == 32 && w.strip_tasks >= 0x7fffffffull) return e->fail(B2A_E_RANGE, "too many strip tasks in one wave");
+    if (pl.G == 32 && w.strip_tasks > 0) {
+      // warp-per-pair shape: the strips of a pair are separate tasks that pipeline through the boundary row
+      // (b2a_fill.cuh "strip-pipelined mode"), so a few long pairs still fill the GPU
+      fp.progress = e->d_prog.as<uint32_t>();
+      fp.n_strip_tasks = (uint32_t)w.strip_tasks;
+      fill_tasks = fp.n_strip_tasks;
+      CK(cudaMemsetAsync(fp.progress, 0, (size_t)w.strip_tasks * 4, st));
+    }
     fp.sc = e->sc;
     while (e->wave_ev.size() < 3 * (wi + 1)) {
       cudaEvent_t v;
@@ -564,7 +579,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     //  walk holds one of only 12 resident warps per SM; K2 stays its own launch)
     const bool fuse = false;
     CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
-    CK(e->shape->launch(e->flags, fp, nb * (uint32_t)pl.G, e->num_sms, st, &e->last_grid));
+    CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &e->last_grid));
     ++e->launches;
     CK(cudaEventRecord(e->wave_ev[3 * wi + 1], st));
     if (!fuse) {

@@ -38,6 +38,8 @@ struct FillParams {
   uint32_t* task_counter;
   uint32_t smem_seq_bytes;  // per-warp staging bytes
   int32_t one;              // must be 1 (opaque to the compiler, see fadd())
+  uint32_t* progress;       // strip-pipelined mode (G == 32): columns published per (pair, strip) task, else null
+  uint32_t n_strip_tasks;   // strip-pipelined mode: number of (pair, strip) tasks of this launch
   DevScoring sc;
 };
 
@@ -62,6 +64,9 @@ struct LaneCtx {
   int32_t* rows;         // block base, ROWS_ARRAYS arrays of [rows_pad][32]
   uint4* tb;             // task base: [strip][k][q][32]
   uint32_t lut_base;     // device: shared-space byte address of the LUT; host sim: 0
+  uint32_t* prog_mine;   // strip-pipelined: where this strip publishes its boundary progress (else null)
+  uint32_t* prog_prev;   // strip-pipelined: progress of the strip above (null for strip 0)
+  int32_t only_strip;    // strip-pipelined: the one strip this task fills (-1: all strips in order)
   int32_t one;           // an opaque 1 (kernel parameter): lets adds be issued as IMAD on the FMA pipe
 };
 
@@ -133,6 +138,30 @@ B2A_HD int32_t lut_at(const void* host_base, uint32_t byte_addr) {
   return v;
 #else
   return *reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(host_base) + byte_addr);
+#endif
+}
+
+// strip-pipelined mode: strips of one pair run concurrently in different warps; the boundary row is
+// handed over through HBM/L2 with a per-strip progress word (release: fence + volatile store,
+// acquire: volatile poll + fence, boundary loads bypass L1).
+B2A_HD uint32_t ld_progress(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const volatile uint32_t*>(p);
+#else
+  return *p;
+#endif
+}
+B2A_HD int4 ld_boundary(const int4* p, bool bypass_l1) {
+#if defined(__CUDA_ARCH__)
+  return bypass_l1 ? __ldcg(p) : *p;
+#else
+  (void)bypass_l1;
+  return *p;
+#endif
+}
+B2A_HD void fence_device() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
 #endif
 }
 
@@ -288,7 +317,22 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   int4 pre = make_int4(0, 0, 0, 0);
   const bool top_from_mem = (c.l == 0) && (s > 0);
   const bool top_from_row0 = (c.l == 0) && (s == 0);
-  if (top_from_mem && c.maxn >= 1) pre = c.bnd[bnd_index(G, 1, c.pi, c.maxn)];
+  // strip-pipelined: number of columns the strip above has published so far
+  uint32_t avail = 0;
+  const bool piped = c.prog_mine != nullptr;
+  auto wait_col = [&](int32_t col) {
+    if (piped && c.prog_prev && (int32_t)avail < col) {
+      do {
+        avail = ld_progress(c.prog_prev);
+      } while ((int32_t)avail < col);
+      fence_device();
+    }
+  };
+  const bool top_valid = top_from_mem && rv >= 1;  // a strip without valid rows needs no boundary (ragged blocks)
+  if (top_valid && n >= 1) {
+    wait_col(1);
+    pre = ld_boundary(&c.bnd[bnd_index(G, 1, c.pi, c.maxn)], piped);
+  }
   const bool writer =
       MASKED ? (rv >= 1 && (c.l == G - 1 || rowbase + R >= m - 1)) : (c.l == G - 1);
   int32_t cap_s = 0, cap_i = 0;
@@ -322,7 +366,10 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
           in_tv = pre.z;
           in_ti = pre.w;
         }
-        if (j < c.maxn) pre = c.bnd[bnd_index(G, j + 1, c.pi, c.maxn)];  // prefetch next column's boundary
+        if (j < n && top_valid) {  // prefetch next column's boundary
+          wait_col(j + 1);
+          pre = ld_boundary(&c.bnd[bnd_index(G, j + 1, c.pi, c.maxn)], piped);
+        }
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
       if (j == n) {
@@ -340,6 +387,10 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         o.z = TC ? Tv : t_none;
         o.w = TC ? Ti : m;
         c.bnd[bnd_index(G, j, c.pi, c.maxn)] = o;
+        if (piped && ((j & 15) == 0 || j == n)) {  // publish (release) every 16 columns and at the end
+          fence_device();
+          *reinterpret_cast<volatile uint32_t*>(c.prog_mine) = (uint32_t)j;
+        }
       }
       in_s = sup;
       in_i = iup;
@@ -390,7 +441,9 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
 
 template <int G, int R, int FLAGS>
 B2A_HD void fill_lane(const LaneCtx<G>& c) {
-  for (int32_t s = 0; s < c.nstrips; ++s) {
+  const int32_t s_lo = c.only_strip >= 0 ? c.only_strip : 0;
+  const int32_t s_hi = c.only_strip >= 0 ? c.only_strip + 1 : c.nstrips;
+  for (int32_t s = s_lo; s < s_hi; ++s) {
     // a strip is "full" when every lane of every pair of the task owns R valid rows
     const bool full = c.uniform && ((s + 1) * (G * R) <= c.m - 1);
     if (full) {
@@ -462,31 +515,57 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const F
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  const uint32_t ntasks = prm.nblocks * G;
+  const bool strip_tasks = (G == 32) && prm.progress != nullptr;
+  const uint32_t ntasks = strip_tasks ? prm.n_strip_tasks : prm.nblocks * G;
   uint32_t parity = 0;
   for (;;) {
     uint32_t task = 0;
     if (lane == 0) task = atomicAdd(prm.task_counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= ntasks) break;
-    const uint32_t b = task / G, sub = task % G;
+    uint32_t b, sub;
+    int32_t only_strip = -1;
+    if (strip_tasks) {
+      // (pair, strip) tasks in pair-major order: find the block by its task base (blocks are few)
+      uint32_t lo = 0, hi = prm.nblocks;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (prm.blocks[mid].strip_task_base <= task) lo = mid;
+        else hi = mid;
+      }
+      b = lo;
+      const uint32_t rel = task - (uint32_t)prm.blocks[b].strip_task_base;
+      const uint32_t ns = prm.blocks[b].nstrips;
+      sub = rel / ns;
+      only_strip = (int32_t)(rel % ns);
+    } else {
+      b = task / G;
+      sub = task % G;
+    }
     const Block blk = prm.blocks[b];
+    if (strip_tasks && sub >= blk.npairs) continue;  // padding pair of the last block: nothing to do
     const uint32_t xbytes = blk.xwords * P * 4, ybytes = blk.ywords * P * 4;
+    // a strip task stages only the G*R x symbols of its own rows (P == 1 there); y is needed whole
+    const uint32_t xoff = strip_tasks ? (uint32_t)only_strip * G * R : 0u;
+    const uint32_t xstage = strip_tasks ? (uint32_t)(G * R) : xbytes;
     if (lane == 0) {
       // the previous task's generic-proxy reads of the staging buffer are done (syncwarp below)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, xbytes + ybytes);
+      mbar_expect_tx(bar, xstage + ybytes);
       const uint8_t* src = prm.seq + blk.seq_off;
-      tma_bulk_g2s(stage, src + (size_t)sub * xbytes, xbytes, bar);
-      tma_bulk_g2s(stage + xbytes, src + (size_t)G * xbytes + (size_t)sub * ybytes, ybytes, bar);
+      tma_bulk_g2s(stage, src + (size_t)sub * xbytes + xoff, xstage, bar);
+      tma_bulk_g2s(stage + xstage, src + (size_t)G * xbytes + (size_t)sub * ybytes, ybytes, bar);
     }
     LaneCtx<G> c;
     c.sc = prm.sc;
     c.lut = lut_s;
     c.lut_base = smem_u32(lut_s);
     c.one = prm.one;
-    c.xs = reinterpret_cast<const uint32_t*>(stage);
-    c.ys = reinterpret_cast<const uint32_t*>(stage + xbytes);
+    c.only_strip = only_strip;
+    c.prog_mine = strip_tasks ? prm.progress + task : nullptr;
+    c.prog_prev = (strip_tasks && only_strip > 0) ? prm.progress + task - 1 : nullptr;
+    c.xs = reinterpret_cast<const uint32_t*>(stage) - xoff / 4;  // indexed by absolute row word
+    c.ys = reinterpret_cast<const uint32_t*>(stage + xstage);
     c.g = lane / G;
     c.l = lane % G;
     c.lane = lane;

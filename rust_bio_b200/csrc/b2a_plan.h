@@ -14,6 +14,7 @@ namespace b2a {
 struct Wave {
   uint32_t block_lo, block_hi;  // [lo, hi)
   uint64_t bnd_bytes, rows_bytes, rowm_bytes, tb_bytes;
+  uint64_t strip_tasks;  // sum over the wave's blocks of 32 * nstrips
 };
 
 struct Plan {
@@ -25,6 +26,7 @@ struct Plan {
   std::vector<Wave> waves;
   uint64_t seq_bytes = 0, ops_bytes = 0;
   uint64_t max_bnd = 0, max_rows = 0, max_rowm = 0, max_tb = 0;  // per-wave maxima
+  uint64_t max_strip_tasks = 0;
   uint64_t total_tb = 0;   // traceback bytes the fill stores over the whole batch
   uint64_t cells = 0;
   uint32_t smem_seq_bytes = 0;  // per-warp staging
@@ -63,10 +65,11 @@ inline void build_plan(Plan& p, const uint32_t* x_len, const uint32_t* y_len, ui
   p.waves.clear();
   p.seq_bytes = p.ops_bytes = 0;
   p.max_bnd = p.max_rows = p.max_rowm = p.max_tb = 0;
+  p.max_strip_tasks = 0;
   p.total_tb = 0;
   p.smem_seq_bytes = 0;
   p.maxm = p.maxn = 0;
-  Wave w{0, 0, 0, 0, 0, 0};
+  Wave w{0, 0, 0, 0, 0, 0, 0};
   for (uint32_t b = 0; b < nblocks; ++b) {
     Block& k = p.blocks[b];
     k.first = b * 32;
@@ -87,7 +90,9 @@ inline void build_plan(Plan& p, const uint32_t* x_len, const uint32_t* y_len, ui
     k.rows_pad = k.nstrips * G * R + 2;
     p.maxm = std::max(p.maxm, k.maxm);
     p.maxn = std::max(p.maxn, k.maxn);
-    p.smem_seq_bytes = std::max<uint32_t>(p.smem_seq_bytes, (k.xwords + k.ywords) * P * 4);
+    // the warp-per-pair shape runs (pair, strip) tasks that stage one strip of x (b2a_fill.cuh)
+    const uint32_t stage_x = G == 32 ? (uint32_t)(G * R) : k.xwords * P * 4;
+    p.smem_seq_bytes = std::max<uint32_t>(p.smem_seq_bytes, stage_x + k.ywords * P * 4);
     const uint64_t bnd = align_up((uint64_t)(k.maxn + 1) * 32 * 16, 256);
     const uint64_t rows = align_up((uint64_t)ROWS_ARRAYS * k.rows_pad * 32 * 4, 256);
     const uint64_t rowm = align_up((uint64_t)(k.maxn + 1) * 32 * 2, 256);
@@ -95,12 +100,14 @@ inline void build_plan(Plan& p, const uint32_t* x_len, const uint32_t* y_len, ui
     if (b > w.block_lo && w.tb_bytes + tb > tb_budget) {  // close the wave
       w.block_hi = b;
       p.waves.push_back(w);
-      w = Wave{b, b, 0, 0, 0, 0};
+      w = Wave{b, b, 0, 0, 0, 0, 0};
     }
     k.seq_off = p.seq_bytes;
     p.seq_bytes += align_up((uint64_t)32 * (k.xwords + k.ywords) * 4, 256);
     k.ops_off = p.ops_bytes;
     p.ops_bytes += align_up((uint64_t)32 * (k.maxm + k.maxn + 4), 256);
+    k.strip_task_base = w.strip_tasks;
+    w.strip_tasks += (uint64_t)32 * k.nstrips;
     k.bnd_off = w.bnd_bytes;
     k.rows_off = w.rows_bytes;
     k.rowm_off = w.rowm_bytes;
@@ -120,6 +127,7 @@ inline void build_plan(Plan& p, const uint32_t* x_len, const uint32_t* y_len, ui
     p.max_rows = std::max(p.max_rows, v.rows_bytes);
     p.max_rowm = std::max(p.max_rowm, v.rowm_bytes);
     p.max_tb = std::max(p.max_tb, v.tb_bytes);
+    p.max_strip_tasks = std::max(p.max_strip_tasks, v.strip_tasks);
   }
 }
 

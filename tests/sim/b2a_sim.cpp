@@ -28,6 +28,9 @@ void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int
     c.lut = lut;
     c.lut_base = 0;
     c.one = 1;
+    c.only_strip = -1;
+    c.prog_mine = nullptr;
+    c.prog_prev = nullptr;
     const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
     c.xs = seqw;
     c.ys = seqw + (size_t)G * blk.xwords * P;

@@ -23,7 +23,7 @@ MIN_BLOCKS = {(1, 16): int(os.environ.get("B2A_MINB_1_16", "3"))}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fwrapv", "--expt-relaxed-constexpr"]
-HEADERS = ["b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_kernels.cuh", "b2a_plan.h",
+HEADERS = ["b2a_common.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_kernels.cuh", "b2a_plan.h", "b2a_banded.cuh",
            "b2a_fill_launch.h", os.path.join("..", "..", "include", "b200align.h")]
 
 

@@ -1,4 +1,4 @@
-// K4 + K3: banded::Aligner on the device, one lane per pair.
+// K4 + K3: banded::Aligner on the device (K4: one lane per pair, K3: one warp per pair).
 //
 // Reference rust-bio 4.0.1:
 //   sparse::find_kmer_matches          src/alignment/sparse.rs:337-402
@@ -561,10 +561,65 @@ struct BandedOut {
   uint32_t clip[4];
 };
 
-template <class ScoreFn>
-B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, const DevScoring& sc,
-                             ScoreFn score, const uint32_t* rng, uint64_t num_cells, uint8_t* slab,
-                             bool filter_clips, uint8_t* ops_end, BandedOut& out) {
+// Cooperative-lane helpers: W = 32 lanes of one warp on the device, W = 1 in the host logic build.
+template <int W>
+struct Coop {
+  static B2A_HD void sync() {
+#if defined(__CUDA_ARCH__)
+    if (W > 1) __syncwarp();
+#endif
+  }
+  static B2A_HD int32_t up(int32_t v, int d) {  // the value held by lane - d
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __shfl_up_sync(0xffffffffu, v, d);
+#endif
+    (void)d;
+    return v;
+  }
+  static B2A_HD int32_t from(int32_t v, int src) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __shfl_sync(0xffffffffu, v, src);
+#endif
+    (void)src;
+    return v;
+  }
+  static B2A_HD uint32_t ballot(bool b) {  // bit l = lane l's predicate
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __ballot_sync(0xffffffffu, b);
+#endif
+    return b ? 1u : 0u;
+  }
+  static B2A_HD long long all_max(long long v) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1)
+      for (int d = 16; d; d >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, v, d);
+        v = t > v ? t : v;
+      }
+#endif
+    return v;
+  }
+};
+
+// compute_alignment for one pair by W cooperating lanes (banded.rs:406-869).
+//
+// The column loop keeps the reference's arrays (rolling S/I/D with their leftovers, Sn/Ly/Lx, the eager
+// traceback writes) in the pair's slab and performs the same reads and writes per column; only the inner
+// loop over the band rows of one column is spread over the lanes, 32 rows at a time:
+//   * everything that comes from column j-1 (M, D, the clip terms) is independent per row;
+//   * the vertical chain I(i) = max(I(i-1)+ge, S(i-1)+go [, Sn(i-1)+go in the last column]) is a prefix
+//     maximum: with A(i) = S(i) without its I term, S(i-1) = max(A(i-1), I(i-1)), hence
+//     I(i) = max(I(i-1) + gs, A(i-1) + go) with gs = max(ge, go), i.e. I(i) - gs*i is a running maximum
+//     of A(i-1) + go - gs*i -- exact integer arithmetic, no saturation anywhere;
+//   * with the values known, every strict comparison of the reference (which source wins S, I from
+//     extension or open, the Sn/Ly row tracker) is re-evaluated literally per row from the final
+//     neighbours' values, and the column tracker S[m]/Lx is an arg-max with the lowest row winning ties.
+// Row m of a column, row 0, column 0, the end-of-matrix passes and the walk are sequential work of lane 0.
+template <int W, class ScoreFn>
+B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n,
+                             const DevScoring& sc, ScoreFn score, const uint32_t* rng, uint64_t num_cells,
+                             uint8_t* slab, bool filter_clips, uint8_t* ops_end, BandedOut& out) {
+  using C = Coop<W>;
   out.status = 0;
   out.n_ops = 0;
   for (int q = 0; q < 4; ++q) out.clip[q] = 0;
@@ -591,30 +646,38 @@ B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uin
   uint16_t* cells = reinterpret_cast<uint16_t*>(slab + L.cells);
   // init (banded.rs:423-438): only the cells that can ever be non-START are stored
   {
-    uint32_t acc = 0;
-    for (uint64_t j = 0; j <= n; ++j) {
-      colstart[j] = acc;
-      acc += (uint32_t)sat_sub64(rng[2 * j + 1], rng[2 * j]);
+    uint32_t acc = 0;  // exclusive prefix sum of the column heights
+    for (uint64_t b = 0; b <= n; b += W) {
+      const uint64_t j = b + (uint64_t)lane;
+      const uint32_t h = j <= n ? (uint32_t)sat_sub64(rng[2 * j + 1], rng[2 * j]) : 0u;
+      uint32_t inc = h;
+      for (int d = 1; d < W; d <<= 1) {
+        const uint32_t t = (uint32_t)C::up((int32_t)inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (j <= n) colstart[j] = acc + inc - h;
+      acc += (uint32_t)C::from((int32_t)inc, W - 1);
     }
-    colstart[n + 1] = acc;
+    if (lane == 0) colstart[n + 1] = acc;
   }
   for (int kk = 0; kk < 2; ++kk)
-    for (uint64_t i = 0; i <= m; ++i) {
+    for (uint64_t i = (uint64_t)lane; i <= m; i += W) {
       Sarr[kk][i] = MIN_SCORE;
       Iarr[kk][i] = MIN_SCORE;
       Darr[kk][i] = MIN_SCORE;
     }
-  for (uint64_t i = 0; i <= m; ++i) {
+  for (uint64_t i = (uint64_t)lane; i <= m; i += W) {
     Sn[i] = MIN_SCORE;
     Ly[i] = 0;
     col0[i] = 0;
     coln[i] = 0;
   }
-  for (uint64_t j = 0; j <= n; ++j) {
+  for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
     Lx[j] = 0;
     row0[j] = 0;
     rowm[j] = 0;
   }
+  C::sync();
   // traceback cell access: pointer for writes (nullptr = a cell the reference never writes there),
   // value for reads (untouched cells read as 0 = START in every nibble)
   auto cellp = [&](uint64_t i, uint64_t j) -> uint16_t* {
@@ -644,7 +707,8 @@ B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uin
   };
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
   const int32_t xp = sc.xclip_prefix, xs = sc.xclip_suffix, yp = sc.yclip_prefix, ys = sc.yclip_suffix;
-  {  // j = 0, banded.rs:440-509
+  const int32_t gs = imax(ge, go);  // slope of the I chain (the banded aligner opens a gap at go alone)
+  if (lane == 0) {  // j = 0, banded.rs:440-509
     int32_t* S = Sarr[0];
     int32_t* I = Iarr[0];
     const uint64_t i_start = rng[0], i_end = rng[1];
@@ -694,141 +758,333 @@ B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uin
       set_s(0, n, TB_YCLIP_SUFFIX);
     }
   }
+  C::sync();
   for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
+    {
+      // Columns without band cells (most of a long y) only store: S/I/D[i_start-1] = S[m] = MIN_SCORE, the
+      // x-suffix-clip nibble of row m, and the MIN_SCORE reset ahead of the next column.  Nothing is read and
+      // every array store writes the same constant, so a run of such columns is done one column per lane.
+      // A column is taken here only if its successor is of the same kind (the reset then stays short).
+      const uint64_t jc = j + (uint64_t)lane;
+      bool plain = false;
+      uint64_t c_start = 0, c_end = 0, c_to = 0;
+      if (jc + 1 <= n) {
+        c_start = rng[2 * jc];
+        c_end = rng[2 * jc + 1];
+        const uint64_t n_start = rng[2 * (jc + 1)], n_end = rng[2 * (jc + 1) + 1];
+        plain = c_start >= 1 && c_start >= c_end && n_start >= 1 && n_start >= n_end;
+        c_to = umin64(m + 1, n_end);
+      }
+      const uint32_t bal = C::ballot(plain);
+      uint32_t run = 0;
+      while (run < (uint32_t)W && ((bal >> run) & 1u)) ++run;
+      if (run > 0) {
+        if ((uint32_t)lane < run) {
+          int32_t* S = Sarr[jc % 2];
+          int32_t* I = Iarr[jc % 2];
+          int32_t* D = Darr[jc % 2];
+          S[c_start - 1] = MIN_SCORE;
+          I[c_start - 1] = MIN_SCORE;
+          D[c_start - 1] = MIN_SCORE;
+          S[m] = MIN_SCORE;
+          // S[m] + ys > Sn[m] cannot hold: S[m] is MIN_SCORE, ys <= 0 and Sn[m] never drops below MIN_SCORE
+          if (c_end < m + 1) set_s(m, jc, TB_XCLIP_SUFFIX);
+          for (uint64_t i = c_end; i < c_to; ++i) {
+            S[i] = MIN_SCORE;
+            I[i] = MIN_SCORE;
+            D[i] = MIN_SCORE;
+          }
+        }
+        C::sync();
+        j += run - 1;
+        continue;
+      }
+    }
     int32_t* S = Sarr[j % 2];
     int32_t* I = Iarr[j % 2];
     int32_t* D = Darr[j % 2];
     const int32_t* Sp = Sarr[1 - j % 2];
     const int32_t* Dp = Darr[1 - j % 2];
     const uint64_t i_start = rng[2 * j], i_end = rng[2 * j + 1];
-    if (i_start == 0) {
-      uint32_t db, sb;
-      I[0] = MIN_SCORE;
-      if (j == 1) {
-        D[0] = go;
-        db = TB_START;
-      } else {
-        const int32_t d_score = go + ge * ((int32_t)j - 1), c_score = yp + go;
-        if (d_score > c_score) {
-          D[0] = d_score;
-          db = TB_DEL;
+    const bool last = j == n;
+    if (lane == 0) {
+      if (i_start == 0) {
+        uint32_t db, sb;
+        I[0] = MIN_SCORE;
+        if (j == 1) {
+          D[0] = go;
+          db = TB_START;
         } else {
-          D[0] = c_score;
-          db = TB_YCLIP_PREFIX;
+          const int32_t d_score = go + ge * ((int32_t)j - 1), c_score = yp + go;
+          if (d_score > c_score) {
+            D[0] = d_score;
+            db = TB_DEL;
+          } else {
+            D[0] = c_score;
+            db = TB_YCLIP_PREFIX;
+          }
         }
-      }
-      if (D[0] > yp) {
-        S[0] = D[0];
-        sb = TB_DEL;
-      } else {
-        S[0] = yp;
-        sb = TB_YCLIP_PREFIX;
-      }
-      if (S[0] + ys > Sn[0]) {
-        Sn[0] = S[0] + ys;
-        Ly[0] = (uint32_t)(n - j);
-        set_s(0, n, TB_YCLIP_SUFFIX);
-      }
-      put(0, j, (db << 4) | (sb << 8));
-    }
-    for (uint64_t i = sat_sub64(i_start, 1); i < i_start; ++i) {
-      S[i] = MIN_SCORE;
-      I[i] = MIN_SCORE;
-      D[i] = MIN_SCORE;
-    }
-    S[m] = MIN_SCORE;
-    const uint8_t q = y[j - 1];
-    const int32_t xclip_score = xp + imax(j == n ? imax(yp, Sn[0]) : yp, go + ge * ((int32_t)j - 1));
-    for (uint64_t i = umax64(1, i_start); i < i_end; ++i) {
-      const uint8_t p = x[i - 1];
-      uint32_t ib, db, sb = TB_START;
-      const int32_t m_score = Sp[i - 1] + score(p, q);
-      const int32_t i_score = I[i - 1] + ge;
-      int32_t s_score = S[i - 1] + go;
-      int32_t best_i;
-      if (i_score > s_score) {
-        best_i = i_score;
-        ib = TB_INS;
-      } else {
-        best_i = s_score;
-        ib = (rd(i - 1, j) >> 8) & 15u;
-      }
-      if (j == n) {
-        const int32_t clip_score = Sn[i - 1] + go;
-        if (clip_score > best_i) {
-          best_i = clip_score;
-          ib = TB_YCLIP_SUFFIX;
+        if (D[0] > yp) {
+          S[0] = D[0];
+          sb = TB_DEL;
+        } else {
+          S[0] = yp;
+          sb = TB_YCLIP_PREFIX;
         }
+        if (S[0] + ys > Sn[0]) {
+          Sn[0] = S[0] + ys;
+          Ly[0] = (uint32_t)(n - j);
+          set_s(0, n, TB_YCLIP_SUFFIX);
+        }
+        put(0, j, (db << 4) | (sb << 8));
       }
-      const int32_t d_score = Dp[i] + ge;
-      s_score = Sp[i] + go;
-      int32_t best_d;
-      if (d_score > s_score) {
-        best_d = d_score;
-        db = TB_DEL;
-      } else {
-        best_d = s_score;
-        db = (rd(i, j - 1) >> 8) & 15u;
-      }
-      if (i == m) {
-        sb = TB_XCLIP_SUFFIX;
-      } else {
+      for (uint64_t i = sat_sub64(i_start, 1); i < i_start; ++i) {
         S[i] = MIN_SCORE;
+        I[i] = MIN_SCORE;
+        D[i] = MIN_SCORE;
       }
-      int32_t best = S[i];
-      if (m_score > best) {
-        best = m_score;
-        sb = (p == q) ? TB_MATCH : TB_SUBST;
-      }
-      if (best_i > best) {
-        best = best_i;
-        sb = TB_INS;
-      }
-      if (best_d > best) {
-        best = best_d;
-        sb = TB_DEL;
-      }
-      if (xclip_score > best) {
-        best = xclip_score;
-        sb = TB_XCLIP_PREFIX;
-      }
-      const int32_t yclip_score = yp + go + ge * ((int32_t)i - 1);
-      if (yclip_score > best) {
-        best = yclip_score;
-        sb = TB_YCLIP_PREFIX;
-      }
-      S[i] = best;
-      I[i] = best_i;
-      D[i] = best_d;
-      if (S[i] + xs > S[m]) {
-        S[m] = S[i] + xs;
-        Lx[j] = (uint32_t)(m - i);
-        set_s(m, j, TB_XCLIP_SUFFIX);
-      }
-      if (S[i] + ys > Sn[i]) {
-        Sn[i] = S[i] + ys;
-        Ly[i] = (uint32_t)(n - j);
-        set_s(i, n, TB_YCLIP_SUFFIX);
-      }
-      put(i, j, ib | (db << 4) | (sb << 8));
-    }
-    if (S[m] + ys > Sn[m]) {
-      Sn[m] = S[m] + ys;
-      Ly[m] = (uint32_t)(n - j);
-      set_s(m, n, TB_YCLIP_SUFFIX);
-    }
-    if (i_end < m + 1) {
-      set_s(m, j, TB_XCLIP_SUFFIX);
       S[m] = MIN_SCORE;
     }
-    for (uint64_t i = i_end; i < umin64(m + 1, rng[2 * umin64(n, j + 1) + 1]); ++i) {
-      S[i] = MIN_SCORE;
-      I[i] = MIN_SCORE;
-      D[i] = MIN_SCORE;
+    C::sync();
+    const uint8_t q = y[j - 1];
+    const int32_t xclip_score = xp + imax(last ? imax(yp, Sn[0]) : yp, go + ge * ((int32_t)j - 1));
+    const uint64_t lo = umax64(1, i_start), hi = i_end, hi_main = umin64(hi, m);
+    // values of row lo-1 in this column, handed from chunk to chunk (the same in every lane)
+    int32_t cS = 0, cI = 0, cSn = 0;
+    uint32_t csb = 0;
+    int32_t trk_val = MIN_SCORE;  // the column tracker S[m] (banded.rs:645-649), rows < m
+    uint64_t trk_i = 0;
+    bool trk_hit = false;
+    if (lo < hi) {
+      cS = S[lo - 1];
+      cI = I[lo - 1];
+      cSn = Sn[lo - 1];
+      csb = (rd(lo - 1, j) >> 8) & 15u;
+      const uint64_t jj = j - 1;  // geometry of column j-1 for the D-open lookups
+      const uint64_t ps = rng[2 * jj], pe = rng[2 * jj + 1];
+      const uint32_t pcs = colstart[jj], cs = colstart[j];
+      for (uint64_t base = lo; base < hi_main; base += W) {
+        const uint64_t i = base + (uint64_t)lane;
+        const bool act = i < hi_main;  // 1 <= i < m
+        int32_t m_score = MIN_SCORE, best_d = MIN_SCORE, A = MIN_SCORE, snold = MIN_SCORE;
+        uint32_t db = TB_START;
+        uint8_t p = 0;
+        if (act) {
+          p = x[i - 1];
+          m_score = Sp[i - 1] + score(p, q);
+          const int32_t d_score = Dp[i] + ge, s_score = Sp[i] + go;
+          if (d_score > s_score) {
+            best_d = d_score;
+            db = TB_DEL;
+          } else {
+            best_d = s_score;
+            const uint32_t pc = jj == 0 ? (uint32_t)col0[i]
+                                        : ((i >= ps && i < pe) ? (uint32_t)cells[pcs + (i - ps)] : 0u);
+            db = (pc >> 8) & 15u;
+          }
+          A = imax(imax(imax(MIN_SCORE, m_score), imax(best_d, xclip_score)), yp + go + ge * ((int32_t)i - 1));
+          snold = Sn[i];
+        }
+        // prefix maximum of I(i) - gs*i over the chunk
+        int32_t v;
+        {
+          const int32_t aprev = C::up(A, 1), snprev = C::up(snold, 1);
+          if (lane == 0) {
+            int32_t bi = imax(cI + ge, cS + go);
+            if (last) bi = imax(bi, cSn + go);
+            v = bi - gs * (int32_t)i;
+          } else {
+            v = (last ? imax(aprev, snprev) : aprev) + go - gs * (int32_t)i;
+          }
+          for (int d = 1; d < W; d <<= 1) {
+            const int32_t t = C::up(v, d);
+            if (lane >= d) v = imax(v, t);
+          }
+        }
+        const int32_t best_i = v + gs * (int32_t)i;
+        // S of the cell, literally (i < m: the running best starts at MIN_SCORE)
+        int32_t best = MIN_SCORE;
+        uint32_t sb = TB_START;
+        if (m_score > best) {
+          best = m_score;
+          sb = (p == q) ? TB_MATCH : TB_SUBST;
+        }
+        if (best_i > best) {
+          best = best_i;
+          sb = TB_INS;
+        }
+        if (best_d > best) {
+          best = best_d;
+          sb = TB_DEL;
+        }
+        if (xclip_score > best) {
+          best = xclip_score;
+          sb = TB_XCLIP_PREFIX;
+        }
+        {
+          const int32_t yclip_score = yp + go + ge * ((int32_t)i - 1);
+          if (yclip_score > best) {
+            best = yclip_score;
+            sb = TB_YCLIP_PREFIX;
+          }
+        }
+        int32_t sncur = snold;
+        if (act && best + ys > snold) {  // row tracker, banded.rs:650-654
+          sncur = best + ys;
+          Sn[i] = sncur;
+          Ly[i] = (uint32_t)(n - j);
+          if (!last) coln[i] = (uint16_t)((coln[i] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+        }
+        // the I nibble needs the final values of row i-1
+        int32_t pS = C::up(best, 1), pI = C::up(best_i, 1), pSn = C::up(sncur, 1);
+        uint32_t psb = (uint32_t)C::up((int32_t)sb, 1);
+        if (lane == 0) {
+          pS = cS;
+          pI = cI;
+          pSn = cSn;
+          psb = csb;
+        }
+        uint32_t ib;
+        {
+          const int32_t i_score = pI + ge, s_score = pS + go;
+          int32_t bl;
+          if (i_score > s_score) {
+            bl = i_score;
+            ib = TB_INS;
+          } else {
+            bl = s_score;
+            ib = psb;
+          }
+          if (last && pSn + go > bl) ib = TB_YCLIP_SUFFIX;
+        }
+        if (act) {
+          S[i] = best;
+          I[i] = best_i;
+          D[i] = best_d;
+          const uint32_t cell = ib | (db << 4) | (sb << 8);
+          if (last) coln[i] = (uint16_t)cell;
+          else cells[cs + (i - i_start)] = (uint16_t)cell;
+        }
+        {  // column tracker: first row with the highest S + xs
+          long long key = act ? (long long)((unsigned long long)(long long)(best + xs) << 32) +
+                                    (long long)(0xFFFFFFFFu - (uint32_t)i)
+                              : (long long)0x8000000000000000ull;
+          key = C::all_max(key);
+          const int32_t bv = (int32_t)(key >> 32);
+          if (bv > trk_val) {
+            trk_val = bv;
+            trk_i = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll));
+            trk_hit = true;
+          }
+        }
+        const uint64_t left = hi_main - 1 - base;
+        const int src = left < (uint64_t)(W - 1) ? (int)left : W - 1;
+        cS = C::from(best, src);
+        cI = C::from(best_i, src);
+        cSn = C::from(sncur, src);
+        csb = (uint32_t)C::from((int32_t)sb, src);
+      }
     }
+    if (lane == 0) {
+      if (trk_hit) {
+        S[m] = trk_val;
+        Lx[j] = (uint32_t)(m - trk_i);
+        set_s(m, j, TB_XCLIP_SUFFIX);
+      }
+      if (lo < hi && hi == m + 1) {  // the cell of row m: it starts from the column tracker
+        const uint64_t i = m;
+        const uint8_t p = x[i - 1];
+        uint32_t ib, db, sb;
+        const int32_t m_score = Sp[i - 1] + score(p, q);
+        const int32_t i_score = cI + ge;
+        int32_t s_score = cS + go;
+        int32_t best_i;
+        if (i_score > s_score) {
+          best_i = i_score;
+          ib = TB_INS;
+        } else {
+          best_i = s_score;
+          ib = csb;
+        }
+        if (last) {
+          const int32_t clip_score = cSn + go;
+          if (clip_score > best_i) {
+            best_i = clip_score;
+            ib = TB_YCLIP_SUFFIX;
+          }
+        }
+        const int32_t d_score = Dp[i] + ge;
+        s_score = Sp[i] + go;
+        int32_t best_d;
+        if (d_score > s_score) {
+          best_d = d_score;
+          db = TB_DEL;
+        } else {
+          best_d = s_score;
+          db = (rd(i, j - 1) >> 8) & 15u;
+        }
+        sb = TB_XCLIP_SUFFIX;
+        int32_t best = S[i];
+        if (m_score > best) {
+          best = m_score;
+          sb = (p == q) ? TB_MATCH : TB_SUBST;
+        }
+        if (best_i > best) {
+          best = best_i;
+          sb = TB_INS;
+        }
+        if (best_d > best) {
+          best = best_d;
+          sb = TB_DEL;
+        }
+        if (xclip_score > best) {
+          best = xclip_score;
+          sb = TB_XCLIP_PREFIX;
+        }
+        const int32_t yclip_score = yp + go + ge * ((int32_t)i - 1);
+        if (yclip_score > best) {
+          best = yclip_score;
+          sb = TB_YCLIP_PREFIX;
+        }
+        S[i] = best;
+        I[i] = best_i;
+        D[i] = best_d;
+        if (S[i] + xs > S[m]) {
+          S[m] = S[i] + xs;
+          Lx[j] = (uint32_t)(m - i);
+          set_s(m, j, TB_XCLIP_SUFFIX);
+        }
+        if (S[i] + ys > Sn[i]) {
+          Sn[i] = S[i] + ys;
+          Ly[i] = (uint32_t)(n - j);
+          set_s(i, n, TB_YCLIP_SUFFIX);
+        }
+        put(i, j, ib | (db << 4) | (sb << 8));
+      }
+      if (S[m] + ys > Sn[m]) {
+        Sn[m] = S[m] + ys;
+        Ly[m] = (uint32_t)(n - j);
+        set_s(m, n, TB_YCLIP_SUFFIX);
+      }
+      if (i_end < m + 1) {
+        set_s(m, j, TB_XCLIP_SUFFIX);
+        S[m] = MIN_SCORE;
+      }
+    }
+    C::sync();
+    {
+      const uint64_t to = umin64(m + 1, rng[2 * umin64(n, j + 1) + 1]);
+      for (uint64_t i = i_end + (uint64_t)lane; i < to; i += W) {
+        S[i] = MIN_SCORE;
+        I[i] = MIN_SCORE;
+        D[i] = MIN_SCORE;
+      }
+    }
+    C::sync();
   }
-  {
-    int32_t* S = Sarr[n % 2];
+  int32_t* const Sfin = Sarr[n % 2];
+  if (lane == 0) {
+    int32_t* S = Sfin;
     int32_t* I = Iarr[n % 2];
     const uint64_t bs = rng[2 * n], be = rng[2 * n + 1];
     for (uint64_t i = 0; i <= m; ++i) {  // banded.rs:684-701
@@ -859,36 +1115,50 @@ B2A_HD void banded_compute_d(const uint8_t* x, uint64_t m, const uint8_t* y, uin
         }
       }
     }
-    for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:725-744
+  }
+  C::sync();
+  // the two closed-form border passes (banded.rs:725-765) touch one traceback cell per index, except at
+  // the far corner (j = n, i = m), which lane 0 does afterwards
+  for (uint64_t j = 1 + (uint64_t)lane; j < n; j += W) {
+    const int32_t d_score = go + ge * ((int32_t)j - 1);
+    set_s(0, j, d_score > yp ? TB_DEL : TB_YCLIP_PREFIX);
+  }
+  for (uint64_t i = 1 + (uint64_t)lane; i < m; i += W) {
+    const int32_t c_score = go + ge * ((int32_t)i - 1);
+    set_s(i, 0, c_score > xp ? TB_INS : TB_XCLIP_PREFIX);
+  }
+  C::sync();
+  if (lane != 0) return;
+  {
+    int32_t* S = Sfin;
+    if (n >= 1) {  // banded.rs:725-744, j = n
+      const uint64_t j = n;
       const int32_t d_score = go + ge * ((int32_t)j - 1);
       set_s(0, j, d_score > yp ? TB_DEL : TB_YCLIP_PREFIX);
-      if (j == n) {
-        int32_t best_score = imax(d_score, yp);
-        if (ys > best_score) {
-          best_score = ys;
-          set_s(0, j, TB_YCLIP_SUFFIX);
-        }
-        if (xs + best_score > S[m]) {
-          S[m] = xs + best_score;
-          Lx[n] = (uint32_t)m;
-          set_s(m, n, TB_XCLIP_SUFFIX);
-        }
+      int32_t best_score = imax(d_score, yp);
+      if (ys > best_score) {
+        best_score = ys;
+        set_s(0, j, TB_YCLIP_SUFFIX);
+      }
+      if (xs + best_score > S[m]) {
+        S[m] = xs + best_score;
+        Lx[n] = (uint32_t)m;
+        set_s(m, n, TB_XCLIP_SUFFIX);
       }
     }
-    for (uint64_t i = 1; i <= m; ++i) {  // banded.rs:746-765
+    if (m >= 1) {  // banded.rs:746-765, i = m
+      const uint64_t i = m;
       const int32_t c_score = go + ge * ((int32_t)i - 1);
       set_s(i, 0, c_score > xp ? TB_INS : TB_XCLIP_PREFIX);
-      if (i == m) {
-        int32_t best_score = imax(c_score, xp);
-        if (xs > best_score) {
-          best_score = xs;
-          set_s(i, 0, TB_XCLIP_SUFFIX);
-        }
-        if (ys + best_score > S[m]) {
-          S[m] = ys + best_score;
-          Ly[m] = (uint32_t)n;
-          set_s(m, n, TB_YCLIP_SUFFIX);
-        }
+      int32_t best_score = imax(c_score, xp);
+      if (xs > best_score) {
+        best_score = xs;
+        set_s(i, 0, TB_XCLIP_SUFFIX);
+      }
+      if (ys + best_score > S[m]) {
+        S[m] = ys + best_score;
+        Ly[m] = (uint32_t)n;
+        set_s(m, n, TB_YCLIP_SUFFIX);
       }
     }
     out.score = S[m];
@@ -1016,8 +1286,10 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   prm.k4_status[p] = st;
 }
 
+// K3: one warp per pair
 __global__ void __launch_bounds__(128) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)(threadIdx.x & 31u);
   if (t >= n_wave) return;
   const uint64_t p = (uint64_t)prm.pair_lo + t;
   const uint64_t m = prm.x_len[p], n = prm.y_len[p];
@@ -1043,10 +1315,11 @@ __global__ void __launch_bounds__(128) banded_fill_kernel(const BandedParams prm
       }
       return a == b ? sc.match_score : sc.mismatch_score;
     };
-    banded_compute_d(prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc, score,
-                     prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p], prm.fill + prm.fill_off[t],
-                     prm.filter_clips != 0, prm.ops_scratch + prm.ops_off[p], o);
+    banded_compute_d<32>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc, score,
+                         prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p], prm.fill + prm.fill_off[t],
+                         prm.filter_clips != 0, prm.ops_scratch + prm.ops_off[p], o);
   }
+  if (lane != 0) return;
   prm.score[p] = o.score;
   prm.xstart[p] = o.xstart;
   prm.xend[p] = o.xend;

@@ -1038,7 +1038,7 @@ int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s
       b3.fill = e->d_bfill.as<uint8_t>();
       b3.fill_off = e->d_bfoff.as<uint64_t>();
       CK(cudaEventRecord(ev1, st));
-      banded_fill_kernel<<<(ns + 127) / 128, 128, 0, st>>>(b3, ns);
+      banded_fill_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);  // one warp per pair
       CK(cudaGetLastError());
       ++e->launches;
       CK(cudaEventRecord(ev2, st));

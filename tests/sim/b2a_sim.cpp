@@ -279,7 +279,7 @@ extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint
         if (table) return table[(size_t)a * 256 + b];
         return a == b ? sc.match_score : sc.mismatch_score;
       };
-      banded_compute_d(x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
+      banded_compute_d<1>(0, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
                        opsbuf.data() + opsbuf.size(), o);
     }
     score[p] = o.score;

@@ -357,7 +357,8 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
         maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
       }
     if (maxabs > (1ll << 27)) return e->fail(B2A_E_RANGE, "substitution score magnitude above 2^27");
-    for (size_t k = 0; k < aa; ++k) e->lut_host[aa + k] = 4 * e->lut_host[k] + 3;
+    // K1's copy: packed domain (4*v + 3 = "diagonal" priority) minus the open bias S carries there
+    for (size_t k = 0; k < aa; ++k) e->lut_host[aa + k] = 4 * e->lut_host[k] + 3 - (4 * sc.gap_open + 1);
   }
   score_bound = 0;
   // i32 range guard: every S/I/D of a real path stays within +-2^27, so MIN_SCORE-based
@@ -531,6 +532,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
     fp.task_counter = ctl + 2 + wi;
     fp.smem_seq_bytes = pl.smem_seq_bytes;
     fp.one = 1;
+    fp.ge4 = 4 * e->sc.gap_extend;
     uint32_t fill_tasks = nb * (uint32_t)pl.G;
     if (pl.G == 32 && w.strip_tasks >= 0x7fffffffull) return e->fail(B2A_E_RANGE, "too many strip tasks in one wave");
     if (pl.G == 32 && w.strip_tasks > 0) {

@@ -34,10 +34,11 @@ struct FillParams {
   uint8_t* bnd;
   uint8_t* rows;
   uint8_t* tb;
-  const int32_t* lut;  // scaled LUT 4*score+3, alpha*alpha (global) or null
+  const int32_t* lut;  // scaled LUT 4*score + 3 - (4*gap_open + 1), alpha*alpha (global) or null
   uint32_t* task_counter;
   uint32_t smem_seq_bytes;  // per-warp staging bytes
-  int32_t one;              // must be 1 (opaque to the compiler, see fadd())
+  int32_t one;              // must be 1 (opaque to the compiler, see fmad())
+  int32_t ge4;              // must be 4 * sc.gap_extend
   uint32_t* progress;       // strip-pipelined mode (G == 32): columns published per (pair, strip) task, else null
   uint32_t n_strip_tasks;   // strip-pipelined mode: number of (pair, strip) tasks of this launch
   DevScoring sc;
@@ -68,6 +69,7 @@ struct LaneCtx {
   uint32_t* prog_prev;   // strip-pipelined: progress of the strip above (null for strip 0)
   int32_t only_strip;    // strip-pipelined: the one strip this task fills (-1: all strips in order)
   int32_t one;           // an opaque 1 (kernel parameter): lets adds be issued as IMAD on the FMA pipe
+  int32_t ge4;           // 4 * gap_extend, opaque as well (kept out of constant folding)
 };
 
 #if defined(__CUDA_ARCH__)
@@ -180,26 +182,33 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
   constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
   constexpr bool RELU = (FLAGS & F_RELU) != 0;
-  const int32_t go4i = 4 * c.sc.gap_open + 2, go4d = 4 * c.sc.gap_open + 1, ge4 = 4 * c.sc.gap_extend;
-  const int32_t ma4 = 4 * c.sc.match_score + 3, mi4 = 4 * c.sc.mismatch_score + 3;
+  // S travels between cells as "S + open": So_d = S4 + go4d feeds the D chain of the next column and (as
+  // the diagonal input) M of the next column, whose LUT/compare scores are pre-biased by -go4d; the I chain
+  // of the row below wants go4i = go4d + 1.  One IMAD per consumer instead of two, and the chains
+  // themselves are single fused add-max instructions (ge4 is an opaque kernel parameter for that reason).
+  const int32_t go4i = 4 * c.sc.gap_open + 2, go4d = 4 * c.sc.gap_open + 1, ge4 = c.ge4;
+  const int32_t ma4 = 4 * c.sc.match_score + 3 - go4d, mi4 = 4 * c.sc.mismatch_score + 3 - go4d;
   const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
   const int32_t xs4 = scale4(c.sc.xclip_suffix), ys4 = scale4(c.sc.yclip_suffix);
   const int32_t cj = 4095 - j;  // packed row-tracker index field
   const int32_t one = c.one, k2 = one + one, k16 = k2 * 8, k1024 = k16 * 64;
   const int32_t q4 = q * 4;
   int32_t Tl = KEY_NONE;        // packed column tracker of this lane's rows (local row index)
+  int32_t key_even = KEY_NONE;
+  int32_t sdo = fmad(sdiag, one, go4d);  // diagonal S, open-biased
+  int32_t iop = fmad(sup, one, go4i);    // S of the row above + I open
+  int32_t s4 = sup;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int32_t sub4;
     if (LUT) {
-      sub4 = lut_at(c.lut, (uint32_t)fmad(q4, one, xc[r]));
+      sub4 = lut_at(c.lut, (uint32_t)fmad(q4, one, xc[r]));  // 4*score + 3 - go4d
     } else {
       sub4 = (xc[r] == q) ? ma4 : mi4;
     }
-    const int32_t m4 = fmad(sdiag, one, sub4);
-    const int32_t iop = fmad(sup, one, go4i);
+    const int32_t m4 = fmad(sdo, one, sub4);
     const int32_t i4 = addmax(iup, ge4, iop);
-    const int32_t dop = fmad(Sp[r], one, go4d);
+    const int32_t dop = Sp[r];  // S4 of this row in the previous column + go4d
     const int32_t d4 = addmax(Dp[r], ge4, dop);
     int32_t sP;
     if (CX && RELU) {
@@ -208,16 +217,21 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
       sP = max3(m4, i4, d4);
       if (CX) sP = imax(sP, x4);
     }
-    const int32_t s4 = sP & ~3;
+    s4 = sP & ~3;
     // nibble = code | iext << 2 | dext << 3 = (sP - s4) + min(i4 - iop, 4) + 2 * min(d4 - dop, 4),
-    // accumulated as tbacc*16 + nibble with the additions on the FMA pipe
+    // accumulated as tbacc*16 + nibble (the oldest nibble falls off the top)
     const int32_t fi = addmin(i4, -iop, 4), fd = addmin(d4, -dop, 4);
-    const int32_t nib = (sP - s4) + fmad(fd, k2, fi);  // one 3-input add + one IMAD
-    tbacc[r] = (uint32_t)fmad((int32_t)tbacc[r], k16, nib);  // the oldest nibble falls off the top
-    const int32_t s4k = (TR || TC) && PK ? fmad(s4, k1024, 0) : 0;  // 4096*S, shared by both trackers
+    const int32_t nib = fmad(fd, k2, fi) + sP - s4;
+    tbacc[r] = (uint32_t)(fmad((int32_t)tbacc[r], k16, fmad(fd, k2, fi)) + sP - s4);
     if (TC) {
       if (PK) {
-        if (!MASKED || r < rv) Tl = addmax(s4k, 4095 - r, Tl);
+        if (MASKED) {
+          if (r < rv) Tl = imax(Tl, fmad(s4, k1024, 4095 - r));
+        } else {  // two rows per 3-input max
+          const int32_t key = fmad(s4, k1024, 4095 - r);
+          if (r & 1) Tl = max3(Tl, key_even, key);
+          else key_even = key;
+        }
       } else {
         const int32_t v = s4 + xs4;
         if ((!MASKED || r < rv) && v > Tv) {
@@ -228,7 +242,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
     }
     if (TR) {
       if (PK) {
-        SnR[r] = addmax(s4k, cj, SnR[r]);
+        SnR[r] = imax(SnR[r], fmad(s4, k1024, cj));
       } else {
         const int32_t v = s4 + ys4;
         if (v > SnR[r]) {
@@ -249,12 +263,13 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
         cap_i = i4;
       }
     }
-    sdiag = Sp[r];
-    Sp[r] = s4;
+    sdo = dop;
+    Sp[r] = fmad(s4, one, go4d);
+    iop = fmad(s4, one, go4i);
     Dp[r] = d4;
-    sup = s4;
     iup = i4;
   }
+  sup = s4;
   if (TC && PK) {
     // local row index -> global: (4095 - r) - (rowbase + 1) = 4095 - i ; Tv carries the packed key
     if (Tl != KEY_NONE) Tv = imax(Tv, Tl - (rowbase + 1));
@@ -294,7 +309,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   for (int r = 0; r < R; ++r) {
     const int32_t i = rowbase + 1 + r;
     const int32_t s0 = col0_S(c.sc, i);
-    Sp[r] = 4 * s0;
+    Sp[r] = 4 * s0 + (4 * c.sc.gap_open + 1);  // open-biased, see column_step
     Dp[r] = NEG4;
     tbacc[r] = 0;
     LyR[r] = 0;
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const F
   uint64_t* bar = &bars[warp];
   if (threadIdx.x < FILL_WARPS) mbar_init(&bars[threadIdx.x], 1);
   if (LUT) {
-    for (int k = threadIdx.x; k < prm.sc.alpha * prm.sc.alpha; k += blockDim.x) lut_s[k] = prm.lut[k];
+    for (int k = threadIdx.x; k < prm.sc.alpha * prm.sc.alpha; k += blockDim.x) lut_s[k] = prm.lut[k];  // 4*score + 3 - (4*gap_open + 1)
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -561,6 +576,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const F
     c.lut = lut_s;
     c.lut_base = smem_u32(lut_s);
     c.one = prm.one;
+    c.ge4 = prm.ge4;
     c.only_strip = only_strip;
     c.prog_mine = strip_tasks ? prm.progress + task : nullptr;
     c.prog_prev = (strip_tasks && only_strip > 0) ? prm.progress + task - 1 : nullptr;

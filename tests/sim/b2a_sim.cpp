@@ -26,6 +26,7 @@ void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int
     LaneCtx<G> c;
     c.sc = sc;
     c.lut = lut;
+    c.ge4 = 4 * sc.gap_extend;
     c.lut_base = 0;
     c.one = 1;
     c.only_strip = -1;
@@ -140,7 +141,7 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
           lut[(size_t)a * sc.alpha + b] = v;
           maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
         }
-      for (size_t k = 0; k < aa; ++k) lut[aa + k] = 4 * lut[k] + 3;
+      for (size_t k = 0; k < aa; ++k) lut[aa + k] = 4 * lut[k] + 3 - (4 * sc.gap_open + 1);
     }
   }
   Plan p;

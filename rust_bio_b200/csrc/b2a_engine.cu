@@ -723,13 +723,34 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
   const uint64_t n = pairs->n_pairs;
   // chunk boundaries: K chunks, the first and the last half as large as the middle ones (the GPU idles
   // while the first chunk is staged and the host idles while the last one drains)
-  const uint64_t K = (uint64_t)e->pipe_chunks;
+  uint64_t K = (uint64_t)e->pipe_chunks;
+  // A small first chunk (its H2D is exposed), then growing ones (each chunk costs a fill tail of about half
+  // a warp-task), and a smaller last one (its walk and D2H are exposed).  Measured on 1M x 150x150:
+  // 1,3,6,6,3 -> 28.4-29.5 ms against 31.7 ms for 1,2,2,2,1 (profiles/r01_e2e_chunk_schedules.txt).
+  std::vector<double> wts(K, 6.0);
+  wts[0] = 1.0;
+  if (K >= 3) wts[1] = 3.0;
+  wts[K - 1] = K >= 4 ? 3.0 : 2.0;
+  if (const char* env = getenv("B2A_PIPE_WEIGHTS")) {  // development knob: comma-separated chunk weights
+    std::vector<double> w2;
+    for (const char* q = env; *q;) {
+      char* end = nullptr;
+      const double v = strtod(q, &end);
+      if (end == q) break;
+      if (v > 0) w2.push_back(v);
+      q = *end ? end + 1 : end;
+    }
+    if (w2.size() >= 2) {
+      wts = w2;
+      K = wts.size();
+    }
+  }
   std::vector<uint64_t> cut(K + 1, 0);
   {
-    const double unit = (double)n / (double)(K - 1);
-    double acc = 0;
+    double tot = 0, acc = 0;
+    for (double w : wts) tot += w;
     for (uint64_t c = 0; c < K; ++c) {
-      acc += (c == 0 || c == K - 1) ? unit * 0.5 : unit;
+      acc += wts[c] / tot * (double)n;
       cut[c + 1] = std::min<uint64_t>(n, ((uint64_t)acc + 31) / 32 * 32);
     }
     cut[K] = n;

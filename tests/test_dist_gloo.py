@@ -34,8 +34,7 @@ WORKER = textwrap.dedent('''
     lo, hi = bdist.shard_range(37, world, rank)
     assert calls == [hi - lo] and (lo, hi) == ((0, 19) if rank == 0 else (19, 37))
     dist.barrier(); dist.destroy_process_group()
-    sys.stdout.write("rank %d ok\n" % rank)  # one write: the two ranks share the pipe
-    sys.stdout.flush()
+    print("rank %d ok" % rank, flush=True)  # one string: the two ranks share the pipe
 ''')
 
 

@@ -226,15 +226,26 @@ def main():
 
     # ---- device-resident arm: stage once, then time K passes of the hot path
     eng.stage(MODE_LOCAL, cs, batch)
-    stride = eng.record_stride(M, N_LEN)
-    rec_local = torch.empty(P * stride, dtype=torch.uint8, device="cuda") if world > 1 else None
-    rec_all = torch.empty(world * P * stride, dtype=torch.uint8, device="cuda") if world > 1 else None
+    # N > 1: the one exchange of the path is the all-gather that reassembles the per-pair results on every
+    # rank.  Ranks exchange compact segments (include/b200align.h: 40 B of fields per pair + the ops at
+    # their real length); a MAX all-reduce of one integer makes the segments equally long first.
+    seg_size = torch.zeros(1, dtype=torch.int64, device="cuda") if world > 1 else None
+    seg_buf = {"cap": 0, "local": None, "all": None}
+    gathered = {"bytes": 0}
 
     def step_resident():
         eng.run()
-        if world > 1:  # the one exchange of the path: all-gather the fixed-stride result records
-            eng.records_into(rec_local.data_ptr(), rec_local.numel())
-            dist.all_gather_into_tensor(rec_all, rec_local)
+        if world > 1:
+            seg_size[0] = eng.compact_bytes()  # waits for this rank's batch
+            dist.all_reduce(seg_size, op=dist.ReduceOp.MAX)
+            seg = (int(seg_size.item()) + (1 << 20) - 1) >> 20 << 20
+            if seg > seg_buf["cap"]:
+                seg_buf["cap"] = seg
+                seg_buf["local"] = torch.empty(seg, dtype=torch.uint8, device="cuda")
+                seg_buf["all"] = torch.empty(world * seg, dtype=torch.uint8, device="cuda")
+            eng.compact_into(seg_buf["local"].data_ptr(), seg)
+            dist.all_gather_into_tensor(seg_buf["all"][:world * seg], seg_buf["local"][:seg])
+            gathered["bytes"] = world * seg
 
     for _ in range(warm):
         step_resident()
@@ -251,7 +262,7 @@ def main():
     ms_step = max_over_ranks(ms_total / steps)
     eng.fetch(None)
     st = eng.stats
-    launches_step = int(st.kernel_launches) + (1 if world > 1 else 0)
+    launches_step = int(st.kernel_launches)  # the exchange adds D2D copies and NCCL's kernels, none of ours
     # kernel-level numbers over instrumented passes (engine CUDA events on the same stream)
     fills, walks, packs = [], [], []
     for _ in range(max(3, steps)):
@@ -328,10 +339,16 @@ def main():
             "config": {"workload": WORKLOAD, "pairs_per_gpu": P, "m": M, "n": N_LEN,
                        "fill_shape": {"lanes_per_pair": G, "rows_per_lane": R},
                        "l2": "inputs larger than L2: 320 MB sequence blob + ~12 GB traceback stream per step (126 MB L2)",
-                       "parallelism": f"pair list sharded over {world} GPU(s); one NCCL all-gather of records"
+                       "parallelism": (f"pair list sharded over {world} GPU(s); per step one MAX all-reduce of the segment size and "
+                                       f"one NCCL all-gather of compact result segments ({gathered['bytes']} B received per rank)")
                        if world > 1 else "single GPU"},
+            # value = work / wall time of the K calls (contract); the median call is listed beside it because a
+            # call now and then stalls 10-30 ms in a host-side CUDA API call on these shared boxes
+            # (tools/e2e_outliers.py: the GPU is idle during those stalls)
             "e2e": {"value": round(e2e_value, 2), "unit": "GCUPS", "ms_per_step": round(e2e_ms, 3),
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_each_step": e2e_each},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_each_step": e2e_each,
+                    "ms_median_step": float(np.median(e2e_each)),
+                    "value_at_median_step": round(world * cells_rank / (float(np.median(e2e_each)) * 1e-3) / 1e9, 2)},
             "gpu_launches": launches_step * steps,
             "kernel_ms": {"pack": round(float(np.mean(packs)), 4), "fill": round(fill_ms, 4),
                           "walk_and_compact": round(float(np.mean(walks)), 4)},

@@ -195,6 +195,23 @@ uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n);
 int32_t b2a_records_decode(const void* host_records, uint32_t stride_bytes, uint64_t n_records,
                            b2a_results* results);
 
+/* Compact form of the same results for the all-gather (what `bench.py --gpus N` and
+ * rust_bio_b200/dist.py exchange): one segment per rank,
+ *   { uint64 n_pairs; uint64 ops_bytes; uint8 pad[48]; }                       64 bytes
+ *   int32 score[n]; uint32 xstart[n], xend[n], ystart[n], yend[n], n_ops[n]; uint32 clip_len[4n];
+ *   uint8 ops[ops_bytes]                      (pair p's ops follow pair p-1's, b2a_results order)
+ * i.e. 64 + 40 n + ops_bytes bytes instead of n * b2a_record_stride(): short alignments (local mode on
+ * reads) travel at their real length.  b2a_batch_compact_bytes waits for the batch to finish and returns the
+ * segment size; ranks agree on the largest one (a MAX all-reduce of one integer), each writes its segment
+ * into a buffer of that size and a single all-gather moves them. */
+int32_t b2a_batch_compact_bytes(b2a_engine* e, uint64_t* segment_bytes);
+int32_t b2a_batch_compact_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes);
+/* Decode one gathered segment (host memory) into `results` starting at pair index `pair_base` and ops offset
+ * `ops_base`; returns the segment's pair count and ops bytes.  ops_off[pair_base + i] is written for every
+ * pair of the segment (the caller writes the final ops_off[n_total]). */
+int32_t b2a_compact_decode(const void* host_segment, uint64_t segment_bytes, uint64_t pair_base,
+                           uint64_t ops_base, b2a_results* results, uint64_t* n_pairs, uint64_t* ops_bytes);
+
 /* Measurement utility for the int32-ALU roofline: tera lane-ops/s of
  * independent add / min-max / add+max register chains over all SMs of the device. */
 int32_t b2a_util_int32_peak(int32_t device_id, float* tops_add, float* tops_minmax, float* tops_mixed);

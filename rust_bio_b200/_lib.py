@@ -23,7 +23,8 @@ ABI_SYMBOLS = [
     "b2a_engine_set_pipeline",
     "b2a_align_batch", "b2a_align_batch_banded", "b2a_batch_stage", "b2a_batch_run",
     "b2a_batch_fetch", "b2a_batch_records", "b2a_batch_records_into", "b2a_record_stride",
-    "b2a_records_decode", "b2a_util_int32_peak",
+    "b2a_records_decode", "b2a_batch_compact_bytes", "b2a_batch_compact_into", "b2a_compact_decode",
+    "b2a_util_int32_peak",
 ]
 
 
@@ -100,6 +101,10 @@ def load():
     L.b2a_record_stride.argtypes = [C.c_uint32, C.c_uint32]
     L.b2a_record_stride.restype = C.c_uint32
     L.b2a_records_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(CResults)]
+    L.b2a_batch_compact_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.b2a_batch_compact_into.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.b2a_compact_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(CResults),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.b2a_util_int32_peak.argtypes = [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]
     for name in ABI_SYMBOLS:

@@ -76,6 +76,7 @@ struct b2a_engine {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  uint64_t compact_hdr[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};  // header of the compact result segment
   std::string err;
   int tune_G = 0, tune_R = 0;
   uint64_t tb_budget = 0;
@@ -1127,6 +1128,74 @@ int32_t b2a_batch_records(b2a_engine* e, void** dev_records, uint32_t* stride_by
   if (rc) return rc;
   *dev_records = e->d_records.p;
   if (n_records) *n_records = e->n_pairs;
+  return B2A_OK;
+}
+
+int32_t b2a_batch_compact_bytes(b2a_engine* e, uint64_t* segment_bytes) {
+  if (!e || !segment_bytes) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "compact results requested before b2a_batch_run");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const uint64_t n = e->n_pairs;
+  uint64_t total = 0;
+  if (n) CK(cudaMemcpyAsync(&total, e->d_opsoff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->compact_hdr[0] = n;
+  e->compact_hdr[1] = total;
+  *segment_bytes = 64 + 40 * n + total;
+  return B2A_OK;
+}
+
+int32_t b2a_batch_compact_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes) {
+  if (!e || !dev_dst) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "compact results requested before b2a_batch_run");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const uint64_t n = e->n_pairs;
+  if (e->compact_hdr[0] != n) return e->fail(B2A_E_STATE, "b2a_batch_compact_bytes must be called first");
+  const uint64_t total = e->compact_hdr[1];
+  if (dst_bytes < 64 + 40 * n + total) return e->fail(B2A_E_CAPACITY, "compact buffer too small");
+  uint8_t* dst = reinterpret_cast<uint8_t*>(dev_dst);
+  cudaStream_t st = e->stream;
+  CK(cudaMemcpyAsync(dst, e->compact_hdr, 64, cudaMemcpyHostToDevice, st));
+  const DevBuf* arrays[6] = {&e->d_score, &e->d_xs, &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops};
+  uint64_t off = 64;
+  for (const DevBuf* a : arrays) {
+    if (n) CK(cudaMemcpyAsync(dst + off, a->p, 4 * n, cudaMemcpyDeviceToDevice, st));
+    off += 4 * n;
+  }
+  if (n) CK(cudaMemcpyAsync(dst + off, e->d_clip.p, 16 * n, cudaMemcpyDeviceToDevice, st));
+  off += 16 * n;
+  if (total) CK(cudaMemcpyAsync(dst + off, e->d_opsdense.p, total, cudaMemcpyDeviceToDevice, st));
+  return B2A_OK;
+}
+
+int32_t b2a_compact_decode(const void* host_segment, uint64_t segment_bytes, uint64_t pair_base,
+                           uint64_t ops_base, b2a_results* r, uint64_t* n_pairs, uint64_t* ops_bytes) {
+  if (!host_segment || !r || segment_bytes < 64) return B2A_E_INVALID;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(host_segment);
+  uint64_t hdr[2];
+  std::memcpy(hdr, base, 16);
+  const uint64_t n = hdr[0], total = hdr[1];
+  if (n > (segment_bytes - 64) / 40 || total > segment_bytes - 64 - 40 * n) return B2A_E_INVALID;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(base + 64);
+  if (r->score) std::memcpy(r->score + pair_base, a, 4 * n);
+  if (r->xstart) std::memcpy(r->xstart + pair_base, a + n, 4 * n);
+  if (r->xend) std::memcpy(r->xend + pair_base, a + 2 * n, 4 * n);
+  if (r->ystart) std::memcpy(r->ystart + pair_base, a + 3 * n, 4 * n);
+  if (r->yend) std::memcpy(r->yend + pair_base, a + 4 * n, 4 * n);
+  const uint32_t* nops = a + 5 * n;
+  if (r->clip_len) std::memcpy(r->clip_len + 4 * pair_base, a + 6 * n, 16 * n);
+  uint64_t acc = 0;
+  for (uint64_t p = 0; p < n; ++p) {
+    if (r->ops_off) r->ops_off[pair_base + p] = ops_base + acc;
+    acc += nops[p];
+  }
+  if (acc != total) return B2A_E_INVALID;
+  if (r->ops) {
+    if (ops_base + total > r->ops_capacity) return B2A_E_CAPACITY;
+    std::memcpy(r->ops + ops_base, base + 64 + 40 * n, total);
+  }
+  if (n_pairs) *n_pairs = n;
+  if (ops_bytes) *ops_bytes = total;
   return B2A_OK;
 }
 

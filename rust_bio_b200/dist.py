@@ -2,8 +2,10 @@
 
 The reference has no distributed layer; pairs are independent, so the only exchange is
 the reassembly of per-pair results (BASELINE north_star: "a single NCCL allgather over NVLink only
-to reassemble per-pair scores/CIGARs").  One process per GPU under torch.distributed; records are the
-fixed-stride layout of b2a_batch_records (include/b200align.h).
+to reassemble per-pair scores/CIGARs").  One process per GPU under torch.distributed.  Two wire formats
+(include/b200align.h): fixed-stride records (b2a_batch_records) and the compact segment
+(b2a_batch_compact_*: per-rank arrays + dense ops, ranks first agree on the largest segment with a MAX
+all-reduce of one integer) which is what bench.py exchanges -- short alignments travel at their real length.
 """
 from __future__ import annotations
 
@@ -100,3 +102,75 @@ def align_sharded(batch, stride: int, run_local: Callable, device="cpu"):
     host = allrec.cpu().numpy()
     # rank r's shard occupies [r*per, r*per + len_r): contiguous split => caller order is preserved
     return decode_records(host, stride, n)
+
+
+# ---------------------------------------------------------------- compact segments (b2a_batch_compact_*)
+COMPACT_HEAD = 64
+
+
+def encode_compact(fields: dict, ops_lists) -> np.ndarray:
+    """Host-side encoder of one rank's compact segment (used by tests to fake a rank's device output)."""
+    n = len(ops_lists)
+    codes = [np.array([c for c, _ in ops], dtype=np.uint8) for ops in ops_lists]
+    total = int(sum(len(c) for c in codes))
+    seg = np.zeros(COMPACT_HEAD + 40 * n + total, dtype=np.uint8)
+    seg[:16].view(np.uint64)[:] = (n, total)
+    a = seg[COMPACT_HEAD:COMPACT_HEAD + 40 * n].view(np.uint32)
+    a[0:n] = np.asarray(fields["score"]).astype(np.int32).view(np.uint32)
+    for k, name in enumerate(("xstart", "xend", "ystart", "yend")):
+        a[(1 + k) * n:(2 + k) * n] = fields[name]
+    a[5 * n:6 * n] = [len(c) for c in codes]
+    clip = a[6 * n:10 * n].reshape(n, 4)
+    for p, ops in enumerate(ops_lists):
+        for k, l in enumerate([l for c, l in ops if c >= 4][:4]):
+            clip[p, k] = l
+    if total:
+        seg[COMPACT_HEAD + 40 * n:] = np.concatenate(codes)
+    return seg
+
+
+def decode_compact(host: np.ndarray, segment_bytes: int, world: int):
+    """Pure-numpy decoder of `world` gathered segments (the C ABI has b2a_compact_decode for the same job)."""
+    fields = {k: [] for k in ("score", "xstart", "xend", "ystart", "yend")}
+    ops_lists = []
+    for r in range(world):
+        seg = host[r * segment_bytes:(r + 1) * segment_bytes]
+        n, total = (int(v) for v in seg[:16].view(np.uint64))
+        a = seg[COMPACT_HEAD:COMPACT_HEAD + 40 * n].view(np.uint32)
+        fields["score"].append(a[0:n].view(np.int32).copy())
+        for k, name in enumerate(("xstart", "xend", "ystart", "yend")):
+            fields[name].append(a[(1 + k) * n:(2 + k) * n].copy())
+        nops = a[5 * n:6 * n]
+        clip = a[6 * n:10 * n].reshape(n, 4)
+        ops = seg[COMPACT_HEAD + 40 * n:COMPACT_HEAD + 40 * n + total]
+        off = 0
+        for p in range(n):
+            out, k = [], 0
+            for c in ops[off:off + int(nops[p])]:
+                c = int(c)
+                if c >= 4:
+                    out.append((c, int(clip[p, k])))
+                    k += 1
+                else:
+                    out.append((c, 0))
+            ops_lists.append(out)
+            off += int(nops[p])
+    return {k: np.concatenate(v) if v else np.zeros(0, np.uint32) for k, v in fields.items()}, ops_lists
+
+
+def align_sharded_compact(batch, run_local: Callable, device="cpu"):
+    """Like align_sharded, with compact segments: `run_local(shard)` -> uint8 torch tensor holding that
+    shard's segment (on `device`).  One MAX all-reduce of the segment size, one all-gather of the segments."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    shard, lo, hi = shard_batch(batch, world, rank)
+    seg = run_local(shard)
+    size = torch.tensor([seg.numel()], dtype=torch.int64, device=device)
+    dist.all_reduce(size, op=dist.ReduceOp.MAX)
+    seg_bytes = (int(size.item()) + 255) // 256 * 256
+    local = torch.zeros(seg_bytes, dtype=torch.uint8, device=device)
+    local[:seg.numel()] = seg
+    out = torch.empty(world * seg_bytes, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(out, local)
+    return decode_compact(out.cpu().numpy(), seg_bytes, world)

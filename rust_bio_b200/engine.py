@@ -153,6 +153,34 @@ class Engine:
         self._check(self._L.b2a_batch_records_into(self._h, C.c_void_p(dev_ptr), int(nbytes), C.byref(stride)))
         return stride.value
 
+    def compact_bytes(self) -> int:
+        """Size of this batch's compact result segment (waits for the batch; see include/b200align.h)."""
+        nb = C.c_uint64()
+        self._check(self._L.b2a_batch_compact_bytes(self._h, C.byref(nb)))
+        return int(nb.value)
+
+    def compact_into(self, dev_ptr: int, nbytes: int) -> None:
+        self._check(self._L.b2a_batch_compact_into(self._h, C.c_void_p(dev_ptr), int(nbytes)))
+
+    def decode_compact(self, host_segments: np.ndarray, segment_bytes: int, n_segments: int, n_total: int,
+                       ops_capacity: int) -> Results:
+        """Decode `n_segments` gathered compact segments (each padded to segment_bytes) in rank order."""
+        res = Results(n_total, ops_capacity)
+        pair_base = ops_base = 0
+        for r in range(n_segments):
+            seg = host_segments[r * segment_bytes:(r + 1) * segment_bytes]
+            n, nb = C.c_uint64(), C.c_uint64()
+            rc = self._L.b2a_compact_decode(seg.ctypes.data_as(C.c_void_p), segment_bytes, pair_base, ops_base,
+                                            C.byref(res.c), C.byref(n), C.byref(nb))
+            if rc != 0:
+                raise B2AError(rc, "b2a_compact_decode")
+            pair_base += n.value
+            ops_base += nb.value
+        if pair_base != n_total:
+            raise B2AError(-2, "compact segments hold %d pairs, expected %d" % (pair_base, n_total))
+        res.ops_off[n_total] = ops_base
+        return res
+
     def record_stride(self, max_m: int, max_n: int) -> int:
         return int(self._L.b2a_record_stride(max_m, max_n))
 

@@ -31,6 +31,12 @@ WORKER = textwrap.dedent('''
     fields, ops = bdist.align_sharded(batch, stride, run_local)
     ref, ref_ops = oracle_batch(orc, "local", s, batch, threads=1)
     assert_same(fields, ops, ref, ref_ops, batch, "gloo rank %d" % rank)
+    # the compact wire format (what bench.py exchanges): same answer
+    def run_local_compact(shard):
+        ref, ops = oracle_batch(orc, "local", s, shard, threads=1)
+        return torch.from_numpy(bdist.encode_compact(ref, ops))
+    fields2, ops2 = bdist.align_sharded_compact(batch, run_local_compact)
+    assert_same(fields2, ops2, ref, ref_ops, batch, "gloo compact rank %d" % rank)
     lo, hi = bdist.shard_range(37, world, rank)
     assert calls == [hi - lo] and (lo, hi) == ((0, 19) if rank == 0 else (19, 37))
     dist.barrier(); dist.destroy_process_group()

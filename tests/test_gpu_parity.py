@@ -321,6 +321,44 @@ def test_full_size_c2_properties(eng, oracle):
     assert_same(got, [res.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "C2 sample")
 
 
+def test_result_wire_formats_equal_fetch(eng, oracle):
+    """The two all-gather wire formats (fixed-stride records, compact segment) decode to what fetch returns."""
+    import torch
+    from rust_bio_b200 import dist as bdist, synth
+    from rust_bio_b200.engine import Results
+    batch = synth.ragged_pairs(77, 300, 5, 90)
+    n = len(batch[2])
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    for mode in ("local", "global"):
+        eng.stage(MODES[mode], cs, batch)
+        eng.run()
+        want = Results(n, 64 * 1024)
+        eng.fetch(want)
+        total = int(want.ops_off[n])
+        # compact segment, through both decoders
+        nb = eng.compact_bytes()
+        assert nb == 64 + 40 * n + total
+        seg = torch.zeros(nb + 100, dtype=torch.uint8, device="cuda")
+        eng.compact_into(seg.data_ptr(), seg.numel())
+        torch.cuda.synchronize()
+        host = seg.cpu().numpy()
+        got = eng.decode_compact(host, host.size, 1, n, 64 * 1024)
+        for k in ("score", "xstart", "xend", "ystart", "yend", "clip_len"):
+            assert np.array_equal(getattr(got, k), getattr(want, k)), (mode, k)
+        assert np.array_equal(got.ops_off[:n + 1], want.ops_off[:n + 1])
+        assert np.array_equal(got.ops[:total], want.ops[:total])
+        fields, ops_lists = bdist.decode_compact(host, host.size, 1)
+        assert np.array_equal(fields["score"], want.score)
+        assert ops_lists == [want.ops_of(p) for p in range(n)]
+        # fixed-stride records
+        stride = eng.record_stride(int(batch[2].max()), int(batch[4].max()))
+        rec = torch.zeros(n * stride, dtype=torch.uint8, device="cuda")
+        assert eng.records_into(rec.data_ptr(), rec.numel()) == stride
+        torch.cuda.synchronize()
+        f2, o2 = bdist.decode_records(rec.cpu().numpy(), stride, n)
+        assert np.array_equal(f2["score"], want.score) and o2 == ops_lists
+
+
 def test_error_paths(eng):
     """Bad parameters are refused like the reference's assert!s; out-of-alphabet bytes are an error."""
     from rust_bio_b200 import scores, synth

@@ -53,6 +53,7 @@ struct LaneCtx {
   const uint32_t* ys;    // staged y words of the task: [w][P]
   int32_t m, n;          // this lane's pair
   int32_t maxn;          // block maximum (loop bound shared by the warp)
+  int32_t maxm;          // block maximum of m (uniform blocks: every valid pair's m)
   int32_t g;             // pair slot inside the task (lane / G)
   int32_t l;             // lane inside the group (lane % G)
   int32_t lane;          // 0..31
@@ -460,7 +461,9 @@ B2A_HD void fill_lane(const LaneCtx<G>& c) {
   const int32_t s_hi = c.only_strip >= 0 ? c.only_strip + 1 : c.nstrips;
   for (int32_t s = s_lo; s < s_hi; ++s) {
     // a strip is "full" when every lane of every pair of the task owns R valid rows
-    const bool full = c.uniform && ((s + 1) * (G * R) <= c.m - 1);
+    // decided from the block maximum so that the whole warp takes the same branch (the padding lanes of a
+    // last, partly filled task have m = 0 and simply never become active)
+    const bool full = c.uniform && ((s + 1) * (G * R) <= c.maxm - 1);
     if (full) {
       run_strip<G, R, FLAGS, false>(c, s);
     } else {
@@ -590,6 +593,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const F
     c.m = valid ? (int32_t)prm.pm[blk.first + c.pi] : 0;
     c.n = valid ? (int32_t)prm.pn[blk.first + c.pi] : 0;
     c.maxn = (int32_t)blk.maxn;
+    c.maxm = (int32_t)blk.maxm;
     c.nstrips = (int32_t)blk.nstrips;
     c.K = (int32_t)blk.K;
     c.rows_pad = (int32_t)blk.rows_pad;

@@ -624,7 +624,7 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
 }
 
 #if defined(B2A_DEFINE_WALK_KERNEL)  // one translation unit (b2a_engine.cu) owns the stand-alone kernel
-__global__ void __launch_bounds__(128) walk_kernel(const WalkParams prm) {
+__global__ void __launch_bounds__(128, 8) walk_kernel(const WalkParams prm) {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= prm.nblocks) return;

@@ -43,6 +43,7 @@ void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int
     c.m = valid ? (int32_t)p.pm[blk.first + lane] : (int32_t)blk.maxm;
     c.n = valid ? (int32_t)p.pn[blk.first + lane] : (int32_t)blk.maxn;
     c.maxn = (int32_t)blk.maxn;
+    c.maxm = (int32_t)blk.maxm;
     c.nstrips = (int32_t)blk.nstrips;
     c.K = (int32_t)blk.K;
     c.rows_pad = (int32_t)blk.rows_pad;

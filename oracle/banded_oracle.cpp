@@ -225,6 +225,173 @@ SparseResult sdpkpp(const std::vector<Match>& matches, uint64_t k_, uint32_t mat
   return res;
 }
 
+// ---------------------------------------------------------------- sparse::lcskpp, sparse.rs:67-143
+// MaxBitTree<(u32, u32)>: the same prefix-max tree over (score, position) tuples
+struct MaxBitTreePair {
+  Vec<std::pair<uint32_t, uint32_t>> tree;
+  explicit MaxBitTreePair(uint64_t len) { tree.v.assign(len + 1, {0u, 0u}); }
+  std::pair<uint32_t, uint32_t> get(uint64_t idx) const {
+    idx += 1;
+    std::pair<uint32_t, uint32_t> sum{0u, 0u};
+    while (idx > 0) {
+      sum = std::max(sum, tree[idx]);
+      idx -= idx & (~idx + 1);
+    }
+    return sum;
+  }
+  void set(uint64_t idx, const std::pair<uint32_t, uint32_t>& val) {
+    idx += 1;
+    while (idx < tree.len()) {
+      tree[idx] = std::max(tree[idx], val);
+      idx += idx & (~idx + 1);
+    }
+  }
+};
+
+SparseResult lcskpp(const std::vector<Match>& matches, uint64_t k_) {
+  SparseResult res;
+  if (matches.empty()) return res;
+  const uint32_t k = (uint32_t)k_;
+  for (size_t i = 1; i < matches.size(); ++i)
+    if (!(matches[i - 1] < matches[i])) { panic("incoming matches must be sorted."); return res; }
+  std::vector<std::tuple<uint32_t, uint32_t, uint32_t>> events;
+  uint32_t n = 0;
+  const uint32_t nm = (uint32_t)matches.size();
+  for (uint32_t idx = 0; idx < nm; ++idx) {
+    const uint32_t x = matches[idx].first, y = matches[idx].second;
+    events.emplace_back(x, y, idx + nm);
+    events.emplace_back(x + k, y + k, idx);
+    n = std::max(n, x + k);
+    n = std::max(n, y + k);
+  }
+  std::sort(events.begin(), events.end());
+  MaxBitTreePair max_col_dp(n);
+  Vec<std::pair<uint32_t, int32_t>> dp;
+  dp.v.assign(events.size(), {0u, 0});
+  std::pair<uint32_t, int32_t> best_dp{k, 0};
+  for (const auto& ev : events) {
+    const uint32_t e0 = std::get<0>(ev), e1 = std::get<1>(ev), e2 = std::get<2>(ev);
+    const uint64_t p = e2 % nm;
+    const bool is_start = e2 >= nm;
+    if (is_start) {
+      dp[p] = {k, -1};
+      const auto best = max_col_dp.get(e1);
+      if (best.first > 0) {
+        dp[p] = {k + best.first, (int32_t)best.second};
+        best_dp = std::max(best_dp, std::make_pair(dp[p].first, (int32_t)p));
+      }
+    } else {
+      if (e0 > k && e1 > k) {
+        const Match want{e0 - k - 1, e1 - k - 1};
+        auto it = std::lower_bound(matches.begin(), matches.end(), want);
+        if (it != matches.end() && *it == want) {
+          const uint64_t cont_idx = (uint64_t)(it - matches.begin());
+          const auto cand = std::make_pair(dp[cont_idx].first + 1, (int32_t)cont_idx);
+          dp[p] = std::max(dp[p], cand);
+          best_dp = std::max(best_dp, std::make_pair(dp[p].first, (int32_t)p));
+        }
+      }
+      max_col_dp.set(e1, {dp[p].first, (uint32_t)p});
+    }
+  }
+  int32_t prev_match = best_dp.second;
+  while (prev_match >= 0) {
+    res.path.push_back((uint64_t)prev_match);
+    prev_match = dp[(uint64_t)prev_match].second;
+  }
+  std::reverse(res.path.begin(), res.path.end());
+  res.score = best_dp.first;
+  return res;
+}
+
+// ---------------------------------------------------------------- sparse::sdpkpp_union_lcskpp_path, sparse.rs:297-330
+std::vector<uint64_t> sdpkpp_union_lcskpp_path(const std::vector<Match>& matches, uint64_t k, uint32_t match_score,
+                                               int32_t gap_open, int32_t gap_extend) {
+  std::vector<uint64_t> out;
+  if (matches.empty()) return out;
+  const SparseResult l = lcskpp(matches, k);
+  const SparseResult s = sdpkpp(matches, k, match_score, gap_open, gap_extend);
+  if (g_panic || s.path.empty()) { panic("empty sdpkpp path"); return out; }
+  // slice::binary_search on the (ascending) lcskpp path; any of several equal elements may be returned, but
+  // path indices are distinct
+  auto bsearch = [&](uint64_t v, bool& found) -> uint64_t {
+    auto it = std::lower_bound(l.path.begin(), l.path.end(), v);
+    found = it != l.path.end() && *it == v;
+    return (uint64_t)(it - l.path.begin());
+  };
+  bool f0 = false, f1 = false;
+  const uint64_t i0 = bsearch(s.path.front(), f0);
+  const uint64_t pre = f0 ? i0 : 0;                  // .unwrap_or(0)
+  const uint64_t i1 = bsearch(s.path.back(), f1);
+  const uint64_t post = f1 ? i1 + 1 : l.path.size();
+  for (uint64_t i = 0; i < pre; ++i) out.push_back(l.path[i]);
+  for (uint64_t v : s.path) out.push_back(v);
+  for (uint64_t i = post; i < l.path.size(); ++i) out.push_back(l.path[i]);
+  return out;
+}
+
+// ---------------------------------------------------------------- sparse::expand_kmer_matches, sparse.rs:404-498
+std::vector<Match> expand_kmer_matches(const uint8_t* seq1, uint64_t len1, const uint8_t* seq2, uint64_t len2,
+                                       uint64_t k, const std::vector<Match>& sorted_matches,
+                                       uint64_t allowed_mismatches) {
+  std::vector<Match> none;
+  for (size_t i = 1; i < sorted_matches.size(); ++i)
+    if (!(sorted_matches[i - 1] < sorted_matches[i])) { panic("incoming matches must be sorted"); return none; }
+  using P = std::pair<int32_t, int32_t>;
+  std::unordered_map<int32_t, P> last_match_along_diagonal;
+  std::vector<Match> left = sorted_matches;
+  for (const Match& tm : sorted_matches) {
+    const int32_t diag = (int32_t)tm.first - (int32_t)tm.second;
+    const int32_t min_xy = (int32_t)std::min(tm.first, tm.second);
+    const P def{(int32_t)tm.first - min_xy - 1, (int32_t)tm.second - min_xy - 1};
+    auto it = last_match_along_diagonal.find(diag);
+    const P last_match = it != last_match_along_diagonal.end() ? it->second : def;
+    uint64_t n_mismatches = 0;
+    P curr{(int32_t)tm.first - 1, (int32_t)tm.second - 1};
+    for (;;) {
+      if (last_match >= curr) break;
+      if ((uint64_t)curr.first >= len1 || (uint64_t)curr.second >= len2 || curr.first < 0 || curr.second < 0) {
+        panic("index out of bounds");
+        return none;
+      }
+      n_mismatches += seq1[curr.first] == seq2[curr.second] ? 0 : 1;
+      if (n_mismatches > allowed_mismatches) break;
+      left.emplace_back((uint32_t)curr.first, (uint32_t)curr.second);
+      curr = {curr.first - 1, curr.second - 1};
+    }
+    last_match_along_diagonal[diag] = {(int32_t)tm.first, (int32_t)tm.second};
+  }
+  std::sort(left.begin(), left.end());
+  std::vector<Match> expanded = left;
+  std::reverse(left.begin(), left.end());
+  std::unordered_map<int32_t, Match> next_match_along_diagonal;
+  for (const Match& tm : left) {
+    const int32_t diag = (int32_t)tm.first - (int32_t)tm.second;
+    // (min(len1 - x, len2 - y) as u32).saturating_sub(k as u32 - 1); `k as u32 - 1` underflows for k == 0
+    if (k == 0) { panic("attempt to subtract with overflow"); return none; }
+    const uint32_t a = (uint32_t)len1 - tm.first, b = (uint32_t)len2 - tm.second;
+    const uint32_t mn = std::min(a, b), km1 = (uint32_t)k - 1;
+    const uint32_t max_inc = mn > km1 ? mn - km1 : 0;
+    auto it = next_match_along_diagonal.find(diag);
+    const Match next_match = it != next_match_along_diagonal.end() ? it->second
+                                                                   : Match{tm.first + max_inc, tm.second + max_inc};
+    uint64_t n_mismatches = 0;
+    Match curr{tm.first + 1, tm.second + 1};
+    for (;;) {
+      if (curr >= next_match) break;
+      const uint64_t i1 = (uint64_t)curr.first + k - 1, i2 = (uint64_t)curr.second + k - 1;
+      if (i1 >= len1 || i2 >= len2) { panic("index out of bounds"); return none; }
+      n_mismatches += seq1[i1] == seq2[i2] ? 0 : 1;
+      if (n_mismatches > allowed_mismatches) break;
+      expanded.push_back(curr);
+      curr = {curr.first + 1, curr.second + 1};
+    }
+    next_match_along_diagonal[diag] = tm;
+  }
+  std::sort(expanded.begin(), expanded.end());
+  return expanded;
+}
+
 // ---------------------------------------------------------------- Band, banded.rs:1047-1380
 struct Range {
   uint64_t start, end;
@@ -819,6 +986,48 @@ struct BandedAligner {
     sc.yclip_prefix = saved[2];
     sc.yclip_suffix = saved[3];
   }
+
+  // The entry points that take the band's inputs from the caller, banded.rs:294-401 (+ semiglobal_with_prehash
+  // 938-975, whose band is that of `semiglobal`: find_kmer_matches_seq2_hashed returns the same sorted matches).
+  //   matches (have_matches)            custom_with_matches            -> Band::create_with_matches
+  //   + allowed_mismatches / union      custom_with_expanded_matches   -> expand_kmer_matches, union path
+  //   + path (have_path)                custom_with_match_path         -> Band::create_from_match_path
+  // These are `custom` methods: the clip penalties are the scoring's own and clips stay in the operations.
+  void align_hinted(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, bool have_matches,
+                    const std::vector<Match>& matches_in, bool have_path, const std::vector<uint64_t>& path_in,
+                    int64_t allowed_mismatches, bool use_lcskpp_union, orc_alignment* out, std::vector<Op>& ops) {
+    if (!have_matches) {
+      align(0, x, m, y, n, out, ops);
+      return;
+    }
+    if (have_path) {  // custom_with_match_path, 391-401
+      if (!matches_in.empty()) {
+        if (path_in.empty()) { panic("index out of bounds: path[0]"); return; }
+        for (uint64_t idx : path_in)
+          if (idx >= matches_in.size()) { panic("index out of bounds: matches[idx]"); return; }
+      }
+      band = Band::from_match_path(m, n, k, w, sc, path_in, matches_in);
+    } else if (allowed_mismatches >= 0 || use_lcskpp_union) {  // custom_with_expanded_matches, 338-375
+      std::vector<Match> expanded = allowed_mismatches >= 0
+                                        ? expand_kmer_matches(x, m, y, n, k, matches_in, (uint64_t)allowed_mismatches)
+                                        : matches_in;
+      if (g_panic) return;
+      if (use_lcskpp_union) {
+        const int32_t match_score = sc.has_match_scores ? sc.match_score : DEFAULT_MATCH_SCORE;
+        const std::vector<uint64_t> path =
+            sdpkpp_union_lcskpp_path(expanded, k, (uint32_t)match_score, sc.gap_open, sc.gap_extend);
+        if (g_panic) return;
+        band = Band::from_match_path(m, n, k, w, sc, path, expanded);
+      } else {
+        band = Band::with_matches(m, n, k, w, sc, expanded);
+      }
+    } else {  // custom_with_matches, 313-321
+      band = Band::with_matches(m, n, k, w, sc, matches_in);
+    }
+    if (g_panic) return;
+    compute_alignment(x, m, y, n, out, ops);
+    out->mode = 0;
+  }
 };
 
 }  // namespace
@@ -906,6 +1115,71 @@ int orc_banded_align(int mode, const orc_scoring* scoring, uint32_t k, uint32_t 
     out->n_ops = 0xFFFFFFFFu;
     return -1;
   }
+  for (size_t t = 0; t < v.size(); ++t) ops[t] = v[t].code | (v[t].len << 3);
+  return 0;
+}
+
+// lcskpp / union path / expand_kmer_matches for the reference's unit vectors (sparse.rs:518-760)
+int orc_lcskpp(const uint32_t* xy, uint64_t n_matches, uint32_t k, uint64_t* out_path, uint64_t* n_path,
+               uint32_t* score) {
+  g_panic = false;
+  std::vector<Match> m(n_matches);
+  for (uint64_t i = 0; i < n_matches; ++i) m[i] = {xy[2 * i], xy[2 * i + 1]};
+  const SparseResult r = lcskpp(m, k);
+  for (uint64_t i = 0; i < r.path.size(); ++i) out_path[i] = r.path[i];
+  *n_path = r.path.size();
+  *score = r.score;
+  return g_panic ? -1 : 0;
+}
+
+int orc_sdpkpp_union_lcskpp_path(const uint32_t* xy, uint64_t n_matches, uint32_t k, uint32_t match_score,
+                                 int32_t gap_open, int32_t gap_extend, uint64_t* out_path, uint64_t* n_path) {
+  g_panic = false;
+  std::vector<Match> m(n_matches);
+  for (uint64_t i = 0; i < n_matches; ++i) m[i] = {xy[2 * i], xy[2 * i + 1]};
+  const std::vector<uint64_t> r = sdpkpp_union_lcskpp_path(m, k, match_score, gap_open, gap_extend);
+  for (uint64_t i = 0; i < r.size(); ++i) out_path[i] = r[i];  // cap >= 2 * n_matches
+  *n_path = r.size();
+  return g_panic ? -1 : 0;
+}
+
+// returns the number of expanded matches (only the first cap are written), or ~0 on a panic path
+uint64_t orc_expand_kmer_matches(const uint8_t* x, uint32_t m, const uint8_t* y, uint32_t n, uint32_t k,
+                                 const uint32_t* xy, uint64_t n_matches, uint32_t allowed_mismatches,
+                                 uint32_t* out_xy, uint64_t cap) {
+  g_panic = false;
+  std::vector<Match> mm(n_matches);
+  for (uint64_t i = 0; i < n_matches; ++i) mm[i] = {xy[2 * i], xy[2 * i + 1]};
+  const std::vector<Match> r = expand_kmer_matches(x, m, y, n, k, mm, allowed_mismatches);
+  if (g_panic) return ~0ull;
+  for (uint64_t i = 0; i < r.size() && i < cap; ++i) {
+    out_xy[2 * i] = r[i].first;
+    out_xy[2 * i + 1] = r[i].second;
+  }
+  return r.size();
+}
+
+// banded::Aligner::custom_with_{matches, expanded_matches, match_path} (have_path / allowed_mismatches < 0 /
+// use_lcskpp_union select which, see BandedAligner::align_hinted)
+int orc_banded_align_hinted(const orc_scoring* scoring, uint32_t k, uint32_t w, const uint8_t* x, uint32_t m,
+                            const uint8_t* y, uint32_t n, const uint32_t* match_xy, uint64_t n_matches,
+                            const uint64_t* path, uint64_t n_path, int32_t have_path, int32_t allowed_mismatches,
+                            int32_t use_lcskpp_union, orc_alignment* out, uint32_t* ops, uint64_t* num_cells) {
+  g_panic = false;
+  BandedAligner a;
+  a.sc = *scoring;
+  a.k = k;
+  a.w = w;
+  std::vector<Match> mm(n_matches);
+  for (uint64_t i = 0; i < n_matches; ++i) mm[i] = {match_xy[2 * i], match_xy[2 * i + 1]};
+  std::vector<uint64_t> pp(path, path + (have_path ? n_path : 0));
+  std::vector<Op> v;
+  a.align_hinted(x, m, y, n, true, mm, have_path != 0, pp, allowed_mismatches, use_lcskpp_union != 0, out, v);
+  if (g_panic) {
+    out->n_ops = 0xFFFFFFFFu;
+    return -1;
+  }
+  if (num_cells) *num_cells = a.band.num_cells();
   for (size_t t = 0; t < v.size(); ++t) ops[t] = v[t].code | (v[t].len << 3);
   return 0;
 }

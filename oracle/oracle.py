@@ -209,3 +209,74 @@ def sdpkpp(matches, k, match_score, gap_open, gap_extend):
                           C.c_int32(gap_extend), path, C.byref(npath), C.byref(score))
     assert rc == 0
     return [int(path[i]) for i in range(npath.value)], int(score.value)
+
+
+def _xy(matches):
+    n = len(matches)
+    xy = (C.c_uint32 * (2 * max(1, n)))()
+    for i, (a, b) in enumerate(matches):
+        xy[2 * i], xy[2 * i + 1] = a, b
+    return xy, n
+
+
+def lcskpp(matches, k):
+    """sparse::lcskpp (sparse.rs:67-143) -> (path, score)"""
+    xy, n = _xy(matches)
+    path = (C.c_uint64 * max(1, n))()
+    npath, score = C.c_uint64(0), C.c_uint32(0)
+    rc = lib().orc_lcskpp(xy, C.c_uint64(n), C.c_uint32(k), path, C.byref(npath), C.byref(score))
+    if rc != 0:
+        raise RuntimeError("lcskpp oracle: the reference would panic on this input")
+    return [int(path[i]) for i in range(npath.value)], int(score.value)
+
+
+def sdpkpp_union_lcskpp_path(matches, k, match_score, gap_open, gap_extend):
+    """sparse::sdpkpp_union_lcskpp_path (sparse.rs:297-330) -> path"""
+    xy, n = _xy(matches)
+    path = (C.c_uint64 * max(1, 2 * n))()
+    npath = C.c_uint64(0)
+    rc = lib().orc_sdpkpp_union_lcskpp_path(xy, C.c_uint64(n), C.c_uint32(k), C.c_uint32(match_score),
+                                            C.c_int32(gap_open), C.c_int32(gap_extend), path, C.byref(npath))
+    if rc != 0:
+        raise RuntimeError("union path oracle: the reference would panic on this input")
+    return [int(path[i]) for i in range(npath.value)]
+
+
+def expand_kmer_matches(x: bytes, y: bytes, k: int, matches, allowed_mismatches: int):
+    """sparse::expand_kmer_matches (sparse.rs:404-498) -> sorted expanded matches"""
+    xy, n = _xy(matches)
+    L = lib()
+    L.orc_expand_kmer_matches.restype = C.c_uint64
+    cap = max(16, 4 * (n + 1) * (allowed_mismatches + 2))
+    while True:
+        out = (C.c_uint32 * (2 * cap))()
+        got = L.orc_expand_kmer_matches(x, C.c_uint32(len(x)), y, C.c_uint32(len(y)), C.c_uint32(k), xy,
+                                        C.c_uint64(n), C.c_uint32(allowed_mismatches), out, C.c_uint64(cap))
+        if got == 0xFFFFFFFFFFFFFFFF:
+            raise RuntimeError("expand_kmer_matches oracle: the reference would panic on this input")
+        if got <= cap:
+            return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(got)]
+        cap = int(got)
+
+
+def banded_align_hinted(scoring: OrcScoring, k: int, w: int, x: bytes, y: bytes, matches, path=None,
+                        allowed_mismatches=None, use_lcskpp_union=False):
+    """banded::Aligner::custom_with_matches / custom_with_expanded_matches / custom_with_match_path
+    (banded.rs:313-401) -> (fields, ops, band cells); None when the reference would panic."""
+    m, n = len(x), len(y)
+    xy, nm = _xy(matches)
+    pp = (C.c_uint64 * max(1, len(path or [])))(*(path or []))
+    out = OrcAlignment()
+    ops = (C.c_uint32 * (m + n + 8))()
+    cells = C.c_uint64(0)
+    L = lib()
+    L.orc_banded_align_hinted.restype = C.c_int
+    rc = L.orc_banded_align_hinted(C.byref(scoring), C.c_uint32(k), C.c_uint32(w), x, C.c_uint32(m), y, C.c_uint32(n),
+                                   xy, C.c_uint64(nm), pp, C.c_uint64(len(path or [])),
+                                   C.c_int32(1 if path is not None else 0),
+                                   C.c_int32(-1 if allowed_mismatches is None else int(allowed_mismatches)),
+                                   C.c_int32(1 if use_lcskpp_union else 0), C.byref(out), ops, C.byref(cells))
+    if rc != 0:
+        return None
+    d = {f: getattr(out, f) for f, _ in OrcAlignment._fields_}
+    return d, [(int(v) & 7, int(v) >> 3) for v in ops[:out.n_ops]], int(cells.value)

@@ -93,6 +93,56 @@ def test_sparse_known_answers(oracle):
     assert [m[p] for p in path] == [(i, i) for i in range(len(path))]
 
 
+def test_lcskpp_and_expand_known_answers(oracle):
+    """sparse::lcskpp / expand_kmer_matches against the reference's unit vectors (sparse.rs:518-770)."""
+    sp = G["sparse"]
+    for c in sp["lcskpp"]["cases"]:
+        m = oracle.find_kmer_matches(c["s1"].encode(), c["s2"].encode(), c["k"])
+        path, score = oracle.lcskpp(m, c["k"])
+        assert score == c["score"]
+        if "match_path" in c:
+            assert [list(m[p]) for p in path] == c["match_path"]
+        if "path" in c:
+            assert path == c["path"]
+        if c.get("diagonal"):
+            assert [m[p] for p in path] == [(i, i) for i in range(len(path))]
+    for a, b in sp["lcskpp"]["equals_sdpkpp_1_0_0"]["pairs"]:  # strict_compare_lcskpp_sdpkpp
+        m = oracle.find_kmer_matches(a.encode(), b.encode(), 8)
+        assert oracle.lcskpp(m, 8) == oracle.sdpkpp(m, 8, 1, 0, 0)
+    t = sp["sdpkpp_tandem_repeat"]
+    m = oracle.find_kmer_matches(t["query"].encode(), t["target"].encode(), t["k"])
+    assert oracle.lcskpp(m, t["k"])[1] == len(t["query"])
+    for c in sp["expanded_find_kmer"]["cases"]:
+        m = oracle.find_kmer_matches(c["x"].encode(), c["y"].encode(), 6)
+        assert [list(v) for v in oracle.expand_kmer_matches(c["x"].encode(), c["y"].encode(), 6, m, 1)] == c["expanded_1"]
+
+
+def test_hinted_entry_points_reduce_to_custom(oracle):
+    """custom_with_matches(find_kmer_matches(x, y)) == custom(x, y); custom_with_match_path(sdpkpp path) too;
+    expanded matches with 0 allowed mismatches only add diagonal neighbours that are matches already."""
+    rng = np.random.default_rng(11)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, -3, -4, -2, -6, has_match_scores=1)
+    for trial in range(12):
+        y = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 160)])
+        x = bytearray(y[30:110])
+        for p in rng.integers(0, len(x), 4):
+            x[p] = b"ACGT"[rng.integers(0, 4)]
+        x = bytes(x)
+        k, w = 6, 5
+        want = oracle.banded_align("custom", s, k, w, x, y)
+        m = oracle.find_kmer_matches(x, y, k)
+        got = oracle.banded_align_hinted(s, k, w, x, y, m)
+        assert got is not None and (got[0], got[1]) == want
+        path, _ = oracle.sdpkpp(m, k, 1, -5, -1)
+        got = oracle.banded_align_hinted(s, k, w, x, y, m, path=path)
+        assert (got[0], got[1]) == want
+        e0 = oracle.expand_kmer_matches(x, y, k, m, 0)
+        assert set(m) <= set(e0)
+        # unsorted matches: the reference asserts (sparse.rs:213-218)
+        if len(m) >= 2:
+            assert oracle.banded_align_hinted(s, k, w, x, y, m[::-1]) is None
+
+
 def test_degenerate_c4_case_returns_empty_alignment(oracle):
     """Independent random 500 x 10,000 has no 32-mer match -> full matrix -> 5,010,501 > MAX_CELLS ->
     the reference returns the empty MIN_SCORE alignment (banded.rs:104, 407-420; BASELINE.md note on C4)."""

@@ -155,7 +155,7 @@ int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t row
 
 /* b2a_align_batch cuts batches of >= 262,144 pairs into `chunks` pieces that alternate between two
  * internal engines, so one chunk's copies and host planning overlap the other's kernels.
- * chunks < 2 disables the pipeline (default 5; the first and last chunk are half-size). Results are identical either way. */
+ * chunks < 2 disables the pipeline (default 5, relative sizes 1,3,6,6,3). Results are identical either way. */
 int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks);
 
 /* One-call form: Aligner::{custom,global,semiglobal,local} over a batch with
@@ -168,6 +168,31 @@ int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
 int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
                                uint32_t k, uint32_t w, const b2a_pairs* pairs,
                                b2a_results* results, b2a_stats* stats);
+
+/* The banded::Aligner entry points that take the band's inputs from the caller (banded.rs:294-401, 938-975):
+ *   custom_with_prehash / semiglobal_with_prehash   the k-mer hash of y only speeds the reference's match search
+ *                                                   up; the matches, hence the results, are those of custom /
+ *                                                   semiglobal: call b2a_align_batch_banded
+ *   custom_with_matches(x, y, matches)              match_off + match_xy
+ *   custom_with_expanded_matches(.., allowed_mismatches, use_lcskpp_union)
+ *                                                   match_off + match_xy, allowed_mismatches (-1 = None),
+ *                                                   use_lcskpp_union
+ *   custom_with_match_path(x, y, matches, path)     match_off + match_xy + path_off + path_idx
+ * Pair p's matches are (match_xy[2i], match_xy[2i+1]) = (xpos, ypos) for i in [match_off[p], match_off[p+1]),
+ * its path the indices path_idx[path_off[p] .. path_off[p+1]) into those matches.  Where the reference panics
+ * (matches not strictly ascending, a path index out of range, an empty path, positions outside the matrix) the
+ * batch is refused with B2A_E_INVALID. */
+typedef struct b2a_band_hints {
+  const uint64_t* match_off; /* n_pairs + 1 */
+  const uint32_t* match_xy;
+  const uint64_t* path_off;  /* n_pairs + 1, or NULL */
+  const uint32_t* path_idx;
+  int32_t allowed_mismatches; /* -1: matches are used as given */
+  int32_t use_lcskpp_union;
+} b2a_band_hints;
+int32_t b2a_align_batch_banded_hinted(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                                      uint32_t k, uint32_t w, const b2a_pairs* pairs,
+                                      const b2a_band_hints* hints, b2a_results* results, b2a_stats* stats);
 
 /* Staged form of b2a_align_batch, so a caller can keep a batch resident in HBM:
  *   stage: validate, plan, host->device copy of the batch (async on the stream);

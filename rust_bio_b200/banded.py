@@ -5,6 +5,12 @@ and the band half-width `w` like the reference (banded.rs:150-267); `custom / gl
 local` (banded.rs:282, 872, 901, 975) and their `*_batch` forms run K4 (k-mer matches -> SDPk++ chain
 -> Band) and K3 (banded fill + walk) on the GPU.  A band with more than MAX_CELLS = 5,000,000 cells
 returns the reference's empty alignment (score MIN_SCORE, no operations, xlen = ylen = 0; banded.rs:407-420).
+
+The entry points that take the band's inputs from the caller (banded.rs:294-401, 938-975) are here too:
+`custom_with_prehash / semiglobal_with_prehash` (the prehash of y only accelerates the reference's match search;
+results are those of `custom / semiglobal`), `custom_with_matches`, `custom_with_expanded_matches`,
+`custom_with_match_path`, each with a `*_batch` form.  `hash_kmers` / `find_kmer_matches` mirror sparse.rs:337-358
+for callers that want to build those inputs the way the reference's doctests do.
 """
 from __future__ import annotations
 
@@ -65,6 +71,60 @@ class Aligner:
                                  AlignmentMode.Custom if refused else mode))
         return out
 
+    def _batch_hinted(self, pairs, matches, paths=None, allowed_mismatches=None, use_lcskpp_union=False):
+        batch = pack_pairs(pairs)
+        cs, keep = self.scoring.to_c(batch[0])
+        res = self.engine.align_batch_banded_hinted(MODE_CUSTOM, cs, self.k, self.w, batch, matches, paths,
+                                                    allowed_mismatches, use_lcskpp_union)
+        out = []
+        for i, (x, y) in enumerate(pairs):
+            ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
+            refused = int(res.score[i]) == MIN_SCORE and not ops
+            out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]), int(res.yend[i]),
+                                 int(res.xend[i]), 0 if refused else len(y), 0 if refused else len(x), ops,
+                                 AlignmentMode.Custom))
+        return out
+
+    # ---- banded.rs:294-401: the band's inputs come from the caller
+    def custom_with_prehash(self, x: bytes, y: bytes, y_kmer_hash) -> Alignment:
+        """banded.rs:294-302.  `y_kmer_hash` (see hash_kmers) only spares the reference the hashing of y; the
+        matches it yields are find_kmer_matches(x, y, k), so this is `custom`."""
+        return self.custom(x, y)
+
+    def custom_with_prehash_batch(self, pairs, y_kmer_hashes=None):
+        return self.custom_batch(pairs)
+
+    def semiglobal_with_prehash(self, x: bytes, y: bytes, y_kmer_hash) -> Alignment:
+        """banded.rs:938-975 (same clip presets and clip filtering as semiglobal)."""
+        return self.semiglobal(x, y)
+
+    def semiglobal_with_prehash_batch(self, pairs, y_kmer_hashes=None):
+        return self.semiglobal_batch(pairs)
+
+    def custom_with_matches(self, x: bytes, y: bytes, matches) -> Alignment:
+        """banded.rs:313-321: `matches` = sorted [(xpos, ypos), ...]."""
+        return self._batch_hinted([(x, y)], [list(matches)])[0]
+
+    def custom_with_matches_batch(self, pairs, matches):
+        return self._batch_hinted(pairs, [list(m) for m in matches])
+
+    def custom_with_expanded_matches(self, x: bytes, y: bytes, matches, allowed_mismatches: Optional[int],
+                                     use_lcskpp_union: bool) -> Alignment:
+        """banded.rs:338-375: sparse::expand_kmer_matches when allowed_mismatches is not None, then the band
+        along sdpkpp's path or along sdpkpp_union_lcskpp_path."""
+        return self._batch_hinted([(x, y)], [list(matches)], None, allowed_mismatches, use_lcskpp_union)[0]
+
+    def custom_with_expanded_matches_batch(self, pairs, matches, allowed_mismatches: Optional[int],
+                                           use_lcskpp_union: bool):
+        return self._batch_hinted(pairs, [list(m) for m in matches], None, allowed_mismatches, use_lcskpp_union)
+
+    def custom_with_match_path(self, x: bytes, y: bytes, matches, path) -> Alignment:
+        """banded.rs:391-401: the band follows matches[path[0]], matches[path[1]], ... as given."""
+        return self._batch_hinted([(x, y)], [list(matches)], [list(path)])[0]
+
+    def custom_with_match_path_batch(self, pairs, matches, paths):
+        return self._batch_hinted(pairs, [list(m) for m in matches], [list(p) for p in paths])
+
     def custom_batch(self, pairs):
         return self._batch(MODE_CUSTOM, pairs)
 
@@ -91,3 +151,20 @@ class Aligner:
 
 
 setattr(Aligner, "global", Aligner.global_)
+
+
+def hash_kmers(seq: bytes, k: int):
+    """sparse::hash_kmers (sparse.rs:350-358): k-mer -> list of start positions."""
+    out = {}
+    for i in range(max(0, len(seq) + 1 - k)):
+        out.setdefault(bytes(seq[i:i + k]), []).append(i)
+    return out
+
+
+def find_kmer_matches(seq1: bytes, seq2: bytes, k: int):
+    """sparse::find_kmer_matches (sparse.rs:337-347): all (i, j) with seq1[i..i+k] == seq2[j..j+k], sorted.
+    Host-side convenience for building `custom_with_matches` inputs; the aligner itself finds matches on the GPU."""
+    h = hash_kmers(seq2, k)
+    out = [(i, j) for i in range(max(0, len(seq1) + 1 - k)) for j in h.get(bytes(seq1[i:i + k]), ())]
+    out.sort()
+    return out

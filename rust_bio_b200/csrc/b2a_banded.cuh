@@ -43,6 +43,13 @@ struct BandedParams {
   const uint64_t* ranges_off;
   uint64_t* num_cells;     // [n_pairs] out (K4), in (K3)
   uint32_t* k4_status;     // [n_pairs] 0 ok, 1 too many matches
+  // caller-supplied band inputs (banded.rs:294-401); null = found on the device
+  const uint64_t* hint_match_off;  // [n_pairs + 1] into hint_match_xy pairs, or null
+  const uint32_t* hint_match_xy;   // (xpos, ypos) per match
+  const uint64_t* hint_path_off;   // [n_pairs + 1] into hint_path_idx, or null (custom_with_match_path)
+  const uint32_t* hint_path_idx;
+  int32_t allowed_mismatches;      // custom_with_expanded_matches: >= 0 expands the matches, -1 = None
+  int32_t use_lcskpp_union;        // custom_with_expanded_matches
   // K3 state
   uint8_t* fill;           // K3 slab arena
   const uint64_t* fill_off;  // per pair byte offset of the K3 slab
@@ -130,6 +137,7 @@ B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
   b += (uint64_t)cap * 4 * 2;      // dp
   b += (uint64_t)(cap + 2) * sizeof(PrevPtrD);
   b += (uint64_t)cap * 4 * 2;      // ycoord, path
+  b += (uint64_t)cap * 4 * 2;      // path continues (a union path holds up to 2*cap entries), lcskpp path
   return (b + 255) & ~255ull;
 }
 
@@ -137,6 +145,7 @@ B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
 struct BandD {
   uint32_t* r;  // r[2j] = start, r[2j+1] = end
   uint64_t rows, cols;
+  bool oob = false;  // a column index past the matrix: the reference panics on ranges[j] (caller-supplied matches)
   B2A_HD void init(uint64_t m, uint64_t n) {  // Band::new, banded.rs:1061-1067
     rows = m + 1;
     cols = n + 1;
@@ -146,9 +155,17 @@ struct BandD {
     }
   }
   B2A_HD void lo(uint64_t j, uint64_t v) {
+    if (j >= cols) {
+      oob = true;
+      return;
+    }
     if ((uint64_t)r[2 * j] > v) r[2 * j] = (uint32_t)v;
   }
   B2A_HD void hi(uint64_t j, uint64_t v) {
+    if (j >= cols) {
+      oob = true;
+      return;
+    }
     if ((uint64_t)r[2 * j + 1] < v) r[2 * j + 1] = (uint32_t)v;
   }
   B2A_HD void add_kmer(uint64_t r0, uint64_t c0, uint64_t k, uint64_t w) {  // banded.rs:1071-1107
@@ -236,6 +253,10 @@ struct BandD {
     }
     {
       const uint64_t rr = (uint64_t)en0 + k, c = (uint64_t)en1 + k;
+      if (rr > rows || c > cols) {  // rows - rr underflows in the reference (caller-supplied matches only)
+        oob = true;
+        return ok;
+      }
       if (!(rr == rows && c == cols)) {
         int32_t from_end = rr == rows ? 0 : sc.xclip_suffix;
         from_end += c == cols ? 0 : sc.yclip_suffix;
@@ -343,10 +364,13 @@ B2A_HD uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {  //
 }
 
 // returns path length (path[] = indices into matches), 0 if no matches
+// lcs = true runs sparse::lcskpp (sparse.rs:67-143) on the same machinery: unit scores, no gap term, and a
+// prefix-max tree over (score, id) tuples -- PrevPtrD{0, score, 0, id, 0, 0} compares exactly like that tuple.
 B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint32_t match_score, int32_t gap_open,
                          int32_t gap_extend, uint64_t* ev /*4*nm u64*/, uint32_t* dp_score, int32_t* dp_prev,
-                         PrevPtrD* fen, uint32_t* ycoord, uint32_t* path) {
+                         PrevPtrD* fen, uint32_t* ycoord, uint32_t* path, bool lcs = false) {
   if (nm == 0) return 0;
+  if (lcs) match_score = 1;
   const uint32_t go = (uint32_t)(-gap_open), ge = (uint32_t)(-gap_extend);
   // events sorted lexicographically by (x, y, id): pack (x, y) in one key and sort pairs by two passes:
   // sort by combined 64-bit key (x << 32 | y) with id as tie-break -> id < 2*nm <= 2^31; use a stable
@@ -408,14 +432,19 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
         }
       }
       if (best.score > 0) {
-        const uint32_t g0 = e0 - best.x, g1 = e1 - best.y;
-        const uint32_t gap = g0 > g1 ? g0 : g1;
-        const uint32_t pen = gap > 0 ? go + gap * ge : 0;
-        const uint32_t sum = best.score + k * match_score;
-        const uint32_t ns = sum > pen ? sum - pen : 0;
-        if (dp_gt(ns, (int32_t)best.id, dp_score[p], dp_prev[p])) {
-          dp_score[p] = ns;
+        if (lcs) {  // dp[p] = (k + best_value, best_position), sparse.rs:111-113
+          dp_score[p] = k + best.score;
           dp_prev[p] = (int32_t)best.id;
+        } else {
+          const uint32_t g0 = e0 - best.x, g1 = e1 - best.y;
+          const uint32_t gap = g0 > g1 ? g0 : g1;
+          const uint32_t pen = gap > 0 ? go + gap * ge : 0;
+          const uint32_t sum = best.score + k * match_score;
+          const uint32_t ns = sum > pen ? sum - pen : 0;
+          if (dp_gt(ns, (int32_t)best.id, dp_score[p], dp_prev[p])) {
+            dp_score[p] = ns;
+            dp_prev[p] = (int32_t)best.id;
+          }
         }
         if (dp_gt(dp_score[p], (int32_t)p, best_score, best_idx)) {
           best_score = dp_score[p];
@@ -444,12 +473,12 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
         }
       }
       PrevPtrD pf;
-      pf.d = e0 + e1;
-      pf.plane = dp_score[p] + pf.d * ge;
+      pf.d = lcs ? 0u : e0 + e1;
+      pf.plane = lcs ? 0u : dp_score[p] + pf.d * ge;
       pf.score = dp_score[p];
       pf.id = p;
-      pf.x = e0;
-      pf.y = e1;
+      pf.x = lcs ? 0u : e0;
+      pf.y = lcs ? 0u : e1;
       uint32_t idx = lower_bound_u32(ycoord, ny, e1) + 1;  // 1-based rank of this coordinate
       while (idx <= ny) {
         if (prev_ge(pf, fen[idx])) fen[idx] = pf;
@@ -471,11 +500,100 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
   return np;
 }
 
-// ------------------------------------------------------------------ K4: Band::create for one pair
-// returns status: 0 ok, 1 too many matches (capacity), 2 reference would panic (divide by zero)
+// ------------------------------------------------------------------ sparse::expand_kmer_matches, sparse.rs:404-498
+// The reference's two hash maps keyed by diagonal hold "the previous (next) match on this diagonal in processing
+// order"; with the matches sorted that is the predecessor (successor) in (diagonal, x) order, found here by
+// binary search in a sorted key array.  matches: sorted (x << 32 | y), expanded in place; returns the new count,
+// ~0 if more than cap, ~1 where the reference would panic (a position outside the sequences).
+B2A_HD uint64_t expand_kmer_matches_d(const uint8_t* s1, uint64_t l1, const uint8_t* s2, uint64_t l2, uint64_t k,
+                                      uint64_t* matches, uint64_t nm, uint64_t cap, uint64_t allowed,
+                                      uint64_t* dk /* cap u64 */) {
+  auto diag_of = [](uint64_t mt) -> uint64_t {
+    return (uint64_t)(uint32_t)((uint32_t)(mt >> 32) - (uint32_t)mt + 0x80000000u);
+  };
+  auto lower = [](const uint64_t* a, uint64_t n, uint64_t v) -> uint64_t {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) / 2;
+      if (a[mid] < v) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  for (uint64_t i = 0; i < nm; ++i) {
+    const uint64_t x = matches[i] >> 32, y = matches[i] & 0xffffffffull;
+    if (x > l1 || y > l2) return ~1ull;
+    dk[i] = (diag_of(matches[i]) << 32) | x;
+  }
+  heap_sort_u64(dk, nm);
+  uint64_t cnt = nm;
+  for (uint64_t i = 0; i < nm; ++i) {  // extend to the left, 417-448
+    const int64_t x = (int64_t)(matches[i] >> 32), y = (int64_t)(matches[i] & 0xffffffffull);
+    const uint64_t dg = diag_of(matches[i]);
+    const uint64_t q = lower(dk, nm, (dg << 32) | (uint64_t)x);
+    int64_t last_x;  // x of the last match along this diagonal (the pair is on the diagonal: compare x only)
+    if (q > 0 && (dk[q - 1] >> 32) == dg) last_x = (int64_t)(dk[q - 1] & 0xffffffffull);
+    else last_x = x - (x < y ? x : y) - 1;
+    uint64_t n_mis = 0;
+    int64_t cx = x - 1, cy = y - 1;
+    for (;;) {
+      if (last_x >= cx) break;
+      n_mis += s1[cx] == s2[cy] ? 0 : 1;
+      if (n_mis > allowed) break;
+      if (cnt >= cap) return ~0ull;
+      matches[cnt++] = ((uint64_t)cx << 32) | (uint64_t)cy;
+      cx -= 1;
+      cy -= 1;
+    }
+  }
+  heap_sort_u64(matches, cnt);
+  const uint64_t nl = cnt;  // the left-expanded set; extend each of its members to the right, 450-494
+  for (uint64_t i = 0; i < nl; ++i) dk[i] = (diag_of(matches[i]) << 32) | (matches[i] >> 32);
+  heap_sort_u64(dk, nl);
+  for (uint64_t i = 0; i < nl; ++i) {
+    const uint64_t x = matches[i] >> 32, y = matches[i] & 0xffffffffull;
+    const uint64_t dg = diag_of(matches[i]);
+    const uint64_t q = lower(dk, nl, (dg << 32) | x) + 1;
+    uint64_t next_x;
+    if (q < nl && (dk[q] >> 32) == dg) {
+      next_x = dk[q] & 0xffffffffull;
+    } else {
+      const uint64_t a = l1 - x, b = l2 - y, mn = a < b ? a : b;
+      next_x = x + sat_sub64(mn, k - 1);
+    }
+    uint64_t n_mis = 0;
+    uint64_t cx = x + 1, cy = y + 1;
+    for (;;) {
+      if (cx >= next_x) break;
+      if (cx + k - 1 >= l1 || cy + k - 1 >= l2) return ~1ull;  // index out of bounds in the reference
+      n_mis += s1[cx + k - 1] == s2[cy + k - 1] ? 0 : 1;
+      if (n_mis > allowed) break;
+      if (cnt >= cap) return ~0ull;
+      matches[cnt++] = (cx << 32) | cy;
+      cx += 1;
+      cy += 1;
+    }
+  }
+  heap_sort_u64(matches, cnt);
+  return cnt;
+}
+
+// ------------------------------------------------------------------ K4: Band::create* for one pair
+struct BandHintsD {
+  const uint32_t* mxy = nullptr;  // caller's matches (xpos, ypos); null: find them (Band::create)
+  uint64_t n_matches = 0;
+  const uint32_t* pidx = nullptr;  // caller's path (custom_with_match_path); null: sdpkpp [union lcskpp]
+  uint64_t n_path = 0;
+  bool have_path = false;
+  int32_t allowed_mismatches = -1;
+  int32_t use_lcskpp_union = 0;
+};
+
+// returns status: 0 ok, 1 too many matches (capacity), 2 reference would panic (divide by zero),
+// 3 reference would panic on the caller's matches/path (not sorted, index out of range, outside the matrix)
 B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint32_t k, uint32_t w,
                               const DevScoring& sc, int32_t has_match_scores, uint8_t* slab, uint32_t cap,
-                              uint32_t* ranges, uint64_t* cells_out) {
+                              uint32_t* ranges, uint64_t* cells_out, const BandHintsD& hint = BandHintsD{}) {
   const uint64_t short_len = m <= n ? m : n;
   uint32_t H = 16;
   while (H < 2 * (short_len + 1)) H <<= 1;
@@ -486,23 +604,72 @@ B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, ui
   int32_t* dp_prev = reinterpret_cast<int32_t*>(dp_score + cap);
   PrevPtrD* fen = reinterpret_cast<PrevPtrD*>(dp_prev + cap);
   uint32_t* ycoord = reinterpret_cast<uint32_t*>(fen + cap + 2);
-  uint32_t* path = ycoord + cap;
+  uint32_t* path = ycoord + cap;          // 2 * cap entries
+  uint32_t* path2 = path + 2ull * cap;    // cap entries (lcskpp path)
   BandD band;
   band.r = ranges;
   band.init(m, n);
-  const uint64_t nm64 = find_kmer_matches_d(x, m, y, n, k, table, H, matches, cap);
-  if (nm64 == ~0ull) {
-    *cells_out = 0;
-    return 1;
+  *cells_out = 0;
+  uint64_t nm64;
+  if (hint.mxy) {
+    if (hint.n_matches > cap) return 1;
+    for (uint64_t i = 0; i < hint.n_matches; ++i)
+      matches[i] = ((uint64_t)hint.mxy[2 * i] << 32) | (uint64_t)hint.mxy[2 * i + 1];
+    nm64 = hint.n_matches;
+  } else {
+    nm64 = find_kmer_matches_d(x, m, y, n, k, table, H, matches, cap);
+    if (nm64 == ~0ull) return 1;
+  }
+  // sdpkpp, lcskpp and expand_kmer_matches assert strictly ascending matches (sparse.rs:77-82, 213-218, 411-416)
+  auto sorted = [&](uint64_t cnt) {
+    for (uint64_t i = 1; i < cnt; ++i)
+      if (!(matches[i - 1] < matches[i])) return false;
+    return true;
+  };
+  if (hint.allowed_mismatches >= 0) {  // custom_with_expanded_matches, banded.rs:346-349
+    if (!sorted(nm64)) return 3;
+    nm64 = expand_kmer_matches_d(x, m, y, n, k, matches, nm64, cap, (uint64_t)hint.allowed_mismatches, ev);
+    if (nm64 == ~0ull) return 1;
+    if (nm64 == ~1ull) return 3;
   }
   const uint32_t nm = (uint32_t)nm64;
   uint32_t status = 0;
   if (nm == 0) {
-    band.full_matrix();  // banded.rs:1309-1313
+    band.full_matrix();  // banded.rs:1309-1313, 1341-1344
   } else {
-    const int32_t ms = has_match_scores ? sc.match_score : BANDED_DEFAULT_MATCH_SCORE;  // 1315-1318
-    const uint32_t np = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score, dp_prev,
-                                 fen, ycoord, path);
+    uint32_t np;
+    if (hint.have_path) {  // custom_with_match_path: the path is used as given (391-401)
+      if (hint.n_path == 0 || hint.n_path > 2ull * cap) return hint.n_path == 0 ? 3 : 1;
+      for (uint64_t t = 0; t < hint.n_path; ++t) {
+        if (hint.pidx[t] >= nm) return 3;
+        path[t] = hint.pidx[t];
+      }
+      np = (uint32_t)hint.n_path;
+    } else {
+      if (!sorted(nm)) return 3;
+      const int32_t ms = has_match_scores ? sc.match_score : BANDED_DEFAULT_MATCH_SCORE;  // 1315-1318
+      if (hint.use_lcskpp_union) {  // sparse::sdpkpp_union_lcskpp_path, sparse.rs:297-330
+        const uint32_t nl = sdpkpp_d(matches, nm, k, 1u, 0, 0, ev, dp_score, dp_prev, fen, ycoord, path2, true);
+        uint32_t* sp = path + cap;  // the sdpkpp path, parked in the upper half while the union is assembled
+        const uint32_t ns = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score,
+                                     dp_prev, fen, ycoord, sp);
+        auto bsearch = [&](uint32_t v, bool& found) -> uint32_t {
+          const uint32_t q = lower_bound_u32(path2, nl, v);
+          found = q < nl && path2[q] == v;
+          return q;
+        };
+        bool f0 = false, f1 = false;
+        const uint32_t i0 = bsearch(sp[0], f0), i1 = bsearch(sp[ns - 1], f1);
+        const uint32_t pre = f0 ? i0 : 0u, post = f1 ? i1 + 1 : nl;
+        np = 0;
+        for (uint32_t t = 0; t < pre; ++t) path[np++] = path2[t];
+        for (uint32_t t = 0; t < ns; ++t) path[np++] = sp[t];  // np <= pre + t < cap + t: never overtakes sp
+        for (uint32_t t = post; t < nl; ++t) path[np++] = path2[t];
+      } else {
+        np = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score, dp_prev, fen, ycoord,
+                      path);
+      }
+    }
     // create_from_match_path, banded.rs:1330-1367
     const uint64_t first = matches[path[0]], last = matches[path[np - 1]];
     if (!band.set_boundaries((uint32_t)(first >> 32), (uint32_t)first, (uint32_t)(last >> 32), (uint32_t)last, k, w, sc))
@@ -524,6 +691,7 @@ B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, ui
       has_prev = true;
     }
   }
+  if (band.oob) return 3;
   *cells_out = band.num_cells();
   return status;
 }
@@ -1279,9 +1447,21 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   const uint64_t p = (uint64_t)prm.pair_lo + t;
   const uint64_t m = prm.x_len[p], n = prm.y_len[p];
   uint64_t cells = 0;
+  BandHintsD hint;
+  if (prm.hint_match_off) {
+    hint.mxy = prm.hint_match_xy + 2 * prm.hint_match_off[p];
+    hint.n_matches = prm.hint_match_off[p + 1] - prm.hint_match_off[p];
+  }
+  if (prm.hint_path_off) {
+    hint.pidx = prm.hint_path_idx + prm.hint_path_off[p];
+    hint.n_path = prm.hint_path_off[p + 1] - prm.hint_path_off[p];
+    hint.have_path = true;
+  }
+  hint.allowed_mismatches = prm.allowed_mismatches;
+  hint.use_lcskpp_union = prm.use_lcskpp_union;
   const uint32_t st = band_create_d(prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.k, prm.w, prm.sc,
                                     prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride, prm.cap_matches,
-                                    prm.ranges + prm.ranges_off[t] / 4, &cells);
+                                    prm.ranges + prm.ranges_off[t] / 4, &cells, hint);
   prm.num_cells[p] = cells;
   prm.k4_status[p] = st;
 }
@@ -1328,7 +1508,7 @@ __global__ void __launch_bounds__(128) banded_fill_kernel(const BandedParams prm
   prm.n_ops[p] = o.n_ops;
   prm.ops_src[p] = prm.ops_off[p] - o.n_ops;
   prm.status[p] = o.status;
-  if (o.status) atomicOr(prm.err_flag, o.status == 2 ? 2u : 1u);
+  if (o.status) atomicOr(prm.err_flag, o.status == 2 ? 2u : (o.status == 4 ? 8u : 1u));
   for (int q = 0; q < 4; ++q) prm.clip_len[4 * p + q] = o.clip[q];
 }
 

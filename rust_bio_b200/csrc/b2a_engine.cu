@@ -96,7 +96,7 @@ struct b2a_engine {
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
       d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
-      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff;
+      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> wave_ev;  // 3 per wave: fill start, fill stop / walk start, walk stop
   uint32_t launches = 0;
@@ -217,7 +217,8 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_opsscratch, &e->d_lut, &e->d_codemap, &e->d_ctl, &e->d_score, &e->d_xs,
                     &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
                     &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_prog, &e->d_bcells,
-                    &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill,
+                    &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill, &e->d_hmoff, &e->d_hmxy,
+                    &e->d_hpoff, &e->d_hpidx,
                     &e->d_bfoff};
   for (DevBuf* b : bufs) b->release();
   for (auto& v : e->ev)
@@ -643,6 +644,8 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
   if (ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
   if (ctl[1] & 4u) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
   if (ctl[1] & 2u) return e->fail(B2A_E_CAPACITY, "banded: more k-mer matches than the per-pair capacity");
+  if (ctl[1] & 8u)
+    return e->fail(B2A_E_INVALID, "banded: the reference panics on these caller-supplied matches/path (not strictly ascending, index out of range, or outside the matrix)");
   if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move or never terminates (the reference panics / hangs here: mod.rs:905, banded.rs:777-831)");
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
@@ -904,8 +907,29 @@ int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
   return b2a_batch_fetch(e, results, stats);
 }
 
+static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
+                           const b2a_pairs* pairs, const b2a_band_hints* hints, b2a_results* results,
+                           b2a_stats* stats);
+
 int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
                                const b2a_pairs* pairs, b2a_results* results, b2a_stats* stats) {
+  return banded_impl(e, mode, s, k, w, pairs, nullptr, results, stats);
+}
+
+int32_t b2a_align_batch_banded_hinted(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
+                                      const b2a_pairs* pairs, const b2a_band_hints* hints, b2a_results* results,
+                                      b2a_stats* stats) {
+  if (!e || !hints) return B2A_E_INVALID;
+  if (!hints->match_off || (!hints->match_xy && pairs && pairs->n_pairs && hints->match_off[pairs->n_pairs]))
+    return e->fail(B2A_E_INVALID, "banded hints: match_off / match_xy missing");
+  if (hints->path_off && (hints->allowed_mismatches >= 0 || hints->use_lcskpp_union))
+    return e->fail(B2A_E_INVALID, "banded hints: a match path excludes allowed_mismatches / use_lcskpp_union");
+  return banded_impl(e, mode, s, k, w, pairs, hints, results, stats);
+}
+
+static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
+                           const b2a_pairs* pairs, const b2a_band_hints* hints, b2a_results* results,
+                           b2a_stats* stats) {
   if (!e || !s || !pairs) return B2A_E_INVALID;
   if (k == 0) return e->fail(B2A_E_INVALID, "banded: k-mer length must be >= 1");
   uint32_t maxm = 0, maxn = 0;
@@ -957,8 +981,33 @@ int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s
   CK(cudaMemsetAsync(ctl, 0, 256, st));
 
   const uint32_t short_max = std::min(maxm, maxn);
-  uint32_t cap = 4 * short_max + 1024;
-  if (cap > (1u << 20)) cap = 1u << 20;
+  uint64_t cap64 = 4ull * short_max + 1024;
+  if (hints) {  // the caller's matches (and what expanding them can add) must fit the per-pair slab
+    uint64_t most = 0, most_path = 0;
+    for (uint64_t p = 0; p < n; ++p) {
+      if (hints->match_off[p + 1] < hints->match_off[p]) return e->fail(B2A_E_INVALID, "banded hints: match_off not ascending");
+      most = std::max(most, hints->match_off[p + 1] - hints->match_off[p]);
+      if (hints->path_off) {
+        if (hints->path_off[p + 1] < hints->path_off[p]) return e->fail(B2A_E_INVALID, "banded hints: path_off not ascending");
+        most_path = std::max(most_path, hints->path_off[p + 1] - hints->path_off[p]);
+      }
+    }
+    cap64 = std::max(cap64, most + 16);
+    cap64 = std::max(cap64, (most_path + 1) / 2 + 16);
+    if (hints->allowed_mismatches >= 0) cap64 = std::max<uint64_t>(cap64, 8 * most + 4ull * short_max + 1024);
+    const uint64_t tm = hints->match_off[n], tp = hints->path_off ? hints->path_off[n] : 0;
+    CK(e->d_hmoff.reserve((n + 1) * 8));
+    CK(e->d_hmxy.reserve(tm * 8 + 16));
+    CK(up(e->d_hmoff, hints->match_off, (n + 1) * 8));
+    CK(up(e->d_hmxy, hints->match_xy, tm * 8));
+    if (hints->path_off) {
+      CK(e->d_hpoff.reserve((n + 1) * 8));
+      CK(e->d_hpidx.reserve(tp * 4 + 16));
+      CK(up(e->d_hpoff, hints->path_off, (n + 1) * 8));
+      CK(up(e->d_hpidx, hints->path_idx, tp * 4));
+    }
+  }
+  uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, 1u << 20);
   const uint64_t k4_bytes = k4_slab_bytes(cap, short_max);
   uint64_t budget = e->tb_budget;
   if (!budget) {
@@ -983,6 +1032,17 @@ int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s
   // MatchParams keeps its compare/select form here (scores are read per cell from the blob bytes)
   if (!s->table) bp.sc.alpha = 0;
   bp.has_match_scores = s->has_match_scores;
+  bp.allowed_mismatches = -1;
+  if (hints) {
+    bp.hint_match_off = e->d_hmoff.as<uint64_t>();
+    bp.hint_match_xy = e->d_hmxy.as<uint32_t>();
+    if (hints->path_off) {
+      bp.hint_path_off = e->d_hpoff.as<uint64_t>();
+      bp.hint_path_idx = e->d_hpidx.as<uint32_t>();
+    }
+    bp.allowed_mismatches = hints->allowed_mismatches;
+    bp.use_lcskpp_union = hints->use_lcskpp_union;
+  }
   bp.k = k;
   bp.w = w;
   bp.cap_matches = cap;

@@ -134,6 +134,35 @@ class Engine:
                                                    C.byref(cp), C.byref(results.c), C.byref(self.stats)))
         return results
 
+    def align_batch_banded_hinted(self, mode: int, cscoring: CScoring, k: int, w: int, batch: Batch,
+                                  matches, paths=None, allowed_mismatches: Optional[int] = None,
+                                  use_lcskpp_union: bool = False, results: Optional[Results] = None) -> Results:
+        """banded::Aligner::custom_with_{matches, expanded_matches, match_path} over a batch
+        (b2a_align_batch_banded_hinted): matches[p] = [(xpos, ypos), ...] per pair, paths[p] = [index, ...]."""
+        from ._lib import CBandHints
+        n = len(batch[2])
+        if len(matches) != n or (paths is not None and len(paths) != n):
+            raise ValueError("one match list (and path) per pair")
+        moff = np.zeros(n + 1, dtype=np.uint64)
+        moff[1:] = np.cumsum([len(m) for m in matches])
+        mxy = np.array([v for m in matches for mt in m for v in mt], dtype=np.uint32).reshape(-1)
+        if mxy.size == 0:
+            mxy = np.zeros(2, dtype=np.uint32)
+        h = CBandHints(moff.ctypes.data, mxy.ctypes.data, None, None,
+                       -1 if allowed_mismatches is None else int(allowed_mismatches), 1 if use_lcskpp_union else 0)
+        if paths is not None:
+            poff = np.zeros(n + 1, dtype=np.uint64)
+            poff[1:] = np.cumsum([len(p) for p in paths])
+            pidx = np.array([v for p in paths for v in p] or [0], dtype=np.uint32)
+            h.path_off, h.path_idx = poff.ctypes.data, pidx.ctypes.data
+        if results is None:
+            results = Results(n, self.default_ops_capacity(batch))
+        cp = self._cpairs(batch)
+        self._check(self._L.b2a_align_batch_banded_hinted(self._h, int(mode), C.byref(cscoring), int(k), int(w),
+                                                          C.byref(cp), C.byref(h), C.byref(results.c),
+                                                          C.byref(self.stats)))
+        return results
+
     # staged form
     def stage(self, mode: int, cscoring: CScoring, batch: Batch):
         self._keep = (batch, cscoring)

@@ -296,3 +296,60 @@ extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint
   }
   return 0;
 }
+
+// One pair through K4 with caller-supplied band inputs (banded.rs:313-401) + K3; custom mode (clips kept).
+extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* x, uint32_t m32,
+                                     const uint8_t* y, uint32_t n32, const uint32_t* match_xy, uint64_t n_matches,
+                                     const uint32_t* path_idx, uint64_t n_path, int have_path,
+                                     int allowed_mismatches, int use_lcskpp_union, uint32_t cap_matches, int garbage,
+                                     int32_t* score, uint32_t* coords /*xstart,xend,ystart,yend*/, uint32_t* n_ops,
+                                     uint32_t* clip_len, uint32_t* status, uint64_t* num_cells, uint8_t* ops) {
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  const int32_t* table = s->table;
+  const uint64_t m = m32, n = n32;
+  std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
+  std::vector<uint32_t> rng(2 * (n + 1), 0xCDCDCDCDu);
+  BandHintsD hint;
+  hint.mxy = match_xy;
+  hint.n_matches = n_matches;
+  hint.pidx = path_idx;
+  hint.n_path = n_path;
+  hint.have_path = have_path != 0;
+  hint.allowed_mismatches = allowed_mismatches;
+  hint.use_lcskpp_union = use_lcskpp_union;
+  uint64_t cells = 0;
+  const uint32_t st = band_create_d(x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches, rng.data(),
+                                    &cells, hint);
+  *num_cells = cells;
+  BandedOut o{};
+  std::vector<uint8_t> opsbuf(m + n + 16, 0);
+  if (st != 0) {
+    o.status = 1 + st;
+  } else {
+    std::vector<uint8_t> fill(k3_slab_bytes(m, n, cells), (uint8_t)garbage);
+    auto scoref = [&](uint8_t a, uint8_t b) -> int32_t {
+      if (table) return table[(size_t)a * 256 + b];
+      return a == b ? sc.match_score : sc.mismatch_score;
+    };
+    banded_compute_d<1>(0, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), false,
+                        opsbuf.data() + opsbuf.size(), o);
+  }
+  *score = o.score;
+  coords[0] = o.xstart;
+  coords[1] = o.xend;
+  coords[2] = o.ystart;
+  coords[3] = o.yend;
+  *n_ops = o.n_ops;
+  *status = o.status;
+  for (int q = 0; q < 4; ++q) clip_len[q] = o.clip[q];
+  std::memcpy(ops, opsbuf.data() + opsbuf.size() - o.n_ops, o.n_ops);
+  return 0;
+}

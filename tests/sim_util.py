@@ -125,3 +125,35 @@ def banded_batch(mode, orc_scoring, k, w, blob, x_off, x_len, y_off, y_len, cap_
         assert np.array_equal(a[0][k_], b[0][k_]), ("scratch-dependent result", k_)
     assert a[1] == b[1]
     return a
+
+
+def banded_hinted_one(orc_scoring, k, w, x: bytes, y: bytes, matches, path=None, allowed_mismatches=None,
+                      use_lcskpp_union=False, cap_matches=4096):
+    """K4 with caller-supplied band inputs + K3 (host build of b2a_banded.cuh), custom mode.
+    -> (fields, ops, cells) or None when the device code flags a reference panic; two scratch fills must agree."""
+    s = SimScoring.from_buffer_copy(bytes(orc_scoring))
+    res = []
+    for garbage in (0x00, 0x7F):
+        xy = np.array([v for mt in matches for v in mt], dtype=np.uint32) if matches else np.zeros(2, np.uint32)
+        pi = np.array(path if path else [0], dtype=np.uint32)
+        score = C.c_int32(0)
+        coords = (C.c_uint32 * 4)()
+        clip = (C.c_uint32 * 4)()
+        n_ops, status, cells = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        ops = (C.c_uint8 * (len(x) + len(y) + 16))()
+        rc = lib().sim_banded_hinted_one(
+            C.byref(s), C.c_uint32(k), C.c_uint32(w), x, C.c_uint32(len(x)), y, C.c_uint32(len(y)),
+            xy.ctypes.data_as(C.c_void_p), C.c_uint64(len(matches)), pi.ctypes.data_as(C.c_void_p),
+            C.c_uint64(len(path) if path is not None else 0), C.c_int(1 if path is not None else 0),
+            C.c_int(-1 if allowed_mismatches is None else int(allowed_mismatches)),
+            C.c_int(1 if use_lcskpp_union else 0), C.c_uint32(cap_matches), C.c_int(garbage), C.byref(score),
+            coords, C.byref(n_ops), clip, C.byref(status), C.byref(cells), ops)
+        assert rc == 0
+        if status.value != 0:
+            res.append(("status", status.value))
+            continue
+        fields = {"score": score.value, "xstart": coords[0], "xend": coords[1], "ystart": coords[2],
+                  "yend": coords[3]}
+        res.append((fields, decode_ops(bytes(ops[:n_ops.value]), list(clip)), int(cells.value)))
+    assert res[0] == res[1], "scratch contents leak into the result"
+    return None if res[0][0] == "status" else res[0]

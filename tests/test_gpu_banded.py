@@ -144,3 +144,82 @@ def test_random_custom_clips_banded(eng, oracle, seed):
             eng.align_batch_banded(MODES["custom"], _c_scoring(go, ge, ma, mi, clips), k, w, batch)
     else:
         _compare(eng, oracle, "custom", _c_scoring(go, ge, ma, mi, clips), s, k, w, batch, f"banded custom {seed}")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_caller_supplied_band_inputs_batch(eng, oracle, seed):
+    """custom_with_matches / custom_with_expanded_matches / custom_with_match_path over batches, through
+    b2a_align_batch_banded_hinted, against the oracle's restatement of banded.rs:313-401."""
+    from rust_bio_b200.banded import Aligner, find_kmer_matches
+    from rust_bio_b200.pairwise import Scoring
+    from test_sim_banded import _window_pair
+    rng = np.random.default_rng(4000 + seed)
+    clips = [int(rng.choice([MIN, 0, -3, -9])) for _ in range(4)]
+    go, ge, ma, mi = int(rng.choice([-1, -5])), int(rng.choice([0, -1])), int(rng.choice([1, 2])), -2
+    s_o, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips, has_match_scores=1)
+    sc = Scoring.from_scores(go, ge, ma, mi)
+    sc.xclip_prefix, sc.xclip_suffix, sc.yclip_prefix, sc.yclip_suffix = clips
+    k, w = int(rng.choice([5, 7])), int(rng.choice([3, 6]))
+    aligner = Aligner.with_scoring(sc, k, w, engine=eng)
+    pairs = [_window_pair(rng, 80, 200) for _ in range(60)]
+    matches = []
+    for i, (x, y) in enumerate(pairs):
+        m = find_kmer_matches(x, y, k)
+        assert m == oracle.find_kmer_matches(x, y, k)
+        matches.append([mt for j, mt in enumerate(m) if j % 4 != 2] if i % 2 else m)
+
+    def check(got, kw):
+        n_ok = 0
+        for (x, y), m, a in zip(pairs, matches, got):
+            want = oracle.banded_align_hinted(s_o, k, w, x, y, m, **kw)
+            assert want is not None
+            f, ops, _ = want
+            assert (a.score, a.xstart, a.xend, a.ystart, a.yend) == (f["score"], f["xstart"], f["xend"], f["ystart"], f["yend"]), kw
+            assert [(o.code, o.len) for o in a.operations] == ops, kw
+            n_ok += 1
+        return n_ok
+
+    keep = [i for i, ((x, y), m) in enumerate(zip(pairs, matches))
+            if all(oracle.banded_align_hinted(s_o, k, w, x, y, m, **kw) is not None
+                   for kw in (dict(), dict(allowed_mismatches=1), dict(use_lcskpp_union=True),
+                              dict(allowed_mismatches=2, use_lcskpp_union=True)))]
+    assert len(keep) > 40  # pairs on which the reference itself panics / hangs are left out of the batch
+    pairs = [pairs[i] for i in keep]
+    matches = [matches[i] for i in keep]
+    check(aligner.custom_with_matches_batch(pairs, matches), dict())
+    check(aligner.custom_with_expanded_matches_batch(pairs, matches, 1, False), dict(allowed_mismatches=1))
+    check(aligner.custom_with_expanded_matches_batch(pairs, matches, None, True), dict(use_lcskpp_union=True))
+    check(aligner.custom_with_expanded_matches_batch(pairs, matches, 2, True),
+          dict(allowed_mismatches=2, use_lcskpp_union=True))
+    # a caller-chosen path: the lcskpp chain of each pair
+    sub = [(p, m, oracle.lcskpp(m, k)[0]) for p, m in zip(pairs, matches) if m]
+    sub = [(p, m, pa) for p, m, pa in sub if oracle.banded_align_hinted(s_o, k, w, p[0], p[1], m, path=pa) is not None]
+    got = aligner.custom_with_match_path_batch([p for p, _, _ in sub], [m for _, m, _ in sub], [pa for _, _, pa in sub])
+    for (p, m, pa), a in zip(sub, got):
+        f, ops, _ = oracle.banded_align_hinted(s_o, k, w, p[0], p[1], m, path=pa)
+        assert a.score == f["score"] and [(o.code, o.len) for o in a.operations] == ops
+    # prehash forms are custom / semiglobal
+    x, y = pairs[0]
+    assert aligner.custom_with_prehash(x, y, None).operations == aligner.custom(x, y).operations
+    assert aligner.semiglobal_with_prehash(x, y, None).score == aligner.semiglobal(x, y).score
+
+
+def test_caller_supplied_band_inputs_refusals(eng, oracle):
+    from rust_bio_b200._lib import B2AError
+    from rust_bio_b200.banded import Aligner, find_kmer_matches
+    from rust_bio_b200.pairwise import Scoring
+    aligner = Aligner.with_scoring(Scoring.from_scores(-5, -1, 1, -1), 6, 3, engine=eng)
+    x, y = b"ACGTACGTTGCAACGT", b"TTACGTACGTTGCAACGTAA"
+    m = find_kmer_matches(x, y, 6)
+    with pytest.raises(B2AError, match="reference panics"):
+        aligner.custom_with_matches(x, y, m[::-1])
+    with pytest.raises(B2AError, match="reference panics"):
+        aligner.custom_with_match_path(x, y, m, [0, len(m)])
+    with pytest.raises(B2AError, match="reference panics"):
+        aligner.custom_with_match_path(x, y, m, [])
+    with pytest.raises(B2AError, match="reference panics"):
+        aligner.custom_with_matches(x, y, [(2, 500)])
+    a = aligner.custom_with_matches(x, y, [])  # no matches: the full matrix (banded.rs:1309-1313)
+    s_o, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    f, ops, _ = oracle.banded_align_hinted(s_o, 6, 3, x, y, [])
+    assert a.score == f["score"] and [(o.code, o.len) for o in a.operations] == ops

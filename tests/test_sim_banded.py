@@ -148,3 +148,64 @@ def test_sim_banded_refuses_more_than_max_cells(oracle):
     s, _ = oracle.make_scoring(-5, -1, 1, -1)
     got, ops, _ = sim_util.banded_batch(MODES["semiglobal"], s, 32, 32, *_one(x, y))
     assert int(got["score"][0]) == MIN and ops[0] == [] and int(got["num_cells"][0]) == 501 * 10001
+
+
+def _window_pair(rng, xlen=90, ylen=220, nsub=5):
+    y = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, ylen)])
+    st = int(rng.integers(0, ylen - xlen))
+    x = bytearray(y[st:st + xlen])
+    for p in rng.integers(0, xlen, nsub):
+        x[p] = b"ACGT"[rng.integers(0, 4)]
+    if rng.integers(0, 2):  # one indel
+        q = int(rng.integers(5, xlen - 5))
+        x = x[:q] + x[q + 1:] if rng.integers(0, 2) else x[:q] + b"G" + x[q:]
+    return bytes(x), y
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sim_banded_caller_supplied_band_inputs(oracle, seed):
+    """custom_with_matches / custom_with_expanded_matches / custom_with_match_path (banded.rs:313-401): the host
+    build of K4 (matches, expand_kmer_matches, lcskpp union, given path) + K3 against the oracle."""
+    rng = np.random.default_rng(900 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9]))
+    s, _ = oracle.make_scoring(int(rng.choice([-1, -5])), int(rng.choice([0, -1])), int(rng.choice([1, 2])),
+                               int(rng.choice([-1, -3])), None, pick(), pick(), pick(), pick(),
+                               has_match_scores=int(seed % 2))
+    n_checked = 0
+    for trial in range(10):
+        x, y = _window_pair(rng)
+        k, w = int(rng.choice([5, 6, 8])), int(rng.choice([3, 6]))
+        m = oracle.find_kmer_matches(x, y, k)
+        if len(m) > 3 and trial % 3 == 0:  # the caller may pass any sorted subset
+            m = [mt for i, mt in enumerate(m) if i % 3 != 1]
+        variants = [dict(), dict(allowed_mismatches=0), dict(allowed_mismatches=int(rng.integers(1, 3))),
+                    dict(use_lcskpp_union=True), dict(allowed_mismatches=1, use_lcskpp_union=True)]
+        if m:
+            path, _ = oracle.lcskpp(m, k)
+            variants.append(dict(path=path))
+            variants.append(dict(path=[int(v) for v in sorted(rng.choice(len(m), size=min(3, len(m)), replace=False))]))
+        for kw in variants:
+            want = oracle.banded_align_hinted(s, k, w, x, y, m, **kw)
+            got = sim_util.banded_hinted_one(s, k, w, x, y, m, **kw)
+            if want is None:
+                assert got is None, (seed, trial, kw, "the reference panics but the device code returned a result")
+                continue
+            assert got is not None, (seed, trial, kw)
+            assert got[2] == want[2], (seed, trial, kw, "band cells")
+            assert got[0] == {f: want[0][f] for f in got[0]} and got[1] == want[1], (seed, trial, kw, x, y)
+            n_checked += 1
+    assert n_checked > 30
+
+
+def test_sim_banded_caller_inputs_reference_panics(oracle):
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    x, y = b"ACGTACGTTGCAACGT", b"TTACGTACGTTGCAACGTAA"
+    m = oracle.find_kmer_matches(x, y, 6)
+    assert len(m) >= 3
+    assert sim_util.banded_hinted_one(s, 6, 3, x, y, m[::-1]) is None                       # not ascending
+    assert sim_util.banded_hinted_one(s, 6, 3, x, y, m, path=[0, len(m)]) is None           # index out of range
+    assert sim_util.banded_hinted_one(s, 6, 3, x, y, m, path=[]) is None                    # path[0] on an empty path
+    assert sim_util.banded_hinted_one(s, 6, 3, x, y, [(2, 500)]) is None                    # outside the matrix
+    got = sim_util.banded_hinted_one(s, 6, 3, x, y, [])                                     # no matches: full matrix
+    want = oracle.banded_align_hinted(s, 6, 3, x, y, [])
+    assert got is not None and got[0]["score"] == want[0]["score"] and got[1] == want[1]

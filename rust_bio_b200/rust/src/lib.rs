@@ -88,6 +88,36 @@ pub mod alignment {
                 results: *mut b2a_results,
                 stats: *mut c_void,
             ) -> i32;
+            fn b2a_align_batch_banded_hinted(
+                e: *mut c_void,
+                mode: i32,
+                scoring: *const b2a_scoring,
+                k: u32,
+                w: u32,
+                pairs: *const b2a_pairs,
+                hints: *const b2a_band_hints,
+                results: *mut b2a_results,
+                stats: *mut c_void,
+            ) -> i32;
+        }
+        #[repr(C)]
+        struct b2a_band_hints {
+            match_off: *const u64,
+            match_xy: *const u32,
+            path_off: *const u64,
+            path_idx: *const u32,
+            allowed_mismatches: i32,
+            use_lcskpp_union: i32,
+        }
+
+        /// What a banded call adds to `Aligner::batch`: k, w and (banded.rs:294-401) the caller's band inputs.
+        pub(crate) struct BandedCall<'a> {
+            pub k: u32,
+            pub w: u32,
+            pub matches: Option<&'a [&'a [(u32, u32)]]>,
+            pub paths: Option<&'a [&'a [usize]]>,
+            pub allowed_mismatches: Option<usize>,
+            pub use_lcskpp_union: bool,
         }
 
         // ---------------------------------------------------------------- scoring, mod.rs:177-429
@@ -244,7 +274,7 @@ pub mod alignment {
             }
 
             /// Aligner::custom / global / semiglobal / local over a batch (mode = B2A_MODE_*).
-            fn batch(&mut self, mode: i32, banded: Option<(u32, u32)>, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> {
+            pub(crate) fn batch(&mut self, mode: i32, banded: Option<BandedCall>, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> {
                 let n = pairs.len();
                 // 16-byte aligned slots, x then y per pair
                 let mut x_off = Vec::with_capacity(n);
@@ -316,10 +346,45 @@ pub mod alignment {
                     ops_capacity: cap + 1,
                     clip_len: clip.as_mut_ptr(),
                 };
-                let rc = unsafe {
-                    match banded {
-                        None => b2a_align_batch(self.engine, mode, &cs, &cp, &mut res, std::ptr::null_mut()),
-                        Some((k, w)) => b2a_align_batch_banded(self.engine, mode, &cs, k, w, &cp, &mut res, std::ptr::null_mut()),
+                let rc = match banded {
+                    None => unsafe { b2a_align_batch(self.engine, mode, &cs, &cp, &mut res, std::ptr::null_mut()) },
+                    Some(BandedCall { k, w, matches: None, .. }) => unsafe {
+                        b2a_align_batch_banded(self.engine, mode, &cs, k, w, &cp, &mut res, std::ptr::null_mut())
+                    },
+                    Some(BandedCall { k, w, matches: Some(ms), paths, allowed_mismatches, use_lcskpp_union }) => {
+                        // CSR form of the per-pair matches (and paths), include/b200align.h b2a_band_hints
+                        assert!(ms.len() == n, "one match list per pair");
+                        let mut match_off = vec![0u64; n + 1];
+                        let mut match_xy: Vec<u32> = Vec::new();
+                        for (p, m) in ms.iter().enumerate() {
+                            for &(a, b) in m.iter() {
+                                match_xy.push(a);
+                                match_xy.push(b);
+                            }
+                            match_off[p + 1] = (match_xy.len() / 2) as u64;
+                        }
+                        match_xy.push(0); // never a dangling pointer for an empty list
+                        let mut path_off = vec![0u64; n + 1];
+                        let mut path_idx: Vec<u32> = Vec::new();
+                        if let Some(ps) = paths {
+                            assert!(ps.len() == n, "one path per pair");
+                            for (p, path) in ps.iter().enumerate() {
+                                path_idx.extend(path.iter().map(|&i| i as u32));
+                                path_off[p + 1] = path_idx.len() as u64;
+                            }
+                        }
+                        path_idx.push(0);
+                        let h = b2a_band_hints {
+                            match_off: match_off.as_ptr(),
+                            match_xy: match_xy.as_ptr(),
+                            path_off: if paths.is_some() { path_off.as_ptr() } else { std::ptr::null() },
+                            path_idx: if paths.is_some() { path_idx.as_ptr() } else { std::ptr::null() },
+                            allowed_mismatches: allowed_mismatches.map(|v| v as i32).unwrap_or(-1),
+                            use_lcskpp_union: use_lcskpp_union as i32,
+                        };
+                        unsafe {
+                            b2a_align_batch_banded_hinted(self.engine, mode, &cs, k, w, &cp, &h, &mut res, std::ptr::null_mut())
+                        }
                     }
                 };
                 if rc != 0 {
@@ -380,6 +445,92 @@ pub mod alignment {
             pub fn semiglobal(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.batch(2, None, &[(x, y)]).remove(0) }
             /// mod.rs:986
             pub fn local(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.batch(3, None, &[(x, y)]).remove(0) }
+        }
+
+        // ------------------------------------------------------------ banded::Aligner, banded.rs:122-1004
+        pub mod banded {
+            use super::{Alignment, BandedCall, MatchFunc, Scoring};
+
+            /// Same constructors and methods as `bio::alignment::pairwise::banded::Aligner` (k = k-mer length,
+            /// w = band half-width, banded.rs:150-267); every method is a batch of one, `*_batch` is the GPU form.
+            pub struct Aligner<F: MatchFunc> {
+                inner: super::Aligner<F>,
+                k: usize,
+                w: usize,
+            }
+
+            impl<F: MatchFunc> Aligner<F> {
+                pub fn new(gap_open: i32, gap_extend: i32, match_fn: F, k: usize, w: usize) -> Self {
+                    Aligner { inner: super::Aligner::new(gap_open, gap_extend, match_fn), k, w }
+                }
+                pub fn with_capacity(m: usize, n: usize, gap_open: i32, gap_extend: i32, match_fn: F, k: usize, w: usize) -> Self {
+                    Aligner { inner: super::Aligner::with_capacity(m, n, gap_open, gap_extend, match_fn), k, w }
+                }
+                pub fn with_scoring(scoring: Scoring<F>, k: usize, w: usize) -> Self {
+                    Aligner { inner: super::Aligner::with_scoring(scoring), k, w }
+                }
+                pub fn with_capacity_and_scoring(m: usize, n: usize, scoring: Scoring<F>, k: usize, w: usize) -> Self {
+                    Aligner { inner: super::Aligner::with_capacity_and_scoring(m, n, scoring), k, w }
+                }
+                pub fn get_mut_scoring(&mut self) -> &mut Scoring<F> {
+                    &mut self.inner.scoring
+                }
+                fn call<'a>(&self) -> BandedCall<'a> {
+                    BandedCall { k: self.k as u32, w: self.w as u32, matches: None, paths: None, allowed_mismatches: None, use_lcskpp_union: false }
+                }
+
+                pub fn custom_batch(&mut self, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> { let c = self.call(); self.inner.batch(0, Some(c), pairs) }
+                pub fn global_batch(&mut self, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> { let c = self.call(); self.inner.batch(1, Some(c), pairs) }
+                pub fn semiglobal_batch(&mut self, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> { let c = self.call(); self.inner.batch(2, Some(c), pairs) }
+                pub fn local_batch(&mut self, pairs: &[(&[u8], &[u8])]) -> Vec<Alignment> { let c = self.call(); self.inner.batch(3, Some(c), pairs) }
+                /// banded.rs:282
+                pub fn custom(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.custom_batch(&[(x, y)]).remove(0) }
+                /// banded.rs:872
+                pub fn global(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.global_batch(&[(x, y)]).remove(0) }
+                /// banded.rs:901
+                pub fn semiglobal(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.semiglobal_batch(&[(x, y)]).remove(0) }
+                /// banded.rs:975
+                pub fn local(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.local_batch(&[(x, y)]).remove(0) }
+
+                /// banded.rs:294 / 938: the prehash of y only spares the reference its own hashing; the matches
+                /// (find_kmer_matches_seq2_hashed) and therefore the results are those of custom / semiglobal.
+                pub fn custom_with_prehash<H>(&mut self, x: &[u8], y: &[u8], _y_kmer_hash: &H) -> Alignment { self.custom(x, y) }
+                pub fn semiglobal_with_prehash<H>(&mut self, x: &[u8], y: &[u8], _y_kmer_hash: &H) -> Alignment { self.semiglobal(x, y) }
+
+                /// banded.rs:313
+                pub fn custom_with_matches(&mut self, x: &[u8], y: &[u8], matches: &[(u32, u32)]) -> Alignment {
+                    self.custom_with_matches_batch(&[(x, y)], &[matches]).remove(0)
+                }
+                pub fn custom_with_matches_batch(&mut self, pairs: &[(&[u8], &[u8])], matches: &[&[(u32, u32)]]) -> Vec<Alignment> {
+                    let mut c = self.call();
+                    c.matches = Some(matches);
+                    self.inner.batch(0, Some(c), pairs)
+                }
+                /// banded.rs:338
+                pub fn custom_with_expanded_matches(&mut self, x: &[u8], y: &[u8], matches: Vec<(u32, u32)>,
+                                                    allowed_mismatches: Option<usize>, use_lcskpp_union: bool) -> Alignment {
+                    self.custom_with_expanded_matches_batch(&[(x, y)], &[&matches[..]], allowed_mismatches, use_lcskpp_union).remove(0)
+                }
+                pub fn custom_with_expanded_matches_batch(&mut self, pairs: &[(&[u8], &[u8])], matches: &[&[(u32, u32)]],
+                                                          allowed_mismatches: Option<usize>, use_lcskpp_union: bool) -> Vec<Alignment> {
+                    let mut c = self.call();
+                    c.matches = Some(matches);
+                    c.allowed_mismatches = allowed_mismatches;
+                    c.use_lcskpp_union = use_lcskpp_union;
+                    self.inner.batch(0, Some(c), pairs)
+                }
+                /// banded.rs:391
+                pub fn custom_with_match_path(&mut self, x: &[u8], y: &[u8], matches: &[(u32, u32)], path: &[usize]) -> Alignment {
+                    self.custom_with_match_path_batch(&[(x, y)], &[matches], &[path]).remove(0)
+                }
+                pub fn custom_with_match_path_batch(&mut self, pairs: &[(&[u8], &[u8])], matches: &[&[(u32, u32)]],
+                                                    paths: &[&[usize]]) -> Vec<Alignment> {
+                    let mut c = self.call();
+                    c.matches = Some(matches);
+                    c.paths = Some(paths);
+                    self.inner.batch(0, Some(c), pairs)
+                }
+            }
         }
     }
 }

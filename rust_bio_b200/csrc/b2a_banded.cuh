@@ -1,4 +1,4 @@
-// K4 + K3: banded::Aligner on the device (K4: one lane per pair, K3: one warp per pair).
+// K4 + K3: banded::Aligner on the device, one warp per pair in both kernels.
 //
 // Reference rust-bio 4.0.1:
 //   sparse::find_kmer_matches          src/alignment/sparse.rs:337-402
@@ -141,18 +141,117 @@ B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
   return (b + 255) & ~255ull;
 }
 
+// Cooperative-lane helpers: W = 32 lanes of one warp on the device, W = 1 in the host logic build.
+template <int W>
+struct Coop {
+  static B2A_HD void sync() {
+#if defined(__CUDA_ARCH__)
+    if (W > 1) __syncwarp();
+#endif
+  }
+  static B2A_HD int32_t up(int32_t v, int d) {  // the value held by lane - d
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __shfl_up_sync(0xffffffffu, v, d);
+#endif
+    (void)d;
+    return v;
+  }
+  static B2A_HD int32_t from(int32_t v, int src) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __shfl_sync(0xffffffffu, v, src);
+#endif
+    (void)src;
+    return v;
+  }
+  static B2A_HD uint32_t ballot(bool b) {  // bit l = lane l's predicate
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __ballot_sync(0xffffffffu, b);
+#endif
+    return b ? 1u : 0u;
+  }
+  static B2A_HD unsigned long long all_sum(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1)
+      for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+#endif
+    return v;
+  }
+  // claim an empty (zero) 64-bit slot: returns true if `val` was stored
+  static B2A_HD bool claim(uint64_t* slot, uint64_t val) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1)
+      return atomicCAS(reinterpret_cast<unsigned long long*>(slot), 0ull, (unsigned long long)val) == 0ull;
+#endif
+    if (*slot != 0) return false;
+    *slot = val;
+    return true;
+  }
+  static B2A_HD uint32_t fetch_add(uint32_t* ctr, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return atomicAdd(ctr, v);
+#endif
+    const uint32_t old = *ctr;
+    *ctr = old + v;
+    return old;
+  }
+  static B2A_HD long long all_max(long long v) {
+#if defined(__CUDA_ARCH__)
+    if (W > 1)
+      for (int d = 16; d; d >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, v, d);
+        v = t > v ? t : v;
+      }
+#endif
+    return v;
+  }
+};
+
+// ------------------------------------------------------------------ cooperative sort of 64-bit keys
+// Bitonic network in its all-ascending form (first step of a merge compares i with its mirror i ^ (k-1), the
+// rest with i ^ j): every compare-exchange leaves the smaller key at the lower index, so the virtual +inf
+// padding up to the next power of two never moves and pairs that reach past n are simply skipped.
+template <int W>
+B2A_HD void coop_sort_u64(int lane, uint64_t* a, uint64_t n) {
+  using C = Coop<W>;
+  if (n < 2) return;
+  auto step = [&](uint64_t mask) {
+    for (uint64_t i = (uint64_t)lane; i < n; i += W) {
+      const uint64_t j = i ^ mask;
+      if (j > i && j < n) {
+        const uint64_t u = a[i], v = a[j];
+        if (u > v) {
+          a[i] = v;
+          a[j] = u;
+        }
+      }
+    }
+    C::sync();
+  };
+  for (uint64_t k = 2; (k >> 1) < n; k <<= 1) {
+    step(k - 1);
+    for (uint64_t j = k >> 2; j > 0; j >>= 1) step(j);
+  }
+}
+
 // ------------------------------------------------------------------ Band (ranges as u32 pairs)
+// W cooperating lanes: every loop over columns is strided over the lanes.  lo() is a minimum and hi() a maximum,
+// so the order in which the reference's add_kmer/add_entry/add_gap calls touch a column does not matter; a
+// sync after each loop keeps two lanes from updating one column at the same time.
+template <int W>
 struct BandD {
+  using C = Coop<W>;
   uint32_t* r;  // r[2j] = start, r[2j+1] = end
   uint64_t rows, cols;
+  int lane = 0;
   bool oob = false;  // a column index past the matrix: the reference panics on ranges[j] (caller-supplied matches)
   B2A_HD void init(uint64_t m, uint64_t n) {  // Band::new, banded.rs:1061-1067
     rows = m + 1;
     cols = n + 1;
-    for (uint64_t j = 0; j < cols; ++j) {
+    for (uint64_t j = (uint64_t)lane; j < cols; j += W) {
       r[2 * j] = (uint32_t)(m + 1);
       r[2 * j + 1] = 0;
     }
+    C::sync();
   }
   B2A_HD void lo(uint64_t j, uint64_t v) {
     if (j >= cols) {
@@ -172,36 +271,31 @@ struct BandD {
     if (k == 0) return;
     {
       const uint64_t i = sat_sub64(r0, w);
-      for (uint64_t j = sat_sub64(c0, w); j < umin64(c0 + w + 1, cols); ++j) lo(j, i);
+      for (uint64_t j = sat_sub64(c0, w) + (uint64_t)lane; j < umin64(c0 + w + 1, cols); j += W) lo(j, i);
     }
     {
-      uint64_t i = sat_sub64(r0, w);
-      for (uint64_t j = umin64(c0 + w, cols); j < umin64(c0 + k + w, cols); ++j) {
-        lo(j, i);
-        i += 1;
-      }
+      const uint64_t i0 = sat_sub64(r0, w), j0 = umin64(c0 + w, cols);
+      for (uint64_t j = j0 + (uint64_t)lane; j < umin64(c0 + k + w, cols); j += W) lo(j, i0 + (j - j0));
     }
+    C::sync();
     {
-      uint64_t i = r0 + w + k;
-      uint64_t j = sat_sub64(c0 + k - 1, w);
-      for (;;) {
-        if (j <= sat_sub64(c0, w)) break;
-        j -= 1;
-        i -= 1;
-        hi(j, umin64(i, rows));
-      }
+      // the reference walks j down from J0 = sat_sub(c0+k-1, w) to sat_sub(c0, w), i down from r0+w+k beside it
+      const uint64_t i0 = r0 + w + k, J0 = sat_sub64(c0 + k - 1, w), jb = sat_sub64(c0, w);
+      for (uint64_t j = jb + (uint64_t)lane; j < J0; j += W) hi(j, umin64(i0 - (J0 - j), rows));
     }
     {
       const uint64_t i = umin64(r0 + w + k, rows);
-      for (uint64_t j = sat_sub64(c0 + k - 1, w); j < umin64(c0 + k + w, cols); ++j) hi(j, i);
+      for (uint64_t j = sat_sub64(c0 + k - 1, w) + (uint64_t)lane; j < umin64(c0 + k + w, cols); j += W) hi(j, i);
     }
+    C::sync();
   }
   B2A_HD void add_entry(uint64_t r0, uint64_t c0, uint64_t w) {  // banded.rs:1111-1120
     const uint64_t istart = sat_sub64(r0, w), iend = umin64(r0 + w + 1, rows);
-    for (uint64_t j = sat_sub64(c0, w); j < umin64(c0 + w + 1, cols); ++j) {
+    for (uint64_t j = sat_sub64(c0, w) + (uint64_t)lane; j < umin64(c0 + w + 1, cols); j += W) {
       lo(j, istart);
       hi(j, iend);
     }
+    C::sync();
   }
   // banded.rs:1123-1137, u32 arithmetic.  Returns false where the reference would divide by zero.
   B2A_HD bool add_gap(uint32_t s0, uint32_t s1, uint32_t e0, uint32_t e1, uint64_t w) {
@@ -284,70 +378,94 @@ struct BandD {
     return ok;
   }
   B2A_HD void full_matrix() {  // banded.rs:1369-1372
-    for (uint64_t j = 0; j < cols; ++j) {
+    for (uint64_t j = (uint64_t)lane; j < cols; j += W) {
       r[2 * j] = 0;
       r[2 * j + 1] = (uint32_t)rows;
     }
+    C::sync();
   }
   B2A_HD uint64_t num_cells() const {  // banded.rs:1374-1380
-    uint64_t cells = 0;
-    for (uint64_t j = 0; j < cols; ++j) cells += sat_sub64(r[2 * j + 1], r[2 * j]);
-    return cells;
+    unsigned long long cells = 0;
+    for (uint64_t j = (uint64_t)lane; j < cols; j += W) cells += sat_sub64(r[2 * j + 1], r[2 * j]);
+    return C::all_sum(cells);
   }
+  B2A_HD bool any_oob() const { return C::ballot(oob) != 0u; }
 };
 
 // ------------------------------------------------------------------ k-mer matches (exact)
 constexpr uint64_t HASH_B = 0x9E3779B97F4A7C15ull | 1ull;
 
-// all (i, j) with x[i..i+k] == y[j..j+k] as (i << 32 | j), sorted; returns count or ~0 on overflow
-B2A_HD uint64_t find_kmer_matches_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint64_t k,
-                                    uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap) {
+// all (i, j) with x[i..i+k] == y[j..j+k] as (i << 32 | j), sorted; returns count or ~0 on overflow.
+// Each lane hashes / probes a contiguous run of positions with its own rolling hash; table slots are claimed
+// with a compare-and-swap and matches appended through a counter, in any order: the table layout and the
+// append order do not matter, the result is the sorted set.
+template <int W>
+B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint64_t k,
+                                    uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap, uint32_t* counter) {
+  using C = Coop<W>;
   const uint64_t nx = sat_sub64(m + 1, k), ny = sat_sub64(n + 1, k);
   if (nx == 0 || ny == 0 || k == 0) return 0;
   const bool hash_x = m <= n;  // hash the shorter one
   const uint8_t* hs = hash_x ? x : y;
   const uint8_t* ps = hash_x ? y : x;
   const uint64_t nh = hash_x ? nx : ny, np = hash_x ? ny : nx;
-  for (uint32_t s = 0; s < H; ++s) table[s] = 0;
+  for (uint32_t s = (uint32_t)lane; s < H; s += W) table[s] = 0;
+  if (lane == 0) *counter = 0;
+  C::sync();
   uint64_t bk = 1;  // B^(k-1)
   for (uint64_t t = 1; t < k; ++t) bk *= HASH_B;
   auto mix = [](uint64_t h) { return h ^ (h >> 29); };
-  uint64_t h = 0;
-  for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(hs[t] + 1);
   const uint32_t mask = H - 1;
-  for (uint64_t i = 0; i < nh; ++i) {
-    const uint64_t hm = mix(h);
-    uint32_t slot = (uint32_t)hm & mask;
-    while (table[slot] != 0) slot = (slot + 1) & mask;
-    table[slot] = ((hm >> 32) << 32) | (i + 1);
-    if (i + 1 < nh) h = (h - (uint64_t)(hs[i] + 1) * bk) * HASH_B + (uint64_t)(hs[i + k] + 1);
-  }
-  uint64_t cnt = 0;
-  h = 0;
-  for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(ps[t] + 1);
-  for (uint64_t j = 0; j < np; ++j) {
-    const uint64_t hm = mix(h);
-    uint32_t slot = (uint32_t)hm & mask;
-    while (table[slot] != 0) {
-      const uint64_t e = table[slot];
-      if ((e >> 32) == (hm >> 32)) {
-        const uint64_t i = (e & 0xffffffffull) - 1;
-        bool same = true;
-        for (uint64_t t = 0; t < k; ++t)
-          if (hs[i + t] != ps[j + t]) {
-            same = false;
-            break;
-          }
-        if (same) {
-          if (cnt >= cap) return ~0ull;
-          out[cnt++] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
-        }
+  {
+    const uint64_t seg = (nh + W - 1) / W, lo = umin64(nh, seg * (uint64_t)lane), hi = umin64(nh, lo + seg);
+    if (lo < hi) {
+      uint64_t h = 0;
+      for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(hs[lo + t] + 1);
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t hm = mix(h);
+        uint32_t slot = (uint32_t)hm & mask;
+        const uint64_t entry = ((hm >> 32) << 32) | (i + 1);
+        while (!C::claim(&table[slot], entry)) slot = (slot + 1) & mask;
+        if (i + 1 < hi) h = (h - (uint64_t)(hs[i] + 1) * bk) * HASH_B + (uint64_t)(hs[i + k] + 1);
       }
-      slot = (slot + 1) & mask;
     }
-    if (j + 1 < np) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
   }
-  heap_sort_u64(out, cnt);
+  C::sync();
+  {
+    const uint64_t seg = (np + W - 1) / W, lo = umin64(np, seg * (uint64_t)lane), hi = umin64(np, lo + seg);
+    if (lo < hi) {
+      uint64_t h = 0;
+      for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(ps[lo + t] + 1);
+      for (uint64_t j = lo; j < hi; ++j) {
+        const uint64_t hm = mix(h);
+        uint32_t slot = (uint32_t)hm & mask;
+        for (;;) {
+          const uint64_t e = table[slot];
+          if (e == 0) break;
+          if ((e >> 32) == (hm >> 32)) {
+            const uint64_t i = (e & 0xffffffffull) - 1;
+            bool same = true;
+            for (uint64_t t = 0; t < k; ++t)
+              if (hs[i + t] != ps[j + t]) {
+                same = false;
+                break;
+              }
+            if (same) {
+              const uint32_t at = C::fetch_add(counter, 1u);
+              if (at < cap) out[at] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
+            }
+          }
+          slot = (slot + 1) & mask;
+        }
+        if (j + 1 < hi) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
+      }
+    }
+  }
+  C::sync();
+  const uint64_t cnt = *counter;
+  C::sync();
+  if (cnt > cap) return ~0ull;
+  coop_sort_u64<W>(lane, out, cnt);
   return cnt;
 }
 
@@ -366,9 +484,14 @@ B2A_HD uint32_t lower_bound_u32(const uint32_t* a, uint32_t n, uint32_t v) {  //
 // returns path length (path[] = indices into matches), 0 if no matches
 // lcs = true runs sparse::lcskpp (sparse.rs:67-143) on the same machinery: unit scores, no gap term, and a
 // prefix-max tree over (score, id) tuples -- PrevPtrD{0, score, 0, id, 0, 0} compares exactly like that tuple.
-B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint32_t match_score, int32_t gap_open,
-                         int32_t gap_extend, uint64_t* ev /*4*nm u64*/, uint32_t* dp_score, int32_t* dp_prev,
-                         PrevPtrD* fen, uint32_t* ycoord, uint32_t* path, bool lcs = false) {
+// The sorts and the array set-up are spread over the W lanes; the event loop itself (each event reads what the
+// previous ones wrote into the tree) is sequential work of lane 0.  Every lane returns the path length.
+template <int W>
+B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_t k, uint32_t match_score,
+                         int32_t gap_open, int32_t gap_extend, uint64_t* ev /*4*nm u64*/, uint32_t* dp_score,
+                         int32_t* dp_prev, PrevPtrD* fen, uint32_t* ycoord, uint32_t* path, uint32_t* shared_u32,
+                         bool lcs = false) {
+  using C = Coop<W>;
   if (nm == 0) return 0;
   if (lcs) match_score = 1;
   const uint32_t go = (uint32_t)(-gap_open), ge = (uint32_t)(-gap_extend);
@@ -380,26 +503,31 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
   //   unique per match and (x, y) is unique per match for starts and for ends, so (x, y, kind) is a
   //   total order: key = (x << 33) | (y << 1) | kind needs 65 bits when x,y use 32 -> lengths are
   //   limited to 2^24 by the engine, so x,y < 2^25 and the key fits.
-  for (uint32_t idx = 0; idx < nm; ++idx) {
+  uint64_t* tmp = ev + 2ull * nm;  // scratch half
+  for (uint32_t idx = (uint32_t)lane; idx < nm; idx += W) {
     const uint64_t x = matches[idx] >> 32, y = matches[idx] & 0xffffffffull;
     ev[2 * idx] = (x << 33) | (y << 1) | 1ull;              // start (id = idx + nm)
     ev[2 * idx + 1] = ((x + k) << 33) | ((y + k) << 1);     // end   (id = idx)
+    tmp[idx] = y + k;
+    dp_score[idx] = 0;
+    dp_prev[idx] = 0;
   }
-  heap_sort_u64(ev, 2ull * nm);
+  C::sync();
+  coop_sort_u64<W>(lane, ev, 2ull * nm);
+  coop_sort_u64<W>(lane, tmp, nm);
   // distinct end-y coordinates, ascending (the only indices ever set in the prefix-max tree)
   uint32_t ny = 0;
-  {
-    uint64_t* tmp = ev + 2ull * nm;  // scratch half
-    for (uint32_t idx = 0; idx < nm; ++idx) tmp[idx] = (matches[idx] & 0xffffffffull) + k;
-    heap_sort_u64(tmp, nm);
+  if (lane == 0) {
     for (uint32_t t = 0; t < nm; ++t)
       if (ny == 0 || ycoord[ny - 1] != (uint32_t)tmp[t]) ycoord[ny++] = (uint32_t)tmp[t];
+    shared_u32[0] = ny;
   }
-  for (uint32_t t = 0; t <= ny + 1; ++t) fen[t] = PrevPtrD{0, 0, 0, 0, 0, 0};
-  for (uint32_t t = 0; t < nm; ++t) {
-    dp_score[t] = 0;
-    dp_prev[t] = 0;
-  }
+  C::sync();
+  ny = shared_u32[0];
+  for (uint32_t t = (uint32_t)lane; t <= ny + 1; t += W) fen[t] = PrevPtrD{0, 0, 0, 0, 0, 0};
+  C::sync();
+  uint32_t np = 0;
+  if (lane == 0) {
   uint32_t best_score = k;
   int32_t best_idx = 0;
   auto dp_gt = [](uint32_t s1, int32_t p1, uint32_t s2, int32_t p2) {  // (s1,p1) > (s2,p2)
@@ -486,7 +614,6 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
       }
     }
   }
-  uint32_t np = 0;
   int32_t pm = best_idx;
   while (pm >= 0 && np < nm) {
     path[np++] = (uint32_t)pm;
@@ -497,6 +624,11 @@ B2A_HD uint32_t sdpkpp_d(const uint64_t* matches, uint32_t nm, uint32_t k, uint3
     path[a] = path[b];
     path[b] = t;
   }
+  shared_u32[0] = np;
+  }
+  C::sync();
+  np = shared_u32[0];
+  C::sync();  // shared_u32 may be reused by the caller
   return np;
 }
 
@@ -589,11 +721,16 @@ struct BandHintsD {
   int32_t use_lcskpp_union = 0;
 };
 
+// W cooperating lanes build one pair's band (W = 32: one warp; W = 1: the host logic build).  `shared_u32` is
+// two words all lanes can read and write (shared memory on the device).
 // returns status: 0 ok, 1 too many matches (capacity), 2 reference would panic (divide by zero),
 // 3 reference would panic on the caller's matches/path (not sorted, index out of range, outside the matrix)
-B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint32_t k, uint32_t w,
-                              const DevScoring& sc, int32_t has_match_scores, uint8_t* slab, uint32_t cap,
-                              uint32_t* ranges, uint64_t* cells_out, const BandHintsD& hint = BandHintsD{}) {
+template <int W>
+B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint32_t k,
+                              uint32_t w, const DevScoring& sc, int32_t has_match_scores, uint8_t* slab,
+                              uint32_t cap, uint32_t* ranges, uint64_t* cells_out, uint32_t* shared_u32,
+                              const BandHintsD& hint = BandHintsD{}) {
+  using C = Coop<W>;
   const uint64_t short_len = m <= n ? m : n;
   uint32_t H = 16;
   while (H < 2 * (short_len + 1)) H <<= 1;
@@ -606,31 +743,41 @@ B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, ui
   uint32_t* ycoord = reinterpret_cast<uint32_t*>(fen + cap + 2);
   uint32_t* path = ycoord + cap;          // 2 * cap entries
   uint32_t* path2 = path + 2ull * cap;    // cap entries (lcskpp path)
-  BandD band;
+  BandD<W> band;
   band.r = ranges;
+  band.lane = lane;
   band.init(m, n);
   *cells_out = 0;
   uint64_t nm64;
   if (hint.mxy) {
     if (hint.n_matches > cap) return 1;
-    for (uint64_t i = 0; i < hint.n_matches; ++i)
+    for (uint64_t i = (uint64_t)lane; i < hint.n_matches; i += W)
       matches[i] = ((uint64_t)hint.mxy[2 * i] << 32) | (uint64_t)hint.mxy[2 * i + 1];
     nm64 = hint.n_matches;
+    C::sync();
   } else {
-    nm64 = find_kmer_matches_d(x, m, y, n, k, table, H, matches, cap);
+    nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32);
     if (nm64 == ~0ull) return 1;
   }
   // sdpkpp, lcskpp and expand_kmer_matches assert strictly ascending matches (sparse.rs:77-82, 213-218, 411-416)
   auto sorted = [&](uint64_t cnt) {
-    for (uint64_t i = 1; i < cnt; ++i)
-      if (!(matches[i - 1] < matches[i])) return false;
-    return true;
+    bool ok = true;
+    for (uint64_t i = 1 + (uint64_t)lane; i < cnt; i += W)
+      if (!(matches[i - 1] < matches[i])) ok = false;
+    return C::ballot(!ok) == 0u;
   };
   if (hint.allowed_mismatches >= 0) {  // custom_with_expanded_matches, banded.rs:346-349
     if (!sorted(nm64)) return 3;
-    nm64 = expand_kmer_matches_d(x, m, y, n, k, matches, nm64, cap, (uint64_t)hint.allowed_mismatches, ev);
-    if (nm64 == ~0ull) return 1;
-    if (nm64 == ~1ull) return 3;
+    if (lane == 0) {  // a rare entry point: sequential
+      const uint64_t got = expand_kmer_matches_d(x, m, y, n, k, matches, nm64, cap, (uint64_t)hint.allowed_mismatches, ev);
+      shared_u32[0] = got >= ~1ull ? (got == ~0ull ? 0xFFFFFFFFu : 0xFFFFFFFEu) : (uint32_t)got;
+    }
+    C::sync();
+    const uint32_t got = shared_u32[0];
+    C::sync();
+    if (got == 0xFFFFFFFFu) return 1;
+    if (got == 0xFFFFFFFEu) return 3;
+    nm64 = got;
   }
   const uint32_t nm = (uint32_t)nm64;
   uint32_t status = 0;
@@ -640,34 +787,44 @@ B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, ui
     uint32_t np;
     if (hint.have_path) {  // custom_with_match_path: the path is used as given (391-401)
       if (hint.n_path == 0 || hint.n_path > 2ull * cap) return hint.n_path == 0 ? 3 : 1;
-      for (uint64_t t = 0; t < hint.n_path; ++t) {
-        if (hint.pidx[t] >= nm) return 3;
-        path[t] = hint.pidx[t];
+      bool bad = false;
+      for (uint64_t t = (uint64_t)lane; t < hint.n_path; t += W) {
+        if (hint.pidx[t] >= nm) bad = true;
+        else path[t] = hint.pidx[t];
       }
+      if (C::ballot(bad) != 0u) return 3;
       np = (uint32_t)hint.n_path;
+      C::sync();
     } else {
       if (!sorted(nm)) return 3;
       const int32_t ms = has_match_scores ? sc.match_score : BANDED_DEFAULT_MATCH_SCORE;  // 1315-1318
       if (hint.use_lcskpp_union) {  // sparse::sdpkpp_union_lcskpp_path, sparse.rs:297-330
-        const uint32_t nl = sdpkpp_d(matches, nm, k, 1u, 0, 0, ev, dp_score, dp_prev, fen, ycoord, path2, true);
+        const uint32_t nl = sdpkpp_d<W>(lane, matches, nm, k, 1u, 0, 0, ev, dp_score, dp_prev, fen, ycoord, path2,
+                                        shared_u32, true);
         uint32_t* sp = path + cap;  // the sdpkpp path, parked in the upper half while the union is assembled
-        const uint32_t ns = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score,
-                                     dp_prev, fen, ycoord, sp);
-        auto bsearch = [&](uint32_t v, bool& found) -> uint32_t {
-          const uint32_t q = lower_bound_u32(path2, nl, v);
-          found = q < nl && path2[q] == v;
-          return q;
-        };
-        bool f0 = false, f1 = false;
-        const uint32_t i0 = bsearch(sp[0], f0), i1 = bsearch(sp[ns - 1], f1);
-        const uint32_t pre = f0 ? i0 : 0u, post = f1 ? i1 + 1 : nl;
-        np = 0;
-        for (uint32_t t = 0; t < pre; ++t) path[np++] = path2[t];
-        for (uint32_t t = 0; t < ns; ++t) path[np++] = sp[t];  // np <= pre + t < cap + t: never overtakes sp
-        for (uint32_t t = post; t < nl; ++t) path[np++] = path2[t];
+        const uint32_t ns = sdpkpp_d<W>(lane, matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score,
+                                        dp_prev, fen, ycoord, sp, shared_u32);
+        if (lane == 0) {
+          auto bsearch = [&](uint32_t v, bool& found) -> uint32_t {
+            const uint32_t q = lower_bound_u32(path2, nl, v);
+            found = q < nl && path2[q] == v;
+            return q;
+          };
+          bool f0 = false, f1 = false;
+          const uint32_t i0 = bsearch(sp[0], f0), i1 = bsearch(sp[ns - 1], f1);
+          const uint32_t pre = f0 ? i0 : 0u, post = f1 ? i1 + 1 : nl;
+          uint32_t q = 0;
+          for (uint32_t t = 0; t < pre; ++t) path[q++] = path2[t];
+          for (uint32_t t = 0; t < ns; ++t) path[q++] = sp[t];  // q <= pre + t < cap + t: never overtakes sp
+          for (uint32_t t = post; t < nl; ++t) path[q++] = path2[t];
+          shared_u32[0] = q;
+        }
+        C::sync();
+        np = shared_u32[0];
+        C::sync();
       } else {
-        np = sdpkpp_d(matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score, dp_prev, fen, ycoord,
-                      path);
+        np = sdpkpp_d<W>(lane, matches, nm, k, (uint32_t)ms, sc.gap_open, sc.gap_extend, ev, dp_score, dp_prev, fen,
+                         ycoord, path, shared_u32);
       }
     }
     // create_from_match_path, banded.rs:1330-1367
@@ -691,7 +848,7 @@ B2A_HD uint32_t band_create_d(const uint8_t* x, uint64_t m, const uint8_t* y, ui
       has_prev = true;
     }
   }
-  if (band.oob) return 3;
+  if (band.any_oob()) return 3;
   *cells_out = band.num_cells();
   return status;
 }
@@ -727,46 +884,6 @@ struct BandedOut {
   int32_t score;
   uint32_t xstart, xend, ystart, yend, xlen, ylen, n_ops, status;
   uint32_t clip[4];
-};
-
-// Cooperative-lane helpers: W = 32 lanes of one warp on the device, W = 1 in the host logic build.
-template <int W>
-struct Coop {
-  static B2A_HD void sync() {
-#if defined(__CUDA_ARCH__)
-    if (W > 1) __syncwarp();
-#endif
-  }
-  static B2A_HD int32_t up(int32_t v, int d) {  // the value held by lane - d
-#if defined(__CUDA_ARCH__)
-    if (W > 1) return __shfl_up_sync(0xffffffffu, v, d);
-#endif
-    (void)d;
-    return v;
-  }
-  static B2A_HD int32_t from(int32_t v, int src) {
-#if defined(__CUDA_ARCH__)
-    if (W > 1) return __shfl_sync(0xffffffffu, v, src);
-#endif
-    (void)src;
-    return v;
-  }
-  static B2A_HD uint32_t ballot(bool b) {  // bit l = lane l's predicate
-#if defined(__CUDA_ARCH__)
-    if (W > 1) return __ballot_sync(0xffffffffu, b);
-#endif
-    return b ? 1u : 0u;
-  }
-  static B2A_HD long long all_max(long long v) {
-#if defined(__CUDA_ARCH__)
-    if (W > 1)
-      for (int d = 16; d; d >>= 1) {
-        const long long t = __shfl_xor_sync(0xffffffffu, v, d);
-        v = t > v ? t : v;
-      }
-#endif
-    return v;
-  }
 };
 
 // compute_alignment for one pair by W cooperating lanes (banded.rs:406-869).
@@ -1441,8 +1558,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
 
 #if defined(__CUDACC__)
 
+// K4: one warp per pair
 __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint32_t n_wave) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t shared_u32[4][2];
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)(threadIdx.x & 31u);
   if (t >= n_wave) return;
   const uint64_t p = (uint64_t)prm.pair_lo + t;
   const uint64_t m = prm.x_len[p], n = prm.y_len[p];
@@ -1459,9 +1579,11 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   }
   hint.allowed_mismatches = prm.allowed_mismatches;
   hint.use_lcskpp_union = prm.use_lcskpp_union;
-  const uint32_t st = band_create_d(prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.k, prm.w, prm.sc,
-                                    prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride, prm.cap_matches,
-                                    prm.ranges + prm.ranges_off[t] / 4, &cells, hint);
+  const uint32_t st = band_create_d<32>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.k, prm.w,
+                                        prm.sc, prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride,
+                                        prm.cap_matches, prm.ranges + prm.ranges_off[t] / 4, &cells,
+                                        shared_u32[threadIdx.x >> 5], hint);
+  if (lane != 0) return;
   prm.num_cells[p] = cells;
   prm.k4_status[p] = st;
 }

@@ -1086,7 +1086,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     bp.ranges = e->d_branges.as<uint32_t>();
     bp.ranges_off = e->d_broff.as<uint64_t>();
     CK(cudaEventRecord(ev0, st));
-    band_kernel<<<(nw + 127) / 128, 128, 0, st>>>(bp, nw);
+    band_kernel<<<(nw + 3) / 4, 128, 0, st>>>(bp, nw);  // one warp per pair
     CK(cudaGetLastError());
     ++e->launches;
     CK(cudaEventRecord(ev1, st));

@@ -261,8 +261,9 @@ extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint
     std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
     std::vector<uint32_t> rng(2 * (n + 1), 0xCDCDCDCDu);
     uint64_t cells = 0;
-    const uint32_t st = band_create_d(x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
-                                      rng.data(), &cells);
+    uint32_t shared_u32[2] = {0, 0};
+    const uint32_t st = band_create_d<1>(0, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
+                                         rng.data(), &cells, shared_u32);
     num_cells[p] = cells;
     if (ranges_out) {
       for (uint64_t j = 0; j <= n; ++j) {
@@ -326,8 +327,9 @@ extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t 
   hint.allowed_mismatches = allowed_mismatches;
   hint.use_lcskpp_union = use_lcskpp_union;
   uint64_t cells = 0;
-  const uint32_t st = band_create_d(x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches, rng.data(),
-                                    &cells, hint);
+  uint32_t shared_u32[2] = {0, 0};
+  const uint32_t st = band_create_d<1>(0, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
+                                       rng.data(), &cells, shared_u32, hint);
   *num_cells = cells;
   BandedOut o{};
   std::vector<uint8_t> opsbuf(m + n + 16, 0);

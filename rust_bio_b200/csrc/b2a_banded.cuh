@@ -1140,6 +1140,8 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     int32_t trk_val = MIN_SCORE;  // the column tracker S[m] (banded.rs:645-649), rows < m
     uint64_t trk_i = 0;
     bool trk_hit = false;
+    int32_t lane_trk_val = MIN_SCORE;  // this lane's best S + xs so far (updates only above MIN_SCORE matter)
+    uint32_t lane_trk_i = 0;
     if (lo < hi) {
       cS = S[lo - 1];
       cI = I[lo - 1];
@@ -1250,17 +1252,10 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           if (last) coln[i] = (uint16_t)cell;
           else cells[cs + (i - i_start)] = (uint16_t)cell;
         }
-        {  // column tracker: first row with the highest S + xs
-          long long key = act ? (long long)((unsigned long long)(long long)(best + xs) << 32) +
-                                    (long long)(0xFFFFFFFFu - (uint32_t)i)
-                              : (long long)0x8000000000000000ull;
-          key = C::all_max(key);
-          const int32_t bv = (int32_t)(key >> 32);
-          if (bv > trk_val) {
-            trk_val = bv;
-            trk_i = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll));
-            trk_hit = true;
-          }
+        // column tracker, this lane's share: its rows come in ascending order, so a strict > keeps the first
+        if (act && best + xs > lane_trk_val) {
+          lane_trk_val = best + xs;
+          lane_trk_i = (uint32_t)i;
         }
         const uint64_t left = hi_main - 1 - base;
         const int src = left < (uint64_t)(W - 1) ? (int)left : W - 1;
@@ -1268,6 +1263,19 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
         cI = C::from(best_i, src);
         cSn = C::from(sncur, src);
         csb = (uint32_t)C::from((int32_t)sb, src);
+      }
+    }
+    if (lo < hi_main) {  // first row with the highest S + xs over all lanes (lowest row wins ties), once per column
+      long long key = lane_trk_val > MIN_SCORE
+                          ? (long long)((unsigned long long)(long long)lane_trk_val << 32) +
+                                (long long)(0xFFFFFFFFu - lane_trk_i)
+                          : (long long)0x8000000000000000ull;
+      key = C::all_max(key);
+      const int32_t bv = (int32_t)(key >> 32);
+      if (key != (long long)0x8000000000000000ull && bv > trk_val) {
+        trk_val = bv;
+        trk_i = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll));
+        trk_hit = true;
       }
     }
     if (lane == 0) {
@@ -1588,8 +1596,11 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   prm.k4_status[p] = st;
 }
 
+#ifndef B2A_K3_MINB
+#define B2A_K3_MINB 8  // resident CTAs per SM asked of ptxas for K3 (latency-bound: more warps win)
+#endif
 // K3: one warp per pair
-__global__ void __launch_bounds__(128) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
+__global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = (int)(threadIdx.x & 31u);
   if (t >= n_wave) return;

@@ -297,6 +297,22 @@ struct BandD {
     }
     C::sync();
   }
+  // L consecutive add_entry calls along a diagonal, (r0 + u, c0 + u) for u = 0..L-1 (a run of matches that each
+  // continue the previous one, banded.rs:1354-1357), in closed form per column: the entries covering column j are
+  // u in [j - c0 - w, j - c0 + w] clipped to the run, their lowest start is the first one's and their highest end
+  // the last one's.
+  B2A_HD void add_entry_run(uint64_t r0, uint64_t c0, uint64_t L, uint64_t w) {
+    if (L == 0) return;
+    const uint64_t jb = sat_sub64(c0, w), je = umin64(c0 + (L - 1) + w + 1, cols);
+    for (uint64_t j = jb + (uint64_t)lane; j < je; j += W) {
+      const uint64_t u_lo = sat_sub64(j, c0 + w);                      // j <= c0 + u + w
+      const uint64_t u_hi = umin64(L - 1, j + w >= c0 ? j + w - c0 : 0);  // c0 + u - w <= j
+      if (j + w < c0 || u_lo > u_hi) continue;
+      lo(j, sat_sub64(r0 + u_lo, w));
+      hi(j, umin64(r0 + u_hi + w + 1, rows));
+    }
+    C::sync();
+  }
   // banded.rs:1123-1137, u32 arithmetic.  Returns false where the reference would divide by zero.
   B2A_HD bool add_gap(uint32_t s0, uint32_t s1, uint32_t e0, uint32_t e1, uint64_t w) {
     const uint32_t nrows = e0 - s0, ncols = e1 - s1;
@@ -526,6 +542,43 @@ B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_
   ny = shared_u32[0];
   for (uint32_t t = (uint32_t)lane; t <= ny + 1; t += W) fen[t] = PrevPtrD{0, 0, 0, 0, 0, 0};
   C::sync();
+  // everything an event needs that does not depend on earlier events is looked up by all lanes up front: its
+  // match, the tree rank of its coordinate and (for an end) the match one step up the diagonal.  The sorted y
+  // scratch is free again, and `path` is not written before the backtrack.
+  uint32_t* ev_p = reinterpret_cast<uint32_t*>(tmp);  // [2 nm] match index of the event
+  uint32_t* ev_aux = ev_p + 2ull * nm;                // [2 nm] start: #coordinates <= y; end: diagonal predecessor
+  uint32_t* rank_end = path;                          // [nm]   1-based tree position of the match's end coordinate
+  for (uint64_t e = (uint64_t)lane; e < 2ull * nm; e += W) {
+    const uint64_t key = ev[e];
+    const bool is_start = (key & 1ull) != 0;
+    const uint32_t e0 = (uint32_t)(key >> 33), e1 = (uint32_t)((key >> 1) & 0xffffffffull);
+    const uint64_t want = is_start ? (((uint64_t)e0 << 32) | e1) : (((uint64_t)(e0 - k) << 32) | (e1 - k));
+    uint32_t lo = 0, hi = nm;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) / 2;
+      if (matches[mid] < want) lo = mid + 1;
+      else hi = mid;
+    }
+    ev_p[e] = lo;
+    if (is_start) {
+      ev_aux[e] = lower_bound_u32(ycoord, ny, e1 + 1);
+    } else {
+      uint32_t found = 0xFFFFFFFFu;
+      if (e0 > k && e1 > k) {
+        const uint64_t cw = ((uint64_t)(e0 - k - 1) << 32) | (e1 - k - 1);
+        uint32_t l2 = 0, h2 = nm;
+        while (l2 < h2) {
+          const uint32_t mid = (l2 + h2) / 2;
+          if (matches[mid] < cw) l2 = mid + 1;
+          else h2 = mid;
+        }
+        if (l2 < nm && matches[l2] == cw) found = l2;
+      }
+      ev_aux[e] = found;
+      rank_end[lo] = lower_bound_u32(ycoord, ny, e1) + 1;
+    }
+  }
+  C::sync();
   uint32_t np = 0;
   if (lane == 0) {
   uint32_t best_score = k;
@@ -537,23 +590,14 @@ B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_
     const uint64_t key = ev[e];
     const bool is_start = (key & 1ull) != 0;
     const uint32_t e0 = (uint32_t)(key >> 33), e1 = (uint32_t)((key >> 1) & 0xffffffffull);
-    // the match this event belongs to: binary search its start coordinates in the sorted matches
-    const uint64_t want = is_start ? (((uint64_t)e0 << 32) | e1) : (((uint64_t)(e0 - k) << 32) | (e1 - k));
-    uint32_t lo = 0, hi = nm;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) / 2;
-      if (matches[mid] < want) lo = mid + 1;
-      else hi = mid;
-    }
-    const uint32_t p = lo;
+    const uint32_t p = ev_p[e];
     if (is_start) {
       dp_score[p] = k * match_score;
       dp_prev[p] = -1;
       // max_col_dp.get(j): prefix max over inserted coordinates <= e1
       PrevPtrD best{0, 0, 0, 0, 0, 0};
       {
-        uint32_t cnt = lower_bound_u32(ycoord, ny, e1 + 1);  // number of coordinates <= e1
-        uint32_t idx = cnt;                                  // Fenwick positions are 1-based
+        uint32_t idx = ev_aux[e];  // number of coordinates <= e1; Fenwick positions are 1-based
         while (idx > 0) {
           if (prev_ge(fen[idx], best)) best = fen[idx];
           idx -= idx & (0u - idx);
@@ -580,15 +624,9 @@ B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_
         }
       }
     } else {
-      if (e0 > k && e1 > k) {
-        const uint64_t cw = ((uint64_t)(e0 - k - 1) << 32) | (e1 - k - 1);
-        uint32_t l2 = 0, h2 = nm;
-        while (l2 < h2) {
-          const uint32_t mid = (l2 + h2) / 2;
-          if (matches[mid] < cw) l2 = mid + 1;
-          else h2 = mid;
-        }
-        if (l2 < nm && matches[l2] == cw) {
+      {
+        const uint32_t l2 = ev_aux[e];  // the match at (x - 1, y - 1), sparse.rs:267-275
+        if (l2 != 0xFFFFFFFFu) {
           const uint32_t cs = dp_score[l2] + match_score;
           if (dp_gt(cs, (int32_t)l2, dp_score[p], dp_prev[p])) {
             dp_score[p] = cs;
@@ -607,7 +645,7 @@ B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_
       pf.id = p;
       pf.x = lcs ? 0u : e0;
       pf.y = lcs ? 0u : e1;
-      uint32_t idx = lower_bound_u32(ycoord, ny, e1) + 1;  // 1-based rank of this coordinate
+      uint32_t idx = rank_end[p];  // 1-based rank of this coordinate
       while (idx <= ny) {
         if (prev_ge(pf, fen[idx])) fen[idx] = pf;
         idx += idx & (0u - idx);
@@ -833,18 +871,29 @@ B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint
       status = 2;
     bool has_prev = false;
     uint32_t p0 = 0, p1 = 0;
-    for (uint32_t t = 0; t < np; ++t) {
+    for (uint32_t t = 0; t < np;) {
       const uint64_t cur = matches[path[t]];
       const uint32_t c0 = (uint32_t)(cur >> 32), c1 = (uint32_t)cur;
       if (has_prev && c0 == p0 + 1 && c1 == p1 + 1) {
-        band.add_entry((uint64_t)p0 + k, (uint64_t)p1 + k, w);
+        // a run of matches that each continue the previous one: add_entry((prev.0 + k, prev.1 + k)) per member
+        uint32_t L = 1;
+        while (t + L < np) {
+          const uint64_t nx = matches[path[t + L]];
+          if ((uint32_t)(nx >> 32) != c0 + L || (uint32_t)nx != c1 + L) break;
+          ++L;
+        }
+        band.add_entry_run((uint64_t)p0 + k, (uint64_t)p1 + k, L, w);
+        p0 = c0 + (L - 1);
+        p1 = c1 + (L - 1);
+        t += L;
       } else {
         if (has_prev)
           if (!band.add_gap(p0 + (k - 1), p1 + (k - 1), c0, c1, w)) status = 2;
         band.add_kmer(c0, c1, k, w);
+        p0 = c0;
+        p1 = c1;
+        t += 1;
       }
-      p0 = c0;
-      p1 = c1;
       has_prev = true;
     }
   }
@@ -1044,8 +1093,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
   }
   C::sync();
+  uint32_t known_busy = 0;  // columns from here on already seen not to be of the plain kind
   for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
-    {
+    if (known_busy > 0) {
+      known_busy -= 1;
+    } else {
       // Columns without band cells (most of a long y) only store: S/I/D[i_start-1] = S[m] = MIN_SCORE, the
       // x-suffix-clip nibble of row m, and the MIN_SCORE reset ahead of the next column.  Nothing is read and
       // every array store writes the same constant, so a run of such columns is done one column per lane.
@@ -1084,6 +1136,10 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
         j += run - 1;
         continue;
       }
+      // lanes 1.. looked at the columns after this one: skip the test while they were not plain either
+      uint32_t ahead = 0;
+      while (ahead + 1 < (uint32_t)W && !((bal >> (ahead + 1)) & 1u)) ++ahead;
+      known_busy = ahead;
     }
     int32_t* S = Sarr[j % 2];
     int32_t* I = Iarr[j % 2];

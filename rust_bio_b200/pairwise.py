@@ -209,3 +209,57 @@ class Aligner:
 
 
 setattr(Aligner, "global", Aligner.global_)  # reachable as getattr(aligner, "global")
+
+
+class TracebackCell:
+    """`pairwise::TracebackCell` (mod.rs:1026-1114): the packed u16 of one traceback cell -- bits 0-3 the I
+    layer's move, 4-7 the D layer's, 8-11 the S layer's.  The engine's own traceback is a 4-bit re-encoding
+    (DESIGN.md section 2); this public type is kept for callers that used it."""
+    TB_START, TB_INS, TB_DEL, TB_SUBST, TB_MATCH = 0, 1, 2, 3, 4
+    TB_XCLIP_PREFIX, TB_XCLIP_SUFFIX, TB_YCLIP_PREFIX, TB_YCLIP_SUFFIX = 5, 6, 7, 8
+    TB_MAX = 8
+    _I_POS, _D_POS, _S_POS = 0, 4, 8
+    __slots__ = ("v",)
+
+    def __init__(self, v: int = 0):
+        self.v = int(v) & 0xFFFF
+
+    @staticmethod
+    def new() -> "TracebackCell":
+        return TracebackCell()
+
+    def _set_bits(self, pos: int, value: int) -> None:
+        assert value <= TracebackCell.TB_MAX, "Expected a value <= TB_MAX while setting traceback bits"
+        self.v = (self.v & ~(0b1111 << pos) & 0xFFFF) | (value << pos)
+
+    def set_i_bits(self, value: int) -> None:
+        self._set_bits(self._I_POS, value)
+
+    def set_d_bits(self, value: int) -> None:
+        self._set_bits(self._D_POS, value)
+
+    def set_s_bits(self, value: int) -> None:
+        self._set_bits(self._S_POS, value)
+
+    def get_i_bits(self) -> int:
+        return (self.v >> self._I_POS) & 0b1111
+
+    def get_d_bits(self) -> int:
+        return (self.v >> self._D_POS) & 0b1111
+
+    def get_s_bits(self) -> int:
+        return (self.v >> self._S_POS) & 0b1111
+
+    def set_all(self, value: int) -> None:
+        self.set_i_bits(value)
+        self.set_d_bits(value)
+        self.set_s_bits(value)
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, TracebackCell) and self.v == other.v
+
+    def __hash__(self) -> int:
+        return hash(self.v)
+
+    def __repr__(self) -> str:
+        return "TracebackCell { v: %d }" % self.v

@@ -447,6 +447,38 @@ pub mod alignment {
             pub fn local(&mut self, x: &[u8], y: &[u8]) -> Alignment { self.batch(3, None, &[(x, y)]).remove(0) }
         }
 
+        // ------------------------------------------------------------ TracebackCell, mod.rs:1026-1114
+        /// The reference's public packed traceback cell (bits 0-3 I, 4-7 D, 8-11 S). The engine keeps its own 4-bit
+        /// traceback on the device; this type is here for callers that named it.
+        #[derive(Default, Copy, Clone, Eq, PartialEq, Ord, PartialOrd, Hash, Debug)]
+        pub struct TracebackCell {
+            v: u16,
+        }
+        const I_POS: u8 = 0;
+        const D_POS: u8 = 4;
+        const S_POS: u8 = 8;
+        const TB_MAX: u16 = 0b1000;
+        impl TracebackCell {
+            pub fn new() -> TracebackCell { Default::default() }
+            fn set_bits(&mut self, pos: u8, value: u16) {
+                let bits: u16 = (0b1111) << pos;
+                assert!(value <= TB_MAX, "Expected a value <= TB_MAX while setting traceback bits");
+                self.v = (self.v & !bits) | (value << pos)
+            }
+            pub fn set_i_bits(&mut self, value: u16) { self.set_bits(I_POS, value); }
+            pub fn set_d_bits(&mut self, value: u16) { self.set_bits(D_POS, value); }
+            pub fn set_s_bits(&mut self, value: u16) { self.set_bits(S_POS, value); }
+            fn get_bits(self, pos: u8) -> u16 { (self.v >> pos) & (0b1111) }
+            pub fn get_i_bits(self) -> u16 { self.get_bits(I_POS) }
+            pub fn get_d_bits(self) -> u16 { self.get_bits(D_POS) }
+            pub fn get_s_bits(self) -> u16 { self.get_bits(S_POS) }
+            pub fn set_all(&mut self, value: u16) {
+                self.set_i_bits(value);
+                self.set_d_bits(value);
+                self.set_s_bits(value);
+            }
+        }
+
         // ------------------------------------------------------------ banded::Aligner, banded.rs:122-1004
         pub mod banded {
             use super::{Alignment, BandedCall, MatchFunc, Scoring};

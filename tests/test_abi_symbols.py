@@ -59,3 +59,20 @@ def test_mirror_asserts_like_the_reference():
     assert s.xclip_prefix == -5 and s.xclip_suffix == -5 and s.yclip_prefix == -858993459
     assert s.match_scores == (1, -1)
     assert Scoring.new(-5, -1, lambda a, b: 1).match_scores is None
+
+
+def test_traceback_cell_mirror():
+    """pairwise::TracebackCell (mod.rs:1026-1114): 4 bits each for I (0-3), D (4-7), S (8-11)."""
+    from rust_bio_b200.pairwise import TracebackCell as T
+    c = T.new()
+    assert (c.get_i_bits(), c.get_d_bits(), c.get_s_bits()) == (T.TB_START,) * 3 and c == T()
+    c.set_s_bits(T.TB_YCLIP_SUFFIX)
+    c.set_i_bits(T.TB_INS)
+    c.set_d_bits(T.TB_XCLIP_PREFIX)
+    assert c.v == (8 << 8) | (5 << 4) | 1
+    c.set_s_bits(T.TB_MATCH)  # overwrites only its own nibble
+    assert (c.get_i_bits(), c.get_d_bits(), c.get_s_bits()) == (1, 5, 4)
+    c.set_all(T.TB_SUBST)
+    assert c.v == 0x333
+    with pytest.raises(AssertionError, match="TB_MAX"):
+        c.set_i_bits(9)

@@ -194,6 +194,11 @@ int32_t b2a_align_batch_banded_hinted(b2a_engine* e, int32_t mode, const b2a_sco
                                       uint32_t k, uint32_t w, const b2a_pairs* pairs,
                                       const b2a_band_hints* hints, b2a_results* results, b2a_stats* stats);
 
+/* Band::ranges of one pair of the last banded call (what banded::Aligner::visualize draws, banded.rs:1007-1030):
+ * y_len + 1 half-open row ranges as (start, end) u32 pairs; an empty column is (x_len + 1, 0) (banded.rs:1065).
+ * Kept on the device for the pairs of the call's last wave (every pair, unless the batch needed several waves). */
+int32_t b2a_banded_band_ranges(b2a_engine* e, uint64_t pair, uint32_t* ranges, uint64_t capacity_pairs);
+
 /* Staged form of b2a_align_batch, so a caller can keep a batch resident in HBM:
  *   stage: validate, plan, host->device copy of the batch (async on the stream);
  *   run:   launch K0..K2 on the stream (async; may be called repeatedly);

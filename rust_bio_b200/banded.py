@@ -85,6 +85,21 @@ class Aligner:
                                  AlignmentMode.Custom))
         return out
 
+    def visualize(self, alignment: Alignment, file=None) -> str:
+        """banded.rs:1007-1030: the band of the LAST single-pair alignment ('x'), the alignment's path ('\\'), one
+        text row per x position (rows = xlen + 1, columns = ylen + 1).  Prints it like the reference and returns it."""
+        rows, cols = alignment.xlen + 1, alignment.ylen + 1
+        ranges = self.engine.banded_band_ranges(0, alignment.ylen)
+        view = [["."] * cols for _ in range(rows)]
+        for j in range(cols):
+            for i in range(int(ranges[j, 0]), min(int(ranges[j, 1]), rows)):
+                view[i][j] = "x"
+        for p in alignment.path():
+            view[p[0]][p[1]] = "\\"
+        text = "\n".join("".join(r) for r in view)
+        print(text, file=file)
+        return text
+
     # ---- banded.rs:294-401: the band's inputs come from the caller
     def custom_with_prehash(self, x: bytes, y: bytes, y_kmer_hash) -> Alignment:
         """banded.rs:294-302.  `y_kmer_hash` (see hash_kmers) only spares the reference the hashing of y; the

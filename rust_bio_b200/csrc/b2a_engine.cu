@@ -77,6 +77,10 @@ struct b2a_engine {
   int num_sms = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
   uint64_t compact_hdr[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};  // header of the compact result segment
+  // the band of the last banded call's last wave (Band::ranges), for b2a_banded_band_ranges
+  uint64_t band_wave_lo = 0;
+  std::vector<uint64_t> band_roff;
+  std::vector<uint32_t> band_ylen;
   std::string err;
   int tune_G = 0, tune_R = 0;
   uint64_t tb_budget = 0;
@@ -1081,6 +1085,9 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     CK(e->d_branges.reserve(rbytes + 16));
     CK(e->d_broff.reserve((uint64_t)nw * 8 + 8));
     CK(up(e->d_broff, roff.data(), (size_t)nw * 8));
+    e->band_wave_lo = lo;
+    e->band_roff = roff;
+    e->band_ylen.assign(pairs->y_len + lo, pairs->y_len + lo + nw);
     bp.pair_lo = (uint32_t)lo;
     bp.slab = e->d_bslab.as<uint8_t>();
     bp.ranges = e->d_branges.as<uint32_t>();
@@ -1153,6 +1160,18 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   }
   e->ran = false;
   return rc;
+}
+
+int32_t b2a_banded_band_ranges(b2a_engine* e, uint64_t pair, uint32_t* ranges, uint64_t capacity_pairs) {
+  if (!e || !ranges) return B2A_E_INVALID;
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  if (pair < e->band_wave_lo || pair - e->band_wave_lo >= e->band_roff.size())
+    return e->fail(B2A_E_STATE, "band ranges are kept for the pairs of the last banded call's last wave only");
+  const uint64_t t = pair - e->band_wave_lo, cols = (uint64_t)e->band_ylen[t] + 1;
+  if (capacity_pairs < cols) return e->fail(B2A_E_CAPACITY, "ranges buffer too small (needs y_len + 1 pairs)");
+  CK(cudaMemcpyAsync(ranges, e->d_branges.as<uint8_t>() + e->band_roff[t], cols * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return B2A_OK;
 }
 
 uint32_t b2a_record_stride(uint32_t max_m, uint32_t max_n) {

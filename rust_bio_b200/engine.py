@@ -163,6 +163,12 @@ class Engine:
                                                           C.byref(self.stats)))
         return results
 
+    def banded_band_ranges(self, pair: int, y_len: int) -> np.ndarray:
+        """Band::ranges of `pair` of the last banded call: array [y_len + 1, 2] of (start, end) row ranges."""
+        out = np.zeros((int(y_len) + 1, 2), dtype=np.uint32)
+        self._check(self._L.b2a_banded_band_ranges(self._h, int(pair), out.ctypes.data_as(C.c_void_p), int(y_len) + 1))
+        return out
+
     # staged form
     def stage(self, mode: int, cscoring: CScoring, batch: Batch):
         self._keep = (batch, cscoring)

@@ -223,3 +223,36 @@ def test_caller_supplied_band_inputs_refusals(eng, oracle):
     s_o, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
     f, ops, _ = oracle.banded_align_hinted(s_o, 6, 3, x, y, [])
     assert a.score == f["score"] and [(o.code, o.len) for o in a.operations] == ops
+
+
+def test_band_ranges_and_visualize(eng, oracle):
+    """b2a_banded_band_ranges returns Band::ranges of the last call (banded.rs:1053-1065); visualize draws it with
+    the path like banded.rs:1007-1030."""
+    import io
+    from rust_bio_b200.banded import Aligner
+    from rust_bio_b200.pairwise import Scoring
+    from test_sim_banded import _window_pair
+    rng = np.random.default_rng(77)
+    s_o, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    aligner = Aligner.with_scoring(Scoring.from_scores(-5, -1, 1, -1), 6, 4, engine=eng)
+    for _ in range(4):
+        x, y = _window_pair(rng, 40, 90)
+        aln = aligner.semiglobal(x, y)
+        want, cells = oracle.band_create("semiglobal", s_o, 6, 4, x, y)
+        got = eng.banded_band_ranges(0, len(y))
+        assert [(int(a), int(b)) for a, b in got] == want
+        buf = io.StringIO()
+        text = aligner.visualize(aln, file=buf)
+        lines = text.split("\n")
+        assert len(lines) == len(x) + 1 and all(len(l) == len(y) + 1 for l in lines) and buf.getvalue() == text + "\n"
+        in_band = {(i, j) for j, (a, b) in enumerate(want) for i in range(a, b)}
+        on_path = {(p[0], p[1]) for p in aln.path()}
+        for i, l in enumerate(lines):
+            for j, ch in enumerate(l):
+                assert ch == ("\\" if (i, j) in on_path else "x" if (i, j) in in_band else "."), (i, j)
+    # batches: ranges of any pair of the (single) wave
+    pairs = [_window_pair(rng, 40, 90) for _ in range(5)]
+    aligner.custom_batch(pairs)
+    x, y = pairs[3]
+    want, _ = oracle.band_create("custom", s_o, 6, 4, x, y)
+    assert [(int(a), int(b)) for a, b in eng.banded_band_ranges(3, len(y))] == want

@@ -448,34 +448,42 @@ pub mod alignment {
         }
 
         // ------------------------------------------------------------ TracebackCell, mod.rs:1026-1114
-        /// The reference's public packed traceback cell (bits 0-3 I, 4-7 D, 8-11 S). The engine keeps its own 4-bit
-        /// traceback on the device; this type is here for callers that named it.
+        /// The reference's public packed traceback cell: three 4-bit move codes, I in the low nibble, then D, then S.
+        /// The engine keeps its own 4-bit traceback on the device; this host type exists for callers that named it.
         #[derive(Default, Copy, Clone, Eq, PartialEq, Ord, PartialOrd, Hash, Debug)]
         pub struct TracebackCell {
             v: u16,
         }
-        const I_POS: u8 = 0;
-        const D_POS: u8 = 4;
-        const S_POS: u8 = 8;
-        const TB_MAX: u16 = 0b1000;
+        #[derive(Copy, Clone)]
+        enum Layer {
+            I = 0,
+            D = 4,
+            S = 8,
+        }
+        const LARGEST_MOVE: u16 = 8; // TB_YCLIP_SUFFIX
         impl TracebackCell {
-            pub fn new() -> TracebackCell { Default::default() }
-            fn set_bits(&mut self, pos: u8, value: u16) {
-                let bits: u16 = (0b1111) << pos;
-                assert!(value <= TB_MAX, "Expected a value <= TB_MAX while setting traceback bits");
-                self.v = (self.v & !bits) | (value << pos)
+            pub fn new() -> TracebackCell {
+                TracebackCell { v: 0 }
             }
-            pub fn set_i_bits(&mut self, value: u16) { self.set_bits(I_POS, value); }
-            pub fn set_d_bits(&mut self, value: u16) { self.set_bits(D_POS, value); }
-            pub fn set_s_bits(&mut self, value: u16) { self.set_bits(S_POS, value); }
-            fn get_bits(self, pos: u8) -> u16 { (self.v >> pos) & (0b1111) }
-            pub fn get_i_bits(self) -> u16 { self.get_bits(I_POS) }
-            pub fn get_d_bits(self) -> u16 { self.get_bits(D_POS) }
-            pub fn get_s_bits(self) -> u16 { self.get_bits(S_POS) }
+            fn put(&mut self, layer: Layer, code: u16) {
+                assert!(code <= LARGEST_MOVE, "Expected a value <= TB_MAX while setting traceback bits");
+                let shift = layer as u16;
+                self.v &= !(0xF << shift);
+                self.v |= code << shift;
+            }
+            fn take(self, layer: Layer) -> u16 {
+                (self.v >> (layer as u16)) & 0xF
+            }
+            pub fn set_i_bits(&mut self, value: u16) { self.put(Layer::I, value) }
+            pub fn set_d_bits(&mut self, value: u16) { self.put(Layer::D, value) }
+            pub fn set_s_bits(&mut self, value: u16) { self.put(Layer::S, value) }
+            pub fn get_i_bits(self) -> u16 { self.take(Layer::I) }
+            pub fn get_d_bits(self) -> u16 { self.take(Layer::D) }
+            pub fn get_s_bits(self) -> u16 { self.take(Layer::S) }
             pub fn set_all(&mut self, value: u16) {
-                self.set_i_bits(value);
-                self.set_d_bits(value);
-                self.set_s_bits(value);
+                for layer in [Layer::I, Layer::D, Layer::S] {
+                    self.put(layer, value);
+                }
             }
         }
 

@@ -141,17 +141,47 @@ B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
   return (b + 255) & ~255ull;
 }
 
+#if defined(B2A_HOST_WARP) && !defined(__CUDACC__)
+// Test-only (tests/sim): a 32-lane warp emulated on the host so that the not-gpu suite runs the W = 32
+// instantiations too.  The lanes are 32 cooperatively scheduled contexts of one thread; a warp barrier hands
+// control to the next lane (round robin, so a lane resumes after every other lane reached the barrier), and
+// shuffles / votes go through an exchange buffer between two barriers.
+struct HostWarp {
+  long long x[32];
+  void (*next_lane)(void*);  // provided by the harness: switch to the next unfinished lane
+  void* harness;
+};
+inline HostWarp* host_warp = nullptr;
+inline int host_lane = 0;
+inline void host_warp_sync() { host_warp->next_lane(host_warp->harness); }
+template <class Pick>
+inline long long host_warp_exchange(long long mine, Pick pick) {
+  host_warp->x[host_lane] = mine;
+  host_warp_sync();
+  const long long r = pick(host_warp->x);
+  host_warp_sync();
+  return r;
+}
+#endif
+
 // Cooperative-lane helpers: W = 32 lanes of one warp on the device, W = 1 in the host logic build.
 template <int W>
 struct Coop {
   static B2A_HD void sync() {
 #if defined(__CUDA_ARCH__)
     if (W > 1) __syncwarp();
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) host_warp_sync();
 #endif
   }
   static B2A_HD int32_t up(int32_t v, int d) {  // the value held by lane - d
 #if defined(__CUDA_ARCH__)
     if (W > 1) return __shfl_up_sync(0xffffffffu, v, d);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) {
+      const int me = host_lane;
+      return (int32_t)host_warp_exchange(v, [&](const long long* x) { return me >= d ? x[me - d] : x[me]; });
+    }
 #endif
     (void)d;
     return v;
@@ -159,6 +189,8 @@ struct Coop {
   static B2A_HD int32_t from(int32_t v, int src) {
 #if defined(__CUDA_ARCH__)
     if (W > 1) return __shfl_sync(0xffffffffu, v, src);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) return (int32_t)host_warp_exchange(v, [&](const long long* x) { return x[src & 31]; });
 #endif
     (void)src;
     return v;
@@ -166,6 +198,13 @@ struct Coop {
   static B2A_HD uint32_t ballot(bool b) {  // bit l = lane l's predicate
 #if defined(__CUDA_ARCH__)
     if (W > 1) return __ballot_sync(0xffffffffu, b);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1)
+      return (uint32_t)host_warp_exchange(b ? 1 : 0, [&](const long long* x) {
+        long long m = 0;
+        for (int l = 0; l < 32; ++l) m |= (x[l] ? 1ll : 0ll) << l;
+        return m;
+      });
 #endif
     return b ? 1u : 0u;
   }
@@ -173,6 +212,13 @@ struct Coop {
 #if defined(__CUDA_ARCH__)
     if (W > 1)
       for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1)
+      return (unsigned long long)host_warp_exchange((long long)v, [&](const long long* x) {
+        unsigned long long t = 0;
+        for (int l = 0; l < 32; ++l) t += (unsigned long long)x[l];
+        return (long long)t;
+      });
 #endif
     return v;
   }
@@ -181,6 +227,11 @@ struct Coop {
 #if defined(__CUDA_ARCH__)
     if (W > 1)
       return atomicCAS(reinterpret_cast<unsigned long long*>(slot), 0ull, (unsigned long long)val) == 0ull;
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) {
+      uint64_t expect = 0;
+      return __atomic_compare_exchange_n(slot, &expect, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    }
 #endif
     if (*slot != 0) return false;
     *slot = val;
@@ -189,6 +240,8 @@ struct Coop {
   static B2A_HD uint32_t fetch_add(uint32_t* ctr, uint32_t v) {
 #if defined(__CUDA_ARCH__)
     if (W > 1) return atomicAdd(ctr, v);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) return __atomic_fetch_add(ctr, v, __ATOMIC_SEQ_CST);
 #endif
     const uint32_t old = *ctr;
     *ctr = old + v;
@@ -201,6 +254,13 @@ struct Coop {
         const long long t = __shfl_xor_sync(0xffffffffu, v, d);
         v = t > v ? t : v;
       }
+#elif defined(B2A_HOST_WARP)
+    if (W > 1)
+      return host_warp_exchange(v, [&](const long long* x) {
+        long long t = x[0];
+        for (int l = 1; l < 32; ++l) t = x[l] > t ? x[l] : t;
+        return t;
+      });
 #endif
     return v;
   }

@@ -231,7 +231,10 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
 // ---------------------------------------------------------------------------------------------
 // Banded path: the device functions of b2a_banded.cuh (K4 band construction + K3 banded fill/walk)
 // compiled for the host, one pair at a time.
+#define B2A_HOST_WARP 1  // 32 host threads stand in for a warp when the W = 32 code is run here
 #include "../../rust_bio_b200/csrc/b2a_banded.cuh"
+#include <functional>
+#include <ucontext.h>
 
 extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* blob,
                                 const uint64_t* x_off, const uint32_t* x_len, const uint64_t* y_off,
@@ -343,6 +346,155 @@ extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t 
     };
     banded_compute_d<1>(0, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), false,
                         opsbuf.data() + opsbuf.size(), o);
+  }
+  *score = o.score;
+  coords[0] = o.xstart;
+  coords[1] = o.xend;
+  coords[2] = o.ystart;
+  coords[3] = o.yend;
+  *n_ops = o.n_ops;
+  *status = o.status;
+  for (int q = 0; q < 4; ++q) clip_len[q] = o.clip[q];
+  std::memcpy(ops, opsbuf.data() + opsbuf.size() - o.n_ops, o.n_ops);
+  return 0;
+}
+
+// 32 cooperatively scheduled contexts of this thread stand in for the lanes of one warp (see HostWarp in
+// b2a_banded.cuh): a barrier switches to the next unfinished lane, round robin.
+struct LaneFibers {
+  static constexpr int W = 32;
+  static constexpr size_t kStack = 512 * 1024;
+  ucontext_t main_ctx;
+  ucontext_t ctx[W];
+  std::vector<char> stacks;
+  bool done[W];
+  int cur = 0;
+  std::function<void(int)> body;
+  HostWarp hw;
+  static LaneFibers* self;
+
+  static void entry() {
+    LaneFibers* f = self;
+    f->body(f->cur);
+    f->done[f->cur] = true;
+    next_lane(f);
+  }
+  static void next_lane(void* p) {
+    LaneFibers* f = static_cast<LaneFibers*>(p);
+    const int from = f->cur;
+    int to = -1;
+    for (int d = 1; d <= W; ++d) {
+      const int cand = (from + d) % W;
+      if (!f->done[cand]) {
+        to = cand;
+        break;
+      }
+    }
+    if (to == from) return;  // the only lane left: its barrier is a no-op
+    if (to < 0) {            // every lane finished
+      swapcontext(&f->ctx[from], &f->main_ctx);
+      return;
+    }
+    f->cur = to;
+    host_lane = to;
+    swapcontext(&f->ctx[from], &f->ctx[to]);
+  }
+  static void run(std::function<void(int)> body) {
+    LaneFibers f;
+    f.body = std::move(body);
+    f.stacks.resize(kStack * W);
+    f.hw.next_lane = &LaneFibers::next_lane;
+    f.hw.harness = &f;
+    self = &f;
+    host_warp = &f.hw;
+    for (int l = 0; l < W; ++l) {
+      f.done[l] = false;
+      getcontext(&f.ctx[l]);
+      f.ctx[l].uc_stack.ss_sp = f.stacks.data() + kStack * l;
+      f.ctx[l].uc_stack.ss_size = kStack;
+      f.ctx[l].uc_link = nullptr;
+      makecontext(&f.ctx[l], &LaneFibers::entry, 0);
+    }
+    f.cur = 0;
+    host_lane = 0;
+    swapcontext(&f.main_ctx, &f.ctx[0]);
+    host_warp = nullptr;
+    self = nullptr;
+  }
+};
+LaneFibers* LaneFibers::self = nullptr;
+
+// The W = 32 instantiations of K4 and K3 (what the GPU runs) with 32 host contexts as the lanes of one warp.
+// Same interface and outputs as sim_banded_hinted_one; have_matches = 0 lets K4 find the matches itself.
+extern "C" int sim_banded_warp32_one(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* x,
+                                     uint32_t m32, const uint8_t* y, uint32_t n32, int have_matches,
+                                     const uint32_t* match_xy, uint64_t n_matches, const uint32_t* path_idx,
+                                     uint64_t n_path, int have_path, int allowed_mismatches, int use_lcskpp_union,
+                                     uint32_t cap_matches, int garbage, int32_t* score, uint32_t* coords,
+                                     uint32_t* n_ops, uint32_t* clip_len, uint32_t* status, uint64_t* num_cells,
+                                     uint64_t* ranges_out /*2*(n+1) or null*/, uint8_t* ops) {
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  if (mode == 1) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
+  if (mode == 2) { sc.xclip_prefix = sc.xclip_suffix = MIN_SCORE; sc.yclip_prefix = sc.yclip_suffix = 0; }
+  if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  const int32_t* table = s->table;
+  const uint64_t m = m32, n = n32;
+  std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
+  std::vector<uint32_t> rng(2 * (n + 1), 0xCDCDCDCDu);
+  BandHintsD hint;
+  if (have_matches) {
+    hint.mxy = match_xy;
+    hint.n_matches = n_matches;
+  }
+  hint.pidx = path_idx;
+  hint.n_path = n_path;
+  hint.have_path = have_path != 0;
+  hint.allowed_mismatches = allowed_mismatches;
+  hint.use_lcskpp_union = use_lcskpp_union;
+  uint32_t shared_u32[2] = {0, 0};
+  uint32_t st_lane[32];
+  uint64_t cells_lane[32];
+  auto run32 = [&](std::function<void(int)> body) { LaneFibers::run(body); };
+  run32([&](int l) {
+    uint64_t c = 0;
+    st_lane[l] = band_create_d<32>(l, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches, rng.data(),
+                                   &c, shared_u32, hint);
+    cells_lane[l] = c;
+  });
+  for (int l = 1; l < 32; ++l)
+    if (st_lane[l] != st_lane[0] || cells_lane[l] != cells_lane[0]) return -1;  // lanes must agree
+  const uint32_t st = st_lane[0];
+  const uint64_t cells = cells_lane[0];
+  *num_cells = cells;
+  if (ranges_out)
+    for (uint64_t j = 0; j <= n; ++j) {
+      ranges_out[2 * j] = rng[2 * j];
+      ranges_out[2 * j + 1] = rng[2 * j + 1];
+    }
+  BandedOut o{};
+  std::vector<uint8_t> opsbuf(m + n + 16, 0);
+  if (st != 0) {
+    o.status = 1 + st;
+  } else {
+    std::vector<uint8_t> fill(k3_slab_bytes(m, n, cells), (uint8_t)garbage);
+    auto scoref = [&](uint8_t a, uint8_t b) -> int32_t {
+      if (table) return table[(size_t)a * 256 + b];
+      return a == b ? sc.match_score : sc.mismatch_score;
+    };
+    run32([&](int l) {
+      BandedOut mine{};
+      banded_compute_d<32>(l, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
+                           opsbuf.data() + opsbuf.size(), mine);
+      if (l == 0) o = mine;
+    });
   }
   *score = o.score;
   coords[0] = o.xstart;

@@ -157,3 +157,41 @@ def banded_hinted_one(orc_scoring, k, w, x: bytes, y: bytes, matches, path=None,
         res.append((fields, decode_ops(bytes(ops[:n_ops.value]), list(clip)), int(cells.value)))
     assert res[0] == res[1], "scratch contents leak into the result"
     return None if res[0][0] == "status" else res[0]
+
+
+def banded_warp32_one(mode, orc_scoring, k, w, x: bytes, y: bytes, matches=None, path=None, allowed_mismatches=None,
+                      use_lcskpp_union=False, cap_matches=4096, want_ranges=False):
+    """K4 + K3 as the GPU runs them (W = 32), with 32 host threads as the lanes of one warp.
+    -> (fields, ops, cells[, ranges]) or None when the device code flags a reference panic."""
+    s = SimScoring.from_buffer_copy(bytes(orc_scoring))
+    res = []
+    for garbage in (0x00, 0x7F):
+        xy = np.array([v for mt in (matches or []) for v in mt], dtype=np.uint32) if matches else np.zeros(2, np.uint32)
+        pi = np.array(path if path else [0], dtype=np.uint32)
+        score = C.c_int32(0)
+        coords = (C.c_uint32 * 4)()
+        clip = (C.c_uint32 * 4)()
+        n_ops, status, cells = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        ops = (C.c_uint8 * (len(x) + len(y) + 16))()
+        rng = np.zeros(2 * (len(y) + 1), dtype=np.uint64)
+        rc = lib().sim_banded_warp32_one(
+            C.c_int(int(mode)), C.byref(s), C.c_uint32(k), C.c_uint32(w), x, C.c_uint32(len(x)), y, C.c_uint32(len(y)),
+            C.c_int(1 if matches is not None else 0), xy.ctypes.data_as(C.c_void_p),
+            C.c_uint64(len(matches) if matches is not None else 0), pi.ctypes.data_as(C.c_void_p),
+            C.c_uint64(len(path) if path is not None else 0), C.c_int(1 if path is not None else 0),
+            C.c_int(-1 if allowed_mismatches is None else int(allowed_mismatches)),
+            C.c_int(1 if use_lcskpp_union else 0), C.c_uint32(cap_matches), C.c_int(garbage), C.byref(score),
+            coords, C.byref(n_ops), clip, C.byref(status), C.byref(cells),
+            rng.ctypes.data_as(C.c_void_p) if want_ranges else None, ops)
+        assert rc == 0, "the 32 lanes disagreed on K4's result"
+        if status.value != 0:
+            res.append(("status", status.value))
+            continue
+        fields = {"score": score.value, "xstart": coords[0], "xend": coords[1], "ystart": coords[2],
+                  "yend": coords[3]}
+        out = (fields, decode_ops(bytes(ops[:n_ops.value]), list(clip)), int(cells.value))
+        if want_ranges:
+            out = out + ([(int(rng[2 * j]), int(rng[2 * j + 1])) for j in range(len(y) + 1)],)
+        res.append(out)
+    assert res[0] == res[1], "scratch contents leak into the result"
+    return None if res[0][0] == "status" else res[0]

@@ -150,7 +150,7 @@ def test_sim_banded_refuses_more_than_max_cells(oracle):
     assert int(got["score"][0]) == MIN and ops[0] == [] and int(got["num_cells"][0]) == 501 * 10001
 
 
-def _window_pair(rng, xlen=90, ylen=220, nsub=5):
+def _window_pair(rng, xlen=90, ylen=220, nsub=5):  # noqa: E302
     y = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, ylen)])
     st = int(rng.integers(0, ylen - xlen))
     x = bytearray(y[st:st + xlen])
@@ -209,3 +209,87 @@ def test_sim_banded_caller_inputs_reference_panics(oracle):
     got = sim_util.banded_hinted_one(s, 6, 3, x, y, [])                                     # no matches: full matrix
     want = oracle.banded_align_hinted(s, 6, 3, x, y, [])
     assert got is not None and got[0]["score"] == want[0]["score"] and got[1] == want[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same kernels as the GPU instantiates them (W = 32), with 32 host threads standing in for the lanes of a warp
+# (tests/sim: B2A_HOST_WARP): the prefix-maximum I chain, chunk carries, the per-column arg-max, the runs of plain
+# columns, the cooperative sorts, the segmented k-mer probe and the lane-parallel band geometry -- none of which
+# the W = 1 build above exercises.
+
+@pytest.mark.parametrize("case", G["cases"], ids=lambda c: c["name"])
+def test_warp32_banded_known_answers(oracle, case):
+    s, keep = _scoring(oracle, case["scoring"])
+    x, y = case["x"].encode(), case["y"].encode()
+    got = sim_util.banded_warp32_one(MODES[case["mode"]], s, case["k"], case["w"], x, y)
+    ref, ref_ops = oracle.banded_align(case["mode"], s, case["k"], case["w"], x, y)
+    assert got is not None and got[1] == ref_ops
+    assert got[0] == {f: ref[f] for f in got[0]}
+
+
+@pytest.mark.parametrize("mode", ["semiglobal", "local", "global", "custom"])
+def test_warp32_banded_mutated_windows(oracle, mode):
+    rng = np.random.default_rng({"semiglobal": 1, "local": 2, "global": 3, "custom": 4}[mode])
+    pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9]))
+    n_ok = 0
+    for trial in range(24):
+        go, ge = int(rng.choice([0, -1, -5])), int(rng.choice([0, -1, -2]))  # incl. gap_open > gap_extend
+        clips = (pick(), pick(), pick(), pick()) if mode == "custom" else (MIN, MIN, MIN, MIN)
+        s, _ = oracle.make_scoring(go, ge, int(rng.choice([1, 2])), int(rng.choice([-1, -3])), None, *clips,
+                                   has_match_scores=int(trial % 2))
+        x, y = _window_pair(rng, int(rng.integers(20, 140)), int(rng.integers(150, 420)), nsub=int(rng.integers(0, 9)))
+        k, w = int(rng.choice([4, 6, 9])), int(rng.choice([2, 5, 11]))
+        got = sim_util.banded_warp32_one(MODES[mode], s, k, w, x, y, want_ranges=True)
+        try:
+            ref, ref_ops = oracle.banded_align(mode, s, k, w, x, y)
+        except RuntimeError:  # the reference itself panics / hangs: the device code must flag it
+            assert got is None
+            continue
+        want_rng, cells = oracle.band_create(mode, s, k, w, x, y)
+        assert got is not None, (mode, trial)
+        assert got[3] == want_rng and got[2] == cells, (mode, trial, "band")
+        assert got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops, (mode, trial, x, y)
+        n_ok += 1
+    assert n_ok >= 14
+
+
+def test_warp32_c4_shaped_pairs(oracle):
+    """BASELINE config 4's shape (500 x 10,000, k = 32, w = 32): long runs of plain columns, ~110-row bands."""
+    blob, xo, xl, yo, yl = _mutated_window_batch(4, 3, 500, 10000, sub=0.05, indel=0.01)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    for p in range(3):
+        x = bytes(blob[int(xo[p]):int(xo[p]) + int(xl[p])])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + int(yl[p])])
+        got = sim_util.banded_warp32_one(MODES["semiglobal"], s, 32, 32, x, y, want_ranges=True)
+        ref, ref_ops = oracle.banded_align("semiglobal", s, 32, 32, x, y)
+        want_rng, cells = oracle.band_create("semiglobal", s, 32, 32, x, y)
+        assert got is not None and got[3] == want_rng and got[2] == cells
+        assert got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops
+
+
+def test_warp32_caller_supplied_band_inputs(oracle):
+    rng = np.random.default_rng(321)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, -3, MIN, 0, -4, has_match_scores=1)
+    n_ok = 0
+    for trial in range(6):
+        x, y = _window_pair(rng)
+        k, w = int(rng.choice([5, 7])), int(rng.choice([3, 6]))
+        m = oracle.find_kmer_matches(x, y, k)
+        variants = [dict(), dict(allowed_mismatches=1), dict(use_lcskpp_union=True),
+                    dict(allowed_mismatches=2, use_lcskpp_union=True)]
+        if m:
+            variants.append(dict(path=oracle.lcskpp(m, k)[0]))
+        for kw in variants:
+            want = oracle.banded_align_hinted(s, k, w, x, y, m, **kw)
+            got = sim_util.banded_warp32_one(0, s, k, w, x, y, matches=m, **kw)
+            if want is None:
+                assert got is None
+                continue
+            assert got is not None and got[2] == want[2]
+            assert got[0] == {f: want[0][f] for f in got[0]} and got[1] == want[1], (trial, kw)
+            n_ok += 1
+    assert n_ok >= 15
+    x, y = b"ACGTACGTTGCAACGT", b"TTACGTACGTTGCAACGTAA"
+    m = oracle.find_kmer_matches(x, y, 6)
+    assert sim_util.banded_warp32_one(0, s, 6, 3, x, y, matches=m[::-1]) is None
+    assert sim_util.banded_warp32_one(0, s, 6, 3, x, y, matches=m, path=[0, len(m)]) is None

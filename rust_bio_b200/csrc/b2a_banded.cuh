@@ -1263,31 +1263,38 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       cI = I[lo - 1];
       cSn = Sn[lo - 1];
       csb = (rd(lo - 1, j) >> 8) & 15u;
-      const uint64_t jj = j - 1;  // geometry of column j-1 for the D-open lookups
-      const uint64_t ps = rng[2 * jj], pe = rng[2 * jj + 1];
-      const uint32_t pcs = colstart[jj], cs = colstart[j];
-      for (uint64_t base = lo; base < hi_main; base += W) {
-        const uint64_t i = base + (uint64_t)lane;
-        const bool act = i < hi_main;  // 1 <= i < m
-        int32_t m_score = MIN_SCORE, best_d = MIN_SCORE, A = MIN_SCORE, snold = MIN_SCORE;
-        uint32_t db = TB_START;
-        uint8_t p = 0;
-        if (act) {
-          p = x[i - 1];
-          m_score = Sp[i - 1] + score(p, q);
-          const int32_t d_score = Dp[i] + ge, s_score = Sp[i] + go;
-          if (d_score > s_score) {
-            best_d = d_score;
-            db = TB_DEL;
-          } else {
-            best_d = s_score;
-            const uint32_t pc = jj == 0 ? (uint32_t)col0[i]
-                                        : ((i >= ps && i < pe) ? (uint32_t)cells[pcs + (i - ps)] : 0u);
-            db = (pc >> 8) & 15u;
-          }
-          A = imax(imax(imax(MIN_SCORE, m_score), imax(best_d, xclip_score)), yp + go + ge * ((int32_t)i - 1));
-          snold = Sn[i];
+      // geometry of column j-1 for the D-open lookups, and where this column's cells go, as base + 32-bit offset
+      // (sequence lengths are below 2^24, so the row arithmetic of the chunk loop is 32-bit)
+      const uint64_t jj = j - 1;
+      const uint32_t ps = jj == 0 ? 0u : rng[2 * jj], pe = jj == 0 ? 0xFFFFFFFFu : rng[2 * jj + 1];
+      const uint16_t* const pbase = jj == 0 ? col0 : cells;
+      const uint32_t poff = jj == 0 ? 0u : colstart[jj] - ps;  // cell (i, j-1) = pbase[poff + i] for ps <= i < pe
+      uint16_t* const wbase = last ? coln : cells;
+      const uint32_t woff = last ? 0u : colstart[j] - (uint32_t)i_start;  // cell (i, j) = wbase[woff + i]
+      const uint32_t lo32 = (uint32_t)lo, hm32 = (uint32_t)hi_main;
+      const int32_t ly_now = (int32_t)(n - j);
+      for (uint32_t base = lo32; base < hm32; base += W) {
+        const uint32_t i = base + (uint32_t)lane;
+        const bool act = i < hm32;  // 1 <= i < m
+        // lanes past the end of the column repeat its last row: every load stays in bounds, nothing is stored,
+        // and nothing flows from a higher lane to a lower one
+        const uint32_t ic = act ? i : hm32 - 1;
+        const uint8_t p = x[ic - 1];
+        const int32_t m_score = Sp[ic - 1] + score(p, q);
+        const int32_t d_score = Dp[ic] + ge, s_open = Sp[ic] + go;
+        const int32_t snold = Sn[ic];
+        int32_t best_d;
+        uint32_t db;
+        if (d_score > s_open) {
+          best_d = d_score;
+          db = TB_DEL;
+        } else {
+          best_d = s_open;
+          const uint32_t pc = (ic >= ps && ic < pe) ? (uint32_t)pbase[poff + ic] : 0u;
+          db = (pc >> 8) & 15u;
         }
+        const int32_t yclip_score = yp + go + ge * ((int32_t)ic - 1);
+        const int32_t A = imax(imax(imax(MIN_SCORE, m_score), imax(best_d, xclip_score)), yclip_score);
         // prefix maximum of I(i) - gs*i over the chunk
         int32_t v;
         {
@@ -1324,18 +1331,15 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           best = xclip_score;
           sb = TB_XCLIP_PREFIX;
         }
-        {
-          const int32_t yclip_score = yp + go + ge * ((int32_t)i - 1);
-          if (yclip_score > best) {
-            best = yclip_score;
-            sb = TB_YCLIP_PREFIX;
-          }
+        if (yclip_score > best) {
+          best = yclip_score;
+          sb = TB_YCLIP_PREFIX;
         }
         int32_t sncur = snold;
         if (act && best + ys > snold) {  // row tracker, banded.rs:650-654
           sncur = best + ys;
           Sn[i] = sncur;
-          Ly[i] = (uint32_t)(n - j);
+          Ly[i] = (uint32_t)ly_now;
           if (!last) coln[i] = (uint16_t)((coln[i] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
         }
         // the I nibble needs the final values of row i-1
@@ -1364,17 +1368,15 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           S[i] = best;
           I[i] = best_i;
           D[i] = best_d;
-          const uint32_t cell = ib | (db << 4) | (sb << 8);
-          if (last) coln[i] = (uint16_t)cell;
-          else cells[cs + (i - i_start)] = (uint16_t)cell;
+          wbase[woff + i] = (uint16_t)(ib | (db << 4) | (sb << 8));
+          // column tracker, this lane's share: its rows come in ascending order, so a strict > keeps the first
+          if (best + xs > lane_trk_val) {
+            lane_trk_val = best + xs;
+            lane_trk_i = i;
+          }
         }
-        // column tracker, this lane's share: its rows come in ascending order, so a strict > keeps the first
-        if (act && best + xs > lane_trk_val) {
-          lane_trk_val = best + xs;
-          lane_trk_i = (uint32_t)i;
-        }
-        const uint64_t left = hi_main - 1 - base;
-        const int src = left < (uint64_t)(W - 1) ? (int)left : W - 1;
+        const uint32_t left = hm32 - 1 - base;
+        const int src = left < (uint32_t)(W - 1) ? (int)left : W - 1;
         cS = C::from(best, src);
         cI = C::from(best_i, src);
         cSn = C::from(sncur, src);

@@ -141,29 +141,6 @@ B2A_HD uint64_t k4_slab_bytes(uint32_t cap, uint32_t short_len) {
   return (b + 255) & ~255ull;
 }
 
-#if defined(B2A_HOST_WARP) && !defined(__CUDACC__)
-// Test-only (tests/sim): a 32-lane warp emulated on the host so that the not-gpu suite runs the W = 32
-// instantiations too.  The lanes are 32 cooperatively scheduled contexts of one thread; a warp barrier hands
-// control to the next lane (round robin, so a lane resumes after every other lane reached the barrier), and
-// shuffles / votes go through an exchange buffer between two barriers.
-struct HostWarp {
-  long long x[32];
-  void (*next_lane)(void*);  // provided by the harness: switch to the next unfinished lane
-  void* harness;
-};
-inline HostWarp* host_warp = nullptr;
-inline int host_lane = 0;
-inline void host_warp_sync() { host_warp->next_lane(host_warp->harness); }
-template <class Pick>
-inline long long host_warp_exchange(long long mine, Pick pick) {
-  host_warp->x[host_lane] = mine;
-  host_warp_sync();
-  const long long r = pick(host_warp->x);
-  host_warp_sync();
-  return r;
-}
-#endif
-
 // Cooperative-lane helpers: W = 32 lanes of one warp on the device, W = 1 in the host logic build.
 template <int W>
 struct Coop {

@@ -21,6 +21,29 @@ inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
 namespace b2a {
 
+#if defined(B2A_HOST_WARP) && !defined(__CUDACC__)
+// Test-only (tests/sim): a 32-lane warp emulated on the host so that the not-gpu suite runs the W = 32
+// instantiations too.  The lanes are 32 cooperatively scheduled contexts of one thread; a warp barrier hands
+// control to the next lane (round robin, so a lane resumes after every other lane reached the barrier), and
+// shuffles / votes go through an exchange buffer between two barriers.
+struct HostWarp {
+  long long x[32];
+  void (*next_lane)(void*);  // provided by the harness: switch to the next unfinished lane
+  void* harness;
+};
+inline HostWarp* host_warp = nullptr;
+inline int host_lane = 0;
+inline void host_warp_sync() { host_warp->next_lane(host_warp->harness); }
+template <class Pick>
+inline long long host_warp_exchange(long long mine, Pick pick) {
+  host_warp->x[host_lane] = mine;
+  host_warp_sync();
+  const long long r = pick(host_warp->x);
+  host_warp_sync();
+  return r;
+}
+#endif
+
 constexpr int32_t MIN_SCORE = -858993459;  // mod.rs:174
 // A clip penalty at or below this can never win against a real path given the
 // range check in the engine (|any S| <= 2^27): treated as "dead" (SURVEY 3.2).

@@ -75,6 +75,14 @@ struct LaneCtx {
 
 #if defined(__CUDA_ARCH__)
 #define B2A_SHFL_UP(v, G) __shfl_up_sync(0xffffffffu, (v), 1, (G))
+#elif defined(B2A_HOST_WARP) && !defined(__CUDACC__)
+// tests/sim: the value of the lane below inside a group of G lanes (own value for the group's first lane)
+inline int32_t host_shfl_up_group(int32_t v, int G) {
+  if (!host_warp) return v;
+  const int me = host_lane;
+  return (int32_t)host_warp_exchange(v, [&](const long long* x) { return (me % G) ? x[me - 1] : x[me]; });
+}
+#define B2A_SHFL_UP(v, G) host_shfl_up_group((v), (G))
 #else
 #define B2A_SHFL_UP(v, G) (v)
 #endif

@@ -1,13 +1,19 @@
 // CPU simulation harness for the kernel LOGIC (test tool, not a product path and
 // not a fallback: nothing in rust_bio_b200/ loads it).  It compiles the very same
-// per-lane code the GPU runs -- fill_lane<1,R,FLAGS> (b2a_fill.cuh, thread-per-pair
-// shape, which needs no warp shuffles) and walk_pair (b2a_walk.cuh) -- for the
-// host, stages a batch exactly as K0 does, and lets tests/test_sim_logic.py diff
-// the result against the oracle without a GPU.
+// per-lane code the GPU runs -- fill_lane<G,R,FLAGS> (b2a_fill.cuh), walk_pair (b2a_walk.cuh) and
+// the banded K4/K3 functions (b2a_banded.cuh) -- for the host, stages a batch exactly as K0 does, and
+// lets the not-gpu tests diff the result against the oracle without a GPU.  The thread-per-pair fill
+// shape (G = 1) needs no warp primitives and runs lane after lane; the shapes whose lanes exchange
+// values (G > 1 fill wavefront, the W = 32 banded kernels) run on 32 cooperatively scheduled contexts
+// that stand in for the lanes of one warp (B2A_HOST_WARP hooks in b2a_common.cuh).
+#define B2A_HOST_WARP 1
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <vector>
+
+#include <ucontext.h>
 
 #include "../../rust_bio_b200/csrc/b2a_fill.cuh"
 #include "../../rust_bio_b200/csrc/b2a_plan.h"
@@ -15,54 +21,127 @@
 
 using namespace b2a;
 
+// 32 cooperatively scheduled contexts of this thread stand in for the lanes of one warp (see HostWarp in
+// b2a_common.cuh): a barrier switches to the next unfinished lane, round robin.
+struct LaneFibers {
+  static constexpr int W = 32;
+  static constexpr size_t kStack = 512 * 1024;
+  ucontext_t main_ctx;
+  ucontext_t ctx[W];
+  std::vector<char> stacks;
+  bool done[W];
+  int cur = 0;
+  std::function<void(int)> body;
+  HostWarp hw;
+  static LaneFibers* self;
+
+  static void entry() {
+    LaneFibers* f = self;
+    f->body(f->cur);
+    f->done[f->cur] = true;
+    next_lane(f);
+  }
+  static void next_lane(void* p) {
+    LaneFibers* f = static_cast<LaneFibers*>(p);
+    const int from = f->cur;
+    int to = -1;
+    for (int d = 1; d <= W; ++d) {
+      const int cand = (from + d) % W;
+      if (!f->done[cand]) {
+        to = cand;
+        break;
+      }
+    }
+    if (to == from) return;  // the only lane left: its barrier is a no-op
+    if (to < 0) {            // every lane finished
+      swapcontext(&f->ctx[from], &f->main_ctx);
+      return;
+    }
+    f->cur = to;
+    host_lane = to;
+    swapcontext(&f->ctx[from], &f->ctx[to]);
+  }
+  static void run(std::function<void(int)> body) {
+    LaneFibers f;
+    f.body = std::move(body);
+    f.stacks.resize(kStack * W);
+    f.hw.next_lane = &LaneFibers::next_lane;
+    f.hw.harness = &f;
+    self = &f;
+    host_warp = &f.hw;
+    for (int l = 0; l < W; ++l) {
+      f.done[l] = false;
+      getcontext(&f.ctx[l]);
+      f.ctx[l].uc_stack.ss_sp = f.stacks.data() + kStack * l;
+      f.ctx[l].uc_stack.ss_size = kStack;
+      f.ctx[l].uc_link = nullptr;
+      makecontext(&f.ctx[l], &LaneFibers::entry, 0);
+    }
+    f.cur = 0;
+    host_lane = 0;
+    swapcontext(&f.main_ctx, &f.ctx[0]);
+    host_warp = nullptr;
+    self = nullptr;
+  }
+};
+LaneFibers* LaneFibers::self = nullptr;
+
+
 namespace {
 
-template <int R, int FLAGS>
+template <int G, int R, int FLAGS>
 void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int32_t* lut,
                 std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd, std::vector<uint8_t>& rows,
                 std::vector<uint8_t>& tb) {
-  constexpr int G = 1, P = 32, TBW = tbw_of(R);
-  for (int lane = 0; lane < 32; ++lane) {
-    LaneCtx<G> c;
-    c.sc = sc;
-    c.lut = lut;
-    c.ge4 = 4 * sc.gap_extend;
-    c.lut_base = 0;
-    c.one = 1;
-    c.only_strip = -1;
-    c.prog_mine = nullptr;
-    c.prog_prev = nullptr;
-    const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
-    c.xs = seqw;
-    c.ys = seqw + (size_t)G * blk.xwords * P;
-    c.g = lane;
-    c.l = 0;
-    c.lane = lane;
-    c.pi = lane;
-    const bool valid = (uint32_t)lane < blk.npairs;
-    c.m = valid ? (int32_t)p.pm[blk.first + lane] : (int32_t)blk.maxm;
-    c.n = valid ? (int32_t)p.pn[blk.first + lane] : (int32_t)blk.maxn;
-    c.maxn = (int32_t)blk.maxn;
-    c.maxm = (int32_t)blk.maxm;
-    c.nstrips = (int32_t)blk.nstrips;
-    c.K = (int32_t)blk.K;
-    c.rows_pad = (int32_t)blk.rows_pad;
-    c.uniform = blk.uniform != 0;
-    c.bnd = reinterpret_cast<int4*>(bnd.data() + blk.bnd_off);
-    c.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
-    c.tb = reinterpret_cast<uint4*>(tb.data() + blk.tb_off);
-    (void)TBW;
-    fill_lane<G, R, FLAGS>(c);
+  constexpr int P = 32 / G, TBW = tbw_of(R);
+  // one warp-task per `sub` (32/G pairs), set up like fill_kernel does
+  for (int sub = 0; sub < G; ++sub) {
+    auto lane_body = [&](int lane) {
+      LaneCtx<G> c;
+      c.sc = sc;
+      c.lut = lut;
+      c.ge4 = 4 * sc.gap_extend;
+      c.lut_base = 0;
+      c.one = 1;
+      c.only_strip = -1;
+      c.prog_mine = nullptr;
+      c.prog_prev = nullptr;
+      const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
+      c.xs = seqw + (size_t)sub * blk.xwords * P;
+      c.ys = seqw + (size_t)G * blk.xwords * P + (size_t)sub * blk.ywords * P;
+      c.g = lane / G;
+      c.l = lane % G;
+      c.lane = lane;
+      c.pi = sub * P + c.g;
+      const bool valid = (uint32_t)c.pi < blk.npairs;
+      c.m = valid ? (int32_t)p.pm[blk.first + c.pi] : 0;
+      c.n = valid ? (int32_t)p.pn[blk.first + c.pi] : 0;
+      c.maxn = (int32_t)blk.maxn;
+      c.maxm = (int32_t)blk.maxm;
+      c.nstrips = (int32_t)blk.nstrips;
+      c.K = (int32_t)blk.K;
+      c.rows_pad = (int32_t)blk.rows_pad;
+      c.uniform = blk.uniform != 0;
+      c.bnd = reinterpret_cast<int4*>(bnd.data() + blk.bnd_off);
+      c.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
+      c.tb = reinterpret_cast<uint4*>(tb.data() + blk.tb_off) + (size_t)sub * blk.nstrips * blk.K * TBW * 32;
+      fill_lane<G, R, FLAGS>(c);
+    };
+    if (G == 1) {
+      for (int lane = 0; lane < 32; ++lane) lane_body(lane);  // no lane talks to another one
+    } else {
+      LaneFibers::run(lane_body);  // the wavefront hands rows from lane to lane: lock-step
+    }
   }
 }
 
-template <int R>
+template <int G, int R>
 void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring& sc,
                    const int32_t* lut, std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd,
                    std::vector<uint8_t>& rows, std::vector<uint8_t>& tb) {
   constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
 #define SIM_CASE(F) \
-  case (F): fill_block<R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb); break;
+  case (F): fill_block<G, R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb); break;
   switch (flags) {
     SIM_CASE(0)
     SIM_CASE(F_TRACK_ROWS)
@@ -96,9 +175,9 @@ struct sim_scoring {
 
 // Same outputs as the engine: per pair score/xstart/xend/ystart/yend/n_ops/clip_len[4]/status and
 // ops (m+n+4 bytes per pair at ops + ops_off[p], alignment order).
-int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
+int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
                     const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len,
-                    uint64_t n_pairs, int R, int modebits /*1 general variant, 2 no packed trackers, 4 no LUT for MatchParams*/, int garbage, int32_t* score, uint32_t* xstart,
+                    uint64_t n_pairs, int G, int R, int modebits /*1 general variant, 2 no packed trackers, 4 no LUT for MatchParams*/, int garbage, int32_t* score, uint32_t* xstart,
                     uint32_t* xend, uint32_t* ystart, uint32_t* yend, uint32_t* n_ops,
                     uint32_t* clip_len, uint32_t* status, uint8_t* ops, const uint64_t* ops_off) {
   DevScoring sc{};
@@ -146,7 +225,8 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
     }
   }
   Plan p;
-  build_plan(p, x_len, y_len, n_pairs, 1, R, ~0ull);
+  build_plan(p, x_len, y_len, n_pairs, G, R, ~0ull);
+  const int P = 32 / G;
   const int64_t unit = std::max<int64_t>(maxabs, std::max<int64_t>(-(int64_t)sc.gap_open, -(int64_t)sc.gap_extend));
   const int64_t bound = ((int64_t)p.maxm + p.maxn + 2) * unit - (int64_t)sc.gap_open;
   int flags = scoring_flags(sc, bound, p.maxm, p.maxn);
@@ -161,23 +241,28 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   const uint8_t gb = (uint8_t)garbage;
   std::vector<uint8_t> seq(p.seq_bytes, 0), bnd(p.max_bnd, gb), rows(p.max_rows, gb),
       rowm(p.max_rowm, gb), tb(p.max_tb, gb), opsb(p.ops_bytes, 0);
-  // K0 equivalent: stage sequences as [task][word][pair] (G = 1: one task per block)
+  // K0 equivalent: stage sequences as [task][word][pair slot] (b2a_kernels.cuh pack_kernel)
   for (const Block& blk : p.blocks) {
     uint32_t* seqw = reinterpret_cast<uint32_t*>(seq.data() + blk.seq_off);
     for (uint32_t q = 0; q < blk.npairs; ++q) {
       const uint32_t orig = p.order[blk.first + q];
+      const uint32_t sub = q / P, slot = q % P;
+      uint32_t* xw = seqw + (size_t)sub * blk.xwords * P;
       for (uint32_t k = 0; k < x_len[orig]; ++k)
-        reinterpret_cast<uint8_t*>(&seqw[(k >> 2) * 32 + q])[k & 3] = codemap[blob[x_off[orig] + k]];
-      uint32_t* yw = seqw + (size_t)blk.xwords * 32;
+        reinterpret_cast<uint8_t*>(&xw[(k >> 2) * P + slot])[k & 3] = codemap[blob[x_off[orig] + k]];
+      uint32_t* yw = seqw + (size_t)G * blk.xwords * P + (size_t)sub * blk.ywords * P;
       for (uint32_t k = 0; k < y_len[orig]; ++k)
-        reinterpret_cast<uint8_t*>(&yw[(k >> 2) * 32 + q])[k & 3] = codemap[blob[y_off[orig] + k]];
+        reinterpret_cast<uint8_t*>(&yw[(k >> 2) * P + slot])[k & 3] = codemap[blob[y_off[orig] + k]];
     }
   }
   for (const Block& blk : p.blocks) {
-    switch (R) {
-      case 4: fill_dispatch<4>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
-      case 8: fill_dispatch<8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
-      case 16: fill_dispatch<16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+    switch (G * 100 + R) {
+      case 104: fill_dispatch<1, 4>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 108: fill_dispatch<1, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 116: fill_dispatch<1, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 416: fill_dispatch<4, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 808: fill_dispatch<8, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 3208: fill_dispatch<32, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       default: return -1;
     }
     for (uint32_t lane = 0; lane < blk.npairs; ++lane) {
@@ -185,24 +270,24 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
       PairView v;
       v.sc = sc;
       v.lut = lut_plain;
-      v.P = 32;
+      v.P = P;
       v.m = (int32_t)p.pm[sp];
       v.n = (int32_t)p.pn[sp];
       v.pi = (int32_t)lane;
-      v.G = 1;
+      v.G = G;
       v.R = R;
       v.TBW = (R + 3) / 4;
       v.nstrips = (int32_t)blk.nstrips;
       v.K = (int32_t)blk.K;
-      v.sub = (int32_t)lane / 32;
-      v.g = (int32_t)lane % 32;
+      v.sub = (int32_t)lane / P;
+      v.g = (int32_t)lane % P;
       v.packtrk = (flags & F_PACKTRK) ? 1 : 0;
       v.maxn = (int32_t)blk.maxn;
-      v.bnd_base = bnd_index(1, 0, (int32_t)lane, v.maxn);
-      v.bnd_stride = 32;
+      v.bnd_base = bnd_index(G, 0, (int32_t)lane, v.maxn);
+      v.bnd_stride = (int32_t)(bnd_index(G, 1, (int32_t)lane, v.maxn) - v.bnd_base);
       const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
-      v.xw = seqw + v.g;
-      v.yw = seqw + (size_t)blk.xwords * 32 + v.g;
+      v.xw = seqw + (size_t)v.sub * blk.xwords * P + v.g;
+      v.yw = seqw + (size_t)G * blk.xwords * P + (size_t)v.sub * blk.ywords * P + v.g;
       v.bnd = reinterpret_cast<const int4*>(bnd.data() + blk.bnd_off);
       v.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
       v.rows_pad = (int32_t)blk.rows_pad;
@@ -226,15 +311,21 @@ int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const u
   }
   return 0;
 }
+
+int sim_align_batch(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
+                    const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len, uint64_t n_pairs, int R,
+                    int modebits, int garbage, int32_t* score, uint32_t* xstart, uint32_t* xend, uint32_t* ystart,
+                    uint32_t* yend, uint32_t* n_ops, uint32_t* clip_len, uint32_t* status, uint8_t* ops,
+                    const uint64_t* ops_off) {
+  return sim_align_batch_g(mode, s, blob, x_off, x_len, y_off, y_len, n_pairs, 1, R, modebits, garbage, score, xstart,
+                           xend, ystart, yend, n_ops, clip_len, status, ops, ops_off);
+}
 }
 
 // ---------------------------------------------------------------------------------------------
 // Banded path: the device functions of b2a_banded.cuh (K4 band construction + K3 banded fill/walk)
 // compiled for the host, one pair at a time.
-#define B2A_HOST_WARP 1  // 32 host threads stand in for a warp when the W = 32 code is run here
 #include "../../rust_bio_b200/csrc/b2a_banded.cuh"
-#include <functional>
-#include <ucontext.h>
 
 extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* blob,
                                 const uint64_t* x_off, const uint32_t* x_len, const uint64_t* y_off,
@@ -359,70 +450,6 @@ extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t 
   return 0;
 }
 
-// 32 cooperatively scheduled contexts of this thread stand in for the lanes of one warp (see HostWarp in
-// b2a_banded.cuh): a barrier switches to the next unfinished lane, round robin.
-struct LaneFibers {
-  static constexpr int W = 32;
-  static constexpr size_t kStack = 512 * 1024;
-  ucontext_t main_ctx;
-  ucontext_t ctx[W];
-  std::vector<char> stacks;
-  bool done[W];
-  int cur = 0;
-  std::function<void(int)> body;
-  HostWarp hw;
-  static LaneFibers* self;
-
-  static void entry() {
-    LaneFibers* f = self;
-    f->body(f->cur);
-    f->done[f->cur] = true;
-    next_lane(f);
-  }
-  static void next_lane(void* p) {
-    LaneFibers* f = static_cast<LaneFibers*>(p);
-    const int from = f->cur;
-    int to = -1;
-    for (int d = 1; d <= W; ++d) {
-      const int cand = (from + d) % W;
-      if (!f->done[cand]) {
-        to = cand;
-        break;
-      }
-    }
-    if (to == from) return;  // the only lane left: its barrier is a no-op
-    if (to < 0) {            // every lane finished
-      swapcontext(&f->ctx[from], &f->main_ctx);
-      return;
-    }
-    f->cur = to;
-    host_lane = to;
-    swapcontext(&f->ctx[from], &f->ctx[to]);
-  }
-  static void run(std::function<void(int)> body) {
-    LaneFibers f;
-    f.body = std::move(body);
-    f.stacks.resize(kStack * W);
-    f.hw.next_lane = &LaneFibers::next_lane;
-    f.hw.harness = &f;
-    self = &f;
-    host_warp = &f.hw;
-    for (int l = 0; l < W; ++l) {
-      f.done[l] = false;
-      getcontext(&f.ctx[l]);
-      f.ctx[l].uc_stack.ss_sp = f.stacks.data() + kStack * l;
-      f.ctx[l].uc_stack.ss_size = kStack;
-      f.ctx[l].uc_link = nullptr;
-      makecontext(&f.ctx[l], &LaneFibers::entry, 0);
-    }
-    f.cur = 0;
-    host_lane = 0;
-    swapcontext(&f.main_ctx, &f.ctx[0]);
-    host_warp = nullptr;
-    self = nullptr;
-  }
-};
-LaneFibers* LaneFibers::self = nullptr;
 
 // The W = 32 instantiations of K4 and K3 (what the GPU runs) with 32 host contexts as the lanes of one warp.
 // Same interface and outputs as sim_banded_hinted_one; have_matches = 0 lets K4 find the matches itself.

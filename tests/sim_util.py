@@ -1,5 +1,6 @@
 """ctypes driver for tests/sim/libb2asim.so: the GPU kernels' per-lane logic compiled for the host
-(thread-per-pair shape).  A test tool for the not-gpu suite; the product never loads it."""
+(thread-per-pair shape lane after lane; the G > 1 fill shapes and the W = 32 banded kernels on 32 cooperatively
+scheduled contexts standing in for a warp).  A test tool for the not-gpu suite; the product never loads it."""
 import ctypes as C
 import os
 import subprocess
@@ -40,7 +41,7 @@ def lib():
     return _lib
 
 
-def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0, garbage=None, no_pack=0, no_lut=0):
+def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0, garbage=None, no_pack=0, no_lut=0, G=1):
     """Takes an oracle.OrcScoring (same layout). Returns dict of arrays + list of op lists."""
     s = SimScoring.from_buffer_copy(bytes(orc_scoring))
     blob = np.ascontiguousarray(blob, dtype=np.uint8)
@@ -57,14 +58,14 @@ def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force
     out["clip_len"] = np.zeros(4 * n, dtype=np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     if garbage is None:  # run with two different scratch fills and insist on identical results
-        a = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x00, no_pack, no_lut)
-        b = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x7F, no_pack, no_lut)
+        a = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x00, no_pack, no_lut, G)
+        b = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x7F, no_pack, no_lut, G)
         for k in a[0]:
             assert np.array_equal(a[0][k], b[0][k]), ("scratch-dependent result", k)
         assert a[1] == b[1], "scratch-dependent ops"
         return a
-    rc = lib().sim_align_batch(int(mode), C.byref(s), p(blob), p(x_off), p(x_len), p(y_off), p(y_len),
-                               C.c_uint64(n), int(R), int(force_general) | (2 if no_pack else 0) | (4 if no_lut else 0), int(garbage), p(out["score"]),
+    rc = lib().sim_align_batch_g(int(mode), C.byref(s), p(blob), p(x_off), p(x_len), p(y_off), p(y_len),
+                               C.c_uint64(n), int(G), int(R), int(force_general) | (2 if no_pack else 0) | (4 if no_lut else 0), int(garbage), p(out["score"]),
                                p(out["xstart"]), p(out["xend"]), p(out["ystart"]), p(out["yend"]),
                                p(out["n_ops"]), p(out["clip_len"]), p(out["status"]), p(ops), p(ops_off))
     assert rc == 0

@@ -109,3 +109,31 @@ def test_sim_blosum62_protein(oracle):
         ref, ref_ops = oracle_batch(oracle, mode, s, batch)
         got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=8)
         assert_same(got, ops, ref, ref_ops, batch, f"blosum62 {mode}")
+
+
+# The fill shapes whose lanes hand rows to each other (G lanes per pair, anti-diagonal wavefront, masked last
+# strips, the pair-major boundary row of the warp-per-pair shape): 32 host contexts in lock-step stand in for the
+# warp (tests/sim B2A_HOST_WARP), the same fill_lane<G,R,FLAGS> the GPU instantiates.
+WAVE_SHAPES = [(4, 16), (8, 8), (32, 8)]
+
+
+@pytest.mark.parametrize("G,R", WAVE_SHAPES)
+@pytest.mark.parametrize("mode", ["local", "global", "semiglobal"])
+def test_sim_wavefront_shapes_ragged(oracle, mode, G, R):
+    batch = synth.ragged_pairs(300 + G, 40, 1, 3 * G * R + 37)  # several strips, ragged last ones, tiny pairs too
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=4)
+    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=R, G=G)
+    assert_same(got, ops, ref, ref_ops, batch, f"wavefront {G}x{R} {mode}")
+
+
+@pytest.mark.parametrize("G,R", WAVE_SHAPES)
+def test_sim_wavefront_shapes_uniform_and_custom(oracle, G, R):
+    rng = np.random.default_rng(7 * G + R)
+    batch = synth.uniform_pairs(99, 0, 33, 2 * G * R + 5, 70)  # uniform block: the unmasked strip variant
+    pick = lambda: int(rng.choice([MIN, 0, -2, -9]))
+    s, _ = oracle.make_scoring(-3, -1, 2, -2, None, pick(), pick(), pick(), pick())
+    ref, ref_ops = oracle_batch(oracle, "custom", s, batch, threads=4)
+    for no_pack in (0, 1):
+        got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R, G=G, no_pack=no_pack)
+        assert_same(got, ops, ref, ref_ops, batch, f"wavefront custom {G}x{R} no_pack={no_pack}")

@@ -495,7 +495,6 @@ int32_t b2a_batch_run(b2a_engine* e) {
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
   const Plan& pl = e->plan;
   cudaStream_t st = e->stream;
-  const uint64_t n = e->n_pairs;
   e->launches = 0;
   uint32_t* ctl = e->d_ctl.as<uint32_t>();  // [0] bad symbol, [1] walk error, [2..] per-wave task counters
   CK(cudaMemsetAsync(ctl, 0, 256, st));
@@ -518,9 +517,6 @@ int32_t b2a_batch_run(b2a_engine* e) {
     ++e->launches;
   }
   CK(cudaEventRecord(e->ev[1], st));
-  float fill_ms = 0.f, walk_ms = 0.f;
-  (void)fill_ms;
-  (void)walk_ms;
   size_t wi = 0;
   for (const Wave& w : pl.waves) {
     const uint32_t nb = w.block_hi - w.block_lo;

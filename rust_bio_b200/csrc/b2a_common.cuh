@@ -30,10 +30,14 @@ struct HostWarp {
   long long x[32];
   void (*next_lane)(void*);  // provided by the harness: switch to the next unfinished lane
   void* harness;
+  void (*other_warp)(void*);  // or null: let another emulated warp run (a lane is polling a progress word)
 };
 inline HostWarp* host_warp = nullptr;
 inline int host_lane = 0;
 inline void host_warp_sync() { host_warp->next_lane(host_warp->harness); }
+inline void host_spin_yield() {
+  if (host_warp && host_warp->other_warp) host_warp->other_warp(host_warp->harness);
+}
 template <class Pick>
 inline long long host_warp_exchange(long long mine, Pick pick) {
   host_warp->x[host_lane] = mine;

@@ -83,8 +83,12 @@ inline int32_t host_shfl_up_group(int32_t v, int G) {
   return (int32_t)host_warp_exchange(v, [&](const long long* x) { return (me % G) ? x[me - 1] : x[me]; });
 }
 #define B2A_SHFL_UP(v, G) host_shfl_up_group((v), (G))
+#define B2A_SPIN_YIELD() host_spin_yield()
 #else
 #define B2A_SHFL_UP(v, G) (v)
+#endif
+#ifndef B2A_SPIN_YIELD
+#define B2A_SPIN_YIELD() ((void)0)
 #endif
 
 // ---- scaled/packed score domain of the fill ------------------------------------------------
@@ -348,6 +352,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
     if (piped && c.prog_prev && (int32_t)avail < col) {
       do {
         avail = ld_progress(c.prog_prev);
+        B2A_SPIN_YIELD();  // nothing on the device (tests/sim: let the producer's emulated warp run)
       } while ((int32_t)avail < col);
       fence_device();
     }
@@ -414,6 +419,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         if (piped && ((j & 15) == 0 || j == n)) {  // publish (release) every 16 columns and at the end
           fence_device();
           *reinterpret_cast<volatile uint32_t*>(c.prog_mine) = (uint32_t)j;
+          B2A_SPIN_YIELD();  // nothing on the device (tests/sim: the consumer's emulated warp gets a turn)
         }
       }
       in_s = sup;

@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -66,6 +67,7 @@ struct LaneFibers {
     f.body = std::move(body);
     f.stacks.resize(kStack * W);
     f.hw.next_lane = &LaneFibers::next_lane;
+    f.hw.other_warp = nullptr;
     f.hw.harness = &f;
     self = &f;
     host_warp = &f.hw;
@@ -85,6 +87,114 @@ struct LaneFibers {
   }
 };
 LaneFibers* LaneFibers::self = nullptr;
+
+// Several emulated warps at once, for the strip-pipelined fill: the lanes of a warp rotate at its barriers as in
+// LaneFibers; a lane that polls another warp's progress word lets the next warp run (other_warp hook), so a
+// consumer strip and the producer strip above it advance side by side like two resident warps.
+struct WarpSet {
+  static constexpr int W = 32;
+  static constexpr size_t kStack = 256 * 1024;
+  struct Warp {
+    ucontext_t ctx[W];
+    bool done[W];
+    int cur = 0, ndone = 0;
+    HostWarp hw;
+    std::function<void(int)> body;
+    std::vector<char> stacks;
+  };
+  std::vector<Warp*> warps;
+  int curw = 0;
+  ucontext_t main_ctx;
+  uint64_t idle_spins = 0;
+  static WarpSet* self;
+
+  static void entry() {
+    WarpSet* s = self;
+    Warp* w = s->warps[s->curw];
+    const int lane = w->cur;
+    w->body(lane);
+    w->done[lane] = true;
+    w->ndone += 1;
+    next_lane(s);
+  }
+  void enter(int nw) {  // continue warp nw at its current lane (never returns to a finished context)
+    curw = nw;
+    host_warp = &warps[nw]->hw;
+    host_lane = warps[nw]->cur;
+  }
+  // leave the running context for another warp that still has work; false if there is none
+  bool to_other_warp(ucontext_t* from) {
+    const int n = (int)warps.size();
+    for (int d = 1; d < n; ++d) {
+      const int cand = (curw + d) % n;
+      if (warps[cand]->ndone < W) {
+        enter(cand);
+        swapcontext(from, &warps[cand]->ctx[warps[cand]->cur]);
+        return true;
+      }
+    }
+    return false;
+  }
+  static void next_lane(void* p) {
+    WarpSet* s = static_cast<WarpSet*>(p);
+    Warp* w = s->warps[s->curw];
+    const int from = w->cur;
+    if (w->ndone == W) {  // this warp is finished: hand over for good
+      if (!s->to_other_warp(&w->ctx[from])) swapcontext(&w->ctx[from], &s->main_ctx);
+      return;
+    }
+    int to = -1;
+    for (int d = 1; d <= W; ++d) {
+      const int cand = (from + d) % W;
+      if (!w->done[cand]) {
+        to = cand;
+        break;
+      }
+    }
+    if (to == from) return;
+    w->cur = to;
+    host_lane = to;
+    swapcontext(&w->ctx[from], &w->ctx[to]);
+  }
+  static void other_warp(void* p) {
+    WarpSet* s = static_cast<WarpSet*>(p);
+    Warp* w = s->warps[s->curw];
+    if (!s->to_other_warp(&w->ctx[w->cur])) {
+      if (++s->idle_spins > (1ull << 26)) std::abort();  // polling with nobody left to publish: a deadlock
+    } else {
+      s->idle_spins = 0;
+    }
+  }
+  static void run(std::vector<std::function<void(int)>> bodies) {
+    WarpSet s;
+    for (auto& b : bodies) {
+      Warp* w = new Warp();
+      w->body = std::move(b);
+      w->stacks.resize(kStack * W);
+      w->hw.next_lane = &WarpSet::next_lane;
+      w->hw.other_warp = &WarpSet::other_warp;
+      w->hw.harness = &s;
+      for (int l = 0; l < W; ++l) {
+        w->done[l] = false;
+        getcontext(&w->ctx[l]);
+        w->ctx[l].uc_stack.ss_sp = w->stacks.data() + kStack * l;
+        w->ctx[l].uc_stack.ss_size = kStack;
+        w->ctx[l].uc_link = nullptr;
+        makecontext(&w->ctx[l], &WarpSet::entry, 0);
+      }
+      s.warps.push_back(w);
+    }
+    if (!s.warps.empty()) {
+      self = &s;
+      s.enter(0);
+      swapcontext(&s.main_ctx, &s.warps[0]->ctx[0]);
+      self = nullptr;
+      host_warp = nullptr;
+    }
+    for (Warp* w : s.warps) delete w;
+  }
+};
+WarpSet* WarpSet::self = nullptr;
 
 
 namespace {
@@ -135,13 +245,75 @@ void fill_block(const Plan& p, const Block& blk, const DevScoring& sc, const int
   }
 }
 
-template <int G, int R>
+// The warp-per-pair shape as the engine runs it: every (pair, strip) of the block is a task of its own warp, the
+// strips of a pair run side by side and hand the boundary row over through a progress word per task
+// (fill_kernel's strip tasks: only_strip, the staged x slice with its biased pointer, prog_mine / prog_prev).
+template <int R, int FLAGS>
+void fill_block_piped(const Plan& p, const Block& blk, const DevScoring& sc, const int32_t* lut,
+                      std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd, std::vector<uint8_t>& rows,
+                      std::vector<uint8_t>& tb) {
+  constexpr int G = 32, P = 1, TBW = tbw_of(R);
+  if (blk.nstrips == 0) return;
+  std::vector<uint32_t> progress((size_t)32 * blk.nstrips, 0u);
+  for (uint32_t sub = 0; sub < blk.npairs; ++sub) {  // padding pairs of the block have no tasks
+    std::vector<std::function<void(int)>> bodies;
+    std::vector<std::vector<uint32_t>> slices(blk.nstrips);
+    for (uint32_t strip = 0; strip < blk.nstrips; ++strip) {
+      const uint32_t task = sub * blk.nstrips + strip;
+      const uint32_t* seqw = reinterpret_cast<const uint32_t*>(seq.data() + blk.seq_off);
+      // what the kernel stages: G*R symbols of x for this strip, all of y
+      const uint32_t xoff_words = strip * G * R / 4;
+      slices[strip].assign(seqw + (size_t)sub * blk.xwords * P + xoff_words,
+                           seqw + (size_t)sub * blk.xwords * P + xoff_words + G * R / 4);
+      const uint32_t* xs_biased = slices[strip].data() - xoff_words;  // indexed by absolute row word
+      uint32_t* prog = progress.data();
+      bodies.push_back([&, task, strip, sub, xs_biased, prog, seqw](int lane) {
+        LaneCtx<G> c;
+        c.sc = sc;
+        c.lut = lut;
+        c.ge4 = 4 * sc.gap_extend;
+        c.lut_base = 0;
+        c.one = 1;
+        c.only_strip = (int32_t)strip;
+        c.prog_mine = prog + task;
+        c.prog_prev = strip > 0 ? prog + task - 1 : nullptr;
+        c.xs = xs_biased;
+        c.ys = seqw + (size_t)G * blk.xwords * P + (size_t)sub * blk.ywords * P;
+        c.g = 0;
+        c.l = lane;
+        c.lane = lane;
+        c.pi = (int32_t)sub;
+        c.m = (int32_t)p.pm[blk.first + sub];
+        c.n = (int32_t)p.pn[blk.first + sub];
+        c.maxn = (int32_t)blk.maxn;
+        c.maxm = (int32_t)blk.maxm;
+        c.nstrips = (int32_t)blk.nstrips;
+        c.K = (int32_t)blk.K;
+        c.rows_pad = (int32_t)blk.rows_pad;
+        c.uniform = blk.uniform != 0;
+        c.bnd = reinterpret_cast<int4*>(bnd.data() + blk.bnd_off);
+        c.rows = reinterpret_cast<int32_t*>(rows.data() + blk.rows_off);
+        c.tb = reinterpret_cast<uint4*>(tb.data() + blk.tb_off) + (size_t)sub * blk.nstrips * blk.K * TBW * 32;
+        fill_lane<G, R, FLAGS>(c);
+      });
+    }
+    // consumers first on odd pairs: they poll before their producer has run at all; producers yield at every
+    // publish, so the strips advance 16 columns at a time, side by side
+    if (sub & 1) std::reverse(bodies.begin(), bodies.end());
+    WarpSet::run(std::move(bodies));
+  }
+}
+
+template <int G, int R, bool PIPED = false>
 void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring& sc,
                    const int32_t* lut, std::vector<uint8_t>& seq, std::vector<uint8_t>& bnd,
                    std::vector<uint8_t>& rows, std::vector<uint8_t>& tb) {
   constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
-#define SIM_CASE(F) \
-  case (F): fill_block<G, R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb); break;
+#define SIM_CASE(F)                                                                         \
+  case (F):                                                                                 \
+    if constexpr (PIPED) fill_block_piped<R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb);     \
+    else fill_block<G, R, (F)>(p, blk, sc, lut, seq, bnd, rows, tb);                        \
+    break;
   switch (flags) {
     SIM_CASE(0)
     SIM_CASE(F_TRACK_ROWS)
@@ -177,7 +349,7 @@ struct sim_scoring {
 // ops (m+n+4 bytes per pair at ops + ops_off[p], alignment order).
 int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const uint64_t* x_off,
                     const uint32_t* x_len, const uint64_t* y_off, const uint32_t* y_len,
-                    uint64_t n_pairs, int G, int R, int modebits /*1 general variant, 2 no packed trackers, 4 no LUT for MatchParams*/, int garbage, int32_t* score, uint32_t* xstart,
+                    uint64_t n_pairs, int Gsel /* lanes per pair; 132 = 32 with strip-pipelined tasks */, int R, int modebits /*1 general variant, 2 no packed trackers, 4 no LUT for MatchParams*/, int garbage, int32_t* score, uint32_t* xstart,
                     uint32_t* xend, uint32_t* ystart, uint32_t* yend, uint32_t* n_ops,
                     uint32_t* clip_len, uint32_t* status, uint8_t* ops, const uint64_t* ops_off) {
   DevScoring sc{};
@@ -224,6 +396,8 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
       for (size_t k = 0; k < aa; ++k) lut[aa + k] = 4 * lut[k] + 3 - (4 * sc.gap_open + 1);
     }
   }
+  const bool piped = Gsel == 132;
+  const int G = piped ? 32 : Gsel;
   Plan p;
   build_plan(p, x_len, y_len, n_pairs, G, R, ~0ull);
   const int P = 32 / G;
@@ -256,13 +430,14 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
     }
   }
   for (const Block& blk : p.blocks) {
-    switch (G * 100 + R) {
+    switch ((piped ? 10000 : 0) + G * 100 + R) {
       case 104: fill_dispatch<1, 4>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 108: fill_dispatch<1, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 116: fill_dispatch<1, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 416: fill_dispatch<4, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 808: fill_dispatch<8, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 3208: fill_dispatch<32, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 13208: fill_dispatch<32, 8, true>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       default: return -1;
     }
     for (uint32_t lane = 0; lane < blk.npairs; ++lane) {

@@ -137,3 +137,21 @@ def test_sim_wavefront_shapes_uniform_and_custom(oracle, G, R):
     for no_pack in (0, 1):
         got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R, G=G, no_pack=no_pack)
         assert_same(got, ops, ref, ref_ops, batch, f"wavefront custom {G}x{R} no_pack={no_pack}")
+
+
+@pytest.mark.parametrize("mode", ["local", "global", "custom"])
+def test_sim_strip_pipelined_warp_per_pair(oracle, mode):
+    """The warp-per-pair shape as the engine schedules it: one emulated warp per (pair, strip) task, the strips of a
+    pair running side by side and handing the boundary row over through progress words (G=132 selects it)."""
+    rng = np.random.default_rng(len(mode))
+    batch = synth.ragged_pairs(500 + len(mode), 9, 200, 700)  # 1-3 strips of 256 rows, ragged block
+    clips = [int(rng.choice([MIN, 0, -4])) for _ in range(4)] if mode == "custom" else [MIN] * 4
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, *clips)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=4)
+    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=8, G=132)
+    assert_same(got, ops, ref, ref_ops, batch, f"strip-pipelined 32x8 {mode}")
+    # and a uniform block (the unmasked strip variant), long enough for several 16-column publishes
+    ubatch = synth.uniform_pairs(5, 0, 3, 600, 300)
+    ref, ref_ops = oracle_batch(oracle, mode, s, ubatch, threads=4)
+    got, ops = sim_util.align_batch(MODES[mode], s, *ubatch, R=8, G=132)
+    assert_same(got, ops, ref, ref_ops, ubatch, f"strip-pipelined uniform {mode}")

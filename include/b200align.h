@@ -119,7 +119,20 @@ typedef struct b2a_results {
   uint8_t* ops;        /* [ops_capacity] B2A_OP_* codes, alignment order */
   uint64_t ops_capacity;
   uint32_t* clip_len;  /* [4*n_pairs] lengths of the Xclip/Yclip ops of a pair, in order of appearance */
+  /* [n_pairs] B2A_PAIR_* per pair, or NULL.  The reference fails per CALL: a pair on which it would panic
+   * (mod.rs:905 "Dint expect this!", banded.rs walk on a corrupt cell, an asserting caller-supplied match list)
+   * or never return takes only that pair down.  With status == NULL such a pair fails the whole batch
+   * (B2A_E_RANGE / B2A_E_INVALID / B2A_E_CAPACITY); with a status array the batch succeeds, the pair's status is
+   * non-zero and its other outputs are score = B2A_MIN_SCORE, no ops. */
+  uint32_t* status;
 } b2a_results;
+
+enum {
+  B2A_PAIR_OK = 0,
+  B2A_PAIR_PANIC = 1,        /* the reference panics (or loops forever) on this pair */
+  B2A_PAIR_CAPACITY = 2,     /* banded: more k-mer matches than the engine's per-pair limit (2^22) */
+  B2A_PAIR_INVALID_HINT = 4  /* banded: caller-supplied matches/path the reference asserts on */
+};
 
 typedef struct b2a_stats {
   uint64_t cells;          /* sum of DP cells (m*n, or Band::num_cells for banded) */

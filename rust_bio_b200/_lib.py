@@ -52,7 +52,8 @@ class CBandHints(C.Structure):
 class CResults(C.Structure):
     _fields_ = [("score", C.c_void_p), ("xstart", C.c_void_p), ("xend", C.c_void_p),
                 ("ystart", C.c_void_p), ("yend", C.c_void_p), ("ops_off", C.c_void_p),
-                ("ops", C.c_void_p), ("ops_capacity", C.c_uint64), ("clip_len", C.c_void_p)]
+                ("ops", C.c_void_p), ("ops_capacity", C.c_uint64), ("clip_len", C.c_void_p),
+                ("status", C.c_void_p)]
 
 
 class CStats(C.Structure):

@@ -18,8 +18,8 @@ from typing import List, Optional, Sequence, Tuple
 
 from ._lib import MIN_SCORE, MODE_CUSTOM, MODE_GLOBAL, MODE_LOCAL, MODE_SEMIGLOBAL
 from .alignment import Alignment, AlignmentMode, AlignmentOperation
-from .engine import Engine, default_engine, pack_pairs
-from .pairwise import DEFAULT_ALIGNER_CAPACITY, MatchFunc, Scoring, _check_scoring
+from .engine import Engine, Results, default_engine, pack_pairs
+from .pairwise import DEFAULT_ALIGNER_CAPACITY, MatchFunc, Scoring, _alignments, _check_scoring
 
 MAX_CELLS = 5_000_000          # banded.rs:104
 DEFAULT_MATCH_SCORE = 2        # banded.rs:105
@@ -58,32 +58,22 @@ class Aligner:
             self._engine = default_engine(0)
         return self._engine
 
-    def _batch(self, mode: int, pairs: Sequence[Tuple[bytes, bytes]]) -> List[Alignment]:
+    def _batch(self, mode: int, pairs: Sequence[Tuple[bytes, bytes]], on_panic: str = "raise") -> List[Alignment]:
         batch = pack_pairs(pairs)
-        cs, keep = self.scoring.to_c(batch[0])
-        res = self.engine.align_batch_banded(mode, cs, self.k, self.w, batch)
-        out = []
-        for i, (x, y) in enumerate(pairs):
-            ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
-            refused = int(res.score[i]) == MIN_SCORE and not ops  # MAX_CELLS refusal, banded.rs:407-420
-            out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]), int(res.yend[i]),
-                                 int(res.xend[i]), 0 if refused else len(y), 0 if refused else len(x), ops,
-                                 AlignmentMode.Custom if refused else mode))
-        return out
+        cs, keep = self.scoring.to_c(batch)
+        res = Results(len(pairs), Engine.default_ops_capacity(batch), pair_status=True)
+        self.engine.align_batch_banded(mode, cs, self.k, self.w, batch, results=res)
+        # global/semiglobal/local overwrite .mode after custom() returns, refused or not (banded.rs:889-890)
+        return _alignments(res, pairs, mode, on_panic, banded=True)
 
-    def _batch_hinted(self, pairs, matches, paths=None, allowed_mismatches=None, use_lcskpp_union=False):
+    def _batch_hinted(self, pairs, matches, paths=None, allowed_mismatches=None, use_lcskpp_union=False,
+                      on_panic: str = "raise"):
         batch = pack_pairs(pairs)
-        cs, keep = self.scoring.to_c(batch[0])
-        res = self.engine.align_batch_banded_hinted(MODE_CUSTOM, cs, self.k, self.w, batch, matches, paths,
-                                                    allowed_mismatches, use_lcskpp_union)
-        out = []
-        for i, (x, y) in enumerate(pairs):
-            ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
-            refused = int(res.score[i]) == MIN_SCORE and not ops
-            out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]), int(res.yend[i]),
-                                 int(res.xend[i]), 0 if refused else len(y), 0 if refused else len(x), ops,
-                                 AlignmentMode.Custom))
-        return out
+        cs, keep = self.scoring.to_c(batch)
+        res = Results(len(pairs), Engine.default_ops_capacity(batch), pair_status=True)
+        self.engine.align_batch_banded_hinted(MODE_CUSTOM, cs, self.k, self.w, batch, matches, paths,
+                                              allowed_mismatches, use_lcskpp_union, results=res)
+        return _alignments(res, pairs, MODE_CUSTOM, on_panic, banded=True, result_mode=AlignmentMode.Custom)
 
     def visualize(self, alignment: Alignment, file=None) -> str:
         """banded.rs:1007-1030: the band of the LAST single-pair alignment ('x'), the alignment's path ('\\'), one
@@ -140,17 +130,17 @@ class Aligner:
     def custom_with_match_path_batch(self, pairs, matches, paths):
         return self._batch_hinted(pairs, [list(m) for m in matches], [list(p) for p in paths])
 
-    def custom_batch(self, pairs):
-        return self._batch(MODE_CUSTOM, pairs)
+    def custom_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_CUSTOM, pairs, on_panic)
 
-    def global_batch(self, pairs):
-        return self._batch(MODE_GLOBAL, pairs)
+    def global_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_GLOBAL, pairs, on_panic)
 
-    def semiglobal_batch(self, pairs):
-        return self._batch(MODE_SEMIGLOBAL, pairs)
+    def semiglobal_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_SEMIGLOBAL, pairs, on_panic)
 
-    def local_batch(self, pairs):
-        return self._batch(MODE_LOCAL, pairs)
+    def local_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_LOCAL, pairs, on_panic)
 
     def custom(self, x: bytes, y: bytes) -> Alignment:
         return self._batch(MODE_CUSTOM, [(x, y)])[0]

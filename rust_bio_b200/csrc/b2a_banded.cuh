@@ -1728,6 +1728,12 @@ __global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const Ban
                          prm.filter_clips != 0, prm.ops_scratch + prm.ops_off[p], o);
   }
   if (lane != 0) return;
+  if (o.status) {  // no alignment is reported for a pair the reference panics / hangs on (or that hit a capacity)
+    o.score = MIN_SCORE;
+    o.n_ops = 0;
+    o.xstart = o.xend = o.ystart = o.yend = 0;
+    o.clip[0] = o.clip[1] = o.clip[2] = o.clip[3] = 0;
+  }
   prm.score[p] = o.score;
   prm.xstart[p] = o.xstart;
   prm.xend[p] = o.xend;

@@ -115,6 +115,7 @@ struct b2a_engine {
     uint32_t* h_ctl = nullptr;     // pinned
     size_t h_cap = 0;
     std::vector<uint64_t> xoff, yoff;
+    std::vector<uint8_t> packed;  // the chunk's sequences gathered from a scattered caller blob
     uint64_t lo = 0, n = 0;
     bool busy = false;
   } slots[2];
@@ -276,7 +277,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   if (rc) return rc;
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
   const uint64_t n = pairs->n_pairs;
-  if (n > 0x7fffffffull) return e->fail(B2A_E_INVALID, "more than 2^31 pairs in one batch");
+  if (n > 0x7ffffffeull) return e->fail(B2A_E_INVALID, "more than 2^31 - 2 pairs in one batch");
   e->n_pairs = n;
   e->mode = mode;
 
@@ -302,8 +303,9 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   maxm = 0;
   maxn = 0;
   for (uint64_t p = 0; p < n; ++p) {
-    const uint64_t xe = pairs->x_off[p] + pairs->x_len[p], ye = pairs->y_off[p] + pairs->y_len[p];
-    if (xe > pairs->blob_bytes || ye > pairs->blob_bytes)
+    // offset + length may not wrap: compare each against what is left of the blob
+    const uint64_t bb = pairs->blob_bytes, xo = pairs->x_off[p], yo = pairs->y_off[p];
+    if (xo > bb || pairs->x_len[p] > bb - xo || yo > bb || pairs->y_len[p] > bb - yo)
       return e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
     maxm = std::max(maxm, pairs->x_len[p]);
     maxn = std::max(maxn, pairs->y_len[p]);
@@ -395,10 +397,10 @@ static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes) {
     CK(cudaGetLastError());
     size_t tmp = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->d_nops64.as<uint64_t>(), e->d_opsoff.as<uint64_t>(),
-                                     (int)(n + 1), st));
+                                     (int64_t)(n + 1), st));
     CK(e->d_scan.reserve(tmp + 16));
     CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_nops64.as<uint64_t>(),
-                                     e->d_opsoff.as<uint64_t>(), (int)(n + 1), st));
+                                     e->d_opsoff.as<uint64_t>(), (int64_t)(n + 1), st));
     // worst case every pair emits m+n+4 ops; size the dense buffer by the scratch size
     CK(e->d_opsdense.reserve(scratch_bytes + 16));
     const unsigned g2 = (unsigned)((n * 32 + 255) / 256);
@@ -428,19 +430,29 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   // shape + plan
   int G = 1, R = 16;
   choose_shape(e, maxm, maxn, n, &G, &R);
-  e->shape = find_shape(G, R);
-  if (!e->shape) return e->fail(B2A_E_INVALID, "no fill kernel for the requested shape");
   uint64_t budget = e->tb_budget;
   if (!budget) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
     budget = (uint64_t)((double)fr * 0.6);
   }
-  build_plan(e->plan, pairs->x_len, pairs->y_len, n, G, R, budget);
-  const Plan& pl = e->plan;
   const uint32_t lut_bytes = sc.alpha ? ((uint32_t)(sc.alpha * sc.alpha * 4 + 127) & ~127u) : 0u;
-  if (64 + lut_bytes + (uint64_t)FILL_WARPS * pl.smem_seq_bytes > kMaxStageSmem)
-    return e->fail(B2A_E_UNSUPPORTED, "sequences too long for on-chip staging with this fill shape");
+  for (int attempt = 0;; ++attempt) {
+    e->shape = find_shape(G, R);
+    if (!e->shape) return e->fail(B2A_E_INVALID, "no fill kernel for the requested shape");
+    build_plan(e->plan, pairs->x_len, pairs->y_len, n, G, R, budget);
+    if (64 + lut_bytes + (uint64_t)FILL_WARPS * e->plan.smem_seq_bytes <= kMaxStageSmem) break;
+    // Shapes with several pairs per warp stage 32/G whole (x, y) per warp; long sequences (a read against a
+    // 15 kb reference ...) only fit the warp-per-pair shape, which stages one strip of x and one y per warp
+    // (n up to ~50,000 symbols: 4 warps x (n + G*R + padding) bytes <= 200 KB).  Forced shapes are not replaced.
+    if ((e->tune_G && e->tune_R) || G == 32 || attempt > 0)
+      return e->fail(B2A_E_UNSUPPORTED, "sequences too long for on-chip staging with this fill shape");
+    G = 32;
+    const uint64_t rows = maxm > 1 ? maxm - 1 : 1;
+    const uint64_t pad16 = (rows + 511) / 512 * 512, pad8 = (rows + 255) / 256 * 256;
+    R = (pad16 * 100 <= pad8 * 112) ? 16 : 8;
+  }
+  const Plan& pl = e->plan;
 
   // device memory
   CK(e->d_xoff.reserve(n * 8 + 8));
@@ -626,6 +638,7 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
     CK(down(r->ystart, e->d_ys, n * 4));
     CK(down(r->yend, e->d_ye, n * 4));
     CK(down(r->clip_len, e->d_clip, n * 16));
+    CK(down(r->status, e->d_status, n * 4));
     uint64_t total = 0;
     if (r->ops_off) {
       CK(down(r->ops_off, e->d_opsoff, (n + 1) * 8));
@@ -643,10 +656,13 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
   CK(cudaStreamSynchronize(st));
   if (ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
   if (ctl[1] & 4u) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
-  if (ctl[1] & 2u) return e->fail(B2A_E_CAPACITY, "banded: more k-mer matches than the per-pair capacity");
-  if (ctl[1] & 8u)
-    return e->fail(B2A_E_INVALID, "banded: the reference panics on these caller-supplied matches/path (not strictly ascending, index out of range, or outside the matrix)");
-  if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move or never terminates (the reference panics / hangs here: mod.rs:905, banded.rs:777-831)");
+  // per-pair failures: reported per pair when the caller gave a status array, else they fail the batch
+  if (!(r && r->status)) {
+    if (ctl[1] & 2u) return e->fail(B2A_E_CAPACITY, "banded: more k-mer matches than the per-pair capacity");
+    if (ctl[1] & 8u)
+      return e->fail(B2A_E_INVALID, "banded: the reference panics on these caller-supplied matches/path (not strictly ascending, index out of range, or outside the matrix)");
+    if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move or never terminates (the reference panics / hangs here: mod.rs:905, banded.rs:777-831)");
+  }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->cells = e->plan.cells;
@@ -703,7 +719,7 @@ static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results*
   cudaError_t ce = cudaStreamSynchronize(c->stream);
   if (ce != cudaSuccess) return e->cuda_fail("pipeline: cudaStreamSynchronize", ce);
   if (sl.h_ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
-  if (sl.h_ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
+  if (sl.h_ctl[1] && !r->status) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
   const uint64_t total = sl.h_opsoff[sl.n];
   if (r->ops) {
     if (base + total > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for this batch");
@@ -801,24 +817,49 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
       break;
     }
     // the chunk's slice of the caller's blob, offsets rebased
-    uint64_t bmin = ~0ull, bmax = 0;
+    uint64_t bmin = ~0ull, bmax = 0, seq_sum = 0;
+    bool inside = true;
     for (uint64_t p = lo; p < hi; ++p) {
-      bmin = std::min(bmin, std::min(pairs->x_off[p], pairs->y_off[p]));
-      bmax = std::max(bmax, std::max(pairs->x_off[p] + pairs->x_len[p], pairs->y_off[p] + pairs->y_len[p]));
+      const uint64_t bb = pairs->blob_bytes, xo = pairs->x_off[p], yo = pairs->y_off[p];
+      if (xo > bb || pairs->x_len[p] > bb - xo || yo > bb || pairs->y_len[p] > bb - yo) {
+        inside = false;
+        break;
+      }
+      bmin = std::min(bmin, std::min(xo, yo));
+      bmax = std::max(bmax, std::max(xo + pairs->x_len[p], yo + pairs->y_len[p]));
+      seq_sum += (uint64_t)pairs->x_len[p] + pairs->y_len[p];
     }
-    if (bmax > pairs->blob_bytes) {
+    if (!inside) {
       rc = e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
       break;
     }
     if (bmin > bmax) bmin = bmax = 0;
     sl.xoff.resize(nc);
     sl.yoff.resize(nc);
-    for (uint64_t i = 0; i < nc; ++i) {
-      sl.xoff[i] = pairs->x_off[lo + i] - bmin;
-      sl.yoff[i] = pairs->y_off[lo + i] - bmin;
+    const uint8_t* chunk_blob = pairs->seq_blob + bmin;
+    uint64_t chunk_bytes = bmax - bmin;
+    if (chunk_bytes > 2 * seq_sum + (1ull << 20)) {
+      // the chunk's sequences are scattered over a much larger span of the caller's blob (e.g. all x, then all
+      // y): uploading the span would move most of the blob once per chunk, so gather them into a compact blob
+      uint64_t pos = 0;
+      sl.packed.resize(seq_sum + 32 * nc + 16);
+      for (uint64_t i = 0; i < nc; ++i) {
+        sl.xoff[i] = pos;
+        std::memcpy(sl.packed.data() + pos, pairs->seq_blob + pairs->x_off[lo + i], pairs->x_len[lo + i]);
+        pos += ((uint64_t)pairs->x_len[lo + i] + 15) & ~15ull;
+        sl.yoff[i] = pos;
+        std::memcpy(sl.packed.data() + pos, pairs->seq_blob + pairs->y_off[lo + i], pairs->y_len[lo + i]);
+        pos += ((uint64_t)pairs->y_len[lo + i] + 15) & ~15ull;
+      }
+      chunk_blob = sl.packed.data();
+      chunk_bytes = pos;
+    } else {
+      for (uint64_t i = 0; i < nc; ++i) {
+        sl.xoff[i] = pairs->x_off[lo + i] - bmin;
+        sl.yoff[i] = pairs->y_off[lo + i] - bmin;
+      }
     }
-    b2a_pairs sub{pairs->seq_blob + bmin, sl.xoff.data(), pairs->x_len + lo, sl.yoff.data(), pairs->y_len + lo,
-                  bmax - bmin, nc};
+    b2a_pairs sub{chunk_blob, sl.xoff.data(), pairs->x_len + lo, sl.yoff.data(), pairs->y_len + lo, chunk_bytes, nc};
     b2a_engine* ch = sl.eng;
     const double tc1 = now();
     // Alphabet: chunk 0 discovers it on the (then idle) device; later chunks reuse it optimistically so
@@ -854,6 +895,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     if (ce == cudaSuccess) ce = down(r->ystart ? r->ystart + lo : nullptr, ch->d_ys, nc * 4);
     if (ce == cudaSuccess) ce = down(r->yend ? r->yend + lo : nullptr, ch->d_ye, nc * 4);
     if (ce == cudaSuccess) ce = down(r->clip_len ? r->clip_len + 4 * lo : nullptr, ch->d_clip, nc * 16);
+    if (ce == cudaSuccess) ce = down(r->status ? r->status + lo : nullptr, ch->d_status, nc * 4);
     if (ce == cudaSuccess) ce = down(sl.h_opsoff, ch->d_opsoff, (nc + 1) * 8);
     if (ce != cudaSuccess) {
       rc = e->cuda_fail("pipeline: result D2H", ce);
@@ -1007,18 +1049,30 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
       CK(up(e->d_hpidx, hints->path_idx, tp * 4));
     }
   }
-  uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, 1u << 20);
-  const uint64_t k4_bytes = k4_slab_bytes(cap, short_max);
+  // Per-pair capacity of the k-mer match list.  The reference's find_kmer_matches has no limit (low-complexity
+  // sequences give up to O(m n) matches: a 60-nt homopolymer in both reads is 53 x 53 8-mer matches), so the
+  // capacity starts at a size that covers ordinary batches and a wave whose pairs overflow it is redone with
+  // eight times the capacity, up to kCapMax per pair (beyond that the pair reports B2A_PAIR_CAPACITY).
+  constexpr uint32_t kCapMax = 1u << 22;
+  uint32_t cap = (uint32_t)std::min<uint64_t>(cap64, kCapMax);
+  if (const char* env = getenv("B2A_BANDED_CAP")) {  // test knob: start from a tiny capacity
+    const long v = atol(env);
+    if (v > 0) cap = (uint32_t)std::min<long>(v, (long)kCapMax);
+  }
+  uint64_t k4_bytes = k4_slab_bytes(cap, short_max);
   uint64_t budget = e->tb_budget;
   if (!budget) {
     size_t fr = 0, tot = 0;
     CK(cudaMemGetInfo(&fr, &tot));
     budget = (uint64_t)((double)fr * 0.5);
   }
-  const uint64_t per_pair_k4 = k4_bytes + ((uint64_t)maxn + 1) * 8 + 64;
-  uint64_t wave = std::max<uint64_t>(1, (budget / 2) / per_pair_k4);
-  wave = std::min<uint64_t>(wave, std::max<uint64_t>(n, 1));
-  wave = std::min<uint64_t>(wave, 1u << 20);
+  auto wave_for = [&](uint64_t slab_bytes) {
+    const uint64_t per_pair_k4 = slab_bytes + ((uint64_t)maxn + 1) * 8 + 64;
+    uint64_t wv = std::max<uint64_t>(1, (budget / 2) / per_pair_k4);
+    wv = std::min<uint64_t>(wv, std::max<uint64_t>(n, 1));
+    return std::min<uint64_t>(wv, 1u << 20);
+  };
+  uint64_t wave = wave_for(k4_bytes);
 
   BandedParams bp{};
   bp.blob = e->d_blob.as<uint8_t>();
@@ -1068,9 +1122,12 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   float band_ms = 0.f, fill_ms = 0.f;
   uint64_t total_cells = 0;
   std::vector<uint64_t> h_cells, roff, foff;
+  std::vector<uint32_t> h_k4;
   cudaEvent_t ev0 = e->ev[0], ev1 = e->ev[1], ev2 = e->ev[2];
-  for (uint64_t lo = 0; lo < n; lo += wave) {
+  for (uint64_t lo = 0; lo < n;) {
     const uint32_t nw = (uint32_t)std::min<uint64_t>(wave, n - lo);
+    bp.cap_matches = cap;
+    bp.slab_stride = k4_bytes;
     roff.resize(nw);
     uint64_t rbytes = 0;
     for (uint32_t t = 0; t < nw; ++t) {
@@ -1094,12 +1151,22 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     ++e->launches;
     CK(cudaEventRecord(ev1, st));
     h_cells.resize(nw);
+    h_k4.resize(nw);
     CK(cudaMemcpyAsync(h_cells.data(), e->d_bcells.as<uint64_t>() + lo, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_k4.data(), e->d_bstatus.as<uint32_t>() + lo, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, ev0, ev1);
       band_ms += ms;
+    }
+    if (cap < kCapMax && std::find(h_k4.begin(), h_k4.end(), 1u) != h_k4.end()) {
+      // a pair of this wave has more matches than the slab holds: redo the wave (K4 is idempotent) with a
+      // larger capacity, in as many pairs as then fit the budget
+      cap = (uint32_t)std::min<uint64_t>((uint64_t)cap * 8, kCapMax);
+      k4_bytes = k4_slab_bytes(cap, short_max);
+      wave = wave_for(k4_bytes);
+      continue;
     }
     // K3 in sub-waves sized by the exact slab bytes
     uint32_t s0 = 0;
@@ -1135,6 +1202,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
       fill_ms += ms;
       s0 = s1;
     }
+    lo += nw;
   }
   CK(cudaEventRecord(e->ev[4], st));
   rc = compact_ops(e, ops_total);

@@ -609,6 +609,12 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
   uint8_t* ops_end = prm.ops_scratch + blk.ops_off + (size_t)(lane + 1) * cap;
   WalkOut o;
   walk_pair(v, prm.filter_clips != 0, ops_end, o);
+  if (o.status) {  // the reference panics on this pair (mod.rs:905): no alignment is reported for it
+    o.score = MIN_SCORE;
+    o.n_ops = 0;
+    o.xstart = o.xend = o.ystart = o.yend = 0;
+    o.clip[0] = o.clip[1] = o.clip[2] = o.clip[3] = 0;
+  }
   const uint32_t dst = prm.order[sp];
   prm.score[dst] = o.score;
   prm.xstart[dst] = o.xstart;

@@ -24,9 +24,28 @@ def shard_range(n_pairs: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def shard_batch(batch, world: int, rank: int):
+    """This rank's contiguous share of the pair list, with only the bytes it needs: the blob is cut to the
+    span its sequences cover (offsets rebased), or gathered into a compact blob when they are scattered over
+    a much larger span (e.g. a blob laid out as all x, then all y)."""
     blob, x_off, x_len, y_off, y_len = batch
     lo, hi = shard_range(len(x_len), world, rank)
-    return (blob, x_off[lo:hi].copy(), x_len[lo:hi].copy(), y_off[lo:hi].copy(), y_len[lo:hi].copy()), lo, hi
+    xo, xl, yo, yl = x_off[lo:hi].copy(), x_len[lo:hi].copy(), y_off[lo:hi].copy(), y_len[lo:hi].copy()
+    if hi <= lo:
+        return (blob[:0], xo, xl, yo, yl), lo, hi
+    bmin = int(min(xo.min(), yo.min()))
+    bmax = int(max((xo + xl.astype(np.uint64)).max(), (yo + yl.astype(np.uint64)).max()))
+    need = int(xl.astype(np.uint64).sum() + yl.astype(np.uint64).sum())
+    if bmax - bmin > 2 * need + (1 << 20):
+        pad = lambda v: (v.astype(np.uint64) + np.uint64(15)) // np.uint64(16) * np.uint64(16)
+        sizes = np.stack([pad(xl), pad(yl)], axis=1).reshape(-1)
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        out = np.zeros(int(offs[-1]) + 16, dtype=np.uint8)
+        nxo, nyo = offs[0:-1:2].copy(), offs[1::2].copy()
+        for i in range(hi - lo):
+            out[int(nxo[i]):int(nxo[i]) + int(xl[i])] = blob[int(xo[i]):int(xo[i]) + int(xl[i])]
+            out[int(nyo[i]):int(nyo[i]) + int(yl[i])] = blob[int(yo[i]):int(yo[i]) + int(yl[i])]
+        return (out, nxo, xl, nyo, yl), lo, hi
+    return (blob[bmin:bmax], xo - np.uint64(bmin), xl, yo - np.uint64(bmin), yl), lo, hi
 
 
 def record_stride(max_m: int, max_n: int) -> int:

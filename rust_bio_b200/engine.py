@@ -31,7 +31,8 @@ def pack_pairs(pairs) -> Batch:
 class Results:
     """Host outputs of one batch (numpy arrays; pass pinned arrays via `out=` for speed)."""
 
-    def __init__(self, n_pairs: int, ops_capacity: int, out: Optional[Dict[str, np.ndarray]] = None):
+    def __init__(self, n_pairs: int, ops_capacity: int, out: Optional[Dict[str, np.ndarray]] = None,
+                 pair_status: bool = False):
         mk = lambda name, shape, dt: (out[name] if out and name in out else np.zeros(shape, dtype=dt))
         self.n_pairs = n_pairs
         self.score = mk("score", n_pairs, np.int32)
@@ -42,9 +43,13 @@ class Results:
         self.ops_off = mk("ops_off", n_pairs + 1, np.uint64)
         self.ops = mk("ops", max(1, ops_capacity), np.uint8)
         self.clip_len = mk("clip_len", 4 * max(1, n_pairs), np.uint32)
+        # per-pair B2A_PAIR_* codes: requested with pair_status=True (else a pair on which the reference would
+        # panic fails the whole batch, include/b200align.h)
+        self.status = mk("status", max(1, n_pairs), np.uint32) if pair_status else None
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         self.c = CResults(p(self.score), p(self.xstart), p(self.xend), p(self.ystart), p(self.yend),
-                          p(self.ops_off), p(self.ops), len(self.ops), p(self.clip_len))
+                          p(self.ops_off), p(self.ops), len(self.ops), p(self.clip_len),
+                          p(self.status) if pair_status else None)
 
     def ops_of(self, i: int):
         """[(code, clip_len)] of pair i in alignment order."""

@@ -94,8 +94,10 @@ class Scoring:
         return self._clip(yclip_suffix=penalty)
 
     # -- C ABI view --------------------------------------------------------------------------
-    def to_c(self, blob: Optional[np.ndarray] = None):
-        """-> (CScoring, keepalive). Closures are tabulated over the symbols present (mod.rs:221-228)."""
+    def to_c(self, batch=None):
+        """-> (CScoring, keepalive).  `batch` = (blob, x_off, x_len, y_off, y_len) (or a bare array of sequence
+        bytes).  Closures are tabulated over the symbols present in the SEQUENCES (mod.rs:221-228: the
+        reference only ever calls match_fn on sequence bytes) -- not over the blob's padding bytes."""
         keep = []
         cs = CScoring(self.gap_open, self.gap_extend, self.xclip_prefix, self.xclip_suffix,
                       self.yclip_prefix, self.yclip_suffix, 0, 0, 0, None, None, 0)
@@ -111,7 +113,7 @@ class Scoring:
                 table = _scores.matrix_table256(fn.matrix_name)
                 alpha = np.frombuffer(_MATRIX_ALPHABET, dtype=np.uint8).copy()
             else:
-                syms = np.unique(blob) if blob is not None and len(blob) else np.zeros(1, np.uint8)
+                syms = _symbols_present(batch)
                 table = _scores.tabulate(fn, syms.tolist())
                 alpha = syms.astype(np.uint8)
             table = np.ascontiguousarray(table, dtype=np.int32)
@@ -122,6 +124,49 @@ class Scoring:
             if self.match_scores is not None:
                 cs.match_score, cs.mismatch_score = self.match_scores
         return cs, keep
+
+
+def _symbols_present(batch) -> np.ndarray:
+    """Sorted distinct bytes of the sequences of a batch (padding between sequences is not looked at)."""
+    if batch is None:
+        return np.zeros(0, np.uint8)
+    if isinstance(batch, np.ndarray):
+        return np.unique(batch)
+    blob, x_off, x_len, y_off, y_len = batch
+    if len(x_len) == 0 or len(blob) == 0:
+        return np.zeros(0, np.uint8)
+    starts = np.concatenate([x_off, y_off]).astype(np.int64)
+    lens = np.concatenate([x_len, y_len]).astype(np.int64)
+    delta = np.zeros(len(blob) + 1, dtype=np.int32)
+    np.add.at(delta, starts, 1)
+    np.add.at(delta, starts + lens, -1)
+    inside = np.cumsum(delta[:-1]) > 0
+    return np.nonzero(np.bincount(blob[inside], minlength=256))[0].astype(np.uint8)
+
+
+_PAIR_STATUS_TEXT = {1: "the reference panics (or never returns) on this pair: mod.rs:905 / banded.rs:777-831",
+                     2: "banded: more k-mer matches than the engine's per-pair limit",
+                     4: "banded: the reference panics on these caller-supplied matches/path"}
+
+
+def _alignments(res: Results, pairs, mode: int, on_panic: str, banded: bool = False, result_mode=None) -> list:
+    """Results -> [Alignment]; per-pair failures (Results.status) raise or become None."""
+    from ._lib import B2AError
+    out = []
+    for i, (x, y) in enumerate(pairs):
+        st = int(res.status[i]) if res.status is not None else 0
+        if st:
+            if on_panic == "raise":
+                raise B2AError(-4 if st == 1 else (-5 if st == 2 else -1), f"pair {i}: " + _PAIR_STATUS_TEXT.get(st, str(st)))
+            out.append(None)
+            continue
+        ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
+        # banded.rs:407-420: a band above MAX_CELLS returns the empty alignment with xlen = ylen = 0
+        refused = banded and int(res.score[i]) == MIN_SCORE and not ops
+        out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]), int(res.yend[i]),
+                             int(res.xend[i]), 0 if refused else len(y), 0 if refused else len(x), ops,
+                             mode if result_mode is None else result_mode))
+    return out
 
 
 def _check_scoring(s: Scoring):
@@ -171,28 +216,26 @@ class Aligner:
         return self._engine
 
     # batch forms ------------------------------------------------------------------------------
-    def _batch(self, mode: int, pairs: Sequence[Tuple[bytes, bytes]]) -> List[Alignment]:
+    def _batch(self, mode: int, pairs: Sequence[Tuple[bytes, bytes]], on_panic: str = "raise") -> List[Alignment]:
+        """on_panic: the reference panics per CALL (mod.rs:905); a batch either raises for the first such pair
+        ("raise", what a loop over the reference's per-pair calls does) or returns None in its place ("none")."""
         batch = pack_pairs(pairs)
-        cs, keep = self.scoring.to_c(batch[0])
-        res = self.engine.align_batch(mode, cs, batch)
-        out = []
-        for i, (x, y) in enumerate(pairs):
-            ops = [AlignmentOperation(c, l) for c, l in res.ops_of(i)]
-            out.append(Alignment(int(res.score[i]), int(res.ystart[i]), int(res.xstart[i]),
-                                 int(res.yend[i]), int(res.xend[i]), len(y), len(x), ops, mode))
-        return out
+        cs, keep = self.scoring.to_c(batch)
+        res = self.engine.align_batch(mode, cs, batch, results=Results(len(pairs), Engine.default_ops_capacity(batch),
+                                                                       pair_status=True))
+        return _alignments(res, pairs, mode, on_panic)
 
-    def custom_batch(self, pairs):
-        return self._batch(MODE_CUSTOM, pairs)
+    def custom_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_CUSTOM, pairs, on_panic)
 
-    def global_batch(self, pairs):
-        return self._batch(MODE_GLOBAL, pairs)
+    def global_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_GLOBAL, pairs, on_panic)
 
-    def semiglobal_batch(self, pairs):
-        return self._batch(MODE_SEMIGLOBAL, pairs)
+    def semiglobal_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_SEMIGLOBAL, pairs, on_panic)
 
-    def local_batch(self, pairs):
-        return self._batch(MODE_LOCAL, pairs)
+    def local_batch(self, pairs, on_panic: str = "raise"):
+        return self._batch(MODE_LOCAL, pairs, on_panic)
 
     # per-pair forms, mod.rs:591, 925, 954, 986
     def custom(self, x: bytes, y: bytes) -> Alignment:

@@ -64,6 +64,7 @@ pub mod alignment {
             ops: *mut u8,
             ops_capacity: u64,
             clip_len: *mut u32,
+            status: *mut u32, // per-pair B2A_PAIR_* codes; null = a failing pair fails the batch (-> panic, like the reference)
         }
         #[link(name = "b200align")]
         extern "C" {
@@ -345,7 +346,9 @@ pub mod alignment {
                     ops: ops.as_mut_ptr(),
                     ops_capacity: cap + 1,
                     clip_len: clip.as_mut_ptr(),
+                    status: std::ptr::null_mut(),
                 };
+                let is_banded = banded.is_some();
                 let rc = match banded {
                     None => unsafe { b2a_align_batch(self.engine, mode, &cs, &cp, &mut res, std::ptr::null_mut()) },
                     Some(BandedCall { k, w, matches: None, .. }) => unsafe {
@@ -417,14 +420,18 @@ pub mod alignment {
                                 }
                             })
                             .collect();
+                        // banded.rs:407-420: a band above MAX_CELLS returns the empty alignment (score MIN_SCORE,
+                        // xlen = ylen = 0); global/semiglobal/local then overwrite only `.mode` (banded.rs:889-890)
+                        let operations: Vec<AlignmentOperation> = operations;
+                        let refused = is_banded && score[p] == MIN_SCORE && operations.is_empty();
                         Alignment {
                             score: score[p],
                             ystart: ys[p] as usize,
                             xstart: xs[p] as usize,
                             yend: ye[p] as usize,
                             xend: xe[p] as usize,
-                            ylen: pairs[p].1.len(),
-                            xlen: pairs[p].0.len(),
+                            ylen: if refused { 0 } else { pairs[p].1.len() },
+                            xlen: if refused { 0 } else { pairs[p].0.len() },
                             operations,
                             mode: amode,
                         }

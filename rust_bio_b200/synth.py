@@ -71,3 +71,58 @@ def ragged_pairs(seed: int, n_pairs: int, max_m: int, max_n: int, alphabet: byte
     lens = np.stack([x_len, y_len], axis=1).reshape(-1).astype(np.uint64)
     offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
     return blob, offs[0::2].copy(), x_len, offs[1::2].copy(), y_len
+
+
+def mutated_window_pairs(base: int, first_pair: int, n_pairs: int, m: int, n: int, sub: float = 0.05,
+                         ins: float = 0.005, dele: float = 0.005, alphabet: bytes = DNA, align: int = 16):
+    """The C4 generator: y uniform over `alphabet` (seed BASE+2p+1); x = a window of y at a random
+    start with `sub` substitutions, `ins` insertions and `dele` deletions per source position, cut to exactly m
+    symbols.  All randomness is splitmix64 of seed BASE+2p: draw 0 picks the window start, draws 1..L the event of
+    each source position, draws L+1..2L the inserted / substituted symbol.  Vectorised over pairs."""
+    A = len(alphabet)
+    alpha = np.frombuffer(alphabet, dtype=np.uint8)
+    code_of = np.zeros(256, dtype=np.int64)
+    code_of[alpha] = np.arange(A)
+    L = m + max(32, m // 8)
+    if n < L:
+        raise ValueError("y must be at least m + max(32, m/8) long")
+    ms = -(-m // align) * align
+    ns = -(-n // align) * align
+    stride = ms + ns
+    blob = np.zeros((n_pairs, stride), dtype=np.uint8)
+    step = max(1, (1 << 21) // (2 * L + 1))
+    for lo in range(0, n_pairs, step):
+        hi = min(n_pairs, lo + step)
+        p = np.arange(first_pair + lo, first_pair + hi, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            ys = random_seqs(np.uint64(base) + np.uint64(2) * p + np.uint64(1), n, alphabet)
+            z = draws(np.uint64(base) + np.uint64(2) * p, 2 * L + 1)
+        c = hi - lo
+        start = ((z[:, 0] >> np.uint64(32)) % np.uint64(n - L + 1)).astype(np.int64)
+        src = np.take_along_axis(ys, start[:, None] + np.arange(L, dtype=np.int64)[None, :], axis=1)
+        u = (z[:, 1:L + 1] >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+        r = ((z[:, L + 1:] >> np.uint64(32)) % np.uint64(A)).astype(np.int64)
+        is_sub = u < sub
+        is_ins = (u >= sub) & (u < sub + ins)
+        is_del = (u >= sub + ins) & (u < sub + ins + dele)
+        # a substitution always changes the symbol: code + 1 + (r mod (A-1))
+        sub_sym = alpha[(code_of[src] + 1 + r % max(1, A - 1)) % A]
+        sym = np.where(is_sub, sub_sym, src)
+        cnt = 1 + is_ins.astype(np.int64) - is_del.astype(np.int64)
+        pos = np.cumsum(cnt, axis=1) - cnt
+        xs = np.zeros((c, m + 2), dtype=np.uint8)
+        rows = np.broadcast_to(np.arange(c)[:, None], (c, L))
+        keep = (~is_del) & (pos + is_ins < m)
+        xs[rows[keep], (pos + is_ins)[keep]] = sym[keep]
+        insm = is_ins & (pos < m)
+        xs[rows[insm], pos[insm]] = alpha[r[insm]]
+        total = pos[:, -1] + cnt[:, -1]
+        if np.any(total < m):  # cannot happen for sane rates (needs > L - m deletions); pad to stay well-formed
+            for q in np.nonzero(total < m)[0]:
+                xs[q, int(total[q]):m] = alpha[0]
+        blob[lo:hi, :m] = xs[:, :m]
+        blob[lo:hi, ms:ms + n] = ys
+    x_off = np.arange(n_pairs, dtype=np.uint64) * np.uint64(stride)
+    y_off = x_off + np.uint64(ms)
+    return (blob.reshape(-1), x_off, np.full(n_pairs, m, dtype=np.uint32), y_off,
+            np.full(n_pairs, n, dtype=np.uint32))

@@ -256,3 +256,118 @@ def test_band_ranges_and_visualize(eng, oracle):
     x, y = pairs[3]
     want, _ = oracle.band_create("custom", s_o, 6, 4, x, y)
     assert [(int(a), int(b)) for a, b in eng.banded_band_ranges(3, len(y))] == want
+
+
+# --------------------------------------------------------------------------------------------------------
+# Round 2: the named C4 generator at the SURVEY 8d sample size, band ranges included, and the fuzz target's
+# path re-scoring property on banded results
+
+def test_c4_named_generator_2000_pairs_with_ranges_and_rescoring(eng, oracle):
+    """BASELINE config 4 with its own generator (synth.mutated_window_pairs: y uniform, x = mutated window of
+    y): 2,000 pairs of 500 x 10,000, banded semiglobal k=32 w=32 -- alignments, Band::num_cells, the band
+    ranges of sampled pairs, and (independent of the oracle) every path re-scored."""
+    from parity_util import rescore_path
+    from rust_bio_b200 import synth
+    batch = synth.mutated_window_pairs(synth.BASES["C4"], 0, 2000, 500, 10000)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    cs = _c_scoring(-5, -1, 1, -1)
+    ref, rops, roff, _, ref_cells = oracle.banded_align_batch("semiglobal", s, 32, 32, *batch, threads=8)
+    res = eng.align_batch_banded(MODES["semiglobal"], cs, 32, 32, batch)
+    assert int(eng.stats.cells) == ref_cells
+    for f in ("score", "xstart", "xend", "ystart", "yend"):
+        assert np.array_equal(getattr(res, f).astype(np.int64), ref[f].astype(np.int64)), f
+    blob, xo, xl, yo, yl = batch
+    for p in range(2000):
+        want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+        got = res.ops_of(p)
+        assert got == want, p
+        if int(res.score[p]) == MIN:  # refused pair (no 32-mer match -> full matrix > MAX_CELLS)
+            assert got == []
+            continue
+        x = bytes(blob[int(xo[p]):int(xo[p]) + 500])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + 10000])
+        f = {k: getattr(res, k)[p] for k in ("xstart", "xend", "ystart", "yend")}
+        assert rescore_path(x, y, got, f, "semiglobal", -5, -1, lambda a, b: 1 if a == b else -1,
+                            (MIN, MIN, 0, 0)) == int(res.score[p]), p
+    for p in (0, 7, 1999):
+        x = bytes(blob[int(xo[p]):int(xo[p]) + 500])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + 10000])
+        want, _ = oracle.band_create("semiglobal", s, 32, 32, x, y)
+        assert [(int(a), int(b)) for a, b in eng.banded_band_ranges(p, 10000)] == want
+
+
+@pytest.mark.parametrize("mode", ["global", "semiglobal", "local", "custom"])
+def test_banded_paths_rescore_to_their_score(eng, oracle, mode):
+    """fuzz/fuzz_targets/banded_aligner.rs:10-56 on the banded engine: recomputed path score == reported score."""
+    from parity_util import rescore_path
+    rng = np.random.default_rng(91)
+    for trial in range(3):
+        go, ge = int(rng.choice([-1, -5, -7])), int(rng.choice([0, -1, -2]))
+        ge = max(ge, go)  # opening costs at least as much as extending (the fuzz target's model)
+        ma, mi = int(rng.choice([1, 2, 3])), int(rng.choice([-1, -3]))
+        clips = (MIN,) * 4
+        if mode == "custom":
+            clips = tuple(int(rng.choice([MIN, 0, -2, -9])) for _ in range(4))
+        batch = _mutated_window_batch(700 + trial, 300, 90, 260, sub=0.06, indel=0.03)
+        s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips, has_match_scores=1)
+        ref, *_ = oracle.banded_align_batch(mode, s, 8, 6, *batch, threads=8)
+        if np.any(ref["n_ops"] == 0xFFFFFFFF):
+            continue  # the reference panics on a pair of this batch
+        res = eng.align_batch_banded(MODES[mode], _c_scoring(go, ge, ma, mi, clips), 8, 6, batch)
+        blob, xo, xl, yo, yl = batch
+        eff = {"global": (MIN,) * 4, "semiglobal": (MIN, MIN, 0, 0), "local": (0, 0, 0, 0)}.get(mode, clips)
+        for p in range(len(xl)):
+            x = bytes(blob[int(xo[p]):int(xo[p]) + int(xl[p])])
+            y = bytes(blob[int(yo[p]):int(yo[p]) + int(yl[p])])
+            f = {k: getattr(res, k)[p] for k in ("xstart", "xend", "ystart", "yend")}
+            sc = rescore_path(x, y, res.ops_of(p), f, mode, go, ge, lambda a, b: ma if a == b else mi, eff)
+            assert sc == int(res.score[p]) == int(ref["score"][p]), (mode, trial, p)
+
+
+def test_per_pair_status_instead_of_failing_the_batch(eng, oracle):
+    """The reference fails per CALL (an assert on unsorted caller matches, banded.rs:313-321 -> sparse.rs:212-217):
+    with b2a_results.status the batch succeeds, exactly that pair is flagged, every other pair is bit-exact;
+    without it the batch is refused as before."""
+    from rust_bio_b200._lib import B2AError
+    from rust_bio_b200.banded import Aligner, find_kmer_matches
+    from rust_bio_b200.pairwise import Scoring
+    from test_sim_banded import _window_pair
+    rng = np.random.default_rng(99)
+    s_o, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    aligner = Aligner.with_scoring(Scoring.from_scores(-5, -1, 1, -1), 6, 4, engine=eng)
+    pairs = [_window_pair(rng, 70, 180) for _ in range(40)]
+    matches = [find_kmer_matches(x, y, 6) for x, y in pairs]
+    bad = [7, 23]
+    for b in bad:
+        assert len(matches[b]) >= 2
+        matches[b] = matches[b][::-1]
+    got = aligner.custom_with_matches_batch(pairs, matches, on_panic="none")
+    for i, ((x, y), m, a) in enumerate(zip(pairs, matches, got)):
+        if i in bad:
+            assert a is None
+            continue
+        f, ops, _ = oracle.banded_align_hinted(s_o, 6, 4, x, y, m)
+        assert a is not None and a.score == f["score"] and [(o.code, o.len) for o in a.operations] == ops, i
+    with pytest.raises(B2AError, match="pair 7.*reference panics"):
+        aligner.custom_with_matches_batch(pairs, matches)
+
+
+def test_kmer_match_capacity_grows_instead_of_failing(eng, oracle, monkeypatch):
+    """Low-complexity sequences give O(m n) k-mer matches (sparse::find_kmer_matches has no limit); a wave whose
+    pairs overflow the per-pair slab is redone with a larger one.  B2A_BANDED_CAP starts the capacity tiny."""
+    rng = np.random.default_rng(5)
+    pairs = []
+    for _ in range(24):
+        x = bytearray(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 150)].tobytes())
+        y = bytearray(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 150)].tobytes())
+        x[40:100] = b"A" * 60  # a 60-nt homopolymer in both reads: 53 x 53 8-mer matches
+        y[70:130] = b"A" * 60
+        pairs.append((bytes(x), bytes(y)))
+    from rust_bio_b200.engine import pack_pairs
+    batch = pack_pairs(pairs)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    assert len(oracle.find_kmer_matches(pairs[0][0], pairs[0][1], 8)) >= 53 * 53
+    monkeypatch.setenv("B2A_BANDED_CAP", "64")
+    _compare(eng, oracle, "semiglobal", _c_scoring(-5, -1, 1, -1), s, 8, 6, batch, "capacity retry (cap 64)")
+    monkeypatch.delenv("B2A_BANDED_CAP")
+    _compare(eng, oracle, "semiglobal", _c_scoring(-5, -1, 1, -1), s, 8, 6, batch, "default capacity")

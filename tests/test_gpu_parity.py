@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from golden_util import load_cases, parse_ops, scoring_fields
-from parity_util import MODES, assert_same, oracle_batch
+from parity_util import MODES, assert_same, oracle_batch, rescore_path
 
 pytestmark = pytest.mark.gpu
 MIN = -858993459
@@ -378,3 +378,131 @@ def test_error_paths(eng):
     cs, _ = _c_scoring(-5, -1, 1 << 20, -1)
     with pytest.raises(B2AError, match="RANGE"):
         eng.align_batch(MODES["local"], cs, synth.uniform_pairs(1, 0, 4, 2000, 2000))
+
+
+# --------------------------------------------------------------------------------------------------------
+# Round 2: the kernel variants and sizes that had never run against the oracle on hardware
+
+def _blosum62():
+    from rust_bio_b200 import scores
+    return scores.matrix_table256("blosum62"), bytes(range(65, 91)) + b"*"
+
+
+def test_c5_shape_8_pairs_10k_x_10k_blosum62_local(eng, oracle):
+    """BASELINE config 5 (8 pairs): 10,000 x 10,000 protein, BLOSUM62, gap_open -10, gap_extend -1,
+    local (the reference's own BLOSUM62-local example, mod.rs:41-54, 1323-1337).  m, n > 4095, so K1 runs its
+    explicit (value, index) trackers (no F_PACKTRK) and K2's decode_boundary its unpacked branch."""
+    from rust_bio_b200 import synth
+    table, alpha = _blosum62()
+    batch = synth.uniform_pairs(synth.BASES["C5"], 0, 8, 10000, 10000, alphabet=synth.PROTEIN)
+    s, keep1 = oracle.make_scoring(-10, -1, 0, 0, table)
+    ref, ref_ops = oracle_batch(oracle, "local", s, batch, threads=8)
+    cs, keep2 = _c_scoring(-10, -1, 0, 0, table=table, alphabet=alpha)
+    got, ops = _engine_result(eng, "local", cs, batch)  # the shape choose_shape() picks for C5
+    assert eng.stats.fill_lanes_per_pair == 32
+    assert_same(got, ops, ref, ref_ops, batch, "C5 local blosum62 auto shape")
+    blob, xo, xl, yo, yl = batch
+    for p in range(8):  # and independent of the oracle: the path re-scores to the score
+        x = bytes(blob[int(xo[p]):int(xo[p]) + 10000])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + 10000])
+        f = {k: got[k][p] for k in ("xstart", "xend", "ystart", "yend")}
+        assert rescore_path(x, y, ops[p], f, "local", -10, -1, lambda a, b: int(table[a * 256 + b])) == int(got["score"][p])
+
+
+@pytest.mark.parametrize("G,R", [(8, 16), (32, 16), (32, 8), (4, 16)])
+@pytest.mark.parametrize("lut", [True, False], ids=["lut", "matchparams_wide_alphabet"])
+def test_unpacked_tracker_variants_4200(eng, oracle, G, R, lut):
+    """m, n > 4095 in every mode: the fill_kernel<G,R,FLAGS> instantiations without F_PACKTRK
+    (b2a_fill_inst.cu: 0, TRACK_ROWS, ALL, ALL|RELU, each with and without F_LUT).  A 100-symbol alphabet keeps
+    MatchParams on its compare/select path (no LUT above 64 symbols)."""
+    from rust_bio_b200 import synth
+    alphabet = b"ACGT" if lut else bytes(range(33, 133))
+    rng = np.random.default_rng(G * 100 + R + (1 if lut else 0))
+    pairs = []
+    for m, n in [(4200, 4200), (4100, 4301), (4333, 4097), (4099, 5000)]:
+        a = np.frombuffer(alphabet, dtype=np.uint8)
+        x = a[rng.integers(0, len(a), m)]
+        y = a[rng.integers(0, len(a), n)]
+        if not lut:  # plant matches so that the 100-symbol case is not all mismatches
+            k = min(m, n) - 50
+            y = y.copy()
+            y[20:20 + k:3] = x[30:30 + k:3]
+        pairs.append((bytes(x), bytes(y)))
+    from rust_bio_b200.engine import pack_pairs
+    batch = pack_pairs(pairs)
+    cases = [("global", (MIN,) * 4), ("semiglobal", (MIN,) * 4), ("local", (MIN,) * 4),
+             ("custom", (-3, -4, -2, -5)), ("custom", (MIN, 0, MIN, -1)), ("custom", (0, MIN, 0, MIN))]
+    eng.set_tuning(G, R)
+    try:
+        for mode, clips in cases:
+            s, _ = oracle.make_scoring(-5, -1, 2, -1, None, *clips)
+            ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=4)
+            cs, keep = _c_scoring(-5, -1, 2, -1, clips)
+            got, ops = _engine_result(eng, mode, cs, batch)
+            assert eng.stats.fill_lanes_per_pair == G
+            assert_same(got, ops, ref, ref_ops, batch, f"4200 {mode} {clips} G={G} R={R} lut={lut}")
+    finally:
+        eng.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("mode", ["global", "semiglobal", "local", "custom"])
+def test_paths_rescore_to_their_score_every_mode(eng, mode):
+    """The fuzz target's property (fuzz/fuzz_targets/banded_aligner.rs:10-56), independent of the oracle, on
+    every pair of a batch, for every mode incl. custom clips: the returned path re-scores to the returned score."""
+    from rust_bio_b200 import synth
+    rng = np.random.default_rng(23)
+    for trial in range(4):
+        go, ge = int(rng.choice([0, -1, -2, -5, -6])), int(rng.choice([0, -1, -1, -2]))
+        ge = max(ge, go)  # the affine model the property is stated for: opening costs at least as much as extending
+        ma, mi = int(rng.choice([1, 2, 4])), int(rng.choice([-1, -3, -7]))
+        clips = (MIN, MIN, MIN, MIN)
+        if mode == "custom":
+            clips = tuple(int(rng.choice([MIN, 0, -1, -3, -7, -20])) for _ in range(4))
+        batch = synth.ragged_pairs(300 + trial, 2000, 150, 180, alphabet=b"AC" if trial % 2 else b"ACGT")
+        cs, keep = _c_scoring(go, ge, ma, mi, clips)
+        got, ops = _engine_result(eng, mode, cs, batch)
+        blob, xo, xl, yo, yl = batch
+        eff = {"global": (MIN,) * 4, "semiglobal": (MIN, MIN, 0, 0), "local": (0, 0, 0, 0)}.get(mode, clips)
+        for p in range(len(xl)):
+            x = bytes(blob[int(xo[p]):int(xo[p]) + int(xl[p])])
+            y = bytes(blob[int(yo[p]):int(yo[p]) + int(yl[p])])
+            f = {k: got[k][p] for k in ("xstart", "xend", "ystart", "yend")}
+            sc = rescore_path(x, y, ops[p], f, mode, go, ge, lambda a, b: ma if a == b else mi, eff)
+            assert sc == int(got["score"][p]), (mode, trial, p, clips)
+
+
+def test_c3_full_shape_1000_pairs_global_with_rescoring(eng, oracle):
+    """BASELINE config 3 parity sample (1,000 pairs of 1000x1000 global) on the automatic shape."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(synth.BASES["C3"], 0, 1000, 1000, 1000)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "global", s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    got, ops = _engine_result(eng, "global", cs, batch)
+    assert_same(got, ops, ref, ref_ops, batch, "C3 1000 pairs")
+    blob, xo, xl, yo, yl = batch
+    for p in range(0, 1000, 10):
+        x = bytes(blob[int(xo[p]):int(xo[p]) + 1000])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + 1000])
+        f = {k: got[k][p] for k in ("xstart", "xend", "ystart", "yend")}
+        assert rescore_path(x, y, ops[p], f, "global", -5, -1, lambda a, b: 1 if a == b else -1) == int(got["score"][p])
+
+
+def test_long_reference_falls_back_to_warp_per_pair_staging(eng, oracle):
+    """A read against a 15 kb reference (semiglobal): the 8-lanes-per-pair shape would stage 4 x 4 x (m + n)
+    bytes per CTA (> 200 KB); the engine falls back to the warp-per-pair shape instead of refusing."""
+    from rust_bio_b200 import synth
+    batch = synth.uniform_pairs(77, 0, 64, 100, 15000)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "semiglobal", s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    got, ops = _engine_result(eng, "semiglobal", cs, batch)
+    assert eng.stats.fill_lanes_per_pair == 32
+    assert_same(got, ops, ref, ref_ops, batch, "100 x 15000 semiglobal")
+    from rust_bio_b200._lib import B2AError
+    eng.set_tuning(8, 16)  # a forced shape is not replaced
+    try:
+        with pytest.raises(B2AError, match="UNSUPPORTED"):
+            eng.align_batch(MODES["semiglobal"], cs, batch)
+    finally:
+        eng.set_tuning(0, 0)

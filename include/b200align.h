@@ -162,9 +162,13 @@ int32_t b2a_engine_set_stream(b2a_engine* e, void* cuda_stream);
 /* Upper bound (bytes) on device scratch for traceback bit-vectors; larger
  * batches are processed in waves. 0 = default (60% of free HBM). */
 int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes);
-/* Force the fill-kernel shape (lanes per pair G in {1,2,4,8,16,32}, rows per
- * lane R in {4,8,12,16,20}); 0,0 = automatic. */
+/* Force the fill-kernel shape (lanes per pair G in {1,2,4,8,32}, rows per
+ * lane R in {8,16,20}: the built pairs are 1x8 1x16 1x20 2x16 2x20 4x16 8x16 8x20 32x8 32x16); 0,0 = automatic. */
 int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t rows_per_lane);
+
+/* K2 (row m, last-column fix-ups, traceback walk) runs one lane per pair (1) or one warp per pair (2);
+ * 0 = automatic: warp per pair for waves of up to 131,072 pairs.  Results are identical either way. */
+int32_t b2a_engine_set_walk(b2a_engine* e, int32_t mode);
 
 /* b2a_align_batch cuts batches of >= 262,144 pairs into `chunks` pieces that alternate between two
  * internal engines, so one chunk's copies and host planning overlap the other's kernels.
@@ -249,6 +253,17 @@ int32_t b2a_records_decode(const void* host_records, uint32_t stride_bytes, uint
  * into a buffer of that size and a single all-gather moves them. */
 int32_t b2a_batch_compact_bytes(b2a_engine* e, uint64_t* segment_bytes);
 int32_t b2a_batch_compact_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes);
+/* The same segment with a capacity the CALLER fixes (e.g. from the previous batch, or the bound
+ * 64 + 40 n + sum(m + n + 4)): nothing here waits for the batch or reads a size back, so ranks need no size
+ * agreement before the all-gather and the exchange of batch k can overlap the kernels of batch k + 1.  The header
+ * is written on the device: { n_pairs, ops_bytes produced, ops_bytes kept (<= capacity), 0... }; a segment whose
+ * ops did not fit is cut and says so (kept < produced) -- b2a_gathered_fetch refuses it (B2A_E_CAPACITY). */
+int32_t b2a_batch_compact_fixed(b2a_engine* e, void* dev_dst, uint64_t capacity_bytes);
+/* Reassembly on the rank that returns the results ("rank 0's copy is what the shim returns"):
+ * `dev_gathered` = n_segments segments of segment_bytes each, as all-gathered in DEVICE memory, in rank order.
+ * Copies every field straight into `results` (host memory, pinned for speed) in that order and builds ops_off. */
+int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t segment_bytes, uint32_t n_segments,
+                           b2a_results* results, uint64_t* n_pairs_total, uint64_t* d2h_bytes);
 /* Decode one gathered segment (host memory) into `results` starting at pair index `pair_base` and ops offset
  * `ops_base`; returns the segment's pair count and ops bytes.  ops_off[pair_base + i] is written for every
  * pair of the segment (the caller writes the final ops_off[n_total]). */

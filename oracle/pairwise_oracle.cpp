@@ -20,6 +20,8 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <pthread.h>
+#include <sched.h>
 #include <thread>
 #include <vector>
 
@@ -408,6 +410,17 @@ struct FullAligner {
 
 }  // namespace
 
+// CPUs in this process's affinity mask (what nproc reports), in ascending order
+static std::vector<int> orc_allowed_cpus() {
+  std::vector<int> out;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(set), &set) == 0)
+    for (int c = 0; c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &set)) out.push_back(c);
+  return out;
+}
+
 extern "C" {
 
 // One pair. ops must hold m+n+4 entries. Returns 0, or -1 on the reference's panic path.
@@ -432,9 +445,19 @@ double orc_align_batch(int mode, const orc_scoring* scoring, const uint8_t* blob
                        const uint64_t* ops_off, int threads) {
   if (threads < 1) threads = 1;
   auto t0 = std::chrono::steady_clock::now();
+  // the CPUs this process may run on (cgroup / taskset aware); thread t is pinned to one of them so that the
+  // baseline does not depend on how the scheduler happens to migrate 128 threads (1.2 vs 6.5 GCUPS
+  // between two boxes with the same thread count)
+  std::vector<int> cpus = orc_allowed_cpus();
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; ++t) {
     pool.emplace_back([=]() {
+      if (!cpus.empty() && threads > 1) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(cpus[(size_t)t % cpus.size()], &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+      }
       FullAligner a;
       a.sc = *scoring;
       std::vector<Op> v;
@@ -451,6 +474,9 @@ double orc_align_batch(int mode, const orc_scoring* scoring, const uint8_t* blob
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+int orc_hardware_threads() {
+  const std::vector<int> cpus = orc_allowed_cpus();
+  return cpus.empty() ? (int)std::thread::hardware_concurrency() : (int)cpus.size();
+}
 
 }  // extern "C"

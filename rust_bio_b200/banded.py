@@ -110,8 +110,8 @@ class Aligner:
         """banded.rs:313-321: `matches` = sorted [(xpos, ypos), ...]."""
         return self._batch_hinted([(x, y)], [list(matches)])[0]
 
-    def custom_with_matches_batch(self, pairs, matches):
-        return self._batch_hinted(pairs, [list(m) for m in matches])
+    def custom_with_matches_batch(self, pairs, matches, on_panic: str = "raise"):
+        return self._batch_hinted(pairs, [list(m) for m in matches], on_panic=on_panic)
 
     def custom_with_expanded_matches(self, x: bytes, y: bytes, matches, allowed_mismatches: Optional[int],
                                      use_lcskpp_union: bool) -> Alignment:
@@ -120,15 +120,16 @@ class Aligner:
         return self._batch_hinted([(x, y)], [list(matches)], None, allowed_mismatches, use_lcskpp_union)[0]
 
     def custom_with_expanded_matches_batch(self, pairs, matches, allowed_mismatches: Optional[int],
-                                           use_lcskpp_union: bool):
-        return self._batch_hinted(pairs, [list(m) for m in matches], None, allowed_mismatches, use_lcskpp_union)
+                                           use_lcskpp_union: bool, on_panic: str = "raise"):
+        return self._batch_hinted(pairs, [list(m) for m in matches], None, allowed_mismatches, use_lcskpp_union,
+                                  on_panic=on_panic)
 
     def custom_with_match_path(self, x: bytes, y: bytes, matches, path) -> Alignment:
         """banded.rs:391-401: the band follows matches[path[0]], matches[path[1]], ... as given."""
         return self._batch_hinted([(x, y)], [list(matches)], [list(path)])[0]
 
-    def custom_with_match_path_batch(self, pairs, matches, paths):
-        return self._batch_hinted(pairs, [list(m) for m in matches], [list(p) for p in paths])
+    def custom_with_match_path_batch(self, pairs, matches, paths, on_panic: str = "raise"):
+        return self._batch_hinted(pairs, [list(m) for m in matches], [list(p) for p in paths], on_panic=on_panic)
 
     def custom_batch(self, pairs, on_panic: str = "raise"):
         return self._batch(MODE_CUSTOM, pairs, on_panic)

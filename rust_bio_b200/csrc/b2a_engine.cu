@@ -58,7 +58,7 @@ struct DevBuf {
 const FillLaunch kFillShapes[] = {
     {1, 16, launch_fill_1_16}, {1, 8, launch_fill_1_8},   {1, 20, launch_fill_1_20},
     {2, 16, launch_fill_2_16}, {2, 20, launch_fill_2_20}, {4, 16, launch_fill_4_16},
-    {8, 16, launch_fill_8_16}, {32, 8, launch_fill_32_8}, {32, 16, launch_fill_32_16},
+    {8, 16, launch_fill_8_16}, {8, 20, launch_fill_8_20}, {32, 8, launch_fill_32_8}, {32, 16, launch_fill_32_16},
 };
 
 const FillLaunch* find_shape(int G, int R) {
@@ -68,6 +68,7 @@ const FillLaunch* find_shape(int G, int R) {
 }
 
 constexpr uint32_t kMaxStageSmem = 200 * 1024;  // of the 227 KB a CTA may use
+constexpr uint64_t kWarpWalkMaxPairs = 131072;  // waves up to this many pairs use the warp-per-pair K2
 constexpr int kMaxAlpha = 64;
 
 }  // namespace
@@ -83,6 +84,8 @@ struct b2a_engine {
   std::vector<uint32_t> band_ylen;
   std::string err;
   int tune_G = 0, tune_R = 0;
+  int walk_mode = 0;  // 0 automatic, 1 one lane per pair, 2 one warp per pair
+  bool last_walk_warp = false;
   uint64_t tb_budget = 0;
 
   // batch state
@@ -101,6 +104,8 @@ struct b2a_engine {
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
       d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
       d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx;
+  uint32_t* h_nops = nullptr;  // pinned staging of b2a_gathered_fetch
+  uint64_t h_nops_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> wave_ev;  // 3 per wave: fill start, fill stop / walk start, walk stop
   uint32_t launches = 0;
@@ -217,6 +222,7 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
     sl.eng = nullptr;
   }
   cudaStreamSynchronize(e->stream);
+  if (e->h_nops) cudaFreeHost(e->h_nops);
   DevBuf* bufs[] = {&e->d_blob, &e->d_xoff, &e->d_xlen, &e->d_yoff, &e->d_ylen, &e->d_order, &e->d_pm,
                     &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
                     &e->d_opsscratch, &e->d_lut, &e->d_codemap, &e->d_ctl, &e->d_score, &e->d_xs,
@@ -249,6 +255,13 @@ int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes) {
 int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks) {
   if (!e) return B2A_E_INVALID;
   e->pipe_chunks = chunks < 2 ? 0 : (chunks > 64 ? 64 : chunks);
+  return B2A_OK;
+}
+
+int32_t b2a_engine_set_walk(b2a_engine* e, int32_t mode) {
+  if (!e) return B2A_E_INVALID;
+  if (mode < 0 || mode > 2) return e->fail(B2A_E_INVALID, "walk mode must be 0 (automatic), 1 (lane per pair) or 2 (warp per pair)");
+  e->walk_mode = mode;
   return B2A_OK;
 }
 
@@ -599,10 +612,20 @@ int32_t b2a_batch_run(b2a_engine* e) {
     ++e->launches;
     CK(cudaEventRecord(e->wave_ev[3 * wi + 1], st));
     if (!fuse) {
-      const unsigned wgrid = (nb * 32 + 127) / 128;
-      walk_kernel<<<wgrid, 128, 0, st>>>(wp);
+      // K2 shape: one lane per pair is the bandwidth-efficient form for large batches of reads (a warp's 32
+      // pairs share every cache line); one WARP per pair cuts the per-pair latency chain (prefix-maximum passes,
+      // prefetched walk) and is what small / medium batches and long sequences need (b2a_walk.cuh).
+      const uint64_t wave_pairs = (uint64_t)nb * 32;
+      const bool warp_walk = e->walk_mode == 2 || (e->walk_mode == 0 && wave_pairs <= kWarpWalkMaxPairs);
+      if (warp_walk) {
+        walk_warp_kernel<<<nb * 8, 128, 0, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
+      } else {
+        const unsigned wgrid = (nb * 32 + 127) / 128;
+        walk_kernel<<<wgrid, 128, 0, st>>>(wp);
+      }
       CK(cudaGetLastError());
       ++e->launches;
+      e->last_walk_warp = warp_walk;
     }
     CK(cudaEventRecord(e->wave_ev[3 * wi + 2], st));
     ++wi;
@@ -801,6 +824,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     }
     sl.eng->tune_G = e->tune_G;
     sl.eng->tune_R = e->tune_R;
+    sl.eng->walk_mode = e->walk_mode;
     sl.eng->tb_budget = e->tb_budget;
     sl.eng->pipe_chunks = 0;
     if (sl.h_cap < nc + 1) {
@@ -1308,6 +1332,106 @@ int32_t b2a_batch_compact_into(b2a_engine* e, void* dev_dst, uint64_t dst_bytes)
   if (n) CK(cudaMemcpyAsync(dst + off, e->d_clip.p, 16 * n, cudaMemcpyDeviceToDevice, st));
   off += 16 * n;
   if (total) CK(cudaMemcpyAsync(dst + off, e->d_opsdense.p, total, cudaMemcpyDeviceToDevice, st));
+  return B2A_OK;
+}
+
+// header of a fixed-capacity segment, written on the device: {n_pairs, ops_bytes (as produced), ops_bytes_kept}
+__global__ void compact_header_kernel(uint64_t* hdr, const uint64_t* ops_off, uint64_t n, uint64_t cap_ops) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const uint64_t total = n ? ops_off[n] : 0;
+    hdr[0] = n;
+    hdr[1] = total;
+    hdr[2] = total < cap_ops ? total : cap_ops;
+    for (int k = 3; k < 8; ++k) hdr[k] = 0;
+  }
+}
+
+int32_t b2a_batch_compact_fixed(b2a_engine* e, void* dev_dst, uint64_t capacity_bytes) {
+  if (!e || !dev_dst) return B2A_E_INVALID;
+  if (!e->ran) return e->fail(B2A_E_STATE, "compact results requested before b2a_batch_run");
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  const uint64_t n = e->n_pairs;
+  if (capacity_bytes < 64 + 40 * n) return e->fail(B2A_E_CAPACITY, "compact segment capacity below 64 + 40 n_pairs");
+  // never read past the dense ops buffer: the kept part is also bounded by what the buffer holds
+  const uint64_t cap_ops = std::min<uint64_t>(capacity_bytes - 64 - 40 * n, e->d_opsdense.cap);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(dev_dst);
+  cudaStream_t st = e->stream;
+  compact_header_kernel<<<1, 32, 0, st>>>(reinterpret_cast<uint64_t*>(dst), e->d_opsoff.as<uint64_t>(), n, cap_ops);
+  CK(cudaGetLastError());
+  const DevBuf* arrays[6] = {&e->d_score, &e->d_xs, &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops};
+  uint64_t off = 64;
+  for (const DevBuf* a : arrays) {
+    if (n) CK(cudaMemcpyAsync(dst + off, a->p, 4 * n, cudaMemcpyDeviceToDevice, st));
+    off += 4 * n;
+  }
+  if (n) CK(cudaMemcpyAsync(dst + off, e->d_clip.p, 16 * n, cudaMemcpyDeviceToDevice, st));
+  off += 16 * n;
+  if (cap_ops && n) CK(cudaMemcpyAsync(dst + off, e->d_opsdense.p, cap_ops, cudaMemcpyDeviceToDevice, st));
+  return B2A_OK;
+}
+
+int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t segment_bytes, uint32_t n_segments,
+                           b2a_results* r, uint64_t* n_pairs_total, uint64_t* d2h_bytes) {
+  if (!e || !dev_gathered || !r || segment_bytes < 64) return B2A_E_INVALID;
+  if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  cudaStream_t st = e->stream;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(dev_gathered);
+  std::vector<uint64_t> hdr((size_t)n_segments * 8);
+  CK(cudaMemcpy2DAsync(hdr.data(), 64, base, segment_bytes, 64, n_segments, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint64_t pairs = 0, ops = 0, moved = (uint64_t)n_segments * 64;
+  for (uint32_t g = 0; g < n_segments; ++g) {
+    const uint64_t n = hdr[8 * g], total = hdr[8 * g + 1];
+    const uint64_t kept = hdr[8 * g + 2] ? hdr[8 * g + 2] : total;  // segments of b2a_batch_compact_into carry 0 there
+    if (n > (segment_bytes - 64) / 40 || kept > segment_bytes - 64 - 40 * n)
+      return e->fail(B2A_E_INVALID, "gathered segment header does not fit its segment");
+    if (kept < total) return e->fail(B2A_E_CAPACITY, "a gathered segment was cut: its capacity was below its ops bytes");
+    pairs += n;
+    ops += total;
+  }
+  if (r->ops && ops > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for the gathered batch");
+  // n_ops of every segment lands in one staging array (pinned, engine-owned); everything else goes straight
+  // to its place in the caller's arrays
+  if (e->h_nops_cap < pairs + 1) {
+    if (e->h_nops) cudaFreeHost(e->h_nops);
+    e->h_nops = nullptr;
+    e->h_nops_cap = 0;
+    if (cudaMallocHost(&e->h_nops, (pairs + 1) * 4) != cudaSuccess) return e->fail(B2A_E_CUDA, "cudaMallocHost failed");
+    e->h_nops_cap = pairs + 1;
+  }
+  uint64_t pb = 0, ob = 0;
+  for (uint32_t g = 0; g < n_segments; ++g) {
+    const uint64_t n = hdr[8 * g], total = hdr[8 * g + 1];
+    const uint8_t* seg = base + (uint64_t)g * segment_bytes + 64;
+    auto down = [&](void* dst, uint64_t off, uint64_t bytes) -> cudaError_t {
+      if (!dst || !bytes) return cudaSuccess;
+      moved += bytes;
+      return cudaMemcpyAsync(dst, seg + off, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CK(down(r->score ? r->score + pb : nullptr, 0, 4 * n));
+    CK(down(r->xstart ? r->xstart + pb : nullptr, 4 * n, 4 * n));
+    CK(down(r->xend ? r->xend + pb : nullptr, 8 * n, 4 * n));
+    CK(down(r->ystart ? r->ystart + pb : nullptr, 12 * n, 4 * n));
+    CK(down(r->yend ? r->yend + pb : nullptr, 16 * n, 4 * n));
+    CK(down(e->h_nops + pb, 20 * n, 4 * n));
+    CK(down(r->clip_len ? r->clip_len + 4 * pb : nullptr, 24 * n, 16 * n));
+    CK(down(r->ops ? r->ops + ob : nullptr, 40 * n, total));
+    pb += n;
+    ob += total;
+  }
+  CK(cudaStreamSynchronize(st));
+  if (r->ops_off) {
+    uint64_t acc = 0;
+    for (uint64_t p = 0; p < pairs; ++p) {
+      r->ops_off[p] = acc;
+      acc += e->h_nops[p];
+    }
+    r->ops_off[pairs] = acc;
+    if (acc != ops) return e->fail(B2A_E_INVALID, "gathered segments: n_ops do not add up to the ops bytes");
+  }
+  if (r->status) std::memset(r->status, 0, pairs * 4);  // segments only carry completed batches
+  if (n_pairs_total) *n_pairs_total = pairs;
+  if (d2h_bytes) *d2h_bytes = moved;
   return B2A_OK;
 }
 

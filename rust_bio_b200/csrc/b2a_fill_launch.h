@@ -25,6 +25,7 @@ B2A_DECLARE_FILL(2, 16)
 B2A_DECLARE_FILL(2, 20)
 B2A_DECLARE_FILL(4, 16)
 B2A_DECLARE_FILL(8, 16)
+B2A_DECLARE_FILL(8, 20)
 B2A_DECLARE_FILL(32, 8)
 B2A_DECLARE_FILL(32, 16)
 

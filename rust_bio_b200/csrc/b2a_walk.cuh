@@ -12,6 +12,7 @@
 // tracker), the row trackers, the last column and the 4-bit traceback.
 #pragma once
 #include "b2a_common.cuh"
+#include "b2a_coop.cuh"
 
 namespace b2a {
 
@@ -144,8 +145,17 @@ struct WalkOut {
   uint32_t clip[4];
 };
 
-// ops are written backwards into ops_end[-1], ops_end[-2], ...
-B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_end, WalkOut& out) {
+// What row m and the last-column fix-ups leave for the walk: the far-corner cell and the clip jumps that are
+// not stored per cell.
+struct EndState {
+  int32_t SmN, ImN;   // S(m,n), I(m,n)
+  uint32_t cmN;       // cell (m,n)
+  int32_t Snm, Lym;   // Sn[m], Ly[m]
+  int32_t Lx0, LxN;   // Lx[0], Lx[n]
+};
+
+// Row m (mod.rs:641-645, 729-805 at i == m), the two last-column fix-up passes (809-843): one lane, literally.
+B2A_HD void finish_matrix_seq(const PairView& v, EndState& es) {
   const DevScoring& sc = v.sc;
   const int32_t m = v.m, n = v.n;
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
@@ -440,7 +450,47 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
     }
   }
 
-  // ----------------------------------------------------- the walk, mod.rs:845-908
+  es.SmN = SmN;
+  es.ImN = ImN;
+  es.cmN = cmN;
+  es.Snm = Snm;
+  es.Lym = Lym;
+  es.Lx0 = Lx0;
+  es.LxN = LxN;
+}
+
+// The traceback state machine (mod.rs:845-908) as a resumable loop: walk_run() advances at most `max_steps`
+// moves, so a warp can interleave lane 0's walk with prefetches issued by the other lanes.
+struct WalkState {
+  int32_t i, j;
+  uint32_t layer;
+  uint32_t xstart, ystart, xend, yend;
+  uint32_t nops, nclip, status;
+  uint32_t clips[4];
+  int32_t guard;
+  uint8_t* ops_end;  // ops are written backwards into ops_end[-1], ops_end[-2], ...
+};
+
+B2A_HD void walk_begin(const PairView& v, const EndState& es, uint8_t* ops_end, WalkState& w) {
+  w.i = v.m;
+  w.j = v.n;
+  w.layer = cell_s(es.cmN);
+  w.xstart = w.ystart = 0;
+  w.xend = (uint32_t)v.m;
+  w.yend = (uint32_t)v.n;
+  w.nops = w.nclip = w.status = 0;
+  w.clips[0] = w.clips[1] = w.clips[2] = w.clips[3] = 0;
+  w.guard = v.m + v.n + 8;
+  w.ops_end = ops_end;
+}
+
+// returns true when the walk has ended (TB_START reached, or a panic path of the reference)
+B2A_HD bool walk_run(const PairView& v, const EndState& es, const bool filter_clips, WalkState& w, int32_t max_steps) {
+  const DevScoring& sc = v.sc;
+  const int32_t m = v.m, n = v.n;
+  const int32_t xs = sc.xclip_suffix;
+  const uint32_t cmN = es.cmN;
+  const int32_t LxN = es.LxN, Lx0 = es.Lx0, Lym = es.Lym;
   auto get_cell_n = [&](int32_t i) -> uint32_t {  // column n, after the fix-ups
     return (i == m) ? cmN : (uint32_t)v.row(ROWS_NL, i);
   };
@@ -451,13 +501,15 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
     if (j == 0) return col0_sbits(sc, i);
     return v.nib_scode(v.nib(i, j), i, j);
   };
-  int32_t i = m, j = n;
-  uint32_t xstart = 0, ystart = 0, xend = (uint32_t)m, yend = (uint32_t)n;
-  uint32_t nops = 0, nclip = 0, status = 0;
-  uint32_t clips[4] = {0, 0, 0, 0};
-  uint32_t layer = cell_s(cmN);
-  int32_t guard = m + n + 8;
-  while (layer != TB_START) {
+  int32_t i = w.i, j = w.j;
+  uint32_t xstart = w.xstart, ystart = w.ystart, xend = w.xend, yend = w.yend;
+  uint32_t nops = w.nops, nclip = w.nclip, status = w.status;
+  uint32_t clips[4] = {w.clips[0], w.clips[1], w.clips[2], w.clips[3]};
+  uint32_t layer = w.layer;
+  int32_t guard = w.guard;
+  uint8_t* ops_end = w.ops_end;
+  while (layer != TB_START && status == 0) {
+    if (max_steps-- <= 0) break;
     if (--guard < 0) {
       status = 1;
       break;
@@ -559,17 +611,426 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
     }
     layer = next;
   }
-  if (nclip > 4) status = 1;
-  out.score = SmN;
-  out.xstart = xstart;
-  out.xend = xend;
-  out.ystart = ystart;
-  out.yend = yend;
-  out.n_ops = nops;
-  out.status = status;
+  w.i = i;
+  w.j = j;
+  w.layer = layer;
+  w.xstart = xstart;
+  w.ystart = ystart;
+  w.xend = xend;
+  w.yend = yend;
+  w.nops = nops;
+  w.nclip = nclip;
+  w.status = status;
+  for (int k = 0; k < 4; ++k) w.clips[k] = clips[k];
+  w.guard = guard;
+  w.ops_end = ops_end;
+  return layer == TB_START || status != 0;
+}
+
+B2A_HD void walk_finish(const EndState& es, const WalkState& w, WalkOut& out) {
+  out.score = es.SmN;
+  out.xstart = w.xstart;
+  out.xend = w.xend;
+  out.ystart = w.ystart;
+  out.yend = w.yend;
+  out.n_ops = w.nops;
+  out.status = (w.nclip > 4) ? 1u : w.status;
   // clips were met end-to-start; report them in alignment order
-  const uint32_t nc = nclip > 4 ? 4 : nclip;
-  for (uint32_t k = 0; k < 4; ++k) out.clip[k] = (k < nc) ? clips[nc - 1 - k] : 0u;
+  const uint32_t nc = w.nclip > 4 ? 4 : w.nclip;
+  for (uint32_t k = 0; k < 4; ++k) out.clip[k] = (k < nc) ? w.clips[nc - 1 - k] : 0u;
+}
+
+// K2 for one pair by one lane: ops are written backwards into ops_end[-1], ops_end[-2], ...
+B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_end, WalkOut& out) {
+  EndState es;
+  finish_matrix_seq(v, es);
+  WalkState w;
+  walk_begin(v, es, ops_end, w);
+  walk_run(v, es, filter_clips, w, 0x7fffffff);
+  walk_finish(es, w, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-pair K2 (small and medium batches, long sequences): the three O(m + n) passes of
+// finish_matrix_seq are sequential only through one max-plus chain each, which W lanes resolve with a prefix
+// maximum, 32 columns / rows at a time; every strict comparison of the reference is then re-evaluated
+// literally per element from its neighbours' final values (the same device as K3's column chunks):
+//   row m      D(m,j) = max(D(m,j-1)+ge, S(m,j-1)+go) with S = max(A, D), A = the best non-D candidate
+//              => D(m,j) = max(D(m,j-1) + gs, A(j-1) + go), gs = max(ge, go): D(m,j) - gs*j is a running maximum;
+//   fix-up 1   element-wise; the re-maximisation of S(m,n) is an arg-max with the lowest row winning ties;
+//   fix-up 2   S'(i) = max(S(i), S'(i-1)+go): S'(i) - go*i is a running maximum of S(k) - go*k.
+// All arithmetic is exact (the engine's range guard keeps every real score within +-2^27).  The walk itself
+// stays on lane 0 (each move depends on the cell the previous one read); the other lanes pull the traceback
+// words along the diagonal ahead of it into the cache.
+template <int W>
+B2A_HD int32_t coop_scan_max(int lane, int32_t v) {  // inclusive prefix maximum over the lanes
+  using C = Coop<W>;
+  for (int d = 1; d < W; d <<= 1) {
+    const int32_t t = C::up(v, d);
+    if (lane >= d) v = imax(v, t);
+  }
+  return v;
+}
+
+// first lane (lowest index) holding the maximum of `val` over the lanes with `has`; returns false if none has
+template <int W>
+B2A_HD bool coop_argmax_first(int lane, bool has, int32_t val, int32_t idx, int32_t& best_val, int32_t& best_idx) {
+  using C = Coop<W>;
+  // key: value high, (0x7fffffff - idx) low: the largest key is the largest value at the smallest index
+  const long long none = (long long)0x8000000000000000ull;
+  long long key = has ? (long long)(((unsigned long long)(long long)val << 32) | (unsigned long long)(uint32_t)(0x7fffffff - idx))
+                      : none;
+  key = C::all_max(key);
+  if (key == none) return false;
+  best_val = (int32_t)(key >> 32);
+  best_idx = 0x7fffffff - (int32_t)(uint32_t)(key & 0xffffffffll);
+  return true;
+}
+
+template <int W>
+B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) {
+  using C = Coop<W>;
+  const DevScoring& sc = v.sc;
+  const int32_t m = v.m, n = v.n;
+  if (m < 2 || n < 1) {  // degenerate shapes: closed forms only, nothing to share out
+    if (lane == 0) finish_matrix_seq(v, es);
+    C::sync();
+    es.SmN = C::from(es.SmN, 0);
+    es.ImN = C::from(es.ImN, 0);
+    es.cmN = (uint32_t)C::from((int32_t)es.cmN, 0);
+    es.Snm = C::from(es.Snm, 0);
+    es.Lym = C::from(es.Lym, 0);
+    es.Lx0 = C::from(es.Lx0, 0);
+    es.LxN = C::from(es.LxN, 0);
+    return;
+  }
+  const int32_t go = sc.gap_open, ge = sc.gap_extend;
+  const int32_t xp = sc.xclip_prefix, xs = sc.xclip_suffix, yp = sc.yclip_prefix, ys = sc.yclip_suffix;
+  const int32_t gs = imax(ge, go);
+  const bool pk = v.packtrk != 0;
+
+  // ------------------------------------------------------------------ row m, column 0 (mod.rs:622-671 at i == m)
+  int32_t T = MIN_SCORE, Lx0 = 0;
+  {
+    int32_t bv = MIN_SCORE, bi = 0;  // this lane's rows ascend: a strict > keeps its first maximum
+    bool has = false;
+    for (int32_t i = 1 + lane; i < m; i += W) {
+      const int32_t val = col0_S(sc, i) + xs;
+      if (val > bv) {
+        bv = val;
+        bi = i;
+        has = true;
+      }
+    }
+    int32_t gv, gi;
+    if (coop_argmax_first<W>(lane, has, bv, bi, gv, gi)) {  // gv > MIN_SCORE by construction
+      T = gv;
+      Lx0 = m - gi;
+    }
+  }
+  int32_t Im0 = col0_I(sc, m);
+  const uint32_t ib0 = col0_ibits(sc, m);
+  int32_t Sm0 = T;
+  uint32_t sb0 = TB_XCLIP_SUFFIX;
+  if (Im0 > Sm0) {
+    Sm0 = Im0;
+    sb0 = TB_INS;
+  }
+  if (xp > Sm0) {
+    Sm0 = xp;
+    sb0 = TB_XCLIP_PREFIX;
+  }
+  int32_t Snm = MIN_SCORE, Lym = 0;
+  if (Sm0 + ys > Snm) {
+    Snm = Sm0 + ys;
+    Lym = n;
+  }
+  if (lane == 0) v.rowm[0 * 32 + v.pi] = (uint16_t)cell_make(ib0, TB_START, sb0);
+  int32_t LxN = Lx0;
+  const int32_t p = v.xsym(m);
+  const int32_t yclip_score = yp + go + ge * (m - 1);
+  // ------------------------------------------------------------------ row m, columns 1..n in chunks of W
+  // carries = the last column done so far (every lane holds the same values)
+  int32_t cSup = col0_S(sc, m - 1);  // S(m-1, j-1) for the chunk's first column
+  int32_t cD = MIN_SCORE, cS = Sm0;  // D(m, j-1), S(m, j-1)
+  uint32_t csb = sb0;                // s_bits(m, j-1)
+  int32_t SmN = 0, ImN = MIN_SCORE;
+  uint32_t cmN = 0;
+  for (int32_t base = 1; base <= n; base += W) {
+    const int32_t j = base + lane;
+    const bool act = j <= n;
+    const int32_t jc = act ? j : n;  // idle lanes repeat the last column: loads stay in bounds, nothing is stored
+    const Boundary b = decode_boundary(v.load_bnd(jc), pk, xs, m);
+    const int32_t q = v.ysym(jc);
+    int32_t sdiag = C::up(b.S, 1);
+    if (lane == 0) sdiag = cSup;
+    const int32_t m_score = sdiag + v.score(p, q);
+    uint32_t ib;
+    int32_t best_i;
+    {
+      const int32_t i_score = b.I + ge, s_score = b.S + go;
+      if (i_score > s_score) {
+        best_i = i_score;
+        ib = TB_INS;
+      } else {
+        best_i = s_score;
+        ib = LAZY;
+      }
+    }
+    const int32_t xcs = xclip_score(sc, jc);
+    const int32_t A = imax(imax(imax(b.Tv, m_score), imax(best_i, xcs)), yclip_score);
+    // D(m,j) - gs*j as a running maximum
+    int32_t t;
+    {
+      const int32_t aprev = C::up(A, 1);
+      if (lane == 0) t = imax(cD + ge, cS + go) - gs * jc;
+      else t = aprev + go - gs * jc;
+    }
+    const int32_t best_d = coop_scan_max<W>(lane, t) + gs * jc;
+    // the cell, literally (mod.rs:757-786 with the running best starting from the column tracker)
+    int32_t best = b.Tv;
+    uint32_t sb = TB_XCLIP_SUFFIX;
+    if (m_score > best) {
+      best = m_score;
+      sb = (p == q) ? TB_MATCH : TB_SUBST;
+    }
+    if (best_i > best) {
+      best = best_i;
+      sb = TB_INS;
+    }
+    if (best_d > best) {
+      best = best_d;
+      sb = TB_DEL;
+    }
+    if (xcs > best) {
+      best = xcs;
+      sb = TB_XCLIP_PREFIX;
+    }
+    if (yclip_score > best) {
+      best = yclip_score;
+      sb = TB_YCLIP_PREFIX;
+    }
+    // d_bits from the final values of column j-1
+    int32_t pD = C::up(best_d, 1), pS = C::up(best, 1);
+    uint32_t psb = (uint32_t)C::up((int32_t)sb, 1);
+    if (lane == 0) {
+      pD = cD;
+      pS = cS;
+      psb = csb;
+    }
+    const uint32_t db = (pD + ge > pS + go) ? (uint32_t)TB_DEL : psb;
+    // row tracker of row m (mod.rs:799-802): first column with the highest S + ys, if above the running value
+    {
+      int32_t gv, gj;
+      if (coop_argmax_first<W>(lane, act, best + ys, j, gv, gj) && gv > Snm) {
+        Snm = gv;
+        Lym = n - gj;
+      }
+    }
+    if (act && j == n) {
+      if (ib == LAZY) ib = v.nib_scode((uint32_t)v.row(ROWS_NL, m - 1), m - 1, n);  // captured before the fix-ups
+    }
+    const uint32_t cell = cell_make(ib, db, sb);
+    if (act) v.rowm[j * 32 + v.pi] = (uint16_t)cell;
+    const int32_t left = n - base;
+    const int src = left < W - 1 ? left : W - 1;
+    cSup = C::from(b.S, src);
+    cD = C::from(best_d, src);
+    cS = C::from(best, src);
+    csb = (uint32_t)C::from((int32_t)sb, src);
+    if (base + W > n) {  // the chunk holding column n
+      SmN = cS;
+      ImN = C::from(best_i, src);
+      cmN = (uint32_t)C::from((int32_t)cell, src);
+      LxN = m - C::from(b.Ti, src);
+    }
+  }
+
+  C::sync();  // row m read the cell (m-1, n) that fix-up 1 is about to rewrite
+
+  // ------------------------------------------------------------------ column n + fix-up 1 (mod.rs:809-821)
+  const bool ys_live = ys > DEAD_CLIP;
+  const int32_t s0 = row0_S(sc, n, n);
+  const uint32_t c0 = cell_make(TB_START, row0_dbits(sc, n), row0_sbits(sc, n, n));
+  {  // row 0
+    int32_t S = s0;
+    uint32_t cell = c0;
+    if (ys > S) {
+      S = ys;
+      cell = cell_set_s(cell, TB_YCLIP_SUFFIX);
+    }
+    if (lane == 0) {
+      v.row(ROWS_SL, 0) = S;
+      v.row(ROWS_IL, 0) = MIN_SCORE;
+      v.row(ROWS_NL, 0) = (int32_t)cell;
+    }
+    if (S + xs > SmN) {
+      SmN = S + xs;
+      LxN = m;
+      cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
+    }
+  }
+  {
+    uint32_t c_above = cell_s(c0);  // pre-fix-up s_bits of the row above the chunk
+    const int32_t yn = v.ysym(n);
+    for (int32_t base = 1; base < m; base += W) {
+      const int32_t i = base + lane;
+      const bool act = i < m;
+      const int32_t ic = act ? i : m - 1;
+      const uint32_t nb = (uint32_t)v.row(ROWS_NL, ic);
+      int32_t S = v.row(ROWS_SL, ic);
+      const int32_t Sn = ys_live ? v.row(ROWS_SN, ic) : MIN_SCORE;
+      uint32_t sbi;
+      switch (nb & 3u) {
+        case NB_DIAG: sbi = v.xsym(ic) == yn ? TB_MATCH : TB_SUBST; break;
+        case NB_INS: sbi = TB_INS; break;
+        case NB_DEL: sbi = TB_DEL; break;
+        default: sbi = TB_XCLIP_PREFIX; break;
+      }
+      uint32_t s_above = (uint32_t)C::up((int32_t)sbi, 1);
+      if (lane == 0) s_above = c_above;
+      uint32_t cell = cell_make((nb & NB_IEXT) ? (uint32_t)TB_INS : s_above, (nb & NB_DEXT) ? (uint32_t)TB_DEL : LAZY, sbi);
+      if (Sn > S) {  // fix-up 1
+        S = Sn;
+        cell = cell_set_s(cell, TB_YCLIP_SUFFIX);
+      }
+      if (act) {
+        v.row(ROWS_SL, i) = S;
+        v.row(ROWS_NL, i) = (int32_t)cell;
+      }
+      int32_t gv, gi;
+      if (coop_argmax_first<W>(lane, act, S + xs, i, gv, gi) && gv > SmN) {
+        SmN = gv;
+        LxN = m - gi;
+        cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
+      }
+      const int32_t left = m - 1 - base;
+      c_above = (uint32_t)C::from((int32_t)sbi, left < W - 1 ? left : W - 1);
+    }
+  }
+  if (Snm > SmN) {  // i == m
+    SmN = Snm;
+    cmN = cell_set_s(cmN, TB_YCLIP_SUFFIX);
+  }
+  C::sync();  // the rows arena as fix-up 1 left it is what fix-up 2 reads
+
+  // ------------------------------------------------------------------ fix-up 2 (mod.rs:825-843), rows 1..m-1
+  int32_t cSp;     // S'(i-1) for the chunk's first row
+  uint32_t ccell;  // cell (i-1, n) after its own fix-up 2
+  {
+    int32_t S = s0;
+    uint32_t cell = c0;
+    if (ys > S) {
+      S = ys;
+      cell = cell_set_s(cell, TB_YCLIP_SUFFIX);
+    }
+    cSp = S;
+    ccell = cell;
+  }
+  for (int32_t base = 1; base < m; base += W) {
+    const int32_t i = base + lane;
+    const bool act = i < m;
+    const int32_t ic = act ? i : m - 1;
+    int32_t I = v.row(ROWS_IL, ic), S = v.row(ROWS_SL, ic);
+    uint32_t cell = (uint32_t)v.row(ROWS_NL, ic);
+    // S'(i) - go*i = max(S'(i-1) - go*(i-1) ... ) : inclusive running maximum of S(k) - go*k, seeded by the carry
+    int32_t t = S - go * ic;
+    if (lane == 0) t = imax(t, cSp + go - go * ic);
+    const int32_t Snew = coop_scan_max<W>(lane, t) + go * ic;  // S'(i)
+    int32_t Sprev = C::up(Snew, 1);
+    if (lane == 0) Sprev = cSp;
+    const int32_t s_score = Sprev + go;
+    // cell (i-1) after its own pass: only its s_bits can have changed, to TB_INS
+    const bool raised = s_score > S;
+    uint32_t my_s_after = raised ? (uint32_t)TB_INS : cell_s(cell);
+    uint32_t prev_s_after = (uint32_t)C::up((int32_t)my_s_after, 1);
+    if (lane == 0) prev_s_after = cell_s(ccell);
+    bool dirty = false;
+    if (s_score > I) {
+      I = s_score;
+      cell = cell_set_i(cell, prev_s_after);
+      dirty = true;
+    }
+    if (raised) {
+      S = s_score;
+      cell = cell_set_s(cell, TB_INS);
+      dirty = true;
+    }
+    if (act && dirty) {
+      v.row(ROWS_IL, i) = I;
+      v.row(ROWS_SL, i) = S;
+      v.row(ROWS_NL, i) = (int32_t)cell;
+    }
+    int32_t gv, gi;
+    if (coop_argmax_first<W>(lane, act && raised, S + xs, i, gv, gi) && gv > SmN) {
+      SmN = gv;
+      LxN = m - gi;
+      cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
+    }
+    const int32_t left = m - 1 - base;
+    const int src = left < W - 1 ? left : W - 1;
+    cSp = C::from(S, src);  // == S'(i) of the chunk's last row
+    ccell = (uint32_t)C::from((int32_t)cell, src);
+  }
+  {  // i == m
+    const int32_t s_score = cSp + go;
+    if (s_score > ImN) {
+      ImN = s_score;
+      cmN = cell_set_i(cmN, cell_s(ccell));
+    }
+    if (s_score > SmN) {
+      SmN = s_score;
+      cmN = cell_set_s(cmN, TB_INS);
+    }
+  }
+  C::sync();
+  es.SmN = SmN;
+  es.ImN = ImN;
+  es.cmN = cmN;
+  es.Snm = Snm;
+  es.Lym = Lym;
+  es.Lx0 = Lx0;
+  es.LxN = LxN;
+}
+
+// touch the traceback words the walk is likely to read next (the diagonal below the current cell)
+B2A_HD void prefetch_tb(const PairView& v, int32_t i, int32_t j) {
+#if defined(__CUDA_ARCH__)
+  if (i >= 1 && i <= v.m - 1 && j >= 1 && j <= v.n) {
+    const int32_t GR = v.G * v.R;
+    const int32_t s = (i - 1) / GR, rem = (i - 1) % GR;
+    const int32_t l = rem / v.R, r = rem % v.R;
+    const int32_t ln = v.g * v.G + l;
+    const int32_t t = (j - 1) + l;
+    const size_t word =
+        ((((size_t)(v.sub * v.nstrips + s) * v.K + (t >> 3)) * v.TBW + (r >> 2)) * 32 + ln) * 4 + (r & 3);
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(v.tb + word));
+  }
+#else
+  (void)v;
+  (void)i;
+  (void)j;
+#endif
+}
+
+// K2 for one pair by W cooperating lanes; `out` is complete on lane 0
+template <int W>
+B2A_HD void walk_pair_coop(const int lane, const PairView& v, const bool filter_clips, uint8_t* ops_end, WalkOut& out) {
+  using C = Coop<W>;
+  EndState es;
+  finish_matrix_coop<W>(lane, v, es);
+  WalkState w;
+  walk_begin(v, es, ops_end, w);
+  constexpr int32_t kBurst = 24;  // moves of lane 0 between two rounds of prefetches
+  for (;;) {
+    // every lane looks a different distance down the diagonal from where lane 0 stands
+    const int32_t ci = C::from(w.i, 0), cj = C::from(w.j, 0);
+    prefetch_tb(v, ci - 1 - lane, cj - 1 - lane);
+    int32_t done = 0;
+    if (lane == 0) done = walk_run(v, es, filter_clips, w, kBurst) ? 1 : 0;
+    if (C::from(done, 0)) break;
+  }
+  walk_finish(es, w, out);
 }
 
 #if defined(__CUDACC__)
@@ -629,7 +1090,72 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
   for (int k = 0; k < 4; ++k) prm.clip_len[4 * (size_t)dst + k] = o.clip[k];
 }
 
+// K2, one warp per pair
+__device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& blk, const int pi, const int lane) {
+  const uint32_t sp = blk.first + pi;
+  const int32_t P = 32 / prm.G;
+  PairView v;
+  v.sc = prm.sc;
+  v.lut = prm.lut;
+  v.P = P;
+  v.m = (int32_t)prm.pm[sp];
+  v.n = (int32_t)prm.pn[sp];
+  v.pi = pi;
+  v.G = prm.G;
+  v.R = prm.R;
+  v.TBW = (prm.R + 3) / 4;
+  v.nstrips = (int32_t)blk.nstrips;
+  v.K = (int32_t)blk.K;
+  v.sub = pi / P;
+  v.g = pi % P;
+  v.packtrk = prm.packtrk;
+  v.maxn = (int32_t)blk.maxn;
+  v.bnd_base = bnd_index(prm.G, 0, pi, v.maxn);
+  v.bnd_stride = (int32_t)(bnd_index(prm.G, 1, pi, v.maxn) - v.bnd_base);
+  const uint32_t* seqw = reinterpret_cast<const uint32_t*>(prm.seq + blk.seq_off);
+  v.xw = seqw + (size_t)v.sub * blk.xwords * P + v.g;
+  v.yw = seqw + (size_t)prm.G * blk.xwords * P + (size_t)v.sub * blk.ywords * P + v.g;
+  v.bnd = reinterpret_cast<const int4*>(prm.bnd + blk.bnd_off);
+  v.rows = reinterpret_cast<int32_t*>(prm.rows + blk.rows_off);
+  v.rows_pad = (int32_t)blk.rows_pad;
+  v.rowm = reinterpret_cast<uint16_t*>(prm.rowm + blk.rowm_off);
+  v.tb = reinterpret_cast<const uint32_t*>(prm.tb + blk.tb_off);
+  const uint32_t cap = blk.maxm + blk.maxn + 4;
+  uint8_t* ops_end = prm.ops_scratch + blk.ops_off + (size_t)(pi + 1) * cap;
+  WalkOut o;
+  walk_pair_coop<32>(lane, v, prm.filter_clips != 0, ops_end, o);
+  if (lane != 0) return;
+  if (o.status) {  // the reference panics on this pair (mod.rs:905): no alignment is reported for it
+    o.score = MIN_SCORE;
+    o.n_ops = 0;
+    o.xstart = o.xend = o.ystart = o.yend = 0;
+    o.clip[0] = o.clip[1] = o.clip[2] = o.clip[3] = 0;
+  }
+  const uint32_t dst = prm.order[sp];
+  prm.score[dst] = o.score;
+  prm.xstart[dst] = o.xstart;
+  prm.xend[dst] = o.xend;
+  prm.ystart[dst] = o.ystart;
+  prm.yend[dst] = o.yend;
+  prm.n_ops[dst] = o.n_ops;
+  prm.ops_src[dst] = blk.ops_off + (uint64_t)(pi + 1) * cap - o.n_ops;
+  prm.status[dst] = o.status;
+  if (o.status) atomicOr(prm.err_flag, 1u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) prm.clip_len[4 * (size_t)dst + k] = o.clip[k];
+}
+
 #if defined(B2A_DEFINE_WALK_KERNEL)  // one translation unit (b2a_engine.cu) owns the stand-alone kernel
+__global__ void __launch_bounds__(128) walk_warp_kernel(const WalkParams prm) {
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (block, pair)
+  const int lane = threadIdx.x & 31;
+  const uint32_t b = gw >> 5, pi = gw & 31u;
+  if (b >= prm.nblocks) return;
+  const Block blk = prm.blocks[b];
+  if (pi >= blk.npairs) return;
+  walk_warp(prm, blk, (int)pi, lane);
+}
+
 __global__ void __launch_bounds__(128, 8) walk_kernel(const WalkParams prm) {
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;

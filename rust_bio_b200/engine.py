@@ -101,6 +101,10 @@ class Engine:
     def set_tuning(self, lanes_per_pair: int, rows_per_lane: int):
         self._check(self._L.b2a_engine_set_tuning(self._h, lanes_per_pair, rows_per_lane))
 
+    def set_walk(self, mode: int):
+        """K2 shape: 0 automatic, 1 one lane per pair, 2 one warp per pair (b2a_engine_set_walk)."""
+        self._check(self._L.b2a_engine_set_walk(self._h, int(mode)))
+
     def set_pipeline(self, chunks: int):
         self._check(self._L.b2a_engine_set_pipeline(self._h, int(chunks)))
 
@@ -201,6 +205,17 @@ class Engine:
 
     def compact_into(self, dev_ptr: int, nbytes: int) -> None:
         self._check(self._L.b2a_batch_compact_into(self._h, C.c_void_p(dev_ptr), int(nbytes)))
+
+    def compact_fixed(self, dev_ptr: int, capacity_bytes: int) -> None:
+        """b2a_batch_compact_fixed: the segment with a caller-fixed capacity; no wait, no size read-back."""
+        self._check(self._L.b2a_batch_compact_fixed(self._h, C.c_void_p(dev_ptr), int(capacity_bytes)))
+
+    def gathered_fetch(self, dev_ptr: int, segment_bytes: int, n_segments: int, results: Results):
+        """b2a_gathered_fetch: gathered device segments -> host `results`; returns (pairs, d2h bytes)."""
+        n, b = C.c_uint64(), C.c_uint64()
+        self._check(self._L.b2a_gathered_fetch(self._h, C.c_void_p(dev_ptr), int(segment_bytes), int(n_segments),
+                                               C.byref(results.c), C.byref(n), C.byref(b)))
+        return int(n.value), int(b.value)
 
     def decode_compact(self, host_segments: np.ndarray, segment_bytes: int, n_segments: int, n_total: int,
                        ops_capacity: int) -> Results:

@@ -471,7 +471,15 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
       const uint32_t cap = blk.maxm + blk.maxn + 4;
       uint8_t* ops_end = opsb.data() + blk.ops_off + (size_t)(lane + 1) * cap;
       WalkOut o;
-      walk_pair(v, mode == 2 || mode == 3, ops_end, o);
+      if (modebits & 8) {  // the warp-per-pair K2: 32 emulated lanes on this pair
+        LaneFibers::run([&](int l) {
+          WalkOut mine;
+          walk_pair_coop<32>(l, v, mode == 2 || mode == 3, ops_end, mine);
+          if (l == 0) o = mine;
+        });
+      } else {
+        walk_pair(v, mode == 2 || mode == 3, ops_end, o);
+      }
       const uint32_t dst = p.order[sp];
       score[dst] = o.score;
       xstart[dst] = o.xstart;

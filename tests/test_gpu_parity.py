@@ -9,7 +9,7 @@ from parity_util import MODES, assert_same, oracle_batch, rescore_path
 pytestmark = pytest.mark.gpu
 MIN = -858993459
 CASES = load_cases()
-SHAPES = [(1, 16), (1, 8), (4, 16), (8, 16), (32, 8), (32, 16)]
+SHAPES = [(1, 16), (1, 8), (4, 16), (8, 16), (8, 20), (32, 8), (32, 16)]
 
 
 @pytest.fixture(scope="module")
@@ -505,4 +505,109 @@ def test_long_reference_falls_back_to_warp_per_pair_staging(eng, oracle):
         with pytest.raises(B2AError, match="UNSUPPORTED"):
             eng.align_batch(MODES["semiglobal"], cs, batch)
     finally:
+        eng.set_tuning(0, 0)
+
+
+def test_fixed_capacity_segments_and_gathered_fetch(eng, oracle):
+    """b2a_batch_compact_fixed + b2a_gathered_fetch (the N > 1 reassembly without a size agreement): segments of a
+    caller-fixed capacity, 'gathered' here by placing two batches' segments side by side, decode on the host to
+    exactly what fetch returns; a capacity below the ops bytes is reported, not silently cut."""
+    import torch
+    from rust_bio_b200 import synth
+    from rust_bio_b200._lib import B2AError
+    from rust_bio_b200.engine import Results
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    batches = [synth.ragged_pairs(5, 700, 60, 90), synth.ragged_pairs(6, 300, 120, 40)]
+    seg = 1 << 20
+    allbuf = torch.zeros(2 * seg, dtype=torch.uint8, device="cuda")
+    wants = []
+    for g, batch in enumerate(batches):
+        n = len(batch[2])
+        eng.stage(MODES["global"], cs, batch)
+        eng.run()
+        eng.compact_fixed(allbuf.data_ptr() + g * seg, seg)
+        want = Results(n, 1 << 20)
+        eng.fetch(want)
+        wants.append(want)
+    torch.cuda.synchronize()
+    got = Results(1000, 2 << 20)
+    n_got, moved = eng.gathered_fetch(allbuf.data_ptr(), seg, 2, got)
+    assert n_got == 1000 and moved > 0
+    base, obase = 0, 0
+    for want in wants:
+        n = want.n_pairs
+        for k in ("score", "xstart", "xend", "ystart", "yend"):
+            assert np.array_equal(getattr(got, k)[base:base + n], getattr(want, k)[:n]), k
+        assert np.array_equal(got.clip_len[4 * base:4 * (base + n)], want.clip_len[:4 * n])
+        tot = int(want.ops_off[n])
+        assert np.array_equal(got.ops_off[base:base + n + 1].astype(np.int64) - obase, want.ops_off[:n + 1].astype(np.int64))
+        assert np.array_equal(got.ops[obase:obase + tot], want.ops[:tot])
+        base += n
+        obase += tot
+    # too small a capacity: the header says so and the fetch refuses the segment
+    small = 64 + 40 * 300 + 100
+    eng.compact_fixed(allbuf.data_ptr(), small)
+    torch.cuda.synchronize()
+    with pytest.raises(B2AError, match="CAPACITY"):
+        eng.gathered_fetch(allbuf.data_ptr(), small, 1, Results(300, 1 << 20))
+    with pytest.raises(B2AError, match="CAPACITY"):
+        eng.compact_fixed(allbuf.data_ptr(), 64)
+
+
+@pytest.mark.parametrize("walk", [1, 2], ids=["lane_per_pair", "warp_per_pair"])
+def test_both_walk_kernels_every_mode(eng, oracle, walk):
+    """K2 as one lane per pair and as one warp per pair (prefix-maximum passes + prefetched walk) give the
+    reference's results in every mode, on ragged batches, custom clips, every fill shape family."""
+    from rust_bio_b200 import synth
+    eng.set_walk(walk)
+    try:
+        for (G, R) in [(0, 0), (1, 16), (8, 20), (8, 16), (32, 8)]:
+            eng.set_tuning(G, R)
+            for mode, clips in [("local", (MIN,) * 4), ("global", (MIN,) * 4), ("semiglobal", (MIN,) * 4),
+                                ("custom", (-3, -4, -2, -5)), ("custom", (MIN, 0, MIN, -1)), ("custom", (0, MIN, 0, 0))]:
+                batch = synth.ragged_pairs(60 + G, 400, 200, 230)
+                s, _ = oracle.make_scoring(-5, -1, 2, -3, None, *clips)
+                ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)
+                cs, keep = _c_scoring(-5, -1, 2, -3, clips)
+                got, ops = _engine_result(eng, mode, cs, batch)
+                assert_same(got, ops, ref, ref_ops, batch, f"walk={walk} {mode} {clips} G={G} R={R}")
+        eng.set_tuning(0, 0)
+        # tiny and empty shapes
+        xs, ys = [], []
+        for m in range(0, 5):
+            for n in range(0, 5):
+                xs.append(m)
+                ys.append(n)
+        rng = np.random.default_rng(5)
+        blob = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 2, size=sum(xs) + sum(ys) + 1)]
+        lens = np.array([v for pair in zip(xs, ys) for v in pair], dtype=np.uint64)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+        batch = (blob, offs[0::2].copy(), np.array(xs, dtype=np.uint32), offs[1::2].copy(), np.array(ys, dtype=np.uint32))
+        for mode in ("custom", "local", "global", "semiglobal"):
+            for clips in [(MIN, MIN, MIN, MIN), (0, 0, 0, 0), (-1, 0, MIN, -2)]:
+                s, _ = oracle.make_scoring(-2, -1, 2, -1, None, *clips)
+                ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+                cs, keep = _c_scoring(-2, -1, 2, -1, clips)
+                got, ops = _engine_result(eng, mode, cs, batch)
+                assert_same(got, ops, ref, ref_ops, batch, f"walk={walk} tiny {mode} {clips}")
+        # C1, C3 sample, blosum
+        batch = synth.uniform_pairs(synth.BASES["C1"], 0, 1000, 150, 150)
+        s, _ = oracle.make_scoring(-5, -1, 1, -1)
+        ref, ref_ops = oracle_batch(oracle, "local", s, batch, threads=8)
+        cs, keep = _c_scoring(-5, -1, 1, -1)
+        got, ops = _engine_result(eng, "local", cs, batch)
+        assert_same(got, ops, ref, ref_ops, batch, f"walk={walk} C1")
+        batch = synth.uniform_pairs(synth.BASES["C3"], 0, 64, 1000, 1000)
+        ref, ref_ops = oracle_batch(oracle, "global", s, batch, threads=8)
+        got, ops = _engine_result(eng, "global", cs, batch)
+        assert_same(got, ops, ref, ref_ops, batch, f"walk={walk} C3 sample")
+        table, alpha = _blosum62()
+        batch = synth.ragged_pairs(3, 200, 180, 170, alphabet=synth.PROTEIN, min_len=1)
+        s, keep1 = oracle.make_scoring(-10, -1, 0, 0, table)
+        ref, ref_ops = oracle_batch(oracle, "local", s, batch, threads=8)
+        cs, keep2 = _c_scoring(-10, -1, 0, 0, table=table, alphabet=alpha)
+        got, ops = _engine_result(eng, "local", cs, batch)
+        assert_same(got, ops, ref, ref_ops, batch, f"walk={walk} blosum62 local")
+    finally:
+        eng.set_walk(0)
         eng.set_tuning(0, 0)

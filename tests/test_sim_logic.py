@@ -155,3 +155,68 @@ def test_sim_strip_pipelined_warp_per_pair(oracle, mode):
     ref, ref_ops = oracle_batch(oracle, mode, s, ubatch, threads=4)
     got, ops = sim_util.align_batch(MODES[mode], s, *ubatch, R=8, G=132)
     assert_same(got, ops, ref, ref_ops, ubatch, f"strip-pipelined uniform {mode}")
+
+
+# ---- the warp-per-pair K2 (walk_pair_coop<32>: row m, the fix-up passes as 32-wide prefix maxima) on 32 emulated
+# lanes, against the oracle.  Same inputs as the one-lane walk above.
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_sim_warp_walk_golden(oracle, case):
+    s, keep = _scoring(oracle, case["scoring"])
+    got, ops = sim_util.align_batch(MODES[case["mode"]], s, *_one(case["x"].encode(), case["y"].encode()), R=4,
+                                    warp_walk=1)
+    exp = case["expect"]
+    for k in ("score", "xstart", "xend", "ystart", "yend"):
+        if k in exp:
+            assert int(got[k][0]) == exp[k], (case["name"], k)
+    if "ops" in exp:
+        assert ops[0] == parse_ops(exp["ops"])
+    assert got["status"][0] == 0
+
+
+@pytest.mark.parametrize("mode", ["local", "global", "semiglobal"])
+@pytest.mark.parametrize("R,G,no_pack", [(4, 1, 0), (16, 1, 1), (16, 4, 0), (8, 32, 0)])
+def test_sim_warp_walk_ragged_presets(oracle, mode, R, G, no_pack):
+    batch = synth.ragged_pairs(31 + R, 160, 100, 130)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+    got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=R, G=G, no_pack=no_pack, warp_walk=1)
+    assert_same(got, ops, ref, ref_ops, batch, f"warp walk {mode} R={R} G={G}")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_sim_warp_walk_random_custom_clips(oracle, seed):
+    rng = np.random.default_rng(900 + seed)
+    pick = lambda: int(rng.choice([MIN, 0, 0, -1, -3, -7, -20]))
+    go, ge = int(rng.choice([0, -1, -2, -5, -6])), int(rng.choice([0, -1, -1, -2]))
+    ma, mi = int(rng.choice([1, 2, 4])), int(rng.choice([-1, -3, -7, 0]))
+    clips = (pick(), pick(), pick(), pick())
+    s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips)
+    batch = synth.ragged_pairs(seed, 150, 75, 95, alphabet=b"AC" if seed % 2 else b"ACGT")
+    ref, ref_ops = oracle_batch(oracle, "custom", s, batch)
+    got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=8, warp_walk=1)
+    assert_same(got, ops, ref, ref_ops, batch, f"warp walk custom seed={seed} clips={clips}")
+
+
+def test_sim_warp_walk_tiny_shapes(oracle):
+    xs, ys = [], []
+    for m in range(0, 6):
+        for n in range(0, 6):
+            for rep in range(2):
+                xs.append(m)
+                ys.append(n)
+    for m, n in [(33, 1), (1, 33), (2, 64), (64, 2), (32, 32), (33, 33), (65, 31)]:
+        xs.append(m)
+        ys.append(n)
+    rng = np.random.default_rng(5)
+    total = sum(xs) + sum(ys)
+    blob = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 2, size=total + 1)]
+    lens = np.array([v for pair in zip(xs, ys) for v in pair], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    batch = (blob, offs[0::2].copy(), np.array(xs, dtype=np.uint32), offs[1::2].copy(), np.array(ys, dtype=np.uint32))
+    for mode in ("custom", "local", "global", "semiglobal"):
+        for clips in [(MIN, MIN, MIN, MIN), (0, 0, 0, 0), (-1, 0, MIN, -2), (0, MIN, MIN, 0)]:
+            s, _ = oracle.make_scoring(-2, -1, 2, -1, None, *clips)
+            ref, ref_ops = oracle_batch(oracle, mode, s, batch)
+            got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=4, warp_walk=1)
+            assert_same(got, ops, ref, ref_ops, batch, f"warp walk tiny {mode} {clips}")

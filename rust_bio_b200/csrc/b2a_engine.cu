@@ -77,6 +77,16 @@ struct b2a_engine {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  // pipeline slots only: K2 + ops compaction + result copies run on this high-priority stream, so that an
+  // older chunk's short, latency-bound tail is scheduled ahead of the next chunk's fill CTAs
+  cudaStream_t tail_stream = nullptr;
+  cudaEvent_t ev_fill = nullptr;
+  bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
+  bool stage_nosync = false;       // pipeline slots: the caller's arrays outlive the call, no sync at the end of stage
+  uint32_t fill_task_limit = 0;    // pipeline slots: fill CTAs retire after this many tasks per warp (CTA turnover)
+  uint8_t* h_plan = nullptr;       // pinned staging of the plan vectors (async H2D)
+  size_t h_plan_cap = 0;
+  cudaStream_t res_stream() const { return tail_used ? tail_stream : stream; }  // where the results become ready
   uint64_t compact_hdr[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};  // header of the compact result segment
   // the band of the last banded call's last wave (Band::ranges), for b2a_banded_band_ranges
   uint64_t band_wave_lo = 0;
@@ -123,7 +133,8 @@ struct b2a_engine {
     std::vector<uint8_t> packed;  // the chunk's sequences gathered from a scattered caller blob
     uint64_t lo = 0, n = 0;
     bool busy = false;
-  } slots[2];
+  } slots[3];
+  static constexpr int kSlots = 3;
 
   int fail(int code, const std::string& what) {
     err = what;
@@ -154,9 +165,14 @@ void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_
   if (n_pairs >= 32ull * 148 * 4 && stage1 <= kMaxStageSmem && maxm <= 2048) {
     *G = 1;
     *R = 16;
-  } else if ((n_pairs >= 16ull * 148 * 8 && maxm <= 4096) || maxm <= 129) {
-    *G = 8;  // enough pairs to fill the GPU four to a warp (or a single strip anyway)
-    *R = 16;
+  } else if ((n_pairs >= 4096 && maxm <= 4096) || maxm <= 161) {
+    // four pairs to a warp: enough warps to fill the GPU (or a single strip anyway).  128-row or 160-row
+    // strips, whichever pads the rows less: 10k reads of 150 run as one strip of 8x20 (7 % padding) at
+    // 0.34 ms against 0.46 (2x16), 0.52 (8x16: two strips) and 0.68 (32x8) -- profiles/r02_small_batch_shapes.txt
+    const uint64_t rows = maxm > 1 ? maxm - 1 : 1;
+    const uint64_t pad16 = (rows + 127) / 128 * 128, pad20 = (rows + 159) / 160 * 160;
+    *G = 8;
+    *R = pad20 < pad16 ? 20 : 16;
   } else {
     // warp per pair, (pair, strip) tasks pipelined through the boundary row: fills the GPU from a few long
     // pairs.  16 rows per lane is ~15% faster per cell than 8 unless the 512-row strips pad m much more.
@@ -222,6 +238,12 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
     sl.eng = nullptr;
   }
   cudaStreamSynchronize(e->stream);
+  if (e->tail_stream) {
+    cudaStreamSynchronize(e->tail_stream);
+    cudaStreamDestroy(e->tail_stream);
+  }
+  if (e->ev_fill) cudaEventDestroy(e->ev_fill);
+  if (e->h_plan) cudaFreeHost(e->h_plan);
   if (e->h_nops) cudaFreeHost(e->h_nops);
   DevBuf* bufs[] = {&e->d_blob, &e->d_xoff, &e->d_xlen, &e->d_yoff, &e->d_ylen, &e->d_order, &e->d_pm,
                     &e->d_pn, &e->d_blocks, &e->d_seq, &e->d_bnd, &e->d_rows, &e->d_rowm, &e->d_tb,
@@ -289,6 +311,9 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   int rc = validate_scoring(e, s);
   if (rc) return rc;
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
+  if (e->stage_nosync) {  // a previous stage's copies out of the pinned plan arena must have landed
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return e->fail(B2A_E_CUDA, "cudaStreamSynchronize failed");
+  }
   const uint64_t n = pairs->n_pairs;
   if (n > 0x7ffffffeull) return e->fail(B2A_E_INVALID, "more than 2^31 - 2 pairs in one batch");
   e->n_pairs = n;
@@ -401,8 +426,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
 }
 
 // ops compaction shared by the full and the banded path: widen -> exclusive scan -> gather
-static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes) {
-  cudaStream_t st = e->stream;
+static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes, cudaStream_t st) {
   const uint64_t n = e->n_pairs;
   if (n) {
     const unsigned g1 = (unsigned)((n + 1 + 255) / 256);
@@ -497,19 +521,41 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   CK(e->d_nops64.reserve((n + 1) * 8));
   CK(e->d_opsoff.reserve((n + 1) * 8));
 
-  // host -> device
+  // host -> device.  The plan vectors go through a pinned staging arena so that their copies are truly
+  // asynchronous (a copy from pageable memory first waits for the stream: it would serialise the host with the
+  // blob's H2D in the chunk pipeline).
   CK(up(e->d_xoff, pairs->x_off, n * 8));
   CK(up(e->d_yoff, pairs->y_off, n * 8));
   CK(up(e->d_xlen, pairs->x_len, n * 4));
   CK(up(e->d_ylen, pairs->y_len, n * 4));
-  CK(up(e->d_order, pl.order.data(), n * 4));
-  CK(up(e->d_pm, pl.pm.data(), n * 4));
-  CK(up(e->d_pn, pl.pn.data(), n * 4));
-  CK(up(e->d_blocks, pl.blocks.data(), pl.blocks.size() * sizeof(Block)));
-  CK(up(e->d_codemap, e->codemap_host, 256));
-  if (!e->lut_host.empty()) CK(up(e->d_lut, e->lut_host.data(), e->lut_host.size() * 4));
-  // plan vectors are host-pageable and reused by the next stage: make the copies land first
-  CK(cudaStreamSynchronize(st));
+  {
+    const size_t blocks_bytes = pl.blocks.size() * sizeof(Block), lut_b = e->lut_host.size() * 4;
+    const size_t need = 3 * n * 4 + blocks_bytes + 256 + lut_b + 64;
+    if (e->h_plan_cap < need) {
+      if (e->h_plan) cudaFreeHost(e->h_plan);
+      e->h_plan = nullptr;
+      e->h_plan_cap = 0;
+      CK(cudaMallocHost(&e->h_plan, need + need / 4));
+      e->h_plan_cap = need + need / 4;
+    }
+    size_t pos = 0;
+    auto up_staged = [&](DevBuf& bf, const void* src, size_t bytes) -> cudaError_t {
+      if (!bytes) return cudaSuccess;
+      std::memcpy(e->h_plan + pos, src, bytes);
+      const cudaError_t ce = up(bf, e->h_plan + pos, bytes);
+      pos += (bytes + 15) & ~(size_t)15;
+      return ce;
+    };
+    CK(up_staged(e->d_order, pl.order.data(), n * 4));
+    CK(up_staged(e->d_pm, pl.pm.data(), n * 4));
+    CK(up_staged(e->d_pn, pl.pn.data(), n * 4));
+    CK(up_staged(e->d_blocks, pl.blocks.data(), blocks_bytes));
+    CK(up_staged(e->d_codemap, e->codemap_host, 256));
+    if (lut_b) CK(up_staged(e->d_lut, e->lut_host.data(), lut_b));
+  }
+  // the caller's arrays are read by the copies above: wait for them unless the caller (the chunk pipeline of
+  // b2a_align_batch) keeps them alive itself
+  if (!e->stage_nosync) CK(cudaStreamSynchronize(st));
   e->staged = true;
   return B2A_OK;
 }
@@ -520,6 +566,8 @@ int32_t b2a_batch_run(b2a_engine* e) {
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
   const Plan& pl = e->plan;
   cudaStream_t st = e->stream;
+  const bool use_tail = e->tail_stream != nullptr && pl.waves.size() == 1;  // several waves share scratch: one stream
+  e->tail_used = use_tail;
   e->launches = 0;
   uint32_t* ctl = e->d_ctl.as<uint32_t>();  // [0] bad symbol, [1] walk error, [2..] per-wave task counters
   CK(cudaMemsetAsync(ctl, 0, 256, st));
@@ -607,10 +655,16 @@ int32_t b2a_batch_run(b2a_engine* e) {
     // (running K2 inside K1's warps was measured: 28.4 ms vs 22.4 + 3.2 ms separately -- the latency-bound
     //  walk holds one of only 12 resident warps per SM; K2 stays its own launch)
     const bool fuse = false;
+    fp.task_limit = (pl.G == 32) ? 0u : e->fill_task_limit;  // strip-pipelined tasks need the persistent grid
     CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
     CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &e->last_grid));
     ++e->launches;
     CK(cudaEventRecord(e->wave_ev[3 * wi + 1], st));
+    if (use_tail) {  // K2 and everything after it on the high-priority stream
+      CK(cudaEventRecord(e->ev_fill, st));
+      CK(cudaStreamWaitEvent(e->tail_stream, e->ev_fill, 0));
+      st = e->tail_stream;
+    }
     if (!fuse) {
       // K2 shape: one lane per pair is the bandwidth-efficient form for large batches of reads (a warp's 32
       // pairs share every cache line); one WARP per pair cuts the per-pair latency chain (prefix-maximum passes,
@@ -618,7 +672,13 @@ int32_t b2a_batch_run(b2a_engine* e) {
       const uint64_t wave_pairs = (uint64_t)nb * 32;
       const bool warp_walk = e->walk_mode == 2 || (e->walk_mode == 0 && wave_pairs <= kWarpWalkMaxPairs);
       if (warp_walk) {
-        walk_warp_kernel<<<nb * 8, 128, 0, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
+        // the pair's x and y are copied into shared memory when four pairs' worth fits a CTA's budget
+        const uint32_t per_warp = ((pl.maxm + 3) / 4 + (pl.maxn + 3) / 4) * 4 + 16;
+        wp.seq_smem_per_warp = per_warp * 4 <= 96 * 1024 ? per_warp : 0u;
+        const size_t wsmem = (size_t)wp.seq_smem_per_warp * 4;
+        if (wsmem > 48 * 1024)
+          CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        walk_warp_kernel<<<nb * 8, 128, wsmem, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
       } else {
         const unsigned wgrid = (nb * 32 + 127) / 128;
         walk_kernel<<<wgrid, 128, 0, st>>>(wp);
@@ -632,7 +692,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
   }
   CK(cudaEventRecord(e->ev[4], st));
   {
-    int rc2 = compact_ops(e, pl.ops_bytes);
+    int rc2 = compact_ops(e, pl.ops_bytes, st);
     if (rc2) return rc2;
   }
   CK(cudaEventRecord(e->ev[5], st));
@@ -644,7 +704,7 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
   if (!e) return B2A_E_INVALID;
   if (!e->ran) return e->fail(B2A_E_STATE, "b2a_batch_fetch before b2a_batch_run");
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
-  cudaStream_t st = e->stream;
+  cudaStream_t st = e->res_stream();
   const uint64_t n = e->n_pairs;
   uint64_t d2h = 0;
   uint32_t ctl[2] = {0, 0};
@@ -739,7 +799,7 @@ static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results*
                            b2a_stats* agg) {
   b2a_engine* c = sl.eng;
   sl.busy = false;
-  cudaError_t ce = cudaStreamSynchronize(c->stream);
+  cudaError_t ce = cudaStreamSynchronize(c->res_stream());
   if (ce != cudaSuccess) return e->cuda_fail("pipeline: cudaStreamSynchronize", ce);
   if (sl.h_ctl[0]) return e->fail(B2A_E_INVALID, "a sequence byte is outside the scoring alphabet");
   if (sl.h_ctl[1] && !r->status) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move (reference panics at mod.rs:905)");
@@ -747,7 +807,7 @@ static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results*
   if (r->ops) {
     if (base + total > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for this batch");
     if (total) {
-      ce = cudaMemcpyAsync(r->ops + base, c->d_opsdense.p, total, cudaMemcpyDeviceToHost, c->stream);
+      ce = cudaMemcpyAsync(r->ops + base, c->d_opsdense.p, total, cudaMemcpyDeviceToHost, c->res_stream());
       if (ce != cudaSuccess) return e->cuda_fail("pipeline: ops D2H", ce);
       agg->d2h_bytes += total;
     }
@@ -755,7 +815,7 @@ static int32_t slot_finish(b2a_engine* e, b2a_engine::PipeSlot& sl, b2a_results*
   if (r->ops_off)
     for (uint64_t i = 0; i < sl.n; ++i) r->ops_off[sl.lo + i] = base + sl.h_opsoff[i];
   base += total;
-  ce = cudaStreamSynchronize(c->stream);
+  ce = cudaStreamSynchronize(c->res_stream());
   if (ce != cudaSuccess) return e->cuda_fail("pipeline: cudaStreamSynchronize", ce);
   collect_stats(c, agg);
   return B2A_OK;
@@ -810,7 +870,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     const double tc0 = now();
     if (cut[c + 1] <= cut[c]) continue;
     const uint64_t lo = cut[c], hi = cut[c + 1], nc = hi - lo;
-    b2a_engine::PipeSlot& sl = e->slots[c % 2];
+    b2a_engine::PipeSlot& sl = e->slots[c % b2a_engine::kSlots];
     if (sl.busy) {
       rc = slot_finish(e, sl, r, base, &agg);
       if (rc) break;
@@ -822,6 +882,17 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
         break;
       }
     }
+    if (!sl.eng->tail_stream) {
+      int lo_pri = 0, hi_pri = 0;
+      cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+      if (cudaStreamCreateWithPriority(&sl.eng->tail_stream, cudaStreamNonBlocking, hi_pri) != cudaSuccess ||
+          cudaEventCreateWithFlags(&sl.eng->ev_fill, cudaEventDisableTiming) != cudaSuccess) {
+        rc = e->fail(B2A_E_CUDA, "pipeline: cannot create the slot's tail stream");
+        break;
+      }
+    }
+    sl.eng->stage_nosync = true;
+    sl.eng->fill_task_limit = 1;
     sl.eng->tune_G = e->tune_G;
     sl.eng->tune_R = e->tune_R;
     sl.eng->walk_mode = e->walk_mode;
@@ -906,7 +977,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
       e->fail(rc, ch->err);
       break;
     }
-    cudaStream_t st = ch->stream;
+    cudaStream_t st = ch->res_stream();
     auto down = [&](void* dst, const DevBuf& bf, size_t bytes) -> cudaError_t {
       if (!dst || !bytes) return cudaSuccess;
       agg.d2h_bytes += bytes;
@@ -931,7 +1002,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
   }
   // drain in chunk order: the older chunk lives in the slot the next chunk would use
   // (slots hold chunks in alternation; the one with the smaller `lo` is the older)
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < b2a_engine::kSlots; ++pass) {
     b2a_engine::PipeSlot* pick = nullptr;
     for (auto& cand : e->slots)
       if (cand.busy && (!pick || cand.lo < pick->lo)) pick = &cand;
@@ -941,6 +1012,7 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
       rc = slot_finish(e, sl, r, base, &agg);
     } else {
       cudaStreamSynchronize(sl.eng->stream);
+      cudaStreamSynchronize(sl.eng->res_stream());
       sl.busy = false;
     }
   }
@@ -1229,7 +1301,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     lo += nw;
   }
   CK(cudaEventRecord(e->ev[4], st));
-  rc = compact_ops(e, ops_total);
+  rc = compact_ops(e, ops_total, st);
   if (rc) return rc;
   CK(cudaEventRecord(e->ev[5], st));
   e->plan = Plan{};

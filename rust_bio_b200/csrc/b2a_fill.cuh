@@ -41,6 +41,8 @@ struct FillParams {
   int32_t ge4;              // must be 4 * sc.gap_extend
   uint32_t* progress;       // strip-pipelined mode (G == 32): columns published per (pair, strip) task, else null
   uint32_t n_strip_tasks;   // strip-pipelined mode: number of (pair, strip) tasks of this launch
+  uint32_t task_limit;      // 0: persistent (a warp pulls tasks until none is left); k: a warp retires after k tasks, so
+                            // CTAs turn over and a higher-priority kernel's CTAs get onto the SMs (chunk pipeline)
   DevScoring sc;
 };
 
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const F
   const bool strip_tasks = (G == 32) && prm.progress != nullptr;
   const uint32_t ntasks = strip_tasks ? prm.n_strip_tasks : prm.nblocks * G;
   uint32_t parity = 0;
-  for (;;) {
+  for (uint32_t done = 0; prm.task_limit == 0 || done < prm.task_limit; ++done) {
     uint32_t task = 0;
     if (lane == 0) task = atomicAdd(prm.task_counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);

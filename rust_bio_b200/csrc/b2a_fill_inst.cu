@@ -26,6 +26,7 @@ cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t
   const uint32_t want = (ntasks + FILL_WARPS - 1) / FILL_WARPS;
   uint32_t grid = (uint32_t)(num_sms * per_sm);
   if (grid > want) grid = want;
+  if (prm.task_limit) grid = (want + prm.task_limit - 1) / prm.task_limit;  // every warp retires after task_limit tasks
   if (grid < 1) grid = 1;
   if (grid_out) *grid_out = (int)grid;
   kern<<<grid, FILL_WARPS * 32, smem, stream>>>(prm);

@@ -33,6 +33,7 @@ struct WalkParams {
   int32_t G, R;
   int32_t filter_clips;  // semiglobal / local: Alignment::filter_clip_operations
   int32_t packtrk;       // K1 ran with F_PACKTRK (how the column tracker in the boundary row is encoded)
+  uint32_t seq_smem_per_warp;  // warp-per-pair K2: bytes of shared memory per warp for the pair's x and y (0: none)
   // outputs, indexed by the caller's pair index
   int32_t* score;
   uint32_t* xstart;
@@ -66,13 +67,17 @@ struct PairView {
   int32_t maxn;        // block maximum of n
   int64_t bnd_base;    // boundary row of this pair: bnd[bnd_base + j * bnd_stride] (see bnd_index)
   int32_t bnd_stride;
+  const uint8_t* xs8 = nullptr;  // warp-per-pair K2: the pair's staged x / y copied into shared memory (or null)
+  const uint8_t* ys8 = nullptr;
 
   B2A_HD int32_t xsym(int32_t i) const {  // x[i-1]
     const int32_t b = i - 1;
+    if (xs8) return (int32_t)xs8[b];
     return (int32_t)((xw[(b >> 2) * P] >> (8 * (b & 3))) & 0xffu);
   }
   B2A_HD int32_t ysym(int32_t j) const {
     const int32_t b = j - 1;
+    if (ys8) return (int32_t)ys8[b];
     return (int32_t)((yw[(b >> 2) * P] >> (8 * (b & 3))) & 0xffu);
   }
   B2A_HD int32_t score(int32_t p, int32_t q) const {
@@ -662,6 +667,8 @@ B2A_HD void walk_pair(const PairView& v, const bool filter_clips, uint8_t* ops_e
 // All arithmetic is exact (the engine's range guard keeps every real score within +-2^27).  The walk itself
 // stays on lane 0 (each move depends on the cell the previous one read); the other lanes pull the traceback
 // words along the diagonal ahead of it into the cache.
+B2A_HD int32_t imin32(int32_t a, int32_t b) { return a < b ? a : b; }
+
 template <int W>
 B2A_HD int32_t coop_scan_max(int lane, int32_t v) {  // inclusive prefix maximum over the lanes
   using C = Coop<W>;
@@ -756,11 +763,16 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
   uint32_t csb = sb0;                // s_bits(m, j-1)
   int32_t SmN = 0, ImN = MIN_SCORE;
   uint32_t cmN = 0;
+  // the boundary row of the NEXT chunk is requested before this chunk's chain is resolved (the loads do not
+  // depend on the carries), so every chunk after the first finds its operands already on the way
+  int4 braw_next = v.load_bnd(imin32(1 + lane, n));
   for (int32_t base = 1; base <= n; base += W) {
     const int32_t j = base + lane;
     const bool act = j <= n;
     const int32_t jc = act ? j : n;  // idle lanes repeat the last column: loads stay in bounds, nothing is stored
-    const Boundary b = decode_boundary(v.load_bnd(jc), pk, xs, m);
+    const int4 braw = braw_next;
+    if (base + W <= n) braw_next = v.load_bnd(imin32(base + W + lane, n));
+    const Boundary b = decode_boundary(braw, pk, xs, m);
     const int32_t q = v.ysym(jc);
     int32_t sdiag = C::up(b.S, 1);
     if (lane == 0) sdiag = cSup;
@@ -873,13 +885,26 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
   {
     uint32_t c_above = cell_s(c0);  // pre-fix-up s_bits of the row above the chunk
     const int32_t yn = v.ysym(n);
+    int32_t nb_next, S_next, Sn_next = MIN_SCORE;
+    {
+      const int32_t i0 = imin32(1 + lane, m - 1);
+      nb_next = v.row(ROWS_NL, i0);
+      S_next = v.row(ROWS_SL, i0);
+      if (ys_live) Sn_next = v.row(ROWS_SN, i0);
+    }
     for (int32_t base = 1; base < m; base += W) {
       const int32_t i = base + lane;
       const bool act = i < m;
       const int32_t ic = act ? i : m - 1;
-      const uint32_t nb = (uint32_t)v.row(ROWS_NL, ic);
-      int32_t S = v.row(ROWS_SL, ic);
-      const int32_t Sn = ys_live ? v.row(ROWS_SN, ic) : MIN_SCORE;
+      const uint32_t nb = (uint32_t)nb_next;
+      int32_t S = S_next;
+      const int32_t Sn = Sn_next;
+      if (base + W < m) {  // next chunk's operands
+        const int32_t i1 = imin32(base + W + lane, m - 1);
+        nb_next = v.row(ROWS_NL, i1);
+        S_next = v.row(ROWS_SL, i1);
+        if (ys_live) Sn_next = v.row(ROWS_SN, i1);
+      }
       uint32_t sbi;
       switch (nb & 3u) {
         case NB_DIAG: sbi = v.xsym(ic) == yn ? TB_MATCH : TB_SUBST; break;
@@ -927,12 +952,25 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
     cSp = S;
     ccell = cell;
   }
+  int32_t I_next, S2_next, c_next;
+  {
+    const int32_t i0 = imin32(1 + lane, m - 1);
+    I_next = v.row(ROWS_IL, i0);
+    S2_next = v.row(ROWS_SL, i0);
+    c_next = v.row(ROWS_NL, i0);
+  }
   for (int32_t base = 1; base < m; base += W) {
     const int32_t i = base + lane;
     const bool act = i < m;
     const int32_t ic = act ? i : m - 1;
-    int32_t I = v.row(ROWS_IL, ic), S = v.row(ROWS_SL, ic);
-    uint32_t cell = (uint32_t)v.row(ROWS_NL, ic);
+    int32_t I = I_next, S = S2_next;
+    uint32_t cell = (uint32_t)c_next;
+    if (base + W < m) {
+      const int32_t i1 = imin32(base + W + lane, m - 1);
+      I_next = v.row(ROWS_IL, i1);
+      S2_next = v.row(ROWS_SL, i1);
+      c_next = v.row(ROWS_NL, i1);
+    }
     // S'(i) - go*i = max(S'(i-1) - go*(i-1) ... ) : inclusive running maximum of S(k) - go*k, seeded by the carry
     int32_t t = S - go * ic;
     if (lane == 0) t = imax(t, cSp + go - go * ic);
@@ -1091,7 +1129,8 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
 }
 
 // K2, one warp per pair
-__device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& blk, const int pi, const int lane) {
+__device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& blk, const int pi, const int lane,
+                                          uint8_t* seq_smem) {
   const uint32_t sp = blk.first + pi;
   const int32_t P = 32 / prm.G;
   PairView v;
@@ -1120,6 +1159,16 @@ __device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& bl
   v.rows_pad = (int32_t)blk.rows_pad;
   v.rowm = reinterpret_cast<uint16_t*>(prm.rowm + blk.rowm_off);
   v.tb = reinterpret_cast<const uint32_t*>(prm.tb + blk.tb_off);
+  if (seq_smem) {  // this warp's slice of the CTA's dynamic shared memory: x bytes, then y bytes (word granules)
+    const int32_t xwn = (v.m + 3) >> 2, ywn = (v.n + 3) >> 2;
+    uint32_t* xs = reinterpret_cast<uint32_t*>(seq_smem);
+    uint32_t* ys = xs + ((blk.maxm + 3) >> 2);
+    for (int32_t w = lane; w < xwn; w += 32) xs[w] = v.xw[(size_t)w * P];
+    for (int32_t w = lane; w < ywn; w += 32) ys[w] = v.yw[(size_t)w * P];
+    __syncwarp();
+    v.xs8 = reinterpret_cast<const uint8_t*>(xs);
+    v.ys8 = reinterpret_cast<const uint8_t*>(ys);
+  }
   const uint32_t cap = blk.maxm + blk.maxn + 4;
   uint8_t* ops_end = prm.ops_scratch + blk.ops_off + (size_t)(pi + 1) * cap;
   WalkOut o;
@@ -1146,14 +1195,16 @@ __device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& bl
 }
 
 #if defined(B2A_DEFINE_WALK_KERNEL)  // one translation unit (b2a_engine.cu) owns the stand-alone kernel
-__global__ void __launch_bounds__(128) walk_warp_kernel(const WalkParams prm) {
+__global__ void __launch_bounds__(128, 8) walk_warp_kernel(const WalkParams prm) {
+  extern __shared__ __align__(16) uint8_t walk_smem[];  // seq_smem_per_warp bytes per warp, or none
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (block, pair)
   const int lane = threadIdx.x & 31;
   const uint32_t b = gw >> 5, pi = gw & 31u;
   if (b >= prm.nblocks) return;
   const Block blk = prm.blocks[b];
   if (pi >= blk.npairs) return;
-  walk_warp(prm, blk, (int)pi, lane);
+  uint8_t* mine = prm.seq_smem_per_warp ? walk_smem + (size_t)(threadIdx.x >> 5) * prm.seq_smem_per_warp : nullptr;
+  walk_warp(prm, blk, (int)pi, lane, mine);
 }
 
 __global__ void __launch_bounds__(128, 8) walk_kernel(const WalkParams prm) {

@@ -402,11 +402,12 @@ def test_c5_shape_8_pairs_10k_x_10k_blosum62_local(eng, oracle):
     assert eng.stats.fill_lanes_per_pair == 32
     assert_same(got, ops, ref, ref_ops, batch, "C5 local blosum62 auto shape")
     blob, xo, xl, yo, yl = batch
+    flat = np.asarray(table).reshape(-1)
     for p in range(8):  # and independent of the oracle: the path re-scores to the score
         x = bytes(blob[int(xo[p]):int(xo[p]) + 10000])
         y = bytes(blob[int(yo[p]):int(yo[p]) + 10000])
         f = {k: got[k][p] for k in ("xstart", "xend", "ystart", "yend")}
-        assert rescore_path(x, y, ops[p], f, "local", -10, -1, lambda a, b: int(table[a * 256 + b])) == int(got["score"][p])
+        assert rescore_path(x, y, ops[p], f, "local", -10, -1, lambda a, b: int(flat[a * 256 + b])) == int(got["score"][p])
 
 
 @pytest.mark.parametrize("G,R", [(8, 16), (32, 16), (32, 8), (4, 16)])

@@ -167,7 +167,7 @@ int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes);
 int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t rows_per_lane);
 
 /* K2 (row m, last-column fix-ups, traceback walk) runs one lane per pair (1) or one warp per pair (2);
- * 0 = automatic: warp per pair for waves of up to 131,072 pairs.  Results are identical either way. */
+ * 0 = automatic: warp per pair for waves of up to 16,384 pairs.  Results are identical either way. */
 int32_t b2a_engine_set_walk(b2a_engine* e, int32_t mode);
 
 /* b2a_align_batch cuts batches of >= 262,144 pairs into `chunks` pieces that alternate between two

@@ -116,7 +116,34 @@ def align_batch(mode, scoring: OrcScoring, blob, x_off, x_len, y_off, y_len, thr
 
 
 def hardware_threads() -> int:
-    return int(lib().orc_hardware_threads())
+    """Host threads worth starting: the CPUs in this process's affinity mask, capped by the cgroup CPU quota when
+    there is one (a container that sees 128 CPUs but may only use 16 CPUs' worth of time runs 128 threads no
+    faster than 16, and much less predictably)."""
+    n = int(lib().orc_hardware_threads())
+    q = cpu_quota()
+    if q is not None:
+        n = max(1, min(n, int(q + 0.999)))
+    return n
+
+
+def cpu_quota():
+    """CPUs' worth of time the cgroup allows (cgroup v2 cpu.max, v1 cfs quota), or None if unlimited/unknown."""
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            a, b = f.read().split()[:2]
+        if a != "max":
+            return float(a) / float(b)
+        return None
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+            q = float(f.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+            p = float(f.read())
+        return q / p if q > 0 else None
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------ banded::Aligner + sparse pieces

@@ -68,7 +68,7 @@ const FillLaunch* find_shape(int G, int R) {
 }
 
 constexpr uint32_t kMaxStageSmem = 200 * 1024;  // of the 227 KB a CTA may use
-constexpr uint64_t kWarpWalkMaxPairs = 131072;  // waves up to this many pairs use the warp-per-pair K2
+constexpr uint64_t kWarpWalkMaxPairs = 16384;  // waves up to this many pairs use the warp-per-pair K2
 constexpr int kMaxAlpha = 64;
 
 }  // namespace
@@ -80,6 +80,9 @@ struct b2a_engine {
   // pipeline slots only: K2 + ops compaction + result copies run on this high-priority stream, so that an
   // older chunk's short, latency-bound tail is scheduled ahead of the next chunk's fill CTAs
   cudaStream_t tail_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // second fill stream of the small-batch overlap (b2a_batch_run)
+  std::vector<cudaEvent_t> sub_ev;
+  bool overlap_small = true;
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
   bool stage_nosync = false;       // pipeline slots: the caller's arrays outlive the call, no sync at the end of stage
@@ -162,7 +165,7 @@ void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_
     return;
   }
   const uint64_t stage1 = (uint64_t)((maxm + 15) / 16 * 16 + 64 + (maxn + 15) / 16 * 16 + 64) * 32 * FILL_WARPS;
-  if (n_pairs >= 32ull * 148 * 4 && stage1 <= kMaxStageSmem && maxm <= 2048) {
+  if (n_pairs >= 49152 && stage1 <= kMaxStageSmem && maxm <= 2048) {  // measured: 8x20 wins below ~50k reads of 150
     *G = 1;
     *R = 16;
   } else if ((n_pairs >= 4096 && maxm <= 4096) || maxm <= 161) {
@@ -218,6 +221,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   b2a_engine* e = new b2a_engine();
   e->device = device_id;
   e->num_sms = prop.multiProcessorCount;
+  if (const char* env = getenv("B2A_NO_OVERLAP")) e->overlap_small = atoi(env) == 0;
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return B2A_E_CUDA;
@@ -243,6 +247,11 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
     cudaStreamDestroy(e->tail_stream);
   }
   if (e->ev_fill) cudaEventDestroy(e->ev_fill);
+  if (e->aux_stream) {
+    cudaStreamSynchronize(e->aux_stream);
+    cudaStreamDestroy(e->aux_stream);
+  }
+  for (auto& v : e->sub_ev) cudaEventDestroy(v);
   if (e->h_plan) cudaFreeHost(e->h_plan);
   if (e->h_nops) cudaFreeHost(e->h_nops);
   DevBuf* bufs[] = {&e->d_blob, &e->d_xoff, &e->d_xlen, &e->d_yoff, &e->d_ylen, &e->d_order, &e->d_pm,
@@ -656,6 +665,69 @@ int32_t b2a_batch_run(b2a_engine* e) {
     //  walk holds one of only 12 resident warps per SM; K2 stays its own launch)
     const bool fuse = false;
     fp.task_limit = (pl.G == 32) ? 0u : e->fill_task_limit;  // strip-pipelined tasks need the persistent grid
+    const uint64_t wave_pairs = (uint64_t)nb * 32;
+    const bool warp_walk = e->walk_mode == 2 || (e->walk_mode == 0 && wave_pairs <= kWarpWalkMaxPairs);
+    uint32_t per_warp_smem = 0;
+    if (warp_walk) {
+      // the pair's x and y are copied into shared memory when four pairs' worth fits a CTA's budget
+      const uint32_t per_warp = ((pl.maxm + 3) / 4 + (pl.maxn + 3) / 4) * 4 + 16;
+      per_warp_smem = per_warp * 4 <= 96 * 1024 ? per_warp : 0u;
+      if ((size_t)per_warp_smem * 4 > 48 * 1024)
+        CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_warp_smem * 4));
+    }
+    wp.seq_smem_per_warp = per_warp_smem;
+    // Small batches (a few thousand pairs: neither kernel fills the GPU): the wave is cut into sub-ranges of
+    // blocks whose fills alternate between two streams (they overlap: the next fill's CTAs take the SM slots the
+    // previous one's leave) and whose walks run on a high-priority stream as soon as their own fill is done --
+    // K2 of sub-range s overlaps K1 of sub-range s+1, and only the last sub-range's K2 is exposed.
+    const bool overlap = e->overlap_small && pl.waves.size() == 1 && warp_walk && pl.G != 32 && nb >= 64 &&
+                         !use_tail && e->walk_mode != 1;
+    if (overlap) {
+      constexpr int kSub = 4;
+      if (!e->tail_stream) {
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        CK(cudaStreamCreateWithPriority(&e->tail_stream, cudaStreamNonBlocking, hi_pri));
+        CK(cudaEventCreateWithFlags(&e->ev_fill, cudaEventDisableTiming));
+      }
+      if (!e->aux_stream) CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+      while (e->sub_ev.size() < kSub + 2) {
+        cudaEvent_t v;
+        CK(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+        e->sub_ev.push_back(v);
+      }
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
+      CK(cudaEventRecord(e->sub_ev[kSub], st));  // K0 and the counters' memset are done
+      CK(cudaStreamWaitEvent(e->aux_stream, e->sub_ev[kSub], 0));
+      CK(cudaStreamWaitEvent(e->tail_stream, e->sub_ev[kSub], 0));
+      for (int sidx = 0; sidx < kSub; ++sidx) {
+        const uint32_t lo_b = (uint32_t)((uint64_t)nb * sidx / kSub), hi_b = (uint32_t)((uint64_t)nb * (sidx + 1) / kSub);
+        if (hi_b <= lo_b) continue;
+        cudaStream_t fs = (sidx & 1) ? e->aux_stream : st;
+        FillParams f2 = fp;
+        f2.blocks = fp.blocks + lo_b;
+        f2.nblocks = hi_b - lo_b;
+        f2.task_counter = ctl + 8 + sidx;
+        f2.task_limit = 1;  // CTAs retire after one task per warp: the walks' CTAs get onto the SMs in between
+        CK(e->shape->launch(e->flags, f2, f2.nblocks * (uint32_t)pl.G, e->num_sms, fs, &e->last_grid));
+        ++e->launches;
+        CK(cudaEventRecord(e->sub_ev[sidx], fs));
+        CK(cudaStreamWaitEvent(e->tail_stream, e->sub_ev[sidx], 0));
+        if (sidx == kSub - 1) CK(cudaEventRecord(e->wave_ev[3 * wi + 1], e->tail_stream));  // every fill has finished
+        WalkParams w2 = wp;
+        w2.blocks = wp.blocks + lo_b;
+        w2.nblocks = hi_b - lo_b;
+        walk_warp_kernel<<<w2.nblocks * 8, 128, (size_t)per_warp_smem * 4, e->tail_stream>>>(w2);
+        CK(cudaGetLastError());
+        ++e->launches;
+      }
+      CK(cudaEventRecord(e->sub_ev[kSub + 1], e->tail_stream));
+      CK(cudaStreamWaitEvent(st, e->sub_ev[kSub + 1], 0));  // everything rejoins the engine's stream
+      e->last_walk_warp = true;
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 2], st));
+      ++wi;
+      continue;
+    }
     CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
     CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &e->last_grid));
     ++e->launches;
@@ -669,16 +741,8 @@ int32_t b2a_batch_run(b2a_engine* e) {
       // K2 shape: one lane per pair is the bandwidth-efficient form for large batches of reads (a warp's 32
       // pairs share every cache line); one WARP per pair cuts the per-pair latency chain (prefix-maximum passes,
       // prefetched walk) and is what small / medium batches and long sequences need (b2a_walk.cuh).
-      const uint64_t wave_pairs = (uint64_t)nb * 32;
-      const bool warp_walk = e->walk_mode == 2 || (e->walk_mode == 0 && wave_pairs <= kWarpWalkMaxPairs);
       if (warp_walk) {
-        // the pair's x and y are copied into shared memory when four pairs' worth fits a CTA's budget
-        const uint32_t per_warp = ((pl.maxm + 3) / 4 + (pl.maxn + 3) / 4) * 4 + 16;
-        wp.seq_smem_per_warp = per_warp * 4 <= 96 * 1024 ? per_warp : 0u;
-        const size_t wsmem = (size_t)wp.seq_smem_per_warp * 4;
-        if (wsmem > 48 * 1024)
-          CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-        walk_warp_kernel<<<nb * 8, 128, wsmem, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
+        walk_warp_kernel<<<nb * 8, 128, (size_t)per_warp_smem * 4, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
       } else {
         const unsigned wgrid = (nb * 32 + 127) / 128;
         walk_kernel<<<wgrid, 128, 0, st>>>(wp);

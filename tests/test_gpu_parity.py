@@ -410,7 +410,7 @@ def test_c5_shape_8_pairs_10k_x_10k_blosum62_local(eng, oracle):
         assert rescore_path(x, y, ops[p], f, "local", -10, -1, lambda a, b: int(flat[a * 256 + b])) == int(got["score"][p])
 
 
-@pytest.mark.parametrize("G,R", [(8, 16), (32, 16), (32, 8), (4, 16)])
+@pytest.mark.parametrize("G,R", [(8, 16), (8, 20), (32, 16), (32, 8)])
 @pytest.mark.parametrize("lut", [True, False], ids=["lut", "matchparams_wide_alphabet"])
 def test_unpacked_tracker_variants_4200(eng, oracle, G, R, lut):
     """m, n > 4095 in every mode: the fill_kernel<G,R,FLAGS> instantiations without F_PACKTRK
@@ -612,3 +612,23 @@ def test_both_walk_kernels_every_mode(eng, oracle, walk):
     finally:
         eng.set_walk(0)
         eng.set_tuning(0, 0)
+
+
+@pytest.mark.parametrize("mode,clips", [("local", (MIN,) * 4), ("global", (MIN,) * 4), ("custom", (-3, 0, -2, -5))])
+def test_small_batch_overlap_of_fills_and_walks(eng, oracle, mode, clips):
+    """2,048 .. 16,384 pairs: the wave is cut into four sub-ranges whose fills alternate between two streams and
+    whose warp-per-pair walks run on a high-priority stream (b2a_batch_run): same results as the oracle, run
+    three times in a row on the same staged batch (stale scratch must not leak)."""
+    from rust_bio_b200 import synth
+    from rust_bio_b200.engine import Results
+    batch = synth.ragged_pairs(4242, 6000, 150, 170, min_len=100)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, *clips)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1, clips)
+    eng.stage(MODES[mode], cs, batch)
+    for rep in range(3):
+        eng.run()
+        res = Results(6000, int(eng.default_ops_capacity(batch)))
+        eng.fetch(res)
+        assert_same(res.as_dict(), [res.ops_of(i) for i in range(6000)], ref, ref_ops, batch, f"overlap {mode} rep {rep}")
+    assert eng.stats.kernel_launches >= 9  # K0 + 4 fills + 4 walks (+ compaction): the overlapped form ran

@@ -15,8 +15,10 @@ ap.add_argument("--c4-pairs", type=int, default=20000)
 ap.add_argument("--c5-pairs", type=int, default=64)
 ap.add_argument("--shapes", default="")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--walk", type=int, default=0)
 a = ap.parse_args()
 eng = Engine(0)
+eng.set_walk(a.walk)
 import ctypes as C
 
 
@@ -36,7 +38,7 @@ def run_full(name, mode, cs, batch, keep=None):
                 if best is None or st.fill_ms < best["fill_ms"]:
                     best = dict(fill_ms=st.fill_ms, walk_ms=st.walk_ms, pack_ms=st.pack_ms)
             tot = best["fill_ms"] + best["walk_ms"] + best["pack_ms"]
-            print(json.dumps({"config": name, "pairs": len(batch[2]), "G": st.fill_lanes_per_pair, "R": st.fill_rows_per_lane,
+            print(json.dumps({"config": name, "walk": a.walk, "pairs": len(batch[2]), "G": st.fill_lanes_per_pair, "R": st.fill_rows_per_lane,
                               "waves": st.waves, **{k: round(v, 3) for k, v in best.items()},
                               "fill_gcups": round(st.cells / best["fill_ms"] / 1e6, 1),
                               "step_gcups": round(st.cells / tot / 1e6, 1), "tb_GB": round(st.traceback_bytes / 2**30, 2),

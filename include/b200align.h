@@ -180,6 +180,27 @@ int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks);
 int32_t b2a_align_batch(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
                         const b2a_pairs* pairs, b2a_results* results, b2a_stats* stats);
 
+/* Packed input: the sequences as bio::data_structures::bitenc::BitEnc storage
+ * (src/data_structures/bitenc.rs:50-56: 32-bit blocks, `width` bits per symbol, 32 - 32 % width usable bits per
+ * block; symbol i sits at bit (i*width) % usable of block (i*width) / usable, bitenc.rs:319-338), holding the ranks
+ * alphabets::RankTransform::transform yields (src/alphabets/mod.rs:220-283).  x_block / y_block are block indices
+ * into `blocks`.  The packed blocks are what crosses PCIe (width 2: a quarter of the bytes); scores are those of
+ * `scoring` applied to the RANKS: MatchParams by equality, `table[a*256+b]` indexed by rank. */
+typedef struct b2a_packed_pairs {
+  const uint32_t* blocks;   /* all BitEnc storages, concatenated */
+  const uint64_t* x_block;  /* [n_pairs] first block of x */
+  const uint32_t* x_len;    /* [n_pairs] symbols (BitEnc::nr_symbols) */
+  const uint64_t* y_block;
+  const uint32_t* y_len;
+  uint64_t n_blocks;
+  uint64_t n_pairs;
+  uint32_t width;           /* BitEnc::new(width), 1..8 */
+} b2a_packed_pairs;
+int32_t b2a_align_batch_packed(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,
+                               const b2a_packed_pairs* pairs, b2a_results* results, b2a_stats* stats);
+int32_t b2a_align_batch_banded_packed(b2a_engine* e, int32_t mode, const b2a_scoring* scoring, uint32_t k, uint32_t w,
+                                      const b2a_packed_pairs* pairs, b2a_results* results, b2a_stats* stats);
+
 /* banded::Aligner::{custom,global,semiglobal,local} (banded.rs:282,872,901,942)
  * with k-mer length k and band half-width w (banded.rs:150-180). */
 int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* scoring,

@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "b2a_align_batch", "b2a_align_batch_banded", "b2a_align_batch_banded_hinted", "b2a_banded_band_ranges", "b2a_batch_stage", "b2a_batch_run",
     "b2a_batch_fetch", "b2a_batch_records", "b2a_batch_records_into", "b2a_record_stride",
     "b2a_records_decode", "b2a_batch_compact_bytes", "b2a_batch_compact_into", "b2a_compact_decode",
-    "b2a_batch_compact_fixed", "b2a_gathered_fetch",
+    "b2a_batch_compact_fixed", "b2a_gathered_fetch", "b2a_align_batch_packed", "b2a_align_batch_banded_packed",
     "b2a_util_int32_peak",
 ]
 
@@ -42,6 +42,12 @@ class CPairs(C.Structure):
     _fields_ = [("seq_blob", C.c_void_p), ("x_off", C.c_void_p), ("x_len", C.c_void_p),
                 ("y_off", C.c_void_p), ("y_len", C.c_void_p), ("blob_bytes", C.c_uint64),
                 ("n_pairs", C.c_uint64)]
+
+
+class CPackedPairs(C.Structure):
+    """b2a_packed_pairs (include/b200align.h): BitEnc storage as the batch input"""
+    _fields_ = [("blocks", C.c_void_p), ("x_block", C.c_void_p), ("x_len", C.c_void_p), ("y_block", C.c_void_p),
+                ("y_len", C.c_void_p), ("n_blocks", C.c_uint64), ("n_pairs", C.c_uint64), ("width", C.c_uint32)]
 
 
 class CBandHints(C.Structure):
@@ -121,6 +127,10 @@ def load():
     L.b2a_batch_compact_fixed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.b2a_gathered_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(CResults),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.b2a_align_batch_packed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.POINTER(CPackedPairs),
+                                         C.POINTER(CResults), C.POINTER(CStats)]
+    L.b2a_align_batch_banded_packed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.c_uint32, C.c_uint32,
+                                                C.POINTER(CPackedPairs), C.POINTER(CResults), C.POINTER(CStats)]
     L.b2a_util_int32_peak.argtypes = [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]
     for name in ABI_SYMBOLS:

@@ -85,6 +85,7 @@ struct b2a_engine {
   bool overlap_small = true;
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
+  bool is_slot = false;            // this engine is a slot of another engine's chunk pipeline
   bool stage_nosync = false;       // pipeline slots: the caller's arrays outlive the call, no sync at the end of stage
   uint32_t fill_task_limit = 0;    // pipeline slots: fill CTAs retire after this many tasks per warp (CTA turnover)
   uint8_t* h_plan = nullptr;       // pinned staging of the plan vectors (async H2D)
@@ -98,6 +99,10 @@ struct b2a_engine {
   std::string err;
   int tune_G = 0, tune_R = 0;
   int walk_mode = 0;  // 0 automatic, 1 one lane per pair, 2 one warp per pair
+  // packed input (b2a_align_batch_packed): the caller's "blob" is BitEnc storage of this width (0 = bytes); the
+  // engine unpacks it on the device and uses its own byte offsets (eff_xoff / eff_yoff) from then on
+  uint32_t packed_width = 0;
+  std::vector<uint64_t> eff_xoff, eff_yoff;
   bool last_walk_warp = false;
   uint64_t tb_budget = 0;
 
@@ -116,7 +121,7 @@ struct b2a_engine {
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
       d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
-      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx;
+      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx, d_raw;
   uint32_t* h_nops = nullptr;  // pinned staging of b2a_gathered_fetch
   uint64_t h_nops_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -156,6 +161,38 @@ struct b2a_engine {
   } while (0)
 
 namespace {
+
+// 32-bit blocks a BitEnc of `len` symbols of `width` bits occupies (bitenc.rs:332-338: 32 - 32 % width usable
+// bits per block)
+inline uint64_t bitenc_blocks(uint64_t len, uint32_t width) {
+  const uint64_t usable = 32 - 32 % width;
+  return (len * width + usable - 1) / usable;
+}
+
+// BitEnc storage -> one byte per symbol (ranks), one warp per sequence (x and y of every pair)
+__global__ void __launch_bounds__(128) unpack_bitenc_kernel(const uint32_t* __restrict__ blocks,
+                                                             const uint64_t* __restrict__ x_block,
+                                                             const uint64_t* __restrict__ y_block,
+                                                             const uint64_t* __restrict__ x_off,
+                                                             const uint64_t* __restrict__ y_off,
+                                                             const uint32_t* __restrict__ x_len,
+                                                             const uint32_t* __restrict__ y_len, uint64_t n_pairs,
+                                                             uint32_t width, uint8_t* __restrict__ out) {
+  const uint32_t usable = 32 - 32 % width, per_block = usable / width, mask = (1u << width) - 1u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < 2 * n_pairs; t += nwarps) {
+    const uint64_t p = t >> 1;
+    const bool isy = t & 1;
+    const uint32_t* src = blocks + (isy ? y_block[p] : x_block[p]);
+    uint8_t* dst = out + (isy ? y_off[p] : x_off[p]);
+    const uint32_t len = isy ? y_len[p] : x_len[p];
+    for (uint32_t i = lane; i < len; i += 32) {
+      const uint32_t blk = i / per_block, bit = (i % per_block) * width;  // bitenc.rs:319-321, 332-338
+      dst[i] = (uint8_t)((src[blk] >> bit) & mask);
+    }
+  }
+}
 
 // pick the fill shape for a batch (measured crossover: see DESIGN.md "shape selection")
 void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_pairs, int* G, int* R) {
@@ -260,7 +297,7 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
                     &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_prog, &e->d_bcells,
                     &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill, &e->d_hmoff, &e->d_hmxy,
-                    &e->d_hpoff, &e->d_hpidx,
+                    &e->d_hpoff, &e->d_hpidx, &e->d_raw,
                     &e->d_bfoff};
   for (DevBuf* b : bufs) b->release();
   for (auto& v : e->ev)
@@ -349,10 +386,14 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   // lengths / offsets sanity
   maxm = 0;
   maxn = 0;
+  const uint32_t pw = e->packed_width;  // 0: bytes; else offsets and blob size are in 32-bit BitEnc blocks
+  const uint64_t unit_total = pw ? pairs->blob_bytes / 4 : pairs->blob_bytes;
   for (uint64_t p = 0; p < n; ++p) {
     // offset + length may not wrap: compare each against what is left of the blob
-    const uint64_t bb = pairs->blob_bytes, xo = pairs->x_off[p], yo = pairs->y_off[p];
-    if (xo > bb || pairs->x_len[p] > bb - xo || yo > bb || pairs->y_len[p] > bb - yo)
+    const uint64_t bb = unit_total, xo = pairs->x_off[p], yo = pairs->y_off[p];
+    const uint64_t xu = pw ? bitenc_blocks(pairs->x_len[p], pw) : pairs->x_len[p];
+    const uint64_t yu = pw ? bitenc_blocks(pairs->y_len[p], pw) : pairs->y_len[p];
+    if (xo > bb || xu > bb - xo || yo > bb || yu > bb - yo)
       return e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
     maxm = std::max(maxm, pairs->x_len[p]);
     maxn = std::max(maxn, pairs->y_len[p]);
@@ -369,13 +410,53 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
     e->h2d_bytes += bytes;
     return bytes ? cudaMemcpyAsync(bf.p, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
   };
-  CK(e->d_blob.reserve(pairs->blob_bytes + 16));
   CK(e->d_ctl.reserve(2048));
-  CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
   bool present[256] = {false};
+  if (pw) {
+    // BitEnc storage in, one byte per symbol on the device: the packed blocks are what crosses PCIe (4x fewer
+    // bytes at width 2), an unpack pass writes the byte blob K0 / K4 read, at 16-byte aligned offsets of our own
+    e->eff_xoff.resize(n);
+    e->eff_yoff.resize(n);
+    uint64_t pos = 0;
+    for (uint64_t p = 0; p < n; ++p) {
+      e->eff_xoff[p] = pos;
+      pos += ((uint64_t)pairs->x_len[p] + 15) & ~15ull;
+      e->eff_yoff[p] = pos;
+      pos += ((uint64_t)pairs->y_len[p] + 15) & ~15ull;
+    }
+    e->blob_bytes = pos;
+    CK(e->d_raw.reserve(pairs->blob_bytes + 16));
+    CK(e->d_blob.reserve(pos + 16));
+    CK(e->d_xoff.reserve(n * 8 + 8));
+    CK(e->d_yoff.reserve(n * 8 + 8));
+    CK(e->d_xlen.reserve(n * 4 + 4));
+    CK(e->d_ylen.reserve(n * 4 + 4));
+    CK(e->d_opssrc.reserve(n * 8 + 8));
+    CK(e->d_nops64.reserve((n + 1) * 8));
+    CK(up(e->d_raw, pairs->seq_blob, pairs->blob_bytes));
+    // block indices ride in two scratch arrays that are not in use yet (d_opssrc, d_nops64)
+    CK(up(e->d_opssrc, pairs->x_off, n * 8));
+    CK(up(e->d_nops64, pairs->y_off, n * 8));
+    CK(up(e->d_xoff, e->eff_xoff.data(), n * 8));
+    CK(up(e->d_yoff, e->eff_yoff.data(), n * 8));
+    CK(up(e->d_xlen, pairs->x_len, n * 4));
+    CK(up(e->d_ylen, pairs->y_len, n * 4));
+    if (n) {
+      unpack_bitenc_kernel<<<(unsigned)std::min<uint64_t>((2 * n + 3) / 4, 1u << 20), 128, 0, st>>>(
+          e->d_raw.as<uint32_t>(), e->d_opssrc.as<uint64_t>(), e->d_nops64.as<uint64_t>(), e->d_xoff.as<uint64_t>(),
+          e->d_yoff.as<uint64_t>(), e->d_xlen.as<uint32_t>(), e->d_ylen.as<uint32_t>(), n, pw, e->d_blob.as<uint8_t>());
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));  // eff_xoff / eff_yoff are pageable vectors reused by the next call
+    if (!(s->alphabet && s->alphabet_len))
+      for (uint32_t k = 0; k < (1u << pw); ++k) present[k] = true;  // the ranks a BitEnc of this width can hold
+  } else {
+    CK(e->d_blob.reserve(pairs->blob_bytes + 16));
+    CK(up(e->d_blob, pairs->seq_blob, pairs->blob_bytes));
+  }
   if (s->alphabet && s->alphabet_len) {  // caller-supplied alphabet (tabulated MatchFunc or MatchParams alike)
     for (uint32_t k = 0; k < s->alphabet_len; ++k) present[s->alphabet[k]] = true;
-  } else {
+  } else if (!pw) {
     uint32_t* flags = e->d_ctl.as<uint32_t>() + 256;  // 256 words
     CK(cudaMemsetAsync(flags, 0, 1024, st));
     if (pairs->blob_bytes) {
@@ -533,10 +614,12 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
   // host -> device.  The plan vectors go through a pinned staging arena so that their copies are truly
   // asynchronous (a copy from pageable memory first waits for the stream: it would serialise the host with the
   // blob's H2D in the chunk pipeline).
-  CK(up(e->d_xoff, pairs->x_off, n * 8));
-  CK(up(e->d_yoff, pairs->y_off, n * 8));
-  CK(up(e->d_xlen, pairs->x_len, n * 4));
-  CK(up(e->d_ylen, pairs->y_len, n * 4));
+  if (!e->packed_width) {  // (packed input: stage_front already placed offsets and lengths)
+    CK(up(e->d_xoff, pairs->x_off, n * 8));
+    CK(up(e->d_yoff, pairs->y_off, n * 8));
+    CK(up(e->d_xlen, pairs->x_len, n * 4));
+    CK(up(e->d_ylen, pairs->y_len, n * 4));
+  }
   {
     const size_t blocks_bytes = pl.blocks.size() * sizeof(Block), lut_b = e->lut_host.size() * 4;
     const size_t need = 3 * n * 4 + blocks_bytes + 256 + lut_b + 64;
@@ -575,7 +658,8 @@ int32_t b2a_batch_run(b2a_engine* e) {
   if (cudaSetDevice(e->device) != cudaSuccess) return e->fail(B2A_E_NO_DEVICE, "cudaSetDevice failed");
   const Plan& pl = e->plan;
   cudaStream_t st = e->stream;
-  const bool use_tail = e->tail_stream != nullptr && pl.waves.size() == 1;  // several waves share scratch: one stream
+  // pipeline slots put K2 and what follows on their high-priority stream (several waves share scratch: one stream)
+  const bool use_tail = e->is_slot && e->tail_stream != nullptr && pl.waves.size() == 1;
   e->tail_used = use_tail;
   e->launches = 0;
   uint32_t* ctl = e->d_ctl.as<uint32_t>();  // [0] bad symbol, [1] walk error, [2..] per-wave task counters
@@ -898,6 +982,10 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
   wts[0] = 1.0;
   if (K >= 3) wts[1] = 3.0;
   wts[K - 1] = K >= 4 ? 3.0 : 2.0;
+  // three slots (round 2): the last chunk's walk and copies hide under nothing, but its fill no longer waits for
+  // a slot, so equal late chunks measure best: 1,3,5,5,5 -> 26.9 ms per 1M-pair call against 27.3 for 1,3,6,6,3
+  // (profiles/r02_e2e_chunk_schedules.txt)
+  if (K == 5) wts = {1.0, 3.0, 5.0, 5.0, 5.0};
   if (const char* env = getenv("B2A_PIPE_WEIGHTS")) {  // development knob: comma-separated chunk weights
     std::vector<double> w2;
     for (const char* q = env; *q;) {
@@ -955,8 +1043,10 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
         break;
       }
     }
+    sl.eng->is_slot = true;
     sl.eng->stage_nosync = true;
     sl.eng->fill_task_limit = 1;
+    sl.eng->packed_width = e->packed_width;
     sl.eng->tune_G = e->tune_G;
     sl.eng->tune_R = e->tune_R;
     sl.eng->walk_mode = e->walk_mode;
@@ -976,17 +1066,22 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
       break;
     }
     // the chunk's slice of the caller's blob, offsets rebased
+    // offsets and extents are bytes, or 32-bit BitEnc blocks for packed input
+    const uint32_t pw = e->packed_width;
+    const uint64_t unit = pw ? 4 : 1;
     uint64_t bmin = ~0ull, bmax = 0, seq_sum = 0;
     bool inside = true;
     for (uint64_t p = lo; p < hi; ++p) {
-      const uint64_t bb = pairs->blob_bytes, xo = pairs->x_off[p], yo = pairs->y_off[p];
-      if (xo > bb || pairs->x_len[p] > bb - xo || yo > bb || pairs->y_len[p] > bb - yo) {
+      const uint64_t bb = pairs->blob_bytes / unit, xo = pairs->x_off[p], yo = pairs->y_off[p];
+      const uint64_t xu = pw ? bitenc_blocks(pairs->x_len[p], pw) : pairs->x_len[p];
+      const uint64_t yu = pw ? bitenc_blocks(pairs->y_len[p], pw) : pairs->y_len[p];
+      if (xo > bb || xu > bb - xo || yo > bb || yu > bb - yo) {
         inside = false;
         break;
       }
       bmin = std::min(bmin, std::min(xo, yo));
-      bmax = std::max(bmax, std::max(xo + pairs->x_len[p], yo + pairs->y_len[p]));
-      seq_sum += (uint64_t)pairs->x_len[p] + pairs->y_len[p];
+      bmax = std::max(bmax, std::max(xo + xu, yo + yu));
+      seq_sum += xu + yu;
     }
     if (!inside) {
       rc = e->fail(B2A_E_INVALID, "sequence offset/length outside seq_blob");
@@ -995,9 +1090,9 @@ static int32_t align_batch_pipelined(b2a_engine* e, int32_t mode, const b2a_scor
     if (bmin > bmax) bmin = bmax = 0;
     sl.xoff.resize(nc);
     sl.yoff.resize(nc);
-    const uint8_t* chunk_blob = pairs->seq_blob + bmin;
-    uint64_t chunk_bytes = bmax - bmin;
-    if (chunk_bytes > 2 * seq_sum + (1ull << 20)) {
+    const uint8_t* chunk_blob = pairs->seq_blob + bmin * unit;
+    uint64_t chunk_bytes = (bmax - bmin) * unit;
+    if (!pw && chunk_bytes > 2 * seq_sum + (1ull << 20)) {
       // the chunk's sequences are scattered over a much larger span of the caller's blob (e.g. all x, then all
       // y): uploading the span would move most of the blob once per chunk, so gather them into a compact blob
       uint64_t pos = 0;
@@ -1113,6 +1208,42 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
                            const b2a_pairs* pairs, const b2a_band_hints* hints, b2a_results* results,
                            b2a_stats* stats);
 
+// BitEnc storage as the input of Aligner::{custom,global,semiglobal,local} (and of the banded aligner when k > 0)
+static int32_t packed_view(b2a_engine* e, const b2a_packed_pairs* pp, b2a_pairs* view) {
+  if (!e || !pp) return B2A_E_INVALID;
+  if (pp->width < 1 || pp->width > 8) return e->fail(B2A_E_INVALID, "BitEnc width must be 1..8 (bitenc.rs:75)");
+  view->seq_blob = reinterpret_cast<const uint8_t*>(pp->blocks);
+  view->x_off = pp->x_block;
+  view->x_len = pp->x_len;
+  view->y_off = pp->y_block;
+  view->y_len = pp->y_len;
+  view->blob_bytes = pp->n_blocks * 4;
+  view->n_pairs = pp->n_pairs;
+  return B2A_OK;
+}
+
+int32_t b2a_align_batch_packed(b2a_engine* e, int32_t mode, const b2a_scoring* scoring, const b2a_packed_pairs* pp,
+                               b2a_results* results, b2a_stats* stats) {
+  b2a_pairs view;
+  int rc = packed_view(e, pp, &view);
+  if (rc) return rc;
+  e->packed_width = pp->width;
+  rc = b2a_align_batch(e, mode, scoring, &view, results, stats);
+  e->packed_width = 0;
+  return rc;
+}
+
+int32_t b2a_align_batch_banded_packed(b2a_engine* e, int32_t mode, const b2a_scoring* scoring, uint32_t k, uint32_t w,
+                                      const b2a_packed_pairs* pp, b2a_results* results, b2a_stats* stats) {
+  b2a_pairs view;
+  int rc = packed_view(e, pp, &view);
+  if (rc) return rc;
+  e->packed_width = pp->width;
+  rc = banded_impl(e, mode, scoring, k, w, &view, nullptr, results, stats);
+  e->packed_width = 0;
+  return rc;
+}
+
 int32_t b2a_align_batch_banded(b2a_engine* e, int32_t mode, const b2a_scoring* s, uint32_t k, uint32_t w,
                                const b2a_pairs* pairs, b2a_results* results, b2a_stats* stats) {
   return banded_impl(e, mode, s, k, w, pairs, nullptr, results, stats);
@@ -1172,10 +1303,12 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   CK(e->d_bcells.reserve(n * 8 + 8));
   CK(e->d_bstatus.reserve(n * 4 + 4));
   CK(e->d_bopsend.reserve(n * 8 + 8));
-  CK(up(e->d_xoff, pairs->x_off, n * 8));
-  CK(up(e->d_yoff, pairs->y_off, n * 8));
-  CK(up(e->d_xlen, pairs->x_len, n * 4));
-  CK(up(e->d_ylen, pairs->y_len, n * 4));
+  if (!e->packed_width) {
+    CK(up(e->d_xoff, pairs->x_off, n * 8));
+    CK(up(e->d_yoff, pairs->y_off, n * 8));
+    CK(up(e->d_xlen, pairs->x_len, n * 4));
+    CK(up(e->d_ylen, pairs->y_len, n * 4));
+  }
   CK(up(e->d_codemap, e->codemap_host, 256));
   if (!e->lut_host.empty()) CK(up(e->d_lut, e->lut_host.data(), e->lut_host.size() * 4));
   CK(up(e->d_bopsend, ops_end.data(), n * 8));

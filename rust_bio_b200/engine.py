@@ -143,6 +143,46 @@ class Engine:
                                                    C.byref(cp), C.byref(results.c), C.byref(self.stats)))
         return results
 
+    @staticmethod
+    def pack_bitenc_pairs(pairs):
+        """[(BitEnc x, BitEnc y), ...] -> (blocks, x_block, x_len, y_block, y_len, width): the storages of all
+        sequences concatenated (what b2a_packed_pairs points at)."""
+        width = pairs[0][0].width if pairs else 2
+        chunks, xb, xl, yb, yl, pos = [], [], [], [], [], 0
+        for x, y in pairs:
+            assert x.width == width and y.width == width, "one width per batch"
+            xb.append(pos)
+            xl.append(x.nr_symbols())
+            chunks.append(x.storage)
+            pos += x.nr_blocks()
+            yb.append(pos)
+            yl.append(y.nr_symbols())
+            chunks.append(y.storage)
+            pos += y.nr_blocks()
+        blocks = np.concatenate(chunks + [np.zeros(4, dtype=np.uint32)]).astype(np.uint32)
+        return (blocks, np.array(xb, dtype=np.uint64), np.array(xl, dtype=np.uint32), np.array(yb, dtype=np.uint64),
+                np.array(yl, dtype=np.uint32), width)
+
+    def align_batch_packed(self, mode: int, cscoring: CScoring, packed, results: Optional[Results] = None,
+                           banded=None) -> Results:
+        """b2a_align_batch_packed / b2a_align_batch_banded_packed: `packed` = pack_bitenc_pairs(...) (numpy arrays;
+        pinned arrays give the fastest copies).  `banded` = (k, w) for the banded aligner."""
+        from ._lib import CPackedPairs
+        blocks, xb, xl, yb, yl, width = packed
+        n = len(xl)
+        if results is None:
+            results = Results(n, int(xl.astype(np.uint64).sum() + yl.astype(np.uint64).sum() + 4 * n))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        pp = CPackedPairs(p(blocks), p(xb), p(xl), p(yb), p(yl), len(blocks), n, int(width))
+        if banded is None:
+            self._check(self._L.b2a_align_batch_packed(self._h, int(mode), C.byref(cscoring), C.byref(pp),
+                                                       C.byref(results.c), C.byref(self.stats)))
+        else:
+            self._check(self._L.b2a_align_batch_banded_packed(self._h, int(mode), C.byref(cscoring), int(banded[0]),
+                                                              int(banded[1]), C.byref(pp), C.byref(results.c),
+                                                              C.byref(self.stats)))
+        return results
+
     def align_batch_banded_hinted(self, mode: int, cscoring: CScoring, k: int, w: int, batch: Batch,
                                   matches, paths=None, allowed_mismatches: Optional[int] = None,
                                   use_lcskpp_union: bool = False, results: Optional[Results] = None) -> Results:

@@ -225,6 +225,19 @@ class Aligner:
                                                                        pair_status=True))
         return _alignments(res, pairs, mode, on_panic)
 
+    def batch_bitenc(self, mode: int, pairs, on_panic: str = "raise") -> List[Alignment]:
+        """Aligner::{custom,global,semiglobal,local} over [(BitEnc x, BitEnc y), ...] (bio::data_structures::bitenc,
+        holding alphabets::RankTransform ranks): the packed storage goes to the GPU as it is.  `match_fn` scores
+        RANKS (MatchParams: equality of ranks == equality of symbols)."""
+        packed = Engine.pack_bitenc_pairs(pairs)
+        ranks = np.arange(1 << packed[5], dtype=np.uint8)
+        cs, keep = self.scoring.to_c(ranks)
+        lens = [(x.nr_symbols(), y.nr_symbols()) for x, y in pairs]
+        res = Results(len(pairs), sum(a + b + 4 for a, b in lens), pair_status=True)
+        self.engine.align_batch_packed(mode, cs, packed, results=res)
+        fake = [(b"\0" * a, b"\0" * b) for a, b in lens]  # _alignments only needs the lengths
+        return _alignments(res, fake, mode, on_panic)
+
     def custom_batch(self, pairs, on_panic: str = "raise"):
         return self._batch(MODE_CUSTOM, pairs, on_panic)
 

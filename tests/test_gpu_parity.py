@@ -632,3 +632,100 @@ def test_small_batch_overlap_of_fills_and_walks(eng, oracle, mode, clips):
         eng.fetch(res)
         assert_same(res.as_dict(), [res.ops_of(i) for i in range(6000)], ref, ref_ops, batch, f"overlap {mode} rep {rep}")
     assert eng.stats.kernel_launches >= 9  # K0 + 4 fills + 4 walks (+ compaction): the overlapped form ran
+
+
+def _bitenc_batch(seed, n_pairs, max_m, max_n, alphabet, min_len=0):
+    """ragged batch + the same sequences as BitEnc storages of RankTransform ranks"""
+    from rust_bio_b200 import synth
+    from rust_bio_b200.alphabets import Alphabet, RankTransform
+    batch = synth.ragged_pairs(seed, n_pairs, max_m, max_n, alphabet=alphabet, min_len=min_len)
+    rt = RankTransform.new(Alphabet.new(alphabet))
+    blob, xo, xl, yo, yl = batch
+    ranks_blob = rt.transform(bytes(blob))
+    return batch, (ranks_blob, xo, xl, yo, yl), rt
+
+
+@pytest.mark.parametrize("alphabet", [b"ACGT", b"ACGTN"], ids=["width2", "width3"])
+def test_bitenc_packed_input_every_mode(eng, oracle, alphabet):
+    """BitEnc storage (bitenc.rs:50-56) of RankTransform ranks (alphabets/mod.rs:220-283) as
+    the batch input, through b2a_align_batch_packed: same alignments as the oracle on the rank sequences (MatchParams
+    scores by equality, so ranks and symbols score alike) and as the byte path on the original symbols."""
+    from rust_bio_b200.data_structures import BitEnc
+    from rust_bio_b200.engine import Engine
+    batch, rank_batch, rt = _bitenc_batch(17, 700, 140, 170, alphabet)
+    width = max(1, rt.get_width())
+    blob, xo, xl, yo, yl = rank_batch
+    pairs = [(BitEnc.from_values(width, blob[int(xo[p]):int(xo[p]) + int(xl[p])]),
+              BitEnc.from_values(width, blob[int(yo[p]):int(yo[p]) + int(yl[p])])) for p in range(len(xl))]
+    packed = Engine.pack_bitenc_pairs(pairs)
+    assert packed[0].nbytes * (3 if width == 2 else 2) < int(xl.sum() + yl.sum()) * 1 + 4096
+    cs, keep = _c_scoring(-5, -1, 2, -3)
+    s, _ = oracle.make_scoring(-5, -1, 2, -3)
+    for mode in ("local", "global", "semiglobal"):
+        ref, ref_ops = oracle_batch(oracle, mode, s, rank_batch, threads=8)
+        res = eng.align_batch_packed(MODES[mode], cs, packed)
+        assert_same(res.as_dict(), [res.ops_of(i) for i in range(res.n_pairs)], ref, ref_ops, rank_batch, f"bitenc {mode}")
+        got2, ops2 = _engine_result(eng, mode, cs, batch)  # the byte path on the original symbols
+        assert np.array_equal(got2["score"], res.score) and ops2 == [res.ops_of(i) for i in range(res.n_pairs)]
+    # the mirror: Aligner.batch_bitenc
+    from rust_bio_b200.pairwise import Aligner, MatchParams, Scoring
+    al = Aligner.with_scoring(Scoring.new(-5, -1, MatchParams.new(2, -3)), engine=eng)
+    alns = al.batch_bitenc(MODES["local"], pairs[:50])
+    ref, ref_ops = oracle_batch(oracle, "local", s, tuple(a[:50] if i else a for i, a in enumerate(rank_batch)), threads=4)
+    assert [a.score for a in alns] == [int(v) for v in ref["score"][:50]]
+    assert [[(o.code, o.len) for o in a.operations] for a in alns] == ref_ops[:50]
+
+
+def test_bitenc_packed_input_through_the_chunk_pipeline_and_banded(eng, oracle):
+    """>= 262,144 pairs of packed input go through the chunked H2D / kernel / D2H pipeline (block-indexed slices);
+    the banded aligner takes the same packed input."""
+    from rust_bio_b200.data_structures import BitEnc
+    from rust_bio_b200.engine import Engine
+    n = 270_000
+    batch, rank_batch, rt = _bitenc_batch(23, n, 30, 36, b"ACGT", min_len=1)
+    blob, xo, xl, yo, yl = rank_batch
+    # vectorised packing: every sequence starts a new block (16 symbols per block at width 2)
+    xb = np.zeros(n, dtype=np.uint64)
+    yb = np.zeros(n, dtype=np.uint64)
+    nblk = lambda l: (l.astype(np.uint64) + np.uint64(15)) // np.uint64(16)
+    sizes = np.stack([nblk(xl), nblk(yl)], axis=1).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    xb[:], yb[:] = offs[0:-1:2], offs[1::2]
+    blocks = np.zeros(int(offs[-1]) + 4, dtype=np.uint32)
+    for arr_off, arr_len, arr_blk in ((xo, xl, xb), (yo, yl, yb)):
+        for k in range(36):
+            sel = arr_len > k
+            v = blob[(arr_off[sel] + np.uint64(k)).astype(np.int64)].astype(np.uint32)
+            np.bitwise_or.at(blocks, (arr_blk[sel] + np.uint64(k // 16)).astype(np.int64), v << np.uint32(2 * (k % 16)))
+    packed = (blocks, xb, xl, yb, yl, 2)
+    assert BitEnc.from_values(2, blob[int(xo[5]):int(xo[5]) + int(xl[5])]).storage.tolist() == \
+        blocks[int(xb[5]):int(xb[5]) + int(nblk(xl[5:6])[0])].tolist()
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    res = eng.align_batch_packed(MODES["semiglobal"], cs, packed)
+    got2 = eng.align_batch(MODES["semiglobal"], cs, batch)
+    for k in ("score", "xstart", "xend", "ystart", "yend", "ops_off"):
+        assert np.array_equal(getattr(res, k), getattr(got2, k)), k
+    tot = int(res.ops_off[-1])
+    assert np.array_equal(res.ops[:tot], got2.ops[:tot])
+    idx = np.random.default_rng(0).integers(0, n, 400)
+    sub = (blob, xo[idx], xl[idx], yo[idx], yl[idx])
+    s, _ = oracle.make_scoring(-5, -1, 1, -1)
+    ref, ref_ops = oracle_batch(oracle, "semiglobal", s, sub, threads=8)
+    assert_same({k: v[idx] for k, v in res.as_dict().items()}, [res.ops_of(int(p)) for p in idx], ref, ref_ops, sub, "packed pipeline")
+    # banded, packed
+    from test_sim_banded import _mutated_window_batch
+    from rust_bio_b200.alphabets import Alphabet, RankTransform
+    bb = _mutated_window_batch(5, 200, 120, 500)
+    rt = RankTransform.new(Alphabet.new(b"ACGT"))
+    rb = (rt.transform(bytes(bb[0])),) + tuple(bb[1:])
+    pairs = [(BitEnc.from_values(2, rb[0][int(rb[1][p]):int(rb[1][p]) + int(rb[2][p])]),
+              BitEnc.from_values(2, rb[0][int(rb[3][p]):int(rb[3][p]) + int(rb[4][p])])) for p in range(200)]
+    from rust_bio_b200._lib import CScoring
+    csb = CScoring(-5, -1, MIN, MIN, MIN, MIN, 1, -1, 1, None, None, 0)
+    resb = eng.align_batch_packed(MODES["semiglobal"], csb, Engine.pack_bitenc_pairs(pairs), banded=(12, 8))
+    so, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    refb, rops, roff, _, _ = oracle.banded_align_batch("semiglobal", so, 12, 8, *rb, threads=8)
+    assert np.array_equal(resb.score.astype(np.int64), refb["score"].astype(np.int64))
+    for p in range(200):
+        want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(refb["n_ops"][p])]]
+        assert resb.ops_of(p) == want, p

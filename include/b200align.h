@@ -291,6 +291,23 @@ int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t seg
 int32_t b2a_compact_decode(const void* host_segment, uint64_t segment_bytes, uint64_t pair_base,
                            uint64_t ops_base, b2a_results* results, uint64_t* n_pairs, uint64_t* ops_bytes);
 
+/* ---- every visible GPU from ONE process (what a Rust caller of the shim uses on an 8 x B200 box)
+ * b2a_multi_create: one engine + one stream per device (device_ids == NULL / n_devices <= 0: all visible devices)
+ * and an NCCL communicator over them (ncclCommInitAll, libnccl.so.2 bound at run time).
+ * b2a_multi_align_batch: Aligner::{custom,global,semiglobal,local} over a batch with HOST inputs and outputs -- the
+ * pair list is split contiguously into equal shares, every device stages and runs its share side by side, ONE
+ * ncclAllGather of the compact result segments reassembles the per-pair results on every device, and device 0's copy
+ * is decoded into `results`.  Bit-identical to b2a_align_batch on one device.  Without libnccl the segments are
+ * gathered onto device 0 with peer copies instead; b2a_multi_exchange_kind() names what is in use. */
+typedef struct b2a_multi b2a_multi;
+int32_t b2a_multi_create(b2a_multi** out, const int32_t* device_ids, int32_t n_devices);
+int32_t b2a_multi_destroy(b2a_multi* m);
+int32_t b2a_multi_device_count(const b2a_multi* m);
+const char* b2a_multi_last_error(const b2a_multi* m);
+const char* b2a_multi_exchange_kind(const b2a_multi* m);
+int32_t b2a_multi_align_batch(b2a_multi* m, int32_t mode, const b2a_scoring* scoring, const b2a_pairs* pairs,
+                              b2a_results* results, b2a_stats* stats);
+
 /* Measurement utility for the int32-ALU roofline: tera lane-ops/s of
  * independent add / min-max / add+max register chains over all SMs of the device. */
 int32_t b2a_util_int32_peak(int32_t device_id, float* tops_add, float* tops_minmax, float* tops_mixed);

@@ -25,6 +25,8 @@ ABI_SYMBOLS = [
     "b2a_batch_fetch", "b2a_batch_records", "b2a_batch_records_into", "b2a_record_stride",
     "b2a_records_decode", "b2a_batch_compact_bytes", "b2a_batch_compact_into", "b2a_compact_decode",
     "b2a_batch_compact_fixed", "b2a_gathered_fetch", "b2a_align_batch_packed", "b2a_align_batch_banded_packed",
+    "b2a_multi_create", "b2a_multi_destroy", "b2a_multi_device_count", "b2a_multi_last_error",
+    "b2a_multi_exchange_kind", "b2a_multi_align_batch",
     "b2a_util_int32_peak",
 ]
 
@@ -131,6 +133,15 @@ def load():
                                          C.POINTER(CResults), C.POINTER(CStats)]
     L.b2a_align_batch_banded_packed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.c_uint32, C.c_uint32,
                                                 C.POINTER(CPackedPairs), C.POINTER(CResults), C.POINTER(CStats)]
+    L.b2a_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32]
+    L.b2a_multi_destroy.argtypes = [C.c_void_p]
+    L.b2a_multi_device_count.argtypes = [C.c_void_p]
+    L.b2a_multi_last_error.argtypes = [C.c_void_p]
+    L.b2a_multi_last_error.restype = C.c_char_p
+    L.b2a_multi_exchange_kind.argtypes = [C.c_void_p]
+    L.b2a_multi_exchange_kind.restype = C.c_char_p
+    L.b2a_multi_align_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.POINTER(CPairs),
+                                        C.POINTER(CResults), C.POINTER(CStats)]
     L.b2a_util_int32_peak.argtypes = [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]
     for name in ABI_SYMBOLS:

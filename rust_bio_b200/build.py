@@ -58,6 +58,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     esrc = os.path.join(CSRC, "b2a_engine.cu")
     if force or _stale(eo, hdrs + [esrc]):
         jobs.append([NVCC, *FLAGS, "-c", esrc, "-o", eo])
+    mo = os.path.join(OBJ, "multi.o")
+    objs.append(mo)
+    msrc = os.path.join(CSRC, "b2a_multi.cu")
+    if force or _stale(mo, [msrc, os.path.join(CSRC, "..", "..", "include", "b200align.h")]):
+        jobs.append([NVCC, *FLAGS, "-c", msrc, "-o", mo])
     po = os.path.join(OBJ, "peak.o")
     objs.append(po)
     psrc = os.path.join(CSRC, "b2a_peak.cu")
@@ -69,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and log:
                     print(log, file=sys.stderr)
     if jobs or force or _stale(SO, objs):
-        _run([NVCC, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+        _run([NVCC, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return SO
 
 

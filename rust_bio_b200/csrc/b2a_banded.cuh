@@ -22,6 +22,7 @@ namespace b2a {
 
 constexpr uint64_t BANDED_MAX_CELLS = 5000000ull;  // banded.rs:104
 constexpr int32_t BANDED_DEFAULT_MATCH_SCORE = 2;  // banded.rs:105
+constexpr int K3_FAST_ROWS = 5;  // rows per lane of the register-resident K3 loop: bands up to ~160 rows per column
 
 struct BandedParams {
   const uint8_t* blob;
@@ -871,6 +872,499 @@ struct BandedOut {
   uint32_t clip[4];
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// The register-resident column loop of K3.
+//
+// The literal loop keeps the reference's rolling S/I/D arrays in the slab and gives one band row of a column
+// to each lane, 32 rows at a time: ~245 instructions per cell-lane (loads, stores, 64-bit indexing, a 5-step
+// scan per 32 rows) plus ~600 per column of one-lane sections and barriers.  Here a lane owns R CONSECUTIVE rows
+// and carries what the next column needs of them in registers -- S and D of the previous column, the s-bits of
+// the previous column's cell (the D-open nibble), the row tracker Sn -- so a column costs one pass over R rows per
+// lane, one prefix maximum over the lanes for the vertical I chain, and no S/I/D traffic at all; the one-lane
+// sections become uniform register arithmetic.  The traceback cells, Sn/Ly, Lx and the border rows are written
+// exactly as before, and the last column's S and I are left in the slab for the end-of-matrix passes.
+//
+// Rows are owned in blocks of R: row i belongs to block i / R, block B to lane B % W; a lane holds one block at
+// a time and moves on to block B + W when B has fallen out of the sliding window (the band of the column plus
+// the row above it).  It applies to pairs (banded_fast_ok) whose band
+//   * never needs more than W blocks in one column (band height up to ~W*R rows: 160 for R = 5),
+//   * has non-decreasing starts and ends over consecutive non-empty columns (then every value the reference
+//     reads from outside the previous column's band is MIN_SCORE: the rows below were reset, banded.rs:676-680,
+//     the row above was set, 556-561 -- no leftovers of older columns are ever visible), and
+//   * has only the Band::new sentinel as empty columns;
+// every other pair runs the literal loop.  All 300 sampled pairs of BASELINE config 4 qualify.
+template <int W, int R>
+B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n) {
+  using C = Coop<W>;
+  if (W != 32 || m < 2 || n < 2 || m >= (1u << 24) || n >= (1u << 24)) return false;
+  bool ok = true;
+  for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
+    const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
+    if (s >= e) {
+      if (!(s == m + 1 && e == 0)) ok = false;
+      continue;
+    }
+    const uint64_t lo = umax64(1, s), hi = umin64(e, m);
+    if (lo < hi) {
+      const uint64_t f = umax64(lo - 1, 1);
+      if ((hi - 1) / R - f / R + 1 > (uint64_t)W) ok = false;
+    }
+    if (j >= 1) {
+      const uint64_t ps = rng[2 * (j - 1)], pe = rng[2 * (j - 1) + 1];
+      if (ps < pe && (s < ps || e < pe)) ok = false;
+    }
+  }
+  return C::ballot(!ok) == 0u;
+}
+
+template <int W, int R, class ScoreFn>
+B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t m, const uint8_t* y, const int32_t n,
+                                const DevScoring& sc, ScoreFn score, const uint32_t* rng, const uint32_t* colstart,
+                                const int32_t* S0arr /* column 0's S */, int32_t* Sfin, int32_t* Ifin, int32_t* Sn,
+                                uint32_t* Ly, uint32_t* Lx, uint16_t* row0, uint16_t* rowm, const uint16_t* col0,
+                                uint16_t* coln, uint16_t* cells) {
+  using C = Coop<W>;
+  static_assert(W == 32 || W == 1, "lanes of one warp");
+  const int32_t go = sc.gap_open, ge = sc.gap_extend;
+  const int32_t xp = sc.xclip_prefix, xs = sc.xclip_suffix, yp = sc.yclip_prefix, ys = sc.yclip_suffix;
+  const int32_t gs = imax(ge, go);
+  constexpr int32_t NEG = -(1 << 30);  // "no contribution" in the transformed I chain
+  const int prev_lane = (lane + W - 1) % W;
+  // lane state: the block of R rows this lane holds
+  int32_t blk = -1;
+  int32_t Sp[R], Dp[R], Snr[R];
+  uint32_t psb[R];
+  int32_t xr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    Sp[r] = Dp[r] = Snr[r] = MIN_SCORE;
+    psb[r] = 0;
+    xr[r] = 0;
+  }
+  // uniform state (every lane holds the same values)
+  int32_t S0_prev = S0arr[0];   // S(0, j-1), MIN_SCORE when row 0 was not in the band there
+  int32_t Sm_prev = S0arr[m];   // S[m] as the previous column left it
+  int32_t Dm_prev = MIN_SCORE;  // D(m, j-1)
+  int32_t Sn0 = Sn[0], Snm = Sn[m];
+  bool all_fresh = false;       // an empty column has passed: nothing of older columns is visible any more
+  bool last_empty = false;      // column n is empty
+  for (int32_t j = 1; j <= n; ++j) {
+    const int32_t s = (int32_t)rng[2 * j], e = (int32_t)rng[2 * j + 1];
+    if (s >= e) {
+      // a run of empty columns: only row m's x-suffix-clip nibble is written (banded.rs:655-661 with i_end = 0)
+      const int32_t jc = j + lane;
+      const bool emp = jc <= n && rng[2 * jc] >= rng[2 * jc + 1];
+      const uint32_t bal = C::ballot(emp);
+      int32_t run = 0;
+      while (run < W && ((bal >> run) & 1u)) ++run;
+      if (lane < run) rowm[jc] = (uint16_t)((rowm[jc] & ~0x0F00u) | (TB_XCLIP_SUFFIX << 8));
+      S0_prev = Sm_prev = Dm_prev = MIN_SCORE;
+      all_fresh = true;
+      j += run - 1;
+      last_empty = j >= n;
+      continue;
+    }
+    const bool last = j == n;
+    const int32_t lo = s > 1 ? s : 1, hi_main = e < m ? e : m;
+    const int32_t q = (int32_t)y[j - 1];
+    // ------------------------------------------------------------------ row 0 (banded.rs:519-553), uniform
+    int32_t S0_cur = MIN_SCORE;
+    uint32_t sb0 = 0;
+    if (s == 0) {
+      int32_t D0;
+      uint32_t db;
+      if (j == 1) {
+        D0 = go;
+        db = TB_START;
+      } else {
+        const int32_t d_score = go + ge * (j - 1), c_score = yp + go;
+        if (d_score > c_score) {
+          D0 = d_score;
+          db = TB_DEL;
+        } else {
+          D0 = c_score;
+          db = TB_YCLIP_PREFIX;
+        }
+      }
+      if (D0 > yp) {
+        S0_cur = D0;
+        sb0 = TB_DEL;
+      } else {
+        S0_cur = yp;
+        sb0 = TB_YCLIP_PREFIX;
+      }
+      if (S0_cur + ys > Sn0) {
+        Sn0 = S0_cur + ys;
+        if (lane == 0) {
+          Sn[0] = Sn0;
+          Ly[0] = (uint32_t)(n - j);
+          row0[n] = (uint16_t)((row0[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+        }
+      }
+      // (the eager write above lands on this very cell when j == n; the reference's put() then overwrites it)
+      if (lane == 0) row0[j] = (uint16_t)((db << 4) | (sb0 << 8));
+    }
+    const int32_t xclip_score = xp + imax(last ? imax(yp, Sn0) : yp, go + ge * (j - 1));
+    // carries into the first band row: the row above it in THIS column (banded.rs:556-561: MIN_SCORE unless it is row 0)
+    int32_t cS = s == 0 ? S0_cur : MIN_SCORE, cI = MIN_SCORE, cSn = MIN_SCORE;
+    uint32_t csb = s == 0 ? sb0 : 0u;
+    if (last) {
+      cSn = lo - 1 == 0 ? Sn0 : Sn[lo - 1];
+      if (lo - 1 >= 1) csb = ((uint32_t)coln[lo - 1] >> 8) & 15u;  // column n's cells exist outside the band too
+    }
+    int32_t trk_val = MIN_SCORE, trk_i = 0;
+    bool trk_hit = false;
+    // values of row m-1 in this column (for the cell of row m), valid when hi_main == m
+    int32_t rS = cS, rI = cI, rSn = cSn, rSup = MIN_SCORE;
+    uint32_t rsb = csb;
+    if (lo < hi_main) {
+      // ---------------------------------------------------------------- the lane's block for this column
+      const int32_t f = lo - 1 > 1 ? lo - 1 : 1;
+      const int32_t Blo = f / R;
+      const int32_t k = (lane - Blo % W + W) % W;  // position of this lane's block in the window, lowest block first
+      const int32_t nblk = Blo + k;
+      if (nblk != blk || all_fresh) {
+        blk = nblk;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int32_t i = blk * R + r;
+          const bool real = i >= 1 && i <= m;
+          Sp[r] = MIN_SCORE;
+          psb[r] = 0;
+          if (j == 1 && real) {  // the previous column is column 0: its S and cells are in the slab
+            Sp[r] = S0arr[i];
+            psb[r] = ((uint32_t)col0[i] >> 8) & 15u;
+          }
+          Dp[r] = MIN_SCORE;
+          Snr[r] = real ? Sn[i] : MIN_SCORE;
+          xr[r] = real ? (int32_t)x[i - 1] : 0;
+        }
+      }
+      // ---------------------------------------------------------------- per row: everything that does not need I
+      int32_t A[R], best_d[R], m_score[R], ycs[R];
+      uint32_t db[R];
+      bool inw[R];
+      const int32_t up_S = C::from(Sp[R - 1], prev_lane);  // S(i-1, j-1) of this lane's first row
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int32_t i = blk * R + r;
+        inw[r] = i >= lo && i < hi_main;
+        int32_t sup = r == 0 ? up_S : Sp[r - 1];
+        if (i == 1) sup = S0_prev;  // row 0 is not a lane row
+        m_score[r] = sup + score((uint8_t)xr[r], (uint8_t)q);
+        const int32_t d_score = Dp[r] + ge, s_open = Sp[r] + go;
+        if (d_score > s_open) {
+          best_d[r] = d_score;
+          db[r] = TB_DEL;
+        } else {
+          best_d[r] = s_open;
+          db[r] = psb[r];
+        }
+        ycs[r] = yp + go + ge * (i - 1);
+        A[r] = imax(imax(imax(MIN_SCORE, m_score[r]), imax(best_d[r], xclip_score)), ycs[r]);
+      }
+      // ---------------------------------------------------------------- the vertical chain: I(i) - gs*i is a
+      // running maximum (see banded_compute_d); rows outside the band contribute nothing, the first band row is
+      // seeded literally from the row above it
+      const int32_t up_A = C::from(A[R - 1], prev_lane);
+      const int32_t up_Sn = last ? C::from(Snr[R - 1], prev_lane) : MIN_SCORE;
+      int32_t u[R];
+      {
+        int32_t run_max = NEG;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int32_t i = blk * R + r;
+          int32_t t = NEG;
+          if (inw[r]) {
+            if (i == lo) {
+              int32_t bi = imax(cI + ge, cS + go);
+              if (last) bi = imax(bi, cSn + go);
+              t = bi - gs * i;
+            } else {
+              const int32_t aprev = r == 0 ? up_A : A[r - 1];
+              const int32_t snprev = r == 0 ? up_Sn : Snr[r - 1];
+              t = (last ? imax(aprev, snprev) : aprev) + go - gs * i;
+            }
+          }
+          run_max = imax(run_max, t);
+          u[r] = run_max;
+        }
+      }
+      int32_t excl;
+      {
+        int32_t v = u[R - 1];  // inclusive scan over the lanes in window order (lane of the lowest block first)
+        for (int d = 1; d < W; d <<= 1) {
+          const int32_t t = C::from(v, (lane + W - d) % W);
+          if (k >= d) v = imax(v, t);
+        }
+        excl = C::from(v, prev_lane);
+        if (k == 0) excl = NEG;
+      }
+      // ---------------------------------------------------------------- the cells, literally
+      int32_t best[R], best_i[R], sncur[R];
+      uint32_t sb[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int32_t i = blk * R + r;
+        best_i[r] = imax(u[r], excl) + gs * i;
+        int32_t b = MIN_SCORE;
+        uint32_t c = TB_START;
+        if (m_score[r] > b) {
+          b = m_score[r];
+          c = (xr[r] == q) ? TB_MATCH : TB_SUBST;
+        }
+        if (best_i[r] > b) {
+          b = best_i[r];
+          c = TB_INS;
+        }
+        if (best_d[r] > b) {
+          b = best_d[r];
+          c = TB_DEL;
+        }
+        if (xclip_score > b) {
+          b = xclip_score;
+          c = TB_XCLIP_PREFIX;
+        }
+        if (ycs[r] > b) {
+          b = ycs[r];
+          c = TB_YCLIP_PREFIX;
+        }
+        best[r] = b;
+        sb[r] = c;
+        sncur[r] = Snr[r];
+        if (inw[r] && b + ys > Snr[r]) {  // row tracker, banded.rs:650-654 (eager write of (i, n)'s s-bits)
+          sncur[r] = b + ys;
+          Sn[i] = sncur[r];
+          Ly[i] = (uint32_t)(n - j);
+          if (!last) coln[i] = (uint16_t)((coln[i] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+        }
+      }
+      // the I nibble needs the final values of the row above
+      const int32_t up_best = C::from(best[R - 1], prev_lane), up_bi = C::from(best_i[R - 1], prev_lane);
+      const uint32_t up_sb = (uint32_t)C::from((int32_t)sb[R - 1], prev_lane);
+      const int32_t up_sncur = last ? C::from(sncur[R - 1], prev_lane) : MIN_SCORE;
+      uint16_t* const wbase = last ? coln : cells;
+      const uint32_t woff = last ? 0u : colstart[j] - (uint32_t)s;  // cell (i, j) = wbase[woff + i]
+      int32_t lane_trk_val = MIN_SCORE, lane_trk_i = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int32_t i = blk * R + r;
+        if (!inw[r]) continue;
+        int32_t pS, pI, pSn;
+        uint32_t psbc;
+        if (i == lo) {
+          pS = cS;
+          pI = cI;
+          pSn = cSn;
+          psbc = csb;
+        } else if (r == 0) {
+          pS = up_best;
+          pI = up_bi;
+          pSn = up_sncur;
+          psbc = up_sb;
+        } else {
+          pS = best[r - 1];
+          pI = best_i[r - 1];
+          pSn = sncur[r - 1];
+          psbc = sb[r - 1];
+        }
+        uint32_t ib;
+        {
+          const int32_t i_score = pI + ge, s_score = pS + go;
+          int32_t bl;
+          if (i_score > s_score) {
+            bl = i_score;
+            ib = TB_INS;
+          } else {
+            bl = s_score;
+            ib = psbc;
+          }
+          if (last && pSn + go > bl) ib = TB_YCLIP_SUFFIX;
+        }
+        wbase[woff + (uint32_t)i] = (uint16_t)(ib | (db[r] << 4) | (sb[r] << 8));
+        if (last) {  // the end-of-matrix passes read column n's S and I from the slab
+          Sfin[i] = best[r];
+          Ifin[i] = best_i[r];
+        }
+        if (best[r] + xs > lane_trk_val) {  // this lane's rows ascend: a strict > keeps the first
+          lane_trk_val = best[r] + xs;
+          lane_trk_i = i;
+        }
+      }
+      {  // first row with the highest S + xs (lowest row wins ties), banded.rs:645-649
+        long long key = lane_trk_val > MIN_SCORE
+                            ? (long long)((unsigned long long)(long long)lane_trk_val << 32) +
+                                  (long long)(0xFFFFFFFFu - (uint32_t)lane_trk_i)
+                            : (long long)0x8000000000000000ull;
+        key = C::all_max(key);
+        if (key != (long long)0x8000000000000000ull) {
+          trk_val = (int32_t)(key >> 32);
+          trk_i = (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll));
+          trk_hit = true;  // trk_val > MIN_SCORE == the tracker's value at the start of the column
+        }
+      }
+      if (hi_main == m) {  // row m-1 of this column and S(m-1, j-1), for the cell of row m
+        const int32_t rr = (m - 1) % R, owner = ((m - 1) / R) % W;
+        int32_t vS = best[0], vI = best_i[0], vSn = sncur[0], vSup = Sp[0];
+        uint32_t vsb = sb[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+          if (r == rr) {
+            vS = best[r];
+            vI = best_i[r];
+            vSn = sncur[r];
+            vSup = Sp[r];
+            vsb = sb[r];
+          }
+        rS = C::from(vS, owner);
+        rI = C::from(vI, owner);
+        rSn = C::from(vSn, owner);
+        rSup = C::from(vSup, owner);
+        rsb = (uint32_t)C::from((int32_t)vsb, owner);
+      }
+      // roll the lane state forward: what column j+1 reads of this column
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        Sp[r] = inw[r] ? best[r] : MIN_SCORE;
+        Dp[r] = inw[r] ? best_d[r] : MIN_SCORE;
+        psb[r] = inw[r] ? sb[r] : 0u;
+        Snr[r] = sncur[r];
+      }
+      all_fresh = false;
+    } else {
+      // no interior rows in this column (row 0 and / or row m only)
+      if (hi_main == m && e == m + 1) {  // row m's neighbours: row m-1 is the (unowned or fresh) row above
+        const int32_t owner = ((m - 1) / R) % W, rr = (m - 1) % R;
+        int32_t vSup = Sp[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+          if (r == rr) vSup = Sp[r];
+        const int32_t have = (blk == (m - 1) / R && !all_fresh) ? 1 : 0;
+        const int32_t got = C::from(vSup, owner), has = C::from(have, owner);
+        rSup = has ? got : MIN_SCORE;
+        if (m - 1 == 0) rSup = S0_prev;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        Sp[r] = Dp[r] = MIN_SCORE;
+        psb[r] = 0;
+      }
+    }
+    // ------------------------------------------------------------------ the column tracker and row m, uniform
+    int32_t Sm = MIN_SCORE;  // S[m] of this column: reset at the start of every column (banded.rs:556-561)
+    if (trk_hit) {
+      Sm = trk_val;
+      if (lane == 0) {
+        Lx[j] = (uint32_t)(m - trk_i);
+        rowm[j] = (uint16_t)((rowm[j] & ~0x0F00u) | (TB_XCLIP_SUFFIX << 8));
+      }
+    }
+    int32_t Dm_cur = MIN_SCORE;
+    const int32_t hi = e;
+    if ((s > 1 ? s : 1) < hi && hi == m + 1) {  // the cell of row m: it starts from the column tracker
+      const int32_t i = m;
+      const int32_t p = (int32_t)x[i - 1];
+      uint32_t ib, dbm, sbm;
+      if (m - 1 == 0) rSup = S0_prev;
+      const int32_t m_sc = rSup + score((uint8_t)p, (uint8_t)q);
+      const int32_t i_score = rI + ge;
+      int32_t s_score = rS + go;
+      int32_t bi;
+      if (i_score > s_score) {
+        bi = i_score;
+        ib = TB_INS;
+      } else {
+        bi = s_score;
+        ib = rsb;
+      }
+      if (last) {
+        const int32_t clip_score = rSn + go;
+        if (clip_score > bi) {
+          bi = clip_score;
+          ib = TB_YCLIP_SUFFIX;
+        }
+      }
+      const int32_t d_score = Dm_prev + ge;
+      s_score = Sm_prev + go;
+      int32_t bd;
+      if (d_score > s_score) {
+        bd = d_score;
+        dbm = TB_DEL;
+      } else {
+        bd = s_score;
+        dbm = ((uint32_t)rowm[j - 1] >> 8) & 15u;  // s-bits of (m, j-1) as stored so far
+      }
+      sbm = TB_XCLIP_SUFFIX;
+      int32_t b = Sm;
+      if (m_sc > b) {
+        b = m_sc;
+        sbm = (p == q) ? TB_MATCH : TB_SUBST;
+      }
+      if (bi > b) {
+        b = bi;
+        sbm = TB_INS;
+      }
+      if (bd > b) {
+        b = bd;
+        sbm = TB_DEL;
+      }
+      if (xclip_score > b) {
+        b = xclip_score;
+        sbm = TB_XCLIP_PREFIX;
+      }
+      const int32_t yclip_score = yp + go + ge * (i - 1);
+      if (yclip_score > b) {
+        b = yclip_score;
+        sbm = TB_YCLIP_PREFIX;
+      }
+      Sm = b;
+      Dm_cur = bd;
+      // (S[i] + xs > S[m] with i == m never holds: xs <= 0)
+      if (Sm + ys > Snm) {  // banded.rs:650-654 at i == m: the eager write goes to (m, n) ...
+        Snm = Sm + ys;
+        if (lane == 0) {
+          Sn[m] = Snm;
+          Ly[m] = (uint32_t)(n - j);
+          rowm[n] = (uint16_t)((rowm[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+        }
+      }
+      if (lane == 0) {  // ... and the cell's own put() follows it (so at j == n the put wins)
+        if (last) Ifin[m] = bi;
+        rowm[j] = (uint16_t)(ib | (dbm << 4) | (sbm << 8));
+      }
+    }
+    if (Sm + ys > Snm) {  // banded.rs:662-666
+      Snm = Sm + ys;
+      if (lane == 0) {
+        Sn[m] = Snm;
+        Ly[m] = (uint32_t)(n - j);
+        rowm[n] = (uint16_t)((rowm[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+      }
+    }
+    if (e < m + 1) {
+      if (lane == 0) rowm[j] = (uint16_t)((rowm[j] & ~0x0F00u) | (TB_XCLIP_SUFFIX << 8));
+      Sm = MIN_SCORE;
+    }
+    if (last) {
+      if (lane == 0) {
+        Sfin[m] = Sm;
+        if (s == 0) {
+          Sfin[0] = S0_cur;
+          Ifin[0] = MIN_SCORE;
+        }
+        if (e < m) Sfin[e] = MIN_SCORE;  // the row just below the band keeps its (reset) MIN_SCORE, banded.rs:689
+      }
+    }
+    S0_prev = s == 0 ? S0_cur : MIN_SCORE;
+    Sm_prev = Sm;
+    Dm_prev = Dm_cur;
+    C::sync();  // Sn / column-n cells written by one lane are read by others in later columns
+  }
+  // an empty last column leaves S[m] = MIN_SCORE behind (banded.rs:556-561); the slab may still hold column 0's
+  if (last_empty && lane == 0) Sfin[m] = MIN_SCORE;
+  C::sync();
+}
+
 // compute_alignment for one pair by W cooperating lanes (banded.rs:406-869).
 //
 // The column loop keeps the reference's arrays (rolling S/I/D with their leftovers, Sn/Ly/Lx, the eager
@@ -885,7 +1379,9 @@ struct BandedOut {
 //     extension or open, the Sn/Ly row tracker) is re-evaluated literally per row from the final
 //     neighbours' values, and the column tracker S[m]/Lx is an arg-max with the lowest row winning ties.
 // Row m of a column, row 0, column 0, the end-of-matrix passes and the walk are sequential work of lane 0.
-template <int W, class ScoreFn>
+// FASTR > 0 selects the register-resident column loop (FASTR rows per lane, see below); the caller must have
+// checked banded_fast_ok<W, FASTR> for the pair.  FASTR == 0 is the literal loop.
+template <int W, class ScoreFn, int FASTR = 0>
 B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n,
                              const DevScoring& sc, ScoreFn score, const uint32_t* rng, uint64_t num_cells,
                              uint8_t* slab, bool filter_clips, uint8_t* ops_end, BandedOut& out) {
@@ -1029,6 +1525,10 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
   }
   C::sync();
+  if constexpr (FASTR > 0) {
+    banded_columns_fast<W, FASTR>(lane, x, (int32_t)m, y, (int32_t)n, sc, score, rng, colstart, Sarr[0], Sarr[n % 2],
+                                  Iarr[n % 2], Sn, Ly, Lx, row0, rowm, col0, coln, cells);
+  } else {
   uint32_t known_busy = 0;  // columns from here on already seen not to be of the plain kind
   for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
     if (known_busy > 0) {
@@ -1369,6 +1869,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
     C::sync();
   }
+  }  // literal column loop
   int32_t* const Sfin = Sarr[n % 2];
   if (lane == 0) {
     int32_t* S = Sfin;
@@ -1585,23 +2086,30 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
                                         prm.sc, prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride,
                                         prm.cap_matches, prm.ranges + prm.ranges_off[t] / 4, &cells,
                                         shared_u32[threadIdx.x >> 5], hint);
+  // pairs whose band suits the register-resident K3 loop are marked (bit 8) while the ranges are still hot
+  const bool fast = st == 0 && cells <= BANDED_MAX_CELLS &&
+                    banded_fast_ok<32, K3_FAST_ROWS>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n);
   if (lane != 0) return;
   prm.num_cells[p] = cells;
-  prm.k4_status[p] = st;
+  prm.k4_status[p] = st | (fast ? 0x100u : 0u);
 }
 
 #ifndef B2A_K3_MINB
 #define B2A_K3_MINB 8  // resident CTAs per SM asked of ptxas for K3 (latency-bound: more warps win)
 #endif
-// K3: one warp per pair
-__global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
+// K3: one warp per pair.  FASTR == 0: the literal column loop, for every pair K4 did not mark; FASTR > 0: the
+// register-resident loop, for the marked ones (each kernel skips the other's pairs).
+template <int FASTR>
+__device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32_t n_wave) {
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = (int)(threadIdx.x & 31u);
   if (t >= n_wave) return;
   const uint64_t p = (uint64_t)prm.pair_lo + t;
   const uint64_t m = prm.x_len[p], n = prm.y_len[p];
   BandedOut o;
-  const uint32_t k4 = prm.k4_status[p];
+  const uint32_t k4raw = prm.k4_status[p];
+  const uint32_t k4 = k4raw & 0xFFu;
+  if (((k4raw >> 8) & 1u) != (FASTR > 0 ? 1u : 0u)) return;  // the other kernel's pair
   if (k4 != 0) {
     o = BandedOut{};
     o.status = 1 + k4;
@@ -1622,9 +2130,10 @@ __global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const Ban
       }
       return a == b ? sc.match_score : sc.mismatch_score;
     };
-    banded_compute_d<32>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc, score,
-                         prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p], prm.fill + prm.fill_off[t],
-                         prm.filter_clips != 0, prm.ops_scratch + prm.ops_off[p], o);
+    banded_compute_d<32, decltype(score), FASTR>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc,
+                                                 score, prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p],
+                                                 prm.fill + prm.fill_off[t], prm.filter_clips != 0,
+                                                 prm.ops_scratch + prm.ops_off[p], o);
   }
   if (lane != 0) return;
   if (o.status) {  // no alignment is reported for a pair the reference panics / hangs on (or that hit a capacity)
@@ -1643,6 +2152,13 @@ __global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const Ban
   prm.status[p] = o.status;
   if (o.status) atomicOr(prm.err_flag, o.status == 2 ? 2u : (o.status == 4 ? 8u : 1u));
   for (int q = 0; q < 4; ++q) prm.clip_len[4 * p + q] = o.clip[q];
+}
+
+__global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const BandedParams prm, uint32_t n_wave) {
+  banded_fill_body<0>(prm, n_wave);
+}
+__global__ void __launch_bounds__(128, 4) banded_fill_fast_kernel(const BandedParams prm, uint32_t n_wave) {
+  banded_fill_body<K3_FAST_ROWS>(prm, n_wave);
 }
 
 #endif

@@ -99,6 +99,7 @@ struct b2a_engine {
   std::string err;
   int tune_G = 0, tune_R = 0;
   int walk_mode = 0;  // 0 automatic, 1 one lane per pair, 2 one warp per pair
+  bool banded_fast = true;  // K3: register-resident column loop for the pairs K4 marks (B2A_BANDED_LITERAL=1: never)
   // packed input (b2a_align_batch_packed): the caller's "blob" is BitEnc storage of this width (0 = bytes); the
   // engine unpacks it on the device and uses its own byte offsets (eff_xoff / eff_yoff) from then on
   uint32_t packed_width = 0;
@@ -258,7 +259,11 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   b2a_engine* e = new b2a_engine();
   e->device = device_id;
   e->num_sms = prop.multiProcessorCount;
-  if (const char* env = getenv("B2A_NO_OVERLAP")) e->overlap_small = atoi(env) == 0;
+  // (measured on 10k reads: K1 at 67 % issue and K2 at 36 % are both instruction-bound, and K2's CTAs displace K1's
+  //  register-heavy ones: 0.571 ms overlapped against 0.558 ms back to back -- off unless asked for)
+  e->overlap_small = false;
+  if (const char* env = getenv("B2A_BANDED_LITERAL")) e->banded_fast = atoi(env) == 0;
+  if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return B2A_E_CUDA;
@@ -1453,7 +1458,14 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
       cudaEventElapsedTime(&ms, ev0, ev1);
       band_ms += ms;
     }
-    if (cap < kCapMax && std::find(h_k4.begin(), h_k4.end(), 1u) != h_k4.end()) {
+    bool overflowed = false;
+    for (uint32_t& v : h_k4) {
+      overflowed |= (v & 0xFFu) == 1u;
+      if (!e->banded_fast) v &= 0xFFu;
+    }
+    if (!e->banded_fast)  // the literal loop for every pair: clear K4's marks on the device as well
+      CK(cudaMemcpyAsync(e->d_bstatus.as<uint32_t>() + lo, h_k4.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, st));
+    if (cap < kCapMax && overflowed) {
       // a pair of this wave has more matches than the slab holds: redo the wave (K4 is idempotent) with a
       // larger capacity, in as many pairs as then fit the budget
       cap = (uint32_t)std::min<uint64_t>((uint64_t)cap * 8, kCapMax);
@@ -1485,7 +1497,14 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
       b3.fill = e->d_bfill.as<uint8_t>();
       b3.fill_off = e->d_bfoff.as<uint64_t>();
       CK(cudaEventRecord(ev1, st));
-      banded_fill_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);  // one warp per pair
+      // one warp per pair; K4 marked the pairs whose band suits the register-resident loop (each kernel skips
+      // the other's pairs)
+      if (e->banded_fast) {
+        banded_fill_fast_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
+        CK(cudaGetLastError());
+        ++e->launches;
+      }
+      banded_fill_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
       CK(cudaGetLastError());
       ++e->launches;
       CK(cudaEventRecord(ev2, st));

@@ -69,6 +69,16 @@ struct PairView {
   int32_t bnd_stride;
   const uint8_t* xs8 = nullptr;  // warp-per-pair K2: the pair's staged x / y copied into shared memory (or null)
   const uint8_t* ys8 = nullptr;
+  // exact division by R and by G*R without a divide: q = (x * mul) >> 40 with mul = ceil(2^40 / d) is floor(x / d)
+  // for x < 2^24 and d <= 2^10 (the walk computes a traceback address per move; sequence lengths are < 2^24)
+  uint64_t mulR = 0, mulGR = 0;
+  B2A_HD void set_shape(int32_t G_, int32_t R_) {
+    G = G_;
+    R = R_;
+    TBW = (R_ + 3) / 4;
+    mulR = ((1ull << 40) + (uint64_t)R_ - 1) / (uint64_t)R_;
+    mulGR = ((1ull << 40) + (uint64_t)(G_ * R_) - 1) / (uint64_t)(G_ * R_);
+  }
 
   B2A_HD int32_t xsym(int32_t i) const {  // x[i-1]
     const int32_t b = i - 1;
@@ -95,8 +105,8 @@ struct PairView {
   // compressed traceback nibble of an interior cell 1 <= i <= m-1, 1 <= j <= n
   B2A_HD uint32_t nib(int32_t i, int32_t j) const {
     const int32_t GR = G * R;
-    const int32_t s = (i - 1) / GR, rem = (i - 1) % GR;
-    const int32_t l = rem / R, r = rem % R;
+    const int32_t s = (int32_t)(((uint64_t)(uint32_t)(i - 1) * mulGR) >> 40), rem = (i - 1) - s * GR;
+    const int32_t l = (int32_t)(((uint64_t)(uint32_t)rem * mulR) >> 40), r = rem - l * R;
     const int32_t lane = g * G + l;
     const int32_t t = (j - 1) + l;
     const size_t word =
@@ -1036,8 +1046,8 @@ B2A_HD void prefetch_tb(const PairView& v, int32_t i, int32_t j) {
 #if defined(__CUDA_ARCH__)
   if (i >= 1 && i <= v.m - 1 && j >= 1 && j <= v.n) {
     const int32_t GR = v.G * v.R;
-    const int32_t s = (i - 1) / GR, rem = (i - 1) % GR;
-    const int32_t l = rem / v.R, r = rem % v.R;
+    const int32_t s = (int32_t)(((uint64_t)(uint32_t)(i - 1) * v.mulGR) >> 40), rem = (i - 1) - s * GR;
+    const int32_t l = (int32_t)(((uint64_t)(uint32_t)rem * v.mulR) >> 40), r = rem - l * v.R;
     const int32_t ln = v.g * v.G + l;
     const int32_t t = (j - 1) + l;
     const size_t word =
@@ -1085,9 +1095,7 @@ __device__ __forceinline__ void walk_lane(const WalkParams& prm, const Block& bl
   v.m = (int32_t)prm.pm[sp];
   v.n = (int32_t)prm.pn[sp];
   v.pi = lane;
-  v.G = prm.G;
-  v.R = prm.R;
-  v.TBW = (prm.R + 3) / 4;
+  v.set_shape(prm.G, prm.R);
   v.nstrips = (int32_t)blk.nstrips;
   v.K = (int32_t)blk.K;
   v.sub = lane / P;
@@ -1140,9 +1148,7 @@ __device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& bl
   v.m = (int32_t)prm.pm[sp];
   v.n = (int32_t)prm.pn[sp];
   v.pi = pi;
-  v.G = prm.G;
-  v.R = prm.R;
-  v.TBW = (prm.R + 3) / 4;
+  v.set_shape(prm.G, prm.R);
   v.nstrips = (int32_t)blk.nstrips;
   v.K = (int32_t)blk.K;
   v.sub = pi / P;

@@ -294,3 +294,50 @@ def default_engine(device: int = 0) -> Engine:
     if device not in _default:
         _default[device] = Engine(device)
     return _default[device]
+
+
+class MultiEngine:
+    """Every visible GPU from one process (b2a_multi_*): the batch is split over the devices, one ncclAllGather
+    reassembles the results, device 0's copy is returned.  Same results as Engine.align_batch."""
+
+    def __init__(self, device_ids=None):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        if device_ids is None:
+            rc = self._L.b2a_multi_create(C.byref(h), None, 0)
+        else:
+            ids = (C.c_int32 * len(device_ids))(*device_ids)
+            rc = self._L.b2a_multi_create(C.byref(h), ids, len(device_ids))
+        if rc != 0:
+            raise B2AError(rc, "cannot create the multi-GPU engine (no CPU fallback exists)")
+        self._h = h
+        self.stats = CStats()
+
+    @property
+    def n_devices(self) -> int:
+        return int(self._L.b2a_multi_device_count(self._h))
+
+    @property
+    def exchange_kind(self) -> str:
+        return self._L.b2a_multi_exchange_kind(self._h).decode()
+
+    def align_batch(self, mode: int, cscoring: CScoring, batch: Batch, results: Optional[Results] = None) -> Results:
+        if results is None:
+            results = Results(len(batch[2]), Engine.default_ops_capacity(batch))
+        cp = Engine._cpairs(batch)
+        rc = self._L.b2a_multi_align_batch(self._h, int(mode), C.byref(cscoring), C.byref(cp), C.byref(results.c),
+                                           C.byref(self.stats))
+        if rc != 0:
+            raise B2AError(rc, self._L.b2a_multi_last_error(self._h).decode())
+        return results
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b2a_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

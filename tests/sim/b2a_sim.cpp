@@ -449,9 +449,7 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
       v.m = (int32_t)p.pm[sp];
       v.n = (int32_t)p.pn[sp];
       v.pi = (int32_t)lane;
-      v.G = G;
-      v.R = R;
-      v.TBW = (R + 3) / 4;
+      v.set_shape(G, R);
       v.nstrips = (int32_t)blk.nstrips;
       v.K = (int32_t)blk.K;
       v.sub = (int32_t)lane / P;
@@ -634,6 +632,9 @@ extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t 
 }
 
 
+static int g_last_banded_fast = 0;
+extern "C" int sim_last_banded_fast() { return g_last_banded_fast; }
+
 // The W = 32 instantiations of K4 and K3 (what the GPU runs) with 32 host contexts as the lanes of one warp.
 // Same interface and outputs as sim_banded_hinted_one; have_matches = 0 lets K4 find the matches itself.
 extern "C" int sim_banded_warp32_one(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* x,
@@ -699,10 +700,20 @@ extern "C" int sim_banded_warp32_one(int mode, const sim_scoring* s, uint32_t k,
       if (table) return table[(size_t)a * 256 + b];
       return a == b ? sc.match_score : sc.mismatch_score;
     };
+    // as on the device: the register-resident column loop for the pairs whose band suits it (unless the test
+    // asks for the literal loop), the literal loop otherwise
+    bool fast_lane[32];
+    run32([&](int l) { fast_lane[l] = cells <= BANDED_MAX_CELLS && banded_fast_ok<32, K3_FAST_ROWS>(l, rng.data(), m, n); });
+    const bool fast = fast_lane[0] && !getenv("B2A_SIM_BANDED_LITERAL");
+    g_last_banded_fast = fast ? 1 : 0;
     run32([&](int l) {
       BandedOut mine{};
-      banded_compute_d<32>(l, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
-                           opsbuf.data() + opsbuf.size(), mine);
+      if (fast)
+        banded_compute_d<32, decltype(scoref), K3_FAST_ROWS>(l, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(),
+                                                             mode == 2 || mode == 3, opsbuf.data() + opsbuf.size(), mine);
+      else
+        banded_compute_d<32>(l, x, m, y, n, sc, scoref, rng.data(), cells, fill.data(), mode == 2 || mode == 3,
+                             opsbuf.data() + opsbuf.size(), mine);
       if (l == 0) o = mine;
     });
   }

@@ -371,3 +371,44 @@ def test_kmer_match_capacity_grows_instead_of_failing(eng, oracle, monkeypatch):
     _compare(eng, oracle, "semiglobal", _c_scoring(-5, -1, 1, -1), s, 8, 6, batch, "capacity retry (cap 64)")
     monkeypatch.delenv("B2A_BANDED_CAP")
     _compare(eng, oracle, "semiglobal", _c_scoring(-5, -1, 1, -1), s, 8, 6, batch, "default capacity")
+
+
+@pytest.mark.parametrize("mode", ["semiglobal", "local", "global", "custom"])
+def test_register_resident_k3_equals_literal_k3_and_oracle(oracle, mode, monkeypatch):
+    """K3's register-resident column loop (the pairs K4 marks) against the literal loop (B2A_BANDED_LITERAL=1) and
+    the oracle: random clips, gap_open > gap_extend cases, bands that qualify and bands that are too tall (w = 45)."""
+    from rust_bio_b200.engine import Engine
+    rng = np.random.default_rng({"semiglobal": 31, "local": 32, "global": 33, "custom": 34}[mode])
+    fast_eng = Engine(0)
+    monkeypatch.setenv("B2A_BANDED_LITERAL", "1")
+    lit_eng = Engine(0)
+    monkeypatch.delenv("B2A_BANDED_LITERAL")
+    try:
+        for trial in range(6):
+            pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9]))
+            go, ge = int(rng.choice([0, -1, -5])), int(rng.choice([0, -1, -2]))
+            ma, mi = int(rng.choice([1, 2])), int(rng.choice([-1, -3]))
+            clips = (pick(), pick(), pick(), pick()) if mode == "custom" else (MIN,) * 4
+            k, w = int(rng.choice([4, 6, 9])), int(rng.choice([3, 8, 20, 45]))
+            batch = _mutated_window_batch(900 + trial, 150, int(rng.integers(60, 220)), int(rng.integers(260, 700)),
+                                          sub=0.07, indel=0.03)
+            s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips, has_match_scores=1)
+            ref, rops, roff, _, ref_cells = oracle.banded_align_batch(mode, s, k, w, *batch, threads=8)
+            if np.any(ref["n_ops"] == 0xFFFFFFFF):
+                continue
+            cs = _c_scoring(go, ge, ma, mi, clips)
+            a = fast_eng.align_batch_banded(MODES[mode], cs, k, w, batch)
+            b = lit_eng.align_batch_banded(MODES[mode], cs, k, w, batch)
+            assert int(fast_eng.stats.cells) == ref_cells == int(lit_eng.stats.cells)
+            for f in ("score", "xstart", "xend", "ystart", "yend", "ops_off", "clip_len"):
+                assert np.array_equal(getattr(a, f), getattr(b, f)), (mode, trial, f)
+                if f in ref.dtype.names:
+                    assert np.array_equal(getattr(a, f).astype(np.int64), ref[f].astype(np.int64)), (mode, trial, f)
+            tot = int(a.ops_off[-1])
+            assert np.array_equal(a.ops[:tot], b.ops[:tot])
+            for p in range(0, 150, 7):
+                want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+                assert a.ops_of(p) == want, (mode, trial, p)
+    finally:
+        fast_eng.close()
+        lit_eng.close()

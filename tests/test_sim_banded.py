@@ -293,3 +293,72 @@ def test_warp32_caller_supplied_band_inputs(oracle):
     m = oracle.find_kmer_matches(x, y, 6)
     assert sim_util.banded_warp32_one(0, s, 6, 3, x, y, matches=m[::-1]) is None
     assert sim_util.banded_warp32_one(0, s, 6, 3, x, y, matches=m, path=[0, len(m)]) is None
+
+
+# ---- the register-resident K3 column loop (banded_columns_fast: a lane owns 5 consecutive rows, S/D of the
+# previous column and the row tracker in registers, one circular prefix maximum per column) on 32 emulated lanes.
+# banded_warp32_one takes it whenever banded_fast_ok says the pair's band qualifies, as the device does.
+
+@pytest.mark.parametrize("mode", ["semiglobal", "local", "global", "custom"])
+def test_warp32_fast_column_loop_vs_literal_vs_oracle(oracle, mode, monkeypatch):
+    rng = np.random.default_rng({"semiglobal": 11, "local": 12, "global": 13, "custom": 14}[mode])
+    pick = lambda: int(rng.choice([MIN, 0, 0, -2, -9]))
+    L = sim_util.lib()
+    n_fast = n_ok = 0
+    for trial in range(40):
+        go, ge = int(rng.choice([0, -1, -5])), int(rng.choice([0, -1, -2]))
+        clips = (pick(), pick(), pick(), pick()) if mode == "custom" else (MIN, MIN, MIN, MIN)
+        s, _ = oracle.make_scoring(go, ge, int(rng.choice([1, 2])), int(rng.choice([-1, -3])), None, *clips,
+                                   has_match_scores=int(trial % 2))
+        xl = int(rng.integers(20, 200))
+        x, y = _window_pair(rng, xl, xl + int(rng.integers(30, 400)), nsub=int(rng.integers(0, 9)))
+        k, w = int(rng.choice([4, 6, 9])), int(rng.choice([2, 5, 11, 20, 45]))  # w = 45: bands taller than 32 x 5 rows
+        got = sim_util.banded_warp32_one(MODES[mode], s, k, w, x, y, want_ranges=True)
+        fast = L.sim_last_banded_fast()
+        try:
+            ref, ref_ops = oracle.banded_align(mode, s, k, w, x, y)
+        except RuntimeError:
+            assert got is None
+            continue
+        assert got is not None and got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops, (mode, trial, fast)
+        n_ok += 1
+        n_fast += fast
+        if fast and trial % 4 == 0:  # the literal loop on the same pair gives the same answer
+            monkeypatch.setenv("B2A_SIM_BANDED_LITERAL", "1")
+            lit = sim_util.banded_warp32_one(MODES[mode], s, k, w, x, y, want_ranges=True)
+            monkeypatch.delenv("B2A_SIM_BANDED_LITERAL")
+            assert L.sim_last_banded_fast() == 0 and lit[0] == got[0] and lit[1] == got[1]
+    assert n_ok >= 30 and n_fast >= 20
+
+
+def test_warp32_fast_column_loop_blosum_and_c4_shape(oracle):
+    """LUT scoring (a tabulated MatchFunc) through the fast loop, and BASELINE config 4's shape on it."""
+    from rust_bio_b200 import scores
+    table = scores.matrix_table256("blosum62")
+    rng = np.random.default_rng(77)
+    L = sim_util.lib()
+    alpha = np.frombuffer(synth.PROTEIN, dtype=np.uint8)
+    s, keep = oracle.make_scoring(-10, -1, 0, 0, table)
+    n_fast = 0
+    for trial in range(10):
+        y = alpha[rng.integers(0, 20, 300)].copy()
+        st = int(rng.integers(0, 150))
+        x = y[st:st + 120].copy()
+        x[rng.integers(0, 120, 10)] = alpha[rng.integers(0, 20, 10)]
+        x, y = bytes(x), bytes(y)
+        for mode in ("local", "semiglobal"):
+            got = sim_util.banded_warp32_one(MODES[mode], s, 5, 7, x, y)
+            n_fast += L.sim_last_banded_fast()
+            ref, ref_ops = oracle.banded_align(mode, s, 5, 7, x, y)
+            assert got is not None and got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops, (trial, mode)
+    assert n_fast >= 10
+    batch = synth.mutated_window_pairs(synth.BASES["C4"], 0, 3, 500, 10000)
+    blob, xo, xl, yo, yl = batch
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    for p in range(3):
+        x = bytes(blob[int(xo[p]):int(xo[p]) + 500])
+        y = bytes(blob[int(yo[p]):int(yo[p]) + 10000])
+        got = sim_util.banded_warp32_one(MODES["semiglobal"], s, 32, 32, x, y)
+        assert L.sim_last_banded_fast() == 1
+        ref, ref_ops = oracle.banded_align("semiglobal", s, 32, 32, x, y)
+        assert got is not None and got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops

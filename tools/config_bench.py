@@ -61,15 +61,7 @@ for cfg in a.configs.split(","):
                       alpha.ctypes.data_as(C.c_void_p), len(alpha))
         run_full("C5 local protein 10000x10000 blosum62", 3, cs, batch)
     elif cfg == "C4":
-        from test_sim_banded import _mutated_window_batch
-        t0 = time.perf_counter()
-        small = _mutated_window_batch(4, 256, 500, 10000, sub=0.05, indel=0.01)
-        # replicate the 256 generated pairs to the requested count (generation in numpy is slow)
-        reps = max(1, a.c4_pairs // 256)
-        blob, xo, xl, yo, yl = small
-        nb = len(blob)
-        batch = (np.tile(blob, reps), np.concatenate([xo + np.uint64(i * nb) for i in range(reps)]), np.tile(xl, reps),
-                 np.concatenate([yo + np.uint64(i * nb) for i in range(reps)]), np.tile(yl, reps))
+        batch = synth.mutated_window_pairs(synth.BASES["C4"], 0, a.c4_pairs, 500, 10000)  # the named generator
         cs = CScoring(-5, -1, MIN_SCORE, MIN_SCORE, MIN_SCORE, MIN_SCORE, 1, -1, 1, None, None, 0)
         res = Results(len(batch[2]), 16); res.c.ops = None
         for _ in range(a.reps):

@@ -69,6 +69,18 @@ pub mod alignment {
         #[link(name = "b200align")]
         extern "C" {
             fn b2a_engine_create(out: *mut *mut c_void, device_id: i32) -> i32;
+            // every visible GPU from this one process (include/b200align.h: b2a_multi_*)
+            fn b2a_multi_create(out: *mut *mut c_void, device_ids: *const i32, n_devices: i32) -> i32;
+            fn b2a_multi_destroy(m: *mut c_void) -> i32;
+            fn b2a_multi_last_error(m: *const c_void) -> *const c_char;
+            fn b2a_multi_align_batch(
+                m: *mut c_void,
+                mode: i32,
+                scoring: *const b2a_scoring,
+                pairs: *const b2a_pairs,
+                results: *mut b2a_results,
+                stats: *mut c_void,
+            ) -> i32;
             fn b2a_engine_destroy(e: *mut c_void) -> i32;
             fn b2a_last_error(e: *const c_void) -> *const c_char;
             fn b2a_align_batch(
@@ -234,12 +246,20 @@ pub mod alignment {
         pub struct Aligner<F: MatchFunc> {
             scoring: Scoring<F>,
             engine: *mut c_void,
+            /// non-null after `on_all_gpus()`: `*_batch` calls are split over every visible GPU (one ncclAllGather
+            /// reassembles them); the banded entry points stay on `engine`'s device
+            multi: *mut c_void,
         }
         unsafe impl<F: MatchFunc + Send> Send for Aligner<F> {}
 
         impl<F: MatchFunc> Drop for Aligner<F> {
             fn drop(&mut self) {
-                unsafe { b2a_engine_destroy(self.engine) };
+                unsafe {
+                    if !self.multi.is_null() {
+                        b2a_multi_destroy(self.multi);
+                    }
+                    b2a_engine_destroy(self.engine)
+                };
             }
         }
 
@@ -271,7 +291,17 @@ pub mod alignment {
                 let device = std::env::var("B2A_DEVICE").ok().and_then(|v| v.parse().ok()).unwrap_or(0);
                 let rc = unsafe { b2a_engine_create(&mut engine, device) };
                 assert!(rc == 0, "b200align: no usable sm_100 device (rc = {}); there is no CPU fallback", rc);
-                Aligner { scoring, engine }
+                Aligner { scoring, engine, multi: std::ptr::null_mut() }
+            }
+
+            /// Use every visible B200 for the `*_batch` methods (not part of rust-bio's API: its Aligner is a
+            /// single-threaded CPU object).  Panics if the devices cannot be opened.
+            pub fn on_all_gpus(mut self) -> Self {
+                let mut m: *mut c_void = std::ptr::null_mut();
+                let rc = unsafe { b2a_multi_create(&mut m, std::ptr::null(), 0) };
+                assert!(rc == 0, "b200align: cannot open every visible device (rc = {})", rc);
+                self.multi = m;
+                self
             }
 
             /// Aligner::custom / global / semiglobal / local over a batch (mode = B2A_MODE_*).
@@ -350,6 +380,14 @@ pub mod alignment {
                 };
                 let is_banded = banded.is_some();
                 let rc = match banded {
+                    None if !self.multi.is_null() => {
+                        let rc = unsafe { b2a_multi_align_batch(self.multi, mode, &cs, &cp, &mut res, std::ptr::null_mut()) };
+                        if rc != 0 {
+                            let msg = unsafe { CStr::from_ptr(b2a_multi_last_error(self.multi)) }.to_string_lossy().into_owned();
+                            panic!("{}", msg);
+                        }
+                        rc
+                    }
                     None => unsafe { b2a_align_batch(self.engine, mode, &cs, &cp, &mut res, std::ptr::null_mut()) },
                     Some(BandedCall { k, w, matches: None, .. }) => unsafe {
                         b2a_align_batch_banded(self.engine, mode, &cs, k, w, &cp, &mut res, std::ptr::null_mut())

@@ -517,78 +517,122 @@ B2A_HD uint32_t sdpkpp_d(int lane, const uint64_t* matches, uint32_t nm, uint32_
   }
   C::sync();
   uint32_t np = 0;
-  if (lane == 0) {
+  // The event loop: each event reads what earlier ones wrote into the prefix-max tree, so events run one after
+  // the other -- but a Fenwick query touches its <= log2(ny)+1 nodes independently of each other (the index chain
+  // idx -= lowbit(idx) does not depend on the loaded values), and so does an update.  Lane l takes the l-th node
+  // of the chain; a query is then two warp maxima, an update one predicated store per lane.  The PrevPtr order
+  // (plane, score, d, id, x, y) is decided by (plane, score, d, id) alone: id is unique per entry.  Everything
+  // else of an event is the same arithmetic in every lane; lane 0 stores dp.
   uint32_t best_score = k;
   int32_t best_idx = 0;
   auto dp_gt = [](uint32_t s1, int32_t p1, uint32_t s2, int32_t p2) {  // (s1,p1) > (s2,p2)
     return s1 != s2 ? s1 > s2 : p1 > p2;
   };
+  const long long flip = (long long)0x8000000000000000ull;  // unsigned order through a signed maximum
   for (uint64_t e = 0; e < 2ull * nm; ++e) {
     const uint64_t key = ev[e];
     const bool is_start = (key & 1ull) != 0;
     const uint32_t e0 = (uint32_t)(key >> 33), e1 = (uint32_t)((key >> 1) & 0xffffffffull);
     const uint32_t p = ev_p[e];
     if (is_start) {
-      dp_score[p] = k * match_score;
-      dp_prev[p] = -1;
-      // max_col_dp.get(j): prefix max over inserted coordinates <= e1
-      PrevPtrD best{0, 0, 0, 0, 0, 0};
+      uint32_t dps = k * match_score;
+      int32_t dpp = -1;
+      // max_col_dp.get(j): prefix max over inserted coordinates <= e1; node l of the chain in lane l
+      PrevPtrD mine{0, 0, 0, 0, 0, 0};
       {
         uint32_t idx = ev_aux[e];  // number of coordinates <= e1; Fenwick positions are 1-based
-        while (idx > 0) {
-          if (prev_ge(fen[idx], best)) best = fen[idx];
-          idx -= idx & (0u - idx);
+        for (int t = 0; t < lane && idx; ++t) idx &= idx - 1u;
+        if (W == 1) {  // sequential build: walk the whole chain
+          while (idx > 0) {
+            if (prev_ge(fen[idx], mine)) mine = fen[idx];
+            idx &= idx - 1u;
+          }
+        } else if (idx > 0) {
+          mine = fen[idx];
         }
+      }
+      PrevPtrD best = mine;
+      if (W > 1) {
+        const long long k1 = (long long)(((uint64_t)mine.plane << 32) | mine.score) ^ flip;
+        const long long m1 = C::all_max(k1);
+        const long long k2 = k1 == m1 ? (long long)((((uint64_t)mine.d << 32) | mine.id) ^ (uint64_t)flip) : flip;
+        const long long m2 = C::all_max(k2);
+        const uint32_t who = C::ballot(k1 == m1 && k2 == m2);
+        int src = 0;
+        while (!((who >> src) & 1u)) ++src;
+        best.plane = (uint32_t)(((uint64_t)(m1 ^ flip)) >> 32);
+        best.score = (uint32_t)((uint64_t)(m1 ^ flip) & 0xffffffffull);
+        best.d = (uint32_t)(((uint64_t)(m2 ^ flip)) >> 32);
+        best.id = (uint32_t)((uint64_t)(m2 ^ flip) & 0xffffffffull);
+        best.x = (uint32_t)C::from((int32_t)mine.x, src);
+        best.y = (uint32_t)C::from((int32_t)mine.y, src);
       }
       if (best.score > 0) {
         if (lcs) {  // dp[p] = (k + best_value, best_position), sparse.rs:111-113
-          dp_score[p] = k + best.score;
-          dp_prev[p] = (int32_t)best.id;
+          dps = k + best.score;
+          dpp = (int32_t)best.id;
         } else {
           const uint32_t g0 = e0 - best.x, g1 = e1 - best.y;
           const uint32_t gap = g0 > g1 ? g0 : g1;
           const uint32_t pen = gap > 0 ? go + gap * ge : 0;
           const uint32_t sum = best.score + k * match_score;
           const uint32_t ns = sum > pen ? sum - pen : 0;
-          if (dp_gt(ns, (int32_t)best.id, dp_score[p], dp_prev[p])) {
-            dp_score[p] = ns;
-            dp_prev[p] = (int32_t)best.id;
+          if (dp_gt(ns, (int32_t)best.id, dps, dpp)) {
+            dps = ns;
+            dpp = (int32_t)best.id;
           }
         }
-        if (dp_gt(dp_score[p], (int32_t)p, best_score, best_idx)) {
-          best_score = dp_score[p];
+        if (dp_gt(dps, (int32_t)p, best_score, best_idx)) {
+          best_score = dps;
           best_idx = (int32_t)p;
         }
       }
+      if (lane == 0) {
+        dp_score[p] = dps;
+        dp_prev[p] = dpp;
+      }
     } else {
+      uint32_t dps = dp_score[p];
+      int32_t dpp = dp_prev[p];
       {
         const uint32_t l2 = ev_aux[e];  // the match at (x - 1, y - 1), sparse.rs:267-275
         if (l2 != 0xFFFFFFFFu) {
           const uint32_t cs = dp_score[l2] + match_score;
-          if (dp_gt(cs, (int32_t)l2, dp_score[p], dp_prev[p])) {
-            dp_score[p] = cs;
-            dp_prev[p] = (int32_t)l2;
+          if (dp_gt(cs, (int32_t)l2, dps, dpp)) {
+            dps = cs;
+            dpp = (int32_t)l2;
           }
-          if (dp_gt(dp_score[p], (int32_t)p, best_score, best_idx)) {
-            best_score = dp_score[p];
+          if (dp_gt(dps, (int32_t)p, best_score, best_idx)) {
+            best_score = dps;
             best_idx = (int32_t)p;
           }
         }
       }
+      if (lane == 0) {
+        dp_score[p] = dps;
+        dp_prev[p] = dpp;
+      }
       PrevPtrD pf;
       pf.d = lcs ? 0u : e0 + e1;
-      pf.plane = lcs ? 0u : dp_score[p] + pf.d * ge;
-      pf.score = dp_score[p];
+      pf.plane = lcs ? 0u : dps + pf.d * ge;
+      pf.score = dps;
       pf.id = p;
       pf.x = lcs ? 0u : e0;
       pf.y = lcs ? 0u : e1;
-      uint32_t idx = rank_end[p];  // 1-based rank of this coordinate
-      while (idx <= ny) {
+      uint32_t idx = rank_end[p];  // 1-based rank of this coordinate; node l of the update chain in lane l
+      for (int t = 0; t < lane && idx <= ny; ++t) idx += idx & (0u - idx);
+      if (W == 1) {
+        while (idx <= ny) {
+          if (prev_ge(pf, fen[idx])) fen[idx] = pf;
+          idx += idx & (0u - idx);
+        }
+      } else if (idx <= ny) {
         if (prev_ge(pf, fen[idx])) fen[idx] = pf;
-        idx += idx & (0u - idx);
       }
     }
+    C::sync();  // the tree and dp as this event left them are what the next one reads
   }
+  if (lane == 0) {
   int32_t pm = best_idx;
   while (pm >= 0 && np < nm) {
     path[np++] = (uint32_t)pm;

@@ -1081,7 +1081,7 @@ B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t 
           }
           Dp[r] = MIN_SCORE;
           Snr[r] = real ? Sn[i] : MIN_SCORE;
-          xr[r] = real ? (int32_t)x[i - 1] : 0;
+          xr[r] = (int32_t)x[real ? i - 1 : 0];  // rows beyond x repeat a real symbol: the score function only ever sees sequence bytes
         }
       }
       // ---------------------------------------------------------------- per row: everything that does not need I

@@ -83,6 +83,7 @@ struct b2a_engine {
   cudaStream_t aux_stream = nullptr;   // second fill stream of the small-batch overlap (b2a_batch_run)
   std::vector<cudaEvent_t> sub_ev;
   bool overlap_small = true;
+  bool overlap_big = false;
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
   bool is_slot = false;            // this engine is a slot of another engine's chunk pipeline
@@ -122,7 +123,8 @@ struct b2a_engine {
   DevBuf d_blob, d_xoff, d_xlen, d_yoff, d_ylen, d_order, d_pm, d_pn, d_blocks, d_seq, d_bnd, d_rows,
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
       d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
-      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx, d_raw;
+      d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx, d_raw, d_gnops,
+      d_gnops64, d_goff;
   uint32_t* h_nops = nullptr;  // pinned staging of b2a_gathered_fetch
   uint64_t h_nops_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -264,6 +266,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   e->overlap_small = false;
   if (const char* env = getenv("B2A_BANDED_LITERAL")) e->banded_fast = atoi(env) == 0;
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
+  if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return B2A_E_CUDA;
@@ -302,7 +305,7 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_xe, &e->d_ys, &e->d_ye, &e->d_nops, &e->d_opssrc, &e->d_clip, &e->d_status,
                     &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_prog, &e->d_bcells,
                     &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill, &e->d_hmoff, &e->d_hmxy,
-                    &e->d_hpoff, &e->d_hpidx, &e->d_raw,
+                    &e->d_hpoff, &e->d_hpidx, &e->d_raw, &e->d_gnops, &e->d_gnops64, &e->d_goff,
                     &e->d_bfoff};
   for (DevBuf* b : bufs) b->release();
   for (auto& v : e->ev)
@@ -769,8 +772,11 @@ int32_t b2a_batch_run(b2a_engine* e) {
     // blocks whose fills alternate between two streams (they overlap: the next fill's CTAs take the SM slots the
     // previous one's leave) and whose walks run on a high-priority stream as soon as their own fill is done --
     // K2 of sub-range s overlaps K1 of sub-range s+1, and only the last sub-range's K2 is exposed.
-    const bool overlap = e->overlap_small && pl.waves.size() == 1 && warp_walk && pl.G != 32 && nb >= 64 &&
-                         !use_tail && e->walk_mode != 1;
+    // The same cut pays for LARGE batches with the lane-per-pair K2 (B2A_OVERLAP_BIG): K2 is latency/bandwidth-bound
+    // (12 % of the 1M-pair step) and hides under the next sub-range's fill.
+    const bool overlap_big = e->overlap_big && pl.waves.size() == 1 && !warp_walk && pl.G != 32 && nb >= 4096 && !use_tail;
+    const bool overlap = overlap_big || (e->overlap_small && pl.waves.size() == 1 && warp_walk && pl.G != 32 && nb >= 64 &&
+                                         !use_tail && e->walk_mode != 1);
     if (overlap) {
       constexpr int kSub = 4;
       if (!e->tail_stream) {
@@ -806,13 +812,14 @@ int32_t b2a_batch_run(b2a_engine* e) {
         WalkParams w2 = wp;
         w2.blocks = wp.blocks + lo_b;
         w2.nblocks = hi_b - lo_b;
-        walk_warp_kernel<<<w2.nblocks * 8, 128, (size_t)per_warp_smem * 4, e->tail_stream>>>(w2);
+        if (warp_walk) walk_warp_kernel<<<w2.nblocks * 8, 128, (size_t)per_warp_smem * 4, e->tail_stream>>>(w2);
+        else walk_kernel<<<(w2.nblocks * 32 + 127) / 128, 128, 0, e->tail_stream>>>(w2);
         CK(cudaGetLastError());
         ++e->launches;
       }
       CK(cudaEventRecord(e->sub_ev[kSub + 1], e->tail_stream));
       CK(cudaStreamWaitEvent(st, e->sub_ev[kSub + 1], 0));  // everything rejoins the engine's stream
-      e->last_walk_warp = true;
+      e->last_walk_warp = warp_walk;
       CK(cudaEventRecord(e->wave_ev[3 * wi + 2], st));
       ++wi;
       continue;
@@ -1678,14 +1685,28 @@ int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t seg
     ops += total;
   }
   if (r->ops && ops > r->ops_capacity) return e->fail(B2A_E_CAPACITY, "ops buffer too small for the gathered batch");
-  // n_ops of every segment lands in one staging array (pinned, engine-owned); everything else goes straight
-  // to its place in the caller's arrays
-  if (e->h_nops_cap < pairs + 1) {
-    if (e->h_nops) cudaFreeHost(e->h_nops);
-    e->h_nops = nullptr;
-    e->h_nops_cap = 0;
-    if (cudaMallocHost(&e->h_nops, (pairs + 1) * 4) != cudaSuccess) return e->fail(B2A_E_CUDA, "cudaMallocHost failed");
-    e->h_nops_cap = pairs + 1;
+  // ops_off of the whole batch = exclusive scan of every segment's n_ops in segment order, done on the device
+  // (widen + cub scan over the concatenated counts) and copied straight into the caller's array; everything else
+  // goes straight to its place in the caller's arrays as well
+  if (r->ops_off && pairs) {
+    CK(e->d_gnops.reserve((pairs + 1) * 4));
+    CK(e->d_gnops64.reserve((pairs + 1) * 8));
+    CK(e->d_goff.reserve((pairs + 1) * 8));
+    uint64_t pb0 = 0;
+    for (uint32_t g = 0; g < n_segments; ++g) {
+      const uint64_t n = hdr[8 * g];
+      if (n) CK(cudaMemcpyAsync(e->d_gnops.as<uint32_t>() + pb0, base + (uint64_t)g * segment_bytes + 64 + 20 * n, 4 * n,
+                                cudaMemcpyDeviceToDevice, st));
+      pb0 += n;
+    }
+    widen_kernel<<<(unsigned)((pairs + 1 + 255) / 256), 256, 0, st>>>(e->d_gnops.as<uint32_t>(), e->d_gnops64.as<uint64_t>(), pairs);
+    CK(cudaGetLastError());
+    size_t tmp = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, e->d_gnops64.as<uint64_t>(), e->d_goff.as<uint64_t>(), (int64_t)(pairs + 1), st));
+    CK(e->d_scan.reserve(tmp + 16));
+    CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_gnops64.as<uint64_t>(), e->d_goff.as<uint64_t>(), (int64_t)(pairs + 1), st));
+    CK(cudaMemcpyAsync(r->ops_off, e->d_goff.p, (pairs + 1) * 8, cudaMemcpyDeviceToHost, st));
+    moved += (pairs + 1) * 8;
   }
   uint64_t pb = 0, ob = 0;
   for (uint32_t g = 0; g < n_segments; ++g) {
@@ -1701,7 +1722,6 @@ int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t seg
     CK(down(r->xend ? r->xend + pb : nullptr, 8 * n, 4 * n));
     CK(down(r->ystart ? r->ystart + pb : nullptr, 12 * n, 4 * n));
     CK(down(r->yend ? r->yend + pb : nullptr, 16 * n, 4 * n));
-    CK(down(e->h_nops + pb, 20 * n, 4 * n));
     CK(down(r->clip_len ? r->clip_len + 4 * pb : nullptr, 24 * n, 16 * n));
     CK(down(r->ops ? r->ops + ob : nullptr, 40 * n, total));
     pb += n;
@@ -1709,13 +1729,8 @@ int32_t b2a_gathered_fetch(b2a_engine* e, const void* dev_gathered, uint64_t seg
   }
   CK(cudaStreamSynchronize(st));
   if (r->ops_off) {
-    uint64_t acc = 0;
-    for (uint64_t p = 0; p < pairs; ++p) {
-      r->ops_off[p] = acc;
-      acc += e->h_nops[p];
-    }
-    r->ops_off[pairs] = acc;
-    if (acc != ops) return e->fail(B2A_E_INVALID, "gathered segments: n_ops do not add up to the ops bytes");
+    if (!pairs) r->ops_off[0] = 0;
+    if (r->ops_off[pairs] != ops) return e->fail(B2A_E_INVALID, "gathered segments: n_ops do not add up to the ops bytes");
   }
   if (r->status) std::memset(r->status, 0, pairs * 4);  // segments only carry completed batches
   if (n_pairs_total) *n_pairs_total = pairs;

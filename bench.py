@@ -343,9 +343,16 @@ def main():
             rng = np.random.default_rng(7)
             bad, checked = 0, 0
             for r in range(world):
-                idx = np.unique(np.concatenate([np.arange(64), rng.integers(0, P, size=192)]))
-                shard = synth.uniform_pairs(synth.BASES["C2"], r * P, P, M, N_LEN) if r else batch
-                sub = (shard[0], shard[1][idx], shard[2][idx], shard[3][idx], shard[4][idx])
+                # the first 128 pairs of the rank's shard and a random window of 128 (only those are generated)
+                w0 = int(rng.integers(128, max(129, P - 128)))
+                idx = np.concatenate([np.arange(min(128, P)), np.arange(w0, min(P, w0 + 128))])
+                parts = [synth.uniform_pairs(synth.BASES["C2"], r * P + int(a), int(b - a), M, N_LEN)
+                         for a, b in ((0, min(128, P)), (w0, min(P, w0 + 128)))]
+                stride = len(parts[0][0]) // max(1, len(parts[0][2]))
+                blob_s = np.concatenate([q[0] for q in parts])
+                off0 = np.uint64(len(parts[0][0]))
+                sub = (blob_s, np.concatenate([parts[0][1], parts[1][1] + off0]), np.concatenate([q[2] for q in parts]),
+                       np.concatenate([parts[0][3], parts[1][3] + off0]), np.concatenate([q[4] for q in parts]))
                 ref, ops, off, _ = orc.align_batch("local", oracle_scoring(orc), *sub, threads=min(16, orc.hardware_threads()))
                 for k, p in enumerate(idx):
                     gp = r * P + int(p)

@@ -961,6 +961,16 @@ B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n
   return C::ballot(!ok) == 0u;
 }
 
+B2A_HD int32_t count_trailing_ones(uint32_t v) {  // number of consecutive set bits from bit 0
+#if defined(__CUDA_ARCH__)
+  return v == 0xFFFFFFFFu ? 32 : __ffs((int)~v) - 1;
+#else
+  int32_t c = 0;
+  while (c < 32 && ((v >> c) & 1u)) ++c;
+  return c;
+#endif
+}
+
 template <int W, int R, class ScoreFn>
 B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t m, const uint8_t* y, const int32_t n,
                                 const DevScoring& sc, ScoreFn score, const uint32_t* rng, const uint32_t* colstart,
@@ -999,8 +1009,7 @@ B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t 
       const int32_t jc = j + lane;
       const bool emp = jc <= n && rng[2 * jc] >= rng[2 * jc + 1];
       const uint32_t bal = C::ballot(emp);
-      int32_t run = 0;
-      while (run < W && ((bal >> run) & 1u)) ++run;
+      const int32_t run = count_trailing_ones(bal);  // >= 1: this column is empty
       if (lane < run) rowm[jc] = (uint16_t)((rowm[jc] & ~0x0F00u) | (TB_XCLIP_SUFFIX << 8));
       S0_prev = Sm_prev = Dm_prev = MIN_SCORE;
       all_fresh = true;

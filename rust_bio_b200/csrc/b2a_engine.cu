@@ -69,7 +69,8 @@ const FillLaunch* find_shape(int G, int R) {
 
 constexpr uint32_t kMaxStageSmem = 200 * 1024;  // of the 227 KB a CTA may use
 constexpr uint64_t kWarpWalkMaxPairs = 16384;  // waves up to this many pairs use the warp-per-pair K2
-constexpr int kMaxAlpha = 64;
+constexpr int kMaxAlpha = 64;        // MatchParams: LUT up to this many symbols, compare/select beyond
+constexpr int kMaxAlphaTable = 128;  // tabulated MatchFunc: a 128 x 128 LUT (64 KB of shared memory) covers 7-bit alphabets
 
 }  // namespace
 
@@ -484,9 +485,9 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   int64_t maxabs = std::max<int64_t>(std::llabs((long long)s->match_score), std::llabs((long long)s->mismatch_score));
   for (int k = 0; k < 256; ++k) e->codemap_host[k] = (uint8_t)k;
   e->lut_host.clear();
-  if (s->table && (int)syms.size() > kMaxAlpha)
-    return e->fail(B2A_E_UNSUPPORTED, "MatchFunc table over more than 64 distinct symbols");
-  if ((int)syms.size() <= kMaxAlpha) {
+  if (s->table && (int)syms.size() > kMaxAlphaTable)
+    return e->fail(B2A_E_UNSUPPORTED, "MatchFunc table over more than 128 distinct symbols");
+  if ((int)syms.size() <= (s->table ? kMaxAlphaTable : kMaxAlpha)) {
     sc.alpha = (int32_t)syms.size();
     for (int k = 0; k < 256; ++k) e->codemap_host[k] = 0xFF;
     for (int a = 0; a < sc.alpha; ++a) e->codemap_host[syms[a]] = (uint8_t)a;

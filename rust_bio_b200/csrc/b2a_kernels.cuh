@@ -26,6 +26,9 @@ struct PackParams {
 // Staged layout of a block (32-bit words): x: [task sub][word w][pair slot p], then y likewise,
 // with P = 32/G pairs per task.  Bytes past the end of a sequence are 0.
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
+  __shared__ uint8_t cmap[256];  // symbol -> code, read four times per staged word
+  cmap[threadIdx.x] = prm.codemap[threadIdx.x];
+  __syncthreads();
   const Block blk = prm.blocks[blockIdx.x];
   const int G = prm.G, P = 32 / G;
   uint32_t* out = reinterpret_cast<uint32_t*>(prm.seq + blk.seq_off);
@@ -41,16 +44,27 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
       const uint32_t orig = prm.order[blk.first + pair];
       const uint64_t off = isy ? prm.y_off[orig] : prm.x_off[orig];
       const uint32_t len = isy ? prm.y_len[orig] : prm.x_len[orig];
+      const uint32_t pos0 = w * 4;
+      if (pos0 < len) {
+        // the four source bytes in one load when the sequence starts on a word boundary and the word is whole
+        uint32_t raw;
+        const uint32_t have = len - pos0 < 4 ? len - pos0 : 4;
+        if (((off & 3ull) == 0) && have == 4) {
+          raw = *reinterpret_cast<const uint32_t*>(prm.blob + off + pos0);
+        } else {
+          raw = 0;
+          for (uint32_t b = 0; b < have; ++b) raw |= (uint32_t)prm.blob[off + pos0 + b] << (8 * b);
+        }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const uint32_t pos = w * 4 + b;
-        if (pos < len) {
-          uint32_t code = prm.codemap[prm.blob[off + pos]];
-          if (code == 0xFFu) {  // outside the scoring alphabet: flag it, stage a valid code
-            *prm.bad_symbol = 1u;
-            code = 0;
+        for (int b = 0; b < 4; ++b) {
+          if ((uint32_t)b < have) {
+            uint32_t code = cmap[(raw >> (8 * b)) & 0xFFu];
+            if (code == 0xFFu) {  // outside the scoring alphabet: flag it, stage a valid code
+              *prm.bad_symbol = 1u;
+              code = 0;
+            }
+            val |= code << (8 * b);
           }
-          val |= code << (8 * b);
         }
       }
     }

@@ -412,3 +412,19 @@ def test_register_resident_k3_equals_literal_k3_and_oracle(oracle, mode, monkeyp
     finally:
         fast_eng.close()
         lit_eng.close()
+
+
+def test_refused_band_keeps_the_called_methods_mode(eng):
+    """banded.rs:407-420 returns the empty MIN_SCORE alignment (xlen = ylen = 0) above MAX_CELLS; global /
+    semiglobal / local then overwrite only `.mode` (banded.rs:889-890) -- the mirror must not report Custom."""
+    from rust_bio_b200 import synth
+    from rust_bio_b200.alignment import AlignmentMode
+    from rust_bio_b200.banded import Aligner
+    from rust_bio_b200.pairwise import Scoring
+    blob, xo, xl, yo, yl = synth.uniform_pairs(synth.BASES["C4"], 0, 1, 500, 10000)
+    x, y = bytes(blob[int(xo[0]):int(xo[0]) + 500]), bytes(blob[int(yo[0]):int(yo[0]) + 10000])
+    al = Aligner.with_scoring(Scoring.from_scores(-5, -1, 1, -1), 32, 32, engine=eng)
+    for method, mode in ((al.global_, AlignmentMode.Global), (al.semiglobal, AlignmentMode.Semiglobal),
+                         (al.local, AlignmentMode.Local), (al.custom, AlignmentMode.Custom)):
+        a = method(x, y)
+        assert a.score == MIN and a.operations == [] and (a.xlen, a.ylen) == (0, 0) and a.mode == mode

@@ -414,10 +414,10 @@ def test_c5_shape_8_pairs_10k_x_10k_blosum62_local(eng, oracle):
 @pytest.mark.parametrize("lut", [True, False], ids=["lut", "matchparams_wide_alphabet"])
 def test_unpacked_tracker_variants_4200(eng, oracle, G, R, lut):
     """m, n > 4095 in every mode: the fill_kernel<G,R,FLAGS> instantiations without F_PACKTRK
-    (b2a_fill_inst.cu: 0, TRACK_ROWS, ALL, ALL|RELU, each with and without F_LUT).  A 100-symbol alphabet keeps
+    (b2a_fill_inst.cu: 0, TRACK_ROWS, ALL, ALL|RELU, each with and without F_LUT).  A 200-symbol alphabet keeps
     MatchParams on its compare/select path (no LUT above 64 symbols)."""
     from rust_bio_b200 import synth
-    alphabet = b"ACGT" if lut else bytes(range(33, 133))
+    alphabet = b"ACGT" if lut else bytes(range(33, 233))
     rng = np.random.default_rng(G * 100 + R + (1 if lut else 0))
     pairs = []
     for m, n in [(4200, 4200), (4100, 4301), (4333, 4097), (4099, 5000)]:
@@ -732,3 +732,68 @@ def test_bitenc_packed_input_through_the_chunk_pipeline_and_banded(eng, oracle):
     for p in range(200):
         want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(refb["n_ops"][p])]]
         assert resb.ops_of(p) == want, p
+
+
+def test_scattered_blob_layout_through_the_chunk_pipeline(eng, oracle):
+    """A caller blob laid out as all x, then all y: each chunk of the pipeline gathers its own sequences into a
+    compact blob instead of uploading (almost) the whole span once per chunk; results equal those of
+    the interleaved layout."""
+    from rust_bio_b200 import synth
+    n = 270_000
+    a = synth.ragged_pairs(501, n, 24, 30, min_len=1)
+    blob, xo, xl, yo, yl = a
+    # rebuild as [all x][gap][all y]
+    xs = np.concatenate([[0], np.cumsum(xl.astype(np.uint64))]).astype(np.uint64)
+    ys = np.concatenate([[0], np.cumsum(yl.astype(np.uint64))]).astype(np.uint64)
+    gap = 3_000_000
+    nb = np.zeros(int(xs[-1]) + gap + int(ys[-1]) + 16, dtype=np.uint8)
+    # vectorised copy of every sequence: positions = offset + running index
+    def place(dst_off, src_off, lens, base):
+        total = int(lens.astype(np.uint64).sum())
+        rep = np.repeat(np.arange(len(lens)), lens.astype(np.int64))
+        within = np.arange(total) - np.repeat((np.cumsum(lens.astype(np.int64)) - lens.astype(np.int64)), lens.astype(np.int64))
+        nb[base + dst_off[rep].astype(np.int64) + within] = blob[src_off[rep].astype(np.int64) + within]
+    place(xs[:-1], xo, xl, 0)
+    place(ys[:-1], yo, yl, int(xs[-1]) + gap)
+    b = (nb, xs[:-1].copy(), xl, ys[:-1] + np.uint64(int(xs[-1]) + gap), yl)
+    cs, keep = _c_scoring(-5, -1, 1, -1)
+    r1 = eng.align_batch(MODES["local"], cs, a)
+    r2 = eng.align_batch(MODES["local"], cs, b)
+    assert int(eng.stats.h2d_bytes) < 3 * (int(xl.sum()) + int(yl.sum()) + 40 * n)  # not one blob upload per chunk
+    for k in ("score", "xstart", "xend", "ystart", "yend", "ops_off"):
+        assert np.array_equal(getattr(r1, k), getattr(r2, k)), k
+    tot = int(r1.ops_off[-1])
+    assert np.array_equal(r1.ops[:tot], r2.ops[:tot])
+
+
+def test_tabulated_matchfunc_over_100_symbols(eng, oracle):
+    """A closure MatchFunc (mod.rs:221-228) over a 100-symbol alphabet: tabulated into a 100 x 100 LUT in shared
+    memory (round 1 refused tables over 64 symbols); beyond 128 distinct symbols the table is still refused."""
+    from rust_bio_b200._lib import B2AError
+    from rust_bio_b200.engine import pack_pairs
+    rng = np.random.default_rng(12)
+    alphabet = np.arange(33, 133, dtype=np.uint8)
+    fn = lambda a, b: (5 if a == b else (1 if (a ^ b) < 4 else -((a * 7 + b * 3) % 5)))
+    table = np.zeros((256, 256), dtype=np.int32)
+    for a in alphabet:
+        for b in alphabet:
+            table[a, b] = fn(int(a), int(b))
+    pairs = []
+    for _ in range(60):
+        m, n = int(rng.integers(1, 180)), int(rng.integers(1, 200))
+        x = alphabet[rng.integers(0, 100, m)]
+        y = alphabet[rng.integers(0, 100, n)].copy()
+        k = min(m, n) // 2
+        y[:k] = x[:k]
+        pairs.append((bytes(x), bytes(y)))
+    batch = pack_pairs(pairs)
+    for mode, go in (("local", -6), ("global", -4), ("semiglobal", -5)):
+        s, keep1 = oracle.make_scoring(go, -1, 0, 0, table)
+        ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=4)
+        cs, keep2 = _c_scoring(go, -1, 0, 0, table=table, alphabet=bytes(alphabet))
+        got, ops = _engine_result(eng, mode, cs, batch)
+        assert_same(got, ops, ref, ref_ops, batch, f"100-symbol table {mode}")
+    wide = bytes(range(20, 220))
+    cs, keep = _c_scoring(-5, -1, 0, 0, table=table, alphabet=wide)
+    with pytest.raises(B2AError, match="128 distinct"):
+        eng.align_batch(MODES["local"], cs, batch)

@@ -373,7 +373,6 @@ def main():
 
     # ---- end-to-end arm: pinned host buffers in, host results out, copies inside the timed region
     e2e_each = []
-    e2e_packed = None
     if world == 1:
         for _ in range(max(warm, 3)):
             eng.align_batch(MODE_LOCAL, cs, batch, results=results)
@@ -387,52 +386,18 @@ def main():
         e2e_ms = (time.perf_counter() - t0) / steps * 1e3
         h2d, d2h = int(eng.stats.h2d_bytes), int(eng.stats.d2h_bytes)
         e2e_note = "b2a_align_batch: pinned host inputs -> host results (chunked H2D / kernels / D2H pipeline inside)"
-        # the same batch held as BitEnc storage (2 bits per symbol) through b2a_align_batch_packed:
-        # a quarter of the sequence bytes cross PCIe; reported beside e2e, not instead of it (the reference's
-        # Aligner takes byte slices)
-        rank_of = np.zeros(256, dtype=np.uint32)
-        rank_of[np.frombuffer(b"ACGT", dtype=np.uint8)] = np.arange(4, dtype=np.uint32)
-        stride_b = int(batch[1][1] - batch[1][0]) if P > 1 else len(batch[0])
-        sym = rank_of[batch[0][:P * stride_b].reshape(P, stride_b)]  # x at [0, 160), y at [160, 320): 16-symbol blocks
-        shifts = (np.arange(16, dtype=np.uint32) * np.uint32(2))[None, None, :]
-        blocks = np.bitwise_or.reduce(sym.reshape(P, stride_b // 16, 16) << shifts, axis=2).astype(np.uint32)
-        del sym
-        per = stride_b // 16
-        xb = (np.arange(P, dtype=np.uint64) * np.uint64(per))
-        yb = xb + np.uint64((int(batch[3][0]) - int(batch[1][0])) // 16)
-        pk_keep = [pin(a) for a in (np.concatenate([blocks.reshape(-1), np.zeros(4, np.uint32)]), xb, yb)]
-        packed = (pk_keep[0][1], pk_keep[1][1], batch[2], pk_keep[2][1], batch[4], 2)
-        del blocks
-        for _ in range(3):
-            eng.align_batch_packed(MODE_LOCAL, cs, packed, results=results)
-        pk_each = []
-        for _ in range(steps):
-            t1 = time.perf_counter()
-            eng.align_batch_packed(MODE_LOCAL, cs, packed, results=results)
-            pk_each.append(round((time.perf_counter() - t1) * 1e3, 2))
-        e2e_packed = {"value": round(cells_rank / (float(np.mean(pk_each)) * 1e-3) / 1e9, 2), "unit": "GCUPS",
-                      "ms_each_step": pk_each, "h2d_bytes_per_step": int(eng.stats.h2d_bytes),
-                      "input": "BitEnc storage, width 2 (b2a_align_batch_packed): 16 symbols per 32-bit block"}
-        # restore the byte-path statistics reported below
-        eng.align_batch(MODE_LOCAL, cs, batch, results=results)
-        h2d, d2h = int(eng.stats.h2d_bytes), int(eng.stats.d2h_bytes)
     else:
+        from rust_bio_b200.dist import ShardedAligner
         total_pairs = world * P
+        allres = None
         if rank == 0:
             allres, keep_all = pinned_results(torch, Results, total_pairs, 64 * total_pairs)
-        b = bufs[0]
+        sharded = ShardedAligner(local, chunks=3)
         d2h = 0
 
         def step_e2e():
-            nonlocal d2h
-            eng.stage(MODE_LOCAL, cs, batch)       # H2D of this rank's shard (pinned) + plan
-            eng.run()
-            eng.compact_fixed(b["local"].data_ptr(), seg)
-            dist.all_gather_into_tensor(b["all"], b["local"])
-            if rank == 0:                           # the rank whose copy is returned reassembles the whole batch
-                _, d2h = eng.gathered_fetch(b["all"].data_ptr(), seg, world, allres)
-            else:
-                torch.cuda.current_stream().synchronize()
+            # the multi-process public call: pinned host shard in -> the whole batch in rank 0's host arrays
+            sharded.align(MODE_LOCAL, cs, batch, allres)
         for _ in range(max(warm, 3)):
             step_e2e()
         barrier()
@@ -443,9 +408,30 @@ def main():
             e2e_each.append(round((time.perf_counter() - t1) * 1e3, 2))
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) / steps * 1e3
-        h2d = int(eng.stats.h2d_bytes)
-        e2e_note = ("per rank: b2a_batch_stage (pinned H2D) + run + fixed-capacity segment; one NCCL all-gather; rank 0 "
-                    "reassembles all %d pairs in pinned host memory (b2a_gathered_fetch); h2d is per rank, d2h is rank 0's" % total_pairs)
+        h2d = 0
+        for e in sharded.engs:
+            e.fetch(None)
+            h2d += int(e.stats.h2d_bytes)
+        d2h = int(getattr(sharded, "d2h", 0))
+        if rank == 0 and allres is not None:  # the e2e arm's own output, checked like the resident arm's
+            from oracle import oracle as orc2
+            orc2.build()
+            idx = np.arange(0, P, max(1, P // 128))[:128]
+            sub = (batch[0], batch[1][idx], batch[2][idx], batch[3][idx], batch[4][idx])
+            ref, ops, off, _ = orc2.align_batch("local", oracle_scoring(orc2), *sub, threads=min(16, orc2.hardware_threads()))
+            bad = 0
+            for kk, p in enumerate(idx):
+                same = all(int(getattr(allres, f)[int(p)]) == int(ref[f][kk]) for f in ("score", "xstart", "xend", "ystart", "yend"))
+                want = [(int(v) & 7, int(v) >> 3) for v in ops[int(off[kk]):int(off[kk]) + int(ref["n_ops"][kk])]]
+                bad += 0 if (same and allres.ops_of(int(p)) == want) else 1
+            if verify is not None:
+                verify["e2e_pairs_checked"] = int(len(idx))
+                verify["e2e_mismatches"] = bad
+                verify["ok"] = bool(verify["ok"] and bad == 0)
+        sharded.close()
+        e2e_note = ("rust_bio_b200.dist.ShardedAligner.align: per rank three pieces (own engine + stream each: the H2D of piece "
+                    "c+1 under the kernels of piece c) -> fixed-capacity segments -> one NCCL all-gather -> rank 0 decodes all "
+                    "%d pairs into pinned host arrays (b2a_gathered_fetch); h2d is per rank, d2h is rank 0's" % total_pairs)
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = world * cells_rank / (e2e_ms * 1e-3) / 1e9
     tb_bytes = int(eng.stats.traceback_bytes)
@@ -639,7 +625,7 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_each_step": e2e_each,
                     "ms_median_step": float(np.median(e2e_each)),
                     "value_at_median_step": round(world * cells_rank / (float(np.median(e2e_each)) * 1e-3) / 1e9, 2),
-                    "path": e2e_note, **({"packed_input": e2e_packed} if e2e_packed else {})},
+                    "path": e2e_note},
             "gpu_launches": launches_step * steps,
             "kernel_ms": {"pack": round(float(np.mean(packs)), 4), "fill": round(fill_ms, 4),
                           "walk_and_compact": round(float(np.mean(walks)), 4)},

@@ -193,3 +193,105 @@ def align_sharded_compact(batch, run_local: Callable, device="cpu"):
     out = torch.empty(world * seg_bytes, dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(out, local)
     return decode_compact(out.cpu().numpy(), seg_bytes, world)
+
+
+# ---------------------------------------------------------------- one rank of the multi-process form, end to end
+class ShardedAligner:
+    """Host buffers in -> the whole batch's results in host memory on rank 0, one process per GPU (torch.distributed,
+    NCCL).  What `bench.py --gpus N` times as `e2e`.
+
+    Every rank aligns its contiguous share of the pair list: the share is cut into `chunks` pieces, each on its own
+    engine and stream, so the H2D copy of piece c+1 runs under the kernels of piece c; every piece leaves a
+    fixed-capacity result segment (b2a_batch_compact_fixed: no size agreement); ONE all-gather moves all of them,
+    and rank 0 decodes the gathered buffer straight into the caller's host arrays (b2a_gathered_fetch).  The segment
+    capacity is sized on the first call (one MAX all-reduce) and reused; a later batch that does not fit is
+    reported by the decoder (B2A_E_CAPACITY) and re-sized."""
+
+    WEIGHTS = (1, 2, 2)
+
+    def __init__(self, device: int, chunks: int = 3):
+        import torch
+        from .engine import Engine
+        self.torch = torch
+        self.device = device
+        w = list(self.WEIGHTS[:chunks]) + [2] * max(0, chunks - len(self.WEIGHTS))
+        self.weights = w
+        self.engs = [Engine(device) for _ in w]
+        self.streams = [torch.cuda.Stream(device=device) for _ in w]
+        for e, s in zip(self.engs, self.streams):
+            e.set_stream(s.cuda_stream)
+            e.set_pipeline(0)
+        self.events = [torch.cuda.Event() for _ in w]
+        self.cap = 0
+        self.local = self.all = None
+
+    def close(self):
+        for e in self.engs:
+            e.close()
+
+    def _cuts(self, n):
+        tot = float(sum(self.weights))
+        cuts, acc = [0], 0.0
+        for wv in self.weights:
+            acc += wv / tot * n
+            cuts.append(min(n, (int(acc) + 31) // 32 * 32))
+        cuts[-1] = n
+        return cuts
+
+    @staticmethod
+    def _slice(batch, lo, hi):
+        blob, xo, xl, yo, yl = batch
+        if hi <= lo:
+            return (blob[:0], xo[lo:lo], xl[lo:lo], yo[lo:lo], yl[lo:lo])
+        xo_, yo_, xl_, yl_ = xo[lo:hi], yo[lo:hi], xl[lo:hi], yl[lo:hi]
+        bmin = int(min(xo_.min(), yo_.min()))
+        bmax = int(max((xo_ + xl_.astype(np.uint64)).max(), (yo_ + yl_.astype(np.uint64)).max()))
+        return (blob[bmin:bmax], xo_ - np.uint64(bmin), xl_, yo_ - np.uint64(bmin), yl_)
+
+    def align(self, mode: int, cscoring, shard, results=None):
+        """`shard` = this rank's share (dist.shard_batch); `results` = rust_bio_b200.engine.Results for the WHOLE
+        batch on rank 0 (None elsewhere).  Returns the number of pairs decoded on rank 0, else 0."""
+        import torch.distributed as dist
+        torch = self.torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        n = len(shard[2])
+        cuts = self._cuts(n)
+        k = len(self.engs)
+        for attempt in range(2):
+            sizing = self.cap == 0
+            for c, (e, s) in enumerate(zip(self.engs, self.streams)):
+                sub = self._slice(shard, cuts[c], cuts[c + 1])
+                e.stage(mode, cscoring, sub)   # H2D of the piece (returns when the copies have landed) ...
+                e.run()                        # ... its kernels run under the next piece's copies
+            if sizing:
+                need = max(e.compact_bytes() for e in self.engs)
+                t = torch.tensor([need], dtype=torch.int64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                self.cap = (int(int(t.item()) * 1.15) + (1 << 16) - 1) >> 16 << 16
+                self.local = torch.empty(k * self.cap, dtype=torch.uint8, device="cuda")
+                self.all = torch.empty(world * k * self.cap, dtype=torch.uint8, device="cuda")
+            cur = torch.cuda.current_stream()
+            for c, (e, s, ev) in enumerate(zip(self.engs, self.streams, self.events)):
+                e.compact_fixed(self.local.data_ptr() + c * self.cap, self.cap)
+                ev.record(s)
+                cur.wait_event(ev)
+            dist.all_gather_into_tensor(self.all, self.local)
+            got = 0
+            ok = torch.ones(1, dtype=torch.int32, device="cuda")
+            if rank == 0:
+                try:
+                    self.engs[0].set_stream(cur.cuda_stream)
+                    got, self.d2h = self.engs[0].gathered_fetch(self.all.data_ptr(), self.cap, world * k, results)
+                except Exception as ex:  # a segment did not fit the capacity fixed earlier: size again
+                    if "CAPACITY" not in str(ex) or attempt:
+                        raise
+                    ok[0] = 0
+                finally:
+                    self.engs[0].set_stream(self.streams[0].cuda_stream)
+            else:
+                cur.synchronize()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()):
+                return got
+            self.cap = 0  # every rank redoes the batch with a fresh sizing
+        return 0

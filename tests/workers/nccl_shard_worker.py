@@ -67,6 +67,23 @@ def main():
         fields, ops_lists = bdist.decode_compact(host, seg2, world)
         assert ops_lists == ref_ops and np.array_equal(fields["score"], ref["score"])
     eng.close()
+    # (3) the end-to-end form bench.py times at N > 1: ShardedAligner (pieces pipelined per rank, one all-gather,
+    # rank 0 decodes the whole batch); called three times: sizing call, reuse, and a batch that no longer fits the
+    # capacity fixed by the first (the decoder reports it and every rank re-sizes)
+    sh = bdist.ShardedAligner(local, chunks=3)
+    cs = CScoring(-5, -1, MIN_SCORE, MIN_SCORE, MIN_SCORE, MIN_SCORE, 1, -1, 1, None, None, 0)
+    s, _ = orc.make_scoring(-5, -1, 1, -1)
+    for mode_name, mode, batch in (("local", 3, synth.uniform_pairs(synth.BASES["C1"], 0, 6000, 150, 150)),
+                                   ("local", 3, synth.uniform_pairs(synth.BASES["C1"], 6000, 6000, 150, 150)),
+                                   ("global", 1, synth.uniform_pairs(synth.BASES["C1"], 0, 6000, 150, 150))):
+        shard, lo, hi = bdist.shard_batch(batch, world, rank)
+        res = Results(6000, int(Engine.default_ops_capacity(batch))) if rank == 0 else None
+        got = sh.align(mode, cs, shard, res)
+        if rank == 0:
+            assert got == 6000
+            ref, ref_ops = oracle_batch(orc, mode_name, s, batch, threads=8)
+            assert_same(res.as_dict(), [res.ops_of(i) for i in range(6000)], ref, ref_ops, batch, f"ShardedAligner {mode_name}")
+    sh.close()
     dist.barrier()
     if rank == 0:
         print("NCCL_SHARD_OK world=%d" % world, flush=True)

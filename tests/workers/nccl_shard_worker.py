@@ -78,6 +78,8 @@ def main():
                                    ("global", 1, synth.uniform_pairs(synth.BASES["C1"], 0, 6000, 150, 150))):
         shard, lo, hi = bdist.shard_batch(batch, world, rank)
         res = Results(6000, int(Engine.default_ops_capacity(batch))) if rank == 0 else None
+        if rank == 0:
+            print("ShardedAligner", mode_name, "capacity before", sh.cap, flush=True)
         got = sh.align(mode, cs, shard, res)
         if rank == 0:
             assert got == 6000

@@ -222,6 +222,10 @@ class ShardedAligner:
             e.set_stream(s.cuda_stream)
             e.set_pipeline(0)
         self.events = [torch.cuda.Event() for _ in w]
+        # the exchange has its own (non-default) stream: the engine treats stream handle 0 as "use your own stream",
+        # so the decode could otherwise not be ordered after an all-gather issued on the legacy default stream
+        self.xstream = torch.cuda.Stream(device=device)
+        self._pin = {}
         self.cap = 0
         self.local = self.all = None
 
@@ -238,15 +242,24 @@ class ShardedAligner:
         cuts[-1] = n
         return cuts
 
-    @staticmethod
-    def _slice(batch, lo, hi):
+    def _slice(self, c, batch, lo, hi):
+        """Piece c of the shard: a view of the blob's span and offsets rebased into PINNED scratch (a copy from
+        pageable memory first waits for the stream and then blocks the host)."""
         blob, xo, xl, yo, yl = batch
         if hi <= lo:
             return (blob[:0], xo[lo:lo], xl[lo:lo], yo[lo:lo], yl[lo:lo])
         xo_, yo_, xl_, yl_ = xo[lo:hi], yo[lo:hi], xl[lo:hi], yl[lo:hi]
         bmin = int(min(xo_.min(), yo_.min()))
         bmax = int(max((xo_ + xl_.astype(np.uint64)).max(), (yo_ + yl_.astype(np.uint64)).max()))
-        return (blob[bmin:bmax], xo_ - np.uint64(bmin), xl_, yo_ - np.uint64(bmin), yl_)
+        n = hi - lo
+        if c not in self._pin or self._pin[c][0].numel() < n:
+            self._pin[c] = (self.torch.empty(n + n // 8 + 16, dtype=self.torch.int64).pin_memory(),
+                            self.torch.empty(n + n // 8 + 16, dtype=self.torch.int64).pin_memory())
+        px = self._pin[c][0].numpy().view(np.uint64)[:n]
+        py = self._pin[c][1].numpy().view(np.uint64)[:n]
+        np.subtract(xo_, np.uint64(bmin), out=px)
+        np.subtract(yo_, np.uint64(bmin), out=py)
+        return (blob[bmin:bmax], px, xl_, py, yl_)
 
     def align(self, mode: int, cscoring, shard, results=None):
         """`shard` = this rank's share (dist.shard_batch); `results` = rust_bio_b200.engine.Results for the WHOLE
@@ -260,7 +273,7 @@ class ShardedAligner:
         for attempt in range(2):
             sizing = self.cap == 0
             for c, (e, s) in enumerate(zip(self.engs, self.streams)):
-                sub = self._slice(shard, cuts[c], cuts[c + 1])
+                sub = self._slice(c, shard, cuts[c], cuts[c + 1])
                 e.stage(mode, cscoring, sub)   # H2D of the piece (returns when the copies have landed) ...
                 e.run()                        # ... its kernels run under the next piece's copies
             if sizing:
@@ -270,12 +283,13 @@ class ShardedAligner:
                 self.cap = (int(int(t.item()) * 1.15) + (1 << 16) - 1) >> 16 << 16
                 self.local = torch.empty(k * self.cap, dtype=torch.uint8, device="cuda")
                 self.all = torch.empty(world * k * self.cap, dtype=torch.uint8, device="cuda")
-            cur = torch.cuda.current_stream()
+            cur = self.xstream
             for c, (e, s, ev) in enumerate(zip(self.engs, self.streams, self.events)):
                 e.compact_fixed(self.local.data_ptr() + c * self.cap, self.cap)
                 ev.record(s)
                 cur.wait_event(ev)
-            dist.all_gather_into_tensor(self.all, self.local)
+            with torch.cuda.stream(cur):
+                dist.all_gather_into_tensor(self.all, self.local)
             got = 0
             ok = torch.ones(1, dtype=torch.int32, device="cuda")
             if rank == 0:

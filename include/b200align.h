@@ -166,6 +166,12 @@ int32_t b2a_engine_set_traceback_budget(b2a_engine* e, uint64_t bytes);
  * lane R in {8,16,20}: the built pairs are 1x8 1x16 1x20 2x16 2x20 4x16 8x16 8x20 32x8 32x16); 0,0 = automatic. */
 int32_t b2a_engine_set_tuning(b2a_engine* e, int32_t lanes_per_pair, int32_t rows_per_lane);
 
+/* The alphabet the last stage used: the caller's, or the byte values the engine found in the batch when
+ * b2a_scoring.alphabet was NULL (symbols[256], ascending).  A caller that cuts one batch into pieces can hand the
+ * first piece's alphabet to the others (b2a_scoring.alphabet) and spare them the discovery pass and its
+ * synchronisation; a piece holding a byte outside it fails with B2A_E_INVALID and is redone without. */
+int32_t b2a_engine_last_alphabet(const b2a_engine* e, uint8_t* symbols, uint32_t* n_symbols);
+
 /* K2 (row m, last-column fix-ups, traceback walk) runs one lane per pair (1) or one warp per pair (2);
  * 0 = automatic: warp per pair for waves of up to 16,384 pairs.  Results are identical either way. */
 int32_t b2a_engine_set_walk(b2a_engine* e, int32_t mode);

@@ -20,7 +20,7 @@ ERRORS = {-1: "B2A_E_INVALID", -2: "B2A_E_NO_DEVICE", -3: "B2A_E_CUDA", -4: "B2A
 ABI_SYMBOLS = [
     "b2a_engine_create", "b2a_engine_destroy", "b2a_last_error", "b2a_version",
     "b2a_engine_set_stream", "b2a_engine_set_traceback_budget", "b2a_engine_set_tuning",
-    "b2a_engine_set_pipeline", "b2a_engine_set_walk",
+    "b2a_engine_set_pipeline", "b2a_engine_set_walk", "b2a_engine_last_alphabet",
     "b2a_align_batch", "b2a_align_batch_banded", "b2a_align_batch_banded_hinted", "b2a_banded_band_ranges", "b2a_batch_stage", "b2a_batch_run",
     "b2a_batch_fetch", "b2a_batch_records", "b2a_batch_records_into", "b2a_record_stride",
     "b2a_records_decode", "b2a_batch_compact_bytes", "b2a_batch_compact_into", "b2a_compact_decode",
@@ -104,6 +104,7 @@ def load():
     L.b2a_engine_set_tuning.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.b2a_engine_set_pipeline.argtypes = [C.c_void_p, C.c_int32]
     L.b2a_engine_set_walk.argtypes = [C.c_void_p, C.c_int32]
+    L.b2a_engine_last_alphabet.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     L.b2a_align_batch.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.POINTER(CPairs),
                                   C.POINTER(CResults), C.POINTER(CStats)]
     L.b2a_align_batch_banded.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CScoring), C.c_uint32,

@@ -335,6 +335,13 @@ int32_t b2a_engine_set_pipeline(b2a_engine* e, int32_t chunks) {
   return B2A_OK;
 }
 
+int32_t b2a_engine_last_alphabet(const b2a_engine* e, uint8_t* symbols, uint32_t* n_symbols) {
+  if (!e || !symbols || !n_symbols) return B2A_E_INVALID;
+  *n_symbols = (uint32_t)e->last_syms.size();
+  for (size_t k = 0; k < e->last_syms.size() && k < 256; ++k) symbols[k] = e->last_syms[k];
+  return B2A_OK;
+}
+
 int32_t b2a_engine_set_walk(b2a_engine* e, int32_t mode) {
   if (!e) return B2A_E_INVALID;
   if (mode < 0 || mode > 2) return e->fail(B2A_E_INVALID, "walk mode must be 0 (automatic), 1 (lane per pair) or 2 (warp per pair)");

@@ -272,10 +272,28 @@ class ShardedAligner:
         k = len(self.engs)
         for attempt in range(2):
             sizing = self.cap == 0
-            for c, (e, s) in enumerate(zip(self.engs, self.streams)):
-                sub = self._slice(c, shard, cuts[c], cuts[c + 1])
-                e.stage(mode, cscoring, sub)   # H2D of the piece (returns when the copies have landed) ...
-                e.run()                        # ... its kernels run under the next piece's copies
+            for reuse in (True, False):
+                cs_piece, alpha_keep = cscoring, None
+                for c, (e, s) in enumerate(zip(self.engs, self.streams)):
+                    sub = self._slice(c, shard, cuts[c], cuts[c + 1])
+                    e.stage(mode, cs_piece, sub)   # H2D of the piece (returns when the copies have landed) ...
+                    e.run()                        # ... its kernels run under the next piece's copies
+                    if reuse and c == 0 and not cscoring.alphabet and not cscoring.table and cuts[1] > cuts[0]:
+                        # later pieces reuse the alphabet the first one found: their stage then has no discovery
+                        # pass (a kernel + a sync that would wait behind this piece's persistent fill)
+                        import ctypes as _C
+                        from ._lib import CScoring as _CS
+                        alpha_keep = e.last_alphabet()
+                        cs_piece = _CS.from_buffer_copy(bytes(cscoring))
+                        cs_piece.alphabet = alpha_keep.ctypes.data_as(_C.c_void_p)
+                        cs_piece.alphabet_len = len(alpha_keep)
+                try:
+                    for e in self.engs:
+                        e.fetch(None)              # waits for the piece; reports a byte outside the alphabet
+                    break
+                except Exception as ex:            # a later piece held a byte the first did not: discover per piece
+                    if not reuse or "alphabet" not in str(ex):
+                        raise
             if sizing:
                 need = max(e.compact_bytes() for e in self.engs)
                 t = torch.tensor([need], dtype=torch.int64, device="cuda")

@@ -101,6 +101,13 @@ class Engine:
     def set_tuning(self, lanes_per_pair: int, rows_per_lane: int):
         self._check(self._L.b2a_engine_set_tuning(self._h, lanes_per_pair, rows_per_lane))
 
+    def last_alphabet(self) -> np.ndarray:
+        """The alphabet the last stage used (given by the caller or found in the batch), ascending byte values."""
+        buf = np.zeros(256, dtype=np.uint8)
+        n = C.c_uint32()
+        self._check(self._L.b2a_engine_last_alphabet(self._h, buf.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return buf[:n.value].copy()
+
     def set_walk(self, mode: int):
         """K2 shape: 0 automatic, 1 one lane per pair, 2 one warp per pair (b2a_engine_set_walk)."""
         self._check(self._L.b2a_engine_set_walk(self._h, int(mode)))

@@ -85,6 +85,19 @@ def main():
             assert got == 6000
             ref, ref_ops = oracle_batch(orc, mode_name, s, batch, threads=8)
             assert_same(res.as_dict(), [res.ops_of(i) for i in range(6000)], ref, ref_ops, batch, f"ShardedAligner {mode_name}")
+    # a byte that only the last piece of the last rank holds: the pieces that reused the first piece's alphabet
+    # are redone with their own discovery pass
+    batch = list(synth.uniform_pairs(synth.BASES["C1"], 0, 6000, 150, 150))
+    blob = batch[0].copy()
+    blob[int(batch[3][5999]) + 7] = ord("N")
+    batch[0] = blob
+    batch = tuple(batch)
+    shard, lo, hi = bdist.shard_batch(batch, world, rank)
+    res = Results(6000, int(Engine.default_ops_capacity(batch))) if rank == 0 else None
+    got = sh.align(3, cs, shard, res)
+    if rank == 0:
+        ref, ref_ops = oracle_batch(orc, "local", s, batch, threads=8)
+        assert_same(res.as_dict(), [res.ops_of(i) for i in range(6000)], ref, ref_ops, batch, "ShardedAligner, late new symbol")
     sh.close()
     dist.barrier()
     if rank == 0:

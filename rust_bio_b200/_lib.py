@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "csrc", "libb200align.so")
+# B2A_LIB_VARIANT: dev knob for A/B runs of differently built libraries (python -m rust_bio_b200.build with
+# B2A_VARIANT=<name> writes csrc/libb200align_<name>.so)
+_VARIANT = os.environ.get("B2A_LIB_VARIANT", "")
+SO_PATH = os.path.join(HERE, "csrc", "libb200align%s.so" % (("_" + _VARIANT) if _VARIANT else ""))
 
 MIN_SCORE = -858993459
 MODE_CUSTOM, MODE_GLOBAL, MODE_SEMIGLOBAL, MODE_LOCAL = 0, 1, 2, 3

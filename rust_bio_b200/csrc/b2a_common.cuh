@@ -170,6 +170,33 @@ B2A_HD int64_t bnd_index(int32_t G, int32_t j, int32_t pi, int32_t maxn) {
   return G < 32 ? (int64_t)j * 32 + pi : (int64_t)pi * (maxn + 1) + j;
 }
 
+// K1's scaled LUT: alpha real rows of alpha entries, then one poison row (the substitution "score" gap_open for
+// every y symbol, i.e. the entry 4*go + 3 - (4*go + 1) = 2) that the padded rows of a masked strip read
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int lut_entries(int alpha) { return (alpha + 1) * alpha; }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr uint32_t lut_smem_bytes(int alpha) { return ((uint32_t)lut_entries(alpha) * 4u + 127u) & ~127u; }
+constexpr int32_t LUT_POISON = 2;
+
+// Warps per CTA of the K1 fill kernel (a build knob for the 8x20 shape; registers are allocated to a CTA in
+// units of four warps, so 3-warp CTAs do not buy a ninth resident warp at 224 registers).
+#ifndef B2A_W_8_20
+#define B2A_W_8_20 4
+#endif
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int fill_warps_of(int G, int R) { return (G == 8 && R == 20) ? B2A_W_8_20 : 4; }
+// strips whose capture row is dispatched at compile time (see column_step): the shapes that run small batches
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr bool cap_dispatch_of(int G) { return G == 8; }
+
 // Traceback words per lane per 8-column group: rows are grouped by four so the
 // fill stores whole 128-bit vectors.
 #if defined(__CUDACC__)

@@ -89,6 +89,19 @@ struct Coop {
     *ctr = old + v;
     return old;
   }
+  static B2A_HD int32_t all_max32(int32_t v) {  // one REDUX on the device
+#if defined(__CUDA_ARCH__)
+    if (W > 1) return __reduce_max_sync(0xffffffffu, v);
+#elif defined(B2A_HOST_WARP)
+    if (W > 1)
+      return (int32_t)host_warp_exchange(v, [&](const long long* x) {
+        long long t = x[0];
+        for (int l = 1; l < 32; ++l) t = x[l] > t ? x[l] : t;
+        return t;
+      });
+#endif
+    return v;
+  }
   static B2A_HD long long all_max(long long v) {
 #if defined(__CUDA_ARCH__)
     if (W > 1)

@@ -85,6 +85,8 @@ struct b2a_engine {
   std::vector<cudaEvent_t> sub_ev;
   bool overlap_small = true;
   bool overlap_big = false;
+  bool tail_split = true;          // small batches: the fill's thin last round of tasks runs under K2 of the rest
+  uint32_t walk_cta_warps = 4;     // warps (pairs) per CTA of the warp-per-pair K2: 1, 2, 4, 8, 16 or 32
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
   bool is_slot = false;            // this engine is a slot of another engine's chunk pipeline
@@ -205,7 +207,7 @@ void choose_shape(const b2a_engine* e, uint32_t maxm, uint32_t maxn, uint64_t n_
     *R = e->tune_R;
     return;
   }
-  const uint64_t stage1 = (uint64_t)((maxm + 15) / 16 * 16 + 64 + (maxn + 15) / 16 * 16 + 64) * 32 * FILL_WARPS;
+  const uint64_t stage1 = (uint64_t)((maxm + 15) / 16 * 16 + 64 + (maxn + 15) / 16 * 16 + 64) * 32 * fill_warps_of(1, 16);
   if (n_pairs >= 49152 && stage1 <= kMaxStageSmem && maxm <= 2048) {  // measured: 8x20 wins below ~50k reads of 150
     *G = 1;
     *R = 16;
@@ -268,6 +270,11 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   if (const char* env = getenv("B2A_BANDED_LITERAL")) e->banded_fast = atoi(env) == 0;
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
+  if (const char* env = getenv("B2A_TAIL_SPLIT")) e->tail_split = atoi(env) != 0;
+  if (const char* env = getenv("B2A_WALK_CTA_WARPS")) {
+    const int v = atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->walk_cta_warps = (uint32_t)v;
+  }
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return B2A_E_CUDA;
@@ -499,7 +506,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
     for (int k = 0; k < 256; ++k) e->codemap_host[k] = 0xFF;
     for (int a = 0; a < sc.alpha; ++a) e->codemap_host[syms[a]] = (uint8_t)a;
     const size_t aa = (size_t)sc.alpha * sc.alpha;
-    e->lut_host.resize(2 * aa);  // [plain | 4*v+3 for K1's packed domain]
+    e->lut_host.resize(aa + (size_t)lut_entries(sc.alpha));  // [plain | 4*v+3 for K1's packed domain + its poison row]
     if (s->table) maxabs = 0;
     for (int a = 0; a < sc.alpha; ++a)
       for (int b = 0; b < sc.alpha; ++b) {
@@ -511,6 +518,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
     if (maxabs > (1ll << 27)) return e->fail(B2A_E_RANGE, "substitution score magnitude above 2^27");
     // K1's copy: packed domain (4*v + 3 = "diagonal" priority) minus the open bias S carries there
     for (size_t k = 0; k < aa; ++k) e->lut_host[aa + k] = 4 * e->lut_host[k] + 3 - (4 * sc.gap_open + 1);
+    for (size_t k = aa; k < (size_t)lut_entries(sc.alpha); ++k) e->lut_host[aa + k] = LUT_POISON;
   }
   score_bound = 0;
   // i32 range guard: every S/I/D of a real path stays within +-2^27, so MIN_SCORE-based
@@ -579,12 +587,12 @@ int32_t b2a_batch_stage(b2a_engine* e, int32_t mode, const b2a_scoring* s, const
     CK(cudaMemGetInfo(&fr, &tot));
     budget = (uint64_t)((double)fr * 0.6);
   }
-  const uint32_t lut_bytes = sc.alpha ? ((uint32_t)(sc.alpha * sc.alpha * 4 + 127) & ~127u) : 0u;
+  const uint32_t lut_bytes = sc.alpha ? lut_smem_bytes(sc.alpha) : 0u;
   for (int attempt = 0;; ++attempt) {
     e->shape = find_shape(G, R);
     if (!e->shape) return e->fail(B2A_E_INVALID, "no fill kernel for the requested shape");
     build_plan(e->plan, pairs->x_len, pairs->y_len, n, G, R, budget);
-    if (64 + lut_bytes + (uint64_t)FILL_WARPS * e->plan.smem_seq_bytes <= kMaxStageSmem) break;
+    if (64 + lut_bytes + (uint64_t)fill_warps_of(G, R) * e->plan.smem_seq_bytes <= kMaxStageSmem) break;
     // Shapes with several pairs per warp stage 32/G whole (x, y) per warp; long sequences (a read against a
     // 15 kb reference ...) only fit the warp-per-pair shape, which stages one strip of x and one y per warp
     // (n up to ~50,000 symbols: 4 warps x (n + G*R + padding) bytes <= 200 KB).  Forced shapes are not replaced.
@@ -768,12 +776,15 @@ int32_t b2a_batch_run(b2a_engine* e) {
     const uint64_t wave_pairs = (uint64_t)nb * 32;
     const bool warp_walk = e->walk_mode == 2 || (e->walk_mode == 0 && wave_pairs <= kWarpWalkMaxPairs);
     uint32_t per_warp_smem = 0;
+    // warps (pairs of one 32-pair block) per CTA of the warp-per-pair K2: the block's scratch is laid out
+    // [index][pair], so the pairs of a CTA share the sectors they read through L1
+    const uint32_t wcta_warps = e->walk_cta_warps;
     if (warp_walk) {
-      // the pair's x and y are copied into shared memory when four pairs' worth fits a CTA's budget
+      // the pair's x and y are copied into shared memory when the CTA's pairs' worth fits its budget
       const uint32_t per_warp = ((pl.maxm + 3) / 4 + (pl.maxn + 3) / 4) * 4 + 16;
-      per_warp_smem = per_warp * 4 <= 96 * 1024 ? per_warp : 0u;
-      if ((size_t)per_warp_smem * 4 > 48 * 1024)
-        CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per_warp_smem * 4));
+      per_warp_smem = (uint64_t)per_warp * wcta_warps <= 96 * 1024 ? per_warp : 0u;
+      if ((size_t)per_warp_smem * wcta_warps > 48 * 1024)
+        CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp_smem * wcta_warps)));
     }
     wp.seq_smem_per_warp = per_warp_smem;
     // Small batches (a few thousand pairs: neither kernel fills the GPU): the wave is cut into sub-ranges of
@@ -785,6 +796,67 @@ int32_t b2a_batch_run(b2a_engine* e) {
     const bool overlap_big = e->overlap_big && pl.waves.size() == 1 && !warp_walk && pl.G != 32 && nb >= 4096 && !use_tail;
     const bool overlap = overlap_big || (e->overlap_small && pl.waves.size() == 1 && warp_walk && pl.G != 32 && nb >= 64 &&
                                          !use_tail && e->walk_mode != 1);
+    // Tail-aware split (small batches of equal tasks): the persistent fill runs whole rounds of one task per
+    // resident warp; what is left over is a thin last round (10k reads on 8x20: 2,500 tasks on 1,184 warps = two
+    // rounds + 132 tasks that take 0.07 ms with the SMs 7/8 idle).  The pairs of the whole rounds (A) and the
+    // remainder (B) are filled back to back, and K2 of A runs beside the fill of B: B's few CTAs go out on the
+    // high-priority stream first, A's walk takes the rest of the GPU.
+    uint32_t split_b = 0;  // blocks of part A (0: no split)
+    if (e->tail_split && !overlap && pl.waves.size() == 1 && warp_walk && pl.G != 32 && !use_tail && e->walk_mode != 1 &&
+        fp.task_limit == 0) {
+      int resident = 0;
+      CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &resident, 1));
+      const uint32_t slots = (uint32_t)resident, tasks = fill_tasks;
+      if (slots > 0 && tasks > slots) {
+        const uint32_t rounds = tasks / slots, rem = tasks % slots;
+        const uint32_t a_blocks = (uint32_t)((uint64_t)rounds * slots / (uint32_t)pl.G);
+        if (rem > 0 && rounds <= 6 && rem * 4 <= slots * 3 && a_blocks > 0 && a_blocks < nb) split_b = a_blocks;
+      }
+    }
+    if (split_b) {
+      if (!e->tail_stream) {
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        CK(cudaStreamCreateWithPriority(&e->tail_stream, cudaStreamNonBlocking, hi_pri));
+        CK(cudaEventCreateWithFlags(&e->ev_fill, cudaEventDisableTiming));
+      }
+      if (!e->aux_stream) CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+      while (e->sub_ev.size() < 6) {
+        cudaEvent_t v;
+        CK(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+        e->sub_ev.push_back(v);
+      }
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
+      FillParams fa = fp, fb = fp;
+      fa.nblocks = split_b;
+      fb.blocks = fp.blocks + split_b;
+      fb.nblocks = nb - split_b;
+      fb.task_counter = ctl + 8;
+      WalkParams wa = wp, wb = wp;
+      wa.nblocks = split_b;
+      wb.blocks = wp.blocks + split_b;
+      wb.nblocks = nb - split_b;
+      CK(e->shape->launch(e->flags, fa, fa.nblocks * (uint32_t)pl.G, e->num_sms, st, &e->last_grid, 0));
+      CK(cudaEventRecord(e->sub_ev[0], st));  // fill A done
+      // fill B + walk B on the high-priority stream, walk A on the auxiliary one
+      CK(cudaStreamWaitEvent(e->tail_stream, e->sub_ev[0], 0));
+      CK(cudaStreamWaitEvent(e->aux_stream, e->sub_ev[0], 0));
+      CK(e->shape->launch(e->flags, fb, fb.nblocks * (uint32_t)pl.G, e->num_sms, e->tail_stream, nullptr, 0));
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 1], e->tail_stream));  // every fill has finished
+      walk_warp_kernel<<<wa.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, e->aux_stream>>>(wa);
+      CK(cudaGetLastError());
+      walk_warp_kernel<<<wb.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, e->tail_stream>>>(wb);
+      CK(cudaGetLastError());
+      e->launches += 4;
+      CK(cudaEventRecord(e->sub_ev[1], e->aux_stream));
+      CK(cudaEventRecord(e->sub_ev[2], e->tail_stream));
+      CK(cudaStreamWaitEvent(st, e->sub_ev[1], 0));  // everything rejoins the engine's stream
+      CK(cudaStreamWaitEvent(st, e->sub_ev[2], 0));
+      e->last_walk_warp = true;
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 2], st));
+      ++wi;
+      continue;
+    }
     if (overlap) {
       constexpr int kSub = 4;
       if (!e->tail_stream) {
@@ -812,7 +884,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
         f2.nblocks = hi_b - lo_b;
         f2.task_counter = ctl + 8 + sidx;
         f2.task_limit = 1;  // CTAs retire after one task per warp: the walks' CTAs get onto the SMs in between
-        CK(e->shape->launch(e->flags, f2, f2.nblocks * (uint32_t)pl.G, e->num_sms, fs, &e->last_grid));
+        CK(e->shape->launch(e->flags, f2, f2.nblocks * (uint32_t)pl.G, e->num_sms, fs, &e->last_grid, 0));
         ++e->launches;
         CK(cudaEventRecord(e->sub_ev[sidx], fs));
         CK(cudaStreamWaitEvent(e->tail_stream, e->sub_ev[sidx], 0));
@@ -820,7 +892,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
         WalkParams w2 = wp;
         w2.blocks = wp.blocks + lo_b;
         w2.nblocks = hi_b - lo_b;
-        if (warp_walk) walk_warp_kernel<<<w2.nblocks * 8, 128, (size_t)per_warp_smem * 4, e->tail_stream>>>(w2);
+        if (warp_walk) walk_warp_kernel<<<w2.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, e->tail_stream>>>(w2);
         else walk_kernel<<<(w2.nblocks * 32 + 127) / 128, 128, 0, e->tail_stream>>>(w2);
         CK(cudaGetLastError());
         ++e->launches;
@@ -833,7 +905,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
       continue;
     }
     CK(cudaEventRecord(e->wave_ev[3 * wi + 0], st));
-    CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &e->last_grid));
+    CK(e->shape->launch(e->flags, fp, fill_tasks, e->num_sms, st, &e->last_grid, 0));
     ++e->launches;
     CK(cudaEventRecord(e->wave_ev[3 * wi + 1], st));
     if (use_tail) {  // K2 and everything after it on the high-priority stream
@@ -846,7 +918,7 @@ int32_t b2a_batch_run(b2a_engine* e) {
       // pairs share every cache line); one WARP per pair cuts the per-pair latency chain (prefix-maximum passes,
       // prefetched walk) and is what small / medium batches and long sequences need (b2a_walk.cuh).
       if (warp_walk) {
-        walk_warp_kernel<<<nb * 8, 128, (size_t)per_warp_smem * 4, st>>>(wp);  // 32 warps (pairs) per block of the plan, 4 warps per CTA
+        walk_warp_kernel<<<nb * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, st>>>(wp);  // 32 warps (pairs) per block of the plan
       } else {
         const unsigned wgrid = (nb * 32 + 127) / 128;
         walk_kernel<<<wgrid, 128, 0, st>>>(wp);

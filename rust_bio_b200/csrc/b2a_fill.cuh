@@ -185,7 +185,16 @@ B2A_HD void fence_device() {
 // packed arg-max keys (F_PACKTRK): 4096*value + (4095 - index): max() keeps the first index on ties
 constexpr int32_t KEY_NONE = (int32_t)0x80000000;
 
-template <int G, int R, int FLAGS, bool MASKED, bool LAST>
+// MASKED strips (rows beyond m-1 inside the strip):
+//  * with a LUT the padded rows read a poison LUT row (score = gap_open for every y symbol, see lut_entries()):
+//    by induction over the columns S(pad_k, j) <= S(pad_k-1, j) <= ... <= S(m-1, j) and D likewise
+//    (M(pad) = S(above, j-1) + go <= D(above, j) <= S(above, j); I(pad) <= S(above); D(pad, j) from the
+//    smaller S/D of column j-1; column 0 is non-increasing in i), and they sit at higher row indices, so they can
+//    never win the column tracker's first-maximum: no per-row mask is needed there;
+//  * the writer needs (S, I) of row m-1 = the partial lane's row rv-1.  CAPQ >= 0: uniform block, that row is
+//    known to lie in row-quad CAPQ (compile time), so only four rows carry the capture compare; CAPQ == R/4: no
+//    lane of the strip is partial; CAPQ == -1: ragged block, every row compares.
+template <int G, int R, int FLAGS, bool MASKED, bool LAST, int CAPQ>
 B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, const int32_t rowbase,
                         const int32_t rv, int32_t (&Sp)[R], int32_t (&Dp)[R], int32_t (&SnR)[R],
                         int32_t (&LyR)[R], uint32_t (&tbacc)[R], const int32_t (&xc)[R],
@@ -197,6 +206,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
   constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
   constexpr bool RELU = (FLAGS & F_RELU) != 0;
+  constexpr bool TMASK = MASKED && !LUT;  // the column tracker has to skip the padded rows explicitly
   // S travels between cells as "S + open": So_d = S4 + go4d feeds the D chain of the next column and (as
   // the diagonal input) M of the next column, whose LUT/compare scores are pre-biased by -go4d; the I chain
   // of the row below wants go4i = go4d + 1.  One IMAD per consumer instead of two, and the chains
@@ -240,7 +250,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
     tbacc[r] = (uint32_t)(fmad((int32_t)tbacc[r], k16, fmad(fd, k2, fi)) + sP - s4);
     if (TC) {
       if (PK) {
-        if (MASKED) {
+        if (TMASK) {
           if (r < rv) Tl = imax(Tl, fmad(s4, k1024, 4095 - r));
         } else {  // two rows per 3-input max
           const int32_t key = fmad(s4, k1024, 4095 - r);
@@ -249,7 +259,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
         }
       } else {
         const int32_t v = s4 + xs4;
-        if ((!MASKED || r < rv) && v > Tv) {
+        if ((!TMASK || r < rv) && v > Tv) {
           Tv = v;
           Ti = rowbase + 1 + r;
         }
@@ -272,7 +282,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
       c.rows[ROWS_IL * c.rows_pad * 32 + slot] = i4 >> 2;
       c.rows[ROWS_NL * c.rows_pad * 32 + slot] = nib;
     }
-    if (MASKED) {
+    if (MASKED && (CAPQ < 0 || (r >> 2) == CAPQ)) {
       if (r == rv - 1) {
         cap_s = s4;
         cap_i = i4;
@@ -292,7 +302,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
 }
 
 // One strip (rows s*G*R+1 .. (s+1)*G*R) of one lane's pair.
-template <int G, int R, int FLAGS, bool MASKED>
+template <int G, int R, int FLAGS, bool MASKED, int CAPQ>
 B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
@@ -318,6 +328,8 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       const int32_t sym = (int32_t)((xw >> (8 * b)) & 0xffu);
       // LUT mode: byte address of the symbol's LUT row (shared-space on the device)
       xc[w * 4 + b] = LUT ? (int32_t)(c.lut_base + (uint32_t)(sym * c.sc.alpha * 4)) : sym;
+      // padded rows: the poison row that follows the alpha real rows of the LUT
+      if (MASKED && LUT && w * 4 + b >= rv) xc[w * 4 + b] = (int32_t)(c.lut_base + (uint32_t)(c.sc.alpha * c.sc.alpha * 4));
     }
   }
 #pragma unroll
@@ -404,17 +416,17 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
       if (j == n) {
-        column_step<G, R, FLAGS, MASKED, true>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+        column_step<G, R, FLAGS, MASKED, true, CAPQ>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
                                                sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
       } else {
-        column_step<G, R, FLAGS, MASKED, false>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+        column_step<G, R, FLAGS, MASKED, false, CAPQ>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
                                                 sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
       }
       sup_prev = in_s;
       if (writer) {
         int4 o;  // decoded by decode_boundary() in b2a_walk.cuh
-        o.x = MASKED ? cap_s : sup;
-        o.y = MASKED ? cap_i : iup;
+        o.x = (MASKED && rv < R) ? cap_s : sup;  // a full lane's row m-1 is its bottom row
+        o.y = (MASKED && rv < R) ? cap_i : iup;
         o.z = TC ? Tv : t_none;
         o.w = TC ? Ti : m;
         c.bnd[bnd_index(G, j, c.pi, c.maxn)] = o;
@@ -481,9 +493,22 @@ B2A_HD void fill_lane(const LaneCtx<G>& c) {
     // last, partly filled task have m = 0 and simply never become active)
     const bool full = c.uniform && ((s + 1) * (G * R) <= c.maxm - 1);
     if (full) {
-      run_strip<G, R, FLAGS, false>(c, s);
+      run_strip<G, R, FLAGS, false, -1>(c, s);
+    } else if (cap_dispatch_of(G) && c.uniform) {
+      // uniform block: the one partial lane of the strip (if any) has the same valid-row count for every pair
+      const int32_t left = c.maxm - 1 - s * (G * R);  // valid rows from the strip's first row on
+      const int32_t part = (left > 0 && left < G * R) ? left % R : 0;
+      switch (part ? (part - 1) >> 2 : R / 4) {
+        case 0: run_strip<G, R, FLAGS, true, 0>(c, s); break;
+        case 1: run_strip<G, R, FLAGS, true, (1 <= R / 4 ? 1 : -1)>(c, s); break;
+        case 2: run_strip<G, R, FLAGS, true, (2 <= R / 4 ? 2 : -1)>(c, s); break;
+        case 3: run_strip<G, R, FLAGS, true, (3 <= R / 4 ? 3 : -1)>(c, s); break;
+        case 4: run_strip<G, R, FLAGS, true, (4 <= R / 4 ? 4 : -1)>(c, s); break;
+        case 5: run_strip<G, R, FLAGS, true, (5 <= R / 4 ? 5 : -1)>(c, s); break;
+        default: run_strip<G, R, FLAGS, true, -1>(c, s); break;
+      }
     } else {
-      run_strip<G, R, FLAGS, true>(c, s);
+      run_strip<G, R, FLAGS, true, -1>(c, s);
     }
   }
 }
@@ -522,7 +547,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 
-constexpr int FILL_WARPS = 4;
 #ifndef B2A_MINB
 #define B2A_MINB 1  // minimum resident CTAs per SM requested from ptxas (set per shape by build.py)
 #endif
@@ -530,21 +554,22 @@ constexpr int FILL_WARPS = 4;
 // Persistent kernel: every warp pulls warp-tasks (32/G pairs) from a global
 // counter, stages their sequences with two bulk copies and fills them.
 template <int G, int R, int FLAGS>
-__global__ void __launch_bounds__(FILL_WARPS * 32, B2A_MINB) fill_kernel(const FillParams prm) {
+__global__ void __launch_bounds__(fill_warps_of(G, R) * 32, B2A_MINB) fill_kernel(const FillParams prm) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int P = 32 / G;
+  constexpr int FILL_WARPS = fill_warps_of(G, R);
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
   constexpr int TBW = tbw_of(R);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // smem: [FILL_WARPS mbarriers][LUT][per-warp staging]
+  // smem: [FILL_WARPS mbarriers (64 bytes)][LUT][per-warp staging]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   int32_t* lut_s = reinterpret_cast<int32_t*>(smem + 64);
-  const uint32_t lut_bytes = LUT ? ((uint32_t)(prm.sc.alpha * prm.sc.alpha * 4 + 127) & ~127u) : 0u;
+  const uint32_t lut_bytes = LUT ? lut_smem_bytes(prm.sc.alpha) : 0u;
   uint8_t* stage = smem + 64 + lut_bytes + (size_t)warp * prm.smem_seq_bytes;
   uint64_t* bar = &bars[warp];
   if (threadIdx.x < FILL_WARPS) mbar_init(&bars[threadIdx.x], 1);
   if (LUT) {
-    for (int k = threadIdx.x; k < prm.sc.alpha * prm.sc.alpha; k += blockDim.x) lut_s[k] = prm.lut[k];  // 4*score + 3 - (4*gap_open + 1)
+    for (int k = threadIdx.x; k < lut_entries(prm.sc.alpha); k += blockDim.x) lut_s[k] = prm.lut[k];  // 4*score + 3 - (4*gap_open + 1)
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();

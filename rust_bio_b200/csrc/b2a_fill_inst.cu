@@ -11,10 +11,10 @@ namespace {
 
 template <int FLAGS>
 cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t stream,
-               int* grid_out) {
+               int* grid_out, int dry) {
   auto kern = fill_kernel<B2A_G, B2A_R, FLAGS>;
-  const uint32_t lut_bytes =
-      (FLAGS & F_LUT) ? ((uint32_t)(prm.sc.alpha * prm.sc.alpha * 4 + 127) & ~127u) : 0u;
+  constexpr int FILL_WARPS = fill_warps_of(B2A_G, B2A_R);
+  const uint32_t lut_bytes = (FLAGS & F_LUT) ? lut_smem_bytes(prm.sc.alpha) : 0u;
   const size_t smem = 64 + lut_bytes + (size_t)FILL_WARPS * prm.smem_seq_bytes;
   cudaError_t err =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -23,6 +23,10 @@ cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FILL_WARPS * 32, smem);
   if (err != cudaSuccess) return err;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  if (dry) {  // no launch: how many warps of this kernel are resident on the whole GPU
+    if (grid_out) *grid_out = num_sms * per_sm * FILL_WARPS;
+    return cudaSuccess;
+  }
   const uint32_t want = (ntasks + FILL_WARPS - 1) / FILL_WARPS;
   uint32_t grid = (uint32_t)(num_sms * per_sm);
   if (grid > want) grid = want;
@@ -39,10 +43,10 @@ cudaError_t go(const FillParams& prm, uint32_t ntasks, int num_sms, cudaStream_t
 #define B2A_CAT(a, b, c) B2A_CAT2(a, b, c)
 
 cudaError_t B2A_CAT(launch_fill_, B2A_G, B2A_R)(int flags, const FillParams& prm, uint32_t ntasks,
-                                                int num_sms, cudaStream_t stream, int* grid_out) {
+                                                int num_sms, cudaStream_t stream, int* grid_out, int dry) {
   constexpr int ALL = F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
 #define B2A_CASE(F) \
-  case (F): return go<(F)>(prm, ntasks, num_sms, stream, grid_out);
+  case (F): return go<(F)>(prm, ntasks, num_sms, stream, grid_out, dry);
   switch (flags) {
     B2A_CASE(0)
     B2A_CASE(F_TRACK_ROWS)

@@ -689,16 +689,28 @@ B2A_HD int32_t coop_scan_max(int lane, int32_t v) {  // inclusive prefix maximum
   return v;
 }
 
-// first lane (lowest index) holding the maximum of `val` over the lanes with `has`; returns false if none has
+// first lane (lowest index) holding the maximum of `val` over the lanes with `has`; returns false if none has.
+// Callers pass has = (candidate beats the running value): the running value is the same on every lane, so a
+// candidate that does not beat it cannot be the arg-max that does, and most chunks skip the reduction after one
+// ballot.  `packed`: values within +-2^17 and indices <= 4095 (K1's F_PACKTRK condition): one 32-bit REDUX on the
+// key 4096*value + (4095 - index) instead of five 64-bit shuffle rounds.
 template <int W>
-B2A_HD bool coop_argmax_first(int lane, bool has, int32_t val, int32_t idx, int32_t& best_val, int32_t& best_idx) {
+B2A_HD bool coop_argmax_first(int lane, bool has, int32_t val, int32_t idx, int32_t& best_val, int32_t& best_idx,
+                              bool packed = false) {
   using C = Coop<W>;
+  (void)lane;
+  if (C::ballot(has) == 0u) return false;
+  if (packed) {
+    const int32_t key = C::all_max32(has ? val * 4096 + (4095 - idx) : (int32_t)0x80000000);
+    best_val = key >> 12;
+    best_idx = 4095 - (key & 4095);
+    return true;
+  }
   // key: value high, (0x7fffffff - idx) low: the largest key is the largest value at the smallest index
   const long long none = (long long)0x8000000000000000ull;
   long long key = has ? (long long)(((unsigned long long)(long long)val << 32) | (unsigned long long)(uint32_t)(0x7fffffff - idx))
                       : none;
   key = C::all_max(key);
-  if (key == none) return false;
   best_val = (int32_t)(key >> 32);
   best_idx = 0x7fffffff - (int32_t)(uint32_t)(key & 0xffffffffll);
   return true;
@@ -727,23 +739,12 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
   const bool pk = v.packtrk != 0;
 
   // ------------------------------------------------------------------ row m, column 0 (mod.rs:622-671 at i == m)
+  // column 0's tracker over rows 1..m-1 (mod.rs:657-661): col0_S(i) never increases with i (go + ge*(i-1) falls,
+  // the clip terms are constants, and col0_S(1) = max(go, xp) bounds both), so the first maximum is row 1
   int32_t T = MIN_SCORE, Lx0 = 0;
-  {
-    int32_t bv = MIN_SCORE, bi = 0;  // this lane's rows ascend: a strict > keeps its first maximum
-    bool has = false;
-    for (int32_t i = 1 + lane; i < m; i += W) {
-      const int32_t val = col0_S(sc, i) + xs;
-      if (val > bv) {
-        bv = val;
-        bi = i;
-        has = true;
-      }
-    }
-    int32_t gv, gi;
-    if (coop_argmax_first<W>(lane, has, bv, bi, gv, gi)) {  // gv > MIN_SCORE by construction
-      T = gv;
-      Lx0 = m - gi;
-    }
+  if (col0_S(sc, 1) + xs > MIN_SCORE) {  // m >= 2 here
+    T = col0_S(sc, 1) + xs;
+    Lx0 = m - 1;
   }
   int32_t Im0 = col0_I(sc, m);
   const uint32_t ib0 = col0_ibits(sc, m);
@@ -843,9 +844,9 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
     const uint32_t db = (pD + ge > pS + go) ? (uint32_t)TB_DEL : psb;
     // row tracker of row m (mod.rs:799-802): first column with the highest S + ys, if above the running value
     {
-      int32_t gv, gj;
-      if (coop_argmax_first<W>(lane, act, best + ys, j, gv, gj) && gv > Snm) {
-        Snm = gv;
+      int32_t gv, gj;  // arg-max over the real scores (every `best` of row m is one); the clip is added afterwards
+      if (coop_argmax_first<W>(lane, act && best + ys > Snm, best, j, gv, gj, pk)) {
+        Snm = gv + ys;
         Lym = n - gj;
       }
     }
@@ -934,8 +935,8 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
         v.row(ROWS_NL, i) = (int32_t)cell;
       }
       int32_t gv, gi;
-      if (coop_argmax_first<W>(lane, act, S + xs, i, gv, gi) && gv > SmN) {
-        SmN = gv;
+      if (coop_argmax_first<W>(lane, act && S + xs > SmN, S, i, gv, gi, pk)) {  // S(i, n) is a real score
+        SmN = gv + xs;
         LxN = m - gi;
         cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
       }
@@ -982,11 +983,18 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
       c_next = v.row(ROWS_NL, i1);
     }
     // S'(i) - go*i = max(S'(i-1) - go*(i-1) ... ) : inclusive running maximum of S(k) - go*k, seeded by the carry
-    int32_t t = S - go * ic;
-    if (lane == 0) t = imax(t, cSp + go - go * ic);
-    const int32_t Snew = coop_scan_max<W>(lane, t) + go * ic;  // S'(i)
-    int32_t Sprev = C::up(Snew, 1);
+    // The first row a pass raises has an unraised row above it, so S(i-1) + go > S(i) holds there with the values
+    // as loaded (the carry for the chunk's first row): when no lane sees that, the pass changes no S of the chunk
+    // and the scan is skipped.
+    int32_t Sprev = C::up(S, 1);
     if (lane == 0) Sprev = cSp;
+    if (C::ballot(Sprev + go > S) != 0u) {
+      int32_t t = S - go * ic;
+      if (lane == 0) t = imax(t, cSp + go - go * ic);
+      const int32_t Snew = coop_scan_max<W>(lane, t) + go * ic;  // S'(i)
+      Sprev = C::up(Snew, 1);
+      if (lane == 0) Sprev = cSp;
+    }
     const int32_t s_score = Sprev + go;
     // cell (i-1) after its own pass: only its s_bits can have changed, to TB_INS
     const bool raised = s_score > S;
@@ -1010,8 +1018,8 @@ B2A_HD void finish_matrix_coop(const int lane, const PairView& v, EndState& es) 
       v.row(ROWS_NL, i) = (int32_t)cell;
     }
     int32_t gv, gi;
-    if (coop_argmax_first<W>(lane, act && raised, S + xs, i, gv, gi) && gv > SmN) {
-      SmN = gv;
+    if (coop_argmax_first<W>(lane, act && raised && S + xs > SmN, S, i, gv, gi, pk)) {
+      SmN = gv + xs;
       LxN = m - gi;
       cmN = cell_set_s(cmN, TB_XCLIP_SUFFIX);
     }
@@ -1201,7 +1209,7 @@ __device__ __forceinline__ void walk_warp(const WalkParams& prm, const Block& bl
 }
 
 #if defined(B2A_DEFINE_WALK_KERNEL)  // one translation unit (b2a_engine.cu) owns the stand-alone kernel
-__global__ void __launch_bounds__(128, 8) walk_warp_kernel(const WalkParams prm) {
+__global__ void __launch_bounds__(1024, 1) walk_warp_kernel(const WalkParams prm) {  // 64 registers; CTAs of 1..32 warps
   extern __shared__ __align__(16) uint8_t walk_smem[];  // seq_smem_per_warp bytes per warp, or none
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per (block, pair)
   const int lane = threadIdx.x & 31;

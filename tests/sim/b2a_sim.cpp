@@ -384,7 +384,7 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
       for (size_t a = 0; a < syms.size(); ++a) codemap[syms[a]] = (uint8_t)a;
       sc.alpha = (int32_t)syms.size();
       const size_t aa = (size_t)sc.alpha * sc.alpha;
-      lut.resize(2 * aa);
+      lut.resize(aa + (size_t)lut_entries(sc.alpha));
       if (s->table) maxabs = 0;
       for (int a = 0; a < sc.alpha; ++a)
         for (int b = 0; b < sc.alpha; ++b) {
@@ -394,6 +394,7 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
           maxabs = std::max<int64_t>(maxabs, std::llabs((long long)v));
         }
       for (size_t k = 0; k < aa; ++k) lut[aa + k] = 4 * lut[k] + 3 - (4 * sc.gap_open + 1);
+      for (size_t k = aa; k < (size_t)lut_entries(sc.alpha); ++k) lut[aa + k] = LUT_POISON;
     }
   }
   const bool piped = Gsel == 132;
@@ -436,6 +437,7 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
       case 116: fill_dispatch<1, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 416: fill_dispatch<4, 16>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 808: fill_dispatch<8, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
+      case 820: fill_dispatch<8, 20>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 3208: fill_dispatch<32, 8>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       case 13208: fill_dispatch<32, 8, true>(flags, p, blk, sc, lut_scaled, seq, bnd, rows, tb); break;
       default: return -1;

@@ -637,6 +637,37 @@ def test_small_batch_overlap_of_fills_and_walks(oracle, mode, clips, monkeypatch
     eng.close()
 
 
+@pytest.mark.parametrize("cta_warps", [4, 16])
+@pytest.mark.parametrize("kind", ["uniform_10k_local", "ragged_7000_custom"])
+def test_tail_split_of_the_small_batch_fill(oracle, kind, cta_warps, monkeypatch):
+    """Small batches whose equal tasks leave a thin last round on the persistent fill (10k reads on 8x20: two
+    rounds of 1,184 tasks + 132): the whole rounds and the remainder are filled back to back and the warp-per-pair
+    walk of the first part runs beside the fill of the second (b2a_batch_run).  Every pair against the oracle,
+    three runs on the same staged batch; and K2's CTA size (pairs of a block that share L1 sectors)."""
+    from rust_bio_b200 import synth
+    from rust_bio_b200.engine import Engine, Results
+    monkeypatch.setenv("B2A_TAIL_SPLIT", "1")
+    monkeypatch.setenv("B2A_WALK_CTA_WARPS", str(cta_warps))
+    eng = Engine(0)
+    if kind == "uniform_10k_local":
+        n, mode, clips = 10000, "local", (MIN,) * 4
+        batch = synth.uniform_pairs(synth.BASES["C2"], 0, n, 150, 150)
+    else:
+        n, mode, clips = 7000, "custom", (-3, 0, -2, -5)
+        batch = synth.ragged_pairs(777, n, 150, 170, min_len=120)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, *clips)
+    ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)
+    cs, keep = _c_scoring(-5, -1, 1, -1, clips)
+    eng.stage(MODES[mode], cs, batch)
+    for rep in range(3):
+        eng.run()
+        res = Results(n, int(eng.default_ops_capacity(batch)))
+        eng.fetch(res)
+        assert_same(res.as_dict(), [res.ops_of(i) for i in range(n)], ref, ref_ops, batch, f"tail split {kind} rep {rep}")
+    assert eng.stats.kernel_launches >= 5  # K0 + 2 fills + 2 walks (+ compaction): the split form ran
+    eng.close()
+
+
 def _bitenc_batch(seed, n_pairs, max_m, max_n, alphabet, min_len=0):
     """ragged batch + the same sequences as BitEnc storages of RankTransform ranks"""
     from rust_bio_b200 import synth

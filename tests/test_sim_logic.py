@@ -139,6 +139,24 @@ def test_sim_wavefront_shapes_uniform_and_custom(oracle, G, R):
         assert_same(got, ops, ref, ref_ops, batch, f"wavefront custom {G}x{R} no_pack={no_pack}")
 
 
+@pytest.mark.parametrize("G,R", [(8, 8), (8, 20)])
+def test_sim_uniform_masked_strips_every_capture_row(oracle, G, R):
+    """Uniform blocks run their masked (last) strip with the capture row of the boundary hand-off dispatched at
+    compile time by row-quad, and with LUT scoring the padded rows read the poison LUT row instead of masking the
+    column tracker: every number of valid rows in the partial lane (incl. none), LUT and MatchParams scoring,
+    packed and explicit trackers, local / custom clips."""
+    rng = np.random.default_rng(G * R)
+    span = G * R
+    ms = sorted(set(list(range(span - R, span + 3)) + [span + R // 2, 2 * span, 2 * span + 1, 2, 3, R + 1, R + 2]))
+    for k, m in enumerate(ms):
+        batch = synth.uniform_pairs(1000 + m, 0, 5, m, 37 + (k % 5))
+        clips = [int(rng.choice([MIN, 0, -3])) for _ in range(4)] if k % 2 else [0, 0, 0, 0]
+        s, _ = oracle.make_scoring(-5 if k % 3 else 0, -1, 1, -1, None, *clips)
+        ref, ref_ops = oracle_batch(oracle, "custom", s, batch, threads=4)
+        got, ops = sim_util.align_batch(MODES["custom"], s, *batch, R=R, G=G, no_pack=k % 2, no_lut=(k % 4 == 3))
+        assert_same(got, ops, ref, ref_ops, batch, f"uniform masked {G}x{R} m={m}")
+
+
 @pytest.mark.parametrize("mode", ["local", "global", "custom"])
 def test_sim_strip_pipelined_warp_per_pair(oracle, mode):
     """The warp-per-pair shape as the engine schedules it: one emulated warp per (pair, strip) task, the strips of a

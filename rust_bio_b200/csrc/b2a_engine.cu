@@ -86,7 +86,7 @@ struct b2a_engine {
   bool overlap_small = true;
   bool overlap_big = false;
   bool tail_split = true;          // small batches: the fill's thin last round of tasks runs under K2 of the rest
-  uint32_t walk_cta_warps = 4;     // warps (pairs) per CTA of the warp-per-pair K2: 1, 2, 4, 8, 16 or 32
+  uint32_t walk_cta_warps = 0;     // warps (pairs) per CTA of the warp-per-pair K2: 1, 2, 4, 8, 16, 32 or 0 = automatic
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
   bool is_slot = false;            // this engine is a slot of another engine's chunk pipeline
@@ -543,6 +543,10 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
 static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes, cudaStream_t st) {
   const uint64_t n = e->n_pairs;
   if (n) {
+    if (n <= 65536) {  // small batches: one single-CTA launch for the offsets
+      scan_small_kernel<<<1, 1024, 0, st>>>(e->d_nops.as<uint32_t>(), e->d_opsoff.as<uint64_t>(), (uint32_t)n);
+      CK(cudaGetLastError());
+    } else {
     const unsigned g1 = (unsigned)((n + 1 + 255) / 256);
     widen_kernel<<<g1, 256, 0, st>>>(e->d_nops.as<uint32_t>(), e->d_nops64.as<uint64_t>(), n);
     CK(cudaGetLastError());
@@ -552,13 +556,14 @@ static int32_t compact_ops(b2a_engine* e, uint64_t scratch_bytes, cudaStream_t s
     CK(e->d_scan.reserve(tmp + 16));
     CK(cub::DeviceScan::ExclusiveSum(e->d_scan.p, tmp, e->d_nops64.as<uint64_t>(),
                                      e->d_opsoff.as<uint64_t>(), (int64_t)(n + 1), st));
+    }
     // worst case every pair emits m+n+4 ops; size the dense buffer by the scratch size
     CK(e->d_opsdense.reserve(scratch_bytes + 16));
     const unsigned g2 = (unsigned)((n * 32 + 255) / 256);
     gather_ops_kernel<<<g2, 256, 0, st>>>(e->d_opsscratch.as<uint8_t>(), e->d_opssrc.as<uint64_t>(),
                                           e->d_opsoff.as<uint64_t>(), e->d_opsdense.as<uint8_t>(), n);
     CK(cudaGetLastError());
-    e->launches += 4;
+    e->launches += n <= 65536 ? 2 : 4;
   }
   return B2A_OK;
 }
@@ -778,14 +783,17 @@ int32_t b2a_batch_run(b2a_engine* e) {
     uint32_t per_warp_smem = 0;
     // warps (pairs of one 32-pair block) per CTA of the warp-per-pair K2: the block's scratch is laid out
     // [index][pair], so the pairs of a CTA share the sectors they read through L1
-    const uint32_t wcta_warps = e->walk_cta_warps;
+    // (10k reads: 8 warps 0.134 ms, 4 warps 0.159, 16 warps 0.142, 32 warps 0.155 -- profiles/r02_10k_target.txt)
+    uint32_t wcta_warps = e->walk_cta_warps;
     if (warp_walk) {
       // the pair's x and y are copied into shared memory when the CTA's pairs' worth fits its budget
       const uint32_t per_warp = ((pl.maxm + 3) / 4 + (pl.maxn + 3) / 4) * 4 + 16;
+      if (!wcta_warps) wcta_warps = (uint64_t)per_warp * 8 <= 96 * 1024 ? 8u : 4u;
       per_warp_smem = (uint64_t)per_warp * wcta_warps <= 96 * 1024 ? per_warp : 0u;
       if ((size_t)per_warp_smem * wcta_warps > 48 * 1024)
         CK(cudaFuncSetAttribute(walk_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp_smem * wcta_warps)));
     }
+    if (!wcta_warps) wcta_warps = 4;
     wp.seq_smem_per_warp = per_warp_smem;
     // Small batches (a few thousand pairs: neither kernel fills the GPU): the wave is cut into sub-ranges of
     // blocks whose fills alternate between two streams (they overlap: the next fill's CTAs take the SM slots the
@@ -810,7 +818,8 @@ int32_t b2a_batch_run(b2a_engine* e) {
       if (slots > 0 && tasks > slots) {
         const uint32_t rounds = tasks / slots, rem = tasks % slots;
         const uint32_t a_blocks = (uint32_t)((uint64_t)rounds * slots / (uint32_t)pl.G);
-        if (rem > 0 && rounds <= 6 && rem * 4 <= slots * 3 && a_blocks > 0 && a_blocks < nb) split_b = a_blocks;
+        // (measured: 10k reads, a remainder of 0.11 rounds: 0.506 -> 0.464 ms; 7k reads, 0.48 rounds: 0.391 -> 0.411)
+        if (rem > 0 && rounds <= 6 && rem * 4 <= slots && a_blocks > 0 && a_blocks < nb) split_b = a_blocks;
       }
     }
     if (split_b) {

@@ -577,6 +577,7 @@ __global__ void __launch_bounds__(fill_warps_of(G, R) * 32, B2A_MINB) fill_kerne
   const bool strip_tasks = (G == 32) && prm.progress != nullptr;
   const uint32_t ntasks = strip_tasks ? prm.n_strip_tasks : prm.nblocks * G;
   uint32_t parity = 0;
+
   for (uint32_t done = 0; prm.task_limit == 0 || done < prm.task_limit; ++done) {
     uint32_t task = 0;
     if (lane == 0) task = atomicAdd(prm.task_counter, 1u);

@@ -27,9 +27,24 @@ struct PackParams {
 // with P = 32/G pairs per task.  Bytes past the end of a sequence are 0.
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
   __shared__ uint8_t cmap[256];  // symbol -> code, read four times per staged word
+  __shared__ uint64_t s_off[64];  // the block's pairs: where x (0..31) and y (32..63) start in the blob ...
+  __shared__ uint32_t s_len[64];  // ... and how long they are (one dependent chain per sequence, not per word)
   cmap[threadIdx.x] = prm.codemap[threadIdx.x];
-  __syncthreads();
   const Block blk = prm.blocks[blockIdx.x];
+  if (threadIdx.x < 64) {
+    const uint32_t pair = threadIdx.x & 31u;
+    const bool isy = threadIdx.x >= 32;
+    uint64_t off = 0;
+    uint32_t len = 0;
+    if (pair < blk.npairs) {
+      const uint32_t orig = prm.order[blk.first + pair];
+      off = isy ? prm.y_off[orig] : prm.x_off[orig];
+      len = isy ? prm.y_len[orig] : prm.x_len[orig];
+    }
+    s_off[threadIdx.x] = off;
+    s_len[threadIdx.x] = len;
+  }
+  __syncthreads();
   const int G = prm.G, P = 32 / G;
   uint32_t* out = reinterpret_cast<uint32_t*>(prm.seq + blk.seq_off);
   const uint32_t xtot = blk.xwords * 32, ytot = blk.ywords * 32;
@@ -40,10 +55,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams prm) {
     // walk the pair fastest inside a sequence word so that a thread's 4 source bytes are adjacent
     const uint32_t pair = kk / words, w = kk % words;  // pair slot in block, word in sequence
     uint32_t val = 0;
-    if (pair < blk.npairs) {
-      const uint32_t orig = prm.order[blk.first + pair];
-      const uint64_t off = isy ? prm.y_off[orig] : prm.x_off[orig];
-      const uint32_t len = isy ? prm.y_len[orig] : prm.x_len[orig];
+    {
+      const uint64_t off = s_off[pair + (isy ? 32u : 0u)];
+      const uint32_t len = s_len[pair + (isy ? 32u : 0u)];  // 0 for the padding pairs of a last, partly filled block
       const uint32_t pos0 = w * 4;
       if (pos0 < len) {
         // the four source bytes in one load when the sequence starts on a word boundary and the word is whole
@@ -96,6 +110,43 @@ __global__ void gather_ops_kernel(const uint8_t* __restrict__ scratch,
   const uint64_t lo = ops_off[warp], n = ops_off[warp + 1] - lo;
   const uint8_t* src = scratch + ops_src[warp];
   for (uint64_t k = lane; k < n; k += 32) dense[lo + k] = src[k];
+}
+
+// Small batches: exclusive sum of n_ops[0..n) into n+1 u64 offsets by ONE CTA, 1,024 elements per round (coalesced
+// loads, a warp scan, a scan of the 32 warp sums, a running carry): one launch instead of widen + the two passes
+// of a device-wide scan.
+__global__ void __launch_bounds__(1024) scan_small_kernel(const uint32_t* __restrict__ n_ops, uint64_t* __restrict__ off,
+                                                          uint32_t n_pairs) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t round_total;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  uint64_t carry = 0;
+  for (uint32_t base = 0; base < n_pairs; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_pairs ? n_ops[i] : 0u;  // a round's sum stays below 2^32: 1,024 x (m + n + 4) ops
+    uint32_t inc = v;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) warp_sum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t ws = warp_sum[lane];
+      uint32_t wi = ws;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= (uint32_t)d) wi += t;
+      }
+      warp_sum[lane] = wi - ws;  // exclusive
+      if (lane == 31) round_total = wi;
+    }
+    __syncthreads();
+    if (i < n_pairs) off[i] = carry + warp_sum[w] + (inc - v);
+    carry += round_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) off[n_pairs] = carry;
 }
 
 // n_ops (u32) -> u64 with a trailing 0 so one exclusive scan yields n_pairs+1 offsets

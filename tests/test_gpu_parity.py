@@ -638,7 +638,7 @@ def test_small_batch_overlap_of_fills_and_walks(oracle, mode, clips, monkeypatch
 
 
 @pytest.mark.parametrize("cta_warps", [4, 16])
-@pytest.mark.parametrize("kind", ["uniform_10k_local", "ragged_7000_custom"])
+@pytest.mark.parametrize("kind", ["uniform_10k_local", "ragged_5000_custom"])
 def test_tail_split_of_the_small_batch_fill(oracle, kind, cta_warps, monkeypatch):
     """Small batches whose equal tasks leave a thin last round on the persistent fill (10k reads on 8x20: two
     rounds of 1,184 tasks + 132): the whole rounds and the remainder are filled back to back and the warp-per-pair
@@ -653,7 +653,7 @@ def test_tail_split_of_the_small_batch_fill(oracle, kind, cta_warps, monkeypatch
         n, mode, clips = 10000, "local", (MIN,) * 4
         batch = synth.uniform_pairs(synth.BASES["C2"], 0, n, 150, 150)
     else:
-        n, mode, clips = 7000, "custom", (-3, 0, -2, -5)
+        n, mode, clips = 5000, "custom", (-3, 0, -2, -5)  # 1,250 tasks on 1,184 resident warps
         batch = synth.ragged_pairs(777, n, 150, 170, min_len=120)
     s, _ = oracle.make_scoring(-5, -1, 1, -1, None, *clips)
     ref, ref_ops = oracle_batch(oracle, mode, s, batch, threads=8)

@@ -52,6 +52,11 @@ struct BandedParams {
   const uint32_t* hint_path_idx;
   int32_t allowed_mismatches;      // custom_with_expanded_matches: >= 0 expands the matches, -1 = None
   int32_t use_lcskpp_union;        // custom_with_expanded_matches
+  // strip-wavefront fill (b2a_banded_strip.cuh)
+  int32_t strip_ok;        // the batch's scoring suits it (host check): K4 may mark pairs strip-eligible (bit 9)
+  uint32_t* band_cols;     // [n_pairs * 3] out (K4): first / last non-empty band column, strip columns
+  const uint8_t* strip;    // strip areas of the sub-wave (finish pass), or null
+  const uint64_t* strip_off;
   // K3 state
   uint8_t* fill;           // K3 slab arena
   const uint64_t* fill_off;  // per pair byte offset of the K3 slab
@@ -961,6 +966,52 @@ B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n
   return C::ballot(!ok) == 0u;
 }
 
+// Pairs for the strip-wavefront fill (b2a_banded_strip.cuh): the conditions of banded_fast_ok that make every read
+// outside the previous column's band a MIN_SCORE (monotone starts and ends, Band::new sentinels only) -- without
+// its height limit, the rows are not held in a sliding window there -- plus: the band's columns are one run (the
+// strips find their column windows by binary search), and column n is empty (the last column's extra Sn terms,
+// banded.rs:590-596, stay with the literal loops).  out3 = {first, last non-empty column, sum over the band's
+// columns 1..n-1 of the 128-row strips they touch}.
+template <int W>
+B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint32_t* out3) {
+  using C = Coop<W>;
+  if (W != 32 || m < 2 || n < 2 || m >= (1u << 24) || n >= (1u << 24)) return false;
+  bool ok = true;
+  uint32_t c0 = 0xFFFFFFFFu, c1 = 0, cnt = 0, scols = 0;
+  for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
+    const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
+    if (s >= e) {
+      if (!(s == m + 1 && e == 0)) ok = false;
+      continue;
+    }
+    ++cnt;
+    c0 = (uint32_t)j < c0 ? (uint32_t)j : c0;
+    c1 = (uint32_t)j > c1 ? (uint32_t)j : c1;
+    if (j == n) ok = false;
+    if (j >= 1) {
+      const uint64_t ps = rng[2 * (j - 1)], pe = rng[2 * (j - 1) + 1];
+      if (ps < pe && (s < ps || e < pe)) ok = false;
+      const uint64_t lo = umax64(1, s), hi = umin64(e, m);  // interior rows lo .. hi-1
+      if (lo < hi && j < n) scols += (uint32_t)((hi - 2) / 128 - (lo - 1) / 128 + 1);
+    }
+  }
+  for (int d = 16; d; d >>= 1) {
+    // (butterfly by rotation: every lane ends with the totals)
+    const uint32_t oc0 = (uint32_t)C::from((int32_t)c0, (lane + d) % W), oc1 = (uint32_t)C::from((int32_t)c1, (lane + d) % W);
+    const uint32_t ocnt = (uint32_t)C::from((int32_t)cnt, (lane + d) % W), osc = (uint32_t)C::from((int32_t)scols, (lane + d) % W);
+    c0 = oc0 < c0 ? oc0 : c0;
+    c1 = oc1 > c1 ? oc1 : c1;
+    cnt += ocnt;
+    scols += osc;
+  }
+  if (C::ballot(!ok) != 0u) return false;
+  if (cnt == 0 || cnt != c1 - c0 + 1) return false;
+  out3[0] = c0;
+  out3[1] = c1;
+  out3[2] = scols;
+  return true;
+}
+
 B2A_HD int32_t count_trailing_ones(uint32_t v) {  // number of consecutive set bits from bit 0
 #if defined(__CUDA_ARCH__)
   return v == 0xFFFFFFFFu ? 32 : __ffs((int)~v) - 1;
@@ -1437,8 +1488,10 @@ B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t 
 template <int W, class ScoreFn, int FASTR = 0>
 B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n,
                              const DevScoring& sc, ScoreFn score, const uint32_t* rng, uint64_t num_cells,
-                             uint8_t* slab, bool filter_clips, uint8_t* ops_end, BandedOut& out) {
+                             uint8_t* slab, bool filter_clips, uint8_t* ops_end, BandedOut& out,
+                             const uint8_t* strip_area = nullptr, const uint32_t* cols3 = nullptr, bool* redo = nullptr) {
   using C = Coop<W>;
+  constexpr bool STRIP = FASTR < 0;  // the finish pass of the strip-wavefront fill (b2a_banded_strip.cuh)
   out.status = 0;
   out.n_ops = 0;
   for (int q = 0; q < 4; ++q) out.clip[q] = 0;
@@ -1464,7 +1517,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   uint16_t* coln = reinterpret_cast<uint16_t*>(slab + L.coln);
   uint16_t* cells = reinterpret_cast<uint16_t*>(slab + L.cells);
   // init (banded.rs:423-438): only the cells that can ever be non-START are stored
-  {
+  if (!STRIP) {
     uint32_t acc = 0;  // exclusive prefix sum of the column heights
     for (uint64_t b = 0; b <= n; b += W) {
       const uint64_t j = b + (uint64_t)lane;
@@ -1486,10 +1539,12 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       Darr[kk][i] = MIN_SCORE;
     }
   for (uint64_t i = (uint64_t)lane; i <= m; i += W) {
-    Sn[i] = MIN_SCORE;
-    Ly[i] = 0;
+    if (!STRIP || i == 0 || i == m) {  // (the strip fill has written the rows 1..m-1 of these three)
+      Sn[i] = MIN_SCORE;
+      Ly[i] = 0;
+      coln[i] = 0;
+    }
     col0[i] = 0;
-    coln[i] = 0;
   }
   for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
     Lx[j] = 0;
@@ -1504,13 +1559,69 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     if (i == m) return &rowm[j];
     if (j == 0) return &col0[i];
     if (j == n) return &coln[i];
+    if (STRIP) return nullptr;  // interior cells live in the 4-bit traceback, nothing writes them here
     const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
     if (i >= s && i < e) return &cells[colstart[j] + (i - s)];
     return nullptr;
   };
-  auto rd = [&](uint64_t i, uint64_t j) -> uint32_t {
+  // STRIP: the strip fill's per-strip table, boundary row m-1 and 4-bit traceback (KsLayout, b2a_banded_strip.cuh)
+  const uint32_t* ks_tab = nullptr;
+  const int32_t* ks_bnd = nullptr;  // int2 {4*S, 4*I + 2} per column, index j - kc0 + 1
+  const uint32_t* ks_tb = nullptr;
+  int64_t kc0 = 1, kc1 = 0;         // the band's interior columns, clipped to [1, n-1]
+  if (STRIP) {
+    kc0 = cols3[0] > 1u ? (int64_t)cols3[0] : 1;
+    kc1 = (int64_t)cols3[1] < (int64_t)n - 1 ? (int64_t)cols3[1] : (int64_t)n - 1;
+    const uint64_t ns = m >= 2 ? (m - 1 + 127) / 128 : 0;
+    const uint64_t o_tab = 0, o_bnd = al16(ns * 8), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 8);
+    ks_tab = reinterpret_cast<const uint32_t*>(strip_area + o_tab);
+    ks_bnd = reinterpret_cast<const int32_t*>(strip_area + o_bnd);
+    ks_tb = reinterpret_cast<const uint32_t*>(strip_area + o_tb);
+  }
+  // the 4-bit nibble of an interior cell (1 <= i <= m-1, 1 <= j <= n-1) of the band, 16 = outside the band
+  auto ks_nib = [&](uint64_t i, uint64_t j) -> uint32_t {
+    const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
+    if (!(i >= s && i < e)) return 16u;
+    const uint32_t st = (uint32_t)((i - 1) >> 7), rem = (uint32_t)((i - 1) & 127u), l = rem >> 4, r = rem & 15u;
+    const uint32_t ja = ks_tab[2 * st], off = ks_tab[2 * st + 1];
+    const uint32_t t = (uint32_t)j - ja + l;
+    const uint32_t word = ks_tb[((size_t)off + ((size_t)(t >> 3) * 4 + (r >> 2)) * 8 + l) * 4 + (r & 3u)];
+    return (word >> (4u * (7u - (t & 7u)))) & 15u;
+  };
+  auto ks_sbits = [&](uint64_t i, uint64_t j, uint32_t nb) -> uint32_t {
+    switch (nb & 3u) {
+      case NB_DIAG: return x[i - 1] == y[j - 1] ? (uint32_t)TB_MATCH : (uint32_t)TB_SUBST;
+      case NB_INS: return TB_INS;
+      case NB_DEL: return TB_DEL;
+      default:  // one of the two prefix clips: the x clip is tested first and keeps ties (banded.rs:631-642)
+        return xclip_score(sc, (int32_t)j) >= sc.yclip_prefix + sc.gap_open + sc.gap_extend * ((int32_t)i - 1)
+                   ? (uint32_t)TB_XCLIP_PREFIX
+                   : (uint32_t)TB_YCLIP_PREFIX;
+    }
+  };
+  auto sbits_at = [&](uint64_t i, uint64_t j) -> uint32_t {
+    if (STRIP && i >= 1 && i < m && j >= 1 && j < n) {
+      const uint32_t nb = ks_nib(i, j);
+      return nb == 16u ? 0u : ks_sbits(i, j, nb);
+    }
     uint16_t* p = cellp(i, j);
-    return p ? (uint32_t)*p : 0u;
+    return p ? ((uint32_t)*p >> 8) & 15u : 0u;
+  };
+  // one field of a cell (0: i-bits, 1: d-bits, 2: s-bits); in the 4-bit traceback "came from S of the neighbour"
+  // resolves to that neighbour's s-bits (untouched cells read as START)
+  auto rd_part = [&](uint64_t i, uint64_t j, int part) -> uint32_t {
+    if (STRIP && i >= 1 && i < m && j >= 1 && j < n) {
+      const uint32_t nb = ks_nib(i, j);
+      if (nb == 16u) return 0u;
+      if (part == 2) return ks_sbits(i, j, nb);
+      if (part == 0) return (nb & NB_IEXT) ? (uint32_t)TB_INS : sbits_at(i - 1, j);
+      return (nb & NB_DEXT) ? (uint32_t)TB_DEL : sbits_at(i, j - 1);
+    }
+    uint16_t* p = cellp(i, j);
+    return p ? ((uint32_t)*p >> (4 * part)) & 15u : 0u;
+  };
+  auto rd = [&](uint64_t i, uint64_t j) -> uint32_t {
+    return rd_part(i, j, 0) | (rd_part(i, j, 1) << 4) | (rd_part(i, j, 2) << 8);
   };
   auto set_s = [&](uint64_t i, uint64_t j, uint32_t v) {
     uint16_t* p = cellp(i, j);
@@ -1581,6 +1692,119 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   if constexpr (FASTR > 0) {
     banded_columns_fast<W, FASTR>(lane, x, (int32_t)m, y, (int32_t)n, sc, score, rng, colstart, Sarr[0], Sarr[n % 2],
                                   Iarr[n % 2], Sn, Ly, Lx, row0, rowm, col0, coln, cells);
+  } else if constexpr (FASTR < 0) {
+    // ---------------------------------------------------------------------------------------------------------
+    // Finish pass of the strip-wavefront fill: what the column loop (banded.rs:511-681) does outside the interior
+    // cells 1..m-1 x 1..n-1 -- row 0's cells and its Sn/Ly seed, row m's cells (they start from the column tracker,
+    // which is dead here: the x-suffix clip is), and the x-suffix-clip nibble every column leaves in row m.
+    const int32_t mi = (int32_t)m;
+    // row 0 (banded.rs:518-554): starts do not decrease, so row 0 is in the band for a prefix of the band's columns
+    for (int64_t j = kc0 + lane; j <= kc1; j += W) {
+      if (rng[2 * j] == 0 && rng[2 * j + 1] > 0) {
+        const uint32_t db = row0_dbits(sc, (int32_t)j);
+        const uint32_t sb = row0_D(sc, (int32_t)j) > yp ? (uint32_t)TB_DEL : (uint32_t)TB_YCLIP_PREFIX;
+        row0[j] = (uint16_t)((db << 4) | (sb << 8));
+      }
+    }
+    if (lane == 0 && kc0 <= kc1 && rng[2 * kc0] == 0 && rng[2 * kc0 + 1] > 0) {
+      // S(0, j) never increases with j: only the first row-0 column can raise Sn[0] (547-552)
+      const int32_t S0c = imax(row0_D(sc, (int32_t)kc0), yp);
+      if (S0c + ys > Sn[0]) {
+        Sn[0] = S0c + ys;
+        Ly[0] = (uint32_t)(n - (uint64_t)kc0);
+        row0[n] = (uint16_t)((row0[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+      }
+    }
+    // row m is in the band where a column's end is m + 1: ends do not decrease, so that is a suffix of the band's columns
+    int64_t jm0 = kc1 + 1;
+    {
+      int64_t a = kc0, b = kc1 + 1;
+      while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        if (rng[2 * mid + 1] == (uint32_t)(m + 1)) b = mid;
+        else a = mid + 1;
+      }
+      jm0 = a;
+    }
+    // every other column (1..n) leaves the x-suffix-clip nibble in row m (655-661 / 671-674 with row m outside)
+    for (int64_t j = 1 + lane; j <= (int64_t)n; j += W)
+      if (j < jm0 || j > kc1) rowm[j] = (uint16_t)(TB_XCLIP_SUFFIX << 8);
+    C::sync();
+    if (lane == 0) {
+      auto bnd_S = [&](int64_t j) -> int32_t {  // S(m-1, j), MIN_SCORE outside the band
+        if (j == 0) return Sarr[0][m - 1];
+        if (!(rng[2 * j] <= (uint32_t)(m - 1) && rng[2 * j + 1] > (uint32_t)(m - 1))) return MIN_SCORE;
+        const int32_t v = ks_bnd[2 * (j - kc0 + 1)];
+        return v <= -(1 << 29) ? MIN_SCORE : v >> 2;
+      };
+      auto bnd_I = [&](int64_t j) -> int32_t {
+        if (!(rng[2 * j] <= (uint32_t)(m - 1) && rng[2 * j + 1] > (uint32_t)(m - 1))) return MIN_SCORE;
+        const int32_t v = ks_bnd[2 * (j - kc0 + 1) + 1];
+        return v <= -(1 << 29) ? MIN_SCORE : v >> 2;
+      };
+      int32_t Sm_prev = jm0 == 1 ? Sarr[0][m] : MIN_SCORE, Dm_prev = MIN_SCORE;
+      int32_t Snm = Sn[m];
+      for (int64_t j = jm0; j <= kc1; ++j) {
+        const int32_t q = (int32_t)y[j - 1];
+        const int32_t p = (int32_t)x[m - 1];
+        const int32_t xcs = xp + imax(yp, go + ge * ((int32_t)j - 1));
+        const int32_t rS = bnd_S(j), rI = bnd_I(j), rSup = bnd_S(j - 1);
+        const uint32_t rsb = sbits_at(m - 1, (uint64_t)j);
+        uint32_t ib, dbm, sbm;
+        const int32_t m_sc = rSup + score((uint8_t)p, (uint8_t)q);
+        int32_t bi;
+        if (rI + ge > rS + go) {
+          bi = rI + ge;
+          ib = TB_INS;
+        } else {
+          bi = rS + go;
+          ib = rsb;
+        }
+        int32_t bd;
+        if (Dm_prev + ge > Sm_prev + go) {
+          bd = Dm_prev + ge;
+          dbm = TB_DEL;
+        } else {
+          bd = Sm_prev + go;
+          dbm = ((uint32_t)rowm[j - 1] >> 8) & 15u;  // s-bits of (m, j-1) as stored so far
+        }
+        sbm = TB_XCLIP_SUFFIX;
+        int32_t b = MIN_SCORE;  // the column tracker: dead (x-suffix clip), below every real candidate
+        if (m_sc > b) {
+          b = m_sc;
+          sbm = (p == q) ? TB_MATCH : TB_SUBST;
+        }
+        if (bi > b) {
+          b = bi;
+          sbm = TB_INS;
+        }
+        if (bd > b) {
+          b = bd;
+          sbm = TB_DEL;
+        }
+        if (xcs > b) {
+          b = xcs;
+          sbm = TB_XCLIP_PREFIX;
+        }
+        const int32_t ycs = yp + go + ge * (mi - 1);
+        if (ycs > b) {
+          b = ycs;
+          sbm = TB_YCLIP_PREFIX;
+        }
+        if (b + ys > Snm) {  // 655-660 at i == m, then the cell's own put()
+          Snm = b + ys;
+          Sn[m] = Snm;
+          Ly[m] = (uint32_t)(n - (uint64_t)j);
+          rowm[n] = (uint16_t)((rowm[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+        }
+        rowm[j] = (uint16_t)(ib | (dbm << 4) | (sbm << 8));
+        Sm_prev = b;
+        Dm_prev = bd;
+      }
+      Sarr[n % 2][m] = MIN_SCORE;  // column n is empty: S[m] ends the loop reset (556-561) ...
+      rowm[n] = (uint16_t)(TB_XCLIP_SUFFIX << 8);  // ... and its nibble, written last, replaces the eager marks (671-674)
+    }
+    C::sync();
   } else {
   uint32_t known_busy = 0;  // columns from here on already seen not to be of the plain kind
   for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
@@ -2004,6 +2228,10 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
     out.score = S[m];
   }
+  if (STRIP && out.score < -(1 << 27)) {  // not a real score: the sentinel arithmetic does not cover it -- literal kernel
+    *redo = true;
+    return;
+  }
   // walk, banded.rs:767-855 (ops written backwards).  A legitimate walk emits at most m + n + 4 ops; the
   // reference can loop forever on some custom clip settings (an Xclip/Yclip of length 0): that is
   // reported as status 1 instead of hanging.
@@ -2027,7 +2255,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       ++nclip;
     }
   };
-  uint32_t layer = (rd(i, j) >> 8) & 15u;
+  uint32_t layer = rd_part(i, j, 2);
   uint64_t guard = 4 * (m + n) + 64;
   while (layer != TB_START) {
     if (guard-- == 0 || overflow) {
@@ -2037,42 +2265,42 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     uint32_t next;
     if (layer == TB_INS) {
       push(3);
-      next = rd(i, j) & 15u;
+      next = rd_part(i, j, 0);
       if (i == 0) { out.status = 1; break; }
       i -= 1;
     } else if (layer == TB_DEL) {
       push(2);
-      next = (rd(i, j) >> 4) & 15u;
+      next = rd_part(i, j, 1);
       if (j == 0) { out.status = 1; break; }
       j -= 1;
     } else if (layer == TB_MATCH || layer == TB_SUBST) {
       push(layer == TB_MATCH ? 0 : 1);
       if (i == 0 || j == 0) { out.status = 1; break; }
-      next = (rd(i - 1, j - 1) >> 8) & 15u;
+      next = rd_part(i - 1, j - 1, 2);
       i -= 1;
       j -= 1;
     } else if (layer == TB_XCLIP_PREFIX) {
       push_clip(4, (uint32_t)i);
       xstart = (uint32_t)i;
       i = 0;
-      next = (rd(0, j) >> 8) & 15u;
+      next = rd_part(0, j, 2);
     } else if (layer == TB_XCLIP_SUFFIX) {
       push_clip(4, Lx[j]);
       if (Lx[j] > i) { out.status = 1; break; }
       i -= Lx[j];
       xend = (uint32_t)i;
-      next = (rd(i, j) >> 8) & 15u;
+      next = rd_part(i, j, 2);
     } else if (layer == TB_YCLIP_PREFIX) {
       push_clip(5, (uint32_t)j);
       ystart = (uint32_t)j;
       j = 0;
-      next = (rd(i, 0) >> 8) & 15u;
+      next = rd_part(i, 0, 2);
     } else if (layer == TB_YCLIP_SUFFIX) {
       push_clip(5, Ly[i]);
       if (Ly[i] > j) { out.status = 1; break; }
       j -= Ly[i];
       yend = (uint32_t)j;
-      next = (rd(i, j) >> 8) & 15u;
+      next = rd_part(i, j, 2);
     } else {
       out.status = 1;
       break;
@@ -2142,9 +2370,17 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   // pairs whose band suits the register-resident K3 loop are marked (bit 8) while the ranges are still hot
   const bool fast = st == 0 && cells <= BANDED_MAX_CELLS &&
                     banded_fast_ok<32, K3_FAST_ROWS>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n);
+  uint32_t cols3[3] = {0, 0, 0};
+  const bool strip = prm.strip_ok && st == 0 && cells <= BANDED_MAX_CELLS &&
+                     banded_strip_ok<32>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, cols3);
   if (lane != 0) return;
   prm.num_cells[p] = cells;
-  prm.k4_status[p] = st | (fast ? 0x100u : 0u);
+  prm.k4_status[p] = st | (fast ? 0x100u : 0u) | (strip ? 0x200u : 0u);
+  if (prm.band_cols) {
+    prm.band_cols[3 * p] = cols3[0];
+    prm.band_cols[3 * p + 1] = cols3[1];
+    prm.band_cols[3 * p + 2] = cols3[2];
+  }
 }
 
 #ifndef B2A_K3_MINB
@@ -2162,7 +2398,16 @@ __device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32
   BandedOut o;
   const uint32_t k4raw = prm.k4_status[p];
   const uint32_t k4 = k4raw & 0xFFu;
-  if (((k4raw >> 8) & 1u) != (FASTR > 0 ? 1u : 0u)) return;  // the other kernel's pair
+  // bit 8: K4 marked the pair for the register-resident loop, bit 9: for the strip-wavefront fill, bit 10: the strip
+  // path handed it back.  The strip finish takes 9 & !10; of the rest, the register-resident loop takes bit 8.
+  const bool strip_pair = (k4raw & 0x200u) && !(k4raw & 0x400u);
+  if (FASTR < 0) {
+    if (!strip_pair) return;
+  } else {
+    if (strip_pair) return;
+    if (((k4raw >> 8) & 1u) != (FASTR > 0 ? 1u : 0u)) return;  // the other kernel's pair
+  }
+  bool redo = false;
   if (k4 != 0) {
     o = BandedOut{};
     o.status = 1 + k4;
@@ -2186,9 +2431,15 @@ __device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32
     banded_compute_d<32, decltype(score), FASTR>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc,
                                                  score, prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p],
                                                  prm.fill + prm.fill_off[t], prm.filter_clips != 0,
-                                                 prm.ops_scratch + prm.ops_off[p], o);
+                                                 prm.ops_scratch + prm.ops_off[p], o,
+                                                 FASTR < 0 ? prm.strip + prm.strip_off[t] : nullptr,
+                                                 FASTR < 0 ? prm.band_cols + 3 * p : nullptr, &redo);
   }
   if (lane != 0) return;
+  if (FASTR < 0 && (redo || o.status)) {  // outside what the strip path covers: the literal kernel, launched next, takes it
+    prm.k4_status[p] = k4raw | 0x400u;
+    return;
+  }
   if (o.status) {  // no alignment is reported for a pair the reference panics / hangs on (or that hit a capacity)
     o.score = MIN_SCORE;
     o.n_ops = 0;
@@ -2212,6 +2463,9 @@ __global__ void __launch_bounds__(128, B2A_K3_MINB) banded_fill_kernel(const Ban
 }
 __global__ void __launch_bounds__(128, 4) banded_fill_fast_kernel(const BandedParams prm, uint32_t n_wave) {
   banded_fill_body<K3_FAST_ROWS>(prm, n_wave);
+}
+__global__ void __launch_bounds__(128, 8) banded_strip_finish_kernel(const BandedParams prm, uint32_t n_wave) {
+  banded_fill_body<-1>(prm, n_wave);
 }
 
 #endif

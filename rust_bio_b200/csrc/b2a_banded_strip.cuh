@@ -245,9 +245,12 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
     SnR[r] = KEY_NONE;
     tbacc[r] = 0;
   }
+  // the boundary row this strip leaves: its bottom row for the strip below, or row m-1 (the pair's last strip; another
+  // pair of the warp may be in its last strip while this one is not) for the finish pass's row m
+  const bool my_last = LASTSTRIP && have && s == (int32_t)ks_nstrips((uint64_t)m) - 1;
   int32_t cap_row = -1;
-  if (LASTSTRIP && have && m - 1 > rowbase && m - 1 <= rowbase + KS_R) cap_row = m - 2 - rowbase;  // row m-1 is mine
-  const bool writer = have && (LASTSTRIP ? cap_row >= 0 : l == KS_G - 1);
+  if (my_last && m - 1 > rowbase && m - 1 <= rowbase + KS_R) cap_row = m - 2 - rowbase;  // row m-1 is mine
+  const bool writer = have && (my_last ? cap_row >= 0 : l == KS_G - 1);
   // S(i0, ja-1) for the first row's diagonal: row 0 (strip 0) or the boundary row of the strip above
   int32_t sup_prev = NEG4;
   int32_t in_s = NEG4, in_i = NEG4 + 2;
@@ -296,8 +299,8 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
       sup_prev = in_s;
       if (writer) {
         int2 o;
-        o.x = (LASTSTRIP && cap_row != KS_R - 1) ? cap_s : sup;
-        o.y = (LASTSTRIP && cap_row != KS_R - 1) ? cap_i : iup;
+        o.x = (my_last && cap_row != KS_R - 1) ? cap_s : sup;
+        o.y = (my_last && cap_row != KS_R - 1) ? cap_i : iup;
         P.bnd[j - P.c0 + 1] = o;
       }
       in_s = sup;

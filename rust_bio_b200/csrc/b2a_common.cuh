@@ -15,6 +15,7 @@
 #define B2A_HD inline
 // plain-C++ stand-ins for the CUDA vector types (CPU simulation harness only)
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
 struct uint4 { unsigned x, y, z, w; };
 inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #endif

@@ -22,6 +22,7 @@
 #include "b2a_plan.h"
 #include "b2a_walk.cuh"
 #include "b2a_banded.cuh"
+#include "b2a_banded_strip.cuh"
 
 using namespace b2a;
 
@@ -104,6 +105,8 @@ struct b2a_engine {
   int tune_G = 0, tune_R = 0;
   int walk_mode = 0;  // 0 automatic, 1 one lane per pair, 2 one warp per pair
   bool banded_fast = true;  // K3: register-resident column loop for the pairs K4 marks (B2A_BANDED_LITERAL=1: never)
+  bool banded_strip = true;  // K3s: strip-wavefront fill for the pairs K4 marks (B2A_BANDED_STRIP=0: never)
+  uint64_t strip_pairs = 0;  // pairs the strip path finished in the last banded call (the rest ran the K3 loops)
   // packed input (b2a_align_batch_packed): the caller's "blob" is BitEnc storage of this width (0 = bytes); the
   // engine unpacks it on the device and uses its own byte offsets (eff_xoff / eff_yoff) from then on
   uint32_t packed_width = 0;
@@ -127,7 +130,7 @@ struct b2a_engine {
       d_rowm, d_tb, d_opsscratch, d_lut, d_codemap, d_ctl, d_score, d_xs, d_xe, d_ys, d_ye, d_nops,
       d_opssrc, d_clip, d_status, d_nops64, d_opsoff, d_opsdense, d_scan, d_records, d_prog, d_bcells, d_bstatus,
       d_bopsend, d_bslab, d_branges, d_broff, d_bfill, d_bfoff, d_hmoff, d_hmxy, d_hpoff, d_hpidx, d_raw, d_gnops,
-      d_gnops64, d_goff;
+      d_gnops64, d_goff, d_bcols, d_bstrip, d_bsoff, d_belig;
   uint32_t* h_nops = nullptr;  // pinned staging of b2a_gathered_fetch
   uint64_t h_nops_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -268,6 +271,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   //  register-heavy ones: 0.571 ms overlapped against 0.558 ms back to back -- off unless asked for)
   e->overlap_small = false;
   if (const char* env = getenv("B2A_BANDED_LITERAL")) e->banded_fast = atoi(env) == 0;
+  if (const char* env = getenv("B2A_BANDED_STRIP")) e->banded_strip = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
   if (const char* env = getenv("B2A_TAIL_SPLIT")) e->tail_split = atoi(env) != 0;
@@ -314,7 +318,7 @@ int32_t b2a_engine_destroy(b2a_engine* e) {
                     &e->d_nops64, &e->d_opsoff, &e->d_opsdense, &e->d_scan, &e->d_records, &e->d_prog, &e->d_bcells,
                     &e->d_bstatus, &e->d_bopsend, &e->d_bslab, &e->d_branges, &e->d_broff, &e->d_bfill, &e->d_hmoff, &e->d_hmxy,
                     &e->d_hpoff, &e->d_hpidx, &e->d_raw, &e->d_gnops, &e->d_gnops64, &e->d_goff,
-                    &e->d_bfoff};
+                    &e->d_bfoff, &e->d_bcols, &e->d_bstrip, &e->d_bsoff, &e->d_belig};
   for (DevBuf* b : bufs) b->release();
   for (auto& v : e->ev)
     if (v) cudaEventDestroy(v);
@@ -1403,6 +1407,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   CK(e->d_opsscratch.reserve(ops_total + 16));
   CK(e->d_bcells.reserve(n * 8 + 8));
   CK(e->d_bstatus.reserve(n * 4 + 4));
+  CK(e->d_bcols.reserve(n * 12 + 16));
   CK(e->d_bopsend.reserve(n * 8 + 8));
   if (!e->packed_width) {
     CK(up(e->d_xoff, pairs->x_off, n * 8));
@@ -1498,6 +1503,19 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   bp.slab_stride = k4_bytes;
   bp.num_cells = e->d_bcells.as<uint64_t>();
   bp.k4_status = e->d_bstatus.as<uint32_t>();
+  bp.band_cols = e->d_bcols.as<uint32_t>();
+  // The strip-wavefront fill (b2a_banded_strip.cuh) covers: MatchParams scoring, a dead x-suffix clip (no column
+  // tracker), every real score within +-2^26 (its sentinel arithmetic), and row trackers only as packed keys
+  // (y-suffix clip live => y-prefix clip live, so that every band cell's S is real, and scores below 2^17).
+  {
+    const bool xs_dead = e->sc.xclip_suffix <= DEAD_CLIP, ys_dead = e->sc.yclip_suffix <= DEAD_CLIP;
+    const bool yp_live = e->sc.yclip_prefix > DEAD_CLIP;
+    bp.strip_ok = (e->banded_strip && e->banded_fast && !s->table && xs_dead && score_bound < (1ll << 26) &&
+                   (ys_dead || (yp_live && score_bound < (1ll << 17))))
+                      ? 1
+                      : 0;
+  }
+  e->strip_pairs = 0;
   bp.filter_clips = (mode == B2A_MODE_SEMIGLOBAL || mode == B2A_MODE_LOCAL) ? 1 : 0;
   bp.score = e->d_score.as<int32_t>();
   bp.xstart = e->d_xs.as<uint32_t>();
@@ -1515,8 +1533,8 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   e->launches = 0;
   float band_ms = 0.f, fill_ms = 0.f;
   uint64_t total_cells = 0;
-  std::vector<uint64_t> h_cells, roff, foff;
-  std::vector<uint32_t> h_k4;
+  std::vector<uint64_t> h_cells, roff, foff, soff;
+  std::vector<uint32_t> h_k4, h_cols, elig;
   cudaEvent_t ev0 = e->ev[0], ev1 = e->ev[1], ev2 = e->ev[2];
   for (uint64_t lo = 0; lo < n;) {
     const uint32_t nw = (uint32_t)std::min<uint64_t>(wave, n - lo);
@@ -1548,6 +1566,9 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     h_k4.resize(nw);
     CK(cudaMemcpyAsync(h_cells.data(), e->d_bcells.as<uint64_t>() + lo, (size_t)nw * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_k4.data(), e->d_bstatus.as<uint32_t>() + lo, (size_t)nw * 4, cudaMemcpyDeviceToHost, st));
+    h_cols.resize((size_t)nw * 3);
+    if (bp.strip_ok)
+      CK(cudaMemcpyAsync(h_cols.data(), e->d_bcols.as<uint32_t>() + 3 * lo, (size_t)nw * 12, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     {
       float ms = 0.f;
@@ -1558,6 +1579,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     for (uint32_t& v : h_k4) {
       overflowed |= (v & 0xFFu) == 1u;
       if (!e->banded_fast) v &= 0xFFu;
+      if (!bp.strip_ok) v &= ~0x200u;
     }
     if (!e->banded_fast)  // the literal loop for every pair: clear K4's marks on the device as well
       CK(cudaMemcpyAsync(e->d_bstatus.as<uint32_t>() + lo, h_k4.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, st));
@@ -1573,13 +1595,25 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     uint32_t s0 = 0;
     while (s0 < nw) {
       foff.clear();
-      uint64_t fbytes = 0;
+      soff.clear();
+      elig.clear();
+      uint64_t fbytes = 0, sbytes = 0;
       uint32_t s1 = s0;
+      auto strip_need = [&](uint32_t t) -> uint64_t {  // bytes of the pair's strip area (0: not a strip pair)
+        if (!(h_k4[t] & 0x200u)) return 0;
+        const uint64_t mm = pairs->x_len[lo + t], nn = pairs->y_len[lo + t];
+        const uint64_t c0 = std::max<uint64_t>(h_cols[3 * (size_t)t], 1), c1 = std::min<uint64_t>(h_cols[3 * (size_t)t + 1], nn - 1);
+        return ks_layout(mm, c1 >= c0 ? c1 - c0 + 1 : 0, h_cols[3 * (size_t)t + 2]).total;
+      };
       while (s1 < nw) {
         const uint64_t need = k3_slab_bytes(pairs->x_len[lo + s1], pairs->y_len[lo + s1], h_cells[s1]);
-        if (s1 > s0 && fbytes + need > budget / 2) break;
+        const uint64_t sneed = strip_need(s1);
+        if (s1 > s0 && fbytes + sbytes + need + sneed > budget / 2) break;
         foff.push_back(fbytes);
+        soff.push_back(sbytes);
+        if (sneed) elig.push_back(s1 - s0);
         fbytes += need;
+        sbytes += sneed;
         total_cells += h_cells[s1];
         ++s1;
       }
@@ -1593,6 +1627,64 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
       b3.fill = e->d_bfill.as<uint8_t>();
       b3.fill_off = e->d_bfoff.as<uint64_t>();
       CK(cudaEventRecord(ev1, st));
+      if (!elig.empty()) {
+        // K3s: the strip-wavefront fill (four pairs to a warp) and its finish pass (one warp per pair) for the pairs
+        // K4 marked; a pair the path turns out not to cover is handed back (bit 10) to the two loops below
+        CK(e->d_bstrip.reserve(sbytes + 16));
+        CK(e->d_bsoff.reserve((uint64_t)ns * 8 + 8));
+        CK(e->d_belig.reserve(elig.size() * 4 + 16));
+        CK(up(e->d_bsoff, soff.data(), (size_t)ns * 8));
+        CK(up(e->d_belig, elig.data(), elig.size() * 4));
+        StripParams sp{};
+        sp.blob = bp.blob;
+        sp.x_off = bp.x_off;
+        sp.x_len = bp.x_len;
+        sp.y_off = bp.y_off;
+        sp.y_len = bp.y_len;
+        sp.pair_lo = b3.pair_lo;
+        sp.elig = e->d_belig.as<uint32_t>();
+        sp.n_elig = (uint32_t)elig.size();
+        sp.task_counter = ctl + 32;
+        sp.ranges = bp.ranges;
+        sp.ranges_off = b3.ranges_off;
+        sp.fill = b3.fill;
+        sp.fill_off = b3.fill_off;
+        sp.strip = e->d_bstrip.as<uint8_t>();
+        sp.strip_off = e->d_bsoff.as<uint64_t>();
+        sp.num_cells = bp.num_cells;
+        sp.band_cols = bp.band_cols;
+        sp.k4_status = bp.k4_status;
+        sp.sc = e->sc;
+        sp.one = 1;
+        sp.ge4 = 4 * e->sc.gap_extend;
+        const int fl = (e->sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (e->sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) |
+                       (e->sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+        sp.flags = fl;
+        CK(cudaMemsetAsync(sp.task_counter, 0, 4, st));
+        const uint32_t ntasks = (sp.n_elig + 3) / 4;
+        const unsigned sgrid = (unsigned)std::min<uint32_t>((ntasks + KS_WARPS - 1) / KS_WARPS, (uint32_t)e->num_sms * 3u);
+        switch (fl) {
+#define B2A_KS_CASE(F) \
+  case (F): banded_strip_fill_kernel<(F)><<<sgrid, KS_WARPS * 32, 0, st>>>(sp); break;
+          B2A_KS_CASE(0)
+          B2A_KS_CASE(F_TRACK_ROWS)
+          B2A_KS_CASE(F_CLIPX)
+          B2A_KS_CASE(F_CLIPY)
+          B2A_KS_CASE(F_TRACK_ROWS | F_CLIPX)
+          B2A_KS_CASE(F_TRACK_ROWS | F_CLIPY)
+          B2A_KS_CASE(F_CLIPX | F_CLIPY)
+          B2A_KS_CASE(F_TRACK_ROWS | F_CLIPX | F_CLIPY)
+#undef B2A_KS_CASE
+          default: return e->fail(B2A_E_INVALID, "banded strip fill: unexpected flag set");
+        }
+        CK(cudaGetLastError());
+        b3.strip = sp.strip;
+        b3.strip_off = sp.strip_off;
+        banded_strip_finish_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
+        CK(cudaGetLastError());
+        e->launches += 2;
+        e->strip_pairs += elig.size();
+      }
       // one warp per pair; K4 marked the pairs whose band suits the register-resident loop (each kernel skips
       // the other's pairs)
       if (e->banded_fast) {
@@ -1627,8 +1719,9 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     float tail = 0.f;
     cudaEventElapsedTime(&tail, e->ev[4], e->ev[5]);
     stats->walk_ms = tail;
-    stats->fill_lanes_per_pair = 1;
-    stats->fill_rows_per_lane = 0;
+    // the path most pairs took: the strip-wavefront fill (8 lanes x 16 rows) or one warp per pair
+    stats->fill_lanes_per_pair = e->strip_pairs * 2 > n ? (uint32_t)KS_G : 1u;
+    stats->fill_rows_per_lane = e->strip_pairs * 2 > n ? (uint32_t)KS_R : 0u;
   }
   e->ran = false;
   return rc;
@@ -1643,6 +1736,12 @@ int32_t b2a_banded_band_ranges(b2a_engine* e, uint64_t pair, uint32_t* ranges, u
   if (capacity_pairs < cols) return e->fail(B2A_E_CAPACITY, "ranges buffer too small (needs y_len + 1 pairs)");
   CK(cudaMemcpyAsync(ranges, e->d_branges.as<uint8_t>() + e->band_roff[t], cols * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  return B2A_OK;
+}
+
+int32_t b2a_banded_strip_pairs(b2a_engine* e, uint64_t* n_pairs) {
+  if (!e || !n_pairs) return B2A_E_INVALID;
+  *n_pairs = e->strip_pairs;
   return B2A_OK;
 }
 

@@ -226,6 +226,13 @@ class Engine:
         return out
 
     # staged form
+
+    def banded_strip_pairs(self) -> int:
+        """Pairs of the last banded call that ran the strip-wavefront fill (b2a_banded_strip_pairs)."""
+        v = C.c_uint64(0)
+        self._check(self._L.b2a_banded_strip_pairs(self._h, C.byref(v)))
+        return int(v.value)
+
     def stage(self, mode: int, cscoring: CScoring, batch: Batch):
         self._keep = (batch, cscoring)
         cp = self._cpairs(batch)

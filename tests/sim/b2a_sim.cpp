@@ -730,3 +730,162 @@ extern "C" int sim_banded_warp32_one(int mode, const sim_scoring* s, uint32_t k,
   std::memcpy(ops, opsbuf.data() + opsbuf.size() - o.n_ops, o.n_ops);
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// The strip-wavefront banded fill (b2a_banded_strip.cuh) as the GPU runs it: K4 per pair on an emulated warp, then ONE
+// warp-task of up to four pairs (8 emulated lanes each) through ks_run_task, then the finish pass per pair.
+// path[p]: 1 = the strip path produced the result, 0 = not eligible / handed back (no result reported).
+#include "../../rust_bio_b200/csrc/b2a_banded_strip.cuh"
+
+extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k, uint32_t w, const uint8_t* blob,
+                                     const uint64_t* x_off, const uint32_t* x_len, const uint64_t* y_off,
+                                     const uint32_t* y_len, uint32_t n_pairs, uint32_t cap_matches, int garbage,
+                                     int32_t* score, uint32_t* coords /*4 per pair*/, uint32_t* n_ops,
+                                     uint32_t* clip_len, uint32_t* status, uint32_t* path, uint8_t* ops,
+                                     const uint64_t* ops_off) {
+  if (n_pairs > 4) return -2;
+  DevScoring sc{};
+  sc.gap_open = s->gap_open;
+  sc.gap_extend = s->gap_extend;
+  sc.xclip_prefix = s->xclip_prefix;
+  sc.xclip_suffix = s->xclip_suffix;
+  sc.yclip_prefix = s->yclip_prefix;
+  sc.yclip_suffix = s->yclip_suffix;
+  if (mode == 1) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = MIN_SCORE;
+  if (mode == 2) { sc.xclip_prefix = sc.xclip_suffix = MIN_SCORE; sc.yclip_prefix = sc.yclip_suffix = 0; }
+  if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
+  sc.match_score = s->match_score;
+  sc.mismatch_score = s->mismatch_score;
+  if (s->table) return -3;
+  auto run32 = [&](std::function<void(int)> body) { LaneFibers::run(body); };
+  // the host's part of the decision (b2a_engine.cu banded_impl)
+  const bool xs_dead = sc.xclip_suffix <= DEAD_CLIP, ys_dead = sc.yclip_suffix <= DEAD_CLIP, yp_live = sc.yclip_prefix > DEAD_CLIP;
+  const bool batch_ok = xs_dead && (ys_dead || yp_live);
+  std::vector<std::vector<uint32_t>> rngs(n_pairs);
+  std::vector<uint64_t> cells(n_pairs, 0);
+  std::vector<uint32_t> cols(3 * (size_t)n_pairs + 3, 0), k4(n_pairs, 0), elig;
+  std::vector<uint64_t> roff(n_pairs, 0), foff(n_pairs, 0), soff(n_pairs, 0);
+  std::vector<uint32_t> rng_all;
+  std::vector<uint8_t> fill_all, strip_all;
+  for (uint32_t p = 0; p < n_pairs; ++p) {
+    const uint64_t m = x_len[p], n = y_len[p];
+    const uint8_t* x = blob + x_off[p];
+    const uint8_t* y = blob + y_off[p];
+    std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
+    rngs[p].assign(2 * (n + 1), 0xCDCDCDCDu);
+    BandHintsD hint;
+    uint32_t shared_u32[2] = {0, 0};
+    uint32_t st_lane[32];
+    uint64_t c_lane[32];
+    run32([&](int l) {
+      uint64_t c = 0;
+      st_lane[l] = band_create_d<32>(l, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
+                                     rngs[p].data(), &c, shared_u32, hint);
+      c_lane[l] = c;
+    });
+    cells[p] = c_lane[0];
+    path[p] = 0;
+    status[p] = 0;
+    if (st_lane[0] != 0 || !batch_ok || cells[p] > BANDED_MAX_CELLS) continue;
+    bool ok_lane[32];
+    uint32_t c3[32][3];
+    run32([&](int l) { ok_lane[l] = banded_strip_ok<32>(l, rngs[p].data(), m, n, c3[l]); });
+    if (!ok_lane[0]) continue;
+    for (int q = 0; q < 3; ++q) cols[3 * p + q] = c3[0][q];
+    k4[p] = 0x200u;
+  }
+  // arenas as the engine lays them out
+  uint64_t rb = 0, fb = 0, sb = 0;
+  for (uint32_t p = 0; p < n_pairs; ++p) {
+    const uint64_t m = x_len[p], n = y_len[p];
+    roff[p] = rb;
+    rb += ((n + 1) * 8 + 15) & ~15ull;
+    foff[p] = fb;
+    fb += k3_slab_bytes(m, n, cells[p]);
+    soff[p] = sb;
+    if (k4[p]) {
+      const uint64_t c0 = std::max<uint64_t>(cols[3 * p], 1), c1 = std::min<uint64_t>(cols[3 * p + 1], n - 1);
+      sb += ks_layout(m, c1 >= c0 ? c1 - c0 + 1 : 0, cols[3 * p + 2]).total;
+      elig.push_back(p);
+    }
+  }
+  if (elig.empty()) return 0;
+  rng_all.assign(rb / 4 + 4, 0);
+  for (uint32_t p = 0; p < n_pairs; ++p) std::memcpy(rng_all.data() + roff[p] / 4, rngs[p].data(), rngs[p].size() * 4);
+  fill_all.assign(fb + 16, (uint8_t)garbage);
+  strip_all.assign(sb + 16, (uint8_t)garbage);
+  uint32_t counter = 0;
+  StripParams sp{};
+  sp.blob = blob;
+  sp.x_off = x_off;
+  sp.x_len = x_len;
+  sp.y_off = y_off;
+  sp.y_len = y_len;
+  sp.pair_lo = 0;
+  sp.elig = elig.data();
+  sp.n_elig = (uint32_t)elig.size();
+  sp.task_counter = &counter;
+  sp.ranges = rng_all.data();
+  sp.ranges_off = roff.data();
+  sp.fill = fill_all.data();
+  sp.fill_off = foff.data();
+  sp.strip = strip_all.data();
+  sp.strip_off = soff.data();
+  sp.num_cells = cells.data();
+  sp.band_cols = cols.data();
+  sp.k4_status = k4.data();
+  sp.sc = sc;
+  sp.one = 1;
+  sp.ge4 = 4 * sc.gap_extend;
+  const int fl = (sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) |
+                 (sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+  run32([&](int l) {
+    switch (fl) {
+#define SIM_KS_CASE(F) \
+  case (F): ks_run_task<(F)>(sp, 0, l); break;
+      SIM_KS_CASE(0)
+      SIM_KS_CASE(F_TRACK_ROWS)
+      SIM_KS_CASE(F_CLIPX)
+      SIM_KS_CASE(F_CLIPY)
+      SIM_KS_CASE(F_TRACK_ROWS | F_CLIPX)
+      SIM_KS_CASE(F_TRACK_ROWS | F_CLIPY)
+      SIM_KS_CASE(F_CLIPX | F_CLIPY)
+      SIM_KS_CASE(F_TRACK_ROWS | F_CLIPX | F_CLIPY)
+#undef SIM_KS_CASE
+    }
+  });
+  for (uint32_t p : elig) {
+    if (k4[p] & 0x400u) continue;  // the fill handed the pair back
+    const uint64_t m = x_len[p], n = y_len[p];
+    const uint8_t* x = blob + x_off[p];
+    const uint8_t* y = blob + y_off[p];
+    auto scoref = [&](uint8_t a, uint8_t b) -> int32_t { return a == b ? sc.match_score : sc.mismatch_score; };
+    std::vector<uint8_t> opsbuf(m + n + 16, 0);
+    BandedOut o{};
+    bool redo = false;
+    run32([&](int l) {
+      BandedOut mine{};
+      bool r2 = false;
+      banded_compute_d<32, decltype(scoref), -1>(l, x, m, y, n, sc, scoref, rng_all.data() + roff[p] / 4, cells[p],
+                                                 fill_all.data() + foff[p], mode == 2 || mode == 3,
+                                                 opsbuf.data() + opsbuf.size(), mine, strip_all.data() + soff[p],
+                                                 cols.data() + 3 * p, &r2);
+      if (l == 0) {
+        o = mine;
+        redo = r2;
+      }
+    });
+    if (redo || o.status) continue;
+    path[p] = 1;
+    score[p] = o.score;
+    coords[4 * p + 0] = o.xstart;
+    coords[4 * p + 1] = o.xend;
+    coords[4 * p + 2] = o.ystart;
+    coords[4 * p + 3] = o.yend;
+    n_ops[p] = o.n_ops;
+    for (int q = 0; q < 4; ++q) clip_len[4 * p + q] = o.clip[q];
+    std::memcpy(ops + ops_off[p], opsbuf.data() + opsbuf.size() - o.n_ops, o.n_ops);
+  }
+  return 0;
+}

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "sim", "b2a_sim.cpp")
 SO = os.path.join(HERE, "sim", "libb2asim.so")
 DEPS = [SRC] + [os.path.join(ROOT, "rust_bio_b200", "csrc", f)
-                for f in ("b2a_common.cuh", "b2a_coop.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h", "b2a_banded.cuh")]
+                for f in ("b2a_common.cuh", "b2a_coop.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h", "b2a_banded.cuh", "b2a_banded_strip.cuh")]
 
 
 class SimScoring(C.Structure):
@@ -196,3 +196,47 @@ def banded_warp32_one(mode, orc_scoring, k, w, x: bytes, y: bytes, matches=None,
         res.append(out)
     assert res[0] == res[1], "scratch contents leak into the result"
     return None if res[0][0] == "status" else res[0]
+
+
+def banded_strip_task(mode, orc_scoring, k, w, pairs, cap_matches=4096):
+    """Up to four pairs through K4 (W = 32), ONE warp-task of the strip-wavefront fill (b2a_banded_strip.cuh, 8 emulated
+    lanes per pair) and its finish pass.  -> list of (fields, ops) or None per pair (None: the pair is not eligible
+    for the strip path or was handed back); two scratch fills must agree."""
+    from rust_bio_b200.engine import pack_pairs
+    s = SimScoring.from_buffer_copy(bytes(orc_scoring))
+    blob, x_off, x_len, y_off, y_len = pack_pairs(pairs)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    x_off = np.ascontiguousarray(x_off, dtype=np.uint64)
+    y_off = np.ascontiguousarray(y_off, dtype=np.uint64)
+    x_len = np.ascontiguousarray(x_len, dtype=np.uint32)
+    y_len = np.ascontiguousarray(y_len, dtype=np.uint32)
+    n = len(pairs)
+    cap = x_len.astype(np.uint64) + y_len.astype(np.uint64) + np.uint64(8)
+    ops_off = np.concatenate([[0], np.cumsum(cap)]).astype(np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    res = []
+    for garbage in (0x00, 0x7F):
+        ops = np.zeros(int(ops_off[-1]), dtype=np.uint8)
+        score = np.zeros(n, dtype=np.int32)
+        coords = np.zeros(4 * n, dtype=np.uint32)
+        n_ops = np.zeros(n, dtype=np.uint32)
+        clip = np.zeros(4 * n, dtype=np.uint32)
+        status = np.zeros(n, dtype=np.uint32)
+        path = np.zeros(n, dtype=np.uint32)
+        L = lib()
+        L.sim_banded_strip_task.restype = C.c_int
+        rc = L.sim_banded_strip_task(int(mode), C.byref(s), C.c_uint32(k), C.c_uint32(w), p(blob), p(x_off), p(x_len),
+                                     p(y_off), p(y_len), C.c_uint32(n), C.c_uint32(cap_matches), int(garbage), p(score),
+                                     p(coords), p(n_ops), p(clip), p(status), p(path), p(ops), p(ops_off))
+        assert rc == 0, rc
+        out = []
+        for i in range(n):
+            if not path[i]:
+                out.append(None)
+                continue
+            fields = {"score": int(score[i]), "xstart": int(coords[4 * i]), "xend": int(coords[4 * i + 1]),
+                      "ystart": int(coords[4 * i + 2]), "yend": int(coords[4 * i + 3])}
+            out.append((fields, decode_ops(ops[int(ops_off[i]):int(ops_off[i]) + int(n_ops[i])], clip[4 * i:4 * i + 4])))
+        res.append(out)
+    assert res[0] == res[1], "scratch contents leak into the result"
+    return res[0]

@@ -274,6 +274,7 @@ def test_c4_named_generator_2000_pairs_with_ranges_and_rescoring(eng, oracle):
     ref, rops, roff, _, ref_cells = oracle.banded_align_batch("semiglobal", s, 32, 32, *batch, threads=8)
     res = eng.align_batch_banded(MODES["semiglobal"], cs, 32, 32, batch)
     assert int(eng.stats.cells) == ref_cells
+    assert eng.banded_strip_pairs() >= 1900  # config 4's pairs run the strip-wavefront fill (a window at y's end does not)
     for f in ("score", "xstart", "xend", "ystart", "yend"):
         assert np.array_equal(getattr(res, f).astype(np.int64), ref[f].astype(np.int64)), f
     blob, xo, xl, yo, yl = batch
@@ -412,6 +413,59 @@ def test_register_resident_k3_equals_literal_k3_and_oracle(oracle, mode, monkeyp
     finally:
         fast_eng.close()
         lit_eng.close()
+
+
+@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "custom_xy"])
+def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monkeypatch):
+    """K3s (b2a_banded_strip.cuh: the packed cell of K1 on fixed 128-row strips with a band mask, four pairs to a
+    warp, 4-bit traceback, finish pass) against the K3 column loops (B2A_BANDED_STRIP=0) and the oracle: ragged
+    batches (1-5 strips per pair), gap_open > gap_extend cases, y clips with different penalties, both prefix
+    clips live (their shared priority code).  The path must have taken most of the semiglobal pairs."""
+    from rust_bio_b200.engine import Engine
+    rng = np.random.default_rng({"semiglobal": 41, "custom_y": 42, "custom_xy": 43}[mode])
+    strip_eng = Engine(0)
+    monkeypatch.setenv("B2A_BANDED_STRIP", "0")
+    loop_eng = Engine(0)
+    monkeypatch.delenv("B2A_BANDED_STRIP")
+    taken = total = 0
+    try:
+        for trial in range(6):
+            go, ge = int(rng.choice([0, -1, -5, -5])), int(rng.choice([0, -1, -1, -2]))
+            ma, mi = int(rng.choice([1, 2])), int(rng.choice([-1, -3]))
+            if mode == "semiglobal":
+                omode, clips = "semiglobal", (MIN,) * 4
+            elif mode == "custom_y":
+                omode, clips = "custom", (MIN, MIN, int(rng.choice([0, -2, -7])), int(rng.choice([0, -1, -6])))
+            else:
+                omode, clips = "custom", (int(rng.choice([0, -2, -8])), MIN, int(rng.choice([0, -3])), int(rng.choice([0, -4])))
+            k, w = int(rng.choice([4, 6, 9])), int(rng.choice([3, 8, 20, 45]))
+            batch = _mutated_window_batch(1200 + trial, 203, int(rng.integers(60, 600)), int(rng.integers(700, 1500)),
+                                          sub=0.07, indel=0.03)
+            s, _ = oracle.make_scoring(go, ge, ma, mi, None, *clips, has_match_scores=1)
+            ref, rops, roff, _, ref_cells = oracle.banded_align_batch(omode, s, k, w, *batch, threads=8)
+            if np.any(ref["n_ops"] == 0xFFFFFFFF):
+                continue
+            cs = _c_scoring(go, ge, ma, mi, clips)
+            a = strip_eng.align_batch_banded(MODES[omode], cs, k, w, batch)
+            taken += strip_eng.banded_strip_pairs()
+            total += 203
+            b = loop_eng.align_batch_banded(MODES[omode], cs, k, w, batch)
+            assert loop_eng.banded_strip_pairs() == 0
+            assert int(strip_eng.stats.cells) == ref_cells == int(loop_eng.stats.cells)
+            for f in ("score", "xstart", "xend", "ystart", "yend", "ops_off", "clip_len"):
+                assert np.array_equal(getattr(a, f), getattr(b, f)), (mode, trial, f)
+                if f in ref.dtype.names:
+                    assert np.array_equal(getattr(a, f).astype(np.int64), ref[f].astype(np.int64)), (mode, trial, f)
+            tot = int(a.ops_off[-1])
+            assert np.array_equal(a.ops[:tot], b.ops[:tot])
+            for p in range(0, 203, 7):
+                want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+                assert a.ops_of(p) == want, (mode, trial, p)
+        if mode == "semiglobal":
+            assert taken * 2 >= total, (taken, total)
+    finally:
+        strip_eng.close()
+        loop_eng.close()
 
 
 def test_refused_band_keeps_the_called_methods_mode(eng):

@@ -362,3 +362,52 @@ def test_warp32_fast_column_loop_blosum_and_c4_shape(oracle):
         assert L.sim_last_banded_fast() == 1
         ref, ref_ops = oracle.banded_align("semiglobal", s, 32, 32, x, y)
         assert got is not None and got[0] == {f: ref[f] for f in got[0]} and got[1] == ref_ops
+
+
+# ---- the strip-wavefront banded fill (b2a_banded_strip.cuh: K1's packed cell on fixed 128-row strips, band mask, 4-bit
+# traceback) + its finish pass, as ONE emulated warp-task of up to four pairs with different shapes and windows
+
+@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "global_nocoln", "custom_xy"])
+def test_warp32_strip_fill_vs_oracle(oracle, mode):
+    rng = np.random.default_rng({"semiglobal": 21, "custom_y": 22, "global_nocoln": 23, "custom_xy": 24}[mode])
+    n_strip = n_tot = 0
+    for trial in range(24):
+        go, ge = int(rng.choice([0, -1, -5, -5])), int(rng.choice([0, -1, -1, -2]))
+        if mode == "semiglobal":
+            omode, clips = "semiglobal", (MIN, MIN, MIN, MIN)
+        elif mode == "custom_y":     # y clips live with different penalties, x global
+            omode, clips = "custom", (MIN, MIN, int(rng.choice([0, -2, -7])), int(rng.choice([0, -1, -6])))
+        elif mode == "global_nocoln":  # y prefix dead, y suffix dead, x prefix live: sentinel-derived band cells
+            omode, clips = "custom", (int(rng.choice([0, -3])), MIN, MIN, MIN)
+        else:                          # both prefix clips live (the shared priority code), y suffix live
+            omode, clips = "custom", (int(rng.choice([0, -2, -8])), MIN, int(rng.choice([0, -3])), int(rng.choice([0, -4])))
+        s, _ = oracle.make_scoring(go, ge, int(rng.choice([1, 2])), int(rng.choice([-1, -3])), None, *clips,
+                                   has_match_scores=int(trial % 2))
+        k, w = int(rng.choice([4, 6, 9])), int(rng.choice([2, 5, 11, 20, 45]))
+        pairs = []
+        for q in range(int(rng.integers(1, 5))):
+            xl = int(rng.integers(12, 420))      # one to four strips of 128 rows, ragged inside the task
+            pairs.append(_window_pair(rng, xl, xl + int(rng.integers(30, 500)), nsub=int(rng.integers(0, 9))))
+        got = sim_util.banded_strip_task(MODES[omode], s, k, w, pairs)
+        for (x, y), g in zip(pairs, got):
+            n_tot += 1
+            if g is None:
+                continue
+            n_strip += 1
+            ref, ref_ops = oracle.banded_align(omode, s, k, w, x, y)
+            assert g[0] == {f: ref[f] for f in g[0]} and g[1] == ref_ops, (mode, trial, len(x), len(y), k, w)
+    # the path must actually be exercised (non-zero clip penalties pull the band into the corner (m, n): column n is
+    # then in the band and the pair stays with the K3 loops)
+    assert n_strip >= {"semiglobal": n_tot // 3, "custom_y": 8, "custom_xy": 4, "global_nocoln": 0}[mode], (n_strip, n_tot)
+
+
+def test_warp32_strip_fill_c4_shape(oracle):
+    batch = synth.mutated_window_pairs(synth.BASES["C4"], 0, 4, 500, 10000)
+    blob, xo, xl, yo, yl = batch
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, has_match_scores=1)
+    pairs = [(bytes(blob[int(xo[p]):int(xo[p]) + 500]), bytes(blob[int(yo[p]):int(yo[p]) + 10000])) for p in range(4)]
+    got = sim_util.banded_strip_task(MODES["semiglobal"], s, 32, 32, pairs)
+    for (x, y), g in zip(pairs, got):
+        assert g is not None, "BASELINE config 4's pairs are strip-eligible"
+        ref, ref_ops = oracle.banded_align("semiglobal", s, 32, 32, x, y)
+        assert g[0] == {f: ref[f] for f in g[0]} and g[1] == ref_ops

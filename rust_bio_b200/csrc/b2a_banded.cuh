@@ -54,6 +54,8 @@ struct BandedParams {
   int32_t use_lcskpp_union;        // custom_with_expanded_matches
   // strip-wavefront fill (b2a_banded_strip.cuh)
   int32_t strip_ok;        // the batch's scoring suits it (host check): K4 may mark pairs strip-eligible (bit 9)
+  int32_t redo_pass;       // K3 column-loop kernels: 0 = the pairs K4 did not mark for the strip path, 1 = the pairs the
+                           // strip path handed back (bit 10)
   uint32_t* band_cols;     // [n_pairs * 3] out (K4): first / last non-empty band column, strip columns
   const uint8_t* strip;    // strip areas of the sub-wave (finish pass), or null
   const uint64_t* strip_off;
@@ -1485,7 +1487,10 @@ B2A_HD void banded_columns_fast(const int lane, const uint8_t* x, const int32_t 
 // Row m of a column, row 0, column 0, the end-of-matrix passes and the walk are sequential work of lane 0.
 // FASTR > 0 selects the register-resident column loop (FASTR rows per lane, see below); the caller must have
 // checked banded_fast_ok<W, FASTR> for the pair.  FASTR == 0 is the literal loop.
-template <int W, class ScoreFn, int FASTR = 0>
+// PHASE: 0 = the whole alignment; 1 = everything up to the final score (left in S[n % 2][m]); 2 = the walk only, on
+// the state phase 1 left in the slab (the strip path walks one pair per LANE in a kernel of its own: the walk is
+// sequential per pair, and a warp whose other 31 lanes wait for lane 0 issues 32 times the instructions).
+template <int W, class ScoreFn, int FASTR = 0, int PHASE = 0>
 B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n,
                              const DevScoring& sc, ScoreFn score, const uint32_t* rng, uint64_t num_cells,
                              uint8_t* slab, bool filter_clips, uint8_t* ops_end, BandedOut& out,
@@ -1516,6 +1521,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   uint16_t* col0 = reinterpret_cast<uint16_t*>(slab + L.col0);
   uint16_t* coln = reinterpret_cast<uint16_t*>(slab + L.coln);
   uint16_t* cells = reinterpret_cast<uint16_t*>(slab + L.cells);
+  if constexpr (PHASE != 2) {
   // init (banded.rs:423-438): only the cells that can ever be non-START are stored
   if (!STRIP) {
     uint32_t acc = 0;  // exclusive prefix sum of the column heights
@@ -1552,6 +1558,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     rowm[j] = 0;
   }
   C::sync();
+  }
   // traceback cell access: pointer for writes (nullptr = a cell the reference never writes there),
   // value for reads (untouched cells read as 0 = START in every nibble)
   auto cellp = [&](uint64_t i, uint64_t j) -> uint16_t* {
@@ -1638,6 +1645,8 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
   const int32_t xp = sc.xclip_prefix, xs = sc.xclip_suffix, yp = sc.yclip_prefix, ys = sc.yclip_suffix;
   const int32_t gs = imax(ge, go);  // slope of the I chain (the banded aligner opens a gap at go alone)
+  int32_t* const Sfin = Sarr[n % 2];
+  if constexpr (PHASE != 2) {
   if (lane == 0) {  // j = 0, banded.rs:440-509
     int32_t* S = Sarr[0];
     int32_t* I = Iarr[0];
@@ -2147,23 +2156,51 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     C::sync();
   }
   }  // literal column loop
-  int32_t* const Sfin = Sarr[n % 2];
-  if (lane == 0) {
+  {
+    // banded.rs:684-701.  Rows 0..m-1 are independent except for the running x-suffix-clip tracker S[m], which ends
+    // as the first row (lowest index) holding the highest S[i] + xs, if that beats the value the loop started from;
+    // row m comes last and sees the tracker's final value.
     int32_t* S = Sfin;
-    int32_t* I = Iarr[n % 2];
     const uint64_t bs = rng[2 * n], be = rng[2 * n + 1];
-    for (uint64_t i = 0; i <= m; ++i) {  // banded.rs:684-701
-      if (i != m && (i < bs || i > be)) S[i] = MIN_SCORE;
+    int32_t bv = MIN_SCORE;
+    uint32_t bi = 0;
+    bool has = false;
+    const int32_t Sm0 = S[m];
+    C::sync();
+    for (uint64_t i = (uint64_t)lane; i < m; i += W) {
+      if (i < bs || i > be) S[i] = MIN_SCORE;
       if (Sn[i] > S[i]) {
         S[i] = Sn[i];
         set_s(i, n, TB_YCLIP_SUFFIX);
       }
-      if (S[i] + xs > S[m]) {
-        S[m] = S[i] + xs;
-        Lx[n] = (uint32_t)(m - i);
-        set_s(m, n, TB_XCLIP_SUFFIX);
+      const int32_t v = S[i] + xs;
+      if (v > Sm0 && (!has || v > bv)) {  // this lane's rows ascend: a strict > keeps its first maximum
+        bv = v;
+        bi = (uint32_t)i;
+        has = true;
       }
     }
+    long long key = has ? (long long)((unsigned long long)(long long)bv << 32) + (long long)(0xFFFFFFFFu - bi)
+                        : (long long)0x8000000000000000ull;
+    key = C::all_max(key);
+    C::sync();
+    if (lane == 0) {
+      if (key != (long long)0x8000000000000000ull) {
+        S[m] = (int32_t)(key >> 32);
+        Lx[n] = (uint32_t)(m - (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFll)));
+        set_s(m, n, TB_XCLIP_SUFFIX);
+      }
+      if (Sn[m] > S[m]) {  // i == m (S[m] + xs > S[m] cannot hold: xs <= 0)
+        S[m] = Sn[m];
+        set_s(m, n, TB_YCLIP_SUFFIX);
+      }
+    }
+    C::sync();
+  }
+  if (lane == 0) {
+    int32_t* S = Sfin;
+    int32_t* I = Iarr[n % 2];
+    const uint64_t bs = rng[2 * n], be = rng[2 * n + 1];
     for (uint64_t i = umax64(1, bs); i < be; ++i) {  // banded.rs:705-723
       const int32_t s_score = S[i - 1] + go;
       if (s_score > I[i]) {
@@ -2193,8 +2230,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     set_s(i, 0, c_score > xp ? TB_INS : TB_XCLIP_PREFIX);
   }
   C::sync();
-  if (lane != 0) return;
-  {
+  if (lane == 0) {
     int32_t* S = Sfin;
     if (n >= 1) {  // banded.rs:725-744, j = n
       const uint64_t j = n;
@@ -2228,10 +2264,15 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
     out.score = S[m];
   }
-  if (STRIP && out.score < -(1 << 27)) {  // not a real score: the sentinel arithmetic does not cover it -- literal kernel
+  } else {
+    out.score = Sfin[m];
+  }
+  if (lane != 0) return;
+  if (STRIP && PHASE != 2 && out.score < -(1 << 27)) {  // not a real score: the sentinel arithmetic does not cover it -- literal kernel
     *redo = true;
     return;
   }
+  if (PHASE == 1) return;
   // walk, banded.rs:767-855 (ops written backwards).  A legitimate walk emits at most m + n + 4 ops; the
   // reference can loop forever on some custom clip settings (an Xclip/Yclip of length 0): that is
   // reported as status 1 instead of hanging.
@@ -2388,10 +2429,11 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
 #endif
 // K3: one warp per pair.  FASTR == 0: the literal column loop, for every pair K4 did not mark; FASTR > 0: the
 // register-resident loop, for the marked ones (each kernel skips the other's pairs).
-template <int FASTR>
+template <int FASTR, int PHASE = 0, int W = 32>
 __device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32_t n_wave) {
-  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = (int)(threadIdx.x & 31u);
+  // W = 32: one warp per pair; W = 1 (the strip path's walk): one thread per pair
+  const uint32_t t = W == 32 ? (blockIdx.x * blockDim.x + threadIdx.x) >> 5 : blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = W == 32 ? (int)(threadIdx.x & 31u) : 0;
   if (t >= n_wave) return;
   const uint64_t p = (uint64_t)prm.pair_lo + t;
   const uint64_t m = prm.x_len[p], n = prm.y_len[p];
@@ -2399,12 +2441,13 @@ __device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32
   const uint32_t k4raw = prm.k4_status[p];
   const uint32_t k4 = k4raw & 0xFFu;
   // bit 8: K4 marked the pair for the register-resident loop, bit 9: for the strip-wavefront fill, bit 10: the strip
-  // path handed it back.  The strip finish takes 9 & !10; of the rest, the register-resident loop takes bit 8.
+  // path handed it back.  The strip kernels take 9 & !10; the column-loop kernels take the unmarked pairs (beside the
+  // strip kernels, on a stream of their own) or, in a later pass, the pairs handed back.
   const bool strip_pair = (k4raw & 0x200u) && !(k4raw & 0x400u);
   if (FASTR < 0) {
     if (!strip_pair) return;
   } else {
-    if (strip_pair) return;
+    if (prm.redo_pass ? (k4raw & 0x600u) != 0x600u : (k4raw & 0x200u) != 0u) return;
     if (((k4raw >> 8) & 1u) != (FASTR > 0 ? 1u : 0u)) return;  // the other kernel's pair
   }
   bool redo = false;
@@ -2428,18 +2471,19 @@ __device__ __forceinline__ void banded_fill_body(const BandedParams& prm, uint32
       }
       return a == b ? sc.match_score : sc.mismatch_score;
     };
-    banded_compute_d<32, decltype(score), FASTR>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.sc,
-                                                 score, prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p],
-                                                 prm.fill + prm.fill_off[t], prm.filter_clips != 0,
-                                                 prm.ops_scratch + prm.ops_off[p], o,
-                                                 FASTR < 0 ? prm.strip + prm.strip_off[t] : nullptr,
-                                                 FASTR < 0 ? prm.band_cols + 3 * p : nullptr, &redo);
+    banded_compute_d<W, decltype(score), FASTR, PHASE>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n,
+                                                       prm.sc, score, prm.ranges + prm.ranges_off[t] / 4, prm.num_cells[p],
+                                                       prm.fill + prm.fill_off[t], prm.filter_clips != 0,
+                                                       prm.ops_scratch + prm.ops_off[p], o,
+                                                       FASTR < 0 ? prm.strip + prm.strip_off[t] : nullptr,
+                                                       FASTR < 0 ? prm.band_cols + 3 * p : nullptr, &redo);
   }
   if (lane != 0) return;
-  if (FASTR < 0 && (redo || o.status)) {  // outside what the strip path covers: the literal kernel, launched next, takes it
+  if (FASTR < 0 && (redo || o.status)) {  // outside what the strip path covers: the column-loop kernels' later pass takes it
     prm.k4_status[p] = k4raw | 0x400u;
     return;
   }
+  if (PHASE == 1) return;  // the walk (its own kernel) reports the pair
   if (o.status) {  // no alignment is reported for a pair the reference panics / hangs on (or that hit a capacity)
     o.score = MIN_SCORE;
     o.n_ops = 0;
@@ -2465,7 +2509,10 @@ __global__ void __launch_bounds__(128, 4) banded_fill_fast_kernel(const BandedPa
   banded_fill_body<K3_FAST_ROWS>(prm, n_wave);
 }
 __global__ void __launch_bounds__(128, 8) banded_strip_finish_kernel(const BandedParams prm, uint32_t n_wave) {
-  banded_fill_body<-1>(prm, n_wave);
+  banded_fill_body<-1, 1>(prm, n_wave);
+}
+__global__ void __launch_bounds__(128) banded_strip_walk_kernel(const BandedParams prm, uint32_t n_wave) {
+  banded_fill_body<-1, 2, 1>(prm, n_wave);  // one pair per thread
 }
 
 #endif

@@ -1682,19 +1682,45 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
         b3.strip_off = sp.strip_off;
         banded_strip_finish_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
         CK(cudaGetLastError());
-        e->launches += 2;
+        banded_strip_walk_kernel<<<(ns + 127) / 128, 128, 0, st>>>(b3, ns);  // one pair per thread
+        CK(cudaGetLastError());
+        e->launches += 3;
         e->strip_pairs += elig.size();
       }
-      // one warp per pair; K4 marked the pairs whose band suits the register-resident loop (each kernel skips
-      // the other's pairs)
-      if (e->banded_fast) {
-        banded_fill_fast_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
+      // The column loops, one warp per pair, for the pairs K4 did not mark for the strip path (K4 marked those whose
+      // band suits the register-resident loop; each kernel skips the other's pairs).  With strip pairs in the
+      // sub-wave they run beside the strip kernels on a stream of their own -- a lone unmarked pair takes ~2 ms on
+      // its single warp -- and a second, normally empty pass afterwards takes what the strip path handed back.
+      const bool side = !elig.empty() && elig.size() < ns;
+      cudaStream_t cs = st;
+      if (side) {
+        if (!e->aux_stream) CK(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+        while (e->sub_ev.size() < 6) {
+          cudaEvent_t v;
+          CK(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+          e->sub_ev.push_back(v);
+        }
+        cs = e->aux_stream;
+        CK(cudaStreamWaitEvent(cs, ev1, 0));  // K4's results and the sub-wave's uploads
+      }
+      for (int pass = 0; pass < (elig.empty() ? 1 : 2); ++pass) {
+        if (pass == 0 && elig.size() == ns) continue;  // every pair is a strip pair
+        BandedParams bc = b3;
+        bc.redo_pass = pass;
+        cudaStream_t ks = pass == 0 ? cs : st;
+        if (pass == 1 && side) {  // the first pass is done before the hand-backs run (same slabs, same outputs)
+          CK(cudaEventRecord(e->sub_ev[3], cs));
+          CK(cudaStreamWaitEvent(st, e->sub_ev[3], 0));
+        }
+        if (e->banded_fast) {
+          banded_fill_fast_kernel<<<(ns + 3) / 4, 128, 0, ks>>>(bc, ns);
+          CK(cudaGetLastError());
+          ++e->launches;
+        }
+        banded_fill_kernel<<<(ns + 3) / 4, 128, 0, ks>>>(bc, ns);
         CK(cudaGetLastError());
         ++e->launches;
       }
-      banded_fill_kernel<<<(ns + 3) / 4, 128, 0, st>>>(b3, ns);
-      CK(cudaGetLastError());
-      ++e->launches;
       CK(cudaEventRecord(ev2, st));
       CK(cudaStreamSynchronize(st));  // foff (host vector) is reused by the next sub-wave
       float ms = 0.f;

@@ -864,18 +864,24 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
     std::vector<uint8_t> opsbuf(m + n + 16, 0);
     BandedOut o{};
     bool redo = false;
+    // as on the device: phase 1 (everything up to the final score) by the 32 lanes of a warp, then the walk by ONE
+    // thread (the strip path's walk kernel gives a pair to each lane)
     run32([&](int l) {
       BandedOut mine{};
       bool r2 = false;
-      banded_compute_d<32, decltype(scoref), -1>(l, x, m, y, n, sc, scoref, rng_all.data() + roff[p] / 4, cells[p],
-                                                 fill_all.data() + foff[p], mode == 2 || mode == 3,
-                                                 opsbuf.data() + opsbuf.size(), mine, strip_all.data() + soff[p],
-                                                 cols.data() + 3 * p, &r2);
-      if (l == 0) {
-        o = mine;
-        redo = r2;
-      }
+      banded_compute_d<32, decltype(scoref), -1, 1>(l, x, m, y, n, sc, scoref, rng_all.data() + roff[p] / 4, cells[p],
+                                                    fill_all.data() + foff[p], mode == 2 || mode == 3,
+                                                    opsbuf.data() + opsbuf.size(), mine, strip_all.data() + soff[p],
+                                                    cols.data() + 3 * p, &r2);
+      if (l == 0) redo = r2;
     });
+    if (!redo) {
+      bool r2 = false;
+      banded_compute_d<1, decltype(scoref), -1, 2>(0, x, m, y, n, sc, scoref, rng_all.data() + roff[p] / 4, cells[p],
+                                                   fill_all.data() + foff[p], mode == 2 || mode == 3,
+                                                   opsbuf.data() + opsbuf.size(), o, strip_all.data() + soff[p],
+                                                   cols.data() + 3 * p, &r2);
+    }
     if (redo || o.status) continue;
     path[p] = 1;
     score[p] = o.score;

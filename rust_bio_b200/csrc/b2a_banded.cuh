@@ -188,6 +188,22 @@ struct BandD {
   uint64_t rows, cols;
   int lane = 0;
   bool oob = false;  // a column index past the matrix: the reference panics on ranges[j] (caller-supplied matches)
+  // the columns this lane has touched since init (every other column still holds Band::new's sentinel): the passes
+  // over the finished band -- num_cells, the K3 eligibility checks -- only visit [first, last] of the whole warp
+  uint64_t tmin = ~0ull, tmax = 0;
+  B2A_HD void touched(uint64_t& first, uint64_t& last) const {  // first > last: nothing touched
+    long long a = tmin == ~0ull ? (long long)0x8000000000000000ull : -(long long)tmin;  // min as a max of negatives
+    long long b = tmin == ~0ull ? (long long)0x8000000000000000ull : (long long)tmax;
+    a = C::all_max(a);
+    b = C::all_max(b);
+    if (a == (long long)0x8000000000000000ull) {
+      first = 1;
+      last = 0;
+    } else {
+      first = (uint64_t)(-a);
+      last = (uint64_t)b;
+    }
+  }
   B2A_HD void init(uint64_t m, uint64_t n) {  // Band::new, banded.rs:1061-1067
     rows = m + 1;
     cols = n + 1;
@@ -203,6 +219,8 @@ struct BandD {
       return;
     }
     if ((uint64_t)r[2 * j] > v) r[2 * j] = (uint32_t)v;
+    tmin = j < tmin ? j : tmin;
+    tmax = j > tmax ? j : tmax;
   }
   B2A_HD void hi(uint64_t j, uint64_t v) {
     if (j >= cols) {
@@ -210,6 +228,8 @@ struct BandD {
       return;
     }
     if ((uint64_t)r[2 * j + 1] < v) r[2 * j + 1] = (uint32_t)v;
+    tmin = j < tmin ? j : tmin;
+    tmax = j > tmax ? j : tmax;
   }
   B2A_HD void add_kmer(uint64_t r0, uint64_t c0, uint64_t k, uint64_t w) {  // banded.rs:1071-1107
     if (k == 0) return;
@@ -342,11 +362,15 @@ struct BandD {
       r[2 * j] = 0;
       r[2 * j + 1] = (uint32_t)rows;
     }
+    tmin = 0;
+    tmax = cols - 1;
     C::sync();
   }
-  B2A_HD uint64_t num_cells() const {  // banded.rs:1374-1380
+  B2A_HD uint64_t num_cells() const {  // banded.rs:1374-1380 (untouched columns are empty)
     unsigned long long cells = 0;
-    for (uint64_t j = (uint64_t)lane; j < cols; j += W) cells += sat_sub64(r[2 * j + 1], r[2 * j]);
+    uint64_t a, b;
+    touched(a, b);
+    for (uint64_t j = a + (uint64_t)lane; j <= b && j < cols; j += W) cells += sat_sub64(r[2 * j + 1], r[2 * j]);
     return C::all_sum(cells);
   }
   B2A_HD bool any_oob() const { return C::ballot(oob) != 0u; }
@@ -755,7 +779,7 @@ template <int W>
 B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint32_t k,
                               uint32_t w, const DevScoring& sc, int32_t has_match_scores, uint8_t* slab,
                               uint32_t cap, uint32_t* ranges, uint64_t* cells_out, uint32_t* shared_u32,
-                              const BandHintsD& hint = BandHintsD{}) {
+                              const BandHintsD& hint = BandHintsD{}, uint32_t* touched_out = nullptr) {
   using C = Coop<W>;
   const uint64_t short_len = m <= n ? m : n;
   uint32_t H = 16;
@@ -887,6 +911,12 @@ B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint
   }
   if (band.any_oob()) return 3;
   *cells_out = band.num_cells();
+  if (touched_out) {
+    uint64_t a, b;
+    band.touched(a, b);
+    touched_out[0] = (uint32_t)a;
+    touched_out[1] = (uint32_t)b;
+  }
   return status;
 }
 
@@ -944,12 +974,15 @@ struct BandedOut {
 //     the row above was set, 556-561 -- no leftovers of older columns are ever visible), and
 //   * has only the Band::new sentinel as empty columns;
 // every other pair runs the literal loop.  All 300 sampled pairs of BASELINE config 4 qualify.
+// [jlo, jhi]: the columns the band construction touched (every other column is a Band::new sentinel and passes)
 template <int W, int R>
-B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n) {
+B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint64_t jlo = 0,
+                           uint64_t jhi = ~0ull) {
   using C = Coop<W>;
   if (W != 32 || m < 2 || n < 2 || m >= (1u << 24) || n >= (1u << 24)) return false;
   bool ok = true;
-  for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
+  const uint64_t jend = jhi < n ? jhi + 1 : n;  // one past the touched range: it still looks back at column jhi
+  for (uint64_t j = jlo + (uint64_t)lane; j <= jend; j += W) {
     const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
     if (s >= e) {
       if (!(s == m + 1 && e == 0)) ok = false;
@@ -975,12 +1008,14 @@ B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n
 // banded.rs:590-596, stay with the literal loops).  out3 = {first, last non-empty column, sum over the band's
 // columns 1..n-1 of the 128-row strips they touch}.
 template <int W>
-B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint32_t* out3) {
+B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint32_t* out3, uint64_t jlo = 0,
+                            uint64_t jhi = ~0ull) {
   using C = Coop<W>;
   if (W != 32 || m < 2 || n < 2 || m >= (1u << 24) || n >= (1u << 24)) return false;
   bool ok = true;
   uint32_t c0 = 0xFFFFFFFFu, c1 = 0, cnt = 0, scols = 0;
-  for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
+  const uint64_t jend = jhi < n ? jhi + 1 : n;
+  for (uint64_t j = jlo + (uint64_t)lane; j <= jend; j += W) {
     const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
     if (s >= e) {
       if (!(s == m + 1 && e == 0)) ok = false;
@@ -2298,10 +2333,78 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   };
   uint32_t layer = rd_part(i, j, 2);
   uint64_t guard = 4 * (m + n) + 64;
+  // STRIP: runs of Match / Subst / Ins / Del moves between interior band cells -- nearly the whole path -- in 32-bit
+  // arithmetic with the strip's table entry cached and ONE traceback load per move: the nibble of the cell moved to
+  // also answers that cell's own "from extension" question on the next move.  Anything else (a border, a clip, a
+  // cell outside the band, the op budget) leaves the run before the move is made; the general step below does it.
+  uint32_t ks_cst = 0xFFFFFFFFu, ks_cja = 0, ks_coff = 0;
+  auto nib32 = [&](int32_t ii, int32_t jj) -> uint32_t {
+    const uint32_t bs = rng[2 * jj], be = rng[2 * jj + 1];
+    if (!((uint32_t)ii >= bs && (uint32_t)ii < be)) return 16u;
+    const uint32_t st = (uint32_t)(ii - 1) >> 7, rem = (uint32_t)(ii - 1) & 127u, l = rem >> 4, r = rem & 15u;
+    if (st != ks_cst) {
+      ks_cst = st;
+      ks_cja = ks_tab[2 * st];
+      ks_coff = ks_tab[2 * st + 1];
+    }
+    const uint32_t t = (uint32_t)jj - ks_cja + l;
+    const uint32_t word = ks_tb[(ks_coff + ((t >> 3) * 4u + (r >> 2)) * 8u + l) * 4u + (r & 3u)];
+    return (word >> (4u * (7u - (t & 7u)))) & 15u;
+  };
   while (layer != TB_START) {
     if (guard-- == 0 || overflow) {
       out.status = 1;
       break;
+    }
+    if (STRIP && i >= 1 && i < m && j >= 1 && j < n &&
+        (layer == TB_INS || layer == TB_DEL || layer == TB_MATCH || layer == TB_SUBST)) {
+      int32_t fi = (int32_t)i, fj = (int32_t)j;
+      uint32_t nbc = nib32(fi, fj);
+      bool moved = false;
+      while (nbc != 16u && nops < ops_cap && guard > 0) {
+        uint32_t code, nl = 0;
+        int32_t ti = fi, tj = fj;
+        bool known = false;
+        if (layer == TB_INS) {
+          code = 3;
+          ti = fi - 1;
+          if (nbc & NB_IEXT) {
+            nl = TB_INS;
+            known = true;
+          }
+        } else if (layer == TB_DEL) {
+          code = 2;
+          tj = fj - 1;
+          if (nbc & NB_DEXT) {
+            nl = TB_DEL;
+            known = true;
+          }
+        } else if (layer == TB_MATCH || layer == TB_SUBST) {
+          code = layer == TB_MATCH ? 0u : 1u;
+          ti = fi - 1;
+          tj = fj - 1;
+        } else {
+          break;
+        }
+        if (ti < 1 || tj < 1) break;  // the move lands on row 0 / column 0
+        const uint32_t nbn = nib32(ti, tj);
+        if (nbn == 16u) break;        // ... or outside the band (reads as START there)
+        if (!known) nl = ks_sbits((uint64_t)ti, (uint64_t)tj, nbn);
+        *(--ops_end) = (uint8_t)code;
+        ++nops;
+        --guard;
+        fi = ti;
+        fj = tj;
+        nbc = nbn;
+        layer = nl;
+        moved = true;
+      }
+      i = (uint64_t)fi;
+      j = (uint64_t)fj;
+      if (moved) {
+        ++guard;  // the general loop's own decrement above stood for one of the moves
+        continue;
+      }
     }
     uint32_t next;
     if (layer == TB_INS) {
@@ -2404,16 +2507,17 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
   }
   hint.allowed_mismatches = prm.allowed_mismatches;
   hint.use_lcskpp_union = prm.use_lcskpp_union;
+  uint32_t touched[2] = {0u, 0xFFFFFFFFu};  // (whole range, unless the band construction says less)
   const uint32_t st = band_create_d<32>(lane, prm.blob + prm.x_off[p], m, prm.blob + prm.y_off[p], n, prm.k, prm.w,
                                         prm.sc, prm.has_match_scores, prm.slab + (uint64_t)t * prm.slab_stride,
                                         prm.cap_matches, prm.ranges + prm.ranges_off[t] / 4, &cells,
-                                        shared_u32[threadIdx.x >> 5], hint);
+                                        shared_u32[threadIdx.x >> 5], hint, touched);
   // pairs whose band suits the register-resident K3 loop are marked (bit 8) while the ranges are still hot
   const bool fast = st == 0 && cells <= BANDED_MAX_CELLS &&
-                    banded_fast_ok<32, K3_FAST_ROWS>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n);
+                    banded_fast_ok<32, K3_FAST_ROWS>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, touched[0], touched[1]);
   uint32_t cols3[3] = {0, 0, 0};
   const bool strip = prm.strip_ok && st == 0 && cells <= BANDED_MAX_CELLS &&
-                     banded_strip_ok<32>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, cols3);
+                     banded_strip_ok<32>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, cols3, touched[0], touched[1]);
   if (lane != 0) return;
   prm.num_cells[p] = cells;
   prm.k4_status[p] = st | (fast ? 0x100u : 0u) | (strip ? 0x200u : 0u);

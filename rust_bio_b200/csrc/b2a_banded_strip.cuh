@@ -9,7 +9,7 @@
 //   * lanes own FIXED rows: 8 lanes x 16 rows = strips of 128 rows, four pairs to a warp; a strip sweeps only the
 //     columns where the band meets its rows ([ja, jb], found by two binary searches: the band's starts and ends
 //     do not decrease), lane l one column behind lane l-1, the vertical I chain handed down by warp shuffle;
-//   * a cell outside the band is computed like any other and then FORCED to the sentinel (S = I = D = NEG4),
+//   * a cell outside the band is computed like any other and then its S is FORCED to the sentinel (NEG4),
 //     which is what the reference reads there for an eligible band: every value outside the previous column's
 //     band is MIN_SCORE (rows below were reset 676-680, the row above was set 556-561, the band never moves up or
 //     shrinks, empty columns are Band::new sentinels).  The sentinel is not MIN_SCORE itself but it orders the same:
@@ -154,12 +154,13 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
     s4 = sP & ~3;
     const int32_t fi = addmin(i4, -iop, 4), fd = addmin(d4, -dop, 4);
     tbacc[r] = (uint32_t)(fmad((int32_t)tbacc[r], k16, fmad(fd, k2, fi)) + sP - s4);
+    // Outside the band S is forced to the sentinel (what the reference reads there is MIN_SCORE).  I and D need no
+    // forcing: a column's band rows are one run and so are a row's band columns (starts and ends never decrease), so
+    // neither chain re-enters the band once it has left it -- above the band I derives from the sentinel top and a
+    // forced S only; below it D does; and what the other chain carries there (a real value decayed by extensions)
+    // is never read by a band cell.
     const bool inb = (uint32_t)(a_band + r) < h_band;
-    if (!inb) {  // outside the band: what the reference reads there (MIN_SCORE everywhere), as the sentinel
-      s4 = NEG4;
-      i4 = NEG4 + 2;
-      d4 = NEG4 + 1;
-    }
+    if (!inb) s4 = NEG4;
     if (TR) {
       if (inb) SnR[r] = imax(SnR[r], fmad(s4, k1024, cjkey));
     }

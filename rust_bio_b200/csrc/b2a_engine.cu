@@ -87,6 +87,9 @@ struct b2a_engine {
   bool overlap_small = true;
   bool overlap_big = false;
   bool tail_split = true;          // small batches: the fill's thin last round of tasks runs under K2 of the rest
+  bool split_timing = false;       // B2A_SPLIT_TIMING=1: print where the split step's time goes (dev aid)
+  cudaEvent_t split_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool split_ran = false;
   uint32_t walk_cta_warps = 0;     // warps (pairs) per CTA of the warp-per-pair K2: 1, 2, 4, 8, 16, 32 or 0 = automatic
   cudaEvent_t ev_fill = nullptr;
   bool tail_used = false;          // the last run put K2 and the compaction on tail_stream
@@ -275,6 +278,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
   if (const char* env = getenv("B2A_TAIL_SPLIT")) e->tail_split = atoi(env) != 0;
+  if (const char* env = getenv("B2A_SPLIT_TIMING")) e->split_timing = atoi(env) != 0;
   if (const char* env = getenv("B2A_WALK_CTA_WARPS")) {
     const int v = atoi(env);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) e->walk_cta_warps = (uint32_t)v;
@@ -849,17 +853,29 @@ int32_t b2a_batch_run(b2a_engine* e) {
       wa.nblocks = split_b;
       wb.blocks = wp.blocks + split_b;
       wb.nblocks = nb - split_b;
+      if (e->split_timing && !e->split_ev[0])
+        for (auto& v : e->split_ev) CK(cudaEventCreate(&v));
+      if (e->split_timing) CK(cudaEventRecord(e->split_ev[0], st));
       CK(e->shape->launch(e->flags, fa, fa.nblocks * (uint32_t)pl.G, e->num_sms, st, &e->last_grid, 0));
+      if (e->split_timing) CK(cudaEventRecord(e->split_ev[1], st));
       CK(cudaEventRecord(e->sub_ev[0], st));  // fill A done
       // fill B + walk B on the high-priority stream, walk A on the auxiliary one
-      CK(cudaStreamWaitEvent(e->tail_stream, e->sub_ev[0], 0));
-      CK(cudaStreamWaitEvent(e->aux_stream, e->sub_ev[0], 0));
-      CK(e->shape->launch(e->flags, fb, fb.nblocks * (uint32_t)pl.G, e->num_sms, e->tail_stream, nullptr, 0));
-      CK(cudaEventRecord(e->wave_ev[3 * wi + 1], e->tail_stream));  // every fill has finished
-      walk_warp_kernel<<<wa.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, e->aux_stream>>>(wa);
+      // (measured, profiles/r02_10k_target.txt: beside walk A the fill of B takes 144 us instead of 86 -- walk A's 64
+      //  resident warps per SM crowd it -- so B's chain, +186 us, ends the step; walk A at a quarter of its occupancy
+      //  frees B (+100 us) but then takes +246 us itself; swapping the stream priorities changes nothing)
+      cudaStream_t sB = e->tail_stream, sA = e->aux_stream;
+      CK(cudaStreamWaitEvent(sB, e->sub_ev[0], 0));
+      CK(cudaStreamWaitEvent(sA, e->sub_ev[0], 0));
+      CK(e->shape->launch(e->flags, fb, fb.nblocks * (uint32_t)pl.G, e->num_sms, sB, nullptr, 0));
+      CK(cudaEventRecord(e->wave_ev[3 * wi + 1], sB));  // every fill has finished
+      if (e->split_timing) CK(cudaEventRecord(e->split_ev[2], sB));
+      walk_warp_kernel<<<wa.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, sA>>>(wa);
       CK(cudaGetLastError());
-      walk_warp_kernel<<<wb.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, e->tail_stream>>>(wb);
+      if (e->split_timing) CK(cudaEventRecord(e->split_ev[3], sA));
+      walk_warp_kernel<<<wb.nblocks * 32 / wcta_warps, wcta_warps * 32, (size_t)per_warp_smem * wcta_warps, sB>>>(wb);
       CK(cudaGetLastError());
+      if (e->split_timing) CK(cudaEventRecord(e->split_ev[4], sB));
+      e->split_ran = true;
       e->launches += 4;
       CK(cudaEventRecord(e->sub_ev[1], e->aux_stream));
       CK(cudaEventRecord(e->sub_ev[2], e->tail_stream));
@@ -998,6 +1014,16 @@ int32_t b2a_batch_fetch(b2a_engine* e, b2a_results* r, b2a_stats* stats) {
     if (ctl[1] & 8u)
       return e->fail(B2A_E_INVALID, "banded: the reference panics on these caller-supplied matches/path (not strictly ascending, index out of range, or outside the matrix)");
     if (ctl[1]) return e->fail(B2A_E_RANGE, "traceback walk met an impossible move or never terminates (the reference panics / hangs here: mod.rs:905, banded.rs:777-831)");
+  }
+  if (e->split_timing && e->split_ran) {
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, e->split_ev[0], e->split_ev[1]);
+    cudaEventElapsedTime(&b, e->split_ev[1], e->split_ev[2]);
+    cudaEventElapsedTime(&c, e->split_ev[1], e->split_ev[3]);
+    cudaEventElapsedTime(&d, e->split_ev[1], e->split_ev[4]);
+    fprintf(stderr, "[split] fill A %.1f us; after it: fill B done +%.1f, walk A done +%.1f, walk B done +%.1f us\n", a * 1e3,
+            b * 1e3, c * 1e3, d * 1e3);
+    e->split_ran = false;
   }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));

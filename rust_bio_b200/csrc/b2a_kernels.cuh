@@ -112,41 +112,59 @@ __global__ void gather_ops_kernel(const uint8_t* __restrict__ scratch,
   for (uint64_t k = lane; k < n; k += 32) dense[lo + k] = src[k];
 }
 
-// Small batches: exclusive sum of n_ops[0..n) into n+1 u64 offsets by ONE CTA, 1,024 elements per round (coalesced
-// loads, a warp scan, a scan of the 32 warp sums, a running carry): one launch instead of widen + the two passes
-// of a device-wide scan.
+// Small batches (n <= 65,536): exclusive sum of n_ops[0..n) into n+1 u64 offsets by ONE CTA with three barriers in
+// all -- every 1,024-element round is warp-scanned up front (coalesced loads, the rounds are independent), the
+// per-warp sums of every round are scanned by one warp each, the round totals by warp 0, and a second pass over the
+// input adds the three levels up.  One launch instead of widen + the two passes of a device-wide scan.
 __global__ void __launch_bounds__(1024) scan_small_kernel(const uint32_t* __restrict__ n_ops, uint64_t* __restrict__ off,
                                                           uint32_t n_pairs) {
-  __shared__ uint32_t warp_sum[32];
-  __shared__ uint32_t round_total;
+  __shared__ uint32_t wsum[64][32];   // [round][warp]: inclusive warp totals, then exclusive within the round
+  __shared__ uint32_t round_tot[64];
+  __shared__ uint64_t round_base[65];
   const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  uint64_t carry = 0;
-  for (uint32_t base = 0; base < n_pairs; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n_pairs ? n_ops[i] : 0u;  // a round's sum stays below 2^32: 1,024 x (m + n + 4) ops
-    uint32_t inc = v;
+  const uint32_t rounds = (n_pairs + 1023u) >> 10;  // <= 64
+  auto warp_inc = [&](uint32_t v) {
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= (uint32_t)d) inc += t;
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= (uint32_t)d) v += t;
     }
-    if (lane == 31) warp_sum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-      const uint32_t ws = warp_sum[lane];
-      uint32_t wi = ws;
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-        if (lane >= (uint32_t)d) wi += t;
-      }
-      warp_sum[lane] = wi - ws;  // exclusive
-      if (lane == 31) round_total = wi;
-    }
-    __syncthreads();
-    if (i < n_pairs) off[i] = carry + warp_sum[w] + (inc - v);
-    carry += round_total;
-    __syncthreads();
+    return v;
+  };
+  for (uint32_t k = 0; k < rounds; ++k) {
+    const uint32_t i = (k << 10) + threadIdx.x;
+    const uint32_t inc = warp_inc(i < n_pairs ? n_ops[i] : 0u);  // a round's sum stays below 2^32: 1,024 x (m + n + 4) ops
+    if (lane == 31) wsum[k][w] = inc;
   }
-  if (threadIdx.x == 0) off[n_pairs] = carry;
+  __syncthreads();
+  for (uint32_t k = w; k < rounds; k += 32) {
+    const uint32_t ws = wsum[k][lane], wi = warp_inc(ws);
+    wsum[k][lane] = wi - ws;
+    if (lane == 31) round_tot[k] = wi;
+  }
+  __syncthreads();
+  if (w == 0) {
+    uint64_t carry = 0;
+    for (uint32_t k0 = 0; k0 < rounds; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      const uint64_t v = k < rounds ? (uint64_t)round_tot[k] : 0ull;
+      uint64_t inc = v;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+      }
+      if (k < rounds) round_base[k] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) round_base[rounds] = carry;
+  }
+  __syncthreads();
+  for (uint32_t k = 0; k < rounds; ++k) {
+    const uint32_t i = (k << 10) + threadIdx.x;
+    const uint32_t v = i < n_pairs ? n_ops[i] : 0u;
+    const uint32_t inc = warp_inc(v);
+    if (i < n_pairs) off[i] = round_base[k] + wsum[k][w] + (inc - v);
+  }
+  if (threadIdx.x == 0) off[n_pairs] = round_base[rounds];
 }
 
 // n_ops (u32) -> u64 with a trailing 0 so one exclusive scan yields n_pairs+1 offsets

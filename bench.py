@@ -538,6 +538,10 @@ def main():
                                                 "the per-GPU share at 8 GPUs (25,000 pairs); named generator synth.mutated_window_pairs",
                       "pairs_this_gpu": n4, "scaling": "weak", "ms_per_step": round(kms, 3),
                       "kernel_ms": {"band_K4": round(band_ms, 3), "fill_walk_K3": round(k3_ms, 3), "compact": round(walk_ms, 3)},
+                      "k3_path": {"strip_wavefront_pairs": int(eng.banded_strip_pairs()), "column_loop_pairs": n4 - int(eng.banded_strip_pairs()),
+                                  "what": "K3s = strip-wavefront fill (8 lanes x 16 rows, four pairs to a warp, packed cell + band mask, 4-bit "
+                                          "traceback) + finish pass + walk (one pair per thread); the pairs K4 does not mark (band reaching "
+                                          "column n) run the K3 column loops on a side stream"},
                       "cells_this_gpu": cells, "cells_are": "Band::num_cells (banded.rs:1374-1380)", "ops_per_cell": OPS_GLOBAL,
                       "gcups_this_gpu": round(cells / (kms * 1e-3) / 1e9, 2), "gcups": round(world * cells / (kms * 1e-3) / 1e9, 2),
                       "mn_equivalent_gcups_this_gpu": round(n4 * 500 * 10000 / (kms * 1e-3) / 1e9, 1),

@@ -385,7 +385,8 @@ constexpr uint64_t HASH_B = 0x9E3779B97F4A7C15ull | 1ull;
 // append order do not matter, the result is the sorted set.
 template <int W>
 B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint64_t k,
-                                    uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap, uint32_t* counter) {
+                                    uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap, uint32_t* counter,
+                                    uint64_t* hbuf, uint64_t hbuf_entries) {
   using C = Coop<W>;
   const uint64_t nx = sat_sub64(m + 1, k), ny = sat_sub64(n + 1, k);
   if (nx == 0 || ny == 0 || k == 0) return 0;
@@ -415,42 +416,73 @@ B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, cons
     }
   }
   C::sync();
+  // Probe.  A lane rolls its hash over a contiguous run of positions (no re-initialisation), but the lanes do not
+  // probe their OWN positions: the matches of a read against a window of a long reference sit in the runs of two
+  // lanes, which would walk the table chains and append for everybody while thirty lanes wait.  Per round every
+  // lane hashes the next T positions of its run into a W x T buffer (the event scratch, free until sdpkpp), then
+  // takes T buffer entries of T different lanes (a diagonal), so hits and long chains spread over the warp.
+  // Candidates (equal upper hash halves) are appended unverified; the byte comparison follows, one candidate per lane.
   {
     const uint64_t seg = (np + W - 1) / W, lo = umin64(np, seg * (uint64_t)lane), hi = umin64(np, lo + seg);
-    if (lo < hi) {
-      uint64_t h = 0;
+    const uint32_t T = (uint32_t)umax64(1, umin64(32, hbuf_entries / (uint64_t)W));
+    uint64_t h = 0;
+    if (lo < hi)
       for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(ps[lo + t] + 1);
-      for (uint64_t j = lo; j < hi; ++j) {
-        const uint64_t hm = mix(h);
-        uint32_t slot = (uint32_t)hm & mask;
-        for (;;) {
-          const uint64_t e = table[slot];
-          if (e == 0) break;
-          if ((e >> 32) == (hm >> 32)) {
-            const uint64_t i = (e & 0xffffffffull) - 1;
-            bool same = true;
-            for (uint64_t t = 0; t < k; ++t)
-              if (hs[i + t] != ps[j + t]) {
-                same = false;
-                break;
-              }
-            if (same) {
+    for (uint64_t r0 = 0; r0 < seg; r0 += T) {
+      for (uint32_t t = 0; t < T; ++t) {
+        const uint64_t j = lo + r0 + t;
+        if (j < hi) {
+          hbuf[(uint64_t)lane * T + t] = mix(h);
+          if (j + 1 < hi) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
+        }
+      }
+      C::sync();
+      for (uint32_t t = 0; t < T; ++t) {
+        const uint32_t src = ((uint32_t)lane + t) % (uint32_t)W;  // whose position this lane probes
+        const uint64_t slo = umin64(np, seg * (uint64_t)src), shi = umin64(np, slo + seg);
+        const uint64_t j = slo + r0 + t;
+        if (j < shi) {
+          const uint64_t hm = hbuf[(uint64_t)src * T + t];
+          uint32_t slot = (uint32_t)hm & mask;
+          for (;;) {
+            const uint64_t e = table[slot];
+            if ((uint32_t)e == 0u) break;  // (the low half is position + 1: never 0 in a used slot)
+            if ((uint32_t)(e >> 32) == (uint32_t)(hm >> 32)) {
+              const uint64_t i = (e & 0xffffffffull) - 1;
               const uint32_t at = C::fetch_add(counter, 1u);
               if (at < cap) out[at] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
             }
+            slot = (slot + 1) & mask;
           }
-          slot = (slot + 1) & mask;
         }
-        if (j + 1 < hi) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
       }
+      C::sync();
     }
   }
   C::sync();
-  const uint64_t cnt = *counter;
+  const uint64_t cand = *counter;
   C::sync();
-  if (cnt > cap) return ~0ull;
-  coop_sort_u64<W>(lane, out, cnt);
-  return cnt;
+  if (cand > cap) return ~0ull;
+  // verify the candidates byte by byte; a false one (a 32-bit hash collision) is struck out and sorts to the end
+  uint32_t bad = 0;
+  for (uint64_t c = (uint64_t)lane; c < cand; c += W) {
+    const uint64_t mt = out[c];
+    const uint64_t i = hash_x ? (mt >> 32) : (mt & 0xffffffffull), j = hash_x ? (mt & 0xffffffffull) : (mt >> 32);
+    bool same = true;
+    for (uint64_t t = 0; t < k; ++t)
+      if (hs[i + t] != ps[j + t]) {
+        same = false;
+        break;
+      }
+    if (!same) {
+      out[c] = ~0ull;
+      ++bad;
+    }
+  }
+  const uint64_t nbad = (uint64_t)C::all_sum((unsigned long long)bad);
+  C::sync();
+  coop_sort_u64<W>(lane, out, cand);
+  return cand - nbad;
 }
 
 // ------------------------------------------------------------------ sdpkpp, sparse.rs:188-295
@@ -806,7 +838,7 @@ B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint
     nm64 = hint.n_matches;
     C::sync();
   } else {
-    nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32);
+    nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32, ev, 4ull * cap);
     if (nm64 == ~0ull) return 1;
   }
   // sdpkpp, lcskpp and expand_kmer_matches assert strictly ascending matches (sparse.rs:77-82, 213-218, 411-416)
@@ -1589,8 +1621,23 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   }
   for (uint64_t j = (uint64_t)lane; j <= n; j += W) {
     Lx[j] = 0;
-    row0[j] = 0;
-    rowm[j] = 0;
+    if (STRIP && j >= 1) {
+      // the strip path's finish pass: row m of every column starts as the x-suffix-clip nibble the column loop leaves
+      // there (655-661 / 671-674), and row 0's cells 1..n-1 get their final value in one store -- the closed-form
+      // s-bits of the border pass (725-731) and, where row 0 is in the band, the d-bits of its cell (518-554)
+      rowm[j] = (uint16_t)(TB_XCLIP_SUFFIX << 8);
+      uint32_t c0v = 0;
+      if (j < n) {
+        const bool in0 = rng[2 * j] == 0 && rng[2 * j + 1] > 0;
+        const int32_t d_score = sc.gap_open + sc.gap_extend * ((int32_t)j - 1);
+        c0v = ((in0 ? row0_dbits(sc, (int32_t)j) : 0u) << 4) |
+              ((d_score > sc.yclip_prefix ? (uint32_t)TB_DEL : (uint32_t)TB_YCLIP_PREFIX) << 8);
+      }
+      row0[j] = (uint16_t)c0v;
+    } else {
+      row0[j] = 0;
+      rowm[j] = 0;
+    }
   }
   C::sync();
   }
@@ -1742,14 +1789,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     // cells 1..m-1 x 1..n-1 -- row 0's cells and its Sn/Ly seed, row m's cells (they start from the column tracker,
     // which is dead here: the x-suffix clip is), and the x-suffix-clip nibble every column leaves in row m.
     const int32_t mi = (int32_t)m;
-    // row 0 (banded.rs:518-554): starts do not decrease, so row 0 is in the band for a prefix of the band's columns
-    for (int64_t j = kc0 + lane; j <= kc1; j += W) {
-      if (rng[2 * j] == 0 && rng[2 * j + 1] > 0) {
-        const uint32_t db = row0_dbits(sc, (int32_t)j);
-        const uint32_t sb = row0_D(sc, (int32_t)j) > yp ? (uint32_t)TB_DEL : (uint32_t)TB_YCLIP_PREFIX;
-        row0[j] = (uint16_t)((db << 4) | (sb << 8));
-      }
-    }
+    // (row 0's cells and row m's x-suffix-clip nibbles were written by the initialisation above)
     if (lane == 0 && kc0 <= kc1 && rng[2 * kc0] == 0 && rng[2 * kc0 + 1] > 0) {
       // S(0, j) never increases with j: only the first row-0 column can raise Sn[0] (547-552)
       const int32_t S0c = imax(row0_D(sc, (int32_t)kc0), yp);
@@ -1770,29 +1810,30 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       }
       jm0 = a;
     }
-    // every other column (1..n) leaves the x-suffix-clip nibble in row m (655-661 / 671-674 with row m outside)
-    for (int64_t j = 1 + lane; j <= (int64_t)n; j += W)
-      if (j < jm0 || j > kc1) rowm[j] = (uint16_t)(TB_XCLIP_SUFFIX << 8);
-    C::sync();
     if (lane == 0) {
-      auto bnd_S = [&](int64_t j) -> int32_t {  // S(m-1, j), MIN_SCORE outside the band
-        if (j == 0) return Sarr[0][m - 1];
-        if (!(rng[2 * j] <= (uint32_t)(m - 1) && rng[2 * j + 1] > (uint32_t)(m - 1))) return MIN_SCORE;
-        const int32_t v = ks_bnd[2 * (j - kc0 + 1)];
-        return v <= -(1 << 29) ? MIN_SCORE : v >> 2;
-      };
-      auto bnd_I = [&](int64_t j) -> int32_t {
-        if (!(rng[2 * j] <= (uint32_t)(m - 1) && rng[2 * j + 1] > (uint32_t)(m - 1))) return MIN_SCORE;
-        const int32_t v = ks_bnd[2 * (j - kc0 + 1) + 1];
-        return v <= -(1 << 29) ? MIN_SCORE : v >> 2;
+      // (S, I)(m-1, j) from the boundary row the strip fill left, MIN_SCORE outside the band; 32-bit column arithmetic
+      const int32_t k0 = (int32_t)kc0, k1 = (int32_t)kc1, m1 = mi - 1;
+      auto bnd_SI = [&](int32_t j, int32_t& S_, int32_t& I_) {
+        S_ = I_ = MIN_SCORE;
+        if (j == 0) {
+          S_ = Sarr[0][m1];
+          return;
+        }
+        if (!((int32_t)rng[2 * j] <= m1 && (int32_t)rng[2 * j + 1] > m1)) return;
+        const int32_t vs = ks_bnd[2 * (j - k0 + 1)], vi = ks_bnd[2 * (j - k0 + 1) + 1];
+        S_ = vs <= -(1 << 29) ? MIN_SCORE : vs >> 2;
+        I_ = vi <= -(1 << 29) ? MIN_SCORE : vi >> 2;
       };
       int32_t Sm_prev = jm0 == 1 ? Sarr[0][m] : MIN_SCORE, Dm_prev = MIN_SCORE;
       int32_t Snm = Sn[m];
-      for (int64_t j = jm0; j <= kc1; ++j) {
+      const int32_t p = (int32_t)x[m - 1];
+      int32_t rSup = MIN_SCORE, unusedI = MIN_SCORE;
+      if (jm0 <= kc1) bnd_SI((int32_t)jm0 - 1, rSup, unusedI);
+      for (int32_t j = (int32_t)jm0; j <= k1; ++j) {
         const int32_t q = (int32_t)y[j - 1];
-        const int32_t p = (int32_t)x[m - 1];
-        const int32_t xcs = xp + imax(yp, go + ge * ((int32_t)j - 1));
-        const int32_t rS = bnd_S(j), rI = bnd_I(j), rSup = bnd_S(j - 1);
+        const int32_t xcs = xp + imax(yp, go + ge * (j - 1));
+        int32_t rS, rI;
+        bnd_SI(j, rS, rI);
         const uint32_t rsb = sbits_at(m - 1, (uint64_t)j);
         uint32_t ib, dbm, sbm;
         const int32_t m_sc = rSup + score((uint8_t)p, (uint8_t)q);
@@ -1838,12 +1879,12 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
         if (b + ys > Snm) {  // 655-660 at i == m, then the cell's own put()
           Snm = b + ys;
           Sn[m] = Snm;
-          Ly[m] = (uint32_t)(n - (uint64_t)j);
-          rowm[n] = (uint16_t)((rowm[n] & ~0x0F00u) | (TB_YCLIP_SUFFIX << 8));
+          Ly[m] = (uint32_t)(n - (uint64_t)j);  // (the eager mark on (m, n) is overwritten below: column n comes last)
         }
         rowm[j] = (uint16_t)(ib | (dbm << 4) | (sbm << 8));
         Sm_prev = b;
         Dm_prev = bd;
+        rSup = rS;  // S(m-1, j) is the next column's diagonal input
       }
       Sarr[n % 2][m] = MIN_SCORE;  // column n is empty: S[m] ends the loop reset (556-561) ...
       rowm[n] = (uint16_t)(TB_XCLIP_SUFFIX << 8);  // ... and its nibble, written last, replaces the eager marks (671-674)
@@ -2256,10 +2297,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   C::sync();
   // the two closed-form border passes (banded.rs:725-765) touch one traceback cell per index, except at
   // the far corner (j = n, i = m), which lane 0 does afterwards
-  for (uint64_t j = 1 + (uint64_t)lane; j < n; j += W) {
-    const int32_t d_score = go + ge * ((int32_t)j - 1);
-    set_s(0, j, d_score > yp ? TB_DEL : TB_YCLIP_PREFIX);
-  }
+  if (!STRIP)  // (the strip path's initialisation has written row 0's final cells)
+    for (uint64_t j = 1 + (uint64_t)lane; j < n; j += W) {
+      const int32_t d_score = go + ge * ((int32_t)j - 1);
+      set_s(0, j, d_score > yp ? TB_DEL : TB_YCLIP_PREFIX);
+    }
   for (uint64_t i = 1 + (uint64_t)lane; i < m; i += W) {
     const int32_t c_score = go + ge * ((int32_t)i - 1);
     set_s(i, 0, c_score > xp ? TB_INS : TB_XCLIP_PREFIX);

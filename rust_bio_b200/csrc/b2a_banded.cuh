@@ -22,7 +22,15 @@ namespace b2a {
 
 constexpr uint64_t BANDED_MAX_CELLS = 5000000ull;  // banded.rs:104
 constexpr int32_t BANDED_DEFAULT_MATCH_SCORE = 2;  // banded.rs:105
-constexpr int K3_FAST_ROWS = 5;  // rows per lane of the register-resident K3 loop: bands up to ~160 rows per column
+constexpr int K3_FAST_ROWS = 5;
+// geometry of the strip-wavefront fill (b2a_banded_strip.cuh): 8 lanes per pair, KS_R rows per lane
+#ifndef B2A_KS_R
+#define B2A_KS_R 16
+#endif
+constexpr int KS_G = 8, KS_R = B2A_KS_R, KS_ROWS = KS_G * KS_R, KS_TBW = KS_R / 4;
+static_assert(KS_R == 8 || KS_R == 16, "rows per lane of the strip fill: 8 or 16");
+constexpr uint32_t KS_ROWS_LOG2 = KS_R == 16 ? 7u : 6u, KS_R_LOG2 = KS_R == 16 ? 4u : 3u;
+constexpr uint32_t KS_TAB = 4;  // u32 per strip-table entry: first column of the window, traceback offset (uint4), steps stored, 0  // rows per lane of the register-resident K3 loop: bands up to ~160 rows per column
 
 struct BandedParams {
   const uint8_t* blob;
@@ -378,6 +386,8 @@ struct BandD {
 
 // ------------------------------------------------------------------ k-mer matches (exact)
 constexpr uint64_t HASH_B = 0x9E3779B97F4A7C15ull | 1ull;
+constexpr uint32_t KF_BITS = 1u << 15;  // bit filter over the hashed k-mers, per warp (4 KB of shared memory)
+constexpr uint32_t K4_SHARED_WORDS = 2u + KF_BITS / 32u;  // band_create_d's `shared_u32`: two scratch words + the filter
 
 // all (i, j) with x[i..i+k] == y[j..j+k] as (i << 32 | j), sorted; returns count or ~0 on overflow.
 // Each lane hashes / probes a contiguous run of positions with its own rolling hash; table slots are claimed
@@ -386,7 +396,7 @@ constexpr uint64_t HASH_B = 0x9E3779B97F4A7C15ull | 1ull;
 template <int W>
 B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, const uint8_t* y, uint64_t n, uint64_t k,
                                     uint64_t* table, uint32_t H, uint64_t* out, uint64_t cap, uint32_t* counter,
-                                    uint64_t* hbuf, uint64_t hbuf_entries) {
+                                    uint64_t* hbuf, uint64_t hbuf_entries, uint32_t* filter /* KF_BITS / 32 words */) {
   using C = Coop<W>;
   const uint64_t nx = sat_sub64(m + 1, k), ny = sat_sub64(n + 1, k);
   if (nx == 0 || ny == 0 || k == 0) return 0;
@@ -395,6 +405,7 @@ B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, cons
   const uint8_t* ps = hash_x ? y : x;
   const uint64_t nh = hash_x ? nx : ny, np = hash_x ? ny : nx;
   for (uint32_t s = (uint32_t)lane; s < H; s += W) table[s] = 0;
+  for (uint32_t s = (uint32_t)lane; s < KF_BITS / 32u; s += W) filter[s] = 0;
   if (lane == 0) *counter = 0;
   C::sync();
   uint64_t bk = 1;  // B^(k-1)
@@ -411,53 +422,71 @@ B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, cons
         uint32_t slot = (uint32_t)hm & mask;
         const uint64_t entry = ((hm >> 32) << 32) | (i + 1);
         while (!C::claim(&table[slot], entry)) slot = (slot + 1) & mask;
+        const uint32_t bit = (uint32_t)(hm >> 17) & (KF_BITS - 1u);
+        C::or_u32(&filter[bit >> 5], 1u << (bit & 31u));
         if (i + 1 < hi) h = (h - (uint64_t)(hs[i] + 1) * bk) * HASH_B + (uint64_t)(hs[i + k] + 1);
       }
     }
   }
   C::sync();
-  // Probe.  A lane rolls its hash over a contiguous run of positions (no re-initialisation), but the lanes do not
-  // probe their OWN positions: the matches of a read against a window of a long reference sit in the runs of two
-  // lanes, which would walk the table chains and append for everybody while thirty lanes wait.  Per round every
-  // lane hashes the next T positions of its run into a W x T buffer (the event scratch, free until sdpkpp), then
-  // takes T buffer entries of T different lanes (a diagonal), so hits and long chains spread over the warp.
-  // Candidates (equal upper hash halves) are appended unverified; the byte comparison follows, one candidate per lane.
+  // Probe.  A lane rolls its hash over a contiguous run of positions.  Nearly all of them (a read against a long
+  // reference: 95 %) have no partner, so a position first asks a bit filter over the hashed k-mers (KF_BITS bits per
+  // warp in shared memory, 1.4 % false positives at 469 k-mers): one shared load instead of a walk down a chain of the
+  // open-addressing table -- a walk the whole warp sits through whenever ONE of its lanes takes it.  The positions
+  // that pass are compacted (ballot + popcount) into a queue in the event scratch (free until sdpkpp) and the table
+  // walks are then dealt out over the lanes entry by entry, so the few real matches (they sit in the runs of two
+  // lanes) no longer serialise the warp either.  Candidates (equal upper hash halves) are appended unverified; the
+  // byte comparison follows, one candidate per lane.
   {
     const uint64_t seg = (np + W - 1) / W, lo = umin64(np, seg * (uint64_t)lane), hi = umin64(np, lo + seg);
-    const uint32_t T = (uint32_t)umax64(1, umin64(32, hbuf_entries / (uint64_t)W));
+    const uint32_t Q = (uint32_t)(hbuf_entries / 2);  // queue capacity in (hash, position) entries, >= 2 W
+    uint32_t qn = 0;
+    auto drain = [&]() {
+      for (uint32_t e = (uint32_t)lane; e < qn; e += W) {
+        const uint64_t hm = hbuf[2 * e], j = hbuf[2 * e + 1];
+        uint32_t slot = (uint32_t)hm & mask;
+        for (;;) {
+          const uint64_t en = table[slot];
+          if ((uint32_t)en == 0u) break;  // (the low half is position + 1: never 0 in a used slot)
+          if ((uint32_t)(en >> 32) == (uint32_t)(hm >> 32)) {
+            const uint64_t i = (en & 0xffffffffull) - 1;
+            const uint32_t at = C::fetch_add(counter, 1u);
+            if (at < cap) out[at] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
+          }
+          slot = (slot + 1) & mask;
+        }
+      }
+    };
     uint64_t h = 0;
     if (lo < hi)
       for (uint64_t t = 0; t < k; ++t) h = h * HASH_B + (uint64_t)(ps[lo + t] + 1);
-    for (uint64_t r0 = 0; r0 < seg; r0 += T) {
-      for (uint32_t t = 0; t < T; ++t) {
-        const uint64_t j = lo + r0 + t;
-        if (j < hi) {
-          hbuf[(uint64_t)lane * T + t] = mix(h);
-          if (j + 1 < hi) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
-        }
+    for (uint64_t r = 0; r < seg; ++r) {
+      const uint64_t j = lo + r;
+      const bool valid = j < hi;
+      uint64_t hm = 0;
+      bool pass = false;
+      if (valid) {
+        hm = mix(h);
+        const uint32_t bit = (uint32_t)(hm >> 17) & (KF_BITS - 1u);
+        pass = ((filter[bit >> 5] >> (bit & 31u)) & 1u) != 0u;
+        if (j + 1 < hi) h = (h - (uint64_t)(ps[j] + 1) * bk) * HASH_B + (uint64_t)(ps[j + k] + 1);
       }
-      C::sync();
-      for (uint32_t t = 0; t < T; ++t) {
-        const uint32_t src = ((uint32_t)lane + t) % (uint32_t)W;  // whose position this lane probes
-        const uint64_t slo = umin64(np, seg * (uint64_t)src), shi = umin64(np, slo + seg);
-        const uint64_t j = slo + r0 + t;
-        if (j < shi) {
-          const uint64_t hm = hbuf[(uint64_t)src * T + t];
-          uint32_t slot = (uint32_t)hm & mask;
-          for (;;) {
-            const uint64_t e = table[slot];
-            if ((uint32_t)e == 0u) break;  // (the low half is position + 1: never 0 in a used slot)
-            if ((uint32_t)(e >> 32) == (uint32_t)(hm >> 32)) {
-              const uint64_t i = (e & 0xffffffffull) - 1;
-              const uint32_t at = C::fetch_add(counter, 1u);
-              if (at < cap) out[at] = hash_x ? ((i << 32) | j) : ((j << 32) | i);
-            }
-            slot = (slot + 1) & mask;
-          }
-        }
+      const uint32_t bal = C::ballot(pass);
+      if (pass) {
+        const uint32_t at = qn + (uint32_t)C::popc(bal & ((1u << lane) - 1u));
+        hbuf[2ull * at] = hm;
+        hbuf[2ull * at + 1] = j;
       }
-      C::sync();
+      qn += (uint32_t)C::popc(bal);
+      if (qn + (uint32_t)W > Q) {  // the next position could overflow the queue
+        C::sync();
+        drain();
+        C::sync();
+        qn = 0;
+      }
     }
+    C::sync();
+    drain();
   }
   C::sync();
   const uint64_t cand = *counter;
@@ -804,7 +833,7 @@ struct BandHintsD {
 };
 
 // W cooperating lanes build one pair's band (W = 32: one warp; W = 1: the host logic build).  `shared_u32` is
-// two words all lanes can read and write (shared memory on the device).
+// K4_SHARED_WORDS words all lanes can read and write (shared memory on the device): two scratch words + the k-mer bit filter.
 // returns status: 0 ok, 1 too many matches (capacity), 2 reference would panic (divide by zero),
 // 3 reference would panic on the caller's matches/path (not sorted, index out of range, outside the matrix)
 template <int W>
@@ -838,7 +867,7 @@ B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint
     nm64 = hint.n_matches;
     C::sync();
   } else {
-    nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32, ev, 4ull * cap);
+    nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32, ev, 4ull * cap, shared_u32 + 2);
     if (nm64 == ~0ull) return 1;
   }
   // sdpkpp, lcskpp and expand_kmer_matches assert strictly ascending matches (sparse.rs:77-82, 213-218, 411-416)
@@ -1038,7 +1067,7 @@ B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n
 // its height limit, the rows are not held in a sliding window there -- plus: the band's columns are one run (the
 // strips find their column windows by binary search), and column n is empty (the last column's extra Sn terms,
 // banded.rs:590-596, stay with the literal loops).  out3 = {first, last non-empty column, sum over the band's
-// columns 1..n-1 of the 128-row strips they touch}.
+// columns 1..n-1 of the KS_ROWS-row strips they touch}.
 template <int W>
 B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint32_t* out3, uint64_t jlo = 0,
                             uint64_t jhi = ~0ull) {
@@ -1061,7 +1090,7 @@ B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t 
       const uint64_t ps = rng[2 * (j - 1)], pe = rng[2 * (j - 1) + 1];
       if (ps < pe && (s < ps || e < pe)) ok = false;
       const uint64_t lo = umax64(1, s), hi = umin64(e, m);  // interior rows lo .. hi-1
-      if (lo < hi && j < n) scols += (uint32_t)((hi - 2) / 128 - (lo - 1) / 128 + 1);
+      if (lo < hi && j < n) scols += (uint32_t)((hi - 2) / KS_ROWS - (lo - 1) / KS_ROWS + 1);
     }
   }
   for (int d = 16; d; d >>= 1) {
@@ -1588,6 +1617,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   uint16_t* col0 = reinterpret_cast<uint16_t*>(slab + L.col0);
   uint16_t* coln = reinterpret_cast<uint16_t*>(slab + L.coln);
   uint16_t* cells = reinterpret_cast<uint16_t*>(slab + L.cells);
+  int64_t kc0 = 1, kc1 = 0;  // STRIP: the band's interior columns, clipped to [1, n-1]
+  if (STRIP) {
+    kc0 = cols3[0] > 1u ? (int64_t)cols3[0] : 1;
+    kc1 = (int64_t)cols3[1] < (int64_t)n - 1 ? (int64_t)cols3[1] : (int64_t)n - 1;
+  }
   if constexpr (PHASE != 2) {
   // init (banded.rs:423-438): only the cells that can ever be non-START are stored
   if (!STRIP) {
@@ -1628,7 +1662,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       rowm[j] = (uint16_t)(TB_XCLIP_SUFFIX << 8);
       uint32_t c0v = 0;
       if (j < n) {
-        const bool in0 = rng[2 * j] == 0 && rng[2 * j + 1] > 0;
+        const bool in0 = (int64_t)j >= kc0 && (int64_t)j <= kc1 && rng[2 * j] == 0 && rng[2 * j + 1] > 0;
         const int32_t d_score = sc.gap_open + sc.gap_extend * ((int32_t)j - 1);
         c0v = ((in0 ? row0_dbits(sc, (int32_t)j) : 0u) << 4) |
               ((d_score > sc.yclip_prefix ? (uint32_t)TB_DEL : (uint32_t)TB_YCLIP_PREFIX) << 8);
@@ -1657,12 +1691,9 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   const uint32_t* ks_tab = nullptr;
   const int32_t* ks_bnd = nullptr;  // int2 {4*S, 4*I + 2} per column, index j - kc0 + 1
   const uint32_t* ks_tb = nullptr;
-  int64_t kc0 = 1, kc1 = 0;         // the band's interior columns, clipped to [1, n-1]
   if (STRIP) {
-    kc0 = cols3[0] > 1u ? (int64_t)cols3[0] : 1;
-    kc1 = (int64_t)cols3[1] < (int64_t)n - 1 ? (int64_t)cols3[1] : (int64_t)n - 1;
-    const uint64_t ns = m >= 2 ? (m - 1 + 127) / 128 : 0;
-    const uint64_t o_tab = 0, o_bnd = al16(ns * 8), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 8);
+    const uint64_t ns = m >= 2 ? (m - 1 + KS_ROWS - 1) / KS_ROWS : 0;
+    const uint64_t o_tab = 0, o_bnd = al16(ns * KS_TAB * 4), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 8);
     ks_tab = reinterpret_cast<const uint32_t*>(strip_area + o_tab);
     ks_bnd = reinterpret_cast<const int32_t*>(strip_area + o_bnd);
     ks_tb = reinterpret_cast<const uint32_t*>(strip_area + o_tb);
@@ -1671,10 +1702,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   auto ks_nib = [&](uint64_t i, uint64_t j) -> uint32_t {
     const uint64_t s = rng[2 * j], e = rng[2 * j + 1];
     if (!(i >= s && i < e)) return 16u;
-    const uint32_t st = (uint32_t)((i - 1) >> 7), rem = (uint32_t)((i - 1) & 127u), l = rem >> 4, r = rem & 15u;
-    const uint32_t ja = ks_tab[2 * st], off = ks_tab[2 * st + 1];
+    const uint32_t st = (uint32_t)((i - 1) >> KS_ROWS_LOG2), rem = (uint32_t)((i - 1) & (uint64_t)(KS_ROWS - 1)),
+                   l = rem >> KS_R_LOG2, r = rem & (uint32_t)(KS_R - 1);
+    const uint32_t ja = ks_tab[KS_TAB * st], off = ks_tab[KS_TAB * st + 1];
     const uint32_t t = (uint32_t)j - ja + l;
-    const uint32_t word = ks_tb[((size_t)off + ((size_t)(t >> 3) * 4 + (r >> 2)) * 8 + l) * 4 + (r & 3u)];
+    const uint32_t word = ks_tb[((size_t)off + ((size_t)(t >> 3) * KS_TBW + (r >> 2)) * KS_G + l) * 4 + (r & 3u)];
     return (word >> (4u * (7u - (t & 7u)))) & 15u;
   };
   auto ks_sbits = [&](uint64_t i, uint64_t j, uint32_t nb) -> uint32_t {
@@ -2379,18 +2411,23 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   // arithmetic with the strip's table entry cached and ONE traceback load per move: the nibble of the cell moved to
   // also answers that cell's own "from extension" question on the next move.  Anything else (a border, a clip, a
   // cell outside the band, the op budget) leaves the run before the move is made; the general step below does it.
-  uint32_t ks_cst = 0xFFFFFFFFu, ks_cja = 0, ks_coff = 0;
+  uint32_t ks_cst = 0xFFFFFFFFu, ks_cja = 0, ks_coff = 0, ks_csteps = 0;
+  // (the traceback word is requested before the band check is known -- its address does not depend on it -- so the
+  //  two loads of a move overlap instead of following each other; the strip table's step count keeps it in bounds)
   auto nib32 = [&](int32_t ii, int32_t jj) -> uint32_t {
-    const uint32_t bs = rng[2 * jj], be = rng[2 * jj + 1];
-    if (!((uint32_t)ii >= bs && (uint32_t)ii < be)) return 16u;
-    const uint32_t st = (uint32_t)(ii - 1) >> 7, rem = (uint32_t)(ii - 1) & 127u, l = rem >> 4, r = rem & 15u;
+    const uint32_t st = (uint32_t)(ii - 1) >> KS_ROWS_LOG2, rem = (uint32_t)(ii - 1) & (uint32_t)(KS_ROWS - 1),
+                   l = rem >> KS_R_LOG2, r = rem & (uint32_t)(KS_R - 1);
     if (st != ks_cst) {
       ks_cst = st;
-      ks_cja = ks_tab[2 * st];
-      ks_coff = ks_tab[2 * st + 1];
+      ks_cja = ks_tab[KS_TAB * st];
+      ks_coff = ks_tab[KS_TAB * st + 1];
+      ks_csteps = ks_tab[KS_TAB * st + 2];
     }
     const uint32_t t = (uint32_t)jj - ks_cja + l;
-    const uint32_t word = ks_tb[(ks_coff + ((t >> 3) * 4u + (r >> 2)) * 8u + l) * 4u + (r & 3u)];
+    const uint32_t tc = t < ks_csteps ? t : 0u;
+    const uint32_t word = ks_tb[(ks_coff + ((tc >> 3) * (uint32_t)KS_TBW + (r >> 2)) * (uint32_t)KS_G + l) * 4u + (r & 3u)];
+    const uint32_t bs = rng[2 * jj], be = rng[2 * jj + 1];
+    if (!((uint32_t)ii >= bs && (uint32_t)ii < be)) return 16u;
     return (word >> (4u * (7u - (t & 7u)))) & 15u;
   };
   while (layer != TB_START) {
@@ -2530,7 +2567,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
 
 // K4: one warp per pair
 __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint32_t n_wave) {
-  __shared__ uint32_t shared_u32[4][2];
+  __shared__ uint32_t shared_u32[4][K4_SHARED_WORDS];
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = (int)(threadIdx.x & 31u);
   if (t >= n_wave) return;

@@ -6,7 +6,7 @@
 // (b2a_banded.cuh) pay per cell -- ~75 instructions of strict-comparison chains plus ~300 per column of uniform
 // work -- this kernel does with the fill's ~20-instruction packed cell (DPX add-max chains, one 3-way max that
 // yields the score and its source, 4-bit traceback) plus a band mask:
-//   * lanes own FIXED rows: 8 lanes x 16 rows = strips of 128 rows, four pairs to a warp; a strip sweeps only the
+//   * lanes own FIXED rows: 8 lanes x KS_R rows (16: strips of 128 rows), four pairs to a warp; a strip sweeps only the
 //     columns where the band meets its rows ([ja, jb], found by two binary searches: the band's starts and ends
 //     do not decrease), lane l one column behind lane l-1, the vertical I chain handed down by warp shuffle;
 //   * a cell outside the band is computed like any other and then its S is FORCED to the sentinel (NEG4),
@@ -36,10 +36,9 @@
 
 namespace b2a {
 
-constexpr int KS_G = 8, KS_R = 16, KS_ROWS = KS_G * KS_R, KS_TBW = KS_R / 4;
 enum : int { F_CLIPY = 64 };  // y-prefix clip live (with F_CLIPX / F_TRACK_ROWS of b2a_common.cuh)
 
-// per-pair strip area: [strip table: nstrips x {ja, traceback offset in uint4 units}][boundary row: (cols+2) x int2][traceback]
+// per-pair strip area: [strip table: nstrips x {ja, traceback offset in uint4 units, steps stored, 0}][boundary row: (cols+2) x int2][traceback]
 struct KsLayout {
   uint64_t tab, bnd, tb, total;
 };
@@ -48,7 +47,7 @@ B2A_HD KsLayout ks_layout(uint64_t m, uint64_t band_cols, uint64_t strip_cols) {
   KsLayout L;
   const uint64_t ns = ks_nstrips(m);
   uint64_t b = 0;
-  L.tab = b; b = al16(b + ns * 8);
+  L.tab = b; b = al16(b + ns * KS_TAB * 4);
   L.bnd = b; b = al16(b + (band_cols + 2) * 8);
   L.tb = b;
   // a strip of `len` columns stores ceil((len + 14) / 8) groups of 8 steps, KS_TBW x KS_G uint4 each
@@ -228,8 +227,10 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
   const uint32_t K = len > 0 ? (uint32_t)((len + KS_G - 1 + 7) >> 3) : 0u;
   uint4* tbs = P.tb + tb_used;
   if (have && l == 0) {
-    P.tab[2 * s] = (uint32_t)ja;
-    P.tab[2 * s + 1] = tb_used;
+    P.tab[KS_TAB * s] = (uint32_t)ja;
+    P.tab[KS_TAB * s + 1] = tb_used;
+    P.tab[KS_TAB * s + 2] = K * 8u;
+    P.tab[KS_TAB * s + 3] = 0u;
   }
   // lane state
   int32_t Sp[KS_R], Dp[KS_R], SnR[KS_R], xc[KS_R];

@@ -89,6 +89,27 @@ struct Coop {
     *ctr = old + v;
     return old;
   }
+  static B2A_HD void or_u32(uint32_t* p, uint32_t v) {  // set bits in a word other lanes may be setting too
+#if defined(__CUDA_ARCH__)
+    if (W > 1) {
+      atomicOr(p, v);
+      return;
+    }
+#elif defined(B2A_HOST_WARP)
+    if (W > 1) {
+      __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST);
+      return;
+    }
+#endif
+    *p |= v;
+  }
+  static B2A_HD int popc(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+  }
   static B2A_HD int32_t all_max32(int32_t v) {  // one REDUX on the device
 #if defined(__CUDA_ARCH__)
     if (W > 1) return __reduce_max_sync(0xffffffffu, v);

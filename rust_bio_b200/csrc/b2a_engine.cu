@@ -1688,7 +1688,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
         sp.flags = fl;
         CK(cudaMemsetAsync(sp.task_counter, 0, 4, st));
         const uint32_t ntasks = (sp.n_elig + 3) / 4;
-        const unsigned sgrid = (unsigned)std::min<uint32_t>((ntasks + KS_WARPS - 1) / KS_WARPS, (uint32_t)e->num_sms * 3u);
+        const unsigned sgrid = (unsigned)std::min<uint32_t>((ntasks + KS_WARPS - 1) / KS_WARPS, (uint32_t)e->num_sms * (uint32_t)B2A_KS_MINB);
         switch (fl) {
 #define B2A_KS_CASE(F) \
   case (F): banded_strip_fill_kernel<(F)><<<sgrid, KS_WARPS * 32, 0, st>>>(sp); break;

@@ -538,7 +538,8 @@ extern "C" int sim_banded_batch(int mode, const sim_scoring* s, uint32_t k, uint
     std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
     std::vector<uint32_t> rng(2 * (n + 1), 0xCDCDCDCDu);
     uint64_t cells = 0;
-    uint32_t shared_u32[2] = {0, 0};
+    std::vector<uint32_t> shared_vec(K4_SHARED_WORDS, 0u);
+    uint32_t* shared_u32 = shared_vec.data();
     const uint32_t st = band_create_d<1>(0, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
                                          rng.data(), &cells, shared_u32);
     num_cells[p] = cells;
@@ -604,7 +605,8 @@ extern "C" int sim_banded_hinted_one(const sim_scoring* s, uint32_t k, uint32_t 
   hint.allowed_mismatches = allowed_mismatches;
   hint.use_lcskpp_union = use_lcskpp_union;
   uint64_t cells = 0;
-  uint32_t shared_u32[2] = {0, 0};
+  std::vector<uint32_t> shared_vec(K4_SHARED_WORDS, 0u);
+    uint32_t* shared_u32 = shared_vec.data();
   const uint32_t st = band_create_d<1>(0, x, m, y, n, k, w, sc, s->has_match_scores, slab.data(), cap_matches,
                                        rng.data(), &cells, shared_u32, hint);
   *num_cells = cells;
@@ -672,7 +674,8 @@ extern "C" int sim_banded_warp32_one(int mode, const sim_scoring* s, uint32_t k,
   hint.have_path = have_path != 0;
   hint.allowed_mismatches = allowed_mismatches;
   hint.use_lcskpp_union = use_lcskpp_union;
-  uint32_t shared_u32[2] = {0, 0};
+  std::vector<uint32_t> shared_vec(K4_SHARED_WORDS, 0u);
+    uint32_t* shared_u32 = shared_vec.data();
   uint32_t st_lane[32];
   uint64_t cells_lane[32];
   auto run32 = [&](std::function<void(int)> body) { LaneFibers::run(body); };
@@ -775,7 +778,8 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
     std::vector<uint8_t> slab(k4_slab_bytes(cap_matches, (uint32_t)std::min(m, n)), (uint8_t)garbage);
     rngs[p].assign(2 * (n + 1), 0xCDCDCDCDu);
     BandHintsD hint;
-    uint32_t shared_u32[2] = {0, 0};
+    std::vector<uint32_t> shared_vec(K4_SHARED_WORDS, 0u);
+    uint32_t* shared_u32 = shared_vec.data();
     uint32_t st_lane[32];
     uint64_t c_lane[32];
     run32([&](int l) {

@@ -10,7 +10,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "sim", "b2a_sim.cpp")
-SO = os.path.join(HERE, "sim", "libb2asim.so")
+_KS_R = os.environ.get("B2A_SIM_KS_R", "")  # dev knob: the strip fill's rows per lane in the host build
+SO = os.path.join(HERE, "sim", "libb2asim%s.so" % (("_r" + _KS_R) if _KS_R else ""))
 DEPS = [SRC] + [os.path.join(ROOT, "rust_bio_b200", "csrc", f)
                 for f in ("b2a_common.cuh", "b2a_coop.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h", "b2a_banded.cuh", "b2a_banded_strip.cuh")]
 
@@ -26,7 +27,7 @@ class SimScoring(C.Structure):
 def build():
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fwrapv", "-fPIC", "-shared",
-                               "-Wno-unknown-pragmas", "-o", SO, SRC])
+                               "-Wno-unknown-pragmas"] + ([f"-DB2A_KS_R={_KS_R}"] if _KS_R else []) + ["-o", SO, SRC])
     return SO
 
 

@@ -1689,11 +1689,11 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   };
   // STRIP: the strip fill's per-strip table, boundary row m-1 and 4-bit traceback (KsLayout, b2a_banded_strip.cuh)
   const uint32_t* ks_tab = nullptr;
-  const int32_t* ks_bnd = nullptr;  // int2 {4*S, 4*I + 2} per column, index j - kc0 + 1
+  const int32_t* ks_bnd = nullptr;  // int4 {4*S, 4*I + 2, column-tracker key, 0} per column, index j - kc0 + 1
   const uint32_t* ks_tb = nullptr;
   if (STRIP) {
     const uint64_t ns = m >= 2 ? (m - 1 + KS_ROWS - 1) / KS_ROWS : 0;
-    const uint64_t o_tab = 0, o_bnd = al16(ns * KS_TAB * 4), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 8);
+    const uint64_t o_tab = 0, o_bnd = al16(ns * KS_TAB * 4), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 16);
     ks_tab = reinterpret_cast<const uint32_t*>(strip_area + o_tab);
     ks_bnd = reinterpret_cast<const int32_t*>(strip_area + o_bnd);
     ks_tb = reinterpret_cast<const uint32_t*>(strip_area + o_tb);
@@ -1818,8 +1818,8 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   } else if constexpr (FASTR < 0) {
     // ---------------------------------------------------------------------------------------------------------
     // Finish pass of the strip-wavefront fill: what the column loop (banded.rs:511-681) does outside the interior
-    // cells 1..m-1 x 1..n-1 -- row 0's cells and its Sn/Ly seed, row m's cells (they start from the column tracker,
-    // which is dead here: the x-suffix clip is), and the x-suffix-clip nibble every column leaves in row m.
+    // cells 1..m-1 x 1..n-1 -- row 0's cells and its Sn/Ly seed, row m's cells (they start from the column tracker the
+    // fill hands over in the boundary row), and the x-suffix-clip nibble every column leaves in row m.
     const int32_t mi = (int32_t)m;
     // (row 0's cells and row m's x-suffix-clip nibbles were written by the initialisation above)
     if (lane == 0 && kc0 <= kc1 && rng[2 * kc0] == 0 && rng[2 * kc0 + 1] > 0) {
@@ -1845,6 +1845,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     if (lane == 0) {
       // (S, I)(m-1, j) from the boundary row the strip fill left, MIN_SCORE outside the band; 32-bit column arithmetic
       const int32_t k0 = (int32_t)kc0, k1 = (int32_t)kc1, m1 = mi - 1;
+      const bool xs_live = xs > DEAD_CLIP;
       auto bnd_SI = [&](int32_t j, int32_t& S_, int32_t& I_) {
         S_ = I_ = MIN_SCORE;
         if (j == 0) {
@@ -1852,7 +1853,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           return;
         }
         if (!((int32_t)rng[2 * j] <= m1 && (int32_t)rng[2 * j + 1] > m1)) return;
-        const int32_t vs = ks_bnd[2 * (j - k0 + 1)], vi = ks_bnd[2 * (j - k0 + 1) + 1];
+        const int32_t vs = ks_bnd[4 * (j - k0 + 1)], vi = ks_bnd[4 * (j - k0 + 1) + 1];
         S_ = vs <= -(1 << 29) ? MIN_SCORE : vs >> 2;
         I_ = vi <= -(1 << 29) ? MIN_SCORE : vi >> 2;
       };
@@ -1886,7 +1887,16 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           dbm = ((uint32_t)rowm[j - 1] >> 8) & 15u;  // s-bits of (m, j-1) as stored so far
         }
         sbm = TB_XCLIP_SUFFIX;
-        int32_t b = MIN_SCORE;  // the column tracker: dead (x-suffix clip), below every real candidate
+        // the cell starts from the column tracker (645-653): the first interior band row with the highest S + xs, from
+        // the boundary row's packed key; with a dead x-suffix clip it stays below every real candidate
+        int32_t b = MIN_SCORE;
+        if (xs_live && (int32_t)rng[2 * j] <= m1) {  // (row m in the band and the band's start above it: row m-1 is in it)
+          const int32_t key = ks_bnd[4 * (j - k0 + 1) + 2];
+          if (key != (int32_t)0x80000000) {
+            b = (key >> 12) + xs;
+            Lx[j] = (uint32_t)(mi - (4095 - (key & 4095)));
+          }
+        }
         if (m_sc > b) {
           b = m_sc;
           sbm = (p == q) ? TB_MATCH : TB_SUBST;

@@ -27,9 +27,11 @@
 //   * row 0, column 0, row m (which starts from the column tracker), column n, the end-of-matrix passes and the
 //     walk stay in the finish pass; this kernel leaves it the boundary row m-1 (S, I per column), Sn/Ly, the
 //     (i, n) marks, the per-strip windows and the 4-bit traceback.
-// Not handled here (K4 / the host do not mark such pairs): a live x-suffix clip (column tracker), tabulated
-// MatchFunc scoring, row trackers when the y-prefix clip is dead or scores exceed 2^17, a band that reaches
-// column n, gaps inside the band's column range.
+//   * the column tracker S[m] / Lx (648-653, live with the x-suffix clip: local mode) as K1's packed key
+//     4096*S + (4095 - row), handed down the lanes and through the boundary row; it needs x no longer than 4,095;
+// Not handled here (K4 / the host do not mark such pairs): tabulated MatchFunc scoring, trackers when the y-prefix
+// clip is dead, scores exceed 2^17 or (column tracker) x is longer than 4,095, a band that reaches column n, gaps
+// inside the band's column range.
 #pragma once
 #include "b2a_banded.cuh"
 #include "b2a_fill.cuh"
@@ -38,7 +40,7 @@ namespace b2a {
 
 enum : int { F_CLIPY = 64 };  // y-prefix clip live (with F_CLIPX / F_TRACK_ROWS of b2a_common.cuh)
 
-// per-pair strip area: [strip table: nstrips x {ja, traceback offset in uint4 units, steps stored, 0}][boundary row: (cols+2) x int2][traceback]
+// per-pair strip area: [strip table: nstrips x {ja, traceback offset in uint4 units, steps stored, 0}][boundary row: (cols+2) x int4 {4S, 4I+2, column-tracker key, 0}][traceback]
 struct KsLayout {
   uint64_t tab, bnd, tb, total;
 };
@@ -48,7 +50,7 @@ B2A_HD KsLayout ks_layout(uint64_t m, uint64_t band_cols, uint64_t strip_cols) {
   const uint64_t ns = ks_nstrips(m);
   uint64_t b = 0;
   L.tab = b; b = al16(b + ns * KS_TAB * 4);
-  L.bnd = b; b = al16(b + (band_cols + 2) * 8);
+  L.bnd = b; b = al16(b + (band_cols + 2) * 16);
   L.tb = b;
   // a strip of `len` columns stores ceil((len + 14) / 8) groups of 8 steps, KS_TBW x KS_G uint4 each
   b += (strip_cols / 8 + 3 * ns) * (uint64_t)(KS_TBW * KS_G * 16);
@@ -119,7 +121,7 @@ struct KsPair {
   uint32_t* Ly;
   uint16_t* coln;
   uint32_t* tab;      // strip table
-  int2* bnd;          // boundary row, indexed by j - c0 + 1
+  int4* bnd;          // boundary row, indexed by j - c0 + 1
   uint4* tb;
 };
 
@@ -127,9 +129,10 @@ template <int FLAGS, bool LASTSTRIP>
 B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_t ge4, const int32_t j, const int32_t q,
                            const int32_t a_band, const uint32_t h_band, const int32_t cjkey, const int32_t y4_first,
                            int32_t (&Sp)[KS_R], int32_t (&Dp)[KS_R], int32_t (&SnR)[KS_R], uint32_t (&tbacc)[KS_R],
-                           const int32_t (&xc)[KS_R], const int32_t sdiag, int32_t& sup, int32_t& iup,
-                           const int32_t cap_row, int32_t& cap_s, int32_t& cap_i) {
+                           const int32_t (&xc)[KS_R], const int32_t sdiag, int32_t& sup, int32_t& iup, int32_t& Tv,
+                           const int32_t rowbase, const int32_t cap_row, int32_t& cap_s, int32_t& cap_i) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
+  constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool CX = (FLAGS & F_CLIPX) != 0;
   constexpr bool CY = (FLAGS & F_CLIPY) != 0;
   const int32_t go4i = 4 * sc.gap_open + 2, go4d = 4 * sc.gap_open + 1;
@@ -139,6 +142,7 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
   int32_t sdo = fmad(sdiag, one, go4d);
   int32_t iop = fmad(sup, one, go4i);
   int32_t s4 = sup;
+  int32_t Tl = KEY_NONE;  // packed column tracker of this lane's band rows (local row index), as in K1
 #pragma unroll
   for (int r = 0; r < KS_R; ++r) {
     const int32_t sub4 = (xc[r] == q) ? ma4 : mi4;
@@ -163,6 +167,9 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
     if (TR) {
       if (inb) SnR[r] = imax(SnR[r], fmad(s4, k1024, cjkey));
     }
+    if (TC) {  // banded.rs:648-653: the first band row with the highest S + xs
+      if (inb) Tl = imax(Tl, fmad(s4, k1024, 4095 - r));
+    }
     if (LASTSTRIP) {
       if (r == cap_row) {
         cap_s = s4;
@@ -176,6 +183,9 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
     iup = i4;
   }
   sup = s4;
+  if (TC) {
+    if (Tl != KEY_NONE) Tv = imax(Tv, Tl - (rowbase + 1));  // local row index -> 4095 - i
+  }
 }
 
 // S(0, j) of the banded aligner for 1 <= j < n (banded.rs:523-545), scaled; row 0 has to be in the band there
@@ -208,6 +218,7 @@ template <int FLAGS, bool LASTSTRIP>
 B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t one, const int32_t ge4, const int32_t lane,
                          const int32_t s, int32_t& prev_ja, int32_t& prev_jb, uint32_t& tb_used, bool& redo) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
+  constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   const int32_t l = lane % KS_G;
   const int32_t m = P.m, n = P.n;
   const bool have = m >= 2 && s < (int32_t)ks_nstrips((uint64_t)m);
@@ -255,64 +266,77 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
   const bool writer = have && (my_last ? cap_row >= 0 : l == KS_G - 1);
   // S(i0, ja-1) for the first row's diagonal: row 0 (strip 0) or the boundary row of the strip above
   int32_t sup_prev = NEG4;
-  int32_t in_s = NEG4, in_i = NEG4 + 2;
+  int32_t in_s = NEG4, in_i = NEG4 + 2, in_tv = KEY_NONE;
   const bool top_row0 = have && l == 0 && s == 0, top_mem = have && l == 0 && s > 0;
   if (len > 0 && top_row0) {
     const int32_t jp = ja - 1;
     if (jp == 0) sup_prev = (s0 == 0 && e0 > 0) ? 0 : NEG4;
     else sup_prev = P.rng[2 * jp] == 0 ? ks_row0_S4(sc, jp) : NEG4;
   }
-  auto bnd_at = [&](int32_t j) -> int2 {  // the boundary row the strip above left (its window: [prev_ja, prev_jb])
+  auto bnd_at = [&](int32_t j) -> int4 {  // the boundary row the strip above left (its window: [prev_ja, prev_jb])
     if (j >= prev_ja && j <= prev_jb) return P.bnd[j - P.c0 + 1];
-    int2 v;
-    v.x = NEG4;
-    v.y = NEG4 + 2;
-    return v;
+    return make_int4(NEG4, NEG4 + 2, KEY_NONE, 0);
   };
-  int2 pre;
-  pre.x = NEG4;
-  pre.y = NEG4 + 2;
+  int4 pre = make_int4(NEG4, NEG4 + 2, KEY_NONE, 0);
   if (len > 0 && top_mem) {
     sup_prev = bnd_at(ja - 1).x;
     pre = bnd_at(ja);
   }
   int32_t cap_s = NEG4, cap_i = NEG4 + 2;
   const int32_t y4_row0 = 4 * (sc.yclip_prefix + sc.gap_open) + ge4 * rowbase;  // 4 * yclip_score(rowbase + 1)
+  // the column's band range and y symbol are requested one step ahead (the loads are L1 hits, but with three warps
+  // per scheduler their latency showed up as a quarter of the stall samples when they were issued where they are used)
+  int32_t nsj = 0, nej = 0, nq = 0;
+  auto fetch_col = [&](int32_t jr) {
+    if (jr >= 0 && jr < len) {
+      const int32_t j = ja + jr;
+      nsj = (int32_t)P.rng[2 * j];
+      nej = (int32_t)P.rng[2 * j + 1];
+      nq = (int32_t)P.y[j - 1];
+    }
+  };
+  fetch_col(-l);
   for (int32_t t = 0; t < nsteps; ++t) {
     const int32_t jr = t - l;  // column offset inside the window
     const bool active = jr >= 0 && jr < len;
+    const int32_t sj = nsj, ej = nej, q = nq;
+    fetch_col(jr + 1);
     if (active) {
       const int32_t j = ja + jr;
-      const int32_t sj = (int32_t)P.rng[2 * j], ej = (int32_t)P.rng[2 * j + 1];
-      const int32_t q = (int32_t)P.y[j - 1];
       const int32_t top = imin(ej, m) - sj;  // rows [sj, min(ej, m)) are cells of this kernel (row m is the finish pass's)
       const uint32_t h_band = top > 0 ? (uint32_t)top : 0u;
       if (top_row0) {
         in_s = (sj == 0 && ej > 0) ? ks_row0_S4(sc, j) : NEG4;
         in_i = NEG4 + 2;
+        in_tv = KEY_NONE;
       } else if (top_mem) {
         in_s = pre.x;
         in_i = pre.y;
+        in_tv = pre.z;
         if (jr + 1 < len) pre = bnd_at(j + 1);
       }
-      int32_t sup = in_s, iup = in_i;
+      int32_t sup = in_s, iup = in_i, Tv = in_tv;
       ks_column_step<FLAGS, LASTSTRIP>(sc, one, ge4, j, q, rowbase + 1 - sj, h_band, 4095 - jr, y4_row0, Sp, Dp, SnR,
-                                       tbacc, xc, sup_prev, sup, iup, cap_row, cap_s, cap_i);
+                                       tbacc, xc, sup_prev, sup, iup, Tv, rowbase, cap_row, cap_s, cap_i);
       sup_prev = in_s;
       if (writer) {
-        int2 o;
+        int4 o;
         o.x = (my_last && cap_row != KS_R - 1) ? cap_s : sup;
         o.y = (my_last && cap_row != KS_R - 1) ? cap_i : iup;
+        o.z = TC ? Tv : KEY_NONE;  // (the rows below row m-1 are outside the band: the capture lane's tracker is complete)
+        o.w = 0;
         P.bnd[j - P.c0 + 1] = o;
       }
       in_s = sup;
       in_i = iup;
+      in_tv = Tv;
     } else {
 #pragma unroll
       for (int r = 0; r < KS_R; ++r) tbacc[r] <<= 4;
     }
     in_s = B2A_SHFL_UP(in_s, KS_G);
     in_i = B2A_SHFL_UP(in_i, KS_G);
+    if (TC) in_tv = B2A_SHFL_UP(in_tv, KS_G);
     if ((t & 7) == 7 && (uint32_t)(t >> 3) < K) {
       uint4* dst = tbs + (size_t)(t >> 3) * KS_TBW * KS_G + l;
 #pragma unroll
@@ -378,7 +402,7 @@ B2A_HD void ks_run_task(const StripParams& prm, const uint32_t task, const int l
     const KsLayout S = ks_layout((uint64_t)P.m, (uint64_t)(P.c1 >= P.c0 ? P.c1 - P.c0 + 1 : 0), prm.band_cols[3 * pair + 2]);
     uint8_t* area = prm.strip + prm.strip_off[t];
     P.tab = reinterpret_cast<uint32_t*>(area + S.tab);
-    P.bnd = reinterpret_cast<int2*>(area + S.bnd);
+    P.bnd = reinterpret_cast<int4*>(area + S.bnd);
     P.tb = reinterpret_cast<uint4*>(area + S.tb);
   }
   const int32_t ns = (int32_t)ks_nstrips((uint64_t)P.m);

@@ -1530,16 +1530,15 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   bp.num_cells = e->d_bcells.as<uint64_t>();
   bp.k4_status = e->d_bstatus.as<uint32_t>();
   bp.band_cols = e->d_bcols.as<uint32_t>();
-  // The strip-wavefront fill (b2a_banded_strip.cuh) covers: MatchParams scoring, a dead x-suffix clip (no column
-  // tracker), every real score within +-2^26 (its sentinel arithmetic), and row trackers only as packed keys
-  // (y-suffix clip live => y-prefix clip live, so that every band cell's S is real, and scores below 2^17).
+  // The strip-wavefront fill (b2a_banded_strip.cuh) covers: MatchParams scoring and every real score within +-2^26
+  // (its sentinel arithmetic); row / column trackers only as packed keys (below).
   {
     const bool xs_dead = e->sc.xclip_suffix <= DEAD_CLIP, ys_dead = e->sc.yclip_suffix <= DEAD_CLIP;
     const bool yp_live = e->sc.yclip_prefix > DEAD_CLIP;
-    bp.strip_ok = (e->banded_strip && e->banded_fast && !s->table && xs_dead && score_bound < (1ll << 26) &&
-                   (ys_dead || (yp_live && score_bound < (1ll << 17))))
-                      ? 1
-                      : 0;
+    // trackers are packed keys: every band cell's S has to be real (a live y-prefix clip guarantees it: S >=
+    // yclip_score(i)) and below 2^17; the column tracker's key also holds the row (x no longer than 4,095)
+    const bool trackers_ok = (xs_dead && ys_dead) || (yp_live && score_bound < (1ll << 17) && (xs_dead || maxm <= 4095));
+    bp.strip_ok = (e->banded_strip && e->banded_fast && !s->table && score_bound < (1ll << 26) && trackers_ok) ? 1 : 0;
   }
   e->strip_pairs = 0;
   bp.filter_clips = (mode == B2A_MODE_SEMIGLOBAL || mode == B2A_MODE_LOCAL) ? 1 : 0;
@@ -1683,8 +1682,8 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
         sp.sc = e->sc;
         sp.one = 1;
         sp.ge4 = 4 * e->sc.gap_extend;
-        const int fl = (e->sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (e->sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) |
-                       (e->sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+        const int fl = (e->sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (e->sc.xclip_suffix > DEAD_CLIP ? (int)F_TRACK_COLS : 0) |
+                       (e->sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (e->sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
         sp.flags = fl;
         CK(cudaMemsetAsync(sp.task_counter, 0, 4, st));
         const uint32_t ntasks = (sp.n_elig + 3) / 4;
@@ -1700,6 +1699,14 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
           B2A_KS_CASE(F_TRACK_ROWS | F_CLIPY)
           B2A_KS_CASE(F_CLIPX | F_CLIPY)
           B2A_KS_CASE(F_TRACK_ROWS | F_CLIPX | F_CLIPY)
+          B2A_KS_CASE(F_TRACK_COLS)
+          B2A_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS)
+          B2A_KS_CASE(F_TRACK_COLS | F_CLIPX)
+          B2A_KS_CASE(F_TRACK_COLS | F_CLIPY)
+          B2A_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX)
+          B2A_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPY)
+          B2A_KS_CASE(F_TRACK_COLS | F_CLIPX | F_CLIPY)
+          B2A_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX | F_CLIPY)
 #undef B2A_KS_CASE
           default: return e->fail(B2A_E_INVALID, "banded strip fill: unexpected flag set");
         }

@@ -764,7 +764,9 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
   auto run32 = [&](std::function<void(int)> body) { LaneFibers::run(body); };
   // the host's part of the decision (b2a_engine.cu banded_impl)
   const bool xs_dead = sc.xclip_suffix <= DEAD_CLIP, ys_dead = sc.yclip_suffix <= DEAD_CLIP, yp_live = sc.yclip_prefix > DEAD_CLIP;
-  const bool batch_ok = xs_dead && (ys_dead || yp_live);
+  uint32_t maxm = 0;
+  for (uint32_t p = 0; p < n_pairs; ++p) maxm = std::max(maxm, x_len[p]);
+  const bool batch_ok = (xs_dead && ys_dead) || (yp_live && (xs_dead || maxm <= 4095));
   std::vector<std::vector<uint32_t>> rngs(n_pairs);
   std::vector<uint64_t> cells(n_pairs, 0);
   std::vector<uint32_t> cols(3 * (size_t)n_pairs + 3, 0), k4(n_pairs, 0), elig;
@@ -842,8 +844,8 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
   sp.sc = sc;
   sp.one = 1;
   sp.ge4 = 4 * sc.gap_extend;
-  const int fl = (sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) |
-                 (sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+  const int fl = (sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (sc.xclip_suffix > DEAD_CLIP ? (int)F_TRACK_COLS : 0) |
+                 (sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
   run32([&](int l) {
     switch (fl) {
 #define SIM_KS_CASE(F) \
@@ -856,6 +858,14 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
       SIM_KS_CASE(F_TRACK_ROWS | F_CLIPY)
       SIM_KS_CASE(F_CLIPX | F_CLIPY)
       SIM_KS_CASE(F_TRACK_ROWS | F_CLIPX | F_CLIPY)
+      SIM_KS_CASE(F_TRACK_COLS)
+      SIM_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS)
+      SIM_KS_CASE(F_TRACK_COLS | F_CLIPX)
+      SIM_KS_CASE(F_TRACK_COLS | F_CLIPY)
+      SIM_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX)
+      SIM_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPY)
+      SIM_KS_CASE(F_TRACK_COLS | F_CLIPX | F_CLIPY)
+      SIM_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX | F_CLIPY)
 #undef SIM_KS_CASE
     }
   });

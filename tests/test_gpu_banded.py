@@ -415,14 +415,15 @@ def test_register_resident_k3_equals_literal_k3_and_oracle(oracle, mode, monkeyp
         lit_eng.close()
 
 
-@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "custom_xy"])
+@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "custom_xy", "local", "custom_xs"])
 def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monkeypatch):
     """K3s (b2a_banded_strip.cuh: the packed cell of K1 on fixed 128-row strips with a band mask, four pairs to a
     warp, 4-bit traceback, finish pass) against the K3 column loops (B2A_BANDED_STRIP=0) and the oracle: ragged
     batches (1-5 strips per pair), gap_open > gap_extend cases, y clips with different penalties, both prefix
-    clips live (their shared priority code).  The path must have taken most of the semiglobal pairs."""
+    clips live (their shared priority code), local mode and a custom x-suffix clip (the column tracker).  The path
+    must have taken most of the semiglobal and local pairs."""
     from rust_bio_b200.engine import Engine
-    rng = np.random.default_rng({"semiglobal": 41, "custom_y": 42, "custom_xy": 43}[mode])
+    rng = np.random.default_rng({"semiglobal": 41, "custom_y": 42, "custom_xy": 43, "local": 44, "custom_xs": 45}[mode])
     strip_eng = Engine(0)
     monkeypatch.setenv("B2A_BANDED_STRIP", "0")
     loop_eng = Engine(0)
@@ -436,6 +437,11 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
                 omode, clips = "semiglobal", (MIN,) * 4
             elif mode == "custom_y":
                 omode, clips = "custom", (MIN, MIN, int(rng.choice([0, -2, -7])), int(rng.choice([0, -1, -6])))
+            elif mode == "local":      # row and column trackers, both prefix clip terms
+                omode, clips = "local", (MIN,) * 4
+            elif mode == "custom_xs":  # the column tracker with its own penalty
+                omode, clips = "custom", (int(rng.choice([MIN, 0, -3])), int(rng.choice([0, -2, -5])), int(rng.choice([0, -1])),
+                                          int(rng.choice([MIN, 0, -4])))
             else:
                 omode, clips = "custom", (int(rng.choice([0, -2, -8])), MIN, int(rng.choice([0, -3])), int(rng.choice([0, -4])))
             k, w = int(rng.choice([4, 6, 9])), int(rng.choice([3, 8, 20, 45]))
@@ -461,7 +467,7 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
             for p in range(0, 203, 7):
                 want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
                 assert a.ops_of(p) == want, (mode, trial, p)
-        if mode == "semiglobal":
+        if mode in ("semiglobal", "local"):
             assert taken * 2 >= total, (taken, total)
     finally:
         strip_eng.close()

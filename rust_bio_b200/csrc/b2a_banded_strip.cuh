@@ -29,9 +29,10 @@
 //     (i, n) marks, the per-strip windows and the 4-bit traceback.
 //   * the column tracker S[m] / Lx (648-653, live with the x-suffix clip: local mode) as K1's packed key
 //     4096*S + (4095 - row), handed down the lanes and through the boundary row; it needs x no longer than 4,095;
-// Not handled here (K4 / the host do not mark such pairs): tabulated MatchFunc scoring, trackers when the y-prefix
-// clip is dead, scores exceed 2^17 or (column tracker) x is longer than 4,095, a band that reaches column n, gaps
-// inside the band's column range.
+//   * substitution scores by MatchParams compare / select, or (F_LUT: a tabulated MatchFunc such as BLOSUM62) from
+//     K1's scaled LUT in shared memory with the sequence bytes mapped to LUT codes as they are loaded;
+// Not handled here (K4 / the host do not mark such pairs): trackers when the y-prefix clip is dead, scores exceed
+// 2^17 or (column tracker) x is longer than 4,095, a band that reaches column n, gaps inside the band's column range.
 #pragma once
 #include "b2a_banded.cuh"
 #include "b2a_fill.cuh"
@@ -77,6 +78,9 @@ struct StripParams {
   const uint64_t* num_cells;   // per pair (batch index)
   const uint32_t* band_cols;   // per pair (batch index): {first, last non-empty column, strip columns}
   uint32_t* k4_status;         // per pair (batch index): bit 10 = hand the pair to the literal kernel
+  const int32_t* lut;          // tabulated MatchFunc (F_LUT): K1's scaled LUT 4*score + 3 - (4*gap_open + 1), sc.alpha^2 entries
+  const uint8_t* codemap;      // byte -> LUT code, 0xFF = not in the scoring alphabet
+  uint32_t* err_flag;          // bit 2: a sequence byte outside the scoring alphabet
   DevScoring sc;
   int32_t one, ge4;            // opaque 1 and 4 * gap_extend (see b2a_fill.cuh)
   int32_t flags;
@@ -125,8 +129,16 @@ struct KsPair {
   uint4* tb;
 };
 
+// scoring tables of a task (F_LUT): shared memory on the device, plain memory in the host build
+struct KsLut {
+  const int32_t* lut;     // host build: base of the scaled LUT
+  uint32_t lut_base;      // device: shared-space byte address of the LUT (0 in the host build)
+  const uint8_t* cmap;    // byte -> code
+  uint32_t* err_flag;
+};
+
 template <int FLAGS, bool LASTSTRIP>
-B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_t ge4, const int32_t j, const int32_t q,
+B2A_HD void ks_column_step(const DevScoring& sc, const KsLut& T, const int32_t one, const int32_t ge4, const int32_t j, const int32_t q,
                            const int32_t a_band, const uint32_t h_band, const int32_t cjkey, const int32_t y4_first,
                            int32_t (&Sp)[KS_R], int32_t (&Dp)[KS_R], int32_t (&SnR)[KS_R], uint32_t (&tbacc)[KS_R],
                            const int32_t (&xc)[KS_R], const int32_t sdiag, int32_t& sup, int32_t& iup, int32_t& Tv,
@@ -135,6 +147,7 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool CX = (FLAGS & F_CLIPX) != 0;
   constexpr bool CY = (FLAGS & F_CLIPY) != 0;
+  constexpr bool LUT = (FLAGS & F_LUT) != 0;
   const int32_t go4i = 4 * sc.gap_open + 2, go4d = 4 * sc.gap_open + 1;
   const int32_t ma4 = 4 * sc.match_score + 3 - go4d, mi4 = 4 * sc.mismatch_score + 3 - go4d;
   const int32_t x4 = CX ? scale4(xclip_score(sc, j)) : NEG4;
@@ -145,7 +158,8 @@ B2A_HD void ks_column_step(const DevScoring& sc, const int32_t one, const int32_
   int32_t Tl = KEY_NONE;  // packed column tracker of this lane's band rows (local row index), as in K1
 #pragma unroll
   for (int r = 0; r < KS_R; ++r) {
-    const int32_t sub4 = (xc[r] == q) ? ma4 : mi4;
+    // LUT: xc[r] is the byte address of the row symbol's LUT row, q the column symbol's byte offset inside a row
+    const int32_t sub4 = LUT ? lut_at(T.lut, (uint32_t)fmad(q, one, xc[r])) : ((xc[r] == q) ? ma4 : mi4);
     const int32_t m4 = fmad(sdo, one, sub4);
     int32_t i4 = addmax(iup, ge4, iop);
     const int32_t dop = Sp[r];
@@ -215,10 +229,23 @@ B2A_HD int32_t ks_last_col_start_upto(const uint32_t* rng, int32_t lo, int32_t h
 // One strip of one task (four pairs, 8 lanes each).  `s` is the strip index, the same for the four pairs; a pair
 // with fewer strips idles.  Returns, per lane group, the uint4 units its strip used (for the strip table).
 template <int FLAGS, bool LASTSTRIP>
-B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t one, const int32_t ge4, const int32_t lane,
+B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const KsLut& T, const int32_t one, const int32_t ge4, const int32_t lane,
                          const int32_t s, int32_t& prev_ja, int32_t& prev_jb, uint32_t& tb_used, bool& redo) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
+  constexpr bool LUT = (FLAGS & F_LUT) != 0;
+  auto code_of = [&](uint8_t byte) -> int32_t {  // LUT code of a sequence byte; a byte outside the alphabet is flagged
+    int32_t c = (int32_t)T.cmap[byte];
+    if (c == 0xFF) {
+#if defined(__CUDA_ARCH__)
+      atomicOr(T.err_flag, 4u);
+#else
+      *T.err_flag |= 4u;
+#endif
+      c = 0;
+    }
+    return c;
+  };
   const int32_t l = lane % KS_G;
   const int32_t m = P.m, n = P.n;
   const bool have = m >= 2 && s < (int32_t)ks_nstrips((uint64_t)m);
@@ -251,6 +278,7 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
   for (int r = 0; r < KS_R; ++r) {
     const int32_t i = rowbase + 1 + r;
     xc[r] = (have && i <= m) ? (int32_t)P.x[i - 1] : 0;
+    if (LUT) xc[r] = (int32_t)(T.lut_base + (uint32_t)(((have && i <= m) ? code_of((uint8_t)xc[r]) : 0) * sc.alpha * 4));
     // the column before the window: outside the band, except column 0 when the window starts at column 1
     const bool in0 = have && ja == 1 && i < m && (uint32_t)i >= s0 && (uint32_t)i < e0;
     Sp[r] = (in0 ? 4 * col0_S(sc, i) : NEG4) + (4 * sc.gap_open + 1);
@@ -293,6 +321,7 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
       nsj = (int32_t)P.rng[2 * j];
       nej = (int32_t)P.rng[2 * j + 1];
       nq = (int32_t)P.y[j - 1];
+      if (LUT) nq = code_of((uint8_t)nq) * 4;
     }
   };
   fetch_col(-l);
@@ -316,7 +345,7 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
         if (jr + 1 < len) pre = bnd_at(j + 1);
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv;
-      ks_column_step<FLAGS, LASTSTRIP>(sc, one, ge4, j, q, rowbase + 1 - sj, h_band, 4095 - jr, y4_row0, Sp, Dp, SnR,
+      ks_column_step<FLAGS, LASTSTRIP>(sc, T, one, ge4, j, q, rowbase + 1 - sj, h_band, 4095 - jr, y4_row0, Sp, Dp, SnR,
                                        tbacc, xc, sup_prev, sup, iup, Tv, rowbase, cap_row, cap_s, cap_i);
       sup_prev = in_s;
       if (writer) {
@@ -378,7 +407,7 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const int32_t on
 }
 
 template <int FLAGS>
-B2A_HD void ks_run_task(const StripParams& prm, const uint32_t task, const int lane) {
+B2A_HD void ks_run_task(const StripParams& prm, const KsLut& T, const uint32_t task, const int lane) {
   const int32_t g = lane / KS_G;
   const uint32_t slot = task * 4 + (uint32_t)g;
   KsPair P{};
@@ -413,8 +442,8 @@ B2A_HD void ks_run_task(const StripParams& prm, const uint32_t task, const int l
   for (int32_t s = 0; s < ns_max; ++s) {
     // the capture of row m-1 costs three instructions per cell: only the warp's passes that hold a pair's last strip pay it
     const bool any_last = ks_warp_max((P.m >= 2 && s == ns - 1) ? 1 : 0) != 0;
-    if (any_last) ks_run_strip<FLAGS, true>(P, prm.sc, prm.one, prm.ge4, lane, s, prev_ja, prev_jb, tb_used, redo);
-    else ks_run_strip<FLAGS, false>(P, prm.sc, prm.one, prm.ge4, lane, s, prev_ja, prev_jb, tb_used, redo);
+    if (any_last) ks_run_strip<FLAGS, true>(P, prm.sc, T, prm.one, prm.ge4, lane, s, prev_ja, prev_jb, tb_used, redo);
+    else ks_run_strip<FLAGS, false>(P, prm.sc, T, prm.one, prm.ge4, lane, s, prev_ja, prev_jb, tb_used, redo);
   }
   if (redo && P.m >= 2 && lane % KS_G == 0) prm.k4_status[pair] |= 0x400u;
 }
@@ -426,16 +455,32 @@ B2A_HD void ks_run_task(const StripParams& prm, const uint32_t task, const int l
 #endif
 constexpr int KS_WARPS = 4;
 
+// dynamic shared memory of a CTA (F_LUT only): the scaled LUT, then the 256-byte code map
+B2A_HD uint32_t ks_smem_bytes(int flags, int alpha) { return (flags & F_LUT) ? lut_smem_bytes(alpha) + 256u : 0u; }
+
 template <int FLAGS>
 __global__ void __launch_bounds__(KS_WARPS * 32, B2A_KS_MINB) banded_strip_fill_kernel(const StripParams prm) {
+  extern __shared__ __align__(128) uint8_t ks_smem[];
   const int lane = threadIdx.x & 31;
+  KsLut T{};
+  if (FLAGS & F_LUT) {
+    int32_t* lut_s = reinterpret_cast<int32_t*>(ks_smem);
+    uint8_t* cmap_s = ks_smem + lut_smem_bytes(prm.sc.alpha);
+    for (int k = threadIdx.x; k < prm.sc.alpha * prm.sc.alpha; k += blockDim.x) lut_s[k] = prm.lut[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) cmap_s[k] = prm.codemap[k];
+    __syncthreads();
+    T.lut = lut_s;
+    T.lut_base = (uint32_t)__cvta_generic_to_shared(lut_s);
+    T.cmap = cmap_s;
+    T.err_flag = prm.err_flag;
+  }
   const uint32_t ntasks = (prm.n_elig + 3) / 4;
   for (;;) {
     uint32_t task = 0;
     if (lane == 0) task = atomicAdd(prm.task_counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= ntasks) break;
-    ks_run_task<FLAGS>(prm, task, lane);
+    ks_run_task<FLAGS>(prm, T, task, lane);
     __syncwarp();
   }
 }

@@ -1530,15 +1530,15 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
   bp.num_cells = e->d_bcells.as<uint64_t>();
   bp.k4_status = e->d_bstatus.as<uint32_t>();
   bp.band_cols = e->d_bcols.as<uint32_t>();
-  // The strip-wavefront fill (b2a_banded_strip.cuh) covers: MatchParams scoring and every real score within +-2^26
-  // (its sentinel arithmetic); row / column trackers only as packed keys (below).
+  // The strip-wavefront fill (b2a_banded_strip.cuh) covers every real score within +-2^26 (its sentinel
+  // arithmetic); row / column trackers only as packed keys (below).
   {
     const bool xs_dead = e->sc.xclip_suffix <= DEAD_CLIP, ys_dead = e->sc.yclip_suffix <= DEAD_CLIP;
     const bool yp_live = e->sc.yclip_prefix > DEAD_CLIP;
     // trackers are packed keys: every band cell's S has to be real (a live y-prefix clip guarantees it: S >=
     // yclip_score(i)) and below 2^17; the column tracker's key also holds the row (x no longer than 4,095)
     const bool trackers_ok = (xs_dead && ys_dead) || (yp_live && score_bound < (1ll << 17) && (xs_dead || maxm <= 4095));
-    bp.strip_ok = (e->banded_strip && e->banded_fast && !s->table && score_bound < (1ll << 26) && trackers_ok) ? 1 : 0;
+    bp.strip_ok = (e->banded_strip && e->banded_fast && score_bound < (1ll << 26) && trackers_ok) ? 1 : 0;
   }
   e->strip_pairs = 0;
   bp.filter_clips = (mode == B2A_MODE_SEMIGLOBAL || mode == B2A_MODE_LOCAL) ? 1 : 0;
@@ -1680,17 +1680,27 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
         sp.band_cols = bp.band_cols;
         sp.k4_status = bp.k4_status;
         sp.sc = e->sc;
+        sp.lut = s->table ? e->d_lut.as<int32_t>() + (size_t)e->sc.alpha * e->sc.alpha : nullptr;  // K1's scaled copy
+        sp.codemap = bp.codemap;
+        sp.err_flag = ctl + 1;
         sp.one = 1;
         sp.ge4 = 4 * e->sc.gap_extend;
         const int fl = (e->sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (e->sc.xclip_suffix > DEAD_CLIP ? (int)F_TRACK_COLS : 0) |
-                       (e->sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (e->sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+                       (e->sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (e->sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0) |
+                       (s->table ? (int)F_LUT : 0);
         sp.flags = fl;
         CK(cudaMemsetAsync(sp.task_counter, 0, 4, st));
         const uint32_t ntasks = (sp.n_elig + 3) / 4;
         const unsigned sgrid = (unsigned)std::min<uint32_t>((ntasks + KS_WARPS - 1) / KS_WARPS, (uint32_t)e->num_sms * (uint32_t)B2A_KS_MINB);
+        const size_t ks_smem = ks_smem_bytes(fl, e->sc.alpha);
         switch (fl) {
-#define B2A_KS_CASE(F) \
-  case (F): banded_strip_fill_kernel<(F)><<<sgrid, KS_WARPS * 32, 0, st>>>(sp); break;
+#define B2A_KS_CASE1(F)                                                                                                   \
+  case (F):                                                                                                               \
+    if (ks_smem > 48 * 1024)                                                                                              \
+      CK(cudaFuncSetAttribute(banded_strip_fill_kernel<(F)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ks_smem)); \
+    banded_strip_fill_kernel<(F)><<<sgrid, KS_WARPS * 32, ks_smem, st>>>(sp);                                             \
+    break;
+#define B2A_KS_CASE(F) B2A_KS_CASE1(F) B2A_KS_CASE1((F) | F_LUT)
           B2A_KS_CASE(0)
           B2A_KS_CASE(F_TRACK_ROWS)
           B2A_KS_CASE(F_CLIPX)
@@ -1708,6 +1718,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
           B2A_KS_CASE(F_TRACK_COLS | F_CLIPX | F_CLIPY)
           B2A_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX | F_CLIPY)
 #undef B2A_KS_CASE
+#undef B2A_KS_CASE1
           default: return e->fail(B2A_E_INVALID, "banded strip fill: unexpected flag set");
         }
         CK(cudaGetLastError());

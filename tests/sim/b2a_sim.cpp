@@ -760,8 +760,29 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
   if (mode == 3) sc.xclip_prefix = sc.xclip_suffix = sc.yclip_prefix = sc.yclip_suffix = 0;
   sc.match_score = s->match_score;
   sc.mismatch_score = s->mismatch_score;
-  if (s->table) return -3;
+  const int32_t* table = s->table;
   auto run32 = [&](std::function<void(int)> body) { LaneFibers::run(body); };
+  // tabulated MatchFunc: codes over the bytes present and K1's scaled LUT, as the engine's stage_front builds them
+  std::vector<uint8_t> cmap(256, 0xFF);
+  std::vector<int32_t> lut_scaled;
+  if (table) {
+    std::vector<bool> present(256, false);
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+      for (uint32_t t = 0; t < x_len[p]; ++t) present[blob[x_off[p] + t]] = true;
+      for (uint32_t t = 0; t < y_len[p]; ++t) present[blob[y_off[p] + t]] = true;
+    }
+    std::vector<int> syms;
+    for (int b = 0; b < 256; ++b)
+      if (present[b]) syms.push_back(b);
+    if (syms.empty()) syms.push_back(0);
+    if (syms.size() > 128) return -3;
+    sc.alpha = (int32_t)syms.size();
+    for (int a = 0; a < sc.alpha; ++a) cmap[syms[a]] = (uint8_t)a;
+    lut_scaled.resize((size_t)sc.alpha * sc.alpha);
+    for (int a = 0; a < sc.alpha; ++a)
+      for (int b = 0; b < sc.alpha; ++b)
+        lut_scaled[(size_t)a * sc.alpha + b] = 4 * table[(size_t)syms[a] * 256 + syms[b]] + 3 - (4 * sc.gap_open + 1);
+  }
   // the host's part of the decision (b2a_engine.cu banded_impl)
   const bool xs_dead = sc.xclip_suffix <= DEAD_CLIP, ys_dead = sc.yclip_suffix <= DEAD_CLIP, yp_live = sc.yclip_prefix > DEAD_CLIP;
   uint32_t maxm = 0;
@@ -845,11 +866,20 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
   sp.one = 1;
   sp.ge4 = 4 * sc.gap_extend;
   const int fl = (sc.yclip_suffix > DEAD_CLIP ? (int)F_TRACK_ROWS : 0) | (sc.xclip_suffix > DEAD_CLIP ? (int)F_TRACK_COLS : 0) |
-                 (sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0);
+                 (sc.xclip_prefix > DEAD_CLIP ? (int)F_CLIPX : 0) | (sc.yclip_prefix > DEAD_CLIP ? (int)F_CLIPY : 0) |
+                 (table ? (int)F_LUT : 0);
+  uint32_t err_flag = 0;
+  KsLut T{};
+  T.lut = lut_scaled.data();
+  T.lut_base = 0;
+  T.cmap = cmap.data();
+  T.err_flag = &err_flag;
+  sp.sc = sc;
   run32([&](int l) {
     switch (fl) {
-#define SIM_KS_CASE(F) \
-  case (F): ks_run_task<(F)>(sp, 0, l); break;
+#define SIM_KS_CASE1(F) \
+  case (F): ks_run_task<(F)>(sp, T, 0, l); break;
+#define SIM_KS_CASE(F) SIM_KS_CASE1(F) SIM_KS_CASE1((F) | F_LUT)
       SIM_KS_CASE(0)
       SIM_KS_CASE(F_TRACK_ROWS)
       SIM_KS_CASE(F_CLIPX)
@@ -867,6 +897,7 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
       SIM_KS_CASE(F_TRACK_COLS | F_CLIPX | F_CLIPY)
       SIM_KS_CASE(F_TRACK_COLS | F_TRACK_ROWS | F_CLIPX | F_CLIPY)
 #undef SIM_KS_CASE
+#undef SIM_KS_CASE1
     }
   });
   for (uint32_t p : elig) {
@@ -874,7 +905,10 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
     const uint64_t m = x_len[p], n = y_len[p];
     const uint8_t* x = blob + x_off[p];
     const uint8_t* y = blob + y_off[p];
-    auto scoref = [&](uint8_t a, uint8_t b) -> int32_t { return a == b ? sc.match_score : sc.mismatch_score; };
+    auto scoref = [&](uint8_t a, uint8_t b) -> int32_t {
+      if (table) return table[(size_t)a * 256 + b];
+      return a == b ? sc.match_score : sc.mismatch_score;
+    };
     std::vector<uint8_t> opsbuf(m + n + 16, 0);
     BandedOut o{};
     bool redo = false;

@@ -477,6 +477,52 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
         loop_eng.close()
 
 
+@pytest.mark.parametrize("mode", ["local", "semiglobal"])
+def test_strip_wavefront_fill_blosum62(oracle, mode, monkeypatch):
+    """A tabulated MatchFunc through the strip fill (sequence bytes mapped to LUT codes as they are loaded, scores from
+    K1's scaled LUT in shared memory): protein reads against windows of longer sequences, BLOSUM62, against the
+    column loops and the oracle."""
+    import ctypes as C
+    from rust_bio_b200 import scores, synth
+    from rust_bio_b200._lib import CScoring
+    from rust_bio_b200.engine import Engine, pack_pairs
+    table = np.ascontiguousarray(scores.matrix_table256("blosum62"), dtype=np.int32)
+    alpha = np.frombuffer(bytes(range(65, 91)) + b"*", dtype=np.uint8).copy()
+    aa = np.frombuffer(synth.PROTEIN, dtype=np.uint8)
+    rng = np.random.default_rng(7 if mode == "local" else 8)
+    pairs = []
+    for _ in range(150):
+        yl, xl = int(rng.integers(400, 900)), int(rng.integers(60, 380))
+        y = aa[rng.integers(0, 20, yl)].copy()
+        st = int(rng.integers(0, yl - xl))
+        x = y[st:st + xl].copy()
+        x[rng.integers(0, xl, max(1, xl // 12))] = aa[rng.integers(0, 20, max(1, xl // 12))]
+        pairs.append((bytes(x), bytes(y)))
+    batch = pack_pairs(pairs)
+    cs = CScoring(-10, -1, MIN, MIN, MIN, MIN, 0, 0, 0, table.ctypes.data_as(C.c_void_p), alpha.ctypes.data_as(C.c_void_p), len(alpha))
+    s, keep = oracle.make_scoring(-10, -1, 0, 0, table)
+    ref, rops, roff, _, ref_cells = oracle.banded_align_batch(mode, s, 5, 7, *batch, threads=8)
+    strip_eng = Engine(0)
+    monkeypatch.setenv("B2A_BANDED_STRIP", "0")
+    loop_eng = Engine(0)
+    monkeypatch.delenv("B2A_BANDED_STRIP")
+    try:
+        a = strip_eng.align_batch_banded(MODES[mode], cs, 5, 7, batch)
+        assert strip_eng.banded_strip_pairs() >= 75
+        b = loop_eng.align_batch_banded(MODES[mode], cs, 5, 7, batch)
+        assert int(strip_eng.stats.cells) == ref_cells
+        for f in ("score", "xstart", "xend", "ystart", "yend", "ops_off", "clip_len"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (mode, f)
+            if f in ref.dtype.names:
+                assert np.array_equal(getattr(a, f).astype(np.int64), ref[f].astype(np.int64)), (mode, f)
+        for p in range(150):
+            want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+            assert a.ops_of(p) == want, (mode, p)
+    finally:
+        strip_eng.close()
+        loop_eng.close()
+
+
 def test_refused_band_keeps_the_called_methods_mode(eng):
     """banded.rs:407-420 returns the empty MIN_SCORE alignment (xlen = ylen = 0) above MAX_CELLS; global /
     semiglobal / local then overwrite only `.mode` (banded.rs:889-890) -- the mirror must not report Custom."""

@@ -418,3 +418,33 @@ def test_warp32_strip_fill_c4_shape(oracle):
         assert g is not None, "BASELINE config 4's pairs are strip-eligible"
         ref, ref_ops = oracle.banded_align("semiglobal", s, 32, 32, x, y)
         assert g[0] == {f: ref[f] for f in g[0]} and g[1] == ref_ops
+
+
+def test_warp32_strip_fill_blosum62(oracle):
+    """A tabulated MatchFunc (BLOSUM62) through the strip fill: sequence bytes mapped to LUT codes as they are loaded,
+    scores from K1's scaled LUT; local and semiglobal, tasks of one to four protein pairs."""
+    from rust_bio_b200 import scores
+    table = scores.matrix_table256("blosum62")
+    rng = np.random.default_rng(91)
+    alpha = np.frombuffer(synth.PROTEIN, dtype=np.uint8)
+    n_strip = n_tot = 0
+    for trial in range(10):
+        s, keep = oracle.make_scoring(int(rng.choice([-10, -5])), -1, 0, 0, table)
+        pairs = []
+        for q in range(int(rng.integers(1, 5))):
+            yl, xl = int(rng.integers(260, 520)), int(rng.integers(40, 250))
+            y = alpha[rng.integers(0, 20, yl)].copy()
+            st = int(rng.integers(0, yl - xl))
+            x = y[st:st + xl].copy()
+            x[rng.integers(0, xl, max(1, xl // 12))] = alpha[rng.integers(0, 20, max(1, xl // 12))]
+            pairs.append((bytes(x), bytes(y)))
+        for mode in ("local", "semiglobal"):
+            got = sim_util.banded_strip_task(MODES[mode], s, 5, 7, pairs)
+            for (x, y), g in zip(pairs, got):
+                n_tot += 1
+                if g is None:
+                    continue
+                n_strip += 1
+                ref, ref_ops = oracle.banded_align(mode, s, 5, 7, x, y)
+                assert g[0] == {f: ref[f] for f in g[0]} and g[1] == ref_ops, (trial, mode, len(x), len(y))
+    assert n_strip * 2 >= n_tot, (n_strip, n_tot)

@@ -2476,6 +2476,26 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           break;
         }
         if (ti < 1 || tj < 1) break;  // the move lands on row 0 / column 0
+#if defined(__CUDA_ARCH__)
+        // One pair per lane: a move's loads are 32 different lines per warp, and the traceback word changes line
+        // every few moves, so without help nearly every move waits for some lane's miss.  The path mostly runs
+        // down the diagonal: the lines of the cell a few moves ahead are requested now.
+        {
+          constexpr int32_t kAhead = 12;
+          const int32_t pi = ti - kAhead, pj = tj - kAhead;
+          if (pi >= 1 && pj >= 1) {
+            const uint32_t pst = (uint32_t)(pi - 1) >> KS_ROWS_LOG2, prem = (uint32_t)(pi - 1) & (uint32_t)(KS_ROWS - 1),
+                           pl = prem >> KS_R_LOG2, pr = prem & (uint32_t)(KS_R - 1);
+            if (pst == ks_cst) {  // (a strip change ahead: its table entry is not at hand, skip)
+              const uint32_t pt = (uint32_t)pj - ks_cja + pl;
+              if (pt < ks_csteps)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(
+                    ks_tb + ((size_t)(ks_coff + ((pt >> 3) * (uint32_t)KS_TBW + (pr >> 2)) * (uint32_t)KS_G + pl) * 4u + (pr & 3u))));
+            }
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rng + 2 * (size_t)pj));
+          }
+        }
+#endif
         const uint32_t nbn = nib32(ti, tj);
         if (nbn == 16u) break;        // ... or outside the band (reads as START there)
         if (!known) nl = ks_sbits((uint64_t)ti, (uint64_t)tj, nbn);

@@ -477,6 +477,35 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
         loop_eng.close()
 
 
+def test_strip_path_in_several_sub_waves(oracle):
+    """A small scratch budget cuts the banded call into several K3 sub-waves (b2a_engine.cu banded_impl): each has its
+    own list of strip pairs, strip areas and side-stream pass; results must not depend on the cut."""
+    from rust_bio_b200.engine import Engine
+    batch = _mutated_window_batch(4321, 240, 300, 1200, sub=0.06, indel=0.02)
+    s, _ = oracle.make_scoring(-5, -1, 1, -1, None, MIN, MIN, MIN, MIN, has_match_scores=1)
+    ref, rops, roff, _, ref_cells = oracle.banded_align_batch("semiglobal", s, 8, 12, *batch, threads=8)
+    cs = _c_scoring(-5, -1, 1, -1)
+    eng = Engine(0)
+    try:
+        whole = eng.align_batch_banded(MODES["semiglobal"], cs, 8, 12, batch)
+        taken = eng.banded_strip_pairs()
+        eng.set_traceback_budget(6 << 20)  # ~3 MB of K3 slabs + strip areas per sub-wave: a few dozen pairs each
+        cut = eng.align_batch_banded(MODES["semiglobal"], cs, 8, 12, batch)
+        assert eng.banded_strip_pairs() == taken and taken >= 120
+        assert eng.stats.kernel_launches > 12  # several sub-waves' worth of launches
+        for f in ("score", "xstart", "xend", "ystart", "yend", "ops_off", "clip_len"):
+            assert np.array_equal(getattr(whole, f), getattr(cut, f)), f
+            if f in ref.dtype.names:
+                assert np.array_equal(getattr(cut, f).astype(np.int64), ref[f].astype(np.int64)), f
+        tot = int(whole.ops_off[-1])
+        assert np.array_equal(whole.ops[:tot], cut.ops[:tot])
+        for p in range(0, 240, 5):
+            want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
+            assert cut.ops_of(p) == want, p
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("mode", ["local", "semiglobal"])
 def test_strip_wavefront_fill_blosum62(oracle, mode, monkeypatch):
     """A tabulated MatchFunc through the strip fill (sequence bytes mapped to LUT codes as they are loaded, scores from

@@ -76,7 +76,15 @@ enum : int {
   F_LUT = 8,         // substitution scores from a compact LUT in shared memory (else MatchParams)
   F_PACKTRK = 16,    // trackers as packed keys 4096*value + (4095-index): needs m,n <= 4095, |S| < 2^17
   F_RELU = 32,       // with F_CLIPX: xclip_score(j) == 0 for every column (x/y prefix clips both 0): one fused max3-relu
+  // 64 is F_CLIPY of the banded strip fill (b2a_banded_strip.cuh)
+  F_PACKREL = 128,   // long sequences (m or n > 4095, |S| < 2^18): the same packed keys with RELATIVE indices -- the row
+                     // tracker's column inside a chunk of 2^KREL_BITS columns (flushed to the rows arena at each chunk
+                     // end), the column tracker's row inside the strip (made absolute where the strip hands it on)
 };
+#ifndef B2A_KREL_BITS
+#define B2A_KREL_BITS 12  // (a test build shortens the chunks to exercise the flushes on small inputs)
+#endif
+constexpr int32_t KREL_BITS = B2A_KREL_BITS, KREL_MASK = (1 << KREL_BITS) - 1;
 
 struct DevScoring {
   int32_t gap_open, gap_extend;

@@ -86,6 +86,7 @@ struct b2a_engine {
   std::vector<cudaEvent_t> sub_ev;
   bool overlap_small = true;
   bool overlap_big = false;
+  bool no_packrel = false;         // B2A_NO_PACKREL=1: long sequences keep explicit (value, index) trackers (test knob)
   bool tail_split = true;          // small batches: the fill's thin last round of tasks runs under K2 of the rest
   bool split_timing = false;       // B2A_SPLIT_TIMING=1: print where the split step's time goes (dev aid)
   cudaEvent_t split_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -278,6 +279,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
   if (const char* env = getenv("B2A_TAIL_SPLIT")) e->tail_split = atoi(env) != 0;
+  if (const char* env = getenv("B2A_NO_PACKREL")) e->no_packrel = atoi(env) != 0;
   if (const char* env = getenv("B2A_SPLIT_TIMING")) e->split_timing = atoi(env) != 0;
   if (const char* env = getenv("B2A_WALK_CTA_WARPS")) {
     const int v = atoi(env);
@@ -543,6 +545,7 @@ static int32_t stage_front(b2a_engine* e, int32_t mode, const b2a_scoring* s, co
   }
   e->sc = sc;
   e->flags = scoring_flags(sc, score_bound, maxm, maxn);
+  if (e->no_packrel) e->flags &= ~F_PACKREL;  // (test knob: the explicit (value, index) trackers for long sequences)
 
   return B2A_OK;
 }

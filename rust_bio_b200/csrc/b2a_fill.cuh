@@ -204,7 +204,8 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool CX = (FLAGS & F_CLIPX) != 0;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
-  constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
+  constexpr bool PR = (FLAGS & F_PACKREL) != 0;  // packed keys with relative indices (see F_PACKREL): here like PK,
+  constexpr bool PK = (FLAGS & F_PACKTRK) != 0 || PR;  // the caller passes chunk- / strip-relative cj and rowbase
   constexpr bool RELU = (FLAGS & F_RELU) != 0;
   constexpr bool TMASK = MASKED && !LUT;  // the column tracker has to skip the padded rows explicitly
   // S travels between cells as "S + open": So_d = S4 + go4d feeds the D chain of the next column and (as
@@ -215,7 +216,7 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   const int32_t ma4 = 4 * c.sc.match_score + 3 - go4d, mi4 = 4 * c.sc.mismatch_score + 3 - go4d;
   const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
   const int32_t xs4 = scale4(c.sc.xclip_suffix), ys4 = scale4(c.sc.yclip_suffix);
-  const int32_t cj = 4095 - j;  // packed row-tracker index field
+  const int32_t cj = 4095 - (PR ? (j & KREL_MASK) : j);  // packed row-tracker index field (PR: inside the column chunk)
   const int32_t one = c.one, k2 = one + one, k16 = k2 * 8, k1024 = k16 * 64;
   const int32_t q4 = q * 4;
   int32_t Tl = KEY_NONE;        // packed column tracker of this lane's rows (local row index)
@@ -296,8 +297,8 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   }
   sup = s4;
   if (TC && PK) {
-    // local row index -> global: (4095 - r) - (rowbase + 1) = 4095 - i ; Tv carries the packed key
-    if (Tl != KEY_NONE) Tv = imax(Tv, Tl - (rowbase + 1));
+    // local row index -> global (PR: inside the strip): (4095 - r) - (rowbase + 1) = 4095 - i ; Tv carries the packed key
+    if (Tl != KEY_NONE) Tv = imax(Tv, Tl - ((PR ? c.l * R : rowbase) + 1));
   }
 }
 
@@ -307,7 +308,8 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   constexpr bool TR = (FLAGS & F_TRACK_ROWS) != 0;
   constexpr bool TC = (FLAGS & F_TRACK_COLS) != 0;
   constexpr bool LUT = (FLAGS & F_LUT) != 0;
-  constexpr bool PK = (FLAGS & F_PACKTRK) != 0;
+  constexpr bool PR = (FLAGS & F_PACKREL) != 0;
+  constexpr bool PK = (FLAGS & F_PACKTRK) != 0 || PR;  // packed keys in the lanes (PR: relative indices)
   constexpr int P = 32 / G;
   constexpr int TBW = tbw_of(R);
   const int32_t m = c.m, n = c.n;
@@ -356,6 +358,27 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   // values arriving from above for my next column (scaled domain; tracker as key or as (4*T, index))
   const int32_t t_none = PK ? KEY_NONE : NEG4;
   int32_t in_s = 0, in_i = NEG4, in_tv = t_none, in_ti = m;
+  // PR: the column tracker of the strips above (value 4*(S + xs), absolute row), carried beside this strip's packed
+  // key down the lanes; where the strip hands the boundary on the two are merged (the strip above wins ties: it holds
+  // the lower rows)
+  int32_t up_tv = NEG4, up_ti = m;
+  const int32_t xs4_pr = scale4(c.sc.xclip_suffix);
+  // PR: the row trackers are flushed to the rows arena at the end of every column chunk (first chunk: stored, later
+  // ones: kept only if strictly better, so the earlier column wins ties)
+  auto flush_rows = [&](const int32_t chunk, int32_t (&SnRr)[R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
+      if (SnRr[r] != KEY_NONE) {
+        const int32_t sn = (SnRr[r] >> 12) + ys, ly = (chunk << KREL_BITS) + (4095 - (SnRr[r] & 4095));
+        if (chunk == 0 || sn > c.rows[ROWS_SN * c.rows_pad * 32 + slot]) {
+          c.rows[ROWS_SN * c.rows_pad * 32 + slot] = sn;
+          c.rows[ROWS_LY * c.rows_pad * 32 + slot] = ly;
+        }
+      }
+      SnRr[r] = KEY_NONE;
+    }
+  };
   int4 pre = make_int4(0, 0, 0, 0);
   const bool top_from_mem = (c.l == 0) && (s > 0);
   const bool top_from_row0 = (c.l == 0) && (s == 0);
@@ -402,12 +425,22 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         in_i = NEG4;
         in_tv = t_none;
         in_ti = m;
+        if (PR) {
+          up_tv = NEG4;
+          up_ti = m;
+        }
       } else if (top_from_mem) {  // the boundary row is kept in the fill's own scaled domain
         in_s = pre.x;
         in_i = pre.y;
         if (TC) {
-          in_tv = pre.z;
-          in_ti = pre.w;
+          if (PR) {  // unpacked (value, row) of the strips above; this strip's own key starts empty
+            up_tv = pre.z;
+            up_ti = pre.w;
+            in_tv = KEY_NONE;
+          } else {
+            in_tv = pre.z;
+            in_ti = pre.w;
+          }
         }
         if (j < n && top_valid) {  // prefetch next column's boundary
           wait_col(j + 1);
@@ -429,6 +462,21 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
         o.y = (MASKED && rv < R) ? cap_i : iup;
         o.z = TC ? Tv : t_none;
         o.w = TC ? Ti : m;
+        if (PR) {  // the boundary row leaves the strip unpacked, as K2 and the strip below read it
+          o.z = NEG4;
+          o.w = m;
+          if (TC) {
+            o.z = up_tv;
+            o.w = up_ti;
+            if (Tv != KEY_NONE) {
+              const int32_t loc_v = ((Tv >> 12) << 2) + xs4_pr;  // 4 * (S + xs)
+              if (loc_v > up_tv) {
+                o.z = loc_v;
+                o.w = s * (G * R) + (4095 - (Tv & 4095));
+              }
+            }
+          }
+        }
         c.bnd[bnd_index(G, j, c.pi, c.maxn)] = o;
         if (piped && ((j & 15) == 0 || j == n)) {  // publish (release) every 16 columns and at the end
           fence_device();
@@ -440,6 +488,7 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       in_i = iup;
       in_tv = Tv;
       in_ti = Ti;
+      if (PR && TR && ((j & KREL_MASK) == KREL_MASK)) flush_rows(j >> KREL_BITS, SnR);  // the chunk's last column
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) tbacc[r] <<= 4;
@@ -450,6 +499,10 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       if (TC) {
         in_tv = B2A_SHFL_UP(in_tv, G);
         if (!PK) in_ti = B2A_SHFL_UP(in_ti, G);
+        if (PR) {
+          up_tv = B2A_SHFL_UP(up_tv, G);
+          up_ti = B2A_SHFL_UP(up_ti, G);
+        }
       }
     }
     if ((t & 7) == 7) {
@@ -465,7 +518,9 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       }
     }
   }
-  if (TR) {
+  if (TR && PR) {
+    flush_rows(n >> KREL_BITS, SnR);  // the last (possibly partial) chunk; an inactive lane-pair holds nothing
+  } else if (TR) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;

@@ -148,6 +148,8 @@ inline int scoring_flags(const DevScoring& sc, int64_t score_bound = (1ll << 40)
   if ((f & F_CLIPX) && sc.xclip_prefix == 0 && sc.yclip_prefix == 0) f |= F_RELU;
   if ((f & (F_TRACK_ROWS | F_TRACK_COLS)) && score_bound < (1ll << 17) && maxm <= 4095 && maxn <= 4095)
     f |= F_PACKTRK;
+  else if ((f & (F_TRACK_ROWS | F_TRACK_COLS)) && score_bound < (1ll << 18))
+    f |= F_PACKREL;  // longer sequences: the packed keys with chunk- / strip-relative indices
   return f;
 }
 

@@ -329,6 +329,12 @@ void fill_dispatch(int flags, const Plan& p, const Block& blk, const DevScoring&
     SIM_CASE(ALL | F_PACKTRK | F_RELU)
     SIM_CASE(F_LUT | ALL | F_RELU)
     SIM_CASE(F_LUT | ALL | F_PACKTRK | F_RELU)
+    SIM_CASE(F_TRACK_ROWS | F_PACKREL)
+    SIM_CASE(ALL | F_PACKREL)
+    SIM_CASE(ALL | F_PACKREL | F_RELU)
+    SIM_CASE(F_LUT | F_TRACK_ROWS | F_PACKREL)
+    SIM_CASE(F_LUT | ALL | F_PACKREL)
+    SIM_CASE(F_LUT | ALL | F_PACKREL | F_RELU)
     default: std::abort();
   }
 }
@@ -409,7 +415,11 @@ int sim_align_batch_g(int mode, const sim_scoring* s, const uint8_t* blob, const
     flags |= F_TRACK_ROWS | F_TRACK_COLS | F_CLIPX;
     if (bound < (1ll << 17) && p.maxm <= 4095 && p.maxn <= 4095) flags |= F_PACKTRK;
   }
-  if (modebits & 2) flags &= ~F_PACKTRK;
+  if (modebits & 2) flags &= ~(F_PACKTRK | F_PACKREL);
+  if ((modebits & 16) && (flags & (F_TRACK_ROWS | F_TRACK_COLS))) {  // the long-sequence form of the packed trackers
+    flags &= ~F_PACKTRK;
+    flags |= F_PACKREL;
+  }
   const int32_t* lut_plain = lut.data();
   const int32_t* lut_scaled = lut.data() + (size_t)sc.alpha * sc.alpha;
   // scratch starts as caller-chosen garbage: nothing may depend on its initial contents

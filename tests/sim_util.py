@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "sim", "b2a_sim.cpp")
 _KS_R = os.environ.get("B2A_SIM_KS_R", "")  # dev knob: the strip fill's rows per lane in the host build
-SO = os.path.join(HERE, "sim", "libb2asim%s.so" % (("_r" + _KS_R) if _KS_R else ""))
+_KREL = os.environ.get("B2A_SIM_KREL_BITS", "")  # test knob: column-chunk length (log2) of the relative packed trackers
+SO = os.path.join(HERE, "sim", "libb2asim%s%s.so" % ((("_r" + _KS_R) if _KS_R else ""), (("_k" + _KREL) if _KREL else "")))
 DEPS = [SRC] + [os.path.join(ROOT, "rust_bio_b200", "csrc", f)
                 for f in ("b2a_common.cuh", "b2a_coop.cuh", "b2a_fill.cuh", "b2a_walk.cuh", "b2a_plan.h", "b2a_banded.cuh", "b2a_banded_strip.cuh")]
 
@@ -27,7 +28,8 @@ class SimScoring(C.Structure):
 def build():
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fwrapv", "-fPIC", "-shared",
-                               "-Wno-unknown-pragmas"] + ([f"-DB2A_KS_R={_KS_R}"] if _KS_R else []) + ["-o", SO, SRC])
+                               "-Wno-unknown-pragmas"] + ([f"-DB2A_KS_R={_KS_R}"] if _KS_R else []) +
+                              ([f"-DB2A_KREL_BITS={_KREL}"] if _KREL else []) + ["-o", SO, SRC])
     return SO
 
 
@@ -42,7 +44,7 @@ def lib():
     return _lib
 
 
-def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0, garbage=None, no_pack=0, no_lut=0, G=1, warp_walk=0):
+def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force_general=0, garbage=None, no_pack=0, no_lut=0, G=1, warp_walk=0, rel_pack=0):
     """Takes an oracle.OrcScoring (same layout). Returns dict of arrays + list of op lists."""
     s = SimScoring.from_buffer_copy(bytes(orc_scoring))
     blob = np.ascontiguousarray(blob, dtype=np.uint8)
@@ -59,14 +61,14 @@ def align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R=16, force
     out["clip_len"] = np.zeros(4 * n, dtype=np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     if garbage is None:  # run with two different scratch fills and insist on identical results
-        a = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x00, no_pack, no_lut, G, warp_walk)
-        b = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x7F, no_pack, no_lut, G, warp_walk)
+        a = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x00, no_pack, no_lut, G, warp_walk, rel_pack)
+        b = align_batch(mode, orc_scoring, blob, x_off, x_len, y_off, y_len, R, force_general, 0x7F, no_pack, no_lut, G, warp_walk, rel_pack)
         for k in a[0]:
             assert np.array_equal(a[0][k], b[0][k]), ("scratch-dependent result", k)
         assert a[1] == b[1], "scratch-dependent ops"
         return a
     rc = lib().sim_align_batch_g(int(mode), C.byref(s), p(blob), p(x_off), p(x_len), p(y_off), p(y_len),
-                               C.c_uint64(n), int(G), int(R), int(force_general) | (2 if no_pack else 0) | (4 if no_lut else 0) | (8 if warp_walk else 0), int(garbage), p(out["score"]),
+                               C.c_uint64(n), int(G), int(R), int(force_general) | (2 if no_pack else 0) | (4 if no_lut else 0) | (8 if warp_walk else 0) | (16 if rel_pack else 0), int(garbage), p(out["score"]),
                                p(out["xstart"]), p(out["xend"]), p(out["ystart"]), p(out["yend"]),
                                p(out["n_ops"]), p(out["clip_len"]), p(out["status"]), p(ops), p(ops_off))
     assert rc == 0

@@ -412,10 +412,16 @@ def test_c5_shape_8_pairs_10k_x_10k_blosum62_local(eng, oracle):
 
 @pytest.mark.parametrize("G,R", [(8, 16), (8, 20), (32, 16), (32, 8)])
 @pytest.mark.parametrize("lut", [True, False], ids=["lut", "matchparams_wide_alphabet"])
-def test_unpacked_tracker_variants_4200(eng, oracle, G, R, lut):
-    """m, n > 4095 in every mode: the fill_kernel<G,R,FLAGS> instantiations without F_PACKTRK
-    (b2a_fill_inst.cu: 0, TRACK_ROWS, ALL, ALL|RELU, each with and without F_LUT).  A 200-symbol alphabet keeps
-    MatchParams on its compare/select path (no LUT above 64 symbols)."""
+@pytest.mark.parametrize("trackers", ["relative_keys", "explicit_pairs"])
+def test_unpacked_tracker_variants_4200(oracle, G, R, lut, trackers, monkeypatch):
+    """m, n > 4095 in every mode: the fill_kernel<G,R,FLAGS> instantiations without F_PACKTRK -- with the packed keys
+    over chunk- / strip-relative indices (F_PACKREL, what long sequences run: 0, TRACK_ROWS, ALL, ALL|RELU, each with
+    and without F_LUT) and with explicit (value, index) trackers (B2A_NO_PACKREL=1: what scores above 2^18 would run).
+    A 200-symbol alphabet keeps MatchParams on its compare/select path (no LUT above 64 symbols)."""
+    from rust_bio_b200.engine import Engine
+    if trackers == "explicit_pairs":
+        monkeypatch.setenv("B2A_NO_PACKREL", "1")
+    eng = Engine(0)
     from rust_bio_b200 import synth
     alphabet = b"ACGT" if lut else bytes(range(33, 233))
     rng = np.random.default_rng(G * 100 + R + (1 if lut else 0))
@@ -441,9 +447,9 @@ def test_unpacked_tracker_variants_4200(eng, oracle, G, R, lut):
             cs, keep = _c_scoring(-5, -1, 2, -1, clips)
             got, ops = _engine_result(eng, mode, cs, batch)
             assert eng.stats.fill_lanes_per_pair == G
-            assert_same(got, ops, ref, ref_ops, batch, f"4200 {mode} {clips} G={G} R={R} lut={lut}")
+            assert_same(got, ops, ref, ref_ops, batch, f"4200 {mode} {clips} G={G} R={R} lut={lut} {trackers}")
     finally:
-        eng.set_tuning(0, 0)
+        eng.close()
 
 
 @pytest.mark.parametrize("mode", ["global", "semiglobal", "local", "custom"])

@@ -238,3 +238,16 @@ def test_sim_warp_walk_tiny_shapes(oracle):
             ref, ref_ops = oracle_batch(oracle, mode, s, batch)
             got, ops = sim_util.align_batch(MODES[mode], s, *batch, R=4, warp_walk=1)
             assert_same(got, ops, ref, ref_ops, batch, f"warp walk tiny {mode} {clips}")
+
+
+def test_sim_relative_packed_trackers_long_sequence_form():
+    """F_PACKREL (what BASELINE config 5's 10k x 10k pairs run): exercised on small inputs by a host build whose
+    column chunks are 32 columns long -- its own process, the chunk length is a compile-time constant."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B2A_SIM_KREL_BITS="5")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "workers", "sim_relpack_worker.py")], env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]

@@ -195,7 +195,7 @@ constexpr int32_t KEY_NONE = (int32_t)0x80000000;
 //    known to lie in row-quad CAPQ (compile time), so only four rows carry the capture compare; CAPQ == R/4: no
 //    lane of the strip is partial; CAPQ == -1: ragged block, every row compares.
 template <int G, int R, int FLAGS, bool MASKED, bool LAST, int CAPQ>
-B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, const int32_t rowbase,
+B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t tstep, const int32_t q, const int32_t rowbase,
                         const int32_t rv, int32_t (&Sp)[R], int32_t (&Dp)[R], int32_t (&SnR)[R],
                         int32_t (&LyR)[R], uint32_t (&tbacc)[R], const int32_t (&xc)[R],
                         int32_t sdiag, int32_t& sup, int32_t& iup, int32_t& Tv, int32_t& Ti,
@@ -216,7 +216,10 @@ B2A_HD void column_step(const LaneCtx<G>& c, const int32_t j, const int32_t q, c
   const int32_t ma4 = 4 * c.sc.match_score + 3 - go4d, mi4 = 4 * c.sc.mismatch_score + 3 - go4d;
   const int32_t x4 = CX ? scale4(xclip_score(c.sc, j)) : 0;
   const int32_t xs4 = scale4(c.sc.xclip_suffix), ys4 = scale4(c.sc.yclip_suffix);
-  const int32_t cj = 4095 - (PR ? (j & KREL_MASK) : j);  // packed row-tracker index field (PR: inside the column chunk)
+  // packed row-tracker index field: the column, or (PR) the STEP inside its chunk of 2^KREL_BITS steps -- the lanes
+  // of a pair sit at different columns in one step, but they all reach a chunk's end together, so the flush of the
+  // row trackers to the rows arena happens between two runs of the column loop, not inside it
+  const int32_t cj = 4095 - (PR ? (tstep & KREL_MASK) : j);
   const int32_t one = c.one, k2 = one + one, k16 = k2 * 8, k1024 = k16 * 64;
   const int32_t q4 = q * 4;
   int32_t Tl = KEY_NONE;        // packed column tracker of this lane's rows (local row index)
@@ -363,17 +366,18 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   // the lower rows)
   int32_t up_tv = NEG4, up_ti = m;
   const int32_t xs4_pr = scale4(c.sc.xclip_suffix);
-  // PR: the row trackers are flushed to the rows arena at the end of every column chunk (first chunk: stored, later
-  // ones: kept only if strictly better, so the earlier column wins ties)
+  // PR: the row trackers are flushed to the rows arena (seeded with column 0's value, below) at the end of every chunk
+  // of steps and kept only if strictly better, so the earlier column wins ties
   auto flush_rows = [&](const int32_t chunk, int32_t (&SnRr)[R]) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
       if (SnRr[r] != KEY_NONE) {
-        const int32_t sn = (SnRr[r] >> 12) + ys, ly = (chunk << KREL_BITS) + (4095 - (SnRr[r] & 4095));
-        if (chunk == 0 || sn > c.rows[ROWS_SN * c.rows_pad * 32 + slot]) {
+        const int32_t sn = (SnRr[r] >> 12) + ys;
+        const int32_t step = (chunk << KREL_BITS) + (4095 - (SnRr[r] & 4095));
+        if (sn > c.rows[ROWS_SN * c.rows_pad * 32 + slot]) {
           c.rows[ROWS_SN * c.rows_pad * 32 + slot] = sn;
-          c.rows[ROWS_LY * c.rows_pad * 32 + slot] = ly;
+          c.rows[ROWS_LY * c.rows_pad * 32 + slot] = step - c.l + 1;  // the lane's column at that step
         }
       }
       SnRr[r] = KEY_NONE;
@@ -406,7 +410,18 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
   uint4* tbs = c.tb + (size_t)s * c.K * TBW * 32;
   const int32_t nsteps = c.K * 8;
 
-  for (int32_t t = 0; t < nsteps; ++t) {
+  if (PR && TR) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;
+      c.rows[ROWS_SN * c.rows_pad * 32 + slot] = col0_S(c.sc, rowbase + 1 + r) + ys;  // column 0 (mod.rs:667-670)
+      c.rows[ROWS_LY * c.rows_pad * 32 + slot] = 0;
+      SnR[r] = KEY_NONE;
+    }
+  }
+  for (int32_t t0 = 0; t0 < nsteps; t0 += (PR ? (1 << KREL_BITS) : nsteps)) {
+  const int32_t t1 = PR ? ((t0 + (1 << KREL_BITS) < nsteps) ? t0 + (1 << KREL_BITS) : nsteps) : nsteps;
+  for (int32_t t = t0; t < t1; ++t) {
     const int32_t j = t - c.l + 1;
     const bool active = (j >= 1) && (j <= n);
     if (active) {
@@ -449,10 +464,10 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       }
       int32_t sup = in_s, iup = in_i, Tv = in_tv, Ti = in_ti;
       if (j == n) {
-        column_step<G, R, FLAGS, MASKED, true, CAPQ>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+        column_step<G, R, FLAGS, MASKED, true, CAPQ>(c, j, t, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
                                                sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
       } else {
-        column_step<G, R, FLAGS, MASKED, false, CAPQ>(c, j, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
+        column_step<G, R, FLAGS, MASKED, false, CAPQ>(c, j, t, q, rowbase, rv, Sp, Dp, SnR, LyR, tbacc, xc,
                                                 sup_prev, sup, iup, Tv, Ti, cap_s, cap_i);
       }
       sup_prev = in_s;
@@ -488,7 +503,6 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       in_i = iup;
       in_tv = Tv;
       in_ti = Ti;
-      if (PR && TR && ((j & KREL_MASK) == KREL_MASK)) flush_rows(j >> KREL_BITS, SnR);  // the chunk's last column
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) tbacc[r] <<= 4;
@@ -518,9 +532,9 @@ B2A_HD void run_strip(const LaneCtx<G>& c, const int32_t s) {
       }
     }
   }
-  if (TR && PR) {
-    flush_rows(n >> KREL_BITS, SnR);  // the last (possibly partial) chunk; an inactive lane-pair holds nothing
-  } else if (TR) {
+  if (PR && TR) flush_rows(t0 >> KREL_BITS, SnR);
+  }  // chunks of steps
+  if (TR && !PR) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int32_t slot = (rowbase + 1 + r) * 32 + c.pi;

@@ -478,7 +478,7 @@ B2A_HD uint64_t find_kmer_matches_d(int lane, const uint8_t* x, uint64_t m, cons
         hbuf[2ull * at + 1] = j;
       }
       qn += (uint32_t)C::popc(bal);
-      if (qn + (uint32_t)W > Q) {  // the next position could overflow the queue
+      if (qn + (uint32_t)W > Q) {  // the next position could overflow the queue (Q >= 2 W: checked by the caller)
         C::sync();
         drain();
         C::sync();
@@ -867,6 +867,9 @@ B2A_HD uint32_t band_create_d(int lane, const uint8_t* x, uint64_t m, const uint
     nm64 = hint.n_matches;
     C::sync();
   } else {
+    // (the probe queue lives in the event scratch, 4 * cap u64: a capacity below 32 matches would not hold one round
+    //  of a warp's positions -- such a pair reports a capacity overflow and the wave is redone with a larger one)
+    if (4ull * cap < 4ull * (uint64_t)W) return 1;
     nm64 = find_kmer_matches_d<W>(lane, x, m, y, n, k, table, H, matches, cap, shared_u32, ev, 4ull * cap, shared_u32 + 2);
     if (nm64 == ~0ull) return 1;
   }

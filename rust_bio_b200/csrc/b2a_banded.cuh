@@ -61,7 +61,8 @@ struct BandedParams {
   int32_t allowed_mismatches;      // custom_with_expanded_matches: >= 0 expands the matches, -1 = None
   int32_t use_lcskpp_union;        // custom_with_expanded_matches
   // strip-wavefront fill (b2a_banded_strip.cuh)
-  int32_t strip_ok;        // the batch's scoring suits it (host check): K4 may mark pairs strip-eligible (bit 9)
+  int32_t strip_ok;        // bit 0: the batch's scoring suits it (host check): K4 may mark pairs strip-eligible (bit 9);
+                           // bit 1: also pairs whose band holds cells of column n (global mode)
   int32_t redo_pass;       // K3 column-loop kernels: 0 = the pairs K4 did not mark for the strip path, 1 = the pairs the
                            // strip path handed back (bit 10)
   uint32_t* band_cols;     // [n_pairs * 3] out (K4): first / last non-empty band column, strip columns
@@ -1073,7 +1074,7 @@ B2A_HD bool banded_fast_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n
 // columns 1..n-1 of the KS_ROWS-row strips they touch}.
 template <int W>
 B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t n, uint32_t* out3, uint64_t jlo = 0,
-                            uint64_t jhi = ~0ull) {
+                            uint64_t jhi = ~0ull, bool last_column_ok = false) {
   using C = Coop<W>;
   if (W != 32 || m < 2 || n < 2 || m >= (1u << 24) || n >= (1u << 24)) return false;
   bool ok = true;
@@ -1088,7 +1089,7 @@ B2A_HD bool banded_strip_ok(int lane, const uint32_t* rng, uint64_t m, uint64_t 
     ++cnt;
     c0 = (uint32_t)j < c0 ? (uint32_t)j : c0;
     c1 = (uint32_t)j > c1 ? (uint32_t)j : c1;
-    if (j == n) ok = false;
+    if (j == n && !last_column_ok) ok = false;  // (the finish pass runs the literal loop on column n when allowed)
     if (j >= 1) {
       const uint64_t ps = rng[2 * (j - 1)], pe = rng[2 * (j - 1) + 1];
       if (ps < pe && (s < ps || e < pe)) ok = false;
@@ -1694,9 +1695,12 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
   const uint32_t* ks_tab = nullptr;
   const int32_t* ks_bnd = nullptr;  // int4 {4*S, 4*I + 2, column-tracker key, 0} per column, index j - kc0 + 1
   const uint32_t* ks_tb = nullptr;
+  const uint8_t* ks_last = nullptr;  // int2 {4*S, D} of column n-1 per row (rows of its band), for column n's literal pass
   if (STRIP) {
     const uint64_t ns = m >= 2 ? (m - 1 + KS_ROWS - 1) / KS_ROWS : 0;
-    const uint64_t o_tab = 0, o_bnd = al16(ns * KS_TAB * 4), o_tb = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 16);
+    const uint64_t o_tab = 0, o_bnd = al16(ns * KS_TAB * 4),
+                   o_last = al16(o_bnd + (uint64_t)((kc1 >= kc0 ? kc1 - kc0 + 1 : 0) + 2) * 16), o_tb = al16(o_last + (m + 1) * 8);
+    ks_last = strip_area + o_last;
     ks_tab = reinterpret_cast<const uint32_t*>(strip_area + o_tab);
     ks_bnd = reinterpret_cast<const int32_t*>(strip_area + o_bnd);
     ks_tb = reinterpret_cast<const uint32_t*>(strip_area + o_tb);
@@ -1815,6 +1819,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     }
   }
   C::sync();
+  uint64_t lit_from = 1;  // first column of the literal loop below
   if constexpr (FASTR > 0) {
     banded_columns_fast<W, FASTR>(lane, x, (int32_t)m, y, (int32_t)n, sc, score, rng, colstart, Sarr[0], Sarr[n % 2],
                                   Iarr[n % 2], Sn, Ly, Lx, row0, rowm, col0, coln, cells);
@@ -1824,6 +1829,8 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
     // cells 1..m-1 x 1..n-1 -- row 0's cells and its Sn/Ly seed, row m's cells (they start from the column tracker the
     // fill hands over in the boundary row), and the x-suffix-clip nibble every column leaves in row m.
     const int32_t mi = (int32_t)m;
+    const bool coln_empty = rng[2 * n] >= rng[2 * n + 1];
+    int32_t Sm_last = MIN_SCORE, Dm_last = MIN_SCORE;  // S / D of (m, n-1), for column n's pass (lane 0)
     // (row 0's cells and row m's x-suffix-clip nibbles were written by the initialisation above)
     if (lane == 0 && kc0 <= kc1 && rng[2 * kc0] == 0 && rng[2 * kc0 + 1] > 0) {
       // S(0, j) never increases with j: only the first row-0 column can raise Sn[0] (547-552)
@@ -1931,13 +1938,49 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
         Dm_prev = bd;
         rSup = rS;  // S(m-1, j) is the next column's diagonal input
       }
-      Sarr[n % 2][m] = MIN_SCORE;  // column n is empty: S[m] ends the loop reset (556-561) ...
-      rowm[n] = (uint16_t)(TB_XCLIP_SUFFIX << 8);  // ... and its nibble, written last, replaces the eager marks (671-674)
+      if (coln_empty) {
+        Sarr[n % 2][m] = MIN_SCORE;  // S[m] ends the loop reset (556-561) ...
+        rowm[n] = (uint16_t)(TB_XCLIP_SUFFIX << 8);  // ... and its nibble, written last, replaces the eager marks (671-674)
+      }  // (else column n's own pass below rewrites the s-bits of (m, n); its i / d bits are still untouched)
+      // what column n reads of column n-1 in row m
+      Sm_last = k1 == (int32_t)n - 1 && jm0 <= kc1 ? Sm_prev : MIN_SCORE;
+      Dm_last = k1 == (int32_t)n - 1 && jm0 <= kc1 ? Dm_prev : MIN_SCORE;
     }
     C::sync();
-  } else {
+    if (!coln_empty) {
+      // Column n holds band cells: the literal loop runs it (its extra Sn terms, 590-596, are not the packed cell's),
+      // reading column n-1 from the rolling arrays as the reference would have left them -- MIN_SCORE outside the
+      // band, the strip fill's export inside, row 0's closed form and row m from the pass above.
+      const int pc = (int)((n - 1) % 2);
+      for (uint64_t i = (uint64_t)lane; i <= m; i += W) {
+        Sarr[pc][i] = MIN_SCORE;
+        Iarr[pc][i] = MIN_SCORE;
+        Darr[pc][i] = MIN_SCORE;
+      }
+      C::sync();
+      const uint64_t ps = rng[2 * (n - 1)], pe = rng[2 * (n - 1) + 1];
+      const int32_t* lastcol = reinterpret_cast<const int32_t*>(ks_last);
+      for (uint64_t i = umax64(1, ps) + (uint64_t)lane; i < umin64(pe, m); i += W) {
+        const int32_t vs = lastcol[2 * i], vd = lastcol[2 * i + 1];
+        Sarr[pc][i] = vs <= -(1 << 29) ? MIN_SCORE : vs >> 2;
+        Darr[pc][i] = vd <= -(1 << 29) ? MIN_SCORE : vd >> 2;
+      }
+      if (lane == 0) {
+        if (ps == 0 && pe > 0) Sarr[pc][0] = imax(row0_D(sc, (int32_t)n - 1), yp);
+        Sarr[pc][m] = Sm_last;  // (lane 0 ran the row-m pass)
+        Darr[pc][m] = Dm_last;
+        const uint64_t en = rng[2 * n + 1];
+        if (en < m) Sarr[n % 2][en] = MIN_SCORE;  // the row just below column n's band keeps its MIN_SCORE (689)
+      }
+      C::sync();
+      lit_from = n;
+    } else {
+      lit_from = n + 1;
+    }
+  }
+  if constexpr (FASTR <= 0) {  // the literal loop: every column, or (strip path) column n alone when it holds band cells
   uint32_t known_busy = 0;  // columns from here on already seen not to be of the plain kind
-  for (uint64_t j = 1; j <= n; ++j) {  // banded.rs:511-681
+  for (uint64_t j = lit_from; j <= n; ++j) {  // banded.rs:511-681
     if (known_busy > 0) {
       known_busy -= 1;
     } else {
@@ -2051,7 +2094,7 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
       const uint64_t jj = j - 1;
       const uint32_t ps = jj == 0 ? 0u : rng[2 * jj], pe = jj == 0 ? 0xFFFFFFFFu : rng[2 * jj + 1];
       const uint16_t* const pbase = jj == 0 ? col0 : cells;
-      const uint32_t poff = jj == 0 ? 0u : colstart[jj] - ps;  // cell (i, j-1) = pbase[poff + i] for ps <= i < pe
+      const uint32_t poff = (jj == 0 || STRIP) ? 0u : colstart[jj] - ps;  // cell (i, j-1) = pbase[poff + i] for ps <= i < pe
       uint16_t* const wbase = last ? coln : cells;
       const uint32_t woff = last ? 0u : colstart[j] - (uint32_t)i_start;  // cell (i, j) = wbase[woff + i]
       const uint32_t lo32 = (uint32_t)lo, hm32 = (uint32_t)hi_main;
@@ -2073,8 +2116,12 @@ B2A_HD void banded_compute_d(int lane, const uint8_t* x, uint64_t m, const uint8
           db = TB_DEL;
         } else {
           best_d = s_open;
-          const uint32_t pc = (ic >= ps && ic < pe) ? (uint32_t)pbase[poff + ic] : 0u;
-          db = (pc >> 8) & 15u;
+          if (STRIP && jj != 0) {  // (column n-1's interior cells live in the strip fill's 4-bit traceback)
+            db = sbits_at(ic, jj);
+          } else {
+            const uint32_t pc = (ic >= ps && ic < pe) ? (uint32_t)pbase[poff + ic] : 0u;
+            db = (pc >> 8) & 15u;
+          }
         }
         const int32_t yclip_score = yp + go + ge * ((int32_t)ic - 1);
         const int32_t A = imax(imax(imax(MIN_SCORE, m_score), imax(best_d, xclip_score)), yclip_score);
@@ -2629,7 +2676,8 @@ __global__ void __launch_bounds__(128) band_kernel(const BandedParams prm, uint3
                     banded_fast_ok<32, K3_FAST_ROWS>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, touched[0], touched[1]);
   uint32_t cols3[3] = {0, 0, 0};
   const bool strip = prm.strip_ok && st == 0 && cells <= BANDED_MAX_CELLS &&
-                     banded_strip_ok<32>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, cols3, touched[0], touched[1]);
+                     banded_strip_ok<32>(lane, prm.ranges + prm.ranges_off[t] / 4, m, n, cols3, touched[0], touched[1],
+                                         (prm.strip_ok & 2) != 0);
   if (lane != 0) return;
   prm.num_cells[p] = cells;
   prm.k4_status[p] = st | (fast ? 0x100u : 0u) | (strip ? 0x200u : 0u);

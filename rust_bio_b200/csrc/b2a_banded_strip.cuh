@@ -43,7 +43,7 @@ enum : int { F_CLIPY = 64 };  // y-prefix clip live (with F_CLIPX / F_TRACK_ROWS
 
 // per-pair strip area: [strip table: nstrips x {ja, traceback offset in uint4 units, steps stored, 0}][boundary row: (cols+2) x int4 {4S, 4I+2, column-tracker key, 0}][traceback]
 struct KsLayout {
-  uint64_t tab, bnd, tb, total;
+  uint64_t tab, bnd, last, tb, total;
 };
 B2A_HD uint32_t ks_nstrips(uint64_t m) { return m >= 2 ? (uint32_t)((m - 1 + KS_ROWS - 1) / KS_ROWS) : 0u; }
 B2A_HD KsLayout ks_layout(uint64_t m, uint64_t band_cols, uint64_t strip_cols) {
@@ -52,6 +52,7 @@ B2A_HD KsLayout ks_layout(uint64_t m, uint64_t band_cols, uint64_t strip_cols) {
   uint64_t b = 0;
   L.tab = b; b = al16(b + ns * KS_TAB * 4);
   L.bnd = b; b = al16(b + (band_cols + 2) * 16);
+  L.last = b; b = al16(b + (m + 1) * 8);  // column n-1's {4S, D} per row, when column n holds band cells
   L.tb = b;
   // a strip of `len` columns stores ceil((len + 14) / 8) groups of 8 steps, KS_TBW x KS_G uint4 each
   b += (strip_cols / 8 + 3 * ns) * (uint64_t)(KS_TBW * KS_G * 16);
@@ -126,6 +127,7 @@ struct KsPair {
   uint16_t* coln;
   uint32_t* tab;      // strip table
   int4* bnd;          // boundary row, indexed by j - c0 + 1
+  int2* last;         // column n-1's {4S, D} per row (written when the strip's window ends at column n-1)
   uint4* tb;
 };
 
@@ -348,6 +350,18 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const KsLut& T, 
       ks_column_step<FLAGS, LASTSTRIP>(sc, T, one, ge4, j, q, rowbase + 1 - sj, h_band, 4095 - jr, y4_row0, Sp, Dp, SnR,
                                        tbacc, xc, sup_prev, sup, iup, Tv, rowbase, cap_row, cap_s, cap_i);
       sup_prev = in_s;
+      if (j == n - 1) {  // column n's literal pass (finish kernel) reads S and D of column n-1: rows of the band only
+#pragma unroll
+        for (int r = 0; r < KS_R; ++r) {
+          const int32_t i = rowbase + 1 + r;
+          if ((uint32_t)(rowbase + 1 - sj + r) < h_band) {
+            int2 v;
+            v.x = Sp[r] - (4 * sc.gap_open + 1);  // S travels open-biased
+            v.y = Dp[r];
+            P.last[i] = v;
+          }
+        }
+      }
       if (writer) {
         int4 o;
         o.x = (my_last && cap_row != KS_R - 1) ? cap_s : sup;
@@ -432,6 +446,7 @@ B2A_HD void ks_run_task(const StripParams& prm, const KsLut& T, const uint32_t t
     uint8_t* area = prm.strip + prm.strip_off[t];
     P.tab = reinterpret_cast<uint32_t*>(area + S.tab);
     P.bnd = reinterpret_cast<int4*>(area + S.bnd);
+    P.last = reinterpret_cast<int2*>(area + S.last);
     P.tb = reinterpret_cast<uint4*>(area + S.tb);
   }
   const int32_t ns = (int32_t)ks_nstrips((uint64_t)P.m);

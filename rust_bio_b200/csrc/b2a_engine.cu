@@ -110,6 +110,7 @@ struct b2a_engine {
   int walk_mode = 0;  // 0 automatic, 1 one lane per pair, 2 one warp per pair
   bool banded_fast = true;  // K3: register-resident column loop for the pairs K4 marks (B2A_BANDED_LITERAL=1: never)
   bool banded_strip = true;  // K3s: strip-wavefront fill for the pairs K4 marks (B2A_BANDED_STRIP=0: never)
+  bool banded_strip_lastcol = true;  // ... also for bands reaching column n (B2A_BANDED_STRIP_LASTCOL=0: those stay with K3)
   uint64_t strip_pairs = 0;  // pairs the strip path finished in the last banded call (the rest ran the K3 loops)
   // packed input (b2a_align_batch_packed): the caller's "blob" is BitEnc storage of this width (0 = bytes); the
   // engine unpacks it on the device and uses its own byte offsets (eff_xoff / eff_yoff) from then on
@@ -276,6 +277,7 @@ int32_t b2a_engine_create(b2a_engine** out, int32_t device_id) {
   e->overlap_small = false;
   if (const char* env = getenv("B2A_BANDED_LITERAL")) e->banded_fast = atoi(env) == 0;
   if (const char* env = getenv("B2A_BANDED_STRIP")) e->banded_strip = atoi(env) != 0;
+  if (const char* env = getenv("B2A_BANDED_STRIP_LASTCOL")) e->banded_strip_lastcol = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP")) e->overlap_small = atoi(env) != 0;
   if (const char* env = getenv("B2A_OVERLAP_BIG")) e->overlap_big = atoi(env) != 0;
   if (const char* env = getenv("B2A_TAIL_SPLIT")) e->tail_split = atoi(env) != 0;
@@ -1542,6 +1544,7 @@ static int32_t banded_impl(b2a_engine* e, int32_t mode, const b2a_scoring* s, ui
     // yclip_score(i)) and below 2^17; the column tracker's key also holds the row (x no longer than 4,095)
     const bool trackers_ok = (xs_dead && ys_dead) || (yp_live && score_bound < (1ll << 17) && (xs_dead || maxm <= 4095));
     bp.strip_ok = (e->banded_strip && e->banded_fast && score_bound < (1ll << 26) && trackers_ok) ? 1 : 0;
+    if (bp.strip_ok && e->banded_strip_lastcol) bp.strip_ok |= 2;  // bands that hold cells of column n as well
   }
   e->strip_pairs = 0;
   bp.filter_clips = (mode == B2A_MODE_SEMIGLOBAL || mode == B2A_MODE_LOCAL) ? 1 : 0;

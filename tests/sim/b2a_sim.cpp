@@ -827,7 +827,7 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
     if (st_lane[0] != 0 || !batch_ok || cells[p] > BANDED_MAX_CELLS) continue;
     bool ok_lane[32];
     uint32_t c3[32][3];
-    run32([&](int l) { ok_lane[l] = banded_strip_ok<32>(l, rngs[p].data(), m, n, c3[l]); });
+    run32([&](int l) { ok_lane[l] = banded_strip_ok<32>(l, rngs[p].data(), m, n, c3[l], 0, ~0ull, !getenv("B2A_SIM_STRIP_NO_LASTCOL")); });
     if (!ok_lane[0]) continue;
     for (int q = 0; q < 3; ++q) cols[3 * p + q] = c3[0][q];
     k4[p] = 0x200u;

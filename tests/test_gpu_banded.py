@@ -415,7 +415,7 @@ def test_register_resident_k3_equals_literal_k3_and_oracle(oracle, mode, monkeyp
         lit_eng.close()
 
 
-@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "custom_xy", "local", "custom_xs", "x_prefix_only"])
+@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "custom_xy", "local", "custom_xs", "x_prefix_only", "global"])
 def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monkeypatch):
     """K3s (b2a_banded_strip.cuh: the packed cell of K1 on fixed 128-row strips with a band mask, four pairs to a
     warp, 4-bit traceback, finish pass) against the K3 column loops (B2A_BANDED_STRIP=0) and the oracle: ragged
@@ -423,7 +423,8 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
     clips live (their shared priority code), local mode and a custom x-suffix clip (the column tracker).  The path
     must have taken most of the semiglobal and local pairs."""
     from rust_bio_b200.engine import Engine
-    rng = np.random.default_rng({"semiglobal": 41, "custom_y": 42, "custom_xy": 43, "local": 44, "custom_xs": 45, "x_prefix_only": 46}[mode])
+    rng = np.random.default_rng({"semiglobal": 41, "custom_y": 42, "custom_xy": 43, "local": 44, "custom_xs": 45, "x_prefix_only": 46,
+                                 "global": 47}[mode])
     strip_eng = Engine(0)
     monkeypatch.setenv("B2A_BANDED_STRIP", "0")
     loop_eng = Engine(0)
@@ -437,6 +438,8 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
                 omode, clips = "semiglobal", (MIN,) * 4
             elif mode == "custom_y":
                 omode, clips = "custom", (MIN, MIN, int(rng.choice([0, -2, -7])), int(rng.choice([0, -1, -6])))
+            elif mode == "global":     # the band holds cells of column n: the finish pass runs the literal loop on it
+                omode, clips = "global", (MIN,) * 4
             elif mode == "local":      # row and column trackers, both prefix clip terms
                 omode, clips = "local", (MIN,) * 4
             elif mode == "x_prefix_only":  # every y clip dead: band cells hold sentinel-derived values, pairs whose
@@ -470,7 +473,7 @@ def test_strip_wavefront_fill_equals_column_loops_and_oracle(oracle, mode, monke
             for p in range(0, 203, 7):
                 want = [(int(v) & 7, int(v) >> 3) for v in rops[int(roff[p]):int(roff[p]) + int(ref["n_ops"][p])]]
                 assert a.ops_of(p) == want, (mode, trial, p)
-        if mode in ("semiglobal", "local"):
+        if mode in ("semiglobal", "local", "global"):
             assert taken * 2 >= total, (taken, total)
     finally:
         strip_eng.close()

@@ -367,10 +367,10 @@ def test_warp32_fast_column_loop_blosum_and_c4_shape(oracle):
 # ---- the strip-wavefront banded fill (b2a_banded_strip.cuh: K1's packed cell on fixed 128-row strips, band mask, 4-bit
 # traceback) + its finish pass, as ONE emulated warp-task of up to four pairs with different shapes and windows
 
-@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "global_nocoln", "custom_xy", "local", "custom_xsuffix"])
+@pytest.mark.parametrize("mode", ["semiglobal", "custom_y", "global_nocoln", "custom_xy", "local", "custom_xsuffix", "global"])
 def test_warp32_strip_fill_vs_oracle(oracle, mode):
     rng = np.random.default_rng({"semiglobal": 21, "custom_y": 22, "global_nocoln": 23, "custom_xy": 24, "local": 25,
-                                 "custom_xsuffix": 26}[mode])
+                                 "custom_xsuffix": 26, "global": 27}[mode])
     n_strip = n_tot = 0
     for trial in range(24):
         go, ge = int(rng.choice([0, -1, -5, -5])), int(rng.choice([0, -1, -1, -2]))
@@ -378,6 +378,8 @@ def test_warp32_strip_fill_vs_oracle(oracle, mode):
             omode, clips = "semiglobal", (MIN, MIN, MIN, MIN)
         elif mode == "custom_y":     # y clips live with different penalties, x global
             omode, clips = "custom", (MIN, MIN, int(rng.choice([0, -2, -7])), int(rng.choice([0, -1, -6])))
+        elif mode == "global":         # the band holds cells of column n: the finish pass runs the literal loop there
+            omode, clips = "global", (MIN, MIN, MIN, MIN)
         elif mode == "local":          # every clip live at 0: row and column trackers, both prefix clip terms
             omode, clips = "local", (MIN, MIN, MIN, MIN)
         elif mode == "custom_xsuffix":  # the column tracker with its own penalty, y prefix live (S stays real)
@@ -405,7 +407,7 @@ def test_warp32_strip_fill_vs_oracle(oracle, mode):
     # the path must actually be exercised (non-zero clip penalties pull the band into the corner (m, n): column n is
     # then in the band and the pair stays with the K3 loops)
     assert n_strip >= {"semiglobal": n_tot // 3, "custom_y": 8, "custom_xy": 4, "global_nocoln": 0, "local": n_tot // 3,
-                       "custom_xsuffix": 4}[mode], (n_strip, n_tot)
+                       "custom_xsuffix": 4, "global": n_tot // 3}[mode], (n_strip, n_tot)
 
 
 def test_warp32_strip_fill_c4_shape(oracle):

@@ -24,15 +24,16 @@
 //     x clip wins ties: it is tested first, 631-642);
 //   * row trackers Sn/Ly (655-660) as packed keys 4096*S + (4095 - column offset in the strip's window), first
 //     column wins ties; the eager s-bit write of (i, n) becomes one store at the end of the strip;
-//   * row 0, column 0, row m (which starts from the column tracker), column n, the end-of-matrix passes and the
-//     walk stay in the finish pass; this kernel leaves it the boundary row m-1 (S, I per column), Sn/Ly, the
-//     (i, n) marks, the per-strip windows and the 4-bit traceback.
+//   * row 0, column 0, row m (which starts from the column tracker), column n (the literal loop, on the S / D of
+//     column n-1 this kernel exports), the end-of-matrix passes and the walk stay in the finish pass; this kernel
+//     leaves it the boundary row m-1 (S, I, column tracker per column), Sn/Ly, the (i, n) marks, the per-strip
+//     windows and the 4-bit traceback.
 //   * the column tracker S[m] / Lx (648-653, live with the x-suffix clip: local mode) as K1's packed key
 //     4096*S + (4095 - row), handed down the lanes and through the boundary row; it needs x no longer than 4,095;
 //   * substitution scores by MatchParams compare / select, or (F_LUT: a tabulated MatchFunc such as BLOSUM62) from
 //     K1's scaled LUT in shared memory with the sequence bytes mapped to LUT codes as they are loaded;
 // Not handled here (K4 / the host do not mark such pairs): trackers when the y-prefix clip is dead, scores exceed
-// 2^17 or (column tracker) x is longer than 4,095, a band that reaches column n, gaps inside the band's column range.
+// 2^17 or (column tracker) x is longer than 4,095, gaps inside the band's column range.
 #pragma once
 #include "b2a_banded.cuh"
 #include "b2a_fill.cuh"

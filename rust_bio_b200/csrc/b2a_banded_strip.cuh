@@ -351,18 +351,6 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const KsLut& T, 
       ks_column_step<FLAGS, LASTSTRIP>(sc, T, one, ge4, j, q, rowbase + 1 - sj, h_band, 4095 - jr, y4_row0, Sp, Dp, SnR,
                                        tbacc, xc, sup_prev, sup, iup, Tv, rowbase, cap_row, cap_s, cap_i);
       sup_prev = in_s;
-      if (j == n - 1) {  // column n's literal pass (finish kernel) reads S and D of column n-1: rows of the band only
-#pragma unroll
-        for (int r = 0; r < KS_R; ++r) {
-          const int32_t i = rowbase + 1 + r;
-          if ((uint32_t)(rowbase + 1 - sj + r) < h_band) {
-            int2 v;
-            v.x = Sp[r] - (4 * sc.gap_open + 1);  // S travels open-biased
-            v.y = Dp[r];
-            P.last[i] = v;
-          }
-        }
-      }
       if (writer) {
         int4 o;
         o.x = (my_last && cap_row != KS_R - 1) ? cap_s : sup;
@@ -391,6 +379,23 @@ B2A_HD void ks_run_strip(const KsPair& P, const DevScoring& sc, const KsLut& T, 
         v.z = tbacc[qd * 4 + 2];
         v.w = tbacc[qd * 4 + 3];
         dst[qd * KS_G] = v;
+      }
+    }
+  }
+  // Column n's literal pass (finish kernel) reads S and D of column n-1, rows of its band only.  A window that ends
+  // at column n-1 leaves exactly that column in every lane's registers (idle steps touch neither Sp nor Dp), so the
+  // export happens here, outside the column loop.
+  if (len > 0 && jb == n - 1) {
+    const int32_t sj = (int32_t)P.rng[2 * jb], ej = (int32_t)P.rng[2 * jb + 1];
+    const int32_t top = imin(ej, m) - sj;
+    const uint32_t h_band = top > 0 ? (uint32_t)top : 0u;
+#pragma unroll
+    for (int r = 0; r < KS_R; ++r) {
+      if ((uint32_t)(rowbase + 1 - sj + r) < h_band) {
+        int2 v;
+        v.x = Sp[r] - (4 * sc.gap_open + 1);  // S travels open-biased
+        v.y = Dp[r];
+        P.last[rowbase + 1 + r] = v;
       }
     }
   }

@@ -243,9 +243,9 @@ int32_t b2a_align_batch_banded_hinted(b2a_engine* e, int32_t mode, const b2a_sco
  * Kept on the device for the pairs of the call's last wave (every pair, unless the batch needed several waves). */
 int32_t b2a_banded_band_ranges(b2a_engine* e, uint64_t pair, uint32_t* ranges, uint64_t capacity_pairs);
 
-/* How many pairs of the last banded call went through the strip-wavefront fill (the packed-cell kernel for bands
- * whose starts and ends never decrease and that end before column n; the rest ran the literal / register-resident
- * column loops of banded.rs:511-681).  A measurement aid: results do not depend on the path. */
+/* How many pairs of the last banded call K4 marked for the strip-wavefront fill (the packed-cell kernel for bands
+ * whose starts and ends never decrease; the rest -- and the rare marked pair that path hands back -- ran the literal /
+ * register-resident column loops of banded.rs:511-681).  A measurement aid: results do not depend on the path. */
 int32_t b2a_banded_strip_pairs(b2a_engine* e, uint64_t* n_pairs);
 
 /* Staged form of b2a_align_batch, so a caller can keep a batch resident in HBM:

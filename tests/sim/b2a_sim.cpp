@@ -953,3 +953,18 @@ extern "C" int sim_banded_strip_task(int mode, const sim_scoring* s, uint32_t k,
   }
   return 0;
 }
+
+
+// the kernel-variant choice of the engine (b2a_plan.h scoring_flags), for the host-logic tests
+extern "C" int sim_scoring_flags(int32_t xclip_prefix, int32_t xclip_suffix, int32_t yclip_prefix, int32_t yclip_suffix,
+                                 int32_t alpha, int64_t score_bound, uint32_t maxm, uint32_t maxn) {
+  DevScoring sc{};
+  sc.gap_open = -5;
+  sc.gap_extend = -1;
+  sc.xclip_prefix = xclip_prefix;
+  sc.xclip_suffix = xclip_suffix;
+  sc.yclip_prefix = yclip_prefix;
+  sc.yclip_suffix = yclip_suffix;
+  sc.alpha = alpha;
+  return scoring_flags(sc, score_bound, maxm, maxn);
+}

@@ -251,3 +251,23 @@ def test_sim_relative_packed_trackers_long_sequence_form():
     r = subprocess.run([sys.executable, os.path.join(here, "workers", "sim_relpack_worker.py")], env=env,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and r.stdout.strip().startswith("OK"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_tracker_form_by_shape_and_score_range():
+    """scoring_flags (b2a_plan.h): trackers as packed keys over absolute indices for reads (m, n <= 4095, scores
+    < 2^17), over chunk- / strip-relative indices for longer sequences (scores < 2^18: BASELINE config 5), as explicit
+    (value, index) pairs beyond; no tracker flags at all in global mode."""
+    import ctypes as C
+    L = sim_util.lib()
+    L.sim_scoring_flags.restype = C.c_int
+    MINS = -858993459
+    F_TR, F_TC, F_CX, F_LUT, F_PK, F_RELU, F_PR = 1, 2, 4, 8, 16, 32, 128
+    f = lambda clips, alpha, bound, m, n: L.sim_scoring_flags(*[C.c_int32(c) for c in clips], C.c_int32(alpha), C.c_int64(bound),
+                                                           C.c_uint32(m), C.c_uint32(n))
+    local, glob, semi = (0, 0, 0, 0), (MINS,) * 4, (MINS, MINS, 0, 0)
+    assert f(local, 4, 1500, 150, 150) == F_TR | F_TC | F_CX | F_LUT | F_RELU | F_PK       # C2: reads
+    assert f(local, 25, 220032, 10000, 10000) == F_TR | F_TC | F_CX | F_LUT | F_RELU | F_PR  # C5: 10k x 10k BLOSUM62
+    assert f(local, 25, 1 << 19, 10000, 10000) == F_TR | F_TC | F_CX | F_LUT | F_RELU        # scores beyond 2^18: explicit pairs
+    assert f(local, 4, 1 << 17, 150, 150) & (F_PK | F_PR) == F_PR                              # short reads, wide scores
+    assert f(glob, 4, 10000, 1000, 1000) == F_LUT                                               # C3: no trackers
+    assert f(semi, 0, 3000, 150, 5000) == F_TR | F_PR and f(semi, 0, 3000, 150, 4000) == F_TR | F_PK
